@@ -1,0 +1,225 @@
+"""CPU oracle for the uni 3PRF path -- TEST INFRASTRUCTURE ONLY.
+
+NumPy restatement of `uni.stats.Tprf3` (Scala) for the fits SURVEY.md section 8a rows
+a15-a17 name.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
+`--impl reference` legs may import this module; the product path never does.
+
+Parity is PINNED three ways (tests/test_oracle_tprf.py):
+  * Kelly-Pruitt MATLAB known answers `t3prf-validation/kp_{yhat,alpha,rsquare}.csv`;
+  * every `*/isfull` and `*/closed` row of `test-data/tprf3-parity/scala-reference.txt`
+    (the reference's own cross-language fixture, tolerance rule
+    src/test/scala/uni/stats/Tprf3ParitySuite.scala:28-45);
+  * `tests/golden/tprf_pyref/*.npz`: outputs of the reference's own NumPy implementation
+    (`/root/reference/py/tprf3fast.py`) imported and run in the build container by
+    `tests/golden/gen_tprf_pyref.py`.
+
+File:line citations are into /root/reference/.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+
+# ---------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------
+def nan_std_cols(X: np.ndarray) -> np.ndarray:
+    """Sample std per column over non-NaN rows, two-pass; n<=1 or sd==0 -> 1.0.
+    src/main/scala/uni/stats/Tprf3.scala:469-502 (and stdCols :550-578)."""
+    X = np.asarray(X, dtype=np.float64)
+    ok = ~np.isnan(X)
+    n = ok.sum(axis=0)
+    s = np.where(ok, X, 0.0).sum(axis=0)
+    mu = np.where(n > 1, s / np.maximum(n, 1), 0.0)
+    d = np.where(ok, X - mu, 0.0)
+    ss = (d * d).sum(axis=0)
+    with np.errstate(all="ignore"):
+        sd = np.sqrt(ss / (n - 1))
+    sd = np.where((n > 1) & (sd != 0.0), sd, 1.0)
+    return sd.reshape(1, -1)
+
+
+def center_columns(M: np.ndarray) -> np.ndarray:
+    """J(rows) @ M as `m - m.sum(0)/rows` (Tprf3.scala:458-459)."""
+    return M - M.sum(axis=0, keepdims=True) / float(M.shape[0])
+
+
+def with_intercept(M: np.ndarray) -> np.ndarray:
+    """[1 | M] (Tprf3.scala:835-846)."""
+    return np.column_stack([np.ones(M.shape[0]), M])
+
+
+def lu_inverse(A: np.ndarray) -> np.ndarray:
+    """`Mat.inverse`: LU with partial pivoting + n substitutions
+    (src/main/scala/uni/data/Mat.scala:970-1001,2979-3006).  Singular -> ArithmeticError."""
+    from .mat_oracle import from2d, inverse  # local import: same test-only package
+
+    return inverse(from2d(np.asarray(A, dtype=np.float64))).to2d()
+
+
+@dataclass
+class TprfResult:
+    forecasts: np.ndarray  # T x 1
+    residuals: np.ndarray  # T x 1
+    r_squared: float
+    phi: Optional[np.ndarray] = None  # N x L
+    sigma: Optional[np.ndarray] = None  # T x L
+    beta3: Optional[np.ndarray] = None  # (L+1) x 1
+    phi_hat: Optional[np.ndarray] = None  # (L+1) x N
+    alpha: Optional[np.ndarray] = None  # N x 1
+    extra: dict = field(default_factory=dict)
+
+
+def _r2_guarded(y, resid):
+    """ssy == 0 -> 0 else 1 - sum(e^2)/ssy (Tprf3.scala:239-241, 274-275)."""
+    ssy = float(((y - y.mean()) ** 2).sum())
+    return 0.0 if ssy == 0.0 else 1.0 - float((resid**2).sum()) / ssy
+
+
+# ---------------------------------------------------------------------------------------
+# literal restatements (small N only: they form the N x N Sxx)
+# ---------------------------------------------------------------------------------------
+def tprf_closed_form_literal(y, X, Z) -> TprfResult:
+    """`Tprf3.tprfClosedForm` exactly as written (Tprf3.scala:199-252), including the
+    N x N `Sxx` and the per-column / per-row pass-1/2 `Lm` fits -- usable for small N only."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    X = np.asarray(X, dtype=np.float64)
+    Z = np.asarray(Z, dtype=np.float64)
+    Xn = X / nan_std_cols(X)
+    T, N = Xn.shape
+    L = Z.shape[1]
+    JtX = center_columns(Xn)
+    XtJt = JtX.T
+    Wxz = center_columns(XtJt @ Z)
+    Sxx = XtJt @ Xn
+    core = Wxz.T @ Sxx @ Wxz
+    factor = Wxz @ lu_inverse(core) @ Wxz.T @ XtJt
+    alpha = factor @ y
+    yhat = JtX @ alpha + y.mean()
+    # pass 1 / pass 2 / pass 3 fields (:211-231): plain OLS with intercept
+    dZ = with_intercept(Z)
+    B1 = lu_inverse(dZ.T @ dZ) @ (dZ.T @ Xn)
+    phi = B1[1:, :].T
+    dP = with_intercept(phi)
+    B2 = lu_inverse(dP.T @ dP) @ (dP.T @ Xn.T)
+    sigma = B2[1:, :].T
+    Xaug = with_intercept(sigma)
+    beta3 = lu_inverse(Xaug.T @ Xaug) @ (Xaug.T @ y)
+    resid = y - yhat
+    return TprfResult(yhat, resid, _r2_guarded(y, resid), phi=phi, sigma=sigma, beta3=beta3,
+                      phi_hat=B1, alpha=alpha)
+
+
+def t3prf(y, X, Z) -> TprfResult:
+    """`Tprf3.t3prf` (Tprf3.scala:260-289): three batch OLS passes on Xn = X / sd."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    X = np.asarray(X, dtype=np.float64)
+    Z = np.asarray(Z, dtype=np.float64)
+    Xn = X / nan_std_cols(X)
+    dZ = with_intercept(Z)
+    B1 = lu_inverse(dZ.T @ dZ) @ (dZ.T @ Xn)
+    phi = B1[1:, :].T
+    dP = with_intercept(phi)
+    B2 = lu_inverse(dP.T @ dP) @ (dP.T @ Xn.T)
+    sigma = B2[1:, :].T
+    Xaug = with_intercept(sigma)
+    beta = lu_inverse(Xaug.T @ Xaug) @ (Xaug.T @ y)
+    yhat = Xaug @ beta
+    resid = y - yhat
+    return TprfResult(yhat, resid, _r2_guarded(y, resid), phi=phi, sigma=sigma, beta3=beta,
+                      phi_hat=B1)
+
+
+def estimate3prf_is_full(y, X, Z, min_obs: int = 10) -> TprfResult:
+    """`Tprf3.estimate3prf(y, X, Right(Z), "IS Full")` for NaN-free input
+    (Tprf3.scala:1056-1110 -> runT3prf :973 -> t3prfFast :883-901 -> t3prfTail :913-943;
+    R^2 :1214-1225 -- no zero guard; alpha :1240-1250 -- the N x N form)."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    X = np.asarray(X, dtype=np.float64)
+    Z = np.asarray(Z, dtype=np.float64)
+    T, N = X.shape
+    L = Z.shape[1]
+    Xn = X / nan_std_cols(X)
+    if T < min_obs:
+        f = np.full((T, 1), np.nan)
+        return TprfResult(f, y - f, float("nan"))
+    dZ = with_intercept(Z)
+    B1 = lu_inverse(dZ.T @ dZ) @ (dZ.T @ Xn)
+    dP = with_intercept(B1[1:, :].T)
+    PtPinv = lu_inverse(dP.T @ dP)
+    sigma = ((Xn @ dP) @ PtPinv.T)[:, 1 : L + 1]
+    Xaug = with_intercept(sigma)
+    beta = lu_inverse(Xaug.T @ Xaug) @ (Xaug.T @ y)
+    f = Xaug @ beta
+    resid = y - f
+    with np.errstate(all="ignore"):
+        r2 = 1.0 - float((resid**2).sum()) / float(((y - y.mean()) ** 2).sum())
+    XtJt = center_columns(Xn).T
+    Wxz = center_columns(XtJt @ Z)
+    Sxx = XtJt @ Xn
+    alpha = Wxz @ lu_inverse(Wxz.T @ Sxx @ Wxz) @ Wxz.T @ (XtJt @ y)
+    return TprfResult(f, resid, r2, phi=B1[1:, :].T, sigma=sigma, beta3=beta, phi_hat=B1, alpha=alpha)
+
+
+# ---------------------------------------------------------------------------------------
+# scalable (Gram-reassociated) closed form -- the reference's own Rust port does this
+# ---------------------------------------------------------------------------------------
+def tprf_closed_form_gram(y, X, Z) -> TprfResult:
+    """Closed form with `Wxz' Sxx Wxz = G'G`, `G = J(T) Xn Wxz` -- never forms N x N.
+    rust/src/t3prf.rs:847-879 (`tprfClosedForm`); same result as Tprf3.scala:199-209."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    X = np.asarray(X, dtype=np.float64)
+    Z = np.asarray(Z, dtype=np.float64)
+    Xn = X / nan_std_cols(X)
+    JtX = center_columns(Xn)
+    Wxz = center_columns(JtX.T @ Z)
+    G = JtX @ Wxz
+    core = G.T @ G
+    rhs = Wxz.T @ (JtX.T @ y)
+    s = np.linalg.solve(core, rhs)
+    alpha = Wxz @ s
+    ybar = float(y.mean())
+    yhat = JtX @ alpha + ybar
+    resid = y - yhat
+    return TprfResult(yhat, resid, _r2_guarded(y, resid), alpha=alpha)
+
+
+def closed_form_partials(X_shard, Z, T_total=None):
+    """The shard-local accumulators of the fused device sweep, in
+    NumPy: used by the world_size-2 gloo test and by `bench.py --impl reference` to time a
+    column-sharded CPU fit.  Returns a dict of partial sums that add across shards."""
+    X = np.asarray(X_shard, dtype=np.float64)
+    Z = np.asarray(Z, dtype=np.float64)
+    T = X.shape[0]
+    sd = nan_std_cols(X).reshape(-1)
+    mu = X.mean(axis=0)
+    Zc = Z - Z.mean(axis=0, keepdims=True)
+    W0 = ((X - mu) / sd).T @ Zc  # N_s x L  (= Xn' J(T) Z)
+    Xn = X / sd
+    return {
+        "PX": Xn @ W0,  # T x L
+        "h0": Xn.sum(axis=1),  # T
+        "sw": W0.sum(axis=0),  # L
+        "SWW": W0.T @ W0,  # L x L
+        "smw": (mu / sd) @ W0,  # L
+        "smu": float((mu / sd).sum()),
+        "n": X.shape[1],
+        "W0": W0,
+    }
+
+
+def closed_form_from_partials(y, parts_sum, n_total):
+    """Finish step shared by every rank after the all-reduce."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    wbar = parts_sum["sw"] / n_total
+    XcW0 = parts_sum["PX"] - parts_sum["smw"][None, :]
+    r = parts_sum["h0"] - parts_sum["smu"]
+    G = XcW0 - np.outer(r, wbar)
+    core = G.T @ G
+    rhs = G.T @ (y - y.mean())
+    s = np.linalg.solve(core, rhs)
+    yhat = G @ s + float(y.mean())
+    return yhat, s, wbar

@@ -1,0 +1,113 @@
+"""Pins oracle/tprf_oracle.py against the reference's golden vectors (CPU only)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import tprf_oracle as to
+
+CASES = ["T100N10L2", "T140N12L3", "T60N25L2"]
+
+
+def _close(a, b):
+    """src/test/scala/uni/stats/Tprf3ParitySuite.scala:28-45"""
+    if np.isnan(a) and np.isnan(b):
+        return True
+    return abs(a - b) <= 1e-12 + 1e-9 * max(abs(a), abs(b))
+
+
+def _load_scala_ref(golden_dir):
+    ref = {}
+    with open(os.path.join(golden_dir, "tprf3-parity", "scala-reference.txt")) as fh:
+        for line in fh:
+            if line.startswith("#") or not line.strip():
+                continue
+            tag, key, val = line.split()
+            ref[(tag, key)] = float(val)
+    return ref
+
+
+def _panel(golden_dir, case):
+    d = os.path.join(golden_dir, "tprf3-parity")
+    X = np.loadtxt(os.path.join(d, f"{case}_X.csv"), delimiter=",", ndmin=2)
+    y = np.loadtxt(os.path.join(d, f"{case}_y.csv"), delimiter=",", ndmin=2).reshape(-1, 1)
+    Z = np.loadtxt(os.path.join(d, f"{case}_Z.csv"), delimiter=",", ndmin=2)
+    return y, X, Z
+
+
+def test_kp_known_answers(golden_dir):
+    d = os.path.join(golden_dir, "t3prf-validation")
+    X = np.loadtxt(os.path.join(d, "ref_X.csv"), delimiter=",")
+    Z = np.loadtxt(os.path.join(d, "ref_Z.csv"), delimiter=",")
+    y = np.loadtxt(os.path.join(d, "ref_y.csv"), delimiter=",").reshape(-1, 1)
+    kp_yhat = np.loadtxt(os.path.join(d, "kp_yhat.csv"), delimiter=",").reshape(-1, 1)
+    kp_alpha = np.loadtxt(os.path.join(d, "kp_alpha.csv"), delimiter=",").reshape(-1, 1)
+    kp_r2 = float(np.loadtxt(os.path.join(d, "kp_rsquare.csv"), delimiter=","))
+    # fixture inputs are numpy default_rng(1234): Z, X, y (jsrc/generate3prfData.sc:21-25)
+    rng = np.random.default_rng(1234)
+    assert np.array_equal(rng.standard_normal((50, 2)), Z)
+    assert np.array_equal(rng.standard_normal((50, 6)), X)
+    for fit in (to.estimate3prf_is_full, to.t3prf, to.tprf_closed_form_literal, to.tprf_closed_form_gram):
+        r = fit(y, X, Z)
+        assert np.max(np.abs(r.forecasts - kp_yhat)) < 1e-10, fit.__name__
+        assert abs(r.r_squared - kp_r2) < 1e-10, fit.__name__
+        if r.alpha is not None:
+            assert np.max(np.abs(r.alpha - kp_alpha)) < 1e-10, fit.__name__
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_scala_parity_rows(golden_dir, case):
+    ref = _load_scala_ref(golden_dir)
+    y, X, Z = _panel(golden_dir, case)
+    T = X.shape[0]
+    isf = to.estimate3prf_is_full(y, X, Z)
+    assert _close(isf.r_squared, ref[(f"{case}/isfull", "r2")])
+    for i in range(T):
+        assert _close(float(isf.forecasts[i, 0]), ref[(f"{case}/isfull", f"f{i}")]), i
+    for fit in (to.tprf_closed_form_literal, to.tprf_closed_form_gram, to.t3prf):
+        r = fit(y, X, Z)
+        assert _close(r.r_squared, ref[(f"{case}/closed", "r2")]), fit.__name__
+        for i in range(T):
+            assert _close(float(r.forecasts[i, 0]), ref[(f"{case}/closed", f"f{i}")]), (fit.__name__, i)
+
+
+def test_python_reference_vectors(golden_dir):
+    d = os.path.join(golden_dir, "tprf_pyref")
+    names = sorted(f for f in os.listdir(d) if f.endswith(".npz"))
+    assert names
+    for f in names:
+        g = np.load(os.path.join(d, f))
+        rng = np.random.default_rng(int(g["seed"]))
+        T, N, L = int(g["T"]), int(g["N"]), int(g["L"])
+        X = rng.standard_normal((T, N)); y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, L))
+        for fit in (to.estimate3prf_is_full, to.tprf_closed_form_gram):
+            r = fit(y, X, Z)
+            np.testing.assert_allclose(r.forecasts, g["forecasts"], rtol=1e-9, atol=1e-12, err_msg=f)
+            np.testing.assert_allclose(r.alpha, g["alpha"], rtol=1e-8, atol=1e-12, err_msg=f)
+            assert abs(r.r_squared - float(g["rsquare"])) < 1e-10
+
+
+def test_sharded_partials_sum_to_full_fit():
+    rng = np.random.default_rng(3)
+    T, N, L = 120, 48, 3
+    X = rng.standard_normal((T, N)) * 3 + 1.5; y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, L))
+    full = to.tprf_closed_form_gram(y, X, Z)
+    parts = [to.closed_form_partials(X[:, a:b], Z) for a, b in ((0, 10), (10, 31), (31, 48))]
+    tot = {k: sum(p[k] for p in parts) for k in ("PX", "h0", "sw", "SWW", "smw", "smu")}
+    yhat, s, wbar = to.closed_form_from_partials(y, tot, N)
+    np.testing.assert_allclose(yhat, full.forecasts, rtol=1e-10, atol=1e-12)
+    alpha = np.concatenate([(p["W0"] - wbar) @ s for p in parts])
+    np.testing.assert_allclose(alpha, full.alpha, rtol=1e-9, atol=1e-13)
+
+
+def test_edge_semantics():
+    """TprfCoverageSuite.scala:176-230: constant column -> sd 1.0; T < minObs -> NaN."""
+    X = np.ones((12, 3)); X[:, 1] = np.arange(12.0)
+    sd = to.nan_std_cols(X)
+    assert sd[0, 0] == 1.0 and sd[0, 2] == 1.0 and sd[0, 1] > 0
+    Xn = np.array([[1.0, np.nan], [3.0, np.nan]])
+    sd = to.nan_std_cols(Xn)
+    assert sd[0, 1] == 1.0 and abs(sd[0, 0] - np.sqrt(2.0)) < 1e-15
+    rng = np.random.default_rng(0)
+    r = to.estimate3prf_is_full(rng.standard_normal((5, 1)), rng.standard_normal((5, 4)), rng.standard_normal((5, 1)))
+    assert np.isnan(r.forecasts).all() and np.isnan(r.r_squared)
