@@ -1,0 +1,399 @@
+#!/usr/bin/env python3
+"""bench.py -- 3PRF closed-form fit on the BASELINE.json config-4 panel (T=8192 x N=262144 x L=8,
+FP64, synthetic, 16 GiB), column-sharded over --gpus N B200s; plus (N=1) the config-2 MatD
+elementwise / reduction ops and a config-3 matmul sweep as extras.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference algorithm on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = algorithmic FP64 TFLOP/s of the whole job
+(T*N*(4L+6) flop per fit) with inputs resident in HBM; `ms_per_step` is the
+fit time; `e2e` is the same fit through the C-ABI host entry point (`um_tprf_fit_host`: pinned
+host panel streamed in, forecasts/alpha/R^2 copied out, all inside the timed region).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_ROWS, N_COLS, L_PROX = 8192, 262144, 8
+METRIC = "3prf_closed_form_fit_fp64_tflops"
+UNIT = "TFLOP/s"
+
+
+def tprf_flops(T, N, L):
+    return float(T) * float(N) * (4.0 * L + 6.0)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi SM clock / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the reference's algorithm on the host cores (oracle port; no JVM on the box)
+# ------------------------------------------------------------------------------------------
+def cpu_closed_form_sample(T, Ns, L, seed=0):
+    """Times oracle/tprf_oracle.tprf_closed_form_gram (NumPy/OpenBLAS, all host threads) on a
+    column sample of the panel.  Returns (seconds, flops)."""
+    import numpy as np
+    from oracle import tprf_oracle as to
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((T, Ns)); y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, L))
+    to.tprf_closed_form_gram(y[:256], X[:256, :64], Z[:256])  # warm the BLAS threads
+    t0 = time.perf_counter()
+    to.tprf_closed_form_gram(y, X, Z)
+    return time.perf_counter() - t0, tprf_flops(T, Ns, L), (y, X, Z)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import tprf_oracle as to
+    Ns = 4096
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((T_ROWS, Ns)); y = rng.standard_normal((T_ROWS, 1)); Z = rng.standard_normal((T_ROWS, L_PROX))
+    for _ in range(max(1, args.warmup)):
+        to.tprf_closed_form_gram(y, X, Z)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        to.tprf_closed_form_gram(y, X, Z)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = tprf_flops(T_ROWS, Ns, L_PROX) / dt / 1e12
+    sample = (f"Gram-form closed fit (oracle/tprf_oracle.py, NumPy+OpenBLAS, {cores} threads) on a {Ns}-column "
+              f"sample of the {N_COLS}-column panel per step; full-panel ms extrapolated linearly in N")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3 * (N_COLS / Ns), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3PRF closed-form, T=8192 x N=262144 x L=8 FP64 panel (BASELINE config 4)",
+                   "T": T_ROWS, "N": N_COLS, "L": L_PROX, "sample_cols": Ns},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------
+def time_op(u, fn, warm=3, reps=7):
+    from uni_b200._lib import lib, check
+    for _ in range(warm):
+        fn()
+    best = 1e30
+    ms = C.c_float(0)
+    for _ in range(reps):
+        check(lib.um_timer_start())
+        fn()
+        check(lib.um_timer_stop(C.byref(ms)))
+        best = min(best, ms.value)
+    return best
+
+
+def matd_ops(u, peak_gbs, n=32768):
+    """BASELINE config 2: ops on a 32768^2 FP64 matrix, min-of-7 CUDA-event timings; GB/s against the
+    ALGORITHMIC bytes of SURVEY.md section 8d (E = n^2 elements)."""
+    E = float(n) * n
+    m = u.MatD.randn(n, n, seed=42)
+    rowv = m.mean(0)
+    colv = m.mean(1)
+    out = {}
+
+    def rec(name, fn, alg_bytes, note=None):
+        ms = time_op(u, fn)
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        out[name] = {"ms": round(ms, 4), "gbs": round(gbs, 1), "frac_hbm": round(gbs / peak_gbs, 4)}
+        if note:
+            out[name]["note"] = note
+
+    rec("sub_rowvec(m - m.mean(0))", lambda: m - rowv, 16 * E)
+    rec("sub_colvec(m - m.mean(1))", lambda: m - colv, 16 * E)
+    rec("add_same_shape", lambda: m + m, 24 * E, "both operands are the same buffer: 16E bytes of DRAM traffic")
+    rec("mul_scalar", lambda: m * 1.5, 16 * E)
+    rec("neg", lambda: -m, 16 * E)
+    rec("relu", lambda: m.relu(), 16 * E)
+    rec("sigmoid", lambda: m.sigmoid(), 16 * E)
+    rec("softmax_axis1", lambda: m.softmax(1), 16 * E, "single read: lane held in registers across a 4-CTA cluster")
+    rec("softmax_axis0", lambda: m.softmax(0), 16 * E, "two-read implementation (24E bytes moved)")
+    rec("sum_axis0", lambda: m.sum(0), 8 * E)
+    rec("sum_axis1", lambda: m.sum(1), 8 * E)
+    rec("mean_axis0", lambda: m.mean(0), 8 * E)
+    rec("mean_axis1", lambda: m.mean(1), 8 * E)
+    rec("var_axis0", lambda: m.var(0), 8 * E, "single read (shifted sums + Chan merge)")
+    rec("var_axis1", lambda: m.var(1), 8 * E, "single read (shifted sums + Chan merge)")
+    rec("std_axis0", lambda: m.std(0), 8 * E)
+    rec("sum_all", lambda: m.sum(), 8 * E)
+    rec("argmax_all", lambda: m.argmax(), 8 * E)
+    rec("gt_mask", lambda: m.gt(0.0), 9 * E)
+    t = m.T
+    rec("sum_axis0@transposed_view", lambda: t.sum(0), 8 * E)
+    rec("sub_rowvec@row_slice_view", lambda: m.slice(1024, n, 0, n) - rowv, 16 * (E - 1024.0 * n))
+
+    def inplace():
+        m.__iadd__(0.0)
+    rec("inplace_add_scalar(:+=)", inplace, 16 * E)
+    return out
+
+
+def matmul_sweep(u, sizes=(1024, 2048, 4096, 8192)):
+    out = {}
+    for dt_name, fac in (("f64", u.MatD), ("f32", u.MatF)):
+        for n in sizes:
+            a = fac.randn(n, n, seed=42); b = fac.randn(n, n, seed=43)
+            ms = time_op(u, lambda: a @ b, warm=2, reps=3)
+            out[f"{dt_name}_{n}"] = {"ms": round(ms, 3), "tflops": round(2.0 * n ** 3 / (ms * 1e-3) / 1e12, 2)}
+            if dt_name == "f64" and n <= 4096:
+                at = a.T
+                ms = time_op(u, lambda: at @ b, warm=2, reps=3)
+                out[f"{dt_name}_{n}_transposed_left"] = {"ms": round(ms, 3), "tflops": round(2.0 * n ** 3 / (ms * 1e-3) / 1e12, 2)}
+            del a, b
+    return out
+
+
+def run_ours(args, rank, world, local_rank):
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    import numpy as np
+    import uni_b200 as u
+    from uni_b200 import _lib as L_
+    from uni_b200._lib import check, lib
+    from uni_b200.dist import init_comm, shard_range
+
+    if u.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device (uni_b200 has no CPU fallback)")
+    u.init(local_rank)
+    if world > 1:
+        def bcast(b):
+            import torch
+            t = torch.tensor(list(b), dtype=torch.uint8, device="cuda")
+            dist.broadcast(t, src=0)
+            return bytes(t.cpu().tolist())
+        init_comm(rank, world, bcast)
+
+    def barrier():
+        u.sync()
+        if dist is not None:
+            import torch
+            dist.barrier(device_ids=[local_rank])
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    T, N, Lp = T_ROWS, N_COLS, L_PROX
+    if args.small:
+        T, N = 2048, 16384
+    c0, c1 = shard_range(N, rank, world)
+    Nl = c1 - c0
+    X = u.MatD.randn(T, Nl, seed=1000 + rank)
+    y = u.MatD.randn(T, 1, seed=2)
+    Z = u.MatD.randn(T, Lp, seed=3)
+    fit = lambda: u.tprf3._fit(L_.TPRF_CLOSED, y, X, Z, n_total=N, want_all=False)
+    for _ in range(max(args.warmup, 3)):
+        r = fit()
+    barrier()
+    peak_gbs, peak_src = load_peaks()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n_launch0 = u.launch_count()
+    ms = C.c_float(0)
+    t0 = time.perf_counter()
+    check(lib.um_timer_start())
+    for _ in range(args.steps):
+        r = fit()
+    check(lib.um_timer_stop(C.byref(ms)))
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = u.launch_count() - n_launch0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = max_over_ranks(ms.value / args.steps)
+    flops = tprf_flops(T, N, Lp)
+    value = flops / (ms_step * 1e-3) / 1e12
+
+    # ---- per-kernel device times (outside the timed region) -> roofline of the dominant kernel
+    check(lib.um_prof_enable(1)); check(lib.um_prof_reset())
+    PROF_N = 5
+    for _ in range(PROF_N):
+        fit()
+    names = ["colstats", "colfinal", "project", "gather", "finish", "outputs", "allreduce", "prep"]
+    kt = {}
+    for i, nm in enumerate(names):
+        tot, cnt = C.c_double(0), C.c_int64(0)
+        check(lib.um_prof_read(i, C.byref(tot), C.byref(cnt)))
+        if cnt.value:
+            kt[nm] = tot.value / cnt.value
+    check(lib.um_prof_enable(0))
+    dom = max(("colstats", "project"), key=lambda k: kt.get(k, 0.0))
+    dom_ms = max_over_ranks(kt[dom])
+    alg_bytes = 8.0 * T * Nl
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": f"k_tprf_{dom}", "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s",
+        "frac": round(achieved / peak_gbs, 4), "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg_bytes,
+        "kernel_ms": {k: round(v, 4) for k, v in kt.items()},
+        "fit_frac_x_read_once": round((8.0 * T * N / world) / (ms_step * 1e-3) / 1e9 / peak_gbs, 4),
+        "note": "each of the two sweeps (colstats, project) reads the shard once: 8*T*N_local bytes per launch; "
+                "fit_frac_x_read_once charges the whole fit with ONE read of X (SURVEY 8d)",
+    }
+
+    # ---- end to end through the C-ABI host entry point (pinned host panel, H2D inside the timed region)
+    e2e = None
+    try:
+        nbytes = T * Nl * 8
+        hx = C.c_void_p()
+        check(lib.um_malloc_host(nbytes, C.byref(hx)))
+        check(lib.um_d2h(hx, C.c_void_p(X._buf.ptr), nbytes))
+        yh = y.to_numpy(); zh = Z.to_numpy()
+        fh = np.zeros(T); ah = np.zeros(Nl); r2 = C.c_double(0)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        call = lambda: check(lib.um_tprf_fit_host(L_.TPRF_CLOSED, vp(yh), hx, Nl, vp(zh), T, Nl, Lp, N, vp(fh), vp(ah), C.byref(r2)))
+        call()
+        barrier()
+        esteps = max(1, min(args.steps, 3))
+        t1 = time.perf_counter()
+        for _ in range(esteps):
+            call()
+        barrier()
+        e_ms = max_over_ranks((time.perf_counter() - t1) * 1e3 / esteps)
+        dev_f = r.forecasts.to_numpy().ravel()
+        e2e = {"value": flops / (e_ms * 1e-3) / 1e12, "unit": UNIT, "ms_per_step": e_ms, "steps": esteps,
+               "h2d_bytes_per_step": nbytes + T * (Lp + 1) * 8, "d2h_bytes_per_step": T * 8 + Nl * 8 + 16,
+               "api": "um_tprf_fit_host (C ABI, host pointers)",
+               "max_abs_diff_vs_device_resident_fit": float(np.max(np.abs(dev_f - fh))) if world == 1 else None}
+        check(lib.um_free_host(hx))
+    except Exception as ex:  # e.g. the box cannot pin 16 GiB
+        e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+    extras = {}
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        Ns = 4096
+        dt, fl, _ = cpu_closed_form_sample(T, Ns, Lp)
+        cores = os.cpu_count() or 1
+        cpu_baseline = {"value": fl / dt / 1e12, "unit": UNIT, "cores": cores, "kind": "port",
+                        "ms_full_panel_extrapolated": dt * 1e3 * (N / Ns),
+                        "sample": f"oracle Gram closed form (NumPy+OpenBLAS, {cores} threads) on {Ns} of {N} columns, T={T}"}
+        if not args.skip_ops:
+            del X
+            try:
+                extras["matd_ops_32768x32768_f64"] = matd_ops(u, peak_gbs, 4096 if args.small else 32768)
+                extras["matmul_sweep"] = matmul_sweep(u, (1024, 2048) if args.small else (1024, 2048, 4096, 8192))
+            except Exception as ex:
+                extras["ops_error"] = str(ex)[:300]
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "3PRF closed-form fit, T=8192 x N=262144 x L=8 FP64 panel (BASELINE config 4), "
+                                   "sharded by predictor column", "T": T, "N": N, "L": Lp, "cols_per_gpu": Nl,
+                       "l2": "inputs (16 GiB / n_gpus per rank) are larger than L2; no flush needed",
+                       "parallelism": f"column-shard x{world}, one packed all-reduce per fit"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "wall_ms_per_step": wall_ms / args.steps, "r_squared": r.rSquared,
+        }
+        line.update(extras)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        from uni_b200.dist import destroy_comm
+        barrier()
+        destroy_comm()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-ops", action="store_true", help="skip the config-2/3 extras (MatD ops, matmul sweep)")
+    ap.add_argument("--small", action="store_true", help="debug: T=2048 x N=16384 panel")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,225 @@
+/* unimat.h -- C ABI of libunimat.so: a B200 (sm_100a) device backend for the data-parallel
+ * matrix hot path of philwalk/uni (`MatD`/`MatF` operators and the 3PRF fits).
+ *
+ * The reference has NO native seam for this path (its `Mat[T]` operators are Scala
+ * extension methods over a JVM array, src/main/scala/uni/data/Mat.scala:18,125-133); the
+ * only native calls it makes today are JNI BLAS (`netlib.dgemm` Mat.scala:3317,
+ * `cblas_dgemm` Mat.scala:3336).  This header is therefore the interface a Scala 3 Panama
+ * (java.lang.foreign) binding module downcalls into; each entry point names the reference
+ * operator (file:line under /root/reference/src/main/scala/uni/) it stands in for.
+ * INTEGRATION.md shows the Scala-side binding.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs; no C++/torch types.
+ *   - every function returns an `um_status`; `um_last_error()` gives the thread-local text.
+ *     Status -> reference exception: UM_ERR_ARG   -> IllegalArgumentException (`require`)
+ *                                    UM_ERR_SINGULAR -> ArithmeticException (Mat.scala:990)
+ *                                    UM_ERR_EMPTY -> UnsupportedOperationException (Mat.scala:2216)
+ *   - device memory is owned by the CALLER (the host `Mat` object): `um_malloc`/`um_free`.
+ *     Operators never allocate results: the caller passes an output view of the result
+ *     shape (fresh contiguous buffer, or the receiver itself for the in-place family).
+ *   - a matrix is a `um_view`: device pointer + the reference's stride descriptor
+ *     `(offset, rows, cols, rs, cs, transposed)` (Mat.scala:125-133) with 64-bit sizes, so
+ *     transposes / slices / stride-0 broadcasts stay zero-copy.
+ *   - all work is issued on the calling host thread's stream (one stream per host thread
+ *     per device); functions returning host scalars synchronise that stream.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *     with UM_ERR_CUDA.
+ */
+#ifndef UNIMAT_H
+#define UNIMAT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UM_VERSION_MAJOR 0
+#define UM_VERSION_MINOR 1
+
+typedef enum um_status {
+  UM_OK = 0,
+  UM_ERR_ARG = 1,
+  UM_ERR_SINGULAR = 2,
+  UM_ERR_EMPTY = 3,
+  UM_ERR_CUDA = 4,
+  UM_ERR_NCCL = 5,
+  UM_ERR_OOM = 6
+} um_status;
+
+typedef enum um_dtype { UM_F64 = 0, UM_F32 = 1, UM_BOOL = 2, UM_I32 = 3 } um_dtype;
+
+/* MatData(_tdata, _rows, _cols, _transposed, _offset, _rs, _cs): Mat.scala:125-133 */
+typedef struct um_view {
+  void* data;        /* device pointer to element 0 of the backing buffer            */
+  int64_t offset;    /* element index of (0,0)                                        */
+  int64_t rows, cols;
+  int64_t rs, cs;    /* element strides; 0 = broadcast                                */
+  int32_t dtype;     /* um_dtype                                                      */
+  int32_t transposed; /* the reference's flag; only the layout guard reads it          */
+} um_view;
+
+/* ---- lifecycle / memory ------------------------------------------------------------ */
+int32_t um_version(void);
+const char* um_last_error(void);
+int32_t um_device_count(int32_t* out);
+int32_t um_init(int32_t device);            /* selects the device for the calling thread */
+int32_t um_shutdown(void);
+int32_t um_sync(void);                      /* synchronise the calling thread's stream   */
+int32_t um_device_props(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* total_mem);
+int32_t um_malloc(size_t bytes, void** out);      /* stream-ordered pool (cudaMallocAsync)   */
+int32_t um_free(void* ptr);
+int32_t um_malloc_host(size_t bytes, void** out); /* pinned host memory for staging          */
+int32_t um_free_host(void* ptr);
+int32_t um_h2d(void* dst, const void* src, size_t bytes);
+int32_t um_d2h(void* dst, const void* src, size_t bytes);  /* synchronises                 */
+int32_t um_d2d(void* dst, const void* src, size_t bytes);
+int32_t um_memset(void* dst, int32_t byte, size_t bytes);
+/* strided 2-D host<->device copy (column shards of a row-major host panel) */
+int32_t um_h2d_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height);
+int32_t um_launch_count(int64_t* out);      /* kernels launched by this library so far     */
+/* event timing on the calling thread's stream (bench harness) */
+int32_t um_timer_start(void);
+int32_t um_timer_stop(float* ms_out);       /* synchronises                                */
+
+/* per-kernel device timing of the 3PRF pipeline (CUDA events around each launch while enabled):
+ * slot 0 colstats, 1 colfinal, 2 project, 3 gather, 4 finish, 5 outputs, 6 allreduce, 7 prep */
+int32_t um_prof_enable(int32_t on);
+int32_t um_prof_reset(void);
+int32_t um_prof_read(int32_t slot, double* total_ms, int64_t* count);   /* synchronises */
+
+/* ---- views: Mat.scala:170-199 (create / transposeView), :1865-1880 (layout guard),
+ *      :1905-1927 (slice), :1933-1953 (broadcastTo).  Host-side descriptor arithmetic. */
+int32_t um_view_init(um_view* v, void* data, int64_t rows, int64_t cols, int32_t dtype);
+int32_t um_view_is_weird(const um_view* v, int32_t* out);       /* isWeirdLayout            */
+int32_t um_view_is_contiguous(const um_view* v, int32_t* out);  /* rs == cols && cs == 1     */
+int32_t um_view_transpose(const um_view* v, um_view* out);
+/* `needs_copy` = 1 when Internal.create would materialise the slice (fragmented layout): the
+ * caller must then allocate rows*cols elements and `um_copy` the returned view into it. */
+int32_t um_view_slice(const um_view* v, int64_t r0, int64_t r1, int64_t c0, int64_t c1, um_view* out,
+                      int32_t* needs_copy);
+int32_t um_view_broadcast(const um_view* v, int64_t rows, int64_t cols, um_view* out);
+/* result shape of `a op b` under the reference's broadcasting rule (Mat.scala:1989-2005) */
+int32_t um_broadcast_shape(const um_view* a, const um_view* b, int64_t* rows, int64_t* cols);
+
+/* ---- copies / fills ---------------------------------------------------------------- */
+/* matCopy (Mat.scala:1886-1899) + dtype conversion (f32<->f64, bool/i32 -> f64): dst(r,c) = src(r,c) */
+int32_t um_copy(const um_view* src, const um_view* dst);
+int32_t um_fill(const um_view* dst, double value);              /* MatD.full / zeros / ones  */
+int32_t um_eye(const um_view* dst);                             /* MatD.eye                  */
+/* synthetic N(0,1) / U[0,1) panels generated in HBM (bench inputs; counter-based, seed+index) */
+int32_t um_randn(const um_view* dst, uint64_t seed);
+int32_t um_rand(const um_view* dst, uint64_t seed);
+int32_t um_get(const um_view* v, int64_t r, int64_t c, double* out);   /* m(r, c)            */
+int32_t um_set(const um_view* v, int64_t r, int64_t c, double value);  /* m(r, c) = value    */
+
+/* ---- elementwise (Mat.scala:1989-2102 Mat(+)Mat, :2154-2209,:2514-2531 Mat(+)scalar,
+ *      :1416-1419 scalar(+)Mat, :4513-4588 in-place family = `out` aliasing `a`) ------ */
+typedef enum um_binop { UM_ADD = 0, UM_SUB = 1, UM_MUL = 2, UM_DIV = 3, UM_MAXIMUM = 4, UM_MINIMUM = 5,
+                        UM_POW = 6 } um_binop;
+int32_t um_binary(int32_t op, const um_view* a, const um_view* b, const um_view* out);
+int32_t um_binary_scalar(int32_t op, const um_view* a, double s, int32_t scalar_left, const um_view* out);
+
+/* unary ops: unary_- (Mat.scala:2086), abs (:3557), exp/sqrt/log (MatMathOps.scala:23-41),
+ * sigmoid (MatMathOps.scala:97-122), relu (:125-146), tanh; `out` may be f64 for an f32 input */
+typedef enum um_unop { UM_NEG = 0, UM_ABS = 1, UM_EXP = 2, UM_SQRT = 3, UM_LOG = 4, UM_SIGMOID = 5,
+                       UM_RELU = 6, UM_TANH = 7, UM_SQUARE = 8, UM_RELU_GENERIC = 9 } um_unop;
+int32_t um_unary(int32_t op, const um_view* a, const um_view* out);
+
+/* softmax(axis) (MatMathOps.scala:156-226); out is f64 */
+int32_t um_softmax(const um_view* a, int32_t axis, const um_view* out);
+
+/* ---- masks: IEEE compare -> Mat[Boolean] (Mat.scala:2564-2582,3948-4003), isnan/isinf/
+ *      isfinite (:4214-4225), && || ! (:5157-5170) ------------------------------------ */
+typedef enum um_cmpop { UM_GT = 0, UM_LT = 1, UM_GTE = 2, UM_LTE = 3, UM_EQ = 4, UM_NE = 5 } um_cmpop;
+typedef enum um_classop { UM_ISNAN = 0, UM_ISINF = 1, UM_ISFINITE = 2 } um_classop;
+typedef enum um_logicop { UM_AND = 0, UM_OR = 1, UM_NOT = 2, UM_XOR = 3 } um_logicop;
+int32_t um_compare_scalar(int32_t op, const um_view* a, double s, const um_view* out_bool);
+int32_t um_compare(int32_t op, const um_view* a, const um_view* b, const um_view* out_bool);
+int32_t um_classify(int32_t op, const um_view* a, const um_view* out_bool);
+int32_t um_mask_logic(int32_t op, const um_view* a, const um_view* b /* NULL for NOT */, const um_view* out_bool);
+/* all / any: axis = -1 whole mask -> *host_out; axis 0/1 -> out_bool lanes (Mat.scala:4907-5001) */
+int32_t um_mask_reduce(int32_t want_all, const um_view* a, int32_t axis, const um_view* out_bool,
+                       int32_t* host_out);
+
+/* ---- reductions (Mat.scala:2251-2279 sum, :3469-3485 mean, :4784-4805 variance, :4699-4717
+ *      std, :3414-3467 sum(axis), :3487-3492 mean(axis), :4720-4739 std(axis), :2215-2249
+ *      min/max, :3503-3556 min/max(axis)).  Population statistics (divide by n).  Sums use a
+ *      fixed two-level tree: results are run-to-run reproducible. ---------------------- */
+typedef enum um_redop { UM_SUM = 0, UM_MEAN = 1, UM_VAR = 2, UM_STD = 3, UM_MIN = 4, UM_MAX = 5 } um_redop;
+int32_t um_reduce_all(int32_t kind, const um_view* a, double* host_out);
+int32_t um_reduce_axis(int32_t kind, const um_view* a, int32_t axis, const um_view* out);
+/* argmin/argmax -> (row, col), first occurrence under java.lang.Double.compare (Mat.scala:2281-2334) */
+int32_t um_arg_all(int32_t want_max, const um_view* a, int64_t* row, int64_t* col);
+/* idxmin/idxmax(axis) -> Mat[Int] (MatPandasOps.scala:20-64) */
+int32_t um_idx_axis(int32_t want_max, const um_view* a, int32_t axis, const um_view* out_i32);
+
+/* ---- dense linear algebra ---------------------------------------------------------- */
+/* `a *@ b` (Mat.scala:2815-2881,4811-4817): C fresh contiguous; operands any stride /
+ * transposed view, f64 (DMMA tensor pipe) or f32.  Replaces netlib.dgemm (Mat.scala:3317),
+ * cblas_dgemm (:3336), MatmulPure.multiply (MatmulPure.scala:78) and multiplyFloat (:3236). */
+int32_t um_matmul(const um_view* a, const um_view* b, const um_view* out);
+/* inverse (Mat.scala:2979-3006): LU with partial pivoting (luDecomposeD :970-1001); exact-zero
+ * pivot -> UM_ERR_SINGULAR.  Batched form: `batch` matrices `stride_*` elements apart. */
+int32_t um_inverse(const um_view* a, const um_view* out);
+int32_t um_solve(const um_view* a, const um_view* b, const um_view* out);   /* Mat.scala:3598-3634 */
+int32_t um_inverse_batched(const um_view* a0, int64_t stride_a, const um_view* out0, int64_t stride_out,
+                           int64_t batch);
+
+/* ---- 3PRF (stats/Tprf3.scala) -------------------------------------------------------
+ * One fused sweep over the T x N panel produces every cross product both fits need
+ * (DESIGN.md section 4); the fits differ only in the O(T*L^2) finish. */
+typedef struct um_tprf_out {
+  /* all device pointers into caller-owned f64 buffers; NULL = not wanted */
+  double* forecasts;   /* T                                                            */
+  double* residuals;   /* T                                                            */
+  double* alpha;       /* N_local      closed form / IS Full `alpha` (Tprf3.scala:207,1240-1250) */
+  double* phi;         /* N_local x L  pass-1 slopes (Tprf3.scala:263-264)                 */
+  double* phi_hat;     /* (L+1) x N_local  B1 incl. intercept row (Tprf3.scala:263)        */
+  double* sigma;       /* T x L        pass-2 factors (Tprf3.scala:266-267)                */
+  double* beta3;       /* L+1          pass-3 coefficients (Tprf3.scala:268-269)           */
+  double* xstd;        /* N_local      column sample std (nanStdCols, Tprf3.scala:469-502) */
+  /* host scalars, written after a stream sync */
+  double r_squared;    /* closed/t3prf: ssy==0 -> 0 (Tprf3.scala:239-241); IS Full: unguarded (:1214-1225) */
+  int32_t singular;    /* 1 if a small solve hit an exact-zero pivot                       */
+} um_tprf_out;
+
+typedef enum um_tprf_mode {
+  UM_TPRF_CLOSED = 0,   /* Tprf3.tprfClosedForm  (Tprf3.scala:199-252)                     */
+  UM_TPRF_ITER = 1,     /* Tprf3.t3prf           (Tprf3.scala:260-289)                     */
+  UM_TPRF_IS_FULL = 2   /* Tprf3.estimate3prf(.., "IS Full") (Tprf3.scala:1056-1110,1206-1250) */
+} um_tprf_mode;
+
+/* Single-GPU (or this rank's column shard when a communicator is active: X holds the local
+ * N_local columns, y and Z are replicated, n_total = N over all ranks).  X: T x N_local f64
+ * view with cs == 1; y: T x 1; Z: T x L, L <= 8. */
+int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_view* Z, int64_t n_total,
+                    um_tprf_out* out);
+/* Same fit with y/X/Z in HOST memory (row-major, ldx elements between rows of X): the panel is
+ * streamed to the device in column blocks overlapped with the sweep; outputs to host pointers. */
+int32_t um_tprf_fit_host(int32_t mode, const double* y, const double* X, int64_t ldx, const double* Z,
+                         int64_t T, int64_t N_local, int64_t L, int64_t n_total, double* forecasts_host,
+                         double* alpha_host, double* r_squared);
+/* Batched independent panels (BASELINE config 5): panel p at X + p*stride_x etc.; outputs
+ * forecasts[p*T..], r2[p] (device), alpha[p*N..] (may be NULL). */
+int32_t um_tprf_fit_batched(int32_t mode, const double* y, const double* X, const double* Z, int64_t T,
+                            int64_t N, int64_t L, int64_t batch, double* forecasts, double* alpha,
+                            double* r2);
+/* accounting for bench.py: algorithmic flops/bytes of one fit */
+int32_t um_tprf_work(int64_t T, int64_t N, int64_t L, double* flops, double* bytes);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink -------------------------------- */
+int32_t um_comm_unique_id(uint8_t out[128]);
+int32_t um_comm_init(int32_t rank, int32_t world, const uint8_t id[128]);
+int32_t um_comm_destroy(void);
+int32_t um_comm_info(int32_t* rank, int32_t* world);
+/* deterministic sum: all-gather of each rank's block + fixed rank-order add */
+int32_t um_comm_allreduce_sum_f64(double* buf, int64_t count);
+int32_t um_comm_barrier(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIMAT_H */

@@ -1,0 +1,385 @@
+"""GPU parity tests for the Mat operator path: CUDA (through the C ABI / uni_b200 mirror) vs the
+CPU oracle and the reference's bit-pattern fixture.  Bit-exact for masks, arg*/idx*, min/max and
+exact elementwise ops; FP sums within rel 1e-12 scaled by sum|x|."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import mat_oracle as mo
+from tests import parity_corpus as pc
+
+
+@pytest.fixture(scope="module")
+def u():
+    import uni_b200
+    if uni_b200.device_count() == 0:
+        pytest.fail("no CUDA device: the product path has no CPU fallback")
+    uni_b200.init(0)
+    return uni_b200
+
+
+@pytest.fixture(scope="module")
+def ref(golden_dir):
+    return pc.load_reference(os.path.join(golden_dir, "mat-parity", "scala-reference.txt"))
+
+
+def dev(u, a):
+    return u.Mat.from_numpy(np.ascontiguousarray(a))
+
+
+def omat(a):
+    return mo.from2d(np.ascontiguousarray(a))
+
+
+def sum_tol(a, scale=None):
+    s = np.abs(np.asarray(a, dtype=np.float64)).sum() if scale is None else scale
+    return 1e-12 * max(float(s), 1e-300)
+
+
+# ---------------------------------------------------------------- fixture rows, bit for bit
+@pytest.mark.parametrize("shape", pc.SHAPES)
+def test_fixture_exact_rows(u, ref, shape):
+    r, c = shape
+    lab = f"{r}x{c}"
+    a = pc.corpus()[: r * c].reshape(r, c)
+    m = dev(u, a)
+    mean0 = dev(u, mo.mean_axis(omat(a), 0).to2d())   # reference's own mean vectors: the broadcast op is exact
+    mean1 = dev(u, mo.mean_axis(omat(a), 1).to2d())
+    am, an = m.argmax(), m.argmin()
+    got = {
+        "negfnv": mo.fnv((-m).to_numpy()),
+        "divfnv": mo.fnv((m / (m.abs() + 1.0)).to_numpy()),
+        "bcast0fnv": mo.fnv((m - mean0).to_numpy()),
+        "bcast1fnv": mo.fnv((m - mean1).to_numpy()),
+        "tfnv": mo.fnv(m.T.to_numpy()),
+        "slicefnv": mo.fnv(m.slice(0, r, 1, c).to_numpy()),
+        "min0fnv": mo.fnv(m.min(0).to_numpy()),
+        "max1fnv": mo.fnv(m.max(1).to_numpy()),
+        "argmax": am[0] * c + am[1],
+        "argmin": an[0] * c + an[1],
+        "pd.idxmin0": mo.fnv_words(m.idxmin(0).to_numpy().reshape(-1).tolist()),
+        "pd.idxmax1": mo.fnv_words(m.idxmax(1).to_numpy().reshape(-1).tolist()),
+    }
+    me = dev(u, pc.corpus_exp()[: r * c].reshape(r, c))
+    got["math.relu"] = mo.fnv(me.relu().to_numpy())
+    bad = {k: (hex(v), hex(ref[(lab, k)])) for k, v in got.items() if v != ref[(lab, k)]}
+    assert not bad, bad
+    # transcendental rows on their quantised grids: allow the grid-straddle the fixture documents
+    sig = me.sigmoid().to_numpy()
+    np.testing.assert_allclose(sig, mo.sigmoid(omat(pc.corpus_exp()[: r * c].reshape(r, c))).to2d(), rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("shape", pc.SHAPES)
+def test_fixture_sum_rows_tolerance(u, ref, shape):
+    r, c = shape
+    lab = f"{r}x{c}"
+    a = pc.corpus()[: r * c].reshape(r, c)
+    m = dev(u, a)
+    tol = sum_tol(a)
+    f64 = lambda w: np.array([w], dtype=np.uint64).view(np.float64)[0]
+    assert abs(m.T.sum() - f64(ref[(lab, "tsum")])) <= tol
+    assert abs(m.sum() - f64(ref[(lab, "tsum")])) <= tol
+    assert abs(m.T.mean() - f64(ref[(lab, "tmean")])) <= tol / (r * c)
+    for got, key in ((m.std(), "std"), (m.T.std(), "tstd"), (m.variance(), "var")):
+        want = f64(ref[(lab, key)])
+        assert abs(got - want) <= 1e-12 * max(abs(want), 1e-300), key
+    assert abs(m.slice(0, r, 1, c).sum() - f64(ref[(lab, "slicesum")])) <= tol
+
+
+@pytest.mark.parametrize("n", pc.SIZES)
+def test_fixture_sizes(u, ref, n):
+    a = pc.corpus()[:n]
+    f64 = lambda w: np.array([w], dtype=np.uint64).view(np.float64)[0]
+    if n == 0:
+        m = u.MatD.zeros(0, 1)
+        assert m.sum() == 0.0 and m.mean() == 0.0          # Mat.scala:3470
+        with pytest.raises(u.EmptyMatrixError):
+            m.min()
+        return
+    m = dev(u, a.reshape(-1, 1))
+    assert abs(m.sum() - f64(ref[(str(n), "sum")])) <= sum_tol(a)
+    assert abs(m.mean() - f64(ref[(str(n), "mean")])) <= sum_tol(a) / n
+    me = dev(u, pc.corpus_exp()[:n].reshape(-1, 1))
+    assert mo.bits(me.min()) == ref[(str(n), "min")]
+    assert mo.bits(me.max()) == ref[(str(n), "max")]
+
+
+@pytest.mark.parametrize("name", sorted(pc.ADVERSARIAL))
+def test_adversarial_rows_bit_exact(u, ref, name):
+    arr = np.array(pc.ADVERSARIAL[name], dtype=np.float64)
+    mats = {"col": dev(u, arr.reshape(-1, 1)), "row": dev(u, arr.reshape(1, -1)), "colT": dev(u, arr.reshape(-1, 1)).T}
+    for orient, m in mats.items():
+        lab = f"adv/{name}/{orient}"
+        pos, fin = m.gt(0.0), m.isfinite()
+        an, ax = m.argmin(), m.argmax()
+        fm = lambda x: mo.fnv_mask(x.to_numpy())
+        got = {
+            "min": mo.canon(m.min()), "max": mo.canon(m.max()),
+            "argmin": an[0] * m.cols + an[1], "argmax": ax[0] * m.cols + ax[1],
+            "min0fnv": mo.fnv_canon(m.min(0).to_numpy()), "max1fnv": mo.fnv_canon(m.max(1).to_numpy()),
+            "mask.gt0": fm(pos), "mask.lt0": fm(m.lt(0.0)), "mask.gte0": fm(m.gte(0.0)), "mask.lte0": fm(m.lte(0.0)),
+            "mask.eq0": fm(m.eq(0.0)), "mask.ne0": fm(m.ne(0.0)), "mask.eqnan": fm(m.eq(np.nan)),
+            "mask.nenan": fm(m.ne(np.nan)), "mask.gtinf": fm(m.gt(np.inf)), "mask.gteinf": fm(m.gte(np.inf)),
+            "mask.ltninf": fm(m.lt(-np.inf)), "mask.isnan": fm(m.isnan()), "mask.isinf": fm(m.isinf()),
+            "mask.isfinite": fm(fin), "mask.and": fm(pos & fin), "mask.or": fm(pos | fin), "mask.not": fm(~pos),
+            "mask.all": int(pos.all()), "mask.any": int(pos.any()),
+            "mask.all0": fm(pos.all(0)), "mask.any0": fm(pos.any(0)), "mask.all1": fm(pos.all(1)), "mask.any1": fm(pos.any(1)),
+        }
+        s = m.sum()
+        got["sum"] = mo.canon(s)
+        bad = {k: (hex(v), hex(ref[(lab, k)])) for k, v in got.items() if v != ref[(lab, k)]}
+        assert not bad, (lab, bad)
+
+
+# ---------------------------------------------------------------- elementwise / broadcasting / views
+SHAPES_EW = [(1, 1), (1, 7), (7, 1), (3, 5), (64, 64), (65, 63), (257, 129), (1000, 33), (33, 1000), (2, 4099)]
+
+
+@pytest.mark.parametrize("shape", SHAPES_EW)
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "div"])
+def test_binary_broadcast_exact(u, shape, op):
+    rng = np.random.default_rng(hash((shape, op)) % 2**32)
+    r, c = shape
+    a = rng.standard_normal((r, c)); b = rng.standard_normal((r, c))
+    row = rng.standard_normal((1, c)); col = rng.standard_normal((r, 1))
+    f = {"add": lambda x, y: x + y, "sub": lambda x, y: x - y, "mul": lambda x, y: x * y, "div": lambda x, y: x / y}[op]
+    A, B, R, Cc = dev(u, a), dev(u, b), dev(u, row), dev(u, col)
+    for X, Y, x, y in ((A, B, a, b), (A, R, a, row), (A, Cc, a, col), (R, A, row, a), (Cc, R, col, row), (A, 1.5, a, 1.5)):
+        got = f(X, Y).to_numpy()
+        want = mo.binary(op, omat(x), omat(y)).to2d() if not np.isscalar(y) else mo.binary_scalar(op, omat(x), y).to2d()
+        assert np.array_equal(got, want), (shape, op)
+    got = f(2.5, A).to_numpy()
+    assert np.array_equal(got, mo.binary_scalar(op, omat(a), 2.5, scalar_left=True).to2d())
+    # views: transposed left operand, offset slice, and both at once
+    At = dev(u, a.T.copy()).T
+    assert np.array_equal(f(At, B).to_numpy(), f(a, b))
+    if r > 2 and c > 2:
+        big = rng.standard_normal((r + 2, c + 3))
+        V = dev(u, big).slice(1, r + 1, 2, c + 2)
+        assert np.array_equal(f(V, B).to_numpy(), f(big[1 : r + 1, 2 : c + 2], b))
+        assert np.array_equal(f(B, V).to_numpy(), f(b, big[1 : r + 1, 2 : c + 2]))
+
+
+def test_broadcast_shape_errors(u):
+    a = u.MatD.zeros(3, 4); b = u.MatD.zeros(2, 4)
+    with pytest.raises(ValueError):
+        a + b
+    with pytest.raises(ValueError):
+        a @ b
+    with pytest.raises(ValueError):
+        a.sum(2)
+    c = u.MatD.zeros(3, 1)
+    with pytest.raises(ValueError):  # in-place Mat form requires EQUAL shapes (Mat.scala:4565)
+        a.iadd(c)
+
+
+def test_inplace_through_views(u):
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((40, 30))
+    m = dev(u, a)
+    ref_ = mo.from2d(a)
+    v = m.slice(5, 25, 0, 30)            # row slice: stays a view (tall enough)
+    assert v._buf is m._buf
+    v += 2.0
+    mo.inplace_scalar("add", mo.slice_(ref_, 5, 25, 0, 30), 2.0)
+    t = m.T
+    t *= 0.5
+    mo.inplace_scalar("mul", ref_.T, 0.5)
+    other = rng.standard_normal((30, 40))
+    t -= dev(u, other)
+    mo.inplace_mat("sub", ref_.T, mo.from2d(other))
+    assert np.array_equal(m.to_numpy(), ref_.to2d())
+    # a column slice of a WIDE matrix is materialised: writes do not reach the parent
+    w = dev(u, a[:3, :])
+    s = w.slice(0, 3, 1, 30)
+    assert s._buf is not w._buf
+    s += 1.0
+    assert np.array_equal(w.to_numpy(), a[:3, :])
+    # element get/set through a view
+    t[2, 3] = 7.25
+    assert m[3, 2] == 7.25 and t[2, 3] == 7.25
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (5, 3), (64, 64), (257, 256), (300, 400), (17, 5000)])
+def test_unary_and_activations(u, shape):
+    rng = np.random.default_rng(11)
+    a = rng.standard_normal(shape) * 3
+    a.flat[0] = 0.0
+    if a.size > 3:
+        a.flat[1] = -0.0; a.flat[2] = np.nan; a.flat[3] = np.inf
+    m, o = dev(u, a), omat(a)
+    assert np.array_equal((-m).to_numpy(), -a, equal_nan=True)
+    assert np.array_equal(np.signbit(m.abs().to_numpy()), np.signbit(mo.abs_(o).to2d()))
+    assert np.array_equal(m.abs().to_numpy(), mo.abs_(o).to2d(), equal_nan=True)
+    got = m.relu().to_numpy(); want = mo.relu(o).to2d()
+    assert np.array_equal(got, want, equal_nan=True) and np.array_equal(np.signbit(got), np.signbit(want))
+    np.testing.assert_allclose(m.sigmoid().to_numpy(), mo.sigmoid(o).to2d(), rtol=1e-12, atol=0, equal_nan=True)
+    np.testing.assert_allclose(m.exp().to_numpy(), np.exp(a), rtol=1e-12, equal_nan=True)
+    # views
+    np.testing.assert_allclose(m.T.sigmoid().to_numpy(), mo.sigmoid(o.T).to2d(), rtol=1e-12, atol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (5, 3), (64, 64), (65, 63), (300, 400), (7, 2049), (3, 9000), (2, 20000), (2, 70000), (4097, 3)])
+@pytest.mark.parametrize("axis", [0, 1])
+def test_softmax(u, shape, axis):
+    rng = np.random.default_rng(3)
+    a = rng.uniform(-5.0, 0.5, size=shape)
+    m = dev(u, a)
+    got = m.softmax(axis).to_numpy()
+    want = mo.softmax(omat(a), axis).to2d()
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(m.T.softmax(1 - axis).to_numpy(), want.T, rtol=1e-12, atol=0)
+
+
+def test_softmax_special_lanes(u):
+    a = np.array([[1.0, 2.0, 3.0], [np.nan, 1.0, 2.0], [1.0, np.nan, 2.0], [-np.inf, 0.0, 1.0],
+                  [-np.inf, -np.inf, -np.inf], [np.inf, 1.0, 2.0], [0.0, 0.0, 0.0]])
+    for axis, arr in ((1, a), (0, a.T.copy())):
+        got = dev(u, arr).softmax(axis).to_numpy()
+        want = mo.softmax(omat(arr), axis).to2d()
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=0, equal_nan=True)
+    mf = u.Mat.from_numpy(a[:1].astype(np.float32))
+    assert mf.softmax().dtype == 0 and mf.sigmoid().dtype == 0   # Mat[Double] even for MatF
+
+
+# ---------------------------------------------------------------- reductions
+RED_SHAPES = [(1, 1), (1, 9), (9, 1), (3, 5), (5, 3), (64, 64), (65, 63), (257, 256), (300, 400), (4097, 33), (33, 4097), (2, 70001), (70001, 2)]
+
+
+@pytest.mark.parametrize("shape", RED_SHAPES)
+def test_axis_and_whole_reductions(u, shape):
+    rng = np.random.default_rng(17)
+    a = rng.standard_normal(shape) * 10 + 3
+    for M, O in ((dev(u, a), omat(a)), (dev(u, a).T, omat(a).T)):
+        v = O.to2d()
+        tol = sum_tol(v)
+        assert abs(M.sum() - float(mo.mat_sum(O))) <= tol
+        assert abs(M.mean() - float(mo.mat_mean(O))) <= tol / v.size
+        np.testing.assert_allclose(M.variance(), float(mo.mat_variance(O)), rtol=1e-12)
+        np.testing.assert_allclose(M.std(), float(mo.mat_std(O)), rtol=1e-12)
+        for axis in (0, 1):
+            lane_tol = 1e-12 * np.abs(v).sum(axis=axis, keepdims=True)
+            assert np.all(np.abs(M.sum(axis).to_numpy() - mo.sum_axis(O, axis).to2d()) <= lane_tol)
+            n = v.shape[axis]
+            assert np.all(np.abs(M.mean(axis).to_numpy() - mo.mean_axis(O, axis).to2d()) <= lane_tol / n)
+            np.testing.assert_allclose(M.var(axis).to_numpy(), mo.var_axis(O, axis).to2d(), rtol=1e-12, atol=1e-300)
+            np.testing.assert_allclose(M.std(axis).to_numpy(), mo.std_axis(O, axis).to2d(), rtol=1e-12, atol=1e-300)
+            assert np.array_equal(M.min(axis).to_numpy(), mo.min_axis(O, axis).to2d())
+            assert np.array_equal(M.max(axis).to_numpy(), mo.max_axis(O, axis).to2d())
+            assert np.array_equal(M.idxmin(axis).to_numpy(), mo.idxmin(O, axis).to2d())
+            assert np.array_equal(M.idxmax(axis).to_numpy(), mo.idxmax(O, axis).to2d())
+        assert M.argmin() == mo.argmin(O) and M.argmax() == mo.argmax(O)
+        assert M.min() == mo.mat_min(O) and M.max() == mo.mat_max(O)
+
+
+def test_reductions_with_ties_and_specials(u):
+    a = np.array([[3.0, 1.0, 1.0, 3.0], [np.nan, 1.0, -0.0, 0.0], [0.0, -0.0, np.inf, np.nan], [-np.inf, 2.0, 2.0, -np.inf]])
+    for M, O in ((dev(u, a), omat(a)), (dev(u, a).T, omat(a).T)):
+        assert M.argmin() == mo.argmin(O) and M.argmax() == mo.argmax(O)
+        for axis in (0, 1):
+            assert np.array_equal(M.idxmin(axis).to_numpy(), mo.idxmin(O, axis).to2d())
+            assert np.array_equal(M.idxmax(axis).to_numpy(), mo.idxmax(O, axis).to2d())
+            g, w = M.min(axis).to_numpy(), mo.min_axis(O, axis).to2d()
+            assert np.array_equal(g, w, equal_nan=True) and np.array_equal(np.signbit(g), np.signbit(w))
+    big = np.zeros((3, 100000)); big[1, 70000] = -1.0; big[1, 99999] = -1.0; big[2, 5] = 5.0; big[0, 99998] = 5.0
+    B = dev(u, big)
+    assert B.argmin() == (1, 70000) and B.argmax() == (0, 99998)
+    assert B.idxmax(1).to_numpy().ravel().tolist() == [99998, 0, 5]
+
+
+def test_variance_is_shift_robust(u):
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((2000, 50)) + 1e6
+    m = dev(u, a)
+    np.testing.assert_allclose(m.var(0).to_numpy(), mo.var_axis(omat(a), 0).to2d(), rtol=1e-9)
+    np.testing.assert_allclose(m.variance(), float(mo.mat_variance(omat(a))), rtol=1e-9)
+    const = dev(u, np.full((300, 7), 4.25))
+    assert np.array_equal(const.std(0).to_numpy(), np.zeros((1, 7)))
+
+
+def test_reduction_reproducible(u):
+    a = np.random.default_rng(2).standard_normal((3001, 517))
+    m = dev(u, a)
+    s0 = [m.sum(), m.sum(0).to_numpy().tobytes(), m.var(1).to_numpy().tobytes()]
+    for _ in range(3):
+        assert [m.sum(), m.sum(0).to_numpy().tobytes(), m.var(1).to_numpy().tobytes()] == s0
+
+
+# ---------------------------------------------------------------- MatF
+def test_matf_ops(u):
+    rng = np.random.default_rng(9)
+    a = rng.uniform(-5, 0.5, size=(65, 63)).astype(np.float32)
+    m, o = dev(u, a), omat(a)
+    assert np.array_equal((m * m).to_numpy(), a * a)
+    assert np.array_equal((m / (m + 10.0)).to_numpy(), a / (a + np.float32(10.0)))
+    assert np.array_equal((m - 0.5).to_numpy(), a - np.float32(0.5))
+    assert np.array_equal(m.gt(-1.0).to_numpy(), a > -1.0)
+    assert m.argmin() == mo.argmin(o) and m.argmax() == mo.argmax(o)
+    np.testing.assert_allclose(m.sum(), float(mo.mat_sum(o)), rtol=1e-5)
+    np.testing.assert_allclose(m.sum(0).to_numpy(), mo.sum_axis(o, 0).to2d(), rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(m.std(0).to_numpy(), mo.std_axis(o, 0).to2d(), rtol=1e-5)
+    np.testing.assert_allclose((m @ m.T).to_numpy(), mo.matmul_pure(o, o.T).to2d(), rtol=1e-4, atol=1e-4)
+    assert m.relu().dtype == 1 and np.array_equal(m.relu().to_numpy(), np.maximum(a, 0))
+
+
+# ---------------------------------------------------------------- matmul / inverse / solve
+MM_SHAPES = [(1, 1, 1), (3, 5, 3), (5, 3, 5), (8, 9, 8), (64, 64, 64), (65, 63, 65), (127, 129, 131), (256, 256, 256),
+             (300, 400, 300), (1, 500, 1), (500, 1, 500), (40, 650, 40), (512, 512, 512), (1000, 17, 9)]
+
+
+@pytest.mark.parametrize("mkn", MM_SHAPES)
+def test_matmul_f64(u, mkn):
+    M, K, N = mkn
+    rng = np.random.default_rng(M * 7 + K * 3 + N)
+    a = rng.standard_normal((M, K)); b = rng.standard_normal((K, N))
+    want = a @ b
+    tol = dict(rtol=1e-9, atol=1e-12 * K)   # MatmulModeSuite.scala:66-83 (BLAS vs pure contract)
+    np.testing.assert_allclose((dev(u, a) @ dev(u, b)).to_numpy(), want, **tol)
+    # transposed views on either side: no copies (Mat.scala:2815-2881; mmfnv / tmmfnv operands)
+    np.testing.assert_allclose((dev(u, a.T.copy()).T @ dev(u, b)).to_numpy(), want, **tol)
+    np.testing.assert_allclose((dev(u, a) @ dev(u, b.T.copy()).T).to_numpy(), want, **tol)
+    np.testing.assert_allclose((dev(u, a.T.copy()).T @ dev(u, b.T.copy()).T).to_numpy(), want, **tol)
+    if M > 4 and K > 4:
+        big = rng.standard_normal((M + 3, K + 5))
+        np.testing.assert_allclose((dev(u, big).slice(1, M + 1, 3, K + 3) @ dev(u, b)).to_numpy(), big[1 : M + 1, 3 : K + 3] @ b, **tol)
+
+
+def test_matmul_matches_pinned_oracle(u):
+    a = pc.corpus()[: 65 * 63].reshape(65, 63)
+    m = dev(u, a)
+    want = mo.matmul_pure(omat(a), omat(a).T).to2d()
+    got = (m @ m.T).to_numpy()
+    scale = np.abs(a) @ np.abs(a).T
+    assert np.all(np.abs(got - want) <= 1e-12 * scale)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 9, 17, 64, 100])
+def test_inverse_and_solve(u, n):
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal((n, n)) + np.eye(n) * 0.1
+    b = rng.standard_normal((n, 3))
+    inv = dev(u, a).inverse().to_numpy()
+    want = mo.inverse(omat(a)).to2d()
+    np.testing.assert_allclose(inv, want, rtol=1e-10, atol=1e-13)
+    assert np.array_equal(inv, want), "same pivoting and operation order as luDecomposeD -> bit-identical"
+    x = dev(u, a).solve(dev(u, b)).to_numpy()
+    assert np.array_equal(x, mo.solve(omat(a), omat(b)).to2d())
+    np.testing.assert_allclose(dev(u, a.T.copy()).T.inverse().to_numpy(), want, rtol=1e-10, atol=1e-13)
+
+
+def test_singular_raises(u):
+    a = np.array([[1.0, 2.0], [2.0, 4.0]])
+    with pytest.raises(u.SingularMatrixError):
+        dev(u, a).inverse()
+    with pytest.raises(ValueError):
+        u.MatD.zeros(2, 3).inverse()
+
+
+def test_launch_counter_moves(u):
+    n0 = u.launch_count()
+    m = u.MatD.ones(8, 8)
+    (m + m).sum()
+    assert u.launch_count() > n0

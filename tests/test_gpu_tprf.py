@@ -1,0 +1,192 @@
+"""GPU parity tests for the 3PRF fits: CUDA vs the reference's golden vectors and the CPU oracle.
+Tolerance: |a-b| <= 1e-12 + 1e-9 max(|a|,|b|) (Tprf3ParitySuite.scala:28-45; north_star 1e-9)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import tprf_oracle as to
+
+
+@pytest.fixture(scope="module")
+def u():
+    import uni_b200
+    if uni_b200.device_count() == 0:
+        pytest.fail("no CUDA device: the product path has no CPU fallback")
+    uni_b200.init(0)
+    return uni_b200
+
+
+def close(a, b, rtol=1e-9, atol=1e-12):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    both_nan = np.isnan(a) & np.isnan(b)
+    ok = np.abs(a - b) <= atol + rtol * np.maximum(np.abs(a), np.abs(b))
+    return bool(np.all(ok | both_nan))
+
+
+def devs(u, y, X, Z):
+    return u.Mat.from_numpy(y), u.Mat.from_numpy(X), u.Mat.from_numpy(Z)
+
+
+def test_kp_known_answers(u, golden_dir):
+    """BASELINE config 1: t3prf-validation reference panel vs the K&P MATLAB outputs."""
+    d = os.path.join(golden_dir, "t3prf-validation")
+    X = np.loadtxt(os.path.join(d, "ref_X.csv"), delimiter=",")
+    Z = np.loadtxt(os.path.join(d, "ref_Z.csv"), delimiter=",")
+    y = np.loadtxt(os.path.join(d, "ref_y.csv"), delimiter=",").reshape(-1, 1)
+    kp_yhat = np.loadtxt(os.path.join(d, "kp_yhat.csv"), delimiter=",").reshape(-1, 1)
+    kp_alpha = np.loadtxt(os.path.join(d, "kp_alpha.csv"), delimiter=",").reshape(-1, 1)
+    kp_r2 = float(np.loadtxt(os.path.join(d, "kp_rsquare.csv"), delimiter=","))
+    dy, dX, dZ = devs(u, y, X, Z)
+    for fit in (u.tprfClosedForm, u.t3prf, lambda a, b, c: u.estimate3prf(a, b, c, "IS Full")):
+        r = fit(dy, dX, dZ)
+        assert close(r.forecasts.to_numpy(), kp_yhat)
+        assert close(r.rSquared, kp_r2)
+        assert close(r.residuals.to_numpy(), y - kp_yhat, atol=1e-11)
+        if r.alpha is not None:
+            assert close(r.alpha.to_numpy(), kp_alpha)
+
+
+@pytest.mark.parametrize("case", ["T100N10L2", "T140N12L3", "T60N25L2"])
+def test_scala_parity_rows(u, golden_dir, case):
+    d = os.path.join(golden_dir, "tprf3-parity")
+    ref = {}
+    with open(os.path.join(d, "scala-reference.txt")) as fh:
+        for line in fh:
+            if line.startswith("#") or not line.strip():
+                continue
+            tag, key, val = line.split()
+            ref[(tag, key)] = float(val)
+    X = np.loadtxt(os.path.join(d, f"{case}_X.csv"), delimiter=",", ndmin=2)
+    y = np.loadtxt(os.path.join(d, f"{case}_y.csv"), delimiter=",", ndmin=2).reshape(-1, 1)
+    Z = np.loadtxt(os.path.join(d, f"{case}_Z.csv"), delimiter=",", ndmin=2)
+    T = X.shape[0]
+    dy, dX, dZ = devs(u, y, X, Z)
+    isf = u.estimate3prf(dy, dX, dZ, "IS Full")
+    want = np.array([ref[(f"{case}/isfull", f"f{i}")] for i in range(T)]).reshape(-1, 1)
+    assert close(isf.forecasts.to_numpy(), want) and close(isf.rSquared, ref[(f"{case}/isfull", "r2")])
+    want = np.array([ref[(f"{case}/closed", f"f{i}")] for i in range(T)]).reshape(-1, 1)
+    for fit in (u.tprfClosedForm, u.t3prf):
+        r = fit(dy, dX, dZ)
+        assert close(r.forecasts.to_numpy(), want) and close(r.rSquared, ref[(f"{case}/closed", "r2")])
+
+
+def test_python_reference_vectors(u, golden_dir):
+    d = os.path.join(golden_dir, "tprf_pyref")
+    for f in sorted(x for x in os.listdir(d) if x.endswith(".npz")):
+        g = np.load(os.path.join(d, f))
+        rng = np.random.default_rng(int(g["seed"]))
+        T, N, L = int(g["T"]), int(g["N"]), int(g["L"])
+        X = rng.standard_normal((T, N)); y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, L))
+        r = u.estimate3prf(*devs(u, y, X, Z))
+        assert close(r.forecasts.to_numpy(), g["forecasts"]), f
+        assert close(r.alpha.to_numpy(), g["alpha"], rtol=1e-8), f
+        assert abs(r.rSquared - float(g["rsquare"])) < 1e-10, f
+
+
+SHAPES = [(10, 1, 1), (33, 7, 1), (50, 6, 2), (100, 64, 3), (127, 65, 2), (129, 200, 8), (512, 2048, 4), (300, 1000, 5), (1000, 130, 7)]
+
+
+@pytest.mark.parametrize("tnl", SHAPES)
+def test_all_outputs_vs_oracle(u, tnl):
+    T, N, L = tnl
+    rng = np.random.default_rng(T + N + L)
+    X = rng.standard_normal((T, N)) * rng.uniform(0.5, 3.0, size=(1, N)) + rng.uniform(-2, 2, size=(1, N))
+    y = rng.standard_normal((T, 1)) + 0.3 * X[:, :1]
+    Z = rng.standard_normal((T, L)) + 0.2 * X[:, : min(L, N)].mean(axis=1, keepdims=True)
+    dy, dX, dZ = devs(u, y, X, Z)
+    oc = to.tprf_closed_form_literal(y, X, Z) if N <= 300 else to.tprf_closed_form_gram(y, X, Z)
+    c = u.tprfClosedForm(dy, dX, dZ)
+    assert close(c.forecasts.to_numpy(), oc.forecasts) and close(c.rSquared, oc.r_squared)
+    assert close(c.alpha.to_numpy(), oc.alpha, rtol=1e-8, atol=1e-13)
+    assert close(c.xstd.to_numpy(), to.nan_std_cols(X), rtol=1e-12)
+    oi = to.t3prf(y, X, Z)
+    it = u.t3prf(dy, dX, dZ)
+    assert close(it.forecasts.to_numpy(), oi.forecasts) and close(it.rSquared, oi.r_squared)
+    assert close(it.phi.to_numpy(), oi.phi, rtol=1e-8, atol=1e-12)
+    assert close(it.phiHat.to_numpy(), oi.phi_hat, rtol=1e-8, atol=1e-12)
+    assert close(it.sigma.to_numpy(), oi.sigma, rtol=1e-8, atol=1e-11)
+    assert close(it.beta3.to_numpy(), oi.beta3, rtol=1e-7, atol=1e-11)
+    # tprfClosedForm == t3prf == IS Full (TprfSuite.scala:20-34)
+    assert close(c.forecasts.to_numpy(), it.forecasts.to_numpy())
+    if T >= 10:
+        isf = u.estimate3prf(dy, dX, dZ)
+        assert close(isf.forecasts.to_numpy(), it.forecasts.to_numpy(), rtol=1e-12)
+    # strided inputs: Z as a column slice of a wider matrix, y as a column of a T x 3 matrix
+    ZZ = u.Mat.from_numpy(np.column_stack([np.zeros(T), Z, np.ones(T)]))._raw_slice(0, T, 1, 1 + L)
+    yy = u.Mat.from_numpy(np.column_stack([y, y * 2, y * 3]))._raw_slice(0, T, 0, 1)
+    c2 = u.tprfClosedForm(yy, dX, ZZ)
+    assert np.array_equal(c2.forecasts.to_numpy(), c.forecasts.to_numpy())
+
+
+def test_edge_semantics(u):
+    """TprfCoverageSuite.scala:176-230."""
+    rng = np.random.default_rng(4)
+    T, N, L = 40, 9, 2
+    X = rng.standard_normal((T, N)); X[:, 3] = 2.5          # constant column -> sd := 1.0
+    y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, L))
+    r = u.tprfClosedForm(*devs(u, y, X, Z))
+    assert r.xstd.to_numpy()[0, 3] == 1.0
+    assert close(r.forecasts.to_numpy(), to.tprf_closed_form_literal(y, X, Z).forecasts)
+    # T < minObs (10) -> all-NaN forecasts, NaN R^2 (Tprf3.scala:893-894)
+    s = u.estimate3prf(*devs(u, y[:5], X[:5], Z[:5]))
+    assert np.isnan(s.forecasts.to_numpy()).all() and np.isnan(s.rSquared)
+    # ssy == 0 -> R^2 = 0 in tprfClosedForm / t3prf (Tprf3.scala:239-241)
+    r0 = u.t3prf(*devs(u, np.ones((T, 1)), X, Z))
+    assert r0.rSquared == 0.0
+    with pytest.raises(ValueError):
+        u.estimate3prf(*devs(u, y, X, Z), procedure="bogus")
+    with pytest.raises(ValueError):
+        u.tprfClosedForm(*devs(u, y[:-1], X, Z))
+    # a NaN in X poisons the fit, as the reference's matmuls do
+    Xn = X.copy(); Xn[7, 2] = np.nan
+    assert np.isnan(u.tprfClosedForm(*devs(u, y, Xn, Z)).forecasts.to_numpy()).all()
+
+
+def test_batched_matches_single(u):
+    import ctypes as C
+    from uni_b200 import _lib as L_
+    B, T, N, L = 6, 64, 200, 4
+    rng = [np.random.default_rng(p) for p in range(B)]
+    Xs = np.stack([g.standard_normal((T, N)) for g in rng]); ys = np.stack([g.standard_normal((T, 1)) for g in rng])
+    Zs = np.stack([g.standard_normal((T, L)) for g in rng])
+    dX = u.Mat.from_numpy(Xs.reshape(B * T, N)); dy = u.Mat.from_numpy(ys.reshape(B * T, 1)); dZ = u.Mat.from_numpy(Zs.reshape(B * T, L))
+    f = u.MatD.zeros(B * T, 1); a = u.MatD.zeros(B * N, 1); r2 = u.MatD.zeros(B, 1)
+    L_.check(L_.lib.um_tprf_fit_batched(L_.TPRF_CLOSED, dy._buf.ptr, dX._buf.ptr, dZ._buf.ptr, T, N, L, B, f._buf.ptr, a._buf.ptr, r2._buf.ptr))
+    F = f.to_numpy().reshape(B, T); A = a.to_numpy().reshape(B, N); R = r2.to_numpy().ravel()
+    for p in range(B):
+        o = to.tprf_closed_form_gram(ys[p], Xs[p], Zs[p])
+        assert close(F[p], o.forecasts.ravel()) and close(A[p], o.alpha.ravel(), rtol=1e-8) and close(R[p], o.r_squared)
+
+
+def test_host_streamed_fit(u):
+    import ctypes as C
+    from uni_b200 import _lib as L_
+    T, N, L = 96, 20000, 3
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((T, N)); y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, L))
+    f = np.zeros(T); a = np.zeros(N); r2 = C.c_double(0)
+    vp = lambda arr: arr.ctypes.data_as(C.c_void_p)
+    L_.check(L_.lib.um_tprf_fit_host(L_.TPRF_CLOSED, vp(y), vp(X), N, vp(Z), T, N, L, N, vp(f), vp(a), C.byref(r2)))
+    o = to.tprf_closed_form_gram(y, X, Z)
+    assert close(f, o.forecasts.ravel()) and close(a, o.alpha.ravel(), rtol=1e-8, atol=1e-13) and close(r2.value, o.r_squared)
+
+
+def test_full_size_properties(u):
+    """BASELINE config 4 at full size (T=8192, N=262144, L=8, 16 GiB panel generated in HBM):
+    closed form and three-pass fit must agree (TprfSuite.scala:20-34); alpha reproduces yhat."""
+    T, N, L = 8192, 262144, 8
+    X = u.MatD.randn(T, N, seed=1); y = u.MatD.randn(T, 1, seed=2); Z = u.MatD.randn(T, L, seed=3)
+    c = u.tprfClosedForm(y, X, Z)
+    it = u.t3prf(y, X, Z)
+    fc, fi = c.forecasts.to_numpy(), it.forecasts.to_numpy()
+    assert np.isfinite(fc).all() and close(fc, fi, rtol=1e-9, atol=1e-12)
+    assert close(c.rSquared, it.rSquared, rtol=1e-9)
+    c2 = u.tprfClosedForm(y, X, Z)
+    assert np.array_equal(fc, c2.forecasts.to_numpy()), "fixed reduction tree: bit-reproducible"
+    # column statistics at full size against the axis reducers (independent kernels)
+    sd = c.xstd.to_numpy()
+    v = X.var(0).to_numpy() * (T / (T - 1.0))
+    assert close(sd * sd, v, rtol=1e-11)

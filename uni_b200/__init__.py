@@ -1,0 +1,14 @@
+"""uni_b200 -- B200-native device backend for uni's `MatD`/`MatF` + 3PRF hot path.
+
+Everything computes in libunimat.so (hand-written sm_100a CUDA behind the C ABI of
+include/unimat.h).  Importing this package loads that library and fails if it is missing.
+"""
+from . import _lib
+from ._lib import (EmptyMatrixError, SingularMatrixError, UnimatError, device_count, launch_count)
+from .mat import Mat, MatD, MatF, init, sync
+from . import tprf3
+from .tprf3 import Tprf3Result, estimate3prf, forecast3prf, t3prf, tprfClosedForm
+
+__all__ = ["Mat", "MatD", "MatF", "init", "sync", "tprf3", "Tprf3Result", "estimate3prf", "forecast3prf",
+           "t3prf", "tprfClosedForm", "device_count", "launch_count", "EmptyMatrixError",
+           "SingularMatrixError", "UnimatError"]

@@ -1,0 +1,124 @@
+// common.cuh -- shared host/device helpers for libunimat (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "unimat.h"
+
+namespace um {
+
+typedef long long i64;
+
+// ---- per-host-thread context: device, stream, timing events, scratch ------------------
+struct Ctx {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 0;
+  void* scratch = nullptr;  // reduction partials etc. (stream-ordered reuse)
+  size_t scratch_bytes = 0;
+};
+
+Ctx* ctx();  // lazily initialised on device 0 (or the device chosen by um_init)
+int ensure_ctx();
+int fail(int code, const char* fmt, ...);
+void* scratch(size_t bytes);  // nullptr + error set on failure
+extern std::atomic<long long> g_launches;
+
+// per-kernel event timing (bench harness): UM_PROF_BEGIN(slot) ... launch ... UM_PROF_END(slot)
+bool prof_on();
+void prof_begin(int slot);
+void prof_end(int slot);
+
+#define UM_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return um::fail(_e == cudaErrorMemoryAllocation ? UM_ERR_OOM : UM_ERR_CUDA, "%s: %s", #expr, \
+                      cudaGetErrorString(_e));                                             \
+  } while (0)
+
+#define UM_CTX()                      \
+  do {                                \
+    int _s = um::ensure_ctx();        \
+    if (_s != UM_OK) return _s;       \
+  } while (0)
+
+// after a kernel launch: count it and surface launch-configuration errors
+#define UM_LAUNCHED()                                                                 \
+  do {                                                                                \
+    um::g_launches.fetch_add(1, std::memory_order_relaxed);                           \
+    cudaError_t _e = cudaGetLastError();                                              \
+    if (_e != cudaSuccess) return um::fail(UM_ERR_CUDA, "kernel launch failed (%s:%d): %s", __FILE__, __LINE__, \
+                                           cudaGetErrorString(_e));                   \
+  } while (0)
+
+#define UM_REQUIRE(cond, ...)                                   \
+  do {                                                          \
+    if (!(cond)) return um::fail(UM_ERR_ARG, __VA_ARGS__);      \
+  } while (0)
+
+inline size_t dtype_size(int dt) { return dt == UM_F64 ? 8 : dt == UM_F32 ? 4 : dt == UM_I32 ? 4 : 1; }
+
+inline int check_view(const um_view* v, const char* name) {
+  if (!v) return fail(UM_ERR_ARG, "%s: null view", name);
+  if (v->rows < 0 || v->cols < 0) return fail(UM_ERR_ARG, "%s: negative shape %lldx%lld", name, (i64)v->rows, (i64)v->cols);
+  if (v->dtype < 0 || v->dtype > UM_I32) return fail(UM_ERR_ARG, "%s: bad dtype %d", name, v->dtype);
+  if (v->rows > 0 && v->cols > 0 && !v->data) return fail(UM_ERR_ARG, "%s: null data", name);
+  return UM_OK;
+}
+#define UM_VIEW(v)                          \
+  do {                                      \
+    int _s = um::check_view((v), #v);       \
+    if (_s != UM_OK) return _s;             \
+  } while (0)
+
+// typed operand: pointer already advanced to element (0,0)
+template <class T>
+struct In {
+  const T* p;
+  i64 rs, cs;
+};
+template <class T>
+struct Out {
+  T* p;
+  i64 rs, cs;
+};
+template <class T>
+inline In<T> in_of(const um_view* v) {
+  return In<T>{static_cast<const T*>(v->data) + v->offset, v->rs, v->cs};
+}
+template <class T>
+inline Out<T> out_of(const um_view* v) {
+  return Out<T>{static_cast<T*>(v->data) + v->offset, v->rs, v->cs};
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// can rows of this operand be read/written with 16-byte vectors of VW elements?
+template <class T>
+inline bool vec_ok(const T* p, i64 rs, i64 cs, i64 rows, int vw) {
+  if (cs == 0) return true;  // splat
+  if (cs != 1) return false;
+  if (!aligned16(p)) return false;
+  if (rows > 1 && (rs % vw) != 0) return false;
+  return true;
+}
+
+// ---- device helpers --------------------------------------------------------------------
+__device__ __forceinline__ double shfl_down_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ i64 shfl_down_l(i64 v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+
+// java.lang.Double.compare order as a signed 64-bit key (Mat.scala:418-440,892-895):
+// -Inf < ... < -0.0 < +0.0 < ... < +Inf < NaN, every NaN equal.
+__device__ __forceinline__ i64 total_key(double x) {
+  if (x != x) return 0x7ff8000000000000LL;
+  i64 b = __double_as_longlong(x);
+  return b < 0 ? (b ^ 0x7fffffffffffffffLL) : b;
+}
+__device__ __forceinline__ i64 total_key(float x) { return total_key((double)x); }
+
+}  // namespace um

@@ -1,0 +1,314 @@
+// matmul.cu -- `a *@ b` for Mat[Double] (FP64 tensor pipe: DMMA m8n8k4) and Mat[Float].
+//
+// FP64: tcgen05 has no f64 kind, so the FP64 tensor path on sm_100a is the warp-level
+// `mma.sync.aligned.m8n8k4.f64` (SASS DMMA.8x8x4).  CTA tile 128x128x16, 8 warps as 2x4
+// (warp tile 64x32 = 8x4 DMMA tiles, 64 accumulator doubles per lane), 3-stage cp.async
+// pipeline into padded shared memory whose pitches (20 / 132 doubles) make every fragment
+// load bank-conflict free for both operand orientations.  Operands are read THROUGH their
+// stride descriptor: a transposed view (rs == 1) is staged with its contiguous dimension
+// along the shared-memory row, so `m.T *@ m` costs no copy (Mat.scala:2815-2881; the
+// reference copies non-BLAS-safe operands first, Mat.scala:1169).
+//
+// FP32: register-tiled FFMA kernel (float accumulate, as multiplyFloat Mat.scala:3236-3268).
+#include "common.cuh"
+
+namespace um {
+
+constexpr int MM_BM = 128, MM_BN = 128, MM_BK = 16, MM_STAGES = 3, MM_THREADS = 256;
+constexpr int MM_PK = MM_BK + 4;     // pitch when the k dimension is contiguous (20 doubles)
+constexpr int MM_PMN = MM_BM + 4;    // pitch when the m/n dimension is contiguous (132 doubles)
+constexpr int MM_TILE_ELEMS = MM_BM * MM_PK;  // 2560 >= 16 * 132 = 2112: one operand stage
+constexpr int MM_SMEM_BYTES = MM_STAGES * 2 * MM_TILE_ELEMS * 8;  // 122880
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Stage one operand tile.  The operand is a (outer x inner) box where `inner` is the
+// memory-contiguous dimension: KMAJOR -> outer = m (or n), inner = k (box 128 x 16, pitch 20);
+// otherwise outer = k, inner = m (or n) (box 16 x 128, pitch 132).  g(o, i) = p[o*ld + i].
+template <bool KMAJOR, bool VEC16>
+__device__ __forceinline__ void stage_tile(double* sm, const double* __restrict__ p, i64 ld, i64 o0, i64 i0,
+                                           i64 o_lim, i64 i_lim, int tid) {
+  constexpr int OUTER = KMAJOR ? MM_BM : MM_BK;
+  constexpr int INNER = KMAJOR ? MM_BK : MM_BM;
+  constexpr int PITCH = KMAJOR ? MM_PK : MM_PMN;
+  constexpr int CH = VEC16 ? 2 : 1;               // doubles per cp.async
+  constexpr int CPR = INNER / CH;                 // chunks per box row
+  constexpr int TOTAL = OUTER * CPR;
+#pragma unroll
+  for (int c = tid; c < TOTAL; c += MM_THREADS) {
+    int o = c / CPR, i = (c % CPR) * CH;
+    i64 go = o0 + o, gi = i0 + i;
+    i64 rem = (go < o_lim) ? (i_lim - gi) : 0;    // valid elements from gi on
+    int nvalid = rem <= 0 ? 0 : (rem >= CH ? CH : (int)rem);
+    const double* src = nvalid ? (p + go * ld + gi) : p;
+    double* dst = sm + o * PITCH + i;
+    if (VEC16) cp_async16(dst, src, nvalid * 8);
+    else cp_async8(dst, src, nvalid * 8);
+  }
+}
+
+// C[m][n] = sum_k A(m,k) B(k,n).  A(m,k) = pa[m*a_rs + k*a_cs] with one of the strides == 1,
+// same for B.  AK: A is k-contiguous (a_cs == 1); BK_: B is k-contiguous (b_rs == 1).
+template <bool AK, bool BKM, bool VEC16>
+__global__ void __launch_bounds__(MM_THREADS, 1)
+k_dgemm(const double* __restrict__ pa, i64 lda, const double* __restrict__ pb, i64 ldb, double* __restrict__ pc, i64 ldc,
+        i64 M, i64 N, i64 K) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+  const i64 m0 = (i64)blockIdx.y * MM_BM, n0 = (i64)blockIdx.x * MM_BN;
+  const int KT = (int)((K + MM_BK - 1) / MM_BK);
+
+  auto stage = [&](int s, int kt) {
+    double* sa = smem + (size_t)s * 2 * MM_TILE_ELEMS;
+    double* sb = sa + MM_TILE_ELEMS;
+    const i64 k0 = (i64)kt * MM_BK;
+    if (AK) stage_tile<true, VEC16>(sa, pa, lda, m0, k0, M, K, tid);     // outer m, inner k
+    else stage_tile<false, VEC16>(sa, pa, lda, k0, m0, K, M, tid);       // outer k, inner m
+    if (BKM) stage_tile<true, VEC16>(sb, pb, ldb, n0, k0, N, K, tid);    // outer n, inner k
+    else stage_tile<false, VEC16>(sb, pb, ldb, k0, n0, K, N, tid);       // outer k, inner n
+  };
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < MM_STAGES - 1; ++s) {
+    if (s < KT) stage(s, s);
+    cp_async_commit();
+  }
+
+  const int fr = lane >> 2, fk = lane & 3;  // fragment row (m or n) and k index
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<MM_STAGES - 2>();
+    __syncthreads();
+    {
+      int nk = kt + MM_STAGES - 1;
+      if (nk < KT) stage(nk % MM_STAGES, nk);
+      cp_async_commit();
+    }
+    const double* sa = smem + (size_t)(kt % MM_STAGES) * 2 * MM_TILE_ELEMS;
+    const double* sb = sa + MM_TILE_ELEMS;
+#pragma unroll
+    for (int kk = 0; kk < MM_BK; kk += 4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int m = wm * 64 + i * 8 + fr;
+        af[i] = AK ? sa[m * MM_PK + kk + fk] : sa[(kk + fk) * MM_PMN + m];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int n = wn * 32 + j * 8 + fr;
+        bf[j] = BKM ? sb[n * MM_PK + kk + fk] : sb[(kk + fk) * MM_PMN + n];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: lane holds C[row = fr][col = 2*fk, 2*fk+1] of each 8x8 tile
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    i64 m = m0 + wm * 64 + i * 8 + fr;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      i64 n = n0 + wn * 32 + j * 8 + 2 * fk;
+      double* dst = pc + m * ldc + n;
+      if (n + 1 < N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+      } else {
+        if (n < N) dst[0] = acc[i][j][0];
+        if (n + 1 < N) dst[1] = acc[i][j][1];
+      }
+    }
+  }
+}
+
+// generic-stride fallback (neither stride of an operand is 1): one thread per C element
+template <class T>
+__global__ void __launch_bounds__(256) k_gemm_naive(In<T> a, In<T> b, T* __restrict__ pc, i64 ldc, i64 M, i64 N, i64 K) {
+  i64 n = (i64)blockIdx.x * 16 + (threadIdx.x & 15);
+  i64 m = (i64)blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (m >= M || n >= N) return;
+  T s = 0;
+  for (i64 k = 0; k < K; ++k) s += a.p[m * a.rs + k * a.cs] * b.p[k * b.rs + n * b.cs];
+  pc[m * ldc + n] = s;
+}
+
+// ---- FP32: 128x128x8 tiles, 8x8 register micro-tile, float accumulate -----------------------------
+constexpr int SG_BM = 128, SG_BN = 128, SG_BK = 8;
+__global__ void __launch_bounds__(256, 2)
+k_sgemm(In<float> a, In<float> b, float* __restrict__ pc, i64 ldc, i64 M, i64 N, i64 K) {
+  __shared__ float As[2][SG_BK][SG_BM + 4];
+  __shared__ float Bs[2][SG_BK][SG_BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 8x8 outputs (strided by 16)
+  const i64 m0 = (i64)blockIdx.y * SG_BM, n0 = (i64)blockIdx.x * SG_BN;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  // loader mapping: 1024 elements per operand tile, 4 per thread.  Pick the thread->element
+  // map so that the memory-contiguous dimension runs along consecutive threads.
+  const bool a_kc = a.cs == 1;  // A contiguous along k
+  const bool b_nc = b.cs == 1;  // B contiguous along n
+  float ra[4], rb[4];
+  auto gload = [&](i64 k0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int e = tid + q * 256;
+      int am, ak;
+      if (a_kc) { ak = e & 7; am = e >> 3; } else { am = e & 127; ak = e >> 7; }
+      i64 gm = m0 + am, gk = k0 + ak;
+      ra[q] = (gm < M && gk < K) ? a.p[gm * a.rs + gk * a.cs] : 0.f;
+      int bn, bk;
+      if (b_nc) { bn = e & 127; bk = e >> 7; } else { bk = e & 7; bn = e >> 3; }
+      i64 gn = n0 + bn;
+      gk = k0 + bk;
+      rb[q] = (gn < N && gk < K) ? b.p[gk * b.rs + gn * b.cs] : 0.f;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int e = tid + q * 256;
+      int am, ak;
+      if (a_kc) { ak = e & 7; am = e >> 3; } else { am = e & 127; ak = e >> 7; }
+      As[buf][ak][am] = ra[q];
+      int bn, bk;
+      if (b_nc) { bn = e & 127; bk = e >> 7; } else { bk = e & 7; bn = e >> 3; }
+      Bs[buf][bk][bn] = rb[q];
+    }
+  };
+  const int KT = (int)((K + SG_BK - 1) / SG_BK);
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < KT; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < KT) gload((i64)(kt + 1) * SG_BK);
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      float av[8], bv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) av[i] = As[buf][k][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bv[j] = Bs[buf][k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < KT) sstore(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    i64 m = m0 + ty + 16 * i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      i64 n = n0 + tx + 16 * j;
+      if (n < N) pc[m * ldc + n] = acc[i][j];
+    }
+  }
+}
+
+template <bool AK, bool BKM>
+static int launch_dgemm(const double* pa, i64 lda, const double* pb, i64 ldb, double* pc, i64 ldc, i64 M, i64 N, i64 K,
+                        bool vec16) {
+  dim3 grid((unsigned)((N + MM_BN - 1) / MM_BN), (unsigned)((M + MM_BM - 1) / MM_BM));
+  cudaStream_t st = ctx()->stream;
+  if (vec16) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      UM_CUDA(cudaFuncSetAttribute(k_dgemm<AK, BKM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+      attr_done = true;
+    }
+    k_dgemm<AK, BKM, true><<<grid, MM_THREADS, MM_SMEM_BYTES, st>>>(pa, lda, pb, ldb, pc, ldc, M, N, K);
+  } else {
+    static bool attr_done = false;
+    if (!attr_done) {
+      UM_CUDA(cudaFuncSetAttribute(k_dgemm<AK, BKM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+      attr_done = true;
+    }
+    k_dgemm<AK, BKM, false><<<grid, MM_THREADS, MM_SMEM_BYTES, st>>>(pa, lda, pb, ldb, pc, ldc, M, N, K);
+  }
+  UM_LAUNCHED();
+  return UM_OK;
+}
+
+}  // namespace um
+
+using namespace um;
+
+extern "C" int32_t um_matmul(const um_view* a, const um_view* b, const um_view* out) {
+  UM_CTX();
+  UM_VIEW(a); UM_VIEW(b); UM_VIEW(out);
+  // require(m.cols == other.rows) -> IllegalArgumentException (Mat.scala:2816-2817)
+  UM_REQUIRE(a->cols == b->rows, "matmul shape mismatch: %lldx%lld *@ %lldx%lld", (i64)a->rows, (i64)a->cols,
+             (i64)b->rows, (i64)b->cols);
+  UM_REQUIRE(out->rows == a->rows && out->cols == b->cols, "matmul output must be %lldx%lld", (i64)a->rows, (i64)b->cols);
+  UM_REQUIRE(a->dtype == b->dtype && a->dtype == out->dtype, "matmul operands must share a dtype");
+  UM_REQUIRE(out->cs == 1 || out->cols == 1, "matmul output must be row-contiguous");
+  const i64 M = a->rows, N = b->cols, K = a->cols;
+  if (M == 0 || N == 0) return UM_OK;
+  if (K == 0) return um_fill(out, 0.0);
+  const i64 ldc = out->rs;
+  if (a->dtype == UM_F64) {
+    In<double> A = in_of<double>(a), B = in_of<double>(b);
+    double* pc = static_cast<double*>(out->data) + out->offset;
+    // degenerate dimensions make either stride usable as "the contiguous one"
+    bool a_k = A.cs == 1 || K == 1, a_m = A.rs == 1 || M == 1;
+    bool b_n = B.cs == 1 || N == 1, b_k = B.rs == 1 || K == 1;
+    if ((a_k || a_m) && (b_n || b_k)) {
+      bool AK = a_k;
+      bool BKM = !b_n;
+      i64 lda = AK ? (M == 1 ? K : A.rs) : (K == 1 ? M : A.cs);
+      i64 ldb = BKM ? (N == 1 ? K : B.cs) : (K == 1 ? N : B.rs);
+      bool vec16 = aligned16(A.p) && aligned16(B.p) && (lda % 2 == 0) && (ldb % 2 == 0);
+      if (AK && !BKM) return launch_dgemm<true, false>(A.p, lda, B.p, ldb, pc, ldc, M, N, K, vec16);
+      if (AK && BKM) return launch_dgemm<true, true>(A.p, lda, B.p, ldb, pc, ldc, M, N, K, vec16);
+      if (!AK && !BKM) return launch_dgemm<false, false>(A.p, lda, B.p, ldb, pc, ldc, M, N, K, vec16);
+      return launch_dgemm<false, true>(A.p, lda, B.p, ldb, pc, ldc, M, N, K, vec16);
+    }
+    dim3 grid((unsigned)((N + 15) / 16), (unsigned)((M + 15) / 16));
+    k_gemm_naive<double><<<grid, 256, 0, ctx()->stream>>>(A, B, pc, ldc, M, N, K);
+    UM_LAUNCHED();
+    return UM_OK;
+  }
+  if (a->dtype == UM_F32) {
+    In<float> A = in_of<float>(a), B = in_of<float>(b);
+    float* pc = static_cast<float*>(out->data) + out->offset;
+    dim3 grid((unsigned)((N + SG_BN - 1) / SG_BN), (unsigned)((M + SG_BM - 1) / SG_BM));
+    k_sgemm<<<grid, 256, 0, ctx()->stream>>>(A, B, pc, ldc, M, N, K);
+    UM_LAUNCHED();
+    return UM_OK;
+  }
+  return fail(UM_ERR_ARG, "matmul needs f64 or f32 operands");
+}

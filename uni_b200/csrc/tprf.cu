@@ -1,0 +1,1098 @@
+// tprf.cu -- Kelly-Pruitt Three-Pass Regression Filter on the device (stats/Tprf3.scala).
+//
+// The reference's closed form builds an N x N `Sxx` and an N x T factor (Tprf3.scala:206-207):
+// infeasible at N = 262144.  Both fits are re-associated here onto ONE
+// set of shard-additive accumulators that never exceed T x L:
+//
+//   per column j :  mu_j, sd_j (sample std, Tprf3.scala:469-502), W0_j = Zc' x_j / sd_j   (L)
+//   PX  = sum_j (x_j / sd_j) W0_j'      (T x L)      h0  = sum_j x_j / sd_j             (T)
+//   sw  = sum_j W0_j    SWW = sum_j W0_j W0_j'    smw = sum_j (mu_j/sd_j) W0_j    smu = sum_j mu_j/sd_j
+//
+// with Zc = J(T) Z.  Closed form (Tprf3.scala:199-209, rust/src/t3prf.rs:861-869):
+//   wbar = sw/N,  G = PX - 1 smw' - (h0 - smu) wbar',  s = (G'G)^-1 G'y,  yhat = G s + ybar,
+//   alpha_j = (W0_j - wbar) s.
+// Three-pass fit (Tprf3.scala:260-289): Phi = W0 Szz^-1 (pass-1 slopes with intercept),
+//   [1|Phi]'[1|Phi] from (N, sw, SWW),  Xn [1|Phi] = [h0 | PX Szz^-1],  then passes 2-3 are O(T L^2).
+//
+// Kernels (all batched over independent panels through blockIdx.z):
+//   k_tprf_prep      Zc, zbar, Szz, ybar, ssy                       (tiny)
+//   k_tprf_colstats  sweep 1 over X: per column  sum(x-k), sum(x-k)^2 (FP64 pipe) and Zc' x
+//                    (DMMA m8n8k4, M = 8 columns, N = L<=8, K = rows), cp.async 3-stage tiles
+//   k_tprf_colfinal  per column mu/sd/W0/V + block partials of sw, SWW, smw, smu
+//   k_tprf_project   sweep 2 over X: PX, h0 (DMMA, M = 8 rows, N = L, K = columns)
+//   k_tprf_gather    fixed-order sum of the chunk partials into the packed all-reduce buffer
+//   k_tprf_finish    the O(T L^2) finish of either fit (one CTA per panel)
+//   k_tprf_outputs   alpha / phi / phi_hat / xstd per column
+// Multi-GPU: X is sharded by predictor column; the packed buffer (T*(L8+1)+81 doubles) is the
+// only thing exchanged (um_comm_allreduce_sum_f64), then every rank runs the same finish.
+#include "common.cuh"
+#include "small_linalg.cuh"
+
+namespace um {
+
+int comm_allreduce_sum_f64_impl(double* buf, i64 count);  // comm.cu
+bool comm_active();
+int comm_world();
+
+constexpr int LP = 8;            // padded proxy count (DMMA N)
+constexpr int ZPITCH = 12;       // smem pitch of an (rows x 8) operand: conflict-free B fragments
+constexpr int NSMALL = 8 + 64 + 8 + 1;  // sw | SWW | smw | smu = 81
+
+// ---- small helpers -----------------------------------------------------------------------------------
+__device__ __forceinline__ void t_cp16(void* smem, const void* g, int bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(g), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void t_cp8(void* smem, const void* g, int bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(g), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void t_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void t_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void t_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// copy a (rows x cols) box of doubles (global row pitch ld) into smem (pitch), zero-filling
+// anything outside [0,row_lim) x [0,col_lim).  cols multiple of 2.
+template <bool VEC16>
+__device__ __forceinline__ void stage_box(double* sm, int pitch, const double* __restrict__ g, i64 ld, i64 r0, i64 c0,
+                                          int rows, int cols, i64 row_lim, i64 col_lim, int tid, int nthreads) {
+  const int ch = VEC16 ? 2 : 1;
+  const int cpr = cols / ch;
+  const int total = rows * cpr;
+  for (int c = tid; c < total; c += nthreads) {
+    int r = c / cpr, q = (c % cpr) * ch;
+    i64 gr = r0 + r, gc = c0 + q;
+    i64 rem = (gr < row_lim) ? (col_lim - gc) : 0;
+    int nv = rem <= 0 ? 0 : (rem >= ch ? ch : (int)rem);
+    const double* src = nv ? (g + gr * ld + gc) : g;
+    if (VEC16) t_cp16(sm + r * pitch + q, src, nv * 8);
+    else t_cp8(sm + r * pitch + q, src, nv * 8);
+  }
+}
+
+// ---- prep: Zc (T x 8, zero padded), zbar, Szz, ybar, ssy ------------------------------------------------
+// small[] layout per panel: zbar[8] | Szz[64] | ybar | ssy | (pad to 80)
+constexpr int SMALL_PREP = 80;
+__global__ void __launch_bounds__(256) k_tprf_prep(const double* __restrict__ Z, i64 z_rs, i64 z_cs, i64 z_bs,
+                                                    const double* __restrict__ y, i64 y_s, i64 y_bs, i64 T, int L,
+                                                    double* __restrict__ zc, double* __restrict__ small) {
+  __shared__ double red[8][48];
+  __shared__ double zbar[LP];
+  __shared__ double ybar_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const i64 b = blockIdx.z;
+  Z += b * z_bs;
+  y += b * y_bs;
+  zc += b * T * LP;
+  small += b * SMALL_PREP;
+  // pass 1: column sums of Z and sum of y
+  double acc[LP + 1];
+#pragma unroll
+  for (int l = 0; l <= LP; ++l) acc[l] = 0.0;
+  for (i64 t = tid; t < T; t += 256) {
+#pragma unroll
+    for (int l = 0; l < LP; ++l)
+      if (l < L) acc[l] += Z[t * z_rs + l * z_cs];
+    acc[LP] += y[t * y_s];
+  }
+#pragma unroll
+  for (int l = 0; l <= LP; ++l) {
+    double v = acc[l];
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if (lane == 0) red[warp][l] = v;
+  }
+  __syncthreads();
+  if (tid <= LP) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += red[w][tid];
+    v /= (double)T;
+    if (tid < LP) zbar[tid] = v;
+    else ybar_s = v;
+  }
+  __syncthreads();
+  // pass 2: Zc, Szz (upper triangle, 36 values), ssy
+  double sz[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) sz[i] = 0.0;
+  double ssy = 0.0;
+  const double yb = ybar_s;
+  for (i64 t = tid; t < T; t += 256) {
+    double z[LP];
+#pragma unroll
+    for (int l = 0; l < LP; ++l) {
+      z[l] = l < L ? Z[t * z_rs + l * z_cs] - zbar[l] : 0.0;
+      zc[t * LP + l] = z[l];
+    }
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < LP; ++a)
+#pragma unroll
+      for (int c = a; c < LP; ++c) sz[q++] += z[a] * z[c];
+    double d = y[t * y_s] - yb;
+    ssy += d * d;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 37; ++i) {
+    double v = i < 36 ? sz[i] : ssy;
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  if (tid < 37) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += red[w][tid];
+    red[0][tid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int l = 0; l < LP; ++l) small[l] = zbar[l];
+    int q = 0;
+    for (int a = 0; a < LP; ++a)
+      for (int c = a; c < LP; ++c) {
+        double v = red[0][q++];
+        small[8 + a * LP + c] = v;
+        small[8 + c * LP + a] = v;
+      }
+    small[72] = ybar_s;
+    small[73] = red[0][36];
+  }
+}
+
+// ---- sweep 1: column statistics + Zc' x ------------------------------------------------------------------
+constexpr int C1_ROWS = 32, C1_COLS = 64, C1_PITCH = 68, C1_STAGES = 3, C1_THREADS = 256;
+constexpr int C1_STAGE_DBL = C1_ROWS * C1_PITCH + C1_ROWS * ZPITCH;  // 2176 + 384 = 2560 doubles
+constexpr int C1_SMEM = C1_STAGES * C1_STAGE_DBL * 8;                // 61440 B
+
+// outputs per (panel, chunk, column): q[8], s1, s2   (column index padded to strips*64)
+template <bool VEC16>
+__global__ void __launch_bounds__(C1_THREADS, 2)
+k_tprf_colstats(const double* __restrict__ X, i64 ldx, i64 x_bs, const double* __restrict__ zc, i64 T, i64 N, i64 npad,
+                i64 rows_per_chunk, double* __restrict__ qp, double* __restrict__ s1p, double* __restrict__ s2p) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const i64 b = blockIdx.z;
+  const int chunk = blockIdx.y, nchunk = gridDim.y;
+  X += b * x_bs;
+  zc += b * T * LP;
+  const i64 c0 = (i64)blockIdx.x * C1_COLS;
+  const i64 r_lo = (i64)chunk * rows_per_chunk;
+  i64 r_hi = r_lo + rows_per_chunk;
+  if (r_hi > T) r_hi = T;
+  const int ntiles = (int)((r_hi - r_lo + C1_ROWS - 1) / C1_ROWS);
+
+  auto stage = [&](int s, int tile) {
+    double* xs = smem + (size_t)s * C1_STAGE_DBL;
+    double* zs = xs + C1_ROWS * C1_PITCH;
+    const i64 r0 = r_lo + (i64)tile * C1_ROWS;
+    stage_box<VEC16>(xs, C1_PITCH, X, ldx, r0, c0, C1_ROWS, C1_COLS, r_hi, N, tid, C1_THREADS);
+    stage_box<true>(zs, ZPITCH, zc, LP, r0, 0, C1_ROWS, LP, r_hi, LP, tid, C1_THREADS);
+  };
+
+  const int fj = lane >> 2, ft = lane & 3;         // fragment column / row-in-k4
+  const i64 col = c0 + warp * 8 + fj;
+  const double kshift = (col < N) ? X[col] : 0.0;  // row 0 of the panel: the variance shift
+  double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
+  double s1 = 0.0, s2 = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < C1_STAGES - 1; ++s) {
+    if (s < ntiles) stage(s, s);
+    t_commit();
+  }
+  for (int tile = 0; tile < ntiles; ++tile) {
+    t_wait<C1_STAGES - 2>();
+    __syncthreads();
+    {
+      int nt = tile + C1_STAGES - 1;
+      if (nt < ntiles) stage(nt % C1_STAGES, nt);
+      t_commit();
+    }
+    const double* xs = smem + (size_t)(tile % C1_STAGES) * C1_STAGE_DBL;
+    const double* zs = xs + C1_ROWS * C1_PITCH;
+    const i64 r0 = r_lo + (i64)tile * C1_ROWS;
+    const bool full = r0 + C1_ROWS <= r_hi;
+#pragma unroll
+    for (int ks = 0; ks < C1_ROWS / 4; ++ks) {
+      const int t = ks * 4 + ft;
+      const double a = xs[t * C1_PITCH + warp * 8 + fj];
+      const double bz = zs[t * ZPITCH + fj];
+      if (ks & 1) t_dmma(acc1[0], acc1[1], a, bz);
+      else t_dmma(acc0[0], acc0[1], a, bz);
+      double d = a - kshift;
+      if (!full && r0 + t >= r_hi) d = 0.0;
+      s1 += d;
+      s2 = fma(d, d, s2);
+    }
+  }
+  t_wait<0>();
+  // fold the 4 row-phases of each column
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+  const i64 pidx = (b * nchunk + chunk) * npad + col;  // col < npad always
+  double2 q = make_double2(acc0[0] + acc1[0], acc0[1] + acc1[1]);
+  *reinterpret_cast<double2*>(qp + pidx * LP + 2 * ft) = q;  // C[j = fj][l = 2*ft, 2*ft+1]
+  if (ft == 0) {
+    s1p[pidx] = s1;
+    s2p[pidx] = s2;
+  }
+}
+
+// ---- per-column finalisation ------------------------------------------------------------------------------
+// cols arrays per panel (npad entries): w0[8], v[8] (= w0/sd), invsd, mun (= mu/sd)
+__global__ void __launch_bounds__(256)
+k_tprf_colfinal(const double* __restrict__ X, i64 x_bs, const double* __restrict__ qp, const double* __restrict__ s1p,
+                const double* __restrict__ s2p, int nchunk, i64 T, i64 N, i64 npad, double* __restrict__ w0,
+                double* __restrict__ v, double* __restrict__ invsd, double* __restrict__ mun,
+                double* __restrict__ blockpart /* [panel][gridDim.x][81] */) {
+  __shared__ double red[8][NSMALL];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const i64 b = blockIdx.z;
+  X += b * x_bs;
+  double loc[NSMALL];
+#pragma unroll
+  for (int i = 0; i < NSMALL; ++i) loc[i] = 0.0;
+  for (i64 j = (i64)blockIdx.x * 256 + tid; j < N; j += (i64)gridDim.x * 256) {
+    double S = 0.0, SS = 0.0, q[LP];
+#pragma unroll
+    for (int l = 0; l < LP; ++l) q[l] = 0.0;
+    for (int c = 0; c < nchunk; ++c) {
+      const i64 pidx = (b * nchunk + c) * npad + j;
+      S += s1p[pidx];
+      SS += s2p[pidx];
+      const double2* qq = reinterpret_cast<const double2*>(qp + pidx * LP);
+#pragma unroll
+      for (int l = 0; l < LP / 2; ++l) {
+        double2 t2 = qq[l];
+        q[2 * l] += t2.x;
+        q[2 * l + 1] += t2.y;
+      }
+    }
+    const double k = X[j];
+    const double dm = S / (double)T;
+    const double mu = k + dm;
+    double sd = 1.0;
+    if (T > 1) {
+      double var = (SS - S * dm) / (double)(T - 1);
+      if (var < 0.0) var = 0.0;
+      sd = sqrt(var);       // NaN input stays NaN (the reference's matmuls would spread it too)
+      if (sd == 0.0) sd = 1.0;  // Tprf3.scala:493-501
+    }
+    const double inv = 1.0 / sd;
+    const double m_n = mu * inv;
+    const i64 cidx = b * npad + j;
+    double w[LP];
+#pragma unroll
+    for (int l = 0; l < LP; ++l) {
+      w[l] = q[l] * inv;
+      w0[cidx * LP + l] = w[l];
+      v[cidx * LP + l] = w[l] * inv;
+    }
+    invsd[cidx] = inv;
+    mun[cidx] = m_n;
+#pragma unroll
+    for (int a = 0; a < LP; ++a) {
+      loc[a] += w[a];
+#pragma unroll
+      for (int c = 0; c < LP; ++c) loc[8 + a * LP + c] += w[a] * w[c];
+      loc[72 + a] += m_n * w[a];
+    }
+    loc[80] += m_n;
+  }
+  // columns beyond N up to npad: zero V / invsd so sweep 2 ignores the padding
+  for (i64 j = N + (i64)blockIdx.x * 256 + tid; j < npad; j += (i64)gridDim.x * 256) {
+    const i64 cidx = b * npad + j;
+#pragma unroll
+    for (int l = 0; l < LP; ++l) { w0[cidx * LP + l] = 0.0; v[cidx * LP + l] = 0.0; }
+    invsd[cidx] = 0.0;
+    mun[cidx] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < NSMALL; ++i) {
+    double x = loc[i];
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(0xffffffffu, x, d);
+    if (lane == 0) red[warp][i] = x;
+  }
+  __syncthreads();
+  if (tid < NSMALL) {
+    double x = 0.0;
+    for (int w = 0; w < 8; ++w) x += red[w][tid];
+    blockpart[(b * gridDim.x + blockIdx.x) * NSMALL + tid] = x;
+  }
+}
+
+// ---- sweep 2: PX = Xn W0, h0 = Xn 1 ----------------------------------------------------------------------
+constexpr int C2_ROWS = 128, C2_COLS = 32, C2_PITCH = 36, C2_STAGES = 3, C2_THREADS = 256;
+constexpr int C2_STAGE_DBL = C2_ROWS * C2_PITCH + C2_COLS * ZPITCH + C2_COLS;  // 4608 + 384 + 32 = 5024
+constexpr int C2_SMEM = C2_STAGES * C2_STAGE_DBL * 8;                          // 120576 B
+
+template <bool VEC16>
+__global__ void __launch_bounds__(C2_THREADS, 1)
+k_tprf_project(const double* __restrict__ X, i64 ldx, i64 x_bs, const double* __restrict__ v,
+               const double* __restrict__ invsd, i64 T, i64 N, i64 npad, i64 cols_per_chunk, i64 tpad,
+               double* __restrict__ pxp /* [panel][chunk][tpad][8] */, double* __restrict__ h0p /* [panel][chunk][tpad] */) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const i64 b = blockIdx.z;
+  const int chunk = blockIdx.y, nchunk = gridDim.y;
+  X += b * x_bs;
+  v += b * npad * LP;
+  invsd += b * npad;
+  const i64 r0 = (i64)blockIdx.x * C2_ROWS;
+  const i64 c_lo = (i64)chunk * cols_per_chunk;
+  i64 c_hi = c_lo + cols_per_chunk;
+  if (c_hi > npad) c_hi = npad;
+  const int ntiles = c_hi > c_lo ? (int)((c_hi - c_lo + C2_COLS - 1) / C2_COLS) : 0;
+
+  auto stage = [&](int s, int tile) {
+    double* xs = smem + (size_t)s * C2_STAGE_DBL;
+    double* vs = xs + C2_ROWS * C2_PITCH;
+    double* is = vs + C2_COLS * ZPITCH;
+    const i64 c0 = c_lo + (i64)tile * C2_COLS;
+    stage_box<VEC16>(xs, C2_PITCH, X, ldx, r0, c0, C2_ROWS, C2_COLS, T, N, tid, C2_THREADS);
+    stage_box<true>(vs, ZPITCH, v, LP, c0, 0, C2_COLS, LP, npad, LP, tid, C2_THREADS);
+    stage_box<true>(is, C2_COLS, invsd, npad, 0, c0, 1, C2_COLS, 1, npad, tid, C2_THREADS);
+  };
+
+  const int fr = lane >> 2, fk = lane & 3;
+  double acc[2][2][2];  // [m-tile][k parity][2]
+  double h[2] = {0.0, 0.0};
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int p = 0; p < 2; ++p) acc[i][p][0] = acc[i][p][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < C2_STAGES - 1; ++s) {
+    if (s < ntiles) stage(s, s);
+    t_commit();
+  }
+  for (int tile = 0; tile < ntiles; ++tile) {
+    t_wait<C2_STAGES - 2>();
+    __syncthreads();
+    {
+      int nt = tile + C2_STAGES - 1;
+      if (nt < ntiles) stage(nt % C2_STAGES, nt);
+      t_commit();
+    }
+    const double* xs = smem + (size_t)(tile % C2_STAGES) * C2_STAGE_DBL;
+    const double* vs = xs + C2_ROWS * C2_PITCH;
+    const double* is = vs + C2_COLS * ZPITCH;
+#pragma unroll
+    for (int ks = 0; ks < C2_COLS / 4; ++ks) {
+      const int j = ks * 4 + fk;
+      const double bv = vs[j * ZPITCH + fr];   // V[j][l = fr]
+      const double si = is[j];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double a = xs[(warp * 16 + i * 8 + fr) * C2_PITCH + j];
+        t_dmma(acc[i][ks & 1][0], acc[i][ks & 1][1], a, bv);
+        h[i] = fma(a, si, h[i]);
+      }
+    }
+  }
+  t_wait<0>();
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    h[i] += __shfl_xor_sync(0xffffffffu, h[i], 1);
+    h[i] += __shfl_xor_sync(0xffffffffu, h[i], 2);
+    const i64 t = r0 + warp * 16 + i * 8 + fr;   // < tpad always
+    const i64 pidx = (b * nchunk + chunk) * tpad + t;
+    double2 q = make_double2(acc[i][0][0] + acc[i][1][0], acc[i][0][1] + acc[i][1][1]);
+    *reinterpret_cast<double2*>(pxp + pidx * LP + 2 * fk) = q;
+    if (fk == 0) h0p[pidx] = h[i];
+  }
+}
+
+// ---- gather chunk partials into the packed buffer: PX[T][8] | h0[T] | small[81] --------------------------
+__global__ void __launch_bounds__(256)
+k_tprf_gather(const double* __restrict__ pxp, const double* __restrict__ h0p, int nchunk, i64 T, i64 tpad,
+              const double* __restrict__ blockpart, int nblk, double* __restrict__ packed, i64 packed_stride,
+              int accumulate) {
+  const i64 b = blockIdx.z;
+  double* out = packed + b * packed_stride;
+  const i64 total = T * (LP + 1) + NSMALL;
+  for (i64 e = (i64)blockIdx.x * 256 + threadIdx.x; e < total; e += (i64)gridDim.x * 256) {
+    double s = 0.0;
+    if (e < T * LP) {
+      const i64 t = e / LP;
+      const int l = (int)(e % LP);
+      for (int c = 0; c < nchunk; ++c) s += pxp[((b * nchunk + c) * tpad + t) * LP + l];
+    } else if (e < T * (LP + 1)) {
+      const i64 t = e - T * LP;
+      for (int c = 0; c < nchunk; ++c) s += h0p[(b * nchunk + c) * tpad + t];
+    } else {
+      const int i = (int)(e - T * (LP + 1));
+      for (int k = 0; k < nblk; ++k) s += blockpart[(b * nblk + k) * NSMALL + i];
+    }
+    out[e] = accumulate ? out[e] + s : s;
+  }
+}
+
+// ---- finish: one CTA per panel -----------------------------------------------------------------------------
+struct FinishArgs {
+  const double* packed; i64 packed_stride;
+  const double* small;          // prep output (zbar | Szz | ybar | ssy), SMALL_PREP per panel
+  const double* y; i64 y_s, y_bs;
+  i64 T; int L; double n_total; int mode;
+  double* forecasts; double* residuals; i64 f_bs;     // per panel stride (elements); may be null
+  double* sigma; double* beta3;                        // single-panel outputs (may be null)
+  double* sigma_ws;                                    // T x 8 workspace per panel
+  double* params;                                      // per panel: s[8] | wbar[8] | szzinv[64] | zbar[8] | r2 | singular
+  double* r2_out;                                      // per panel r2 (device), may be null
+};
+constexpr int PARAMS = 96;
+
+template <int NV>
+__device__ __forceinline__ void block_sum(double* loc, double (*red)[64], double* result, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double x = loc[i];
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(0xffffffffu, x, d);
+    if (lane == 0) red[warp][i] = x;
+  }
+  __syncthreads();
+  if (tid < NV) {
+    double x = 0.0;
+    for (int w = 0; w < 8; ++w) x += red[w][tid];
+    result[tid] = x;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
+  __shared__ double red[8][64];
+  __shared__ double tot[64];
+  __shared__ double sw[LP], smw[LP], wbar[LP], s_cl[LP], szzinv[LP * LP], m2[(LP + 1) * LP], beta[LP + 1];
+  __shared__ double smu_s, ybar_s, ssy_s;
+  __shared__ int singular_s;
+  const int tid = threadIdx.x;
+  const i64 b = blockIdx.x;
+  const i64 T = g.T;
+  const int L = g.L, L1 = g.L + 1;
+  const double* px = g.packed + b * g.packed_stride;
+  const double* h0 = px + T * LP;
+  const double* sm = h0 + T;  // sw[8] | SWW[64] | smw[8] | smu
+  const double* small = g.small + b * SMALL_PREP;
+  const double* y = g.y + b * g.y_bs;
+  double* par = g.params + b * PARAMS;
+  double* fc = g.forecasts ? g.forecasts + b * g.f_bs : nullptr;
+  double* rs = g.residuals ? g.residuals + b * g.f_bs : nullptr;
+  double* sig_ws = g.sigma_ws + b * T * LP;
+  if (tid < LP) {
+    sw[tid] = sm[tid];
+    smw[tid] = sm[72 + tid];
+    wbar[tid] = sm[tid] / g.n_total;
+    s_cl[tid] = 0.0;
+  }
+  if (tid < LP * LP) szzinv[tid] = 0.0;
+  if (tid == 0) {
+    smu_s = sm[80];
+    ybar_s = small[72];
+    ssy_s = small[73];
+    singular_s = 0;
+  }
+  __syncthreads();
+  const double ybar = ybar_s, ssy = ssy_s, smu = smu_s;
+  double r2 = 0.0;
+
+  if (g.mode != UM_TPRF_ITER) {
+    // ---- closed form: G = PX - 1 smw' - (h0 - smu) wbar' ; s = (G'G)^-1 G'y ----
+    double loc[44];
+#pragma unroll
+    for (int i = 0; i < 44; ++i) loc[i] = 0.0;
+    for (i64 t = tid; t < T; t += 256) {
+      double gl[LP];
+      const double r = h0[t] - smu;
+#pragma unroll
+      for (int l = 0; l < LP; ++l) gl[l] = l < L ? px[t * LP + l] - smw[l] - r * wbar[l] : 0.0;
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < LP; ++a)
+#pragma unroll
+        for (int c = a; c < LP; ++c) loc[q++] += gl[a] * gl[c];
+      const double yt = y[t * g.y_s];
+#pragma unroll
+      for (int l = 0; l < LP; ++l) loc[36 + l] += gl[l] * yt;
+    }
+    block_sum<44>(loc, red, tot, tid);
+    if (tid == 0) {
+      double core[LP * LP], inv[LP * LP], rhs[LP];
+      int q = 0;
+      double full[LP][LP];
+      for (int a = 0; a < LP; ++a)
+        for (int c = a; c < LP; ++c) { full[a][c] = tot[q]; full[c][a] = tot[q]; ++q; }
+      for (int a = 0; a < L; ++a) {
+        for (int c = 0; c < L; ++c) core[a * L + c] = full[a][c];
+        rhs[a] = tot[36 + a];
+      }
+      bool ok = lu_inverse_seq(core, L, inv);
+      if (!ok) singular_s = 1;
+      for (int a = 0; a < LP; ++a) {
+        double s = 0.0;
+        if (ok && a < L)
+          for (int c = 0; c < L; ++c) s += inv[a * L + c] * rhs[c];
+        s_cl[a] = ok ? s : nan("");
+        if (a >= L) s_cl[a] = 0.0;
+      }
+    }
+    __syncthreads();
+    if (g.mode == UM_TPRF_CLOSED) {
+      double see = 0.0;
+      for (i64 t = tid; t < T; t += 256) {
+        const double r = h0[t] - smu;
+        double f = 0.0;
+#pragma unroll
+        for (int l = 0; l < LP; ++l)
+          if (l < L) f += (px[t * LP + l] - smw[l] - r * wbar[l]) * s_cl[l];
+        f += ybar;
+        const double e = y[t * g.y_s] - f;
+        if (fc) fc[t] = f;
+        if (rs) rs[t] = e;
+        see += e * e;
+      }
+      double l1[1] = {see};
+      block_sum<1>(l1, red, tot, tid);
+      r2 = ssy == 0.0 ? 0.0 : 1.0 - tot[0] / ssy;  // Tprf3.scala:239-241
+    }
+  }
+
+  if (g.mode != UM_TPRF_CLOSED) {
+    // ---- three-pass fit from the same accumulators ----
+    if (tid == 0) {
+      double szz[LP * LP], tmp[LP * LP];
+      for (int a = 0; a < L; ++a)
+        for (int c = 0; c < L; ++c) szz[a * L + c] = small[8 + a * LP + c];
+      bool ok = lu_inverse_seq(szz, L, tmp);
+      if (!ok) singular_s = 1;
+      for (int a = 0; a < LP; ++a)
+        for (int c = 0; c < LP; ++c) szzinv[a * LP + c] = (ok && a < L && c < L) ? tmp[a * L + c] : (ok ? 0.0 : nan(""));
+      // [1|Phi]'[1|Phi] with Phi = W0 Szz^-1  (Tprf3.scala:265-266)
+      double phisum[LP], sww_i[LP * LP], pp[LP * LP];
+      for (int a = 0; a < L; ++a) {
+        double s = 0.0;
+        for (int c = 0; c < L; ++c) s += szzinv[a * LP + c] * sw[c];
+        phisum[a] = s;
+      }
+      for (int a = 0; a < L; ++a)      // sww_i = Szz^-1 * SWW
+        for (int c = 0; c < L; ++c) {
+          double s = 0.0;
+          for (int k = 0; k < L; ++k) s += szzinv[a * LP + k] * sm[8 + k * LP + c];
+          sww_i[a * L + c] = s;
+        }
+      for (int a = 0; a < L; ++a)      // pp = sww_i * Szz^-1' (Szz^-1 symmetric up to rounding)
+        for (int c = 0; c < L; ++c) {
+          double s = 0.0;
+          for (int k = 0; k < L; ++k) s += sww_i[a * L + k] * szzinv[c * LP + k];
+          pp[a * L + c] = s;
+        }
+      double ptp[(LP + 1) * (LP + 1)], ptpinv[(LP + 1) * (LP + 1)];
+      ptp[0] = g.n_total;
+      for (int a = 0; a < L; ++a) {
+        ptp[0 * L1 + 1 + a] = phisum[a];
+        ptp[(1 + a) * L1 + 0] = phisum[a];
+        for (int c = 0; c < L; ++c) ptp[(1 + a) * L1 + 1 + c] = 0.5 * (pp[a * L + c] + pp[c * L + a]);
+      }
+      bool ok2 = lu_inverse_seq(ptp, L1, ptpinv);
+      if (!ok2) singular_s = 1;
+      // Sigma[t][l] = sum_m XP[t][m] PtPinv[1+l][m],  XP[t][0] = h0[t],  XP[t][1+a] = sum_c PX[t][c] szzinv[c][a]
+      // fold into m2: Sigma[t][l] = m2[0][l] h0[t] + sum_c m2[1+c][l] PX[t][c]
+      for (int l = 0; l < LP; ++l) {
+        m2[0 * LP + l] = (l < L) ? (ok2 ? ptpinv[(1 + l) * L1 + 0] : nan("")) : 0.0;
+        for (int c = 0; c < LP; ++c) {
+          double s = 0.0;
+          if (l < L && c < L)
+            for (int a = 0; a < L; ++a) s += szzinv[c * LP + a] * ptpinv[(1 + l) * L1 + 1 + a];
+          m2[(1 + c) * LP + l] = (ok2 || !(l < L && c < L)) ? s : nan("");
+        }
+      }
+    }
+    __syncthreads();
+    double loc[54];
+#pragma unroll
+    for (int i = 0; i < 54; ++i) loc[i] = 0.0;
+    for (i64 t = tid; t < T; t += 256) {
+      double d[LP + 1];
+      d[0] = 1.0;
+      const double h = h0[t];
+      double pxr[LP];
+#pragma unroll
+      for (int c = 0; c < LP; ++c) pxr[c] = px[t * LP + c];
+#pragma unroll
+      for (int l = 0; l < LP; ++l) {
+        double s = m2[l] * h;
+#pragma unroll
+        for (int c = 0; c < LP; ++c) s += m2[(1 + c) * LP + l] * pxr[c];
+        d[1 + l] = l < L ? s : 0.0;
+        sig_ws[t * LP + l] = d[1 + l];
+      }
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a <= LP; ++a)
+#pragma unroll
+        for (int c = a; c <= LP; ++c) loc[q++] += d[a] * d[c];
+      const double yt = y[t * g.y_s];
+#pragma unroll
+      for (int a = 0; a <= LP; ++a) loc[45 + a] += d[a] * yt;
+    }
+    block_sum<54>(loc, red, tot, tid);
+    if (tid == 0) {
+      double full[LP + 1][LP + 1];
+      int q = 0;
+      for (int a = 0; a <= LP; ++a)
+        for (int c = a; c <= LP; ++c) { full[a][c] = tot[q]; full[c][a] = tot[q]; ++q; }
+      double A[(LP + 1) * (LP + 1)], Ai[(LP + 1) * (LP + 1)];
+      for (int a = 0; a < L1; ++a)
+        for (int c = 0; c < L1; ++c) A[a * L1 + c] = full[a][c];
+      bool ok = lu_inverse_seq(A, L1, Ai);
+      if (!ok) singular_s = 1;
+      for (int a = 0; a <= LP; ++a) {
+        double s = 0.0;
+        if (a < L1)
+          for (int c = 0; c < L1; ++c) s += Ai[a * L1 + c] * tot[45 + c];
+        beta[a] = a < L1 ? (ok ? s : nan("")) : 0.0;
+      }
+    }
+    __syncthreads();
+    double see = 0.0;
+    for (i64 t = tid; t < T; t += 256) {
+      double f = beta[0];
+#pragma unroll
+      for (int l = 0; l < LP; ++l) f += sig_ws[t * LP + l] * beta[1 + l];
+      const double e = y[t * g.y_s] - f;
+      if (fc) fc[t] = f;
+      if (rs) rs[t] = e;
+      see += e * e;
+      if (g.sigma)
+        for (int l = 0; l < L; ++l) g.sigma[(b * T + t) * L + l] = sig_ws[t * LP + l];
+    }
+    double l1[1] = {see};
+    block_sum<1>(l1, red, tot, tid);
+    if (g.mode == UM_TPRF_ITER) r2 = ssy == 0.0 ? 0.0 : 1.0 - tot[0] / ssy;  // Tprf3.scala:274-275
+    else r2 = 1.0 - tot[0] / ssy;                                             // Tprf3.scala:1214-1225
+    if (g.beta3 && tid < L1) g.beta3[b * L1 + tid] = beta[tid];
+  }
+  __syncthreads();
+  if (tid < LP) {
+    par[tid] = s_cl[tid];
+    par[8 + tid] = wbar[tid];
+    par[80 + tid] = small[tid];
+  }
+  if (tid < LP * LP) par[16 + tid] = (g.mode != UM_TPRF_CLOSED) ? szzinv[tid] : 0.0;
+  if (tid == 0) {
+    par[88] = r2;
+    par[89] = (double)singular_s;
+    if (g.r2_out) g.r2_out[b] = r2;
+  }
+}
+
+// ---- per-column outputs ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_tprf_outputs(const double* __restrict__ w0, const double* __restrict__ invsd, const double* __restrict__ mun,
+               const double* __restrict__ params, i64 N, i64 npad, int L, int mode, double* __restrict__ alpha,
+               double* __restrict__ phi, double* __restrict__ phi_hat, double* __restrict__ xstd, i64 out_bs) {
+  __shared__ double par[PARAMS];
+  const i64 b = blockIdx.z;
+  if (threadIdx.x < PARAMS) par[threadIdx.x] = params[b * PARAMS + threadIdx.x];
+  __syncthreads();
+  const double* s = par;
+  const double* wbar = par + 8;
+  const double* szzinv = par + 16;
+  const double* zbar = par + 80;
+  for (i64 j = (i64)blockIdx.x * 256 + threadIdx.x; j < N; j += (i64)gridDim.x * 256) {
+    const i64 cidx = b * npad + j;
+    double w[LP];
+#pragma unroll
+    for (int l = 0; l < LP; ++l) w[l] = w0[cidx * LP + l];
+    if (alpha) {
+      double a = 0.0;
+#pragma unroll
+      for (int l = 0; l < LP; ++l)
+        if (l < L) a += (w[l] - wbar[l]) * s[l];
+      alpha[b * out_bs + j] = a;
+    }
+    if (xstd) xstd[b * out_bs + j] = 1.0 / invsd[cidx];
+    if (phi || phi_hat) {
+      double icpt = mun[cidx];
+      for (int l = 0; l < L; ++l) {
+        double p = 0.0;
+        for (int c = 0; c < L; ++c) p += szzinv[l * LP + c] * w[c];
+        if (phi) phi[(b * out_bs + j) * L + l] = p;
+        if (phi_hat) phi_hat[b * out_bs * (L + 1) + (i64)(1 + l) * N + j] = p;
+        icpt -= zbar[l] * p;
+      }
+      if (phi_hat) phi_hat[b * out_bs * (L + 1) + j] = icpt;
+    }
+  }
+}
+
+__global__ void k_fill_nan(double* p, i64 n) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = nan("");
+}
+
+// ---- host orchestration ------------------------------------------------------------------------------------------
+static i64 cdiv(i64 a, i64 b) { return (a + b - 1) / b; }
+static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct Plan3 {
+  i64 T, N, L, batch;
+  i64 strips, npad, rchunks, rows_per_chunk;     // sweep 1
+  i64 rblocks, tpad, cchunks, cols_per_chunk;    // sweep 2
+  int cf_blocks;                                 // colfinal blocks per panel
+  // workspace offsets (bytes)
+  size_t o_zc, o_small, o_qp, o_s1, o_s2, o_w0, o_v, o_invsd, o_mun, o_bp, o_pxp, o_h0p, o_packed, o_sig, o_par, total;
+  i64 packed_len;
+};
+
+static Plan3 make_plan(i64 T, i64 N, i64 L, i64 batch, int sms) {
+  Plan3 p;
+  p.T = T; p.N = N; p.L = L; p.batch = batch;
+  const i64 target = (i64)sms * 16;
+  p.strips = cdiv(N, C1_COLS);
+  p.npad = p.strips * C1_COLS;
+  i64 rc = 1;
+  if (p.strips * batch < target) {
+    rc = cdiv(target, p.strips * batch);
+    i64 maxc = cdiv(T, 4 * C1_ROWS);
+    if (rc > maxc) rc = maxc;
+    if (rc < 1) rc = 1;
+  }
+  p.rows_per_chunk = cdiv(cdiv(T, rc), C1_ROWS) * C1_ROWS;
+  p.rchunks = cdiv(T, p.rows_per_chunk);
+  p.rblocks = cdiv(T, C2_ROWS);
+  p.tpad = p.rblocks * C2_ROWS;
+  i64 cc = 1;
+  if (p.rblocks * batch < target) {
+    cc = cdiv(target, p.rblocks * batch);
+    i64 maxc = cdiv(p.npad, 4 * C2_COLS);
+    if (cc > maxc) cc = maxc;
+    if (cc < 1) cc = 1;
+  }
+  p.cols_per_chunk = cdiv(cdiv(p.npad, cc), C2_COLS) * C2_COLS;
+  p.cchunks = cdiv(p.npad, p.cols_per_chunk);
+  i64 cfb = cdiv(N, 256 * 4);
+  if (cfb > 1024) cfb = 1024;
+  if (cfb < 1) cfb = 1;
+  p.cf_blocks = (int)cfb;
+  p.packed_len = T * (LP + 1) + NSMALL;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += al(bytes); return at; };
+  p.o_zc = take((size_t)batch * T * LP * 8);
+  p.o_small = take((size_t)batch * SMALL_PREP * 8);
+  p.o_qp = take((size_t)batch * p.rchunks * p.npad * LP * 8);
+  p.o_s1 = take((size_t)batch * p.rchunks * p.npad * 8);
+  p.o_s2 = take((size_t)batch * p.rchunks * p.npad * 8);
+  p.o_w0 = take((size_t)batch * p.npad * LP * 8);
+  p.o_v = take((size_t)batch * p.npad * LP * 8);
+  p.o_invsd = take((size_t)batch * p.npad * 8);
+  p.o_mun = take((size_t)batch * p.npad * 8);
+  p.o_bp = take((size_t)batch * p.cf_blocks * NSMALL * 8);
+  p.o_pxp = take((size_t)batch * p.cchunks * p.tpad * LP * 8);
+  p.o_h0p = take((size_t)batch * p.cchunks * p.tpad * 8);
+  p.o_packed = take((size_t)batch * p.packed_len * 8);
+  p.o_sig = take((size_t)batch * T * LP * 8);
+  p.o_par = take((size_t)batch * PARAMS * 8);
+  p.total = o;
+  return p;
+}
+
+static int set_smem_attrs() {
+  static bool done = false;
+  if (done) return UM_OK;
+  UM_CUDA(cudaFuncSetAttribute(k_tprf_colstats<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
+  UM_CUDA(cudaFuncSetAttribute(k_tprf_colstats<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
+  UM_CUDA(cudaFuncSetAttribute(k_tprf_project<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM));
+  UM_CUDA(cudaFuncSetAttribute(k_tprf_project<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM));
+  done = true;
+  return UM_OK;
+}
+
+// sweeps over one resident X block (T x N, row pitch ldx), writing / accumulating the packed buffer.
+// `ws` is the carved workspace; prep must already have run.
+static int run_sweeps(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_bs, int accumulate) {
+  cudaStream_t st = ctx()->stream;
+  double* zc = reinterpret_cast<double*>(ws + p.o_zc);
+  double* qp = reinterpret_cast<double*>(ws + p.o_qp);
+  double* s1 = reinterpret_cast<double*>(ws + p.o_s1);
+  double* s2 = reinterpret_cast<double*>(ws + p.o_s2);
+  double* w0 = reinterpret_cast<double*>(ws + p.o_w0);
+  double* v = reinterpret_cast<double*>(ws + p.o_v);
+  double* invsd = reinterpret_cast<double*>(ws + p.o_invsd);
+  double* mun = reinterpret_cast<double*>(ws + p.o_mun);
+  double* bp = reinterpret_cast<double*>(ws + p.o_bp);
+  double* pxp = reinterpret_cast<double*>(ws + p.o_pxp);
+  double* h0p = reinterpret_cast<double*>(ws + p.o_h0p);
+  double* packed = reinterpret_cast<double*>(ws + p.o_packed);
+  const bool vec16 = aligned16(X) && (ldx % 2 == 0) && (x_bs % 2 == 0);
+  {
+    dim3 grid((unsigned)p.strips, (unsigned)p.rchunks, (unsigned)p.batch);
+    prof_begin(0);
+    if (vec16) k_tprf_colstats<true><<<grid, C1_THREADS, C1_SMEM, st>>>(X, ldx, x_bs, zc, p.T, p.N, p.npad, p.rows_per_chunk, qp, s1, s2);
+    else k_tprf_colstats<false><<<grid, C1_THREADS, C1_SMEM, st>>>(X, ldx, x_bs, zc, p.T, p.N, p.npad, p.rows_per_chunk, qp, s1, s2);
+    prof_end(0);
+    UM_LAUNCHED();
+  }
+  {
+    dim3 grid((unsigned)p.cf_blocks, 1, (unsigned)p.batch);
+    prof_begin(1);
+    k_tprf_colfinal<<<grid, 256, 0, st>>>(X, x_bs, qp, s1, s2, (int)p.rchunks, p.T, p.N, p.npad, w0, v, invsd, mun, bp);
+    prof_end(1);
+    UM_LAUNCHED();
+  }
+  {
+    dim3 grid((unsigned)p.rblocks, (unsigned)p.cchunks, (unsigned)p.batch);
+    prof_begin(2);
+    if (vec16) k_tprf_project<true><<<grid, C2_THREADS, C2_SMEM, st>>>(X, ldx, x_bs, v, invsd, p.T, p.N, p.npad, p.cols_per_chunk, p.tpad, pxp, h0p);
+    else k_tprf_project<false><<<grid, C2_THREADS, C2_SMEM, st>>>(X, ldx, x_bs, v, invsd, p.T, p.N, p.npad, p.cols_per_chunk, p.tpad, pxp, h0p);
+    prof_end(2);
+    UM_LAUNCHED();
+  }
+  {
+    i64 gx = cdiv(p.packed_len, 256);
+    if (gx > 1024) gx = 1024;
+    dim3 grid((unsigned)gx, 1, (unsigned)p.batch);
+    prof_begin(3);
+    k_tprf_gather<<<grid, 256, 0, st>>>(pxp, h0p, (int)p.cchunks, p.T, p.tpad, bp, p.cf_blocks, packed, p.packed_len, accumulate);
+    prof_end(3);
+    UM_LAUNCHED();
+  }
+  return UM_OK;
+}
+
+static int run_prep(const Plan3& p, char* ws, const double* Z, i64 z_rs, i64 z_cs, i64 z_bs, const double* y, i64 y_s,
+                    i64 y_bs) {
+  dim3 grid(1, 1, (unsigned)p.batch);
+    prof_begin(7);
+  k_tprf_prep<<<grid, 256, 0, ctx()->stream>>>(Z, z_rs, z_cs, z_bs, y, y_s, y_bs, p.T, (int)p.L,
+                                                reinterpret_cast<double*>(ws + p.o_zc),
+                                                reinterpret_cast<double*>(ws + p.o_small));
+  prof_end(7);
+    UM_LAUNCHED();
+  return UM_OK;
+}
+
+static int run_finish(const Plan3& p, char* ws, int mode, const double* y, i64 y_s, i64 y_bs, double n_total,
+                      double* forecasts, double* residuals, i64 f_bs, double* sigma, double* beta3, double* r2_dev) {
+  FinishArgs g;
+  g.packed = reinterpret_cast<double*>(ws + p.o_packed);
+  g.packed_stride = p.packed_len;
+  g.small = reinterpret_cast<double*>(ws + p.o_small);
+  g.y = y; g.y_s = y_s; g.y_bs = y_bs;
+  g.T = p.T; g.L = (int)p.L; g.n_total = n_total; g.mode = mode;
+  g.forecasts = forecasts; g.residuals = residuals; g.f_bs = f_bs;
+  g.sigma = sigma; g.beta3 = beta3;
+  g.sigma_ws = reinterpret_cast<double*>(ws + p.o_sig);
+  g.params = reinterpret_cast<double*>(ws + p.o_par);
+  g.r2_out = r2_dev;
+    prof_begin(4);
+  k_tprf_finish<<<(unsigned)p.batch, 256, 0, ctx()->stream>>>(g);
+  prof_end(4);
+    UM_LAUNCHED();
+  return UM_OK;
+}
+
+static int run_outputs(const Plan3& p, char* ws, int mode, double* alpha, double* phi, double* phi_hat, double* xstd,
+                       i64 out_bs) {
+  if (!alpha && !phi && !phi_hat && !xstd) return UM_OK;
+  i64 gx = cdiv(p.N, 256);
+  if (gx > 2048) gx = 2048;
+  dim3 grid((unsigned)gx, 1, (unsigned)p.batch);
+    prof_begin(5);
+  k_tprf_outputs<<<grid, 256, 0, ctx()->stream>>>(reinterpret_cast<double*>(ws + p.o_w0), reinterpret_cast<double*>(ws + p.o_invsd),
+                                                   reinterpret_cast<double*>(ws + p.o_mun), reinterpret_cast<double*>(ws + p.o_par),
+                                                   p.N, p.npad, (int)p.L, mode, alpha, phi, phi_hat, xstd, out_bs);
+  prof_end(5);
+    UM_LAUNCHED();
+  return UM_OK;
+}
+
+static int fill_nan(double* p, i64 n) {
+  if (!p || n == 0) return UM_OK;
+  k_fill_nan<<<(unsigned)cdiv(n, 256), 256, 0, ctx()->stream>>>(p, n);
+  UM_LAUNCHED();
+  return UM_OK;
+}
+
+}  // namespace um
+
+using namespace um;
+
+extern "C" {
+
+int32_t um_tprf_work(int64_t T, int64_t N, int64_t L, double* flops, double* bytes) {
+  // X'[Z] 2TNL, Xc W0 2TNL, row sums + stats ~6TN -> T*N*(4L+6); X read once = 8TN bytes
+  if (flops) *flops = (double)T * (double)N * (4.0 * (double)L + 6.0);
+  if (bytes) *bytes = 8.0 * (double)T * (double)N;
+  return UM_OK;
+}
+
+int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_view* Z, int64_t n_total, um_tprf_out* out) {
+  UM_CTX();
+  UM_VIEW(y); UM_VIEW(X); UM_VIEW(Z);
+  if (!out) return fail(UM_ERR_ARG, "null out");
+  UM_REQUIRE(mode >= UM_TPRF_CLOSED && mode <= UM_TPRF_IS_FULL, "unknown 3PRF mode %d", mode);
+  UM_REQUIRE(X->dtype == UM_F64 && y->dtype == UM_F64 && Z->dtype == UM_F64, "3PRF needs f64 inputs");
+  const i64 T = X->rows, N = X->cols, L = Z->cols;
+  UM_REQUIRE(y->rows == T && y->cols == 1, "y must be %lld x 1, got %lldx%lld", T, (i64)y->rows, (i64)y->cols);
+  UM_REQUIRE(Z->rows == T, "Z must have %lld rows, got %lld", T, (i64)Z->rows);
+  UM_REQUIRE(L >= 1 && L <= LP, "number of proxies L = %lld outside [1, %d]", L, LP);
+  UM_REQUIRE(T >= 1 && N >= 1, "empty panel");
+  UM_REQUIRE(X->cs == 1 || N == 1, "X must be row-contiguous (cs == 1); materialise the view first");
+  if (n_total <= 0) n_total = N;
+  out->r_squared = nan("");
+  out->singular = 0;
+  if (mode == UM_TPRF_IS_FULL && T < 10) {
+    // T < minObs => all-NaN forecasts (Tprf3.scala:893-894)
+    int s = fill_nan(out->forecasts, T);
+    if (s == UM_OK) s = fill_nan(out->residuals, T);
+    if (s != UM_OK) return s;
+    UM_CUDA(cudaStreamSynchronize(ctx()->stream));
+    return UM_OK;
+  }
+  Plan3 p = make_plan(T, N, L, 1, ctx()->sm_count);
+  char* ws = static_cast<char*>(scratch(p.total));
+  if (!ws) return UM_ERR_OOM;
+  int s = set_smem_attrs();
+  if (s != UM_OK) return s;
+  const double* yp = static_cast<const double*>(y->data) + y->offset;
+  const double* zp = static_cast<const double*>(Z->data) + Z->offset;
+  const double* xp = static_cast<const double*>(X->data) + X->offset;
+  s = run_prep(p, ws, zp, Z->rs, Z->cs, 0, yp, y->rs, 0);
+  if (s != UM_OK) return s;
+  s = run_sweeps(p, ws, xp, N == 1 ? 1 : X->rs, 0, 0);
+  if (s != UM_OK) return s;
+  if (comm_active() && comm_world() > 1) {
+    prof_begin(6);
+    s = comm_allreduce_sum_f64_impl(reinterpret_cast<double*>(ws + p.o_packed), p.packed_len);
+    prof_end(6);
+    if (s != UM_OK) return s;
+  }
+  s = run_finish(p, ws, mode, yp, y->rs, 0, (double)n_total, out->forecasts, out->residuals, 0, out->sigma, out->beta3, nullptr);
+  if (s != UM_OK) return s;
+  s = run_outputs(p, ws, mode, out->alpha, out->phi, out->phi_hat, out->xstd, N);
+  if (s != UM_OK) return s;
+  double res[2];
+  UM_CUDA(cudaMemcpyAsync(res, reinterpret_cast<double*>(ws + p.o_par) + 88, 16, cudaMemcpyDeviceToHost, ctx()->stream));
+  UM_CUDA(cudaStreamSynchronize(ctx()->stream));
+  out->r_squared = res[0];
+  out->singular = res[1] != 0.0;
+  return UM_OK;
+}
+
+int32_t um_tprf_fit_batched(int32_t mode, const double* y, const double* X, const double* Z, int64_t T, int64_t N, int64_t L,
+                            int64_t batch, double* forecasts, double* alpha, double* r2) {
+  UM_CTX();
+  UM_REQUIRE(mode >= UM_TPRF_CLOSED && mode <= UM_TPRF_IS_FULL, "unknown 3PRF mode %d", mode);
+  UM_REQUIRE(y && X && Z, "null input");
+  UM_REQUIRE(L >= 1 && L <= LP, "number of proxies L = %lld outside [1, %d]", (i64)L, LP);
+  UM_REQUIRE(T >= 1 && N >= 1 && batch >= 0, "bad panel shape");
+  UM_REQUIRE(batch <= 65535, "batch %lld > 65535: split the call", (i64)batch);
+  if (batch == 0) return UM_OK;
+  Plan3 p = make_plan(T, N, L, batch, ctx()->sm_count);
+  char* ws = static_cast<char*>(scratch(p.total));
+  if (!ws) return UM_ERR_OOM;
+  int s = set_smem_attrs();
+  if (s != UM_OK) return s;
+  s = run_prep(p, ws, Z, L, 1, T * L, y, 1, T);
+  if (s != UM_OK) return s;
+  s = run_sweeps(p, ws, X, N, T * N, 0);
+  if (s != UM_OK) return s;
+  s = run_finish(p, ws, mode, y, 1, T, (double)N, forecasts, nullptr, T, nullptr, nullptr, r2);
+  if (s != UM_OK) return s;
+  return run_outputs(p, ws, mode, alpha, nullptr, nullptr, nullptr, N);
+}
+
+int32_t um_tprf_fit_host(int32_t mode, const double* y, const double* X, int64_t ldx, const double* Z, int64_t T,
+                         int64_t N_local, int64_t L, int64_t n_total, double* forecasts_host, double* alpha_host,
+                         double* r_squared) {
+  UM_CTX();
+  UM_REQUIRE(mode >= UM_TPRF_CLOSED && mode <= UM_TPRF_IS_FULL, "unknown 3PRF mode %d", mode);
+  UM_REQUIRE(y && X && Z, "null input");
+  UM_REQUIRE(L >= 1 && L <= LP, "number of proxies L = %lld outside [1, %d]", (i64)L, LP);
+  UM_REQUIRE(T >= 1 && N_local >= 1 && ldx >= N_local, "bad panel shape");
+  if (n_total <= 0) n_total = N_local;
+  Ctx& c = *ctx();
+  // column blocks of CB columns are staged through two device buffers: H2D of block k+1 (copy
+  // stream) overlaps the two sweeps of block k (compute stream).
+  i64 CB = 8192;
+  if (CB > N_local) CB = cdiv(N_local, 2) * 2;
+  const i64 nblocks = cdiv(N_local, CB);
+  Plan3 p = make_plan(T, CB, L, 1, c.sm_count);
+  const size_t stage_bytes = al((size_t)T * CB * 8);
+  const size_t w0_all = al((size_t)N_local * LP * 8);  // keep every block's W0 for alpha
+  const size_t yz_bytes = al((size_t)T * (L + 1) * 8) + al((size_t)T * 8);
+  char* base = static_cast<char*>(scratch(p.total + 2 * stage_bytes + w0_all + yz_bytes + al((size_t)N_local * 8)));
+  if (!base) return UM_ERR_OOM;
+  char* ws = base;
+  double* stage_buf[2] = {reinterpret_cast<double*>(base + p.total), reinterpret_cast<double*>(base + p.total + stage_bytes)};
+  double* w0_keep = reinterpret_cast<double*>(base + p.total + 2 * stage_bytes);
+  double* dz = reinterpret_cast<double*>(base + p.total + 2 * stage_bytes + w0_all);
+  double* dy = dz + T * L;
+  double* dfc = reinterpret_cast<double*>(base + p.total + 2 * stage_bytes + w0_all + al((size_t)T * (L + 1) * 8));
+  double* dalpha = reinterpret_cast<double*>(base + p.total + 2 * stage_bytes + w0_all + yz_bytes);
+  int s = set_smem_attrs();
+  if (s != UM_OK) return s;
+  static thread_local cudaStream_t copy_st = nullptr;
+  static thread_local cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  if (!copy_st) {
+    UM_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      UM_CUDA(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+      UM_CUDA(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t st = c.stream;
+  UM_CUDA(cudaMemcpyAsync(dz, Z, (size_t)T * L * 8, cudaMemcpyHostToDevice, st));
+  UM_CUDA(cudaMemcpyAsync(dy, y, (size_t)T * 8, cudaMemcpyHostToDevice, st));
+  s = run_prep(p, ws, dz, L, 1, 0, dy, 1, 0);
+  if (s != UM_OK) return s;
+  UM_CUDA(cudaEventRecord(ev_free[0], st));
+  UM_CUDA(cudaEventRecord(ev_free[1], st));
+  for (i64 k = 0; k < nblocks; ++k) {
+    const int bsel = (int)(k & 1);
+    const i64 c0 = k * CB;
+    const i64 w = (c0 + CB <= N_local) ? CB : (N_local - c0);
+    UM_CUDA(cudaStreamWaitEvent(copy_st, ev_free[bsel], 0));
+    UM_CUDA(cudaMemcpy2DAsync(stage_buf[bsel], (size_t)CB * 8, X + c0, (size_t)ldx * 8, (size_t)w * 8, (size_t)T,
+                              cudaMemcpyHostToDevice, copy_st));
+    UM_CUDA(cudaEventRecord(ev_copied[bsel], copy_st));
+    UM_CUDA(cudaStreamWaitEvent(st, ev_copied[bsel], 0));
+    Plan3 pb = p;
+    pb.N = w;  // narrower last block; strides / padding stay those of the CB plan
+    s = run_sweeps(pb, ws, stage_buf[bsel], CB, 0, k > 0);
+    if (s != UM_OK) return s;
+    UM_CUDA(cudaMemcpyAsync(w0_keep + c0 * LP, ws + p.o_w0, (size_t)w * LP * 8, cudaMemcpyDeviceToDevice, st));
+    UM_CUDA(cudaEventRecord(ev_free[bsel], st));
+  }
+  if (comm_active() && comm_world() > 1) {
+    s = comm_allreduce_sum_f64_impl(reinterpret_cast<double*>(ws + p.o_packed), p.packed_len);
+    if (s != UM_OK) return s;
+  }
+  s = run_finish(p, ws, mode, dy, 1, 0, (double)n_total, dfc, nullptr, 0, nullptr, nullptr, nullptr);
+  if (s != UM_OK) return s;
+  if (alpha_host) {
+    i64 gx = cdiv(N_local, 256);
+    if (gx > 2048) gx = 2048;
+    k_tprf_outputs<<<dim3((unsigned)gx, 1, 1), 256, 0, st>>>(w0_keep, nullptr, nullptr, reinterpret_cast<double*>(ws + p.o_par),
+                                                              N_local, N_local, (int)L, mode, dalpha, nullptr, nullptr, nullptr, N_local);
+    UM_LAUNCHED();
+    UM_CUDA(cudaMemcpyAsync(alpha_host, dalpha, (size_t)N_local * 8, cudaMemcpyDeviceToHost, st));
+  }
+  if (forecasts_host) UM_CUDA(cudaMemcpyAsync(forecasts_host, dfc, (size_t)T * 8, cudaMemcpyDeviceToHost, st));
+  double res[2];
+  UM_CUDA(cudaMemcpyAsync(res, reinterpret_cast<double*>(ws + p.o_par) + 88, 16, cudaMemcpyDeviceToHost, st));
+  UM_CUDA(cudaStreamSynchronize(st));
+  if (r_squared) *r_squared = res[0];
+  return UM_OK;
+}
+
+}  // extern "C"
