@@ -315,6 +315,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end through the C-ABI host entry point (pinned host panel, H2D inside the timed region)
     e2e = None
     try:
+        if args.no_e2e:
+            raise RuntimeError("skipped by --no-e2e (profiling run)")
         nbytes = T * Nl * 8
         hx = C.c_void_p()
         check(lib.um_malloc_host(nbytes, C.byref(hx)))
@@ -384,6 +386,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-ops", action="store_true", help="skip the config-2/3 extras (MatD ops, matmul sweep)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-streamed end-to-end leg (ncu runs)")
     ap.add_argument("--small", action="store_true", help="debug: T=2048 x N=16384 panel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

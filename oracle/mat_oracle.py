@@ -145,12 +145,12 @@ def fnv_words(words) -> int:
 
 
 def fnv(xs) -> int:
-    return fnv_words(np.ascontiguousarray(xs, dtype=np.float64).view(np.uint64).tolist())
+    return fnv_words(np.ascontiguousarray(xs, dtype=np.float64).reshape(-1).view(np.uint64).tolist())
 
 
 def fnv_f32(xs) -> int:
     """fnvF: one word per float, the raw 32 bits zero-extended (MatParityGen fnvF)."""
-    return fnv_words(np.ascontiguousarray(xs, dtype=np.float32).view(np.uint32).astype(np.uint64).tolist())
+    return fnv_words(np.ascontiguousarray(xs, dtype=np.float32).reshape(-1).view(np.uint32).astype(np.uint64).tolist())
 
 
 def fnv_mask(mask) -> int:

@@ -86,7 +86,7 @@ def test_python_reference_vectors(u, golden_dir):
         assert abs(r.rSquared - float(g["rsquare"])) < 1e-10, f
 
 
-SHAPES = [(10, 1, 1), (33, 7, 1), (50, 6, 2), (100, 64, 3), (127, 65, 2), (129, 200, 8), (512, 2048, 4), (300, 1000, 5), (1000, 130, 7)]
+SHAPES = [(10, 3, 1), (33, 7, 1), (50, 6, 2), (100, 64, 3), (127, 65, 2), (129, 200, 8), (512, 2048, 4), (300, 1000, 5), (1000, 130, 7)]
 
 
 @pytest.mark.parametrize("tnl", SHAPES)
