@@ -1,0 +1,121 @@
+// DeviceMat.scala -- device-resident backing for `Mat[Double]` / `Mat[Float]`: the Scala twin of
+// uni_b200/mat.py.  NOT compiled in the build image (no JVM).  It carries the reference's
+// descriptor (Mat.scala:125-133) next to a device pointer, so `T`, `slice`, `broadcastTo` stay
+// zero-copy, and forwards each operator of SURVEY.md section 8a to one libunimat call.
+package uni.cuda
+
+import java.lang.foreign.*
+import java.lang.foreign.ValueLayout.*
+import java.lang.ref.Cleaner
+import UniMatLib.*
+
+/** One device allocation, freed by a Cleaner when the last view dies (views retain their parent). */
+final class DeviceBuffer(val ptr: MemorySegment, val bytes: Long):
+  DeviceBuffer.cleaner.register(this, DeviceBuffer.Free(ptr))
+object DeviceBuffer:
+  private val cleaner = Cleaner.create()
+  private final class Free(p: MemorySegment) extends Runnable:
+    def run(): Unit = um_free.invoke(p)
+  def alloc(bytes: Long): DeviceBuffer =
+    val out = Arena.global().allocate(ADDRESS)
+    check(um_malloc.invoke(math.max(bytes, 1L), out).asInstanceOf[Int])
+    DeviceBuffer(out.get(ADDRESS, 0), bytes)
+
+enum DType(val code: Int, val size: Int):
+  case F64 extends DType(0, 8); case F32 extends DType(1, 4); case Bool extends DType(2, 1); case I32 extends DType(3, 4)
+
+/** `MatData` on the device.  `view` is a 56-byte `um_view` segment owned by this object. */
+final class DeviceMat private (val buf: DeviceBuffer, val view: MemorySegment, val dtype: DType):
+  private inline def L(name: String) = view.get(JAVA_LONG, VIEW.byteOffset(MemoryLayout.PathElement.groupElement(name)))
+  def rows: Int = L("rows").toInt
+  def cols: Int = L("cols").toInt
+  def rs: Long  = L("rs")
+  def cs: Long  = L("cs")
+
+  private def like(r: Long, c: Long, dt: DType = dtype): DeviceMat = DeviceMat.alloc(r, c, dt)
+  private def derived(f: MemorySegment => Int): DeviceMat =
+    val v = Arena.ofAuto().allocate(VIEW); check(f(v)); DeviceMat(buf, v, dtype)
+
+  // ---- views: Mat.scala:198-199 (transposeView), :1905-1927 (slice), :1933-1953 (broadcastTo)
+  def T: DeviceMat = derived(v => um_view_transpose.invoke(view, v).asInstanceOf[Int])
+  def slice(r0: Int, r1: Int, c0: Int, c1: Int): DeviceMat =
+    val need = Arena.ofAuto().allocate(JAVA_INT)
+    val s = derived(v => um_view_slice.invoke(view, r0.toLong, r1.toLong, c0.toLong, c1.toLong, v, need).asInstanceOf[Int])
+    if need.get(JAVA_INT, 0) != 0 then s.matCopy else s      // Internal.create's layout guard (Mat.scala:1865-1876)
+  def broadcastTo(r: Int, c: Int): DeviceMat = derived(v => um_view_broadcast.invoke(view, r.toLong, c.toLong, v).asInstanceOf[Int])
+  def matCopy: DeviceMat = { val o = like(rows, cols); check(um_copy.invoke(view, o.view).asInstanceOf[Int]); o }
+
+  // ---- elementwise (Mat.scala:1989-2102, 2154-2209, 2514-2531, 4513-4588)
+  private def bin(op: Int, b: DeviceMat): DeviceMat =
+    val rc = Arena.ofAuto().allocate(JAVA_LONG, 2)
+    check(um_broadcast_shape.invoke(view, b.view, rc, rc.asSlice(8)).asInstanceOf[Int])
+    val o = like(rc.get(JAVA_LONG, 0), rc.get(JAVA_LONG, 8)); check(um_binary.invoke(op, view, b.view, o.view).asInstanceOf[Int]); o
+  private def binS(op: Int, s: Double, left: Boolean = false): DeviceMat =
+    val o = like(rows, cols); check(um_binary_scalar.invoke(op, view, s, if left then 1 else 0, o.view).asInstanceOf[Int]); o
+  def +(b: DeviceMat) = bin(0, b); def -(b: DeviceMat) = bin(1, b); def *:*(b: DeviceMat) = bin(2, b); def /(b: DeviceMat) = bin(3, b)
+  def +(s: Double) = binS(0, s); def -(s: Double) = binS(1, s); def *(s: Double) = binS(2, s); def /(s: Double) = binS(3, s)
+  def unary_- : DeviceMat = un(0)
+  def :+=(s: Double): DeviceMat = { check(um_binary_scalar.invoke(0, view, s, 0, view).asInstanceOf[Int]); this }
+  def :-=(s: Double): DeviceMat = { check(um_binary_scalar.invoke(1, view, s, 0, view).asInstanceOf[Int]); this }
+  def :*=(s: Double): DeviceMat = { check(um_binary_scalar.invoke(2, view, s, 0, view).asInstanceOf[Int]); this }
+  def :/=(s: Double): DeviceMat = { check(um_binary_scalar.invoke(3, view, s, 0, view).asInstanceOf[Int]); this }
+  def :+=(b: DeviceMat): DeviceMat =
+    require(b.rows == rows && b.cols == cols, "in-place op requires equal shapes")            // Mat.scala:4565
+    check(um_binary.invoke(0, view, b.view, view).asInstanceOf[Int]); this
+  private def un(op: Int, out: DType = dtype): DeviceMat =
+    val o = like(rows, cols, out); check(um_unary.invoke(op, view, o.view).asInstanceOf[Int]); o
+  def sigmoid: DeviceMat = un(5, DType.F64)                                                   // MatMathOps.scala:97-122
+  def relu: DeviceMat    = un(6)                                                              // MatMathOps.scala:125-146
+  def softmax(axis: Int = 1): DeviceMat =                                                     // MatMathOps.scala:156-226
+    val o = like(rows, cols, DType.F64); check(um_softmax.invoke(view, axis, o.view).asInstanceOf[Int]); o
+
+  // ---- reductions (Mat.scala:2251-2279, 3414-3492, 4699-4739, 4784-4805)
+  private def red(kind: Int): Double =
+    val o = Arena.ofAuto().allocate(JAVA_DOUBLE); check(um_reduce_all.invoke(kind, view, o).asInstanceOf[Int]); o.get(JAVA_DOUBLE, 0)
+  private def redAxis(kind: Int, axis: Int): DeviceMat =
+    val o = if axis == 0 then like(1, cols) else like(rows, 1)
+    check(um_reduce_axis.invoke(kind, view, axis, o.view).asInstanceOf[Int]); o
+  def sum: Double = red(0); def mean: Double = red(1); def variance: Double = red(2); def std: Double = red(3)
+  def min: Double = red(4); def max: Double = red(5)
+  def sum(axis: Int) = redAxis(0, axis); def mean(axis: Int) = redAxis(1, axis); def std(axis: Int) = redAxis(3, axis)
+  def argmax: (Int, Int) =
+    val rc = Arena.ofAuto().allocate(JAVA_LONG, 2); check(um_arg_all.invoke(1, view, rc, rc.asSlice(8)).asInstanceOf[Int])
+    (rc.get(JAVA_LONG, 0).toInt, rc.get(JAVA_LONG, 8).toInt)
+  def idxmin(axis: Int): DeviceMat =                                                          // MatPandasOps.scala:20-41
+    val o = if axis == 0 then like(1, cols, DType.I32) else like(rows, 1, DType.I32)
+    check(um_idx_axis.invoke(0, view, axis, o.view).asInstanceOf[Int]); o
+  def gt(s: Double): DeviceMat =                                                              // Mat.scala:3948-3972
+    val o = like(rows, cols, DType.Bool); check(um_compare_scalar.invoke(0, view, s, o.view).asInstanceOf[Int]); o
+
+  // ---- linear algebra (Mat.scala:2815-2881, 2979-3006)
+  def *@(b: DeviceMat): DeviceMat =
+    require(cols == b.rows, s"matmul shape mismatch: ${rows}x$cols *@ ${b.rows}x${b.cols}")
+    val o = like(rows, b.cols); check(um_matmul.invoke(view, b.view, o.view).asInstanceOf[Int]); o
+  def inverse: DeviceMat = { val o = like(rows, cols); check(um_inverse.invoke(view, o.view).asInstanceOf[Int]); o }
+
+object DeviceMat:
+  def alloc(rows: Long, cols: Long, dt: DType = DType.F64): DeviceMat =
+    val b = DeviceBuffer.alloc(rows * cols * dt.size)
+    val v = Arena.ofAuto().allocate(VIEW)
+    check(um_view_init.invoke(v, b.ptr, rows, cols, dt.code).asInstanceOf[Int])
+    new DeviceMat(b, v, dt)
+  /** Upload a host `MatD`'s row-major data (Mat.toArray) to the device. */
+  def fromHost(data: Array[Double], rows: Int, cols: Int): DeviceMat =
+    val m = alloc(rows, cols)
+    val seg = MemorySegment.ofArray(data)
+    val off = Arena.ofAuto().allocate(data.length.toLong * 8); off.copyFrom(seg)
+    check(um_h2d.invoke(m.buf.ptr, off, data.length.toLong * 8).asInstanceOf[Int]); m
+
+/** `uni.stats.Tprf3` on the device (Tprf3.scala:199-289, 1056-1110). */
+object DeviceTprf3:
+  final case class Result(forecasts: DeviceMat, residuals: DeviceMat, rSquared: Double, alpha: Option[DeviceMat])
+  private def fit(mode: Int, y: DeviceMat, X: DeviceMat, Z: DeviceMat): Result =
+    val f = DeviceMat.alloc(X.rows, 1); val r = DeviceMat.alloc(X.rows, 1); val a = DeviceMat.alloc(X.cols, 1)
+    val out = Arena.ofAuto().allocate(TPRF_OUT)
+    out.set(ADDRESS, 0, f.buf.ptr); out.set(ADDRESS, 8, r.buf.ptr)
+    if mode != 1 then out.set(ADDRESS, 16, a.buf.ptr)
+    check(um_tprf_fit.invoke(mode, y.view, X.view, Z.view, 0L, out).asInstanceOf[Int])
+    Result(f, r, out.get(JAVA_DOUBLE, 64), if mode != 1 then Some(a) else None)
+  def tprfClosedForm(y: DeviceMat, X: DeviceMat, Z: DeviceMat): Result = fit(0, y, X, Z)
+  def t3prf(y: DeviceMat, X: DeviceMat, Z: DeviceMat): Result          = fit(1, y, X, Z)
+  def estimate3prfIsFull(y: DeviceMat, X: DeviceMat, Z: DeviceMat): Result = fit(2, y, X, Z)

@@ -1,0 +1,93 @@
+// UniMatLib.scala -- Panama (java.lang.foreign, JDK >= 22) downcall bindings for libunimat.so.
+//
+// NOT compiled in the build image (no JVM there, SURVEY.md section 8c); this is the binding a uni
+// maintainer adds as a separate sbt module (the core library targets -source 17, build.sbt:6).
+// Every handle below corresponds 1:1 to a prototype in include/unimat.h; the Python ctypes twin
+// (uni_b200/_lib.py) binds the same symbols with the same struct layout and IS exercised by the
+// test-suite, so the ABI described here is the tested one.
+package uni.cuda
+
+import java.lang.foreign.*
+import java.lang.foreign.ValueLayout.*
+import java.lang.invoke.MethodHandle
+
+object UniMatLib:
+  private val linker = Linker.nativeLinker()
+  private val arena  = Arena.global()
+  private val lookup: SymbolLookup =
+    SymbolLookup.libraryLookup(sys.props.getOrElse("uni.mat.cuda.lib", "libunimat.so"), arena)
+
+  // struct um_view { void* data; int64 offset, rows, cols, rs, cs; int32 dtype, transposed; }  (56 bytes)
+  val VIEW: StructLayout = MemoryLayout.structLayout(
+    ADDRESS.withName("data"), JAVA_LONG.withName("offset"), JAVA_LONG.withName("rows"), JAVA_LONG.withName("cols"),
+    JAVA_LONG.withName("rs"), JAVA_LONG.withName("cs"), JAVA_INT.withName("dtype"), JAVA_INT.withName("transposed"))
+
+  // struct um_tprf_out { 8 x double* ; double r_squared; int32 singular; (+4 pad) }  (80 bytes)
+  val TPRF_OUT: StructLayout = MemoryLayout.structLayout(
+    ADDRESS.withName("forecasts"), ADDRESS.withName("residuals"), ADDRESS.withName("alpha"), ADDRESS.withName("phi"),
+    ADDRESS.withName("phi_hat"), ADDRESS.withName("sigma"), ADDRESS.withName("beta3"), ADDRESS.withName("xstd"),
+    JAVA_DOUBLE.withName("r_squared"), JAVA_INT.withName("singular"), MemoryLayout.paddingLayout(4))
+
+  private def h(name: String, fd: FunctionDescriptor): MethodHandle =
+    linker.downcallHandle(lookup.find(name).orElseThrow(() => UnsatisfiedLinkError(name)), fd)
+  private def I(args: MemoryLayout*) = FunctionDescriptor.of(JAVA_INT, args*)
+
+  // ---- lifecycle / memory
+  val um_init        = h("um_init", I(JAVA_INT))
+  val um_sync        = h("um_sync", I())
+  val um_last_error  = h("um_last_error", FunctionDescriptor.of(ADDRESS))
+  val um_malloc      = h("um_malloc", I(JAVA_LONG, ADDRESS))
+  val um_free        = h("um_free", I(ADDRESS))
+  val um_malloc_host = h("um_malloc_host", I(JAVA_LONG, ADDRESS))
+  val um_free_host   = h("um_free_host", I(ADDRESS))
+  val um_h2d         = h("um_h2d", I(ADDRESS, ADDRESS, JAVA_LONG))
+  val um_d2h         = h("um_d2h", I(ADDRESS, ADDRESS, JAVA_LONG))
+  // ---- views (host-side descriptor arithmetic incl. the isWeirdLayout guard)
+  val um_view_init      = h("um_view_init", I(ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_INT))
+  val um_view_transpose = h("um_view_transpose", I(ADDRESS, ADDRESS))
+  val um_view_slice     = h("um_view_slice", I(ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS))
+  val um_view_broadcast = h("um_view_broadcast", I(ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS))
+  val um_broadcast_shape = h("um_broadcast_shape", I(ADDRESS, ADDRESS, ADDRESS, ADDRESS))
+  val um_copy = h("um_copy", I(ADDRESS, ADDRESS))
+  val um_fill = h("um_fill", I(ADDRESS, JAVA_DOUBLE))
+  val um_get  = h("um_get", I(ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS))
+  val um_set  = h("um_set", I(ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_DOUBLE))
+  // ---- elementwise / activations / masks
+  val um_binary         = h("um_binary", I(JAVA_INT, ADDRESS, ADDRESS, ADDRESS))
+  val um_binary_scalar  = h("um_binary_scalar", I(JAVA_INT, ADDRESS, JAVA_DOUBLE, JAVA_INT, ADDRESS))
+  val um_unary          = h("um_unary", I(JAVA_INT, ADDRESS, ADDRESS))
+  val um_softmax        = h("um_softmax", I(ADDRESS, JAVA_INT, ADDRESS))
+  val um_compare_scalar = h("um_compare_scalar", I(JAVA_INT, ADDRESS, JAVA_DOUBLE, ADDRESS))
+  val um_compare        = h("um_compare", I(JAVA_INT, ADDRESS, ADDRESS, ADDRESS))
+  val um_classify       = h("um_classify", I(JAVA_INT, ADDRESS, ADDRESS))
+  val um_mask_logic     = h("um_mask_logic", I(JAVA_INT, ADDRESS, ADDRESS, ADDRESS))
+  val um_mask_reduce    = h("um_mask_reduce", I(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS))
+  // ---- reductions
+  val um_reduce_all  = h("um_reduce_all", I(JAVA_INT, ADDRESS, ADDRESS))
+  val um_reduce_axis = h("um_reduce_axis", I(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS))
+  val um_arg_all     = h("um_arg_all", I(JAVA_INT, ADDRESS, ADDRESS, ADDRESS))
+  val um_idx_axis    = h("um_idx_axis", I(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS))
+  // ---- linear algebra
+  val um_matmul  = h("um_matmul", I(ADDRESS, ADDRESS, ADDRESS))
+  val um_inverse = h("um_inverse", I(ADDRESS, ADDRESS))
+  val um_solve   = h("um_solve", I(ADDRESS, ADDRESS, ADDRESS))
+  // ---- 3PRF + multi-GPU
+  val um_tprf_fit = h("um_tprf_fit", I(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS))
+  val um_tprf_fit_host = h("um_tprf_fit_host",
+    I(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS))
+  val um_tprf_fit_batched = h("um_tprf_fit_batched",
+    I(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS))
+  val um_comm_unique_id = h("um_comm_unique_id", I(ADDRESS))
+  val um_comm_init      = h("um_comm_init", I(JAVA_INT, JAVA_INT, ADDRESS))
+  val um_comm_destroy   = h("um_comm_destroy", I())
+
+  // status -> the exception the reference throws for the same condition
+  def check(status: Int): Unit =
+    if status != 0 then
+      val msg = um_last_error.invoke().asInstanceOf[MemorySegment].reinterpret(512).getString(0)
+      status match
+        case 1 => throw IllegalArgumentException(msg)          // `require` failures (Mat.scala:2816-2817 ...)
+        case 2 => throw ArithmeticException(msg)               // singular matrix (Mat.scala:990)
+        case 3 => throw UnsupportedOperationException(msg)     // empty min/max (Mat.scala:2216)
+        case 6 => throw OutOfMemoryError(msg)
+        case _ => throw RuntimeException(s"libunimat status $status: $msg")

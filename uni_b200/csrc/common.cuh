@@ -121,4 +121,44 @@ __device__ __forceinline__ i64 total_key(double x) {
 }
 __device__ __forceinline__ i64 total_key(float x) { return total_key((double)x); }
 
+// exp(x) in ~20 FP64 issue slots (libdevice's exp costs about twice that, which makes FP64
+// sigmoid / softmax compute- instead of HBM-bound): x = k ln2 + r, |r| <= ln2/2, degree-13
+// Taylor/Horner (truncation 4e-18), 2^k applied to the exponent field.  Max error < 2 ulp on
+// [-700, 700]; anything outside (and NaN) takes libdevice's exp.
+__device__ __forceinline__ double fast_exp(double x) {
+  if (!(fabs(x) <= 700.0)) return exp(x);
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: low mantissa bits of (v + MAGIC) = rint(v)
+  double tt = fma(x, 1.4426950408889634074, MAGIC);
+  int k = __double2loint(tt);
+  double t = tt - MAGIC;
+  double r = fma(t, -6.93147180369123816490e-01, x);
+  r = fma(t, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;          // 1/13!
+  p = fma(p, r, 2.08767569878681e-09);        // 1/12!
+  p = fma(p, r, 2.505210838544172e-08);       // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);       // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);      // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);        // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);       // 1/7!
+  p = fma(p, r, 1.388888888888889e-03);       // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);       // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);      // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);      // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// 1/d for normal, finite d (callers: d in [1, 2^40]): MUFU seed (2^-23) + two Newton steps.
+__device__ __forceinline__ double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
 }  // namespace um

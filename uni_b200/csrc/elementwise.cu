@@ -58,7 +58,7 @@ struct BindScalar {
 struct UNeg { template <class TI, class TO> __device__ TO apply(TI x) const { return (TO)(-x); } };
 // abs = x < 0 ? -x : x, keeps -0.0 (Mat.scala:3557-3560)
 struct UAbs { template <class TI, class TO> __device__ TO apply(TI x) const { return (TO)(x < (TI)0 ? -x : x); } };
-struct UExp { template <class TI, class TO> __device__ TO apply(TI x) const { return (TO)exp((double)x); } };
+struct UExp { template <class TI, class TO> __device__ TO apply(TI x) const { return (TO)fast_exp((double)x); } };
 struct USqrt { template <class TI, class TO> __device__ TO apply(TI x) const { return (TO)sqrt((double)x); } };
 struct ULog { template <class TI, class TO> __device__ TO apply(TI x) const { return (TO)log((double)x); } };
 struct UTanh { template <class TI, class TO> __device__ TO apply(TI x) const { return (TO)tanh((double)x); } };
@@ -69,11 +69,12 @@ struct UCast { template <class TI, class TO> __device__ TO apply(TI x) const { r
 struct USigmoid {
   template <class TI, class TO>
   __device__ TO apply(TI xi) const {
+    // same two formulas with z = exp(-|x|): x >= 0 -> 1/(1+z), else z/(1+z); the division is
+    // num * rcp(1+z) with 1+z in [1,2] (<= 2 ulp from the reference's IEEE divide)
     double x = (double)xi;
-    double r;
-    if (x >= 0.0) r = 1.0 / (1.0 + exp(-x));
-    else { double e = exp(x); r = e / (1.0 + e); }
-    return (TO)r;
+    double z = fast_exp(-fabs(x));
+    double num = (x >= 0.0) ? 1.0 : z;
+    return (TO)(num * fast_rcp(1.0 + z));
   }
 };
 // relu: Math.max(x, 0.0) -- NaN survives, -0.0 -> +0.0 (MatMathOps.scala:131); the generic

@@ -28,26 +28,26 @@ struct SumP {
   struct Acc { double s; };
   __device__ static void linit(Local& l) { l.s = 0.0; }
   template <class T> __device__ static void push(Local& l, T x, i64, double) { l.s += (double)x; }
-  __device__ static Acc finish(const Local& l, double) { return Acc{l.s}; }
+  __device__ static Acc finish(const Local& l, double, double) { return Acc{l.s}; }
   __device__ static Acc identity() { return Acc{0.0}; }
   __device__ static void merge(Acc& a, const Acc& b) { a.s += b.s; }
   __device__ static Acc shfl(const Acc& a, int d) { return Acc{shfl_down_d(a.s, d)}; }
 };
 
 struct VarP {
-  struct Local { double s1, s2, n; };
+  struct Local { double s1, s2; };
   struct Acc { double n, mean, m2; };
-  __device__ static void linit(Local& l) { l.s1 = l.s2 = l.n = 0.0; }
+  __device__ static void linit(Local& l) { l.s1 = l.s2 = 0.0; }
   template <class T> __device__ static void push(Local& l, T x, i64, double k) {
     double d = (double)x - k;
     l.s1 += d;
     l.s2 = fma(d, d, l.s2);
-    l.n += 1.0;
   }
-  __device__ static Acc finish(const Local& l, double k) {
-    if (l.n == 0.0) return Acc{0.0, 0.0, 0.0};
-    double m = l.s1 / l.n;
-    return Acc{l.n, k + m, l.s2 - l.s1 * m};
+  // n = number of elements pushed into this local (the kernels count loop trips, not elements)
+  __device__ static Acc finish(const Local& l, double k, double n) {
+    if (n == 0.0) return Acc{0.0, 0.0, 0.0};
+    double m = l.s1 / n;
+    return Acc{n, k + m, l.s2 - l.s1 * m};
   }
   __device__ static Acc identity() { return Acc{0.0, 0.0, 0.0}; }
   __device__ static void merge(Acc& a, const Acc& b) {  // Chan et al. pairwise update
@@ -74,7 +74,7 @@ struct ArgP {
     bool better = l.idx < 0 || (MAX ? k > l.key : k < l.key);  // strict: first occurrence stays
     if (better) { l.key = k; l.idx = idx; }
   }
-  __device__ static Acc finish(const Local& l, double) { return l; }
+  __device__ static Acc finish(const Local& l, double, double) { return l; }
   __device__ static Acc identity() { return Acc{0, -1}; }
   __device__ static void merge(Acc& a, const Acc& b) {
     if (b.idx < 0) return;
@@ -137,9 +137,11 @@ __global__ void __launch_bounds__(RD_THREADS) k_reduce_contig(const T* __restric
     for (int u = 0; u < RD_UNROLL; ++u) P::linit(loc[u]);
     const i64 stride = (i64)nthr * VW;
     i64 i = lo + (i64)t * VW;
+    int trips = 0, tail = 0;  // loc[u] received trips*VW elements, loc[0] `tail` more
     if (VW > 1) {
       typedef RVec<T, VW> V;
       for (; i + (RD_UNROLL - 1) * stride + VW <= hi; i += RD_UNROLL * stride) {
+        ++trips;
         V x[RD_UNROLL];
 #pragma unroll
         for (int u = 0; u < RD_UNROLL; ++u) x[u] = *reinterpret_cast<const V*>(base + i + u * stride);
@@ -151,26 +153,28 @@ __global__ void __launch_bounds__(RD_THREADS) k_reduce_contig(const T* __restric
       for (; i < hi; i += stride) {
         if (i + VW <= hi) {
           V x = *reinterpret_cast<const V*>(base + i);
+          tail += VW;
 #pragma unroll
           for (int j = 0; j < VW; ++j) P::push(loc[0], x.v[j], ibase + (i + j) * irs, k);
         } else {
-          for (i64 ii = i; ii < hi; ++ii) P::push(loc[0], base[ii], ibase + ii * irs, k);
+          for (i64 ii = i; ii < hi; ++ii) { P::push(loc[0], base[ii], ibase + ii * irs, k); ++tail; }
         }
       }
     } else {
       for (; i + (RD_UNROLL - 1) * stride < hi; i += RD_UNROLL * stride) {
+        ++trips;
         T x[RD_UNROLL];
 #pragma unroll
         for (int u = 0; u < RD_UNROLL; ++u) x[u] = base[i + u * stride];
 #pragma unroll
         for (int u = 0; u < RD_UNROLL; ++u) P::push(loc[u], x[u], ibase + (i + u * stride) * irs, k);
       }
-      for (; i < hi; i += stride) P::push(loc[0], base[i], ibase + i * irs, k);
+      for (; i < hi; i += stride) { P::push(loc[0], base[i], ibase + i * irs, k); ++tail; }
     }
-    acc = P::finish(loc[0], k);
+    acc = P::finish(loc[0], k, (double)(trips * VW + tail));
 #pragma unroll
     for (int u = 1; u < RD_UNROLL; ++u) {
-      typename P::Acc o = P::finish(loc[u], k);
+      typename P::Acc o = P::finish(loc[u], k, (double)(trips * VW));
       P::merge(acc, o);
     }
   }
@@ -213,7 +217,9 @@ __global__ void __launch_bounds__(RD_THREADS) k_reduce_strided(const T* __restri
 #pragma unroll
       for (int j = 0; j < VW; ++j) P::linit(loc[u][j]);
     i64 i = lo + ty;
+    int trips = 0, tail = 0;
     for (; i + (RD_UNROLL - 1) * 8 < hi; i += RD_UNROLL * 8) {
+      ++trips;
       V x[RD_UNROLL];
 #pragma unroll
       for (int u = 0; u < RD_UNROLL; ++u) x[u] = *reinterpret_cast<const V*>(p + (i + u * 8) * s_red + l0);
@@ -223,16 +229,17 @@ __global__ void __launch_bounds__(RD_THREADS) k_reduce_strided(const T* __restri
         for (int j = 0; j < VW; ++j) P::push(loc[u][j], x[u].v[j], (l0 + j) * ils + (i + u * 8) * irs, k[j]);
     }
     for (; i < hi; i += 8) {
+      ++tail;
       V x = *reinterpret_cast<const V*>(p + i * s_red + l0);
 #pragma unroll
       for (int j = 0; j < VW; ++j) P::push(loc[0][j], x.v[j], (l0 + j) * ils + i * irs, k[j]);
     }
 #pragma unroll
     for (int j = 0; j < VW; ++j) {
-      acc[j] = P::finish(loc[0][j], k[j]);
+      acc[j] = P::finish(loc[0][j], k[j], (double)(trips + tail));
 #pragma unroll
       for (int u = 1; u < RD_UNROLL; ++u) {
-        typename P::Acc o = P::finish(loc[u][j], k[j]);
+        typename P::Acc o = P::finish(loc[u][j], k[j], (double)trips);
         P::merge(acc[j], o);
       }
     }
@@ -262,7 +269,7 @@ __global__ void __launch_bounds__(RD_THREADS) k_reduce_generic(const T* __restri
   typename P::Local loc;
   P::linit(loc);
   for (i64 i = 0; i < n_red; ++i) P::push(loc, base[i * s_red], lane * ils + i * irs, k);
-  partials[lane] = P::finish(loc, k);
+  partials[lane] = P::finish(loc, k, (double)n_red);
 }
 
 // ---- stage 2 ---------------------------------------------------------------------------------
@@ -543,16 +550,16 @@ struct SoftP {
   template <class T> __device__ static void push(Local& l, T xi, i64, double) {
     double x = (double)xi;
     if (x > l.m) {
-      l.s = l.s * exp(l.m - x) + 1.0;   // exp(-inf) = 0 on the first element
+      l.s = l.s * fast_exp(l.m - x) + 1.0;   // exp(-inf) = 0 on the first element
       l.m = x;
       if (x == INFINITY) l.s = NAN;     // reference: inf - inf = NaN poisons the lane
     } else if (x == -INFINITY) {
       // contributes exp(-inf) = 0 against any finite max; an all -inf lane ends with s = 0 -> NaN
     } else {
-      l.s += exp(x - l.m);              // NaN input -> NaN sum
+      l.s += fast_exp(x - l.m);         // NaN input -> NaN sum
     }
   }
-  __device__ static Acc finish(const Local& l, double) { return l; }
+  __device__ static Acc finish(const Local& l, double, double) { return l; }
   __device__ static Acc identity() { return Acc{-INFINITY, 0.0}; }
   __device__ static void merge(Acc& a, const Acc& b) {
     if (b.m == -INFINITY && b.s == 0.0) return;
@@ -564,6 +571,35 @@ struct SoftP {
   __device__ static Acc shfl(const Acc& a, int d) { return Acc{shfl_down_d(a.m, d), shfl_down_d(a.s, d)}; }
 };
 
+// Branch-free variant for the streaming pass: shift by the lane's first element k instead of a
+// running max, s = sum exp(x - k), mx = max x.  Exact unless exp(x - k) overflows; that (mx - k >
+// 600, or a non-finite k) is flagged with s = -1 and the flagged lane is redone with the online
+// form by k_softmax_lane_stats.
+struct SoftKP {
+  struct Local { double s, mx; };
+  typedef SoftP::Acc Acc;
+  __device__ static void linit(Local& l) { l.s = 0.0; l.mx = -INFINITY; }
+  template <class T> __device__ static void push(Local& l, T xi, i64, double k) {
+    double x = (double)xi;
+    l.s += fast_exp(x - k);
+    l.mx = fmax(l.mx, x);
+  }
+  __device__ static Acc finish(const Local& l, double k, double n) {
+    if (n == 0.0) return Acc{-INFINITY, 0.0};
+    double d = l.mx - k;
+    if (!(d <= 600.0) && !(l.s != l.s && d == d)) return Acc{0.0, -1.0};  // overflow risk (not a plain NaN lane)
+    if (!(fabs(k) <= 1.7e308)) return Acc{0.0, -1.0};
+    return Acc{l.mx, l.s * fast_exp(k - l.mx)};   // re-base on the local max
+  }
+  __device__ static Acc identity() { return Acc{-INFINITY, 0.0}; }
+  __device__ static void merge(Acc& a, const Acc& b) {
+    if (a.s < 0.0) return;
+    if (b.s < 0.0) { a = b; return; }
+    SoftP::merge(a, b);
+  }
+  __device__ static Acc shfl(const Acc& a, int d) { return SoftP::shfl(a, d); }
+};
+
 // normalise pass for strided lanes: out[i][l] = exp(x[i][l] - m[l]) / s[l]
 template <class T>
 __global__ void __launch_bounds__(256) k_softmax_norm(const T* __restrict__ p, i64 s_lane, i64 s_red, i64 n_lane, i64 n_red,
@@ -573,31 +609,167 @@ __global__ void __launch_bounds__(256) k_softmax_norm(const T* __restrict__ p, i
   if (l >= n_lane) return;
   SoftP::Acc a = part[l];
   for (int c = 1; c < chunks; ++c) SoftP::merge(a, part[(i64)c * n_lane + l]);
+  const double inv = 1.0 / a.s;
   for (i64 i = (i64)blockIdx.y * 8 + threadIdx.y; i < n_red; i += (i64)gridDim.y * 8) {
     double x = (double)p[l * s_lane + i * s_red];
-    out[l * o_lane + i * o_red] = exp(x - a.m) / a.s;
+    out[l * o_lane + i * o_red] = fast_exp(x - a.m) * inv;
   }
 }
 
-// register-resident lane softmax.  CTA `rank` of the cluster owns elements
-// [rank*PER_CTA, (rank+1)*PER_CTA) of the lane; thread t holds vectors j*THREADS + t.
+// lane statistics (m, 1/s) from the chunk partials, one thread per lane
+template <class T>
+__global__ void __launch_bounds__(256) k_softmax_lane_stats(const SoftP::Acc* __restrict__ part, int chunks, i64 n_lane,
+                                                             const T* __restrict__ p, i64 s_red, i64 n_red,
+                                                             double* __restrict__ m_out, double* __restrict__ inv_out) {
+  i64 l = (i64)blockIdx.x * 256 + threadIdx.x;
+  if (l >= n_lane) return;
+  SoftP::Acc a = part[l];
+  for (int c = 1; c < chunks; ++c) SoftKP::merge(a, part[(i64)c * n_lane + l]);
+  if (a.s < 0.0) {  // flagged: the shifted sum could overflow -> online form, this thread alone (rare)
+    SoftP::Local loc;
+    SoftP::linit(loc);
+    for (i64 i = 0; i < n_red; ++i) SoftP::push(loc, p[i * s_red + l], 0, 0.0);
+    a = loc;
+  }
+  m_out[l] = a.m;
+  inv_out[l] = 1.0 / a.s;
+}
+
+// vectorised normalise pass for row-major f64 input with unit-stride lanes (axis 0 of a
+// row-major matrix): block (32, 8), each thread 2 adjacent lanes x 4 rows in flight.
+__global__ void __launch_bounds__(256) k_softmax_norm_vec(const double* __restrict__ p, i64 s_red, i64 n_lane, i64 n_red,
+                                                           const double* __restrict__ m_in, const double* __restrict__ inv_in,
+                                                           double* __restrict__ out, i64 o_red) {
+  const i64 l = ((i64)blockIdx.x * 32 + threadIdx.x) * 2;
+  if (l >= n_lane) return;  // n_lane is even on this path
+  const double2 m = *reinterpret_cast<const double2*>(m_in + l);
+  const double2 inv = *reinterpret_cast<const double2*>(inv_in + l);
+  const i64 step = (i64)gridDim.y * 8;
+  i64 i = (i64)blockIdx.y * 8 + threadIdx.y;
+  for (; i + 3 * step < n_red; i += 4 * step) {
+    double2 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = *reinterpret_cast<const double2*>(p + (i + u * step) * s_red + l);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      double2 o = make_double2(fast_exp(x[u].x - m.x) * inv.x, fast_exp(x[u].y - m.y) * inv.y);
+      __stcs(reinterpret_cast<double2*>(out + (i + u * step) * o_red + l), o);
+    }
+  }
+  for (; i < n_red; i += step) {
+    double2 x = *reinterpret_cast<const double2*>(p + i * s_red + l);
+    double2 o = make_double2(fast_exp(x.x - m.x) * inv.x, fast_exp(x.y - m.y) * inv.y);
+    __stcs(reinterpret_cast<double2*>(out + i * o_red + l), o);
+  }
+}
+
+// Long contiguous lanes (a 256 KiB row does not fit one CTA's registers): ONE CTA of 512 threads
+// per lane (two resident per SM), two passes.  Pass A folds an online (max, sum) over the lane from HBM; pass B re-reads
+// the lane -- 296 resident CTAs x 256 KiB = 76 MB, so it comes back from the 126 MB L2, not HBM --
+// and writes exp(x - m) / s with streaming stores.  DRAM traffic stays one read + one write.
+template <class T, int VW>
+__global__ void __launch_bounds__(512, 2) k_softmax_row2pass(const T* __restrict__ p, i64 s_lane, i64 n_red,
+                                                               double* __restrict__ out, i64 o_lane) {
+  __shared__ SoftP::Acc sm[32];
+  __shared__ double bc[2];
+  typedef RVec<T, VW> V;
+  typedef RVec<double, VW> VO;
+  const int t = threadIdx.x;
+  const T* base = p + (i64)blockIdx.x * s_lane;
+  double* obase = out + (i64)blockIdx.x * o_lane;
+  constexpr int U = 8;                 // 8 x 16 B in flight per thread, 2 CTAs per SM
+  const i64 stride = 512 * (i64)VW;
+  const i64 nvec = (n_red / VW) * VW;  // elements covered by whole vectors
+  // ---- pass A: online max / sum -------------------------------------------------------------
+  double m = -INFINITY, s = 0.0;
+  auto fold = [&](const double* x, int n) {
+    double bm = x[0];
+    for (int q = 1; q < n; ++q) bm = fmax(bm, x[q]);   // fmax drops NaNs; the exp below keeps them
+    if (bm > m) {
+      s *= fast_exp(m - bm);   // exp(-inf) = 0 the first time
+      m = bm;
+    }
+    for (int q = 0; q < n; ++q) {
+      // x = -inf against a finite max contributes 0; (+inf) - (+inf) and NaN give NaN, as the reference
+      double e = (x[q] == -INFINITY && m == -INFINITY) ? 0.0 : fast_exp(x[q] - m);
+      s += e;
+    }
+  };
+  i64 i = (i64)t * VW;
+  for (; i + (U - 1) * stride + VW <= nvec; i += U * stride) {
+    V v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = *reinterpret_cast<const V*>(base + i + u * stride);
+    double x[U * VW];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int q = 0; q < VW; ++q) x[u * VW + q] = (double)v[u].v[q];
+    fold(x, U * VW);
+  }
+  for (; i + VW <= nvec; i += stride) {
+    V v = *reinterpret_cast<const V*>(base + i);
+    double x[VW];
+#pragma unroll
+    for (int q = 0; q < VW; ++q) x[q] = (double)v.v[q];
+    fold(x, VW);
+  }
+  if (t == 0)
+    for (i64 ii = nvec; ii < n_red; ++ii) {
+      double x[1] = {(double)base[ii]};
+      fold(x, 1);
+    }
+  SoftP::Acc a{m, s};
+  if (m == INFINITY) a.s = NAN;  // +inf in the lane: inf - inf poisons the reference's sum
+  a = block_merge<SoftP>(a, sm);
+  if (t == 0) {
+    bc[0] = a.m;
+    bc[1] = 1.0 / a.s;
+  }
+  __syncthreads();
+  const double mx = bc[0], inv = bc[1];
+  // ---- pass B: normalise (lane re-read from L2) ---------------------------------------------------
+  i = (i64)t * VW;
+  for (; i + (U - 1) * stride + VW <= nvec; i += U * stride) {
+    V v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = *reinterpret_cast<const V*>(base + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      VO o;
+#pragma unroll
+      for (int q = 0; q < VW; ++q) o.v[q] = fast_exp((double)v[u].v[q] - mx) * inv;
+      if (VW == 2) __stcs(reinterpret_cast<double2*>(obase + i + u * stride), make_double2(o.v[0], o.v[VW - 1]));
+      else *reinterpret_cast<VO*>(obase + i + u * stride) = o;
+    }
+  }
+  for (; i + VW <= nvec; i += stride) {
+    V v = *reinterpret_cast<const V*>(base + i);
+    VO o;
+#pragma unroll
+    for (int q = 0; q < VW; ++q) o.v[q] = fast_exp((double)v.v[q] - mx) * inv;
+    *reinterpret_cast<VO*>(obase + i) = o;
+  }
+  if (t == 0)
+    for (i64 ii = nvec; ii < n_red; ++ii) obase[ii] = fast_exp((double)base[ii] - mx) * inv;
+}
+
+// register-resident lane softmax for lanes up to 4096 elements: one CTA per lane, thread t holds
+// vectors j*THREADS + t; max and sum by shuffle + shared memory in a fixed order.
 template <class T, int NV, int THREADS, int VW>
 __global__ void __launch_bounds__(THREADS) k_softmax_lane(const T* __restrict__ p, i64 s_lane, i64 n_red,
-                                                           double* __restrict__ out, i64 o_lane, int csize) {
+                                                           double* __restrict__ out, i64 o_lane) {
   __shared__ double sm_red[THREADS / 32];
-  __shared__ double sm_xchg[2];  // [0] = this CTA's max, [1] = this CTA's sum (read by cluster peers)
-  unsigned rank = 0;
-  if (csize > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-  const i64 lane = blockIdx.x / csize;
+  __shared__ double sm_bc[2];
+  const i64 lane = blockIdx.x;
   const int t = threadIdx.x;
   const T* base = p + lane * s_lane;
   double* obase = out + lane * o_lane;
-  const i64 cta0 = (i64)rank * NV * THREADS * VW;
   typedef RVec<T, VW> V;
   double x[NV][VW];
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    i64 i = cta0 + ((i64)j * THREADS + t) * VW;
+    i64 i = ((i64)j * THREADS + t) * VW;
     if (VW > 1 && i + VW <= n_red) {
       V v = *reinterpret_cast<const V*>(base + i);
 #pragma unroll
@@ -619,31 +791,18 @@ __global__ void __launch_bounds__(THREADS) k_softmax_lane(const T* __restrict__ 
   if (t == 0) {
     double m = sm_red[0];
     for (int w = 1; w < THREADS / 32; ++w) m = fmax(m, sm_red[w]);
-    sm_xchg[0] = m;
+    sm_bc[0] = m;
   }
   __syncthreads();
-  if (csize > 1) {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    unsigned local = (unsigned)__cvta_generic_to_shared(&sm_xchg[0]);
-    mx = -INFINITY;
-    for (int r = 0; r < csize; ++r) {
-      unsigned remote;
-      double v;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
-      asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote));
-      mx = fmax(mx, v);
-    }
-  } else {
-    mx = sm_xchg[0];
-  }
+  mx = sm_bc[0];
   // ---- exp and sum ----
   double s = 0.0;
 #pragma unroll
   for (int j = 0; j < NV; ++j)
 #pragma unroll
     for (int q = 0; q < VW; ++q) {
-      i64 i = cta0 + ((i64)j * THREADS + t) * VW + q;
-      double e = (i < n_red) ? exp(x[j][q] - mx) : 0.0;
+      i64 i = ((i64)j * THREADS + t) * VW + q;
+      double e = (i < n_red) ? fast_exp(x[j][q] - mx) : 0.0;
       x[j][q] = e;
       s += e;
     }
@@ -654,72 +813,204 @@ __global__ void __launch_bounds__(THREADS) k_softmax_lane(const T* __restrict__ 
   if (t == 0) {
     double a = sm_red[0];
     for (int w = 1; w < THREADS / 32; ++w) a += sm_red[w];
-    sm_xchg[1] = a;
+    sm_bc[1] = 1.0 / a;
   }
   __syncthreads();
-  if (csize > 1) {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    unsigned local = (unsigned)__cvta_generic_to_shared(&sm_xchg[1]);
-    s = 0.0;
-    for (int r = 0; r < csize; ++r) {  // fixed rank order -> reproducible
-      unsigned remote;
-      double v;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
-      asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote));
-      s += v;
-    }
-  } else {
-    s = sm_xchg[1];
-  }
-  // ---- normalise and store ----
+  s = sm_bc[1];
+  // ---- normalise and store (e * (1/s): <= 1.5 ulp from the reference's e / s) ----
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    i64 i = cta0 + ((i64)j * THREADS + t) * VW;
+    i64 i = ((i64)j * THREADS + t) * VW;
     if (VW > 1 && i + VW <= n_red) {
       RVec<double, VW> v;
 #pragma unroll
-      for (int q = 0; q < VW; ++q) v.v[q] = x[j][q] / s;
+      for (int q = 0; q < VW; ++q) v.v[q] = x[j][q] * s;
       *reinterpret_cast<RVec<double, VW>*>(obase + i) = v;
     } else {
 #pragma unroll
       for (int q = 0; q < VW; ++q)
-        if (i + q < n_red) obase[i + q] = x[j][q] / s;
+        if (i + q < n_red) obase[i + q] = x[j][q] * s;
     }
   }
-  // peers may still be reading this CTA's sm_xchg: do not exit before everyone is done
-  if (csize > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <class T, int NV, int THREADS, int VW>
-static int launch_softmax_lane(const T* p, i64 s_lane, i64 n_lane, i64 n_red, double* out, i64 o_lane, int csize) {
+// Rows of 4097..32768 doubles, 16-byte aligned: the WHOLE lane is staged on chip, so HBM sees one
+// read and one write and every load of the lane is in flight at once.  A CTA of 512 threads owns up
+// to 16384 elements: 112 KB of shared memory (cp.async; each thread later reads back only the chunks
+// it copied, so the data needs no barrier) plus 4 doubles per thread in registers.  Two CTAs fit an
+// SM, so one row's exp phase overlaps another row's loads/stores.  Rows longer than 16384 use a
+// 2-CTA cluster: max and sum are exchanged through distributed shared memory in rank order.
+constexpr int OC_THREADS = 512;
+constexpr int OC_REG = 2;                                        // double2 per thread held in registers
+constexpr int OC_SMEM_CHUNKS = 14;                               // 16-byte chunks per thread in shared memory
+constexpr int OC_SMEM_BYTES = OC_THREADS * OC_SMEM_CHUNKS * 16;  // 114688
+constexpr int OC_CTA_VECS = OC_THREADS * (OC_REG + OC_SMEM_CHUNKS);  // 8192 double2 = 16384 doubles
+constexpr int OC_CAP = 2 * OC_CTA_VECS * 2;                      // 32768 with a 2-CTA cluster
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_peer_f64(const double* local_smem, unsigned rank) {
+  unsigned la = (unsigned)__cvta_generic_to_shared(local_smem), ra;
+  double v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra));
+  return v;
+}
+
+template <int CS>
+__global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const double* __restrict__ p, i64 s_lane, i64 n_red,
+                                                                       double* __restrict__ out, i64 o_lane) {
+  extern __shared__ __align__(16) double2 sx[];   // chunk c of thread t at sx[c * OC_THREADS + t]
+  __shared__ double sm_red[OC_THREADS / 32];
+  __shared__ double sm_x[2];                      // [0] this CTA's max, [1] this CTA's sum (read by the peer)
+  const int t = threadIdx.x;
+  unsigned rank = 0;
+  if (CS > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const i64 row = blockIdx.x / CS;
+  const double* base = p + row * s_lane;
+  double* obase = out + row * o_lane;
+  const i64 nv = n_red >> 1;                       // whole double2 vectors of the row
+  const i64 v0 = (i64)rank * OC_CTA_VECS;          // first vector owned by this CTA
+#pragma unroll
+  for (int c = 0; c < OC_SMEM_CHUNKS; ++c) {
+    const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
+    if (v < nv) {
+      unsigned sa = (unsigned)__cvta_generic_to_shared(&sx[c * OC_THREADS + t]);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(base + 2 * v) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  double2 r[OC_REG];
+#pragma unroll
+  for (int c = 0; c < OC_REG; ++c) {
+    const i64 v = v0 + (i64)c * OC_THREADS + t;
+    r[c] = v < nv ? *reinterpret_cast<const double2*>(base + 2 * v) : make_double2(-INFINITY, -INFINITY);
+  }
+  const bool odd_tail = (n_red & 1) && t == 0 && rank == 0;
+  double xt = odd_tail ? base[n_red - 1] : -INFINITY;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // ---- max (fmax drops NaNs; a NaN still poisons the sum) ----
+  double mx = fmax(xt, fmax(fmax(r[0].x, r[0].y), fmax(r[1].x, r[1].y)));
+#pragma unroll
+  for (int c = 0; c < OC_SMEM_CHUNKS; ++c) {
+    const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
+    if (v < nv) {
+      double2 x = sx[c * OC_THREADS + t];
+      mx = fmax(mx, fmax(x.x, x.y));
+    }
+  }
+  for (int d = 16; d > 0; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  if ((t & 31) == 0) sm_red[t >> 5] = mx;
+  __syncthreads();
+  if (t == 0) {
+    double m = sm_red[0];
+    for (int w = 1; w < OC_THREADS / 32; ++w) m = fmax(m, sm_red[w]);
+    sm_x[0] = m;
+  }
+  __syncthreads();
+  if (CS > 1) {
+    cluster_sync_all();
+    mx = fmax(ld_peer_f64(&sm_x[0], 0), ld_peer_f64(&sm_x[0], 1));
+  } else {
+    mx = sm_x[0];
+  }
+  // ---- exp (kept on chip) and sum ----
+  double s = 0.0;
+#pragma unroll
+  for (int c = 0; c < OC_REG; ++c) {
+    const i64 v = v0 + (i64)c * OC_THREADS + t;
+    if (v < nv) {
+      r[c].x = fast_exp(r[c].x - mx);
+      r[c].y = fast_exp(r[c].y - mx);
+      s += r[c].x + r[c].y;
+    }
+  }
+  if (odd_tail) { xt = fast_exp(xt - mx); s += xt; }
+#pragma unroll
+  for (int c = 0; c < OC_SMEM_CHUNKS; ++c) {
+    const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
+    if (v < nv) {
+      double2 x = sx[c * OC_THREADS + t];
+      x.x = fast_exp(x.x - mx);
+      x.y = fast_exp(x.y - mx);
+      s += x.x + x.y;
+      sx[c * OC_THREADS + t] = x;
+    }
+  }
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  __syncthreads();
+  if ((t & 31) == 0) sm_red[t >> 5] = s;
+  __syncthreads();
+  if (t == 0) {
+    double a = sm_red[0];
+    for (int w = 1; w < OC_THREADS / 32; ++w) a += sm_red[w];
+    sm_x[1] = a;
+  }
+  __syncthreads();
+  if (CS > 1) {
+    cluster_sync_all();
+    s = ld_peer_f64(&sm_x[1], 0) + ld_peer_f64(&sm_x[1], 1);   // fixed rank order
+  } else {
+    s = sm_x[1];
+  }
+  const double inv = 1.0 / s;
+  // ---- normalise, streaming stores ----
+#pragma unroll
+  for (int c = 0; c < OC_REG; ++c) {
+    const i64 v = v0 + (i64)c * OC_THREADS + t;
+    if (v < nv) __stcs(reinterpret_cast<double2*>(obase + 2 * v), make_double2(r[c].x * inv, r[c].y * inv));
+  }
+#pragma unroll
+  for (int c = 0; c < OC_SMEM_CHUNKS; ++c) {
+    const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
+    if (v < nv) {
+      double2 x = sx[c * OC_THREADS + t];
+      __stcs(reinterpret_cast<double2*>(obase + 2 * v), make_double2(x.x * inv, x.y * inv));
+    }
+  }
+  if (odd_tail) obase[n_red - 1] = xt * inv;
+  if (CS > 1) cluster_sync_all();   // the peer may still be reading sm_x
+}
+
+template <int CS>
+static int launch_row_onchip(const double* p, i64 s_lane, i64 n_lane, i64 n_red, double* out, i64 o_lane) {
+  static bool attr = false;
+  if (!attr) {
+    UM_CUDA(cudaFuncSetAttribute(k_softmax_row_onchip<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, OC_SMEM_BYTES));
+    attr = true;
+  }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(n_lane * csize), 1, 1);
-  cfg.blockDim = dim3(THREADS, 1, 1);
-  cfg.dynamicSmemBytes = 0;
+  cfg.gridDim = dim3((unsigned)(n_lane * CS), 1, 1);
+  cfg.blockDim = dim3(OC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = OC_SMEM_BYTES;
   cfg.stream = ctx()->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = csize;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
   cfg.numAttrs = 1;
-  UM_CUDA(cudaLaunchKernelEx(&cfg, k_softmax_lane<T, NV, THREADS, VW>, p, s_lane, n_red, out, o_lane, csize));
-  UM_LAUNCHED();
+  UM_CUDA(cudaLaunchKernelEx(&cfg, k_softmax_row_onchip<CS>, p, s_lane, n_red, out, o_lane));
   return UM_OK;
 }
 
 template <class T, int VW>
 static int softmax_contig(const T* p, i64 s_lane, i64 n_lane, i64 n_red, double* out, i64 o_lane) {
-  // capacity per CTA = NV * THREADS * VW
-  if (n_red <= 128 * VW) return launch_softmax_lane<T, 1, 128, VW>(p, s_lane, n_lane, n_red, out, o_lane, 1);
-  if (n_red <= 256 * 2 * VW) return launch_softmax_lane<T, 2, 256, VW>(p, s_lane, n_lane, n_red, out, o_lane, 1);
-  if (n_red <= 256 * 8 * VW) return launch_softmax_lane<T, 8, 256, VW>(p, s_lane, n_lane, n_red, out, o_lane, 1);
-  const i64 cap = 512 * 8 * (i64)VW;
-  int cs = 1;
-  while (cs < 8 && cap * cs < n_red) cs *= 2;
-  if (cap * cs < n_red) return -1;  // caller falls back to the two-pass form
-  return launch_softmax_lane<T, 8, 512, VW>(p, s_lane, n_lane, n_red, out, o_lane, cs);
+  cudaStream_t st = ctx()->stream;
+  const unsigned g = (unsigned)n_lane;
+  if (n_red <= 128 * VW) k_softmax_lane<T, 1, 128, VW><<<g, 128, 0, st>>>(p, s_lane, n_red, out, o_lane);
+  else if (n_red <= 256 * 2 * VW) k_softmax_lane<T, 2, 256, VW><<<g, 256, 0, st>>>(p, s_lane, n_red, out, o_lane);
+  else if (n_red <= 256 * 8 * VW) k_softmax_lane<T, 8, 256, VW><<<g, 256, 0, st>>>(p, s_lane, n_red, out, o_lane);
+  else if (sizeof(T) == 8 && VW == 2 && n_red <= OC_CAP) {
+    const double* pd = reinterpret_cast<const double*>(p);
+    int rc = n_red <= OC_CTA_VECS * 2 ? launch_row_onchip<1>(pd, s_lane, n_lane, n_red, out, o_lane)
+                                      : launch_row_onchip<2>(pd, s_lane, n_lane, n_red, out, o_lane);
+    if (rc != UM_OK) return rc;
+  } else k_softmax_row2pass<T, VW><<<g, 512, 0, st>>>(p, s_lane, n_red, out, o_lane);
+  UM_LAUNCHED();
+  return UM_OK;
 }
 
 template <class T>
@@ -733,15 +1024,35 @@ static int softmax_typed(const um_view* a, int axis, const um_view* out) {
     constexpr int VW = 16 / sizeof(double);  // output vectors are double2
     bool vec = (reinterpret_cast<uintptr_t>(p) % (sizeof(T) * VW) == 0) && (pl.n_lane == 1 || pl.s_lane % VW == 0) &&
                aligned16(o) && (pl.n_lane == 1 || o_lane % VW == 0);
-    int s = vec ? softmax_contig<T, VW>(p, pl.s_lane, pl.n_lane, pl.n_red, o, o_lane)
-                : softmax_contig<T, 1>(p, pl.s_lane, pl.n_lane, pl.n_red, o, o_lane);
-    if (s != -1) return s;
+    return vec ? softmax_contig<T, VW>(p, pl.s_lane, pl.n_lane, pl.n_red, o, o_lane)
+               : softmax_contig<T, 1>(p, pl.s_lane, pl.n_lane, pl.n_red, o, o_lane);
   }
   // two-pass: online (max, sum) per lane, then normalise
   SoftP::Acc* part = nullptr;
   int chunks = 0;
-  int s = stage1<SoftP, T>(pl, &part, &chunks, 0);
+  // two extra lanes' worth of Acc slots hold the per-lane (m, 1/s) vectors of the vectorised pass
+  const bool vecnorm = sizeof(T) == 8 && pl.mode == 1 && pl.s_lane == 1 && o_lane == 1 && pl.n_lane % 2 == 0 &&
+                       pl.s_red % 2 == 0 && o_red % 2 == 0 && aligned16(p) && aligned16(o);
+  int s = vecnorm ? stage1<SoftKP, T>(pl, &part, &chunks, (size_t)pl.n_lane + 2)
+                  : stage1<SoftP, T>(pl, &part, &chunks, (size_t)pl.n_lane + 2);
   if (s != UM_OK) return s;
+  if (vecnorm && sizeof(T) == 8 && pl.mode == 1 && pl.s_lane == 1 && o_lane == 1 && pl.n_lane % 2 == 0 && pl.s_red % 2 == 0 &&
+      o_red % 2 == 0 && aligned16(p) && aligned16(o)) {
+    double* mvec = reinterpret_cast<double*>(part + (i64)chunks * pl.n_lane);
+    double* ivec = mvec + pl.n_lane;
+    k_softmax_lane_stats<T><<<(unsigned)ceil_div(pl.n_lane, 256), 256, 0, ctx()->stream>>>(part, chunks, pl.n_lane, p, pl.s_red, pl.n_red, mvec, ivec);
+    UM_LAUNCHED();
+    i64 gyv = ceil_div(pl.n_red, 8 * 32);
+    i64 tiles = ceil_div(pl.n_lane, 64);
+    i64 want = ceil_div((i64)ctx()->sm_count * 32, tiles);
+    if (gyv > want) gyv = want;
+    if (gyv < 1) gyv = 1;
+    dim3 gridv((unsigned)tiles, (unsigned)gyv), blockv(32, 8);
+    k_softmax_norm_vec<<<gridv, blockv, 0, ctx()->stream>>>(reinterpret_cast<const double*>(p), pl.s_red, pl.n_lane, pl.n_red,
+                                                             mvec, ivec, o, o_red);
+    UM_LAUNCHED();
+    return UM_OK;
+  }
   i64 gy = ceil_div(pl.n_red, 8 * 16);
   if (gy > 2048) gy = 2048;
   if (gy < 1) gy = 1;

@@ -171,7 +171,7 @@ constexpr int C1_SMEM = C1_STAGES * C1_STAGE_DBL * 8;                // 61440 B
 
 // outputs per (panel, chunk, column): q[8], s1, s2   (column index padded to strips*64)
 template <bool VEC16>
-__global__ void __launch_bounds__(C1_THREADS, 2)
+__global__ void __launch_bounds__(C1_THREADS, 3)
 k_tprf_colstats(const double* __restrict__ X, i64 ldx, i64 x_bs, const double* __restrict__ zc, i64 T, i64 N, i64 npad,
                 i64 rows_per_chunk, double* __restrict__ qp, double* __restrict__ s1p, double* __restrict__ s2p) {
   extern __shared__ __align__(16) double smem[];
@@ -329,7 +329,7 @@ k_tprf_colfinal(const double* __restrict__ X, i64 x_bs, const double* __restrict
 }
 
 // ---- sweep 2: PX = Xn W0, h0 = Xn 1 ----------------------------------------------------------------------
-constexpr int C2_ROWS = 128, C2_COLS = 32, C2_PITCH = 36, C2_STAGES = 3, C2_THREADS = 256;
+constexpr int C2_ROWS = 128, C2_COLS = 32, C2_PITCH = 36, C2_STAGES = 4, C2_THREADS = 256;
 constexpr int C2_STAGE_DBL = C2_ROWS * C2_PITCH + C2_COLS * ZPITCH + C2_COLS;  // 4608 + 384 + 32 = 5024
 constexpr int C2_SMEM = C2_STAGES * C2_STAGE_DBL * 8;                          // 120576 B
 
