@@ -25,6 +25,8 @@
 //   k_tprf_outputs   alpha / phi / phi_hat / xstd per column
 // Multi-GPU: X is sharded by predictor column; the packed buffer (T*(L8+1)+81 doubles) is the
 // only thing exchanged (um_comm_allreduce_sum_f64), then every rank runs the same finish.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "small_linalg.cuh"
 
@@ -958,7 +960,12 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
     UM_CUDA(cudaStreamSynchronize(ctx()->stream));
     return UM_OK;
   }
-  Plan3 p = make_plan(T, N, L, 1, ctx()->sm_count);
+  // EXPERIMENT (L2 blocking): sweep the panel in column blocks small enough to stay L2-resident
+  // between the two sweeps of a block.  Per-column outputs are not valid in this mode.
+  i64 blk = 0;
+  if (const char* e = getenv("UM_TPRF_BLOCK_COLS")) blk = atoll(e);
+  if (blk > 0 && blk < N) blk = (blk / 64) * 64; else blk = 0;
+  Plan3 p = make_plan(T, blk ? blk : N, L, 1, ctx()->sm_count);
   char* ws = static_cast<char*>(scratch(p.total));
   if (!ws) return UM_ERR_OOM;
   int s = set_smem_attrs();
@@ -968,8 +975,17 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
   const double* xp = static_cast<const double*>(X->data) + X->offset;
   s = run_prep(p, ws, zp, Z->rs, Z->cs, 0, yp, y->rs, 0);
   if (s != UM_OK) return s;
-  s = run_sweeps(p, ws, xp, N == 1 ? 1 : X->rs, 0, 0);
-  if (s != UM_OK) return s;
+  if (blk) {
+    for (i64 c0 = 0; c0 < N; c0 += blk) {
+      Plan3 pb = p;
+      pb.N = (c0 + blk <= N) ? blk : N - c0;
+      s = run_sweeps(pb, ws, xp + c0, X->rs, 0, c0 > 0);
+      if (s != UM_OK) return s;
+    }
+  } else {
+    s = run_sweeps(p, ws, xp, N == 1 ? 1 : X->rs, 0, 0);
+    if (s != UM_OK) return s;
+  }
   if (comm_active() && comm_world() > 1) {
     prof_begin(6);
     s = comm_allreduce_sum_f64_impl(reinterpret_cast<double*>(ws + p.o_packed), p.packed_len);
