@@ -207,6 +207,16 @@ int32_t um_tprf_fit_host(int32_t mode, const double* y, const double* X, int64_t
 int32_t um_tprf_fit_batched(int32_t mode, const double* y, const double* X, const double* Z, int64_t T,
                             int64_t N, int64_t L, int64_t batch, double* forecasts, double* alpha,
                             double* r2);
+/* Which sweep the fits use: 0 = auto (the single-read cluster sweep whenever it applies: T <= 8192,
+ * X 16-byte aligned with an even row pitch; otherwise two sweeps), 1 = two sweeps only, 2 = the
+ * single-read sweep or UM_ERR_ARG.  Process-wide; for tests and profiling. */
+int32_t um_tprf_set_path(int32_t path);
+/* Shape of the single-read sweep for a T-row panel on the current device: CTAs per cluster (0 = does
+ * not apply), rows of the panel each CTA keeps on chip, clusters resident at once. */
+/* Profiling aid: when non-NULL, cluster 0 of the single-read sweep records clock64() stamps per
+ * (rank, warp, piece) into this device buffer of 16*16*64*8 int64 (tools/fused_timeline.py). */
+int32_t um_tprf_debug_stamps(long long* device_buf);
+int32_t um_tprf_fused_info(int64_t T, int32_t* cluster_size, int32_t* rows_per_piece, int32_t* resident_clusters);
 /* accounting for bench.py: algorithmic flops/bytes of one fit */
 int32_t um_tprf_work(int64_t T, int64_t N, int64_t L, double* flops, double* bytes);
 

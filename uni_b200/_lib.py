@@ -132,6 +132,9 @@ SIGNATURES = {
     "um_tprf_fit_host": (_i32, [_i32, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, C.POINTER(_f64)]),
     "um_tprf_fit_batched": (_i32, [_i32, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "um_tprf_work": (_i32, [_i64, _i64, _i64, C.POINTER(_f64), C.POINTER(_f64)]),
+    "um_tprf_set_path": (_i32, [_i32]),
+    "um_tprf_debug_stamps": (_i32, [_vp]),
+    "um_tprf_fused_info": (_i32, [_i64, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "um_comm_unique_id": (_i32, [C.POINTER(C.c_uint8)]),
     "um_comm_init": (_i32, [_i32, _i32, C.POINTER(C.c_uint8)]),
     "um_comm_destroy": (_i32, []),

@@ -25,8 +25,6 @@
 //   k_tprf_outputs   alpha / phi / phi_hat / xstd per column
 // Multi-GPU: X is sharded by predictor column; the packed buffer (T*(L8+1)+81 doubles) is the
 // only thing exchanged (um_comm_allreduce_sum_f64), then every rank runs the same finish.
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "small_linalg.cuh"
 
@@ -741,6 +739,10 @@ __global__ void k_fill_nan(double* p, i64 n) {
   if (i < n) p[i] = nan("");
 }
 
+}  // namespace um
+#include "tprf_fused.cuh"
+namespace um {
+
 // ---- host orchestration ------------------------------------------------------------------------------------------
 static i64 cdiv(i64 a, i64 b) { return (a + b - 1) / b; }
 static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
@@ -750,10 +752,36 @@ struct Plan3 {
   i64 strips, npad, rchunks, rows_per_chunk;     // sweep 1
   i64 rblocks, tpad, cchunks, cols_per_chunk;    // sweep 2
   int cf_blocks;                                 // colfinal blocks per panel
+  // single-read fused sweep (tprf_fused.cuh): cluster size, rows per piece, chunks per panel, clusters
+  bool fused = false;
+  int fG = 0, fR = 0, fcpp = 0, fncl = 0;
   // workspace offsets (bytes)
   size_t o_zc, o_small, o_qp, o_s1, o_s2, o_w0, o_v, o_invsd, o_mun, o_bp, o_pxp, o_h0p, o_packed, o_sig, o_par, total;
   i64 packed_len;
 };
+
+static void carve(Plan3& p) {
+  const i64 T = p.T, batch = p.batch;
+  p.packed_len = T * (LP + 1) + NSMALL;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += al(bytes); return at; };
+  p.o_zc = take((size_t)batch * T * LP * 8);
+  p.o_small = take((size_t)batch * SMALL_PREP * 8);
+  p.o_qp = take((size_t)batch * p.rchunks * p.npad * LP * 8);
+  p.o_s1 = take((size_t)batch * p.rchunks * p.npad * 8);
+  p.o_s2 = take((size_t)batch * p.rchunks * p.npad * 8);
+  p.o_w0 = take((size_t)batch * p.npad * LP * 8);
+  p.o_v = take((size_t)batch * p.npad * LP * 8);
+  p.o_invsd = take((size_t)batch * p.npad * 8);
+  p.o_mun = take((size_t)batch * p.npad * 8);
+  p.o_bp = take((size_t)batch * p.cf_blocks * NSMALL * 8);
+  p.o_pxp = take((size_t)batch * p.cchunks * p.tpad * LP * 8);
+  p.o_h0p = take((size_t)batch * p.cchunks * p.tpad * 8);
+  p.o_packed = take((size_t)batch * p.packed_len * 8);
+  p.o_sig = take((size_t)batch * T * LP * 8);
+  p.o_par = take((size_t)batch * PARAMS * 8);
+  p.total = o;
+}
 
 static Plan3 make_plan(i64 T, i64 N, i64 L, i64 batch, int sms) {
   Plan3 p;
@@ -785,25 +813,26 @@ static Plan3 make_plan(i64 T, i64 N, i64 L, i64 batch, int sms) {
   if (cfb > 1024) cfb = 1024;
   if (cfb < 1) cfb = 1;
   p.cf_blocks = (int)cfb;
-  p.packed_len = T * (LP + 1) + NSMALL;
-  size_t o = 0;
-  auto take = [&](size_t bytes) { size_t at = o; o += al(bytes); return at; };
-  p.o_zc = take((size_t)batch * T * LP * 8);
-  p.o_small = take((size_t)batch * SMALL_PREP * 8);
-  p.o_qp = take((size_t)batch * p.rchunks * p.npad * LP * 8);
-  p.o_s1 = take((size_t)batch * p.rchunks * p.npad * 8);
-  p.o_s2 = take((size_t)batch * p.rchunks * p.npad * 8);
-  p.o_w0 = take((size_t)batch * p.npad * LP * 8);
-  p.o_v = take((size_t)batch * p.npad * LP * 8);
-  p.o_invsd = take((size_t)batch * p.npad * 8);
-  p.o_mun = take((size_t)batch * p.npad * 8);
-  p.o_bp = take((size_t)batch * p.cf_blocks * NSMALL * 8);
-  p.o_pxp = take((size_t)batch * p.cchunks * p.tpad * LP * 8);
-  p.o_h0p = take((size_t)batch * p.cchunks * p.tpad * 8);
-  p.o_packed = take((size_t)batch * p.packed_len * 8);
-  p.o_sig = take((size_t)batch * T * LP * 8);
-  p.o_par = take((size_t)batch * PARAMS * 8);
-  p.total = o;
+  carve(p);
+  return p;
+}
+
+static void plan_fused(Plan3& p, const double* X, i64 ldx, i64 x_bs);
+// plan for a panel resident at X: the fused single-read sweep when it applies, else two sweeps
+static Plan3 make_plan_for(i64 T, i64 N, i64 L, i64 batch, const double* X, i64 ldx, i64 x_bs) {
+  Plan3 p = make_plan(T, N, L, batch, ctx()->sm_count);
+  plan_fused(p, X, ldx, x_bs);
+  if (p.fused) {
+    // same workspace carving, with the fused sweep's partial counts: no row-chunk partials,
+    // one PX / h0 partial per chunk, one small-sum partial per (chunk, cluster rank)
+    Plan3 q = p;
+    q.rchunks = 0;
+    q.cchunks = p.fcpp;
+    q.tpad = (i64)p.fG * p.fR;
+    q.cf_blocks = p.fcpp * p.fG;
+    carve(q);
+    return q;
+  }
   return p;
 }
 
@@ -815,6 +844,118 @@ static int set_smem_attrs() {
   UM_CUDA(cudaFuncSetAttribute(k_tprf_project<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM));
   UM_CUDA(cudaFuncSetAttribute(k_tprf_project<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM));
   done = true;
+  return UM_OK;
+}
+
+// ---- path selection: 0 = auto (fused when it applies), 1 = two-sweep only, 2 = fused or fail ----
+static std::atomic<int> g_tprf_path{0};
+static long long* g_fused_dbg = nullptr;  // device buffer for clock stamps (um_tprf_debug_stamps)
+
+static int fused_clusters(int G, int R) {
+  // resident clusters of size G of the fused kernel (rows-per-piece variant R/128) on this device, cached
+  static int cache[5][fused::GMAX + 1] = {{0}};
+  static bool attr_done[5] = {false, false, false, false, false};
+  const int j = R / 128;
+  fused::FusedKernel kern = fused::kernel_for(R);
+  if (!attr_done[j]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::SMEM_ALLOC) != cudaSuccess ||
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    attr_done[j] = true;
+  }
+  if (cache[j][G]) return cache[j][G] > 0 ? cache[j][G] : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(G * 64), 1, 1);
+  cfg.blockDim = dim3(fused::NTHREADS, 1, 1);
+  cfg.dynamicSmemBytes = fused::SMEM_ALLOC;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cache[j][G] = n > 0 ? n : -1;
+  return n > 0 ? n : 0;
+}
+
+// decide whether the fused sweep applies to this panel; fill p.fused / fG / fR / fcpp / fncl
+static void plan_fused(Plan3& p, const double* X, i64 ldx, i64 x_bs) {
+  p.fused = false;
+  if (g_tprf_path.load() == 1) return;
+  if (!fused::encode_fn()) return;
+  if (!aligned16(X) || (ldx % 2) != 0 || (x_bs % 2) != 0 || ldx < p.N) return;
+  if (p.N >= (i64(1) << 31) || p.batch >= 65536) return;
+  int G = 0, R = 0;
+  fused::pick_shape(p.T, &G, &R);
+  if (!G) return;
+  const int ncl = fused_clusters(G, R);
+  if (ncl <= 0) return;
+  const i64 ntile = cdiv(p.N, fused::CW);
+  i64 cpp;
+  if (p.batch == 1) {
+    cpp = ntile < ncl ? ntile : ncl;
+  } else {
+    // chunks = batch * cpp go round-robin over the clusters: pick the smallest cpp that balances
+    cpp = 1;
+    while (cpp * 2 * 8 <= ntile) {
+      const i64 tot = p.batch * cpp;
+      const double eff = (double)tot / (double)(cdiv(tot, ncl) * ncl);
+      if (eff >= 0.95) break;
+      cpp *= 2;
+    }
+  }
+  if (cpp < 1) cpp = 1;
+  p.fused = true;
+  p.fG = G; p.fR = R; p.fcpp = (int)cpp; p.fncl = ncl;
+}
+
+static int run_fused(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_bs) {
+  cudaStream_t st = ctx()->stream;
+  fused::Args a;
+  a.T = p.T; a.N = p.N; a.npad = p.npad; a.tpad = p.tpad;
+  a.L = (int)p.L; a.G = p.fG; a.R = p.fR; a.batch = (int)p.batch; a.cpp = p.fcpp;
+  a.ntile = cdiv(p.N, fused::CW);
+  a.zc = reinterpret_cast<const double*>(ws + p.o_zc);
+  a.w0 = reinterpret_cast<double*>(ws + p.o_w0);
+  a.invsd = reinterpret_cast<double*>(ws + p.o_invsd);
+  a.mun = reinterpret_cast<double*>(ws + p.o_mun);
+  a.blockpart = reinterpret_cast<double*>(ws + p.o_bp);
+  a.pxp = reinterpret_cast<double*>(ws + p.o_pxp);
+  a.h0p = reinterpret_cast<double*>(ws + p.o_h0p);
+  a.dbg = g_fused_dbg;
+  CUtensorMap mx, m0;
+  const i64 bs = p.batch > 1 ? x_bs : p.T * ldx;
+  cuuint64_t dims[3] = {(cuuint64_t)p.N, (cuuint64_t)p.T, (cuuint64_t)p.batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ldx * 8, (cuuint64_t)bs * 8};
+  cuuint32_t es[3] = {1, 1, 1};
+  cuuint32_t box[3] = {(cuuint32_t)fused::CW, (cuuint32_t)fused::BOX_ROWS, 1};
+  cuuint32_t box0[3] = {(cuuint32_t)fused::CW, 1, 1};
+  fused::EncodeTiledFn enc = fused::encode_fn();
+  CUresult r1 = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(X), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r2 = enc(&m0, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(X), dims, strides, box0, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return fail(UM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+  i64 nclu = (i64)p.batch * p.fcpp;
+  if (nclu > p.fncl) nclu = p.fncl;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(nclu * p.fG), 1, 1);
+  cfg.blockDim = dim3(fused::NTHREADS, 1, 1);
+  cfg.dynamicSmemBytes = fused::SMEM_ALLOC;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)p.fG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  prof_begin(0);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, fused::kernel_for(p.fR), mx, m0, a);
+  prof_end(0);
+  if (e != cudaSuccess) return fail(UM_ERR_CUDA, "fused 3PRF sweep launch failed: %s", cudaGetErrorString(e));
+  UM_LAUNCHED();
   return UM_OK;
 }
 
@@ -835,6 +976,10 @@ static int run_sweeps(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_
   double* h0p = reinterpret_cast<double*>(ws + p.o_h0p);
   double* packed = reinterpret_cast<double*>(ws + p.o_packed);
   const bool vec16 = aligned16(X) && (ldx % 2 == 0) && (x_bs % 2 == 0);
+  if (p.fused) {
+    int s = run_fused(p, ws, X, ldx, x_bs);
+    if (s != UM_OK) return s;
+  } else {
   {
     dim3 grid((unsigned)p.strips, (unsigned)p.rchunks, (unsigned)p.batch);
     prof_begin(0);
@@ -857,6 +1002,7 @@ static int run_sweeps(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_
     else k_tprf_project<false><<<grid, C2_THREADS, C2_SMEM, st>>>(X, ldx, x_bs, v, invsd, p.T, p.N, p.npad, p.cols_per_chunk, p.tpad, pxp, h0p);
     prof_end(2);
     UM_LAUNCHED();
+  }
   }
   {
     i64 gx = cdiv(p.packed_len, 256);
@@ -930,6 +1076,27 @@ using namespace um;
 
 extern "C" {
 
+int32_t um_tprf_set_path(int32_t path) {
+  if (path < 0 || path > 2) return fail(UM_ERR_ARG, "3PRF path %d outside {0 auto, 1 two-sweep, 2 fused}", path);
+  g_tprf_path.store(path);
+  return UM_OK;
+}
+
+int32_t um_tprf_debug_stamps(long long* device_buf) {
+  g_fused_dbg = device_buf;
+  return UM_OK;
+}
+
+int32_t um_tprf_fused_info(int64_t T, int32_t* cluster_size, int32_t* rows_per_piece, int32_t* resident_clusters) {
+  UM_CTX();
+  int G = 0, R = 0;
+  fused::pick_shape(T, &G, &R);
+  if (cluster_size) *cluster_size = G;
+  if (rows_per_piece) *rows_per_piece = R;
+  if (resident_clusters) *resident_clusters = (G && fused::encode_fn()) ? fused_clusters(G, R) : 0;
+  return UM_OK;
+}
+
 int32_t um_tprf_work(int64_t T, int64_t N, int64_t L, double* flops, double* bytes) {
   // X'[Z] 2TNL, Xc W0 2TNL, row sums + stats ~6TN -> T*N*(4L+6); X read once = 8TN bytes
   if (flops) *flops = (double)T * (double)N * (4.0 * (double)L + 6.0);
@@ -960,32 +1127,21 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
     UM_CUDA(cudaStreamSynchronize(ctx()->stream));
     return UM_OK;
   }
-  // EXPERIMENT (L2 blocking): sweep the panel in column blocks small enough to stay L2-resident
-  // between the two sweeps of a block.  Per-column outputs are not valid in this mode.
-  i64 blk = 0;
-  if (const char* e = getenv("UM_TPRF_BLOCK_COLS")) blk = atoll(e);
-  if (blk > 0 && blk < N) blk = (blk / 64) * 64; else blk = 0;
-  Plan3 p = make_plan(T, blk ? blk : N, L, 1, ctx()->sm_count);
+  const double* xp = static_cast<const double*>(X->data) + X->offset;
+  const i64 ldx = N == 1 ? 1 : X->rs;
+  Plan3 p = make_plan_for(T, N, L, 1, xp, ldx, 0);
+  if (g_tprf_path.load() == 2 && !p.fused)
+    return fail(UM_ERR_ARG, "fused 3PRF sweep requested but not applicable (T = %lld > %d*%d rows, X not 16-byte aligned / odd row pitch, or no cluster launch)", T, fused::GMAX, fused::RMAX);
   char* ws = static_cast<char*>(scratch(p.total));
   if (!ws) return UM_ERR_OOM;
   int s = set_smem_attrs();
   if (s != UM_OK) return s;
   const double* yp = static_cast<const double*>(y->data) + y->offset;
   const double* zp = static_cast<const double*>(Z->data) + Z->offset;
-  const double* xp = static_cast<const double*>(X->data) + X->offset;
   s = run_prep(p, ws, zp, Z->rs, Z->cs, 0, yp, y->rs, 0);
   if (s != UM_OK) return s;
-  if (blk) {
-    for (i64 c0 = 0; c0 < N; c0 += blk) {
-      Plan3 pb = p;
-      pb.N = (c0 + blk <= N) ? blk : N - c0;
-      s = run_sweeps(pb, ws, xp + c0, X->rs, 0, c0 > 0);
-      if (s != UM_OK) return s;
-    }
-  } else {
-    s = run_sweeps(p, ws, xp, N == 1 ? 1 : X->rs, 0, 0);
-    if (s != UM_OK) return s;
-  }
+  s = run_sweeps(p, ws, xp, ldx, 0, 0);
+  if (s != UM_OK) return s;
   if (comm_active() && comm_world() > 1) {
     prof_begin(6);
     s = comm_allreduce_sum_f64_impl(reinterpret_cast<double*>(ws + p.o_packed), p.packed_len);
@@ -1013,7 +1169,7 @@ int32_t um_tprf_fit_batched(int32_t mode, const double* y, const double* X, cons
   UM_REQUIRE(T >= 1 && N >= 1 && batch >= 0, "bad panel shape");
   UM_REQUIRE(batch <= 65535, "batch %lld > 65535: split the call", (i64)batch);
   if (batch == 0) return UM_OK;
-  Plan3 p = make_plan(T, N, L, batch, ctx()->sm_count);
+  Plan3 p = make_plan_for(T, N, L, batch, X, N, T * N);
   char* ws = static_cast<char*>(scratch(p.total));
   if (!ws) return UM_ERR_OOM;
   int s = set_smem_attrs();
@@ -1042,7 +1198,7 @@ int32_t um_tprf_fit_host(int32_t mode, const double* y, const double* X, int64_t
   i64 CB = 8192;
   if (CB > N_local) CB = cdiv(N_local, 2) * 2;
   const i64 nblocks = cdiv(N_local, CB);
-  Plan3 p = make_plan(T, CB, L, 1, c.sm_count);
+  Plan3 p = make_plan_for(T, CB, L, 1, nullptr, CB, 0);  // staging buffers are 256-byte aligned
   const size_t stage_bytes = al((size_t)T * CB * 8);
   const size_t w0_all = al((size_t)N_local * LP * 8);  // keep every block's W0 for alpha
   const size_t yz_bytes = al((size_t)T * (L + 1) * 8) + al((size_t)T * 8);

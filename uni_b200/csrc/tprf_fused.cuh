@@ -1,0 +1,583 @@
+// tprf_fused.cuh -- the single-read 3PRF sweep (included by tprf.cu).
+//
+// The two-sweep path reads X twice because sweep 2 (PX = Xn W0) needs W0_j, which needs the whole of
+// column j.  Here a thread-block CLUSTER keeps a whole column tile (T rows x 16 columns) on chip: CTA
+// `rank` of the cluster owns rows [rank*R, rank*R + R) and pulls its (R x 16) piece with TMA
+// (SWIZZLE_128B boxes of 128 rows, one mbarrier per slot).  Per piece:
+//
+//   phase A  (8 compute warps)    Zc' x (DMMA m8n8k4, M = 8 columns, K = rows) + shifted sum / sum of
+//            squares straight out of shared memory; per-warp partials -> CTA partial -> pushed through
+//            DISTRIBUTED SHARED MEMORY to the CTA that owns the column (column c -> rank c % G),
+//            with `st.async` (the store itself completes transaction bytes on the owner's mbarrier).
+//   finalise (1 warp)            the owner adds the G partials in rank order, forms mu / sd / W0 / V,
+//            pushes V_j and 1/sd_j back to every CTA of the cluster (st.async again), writes W0 etc. for the per-column outputs and accumulates sw / SWW / smw / smu.
+//   phase B  (8 compute warps)    PX += x V, h0 += x / sd for the SAME piece, still in shared memory
+//            (DMMA, M = 8 rows, K = columns), accumulators live in registers for the whole kernel.
+//
+// Phase B of piece i runs after phase A of piece i+1, so the two DSMEM hops and the finalisation are
+// hidden behind a full piece of FP64 work; three 64 KiB slots keep one piece landing while two are in use.
+// X is read from HBM exactly once.  Everything is summed in a fixed order: results are reproducible.
+#pragma once
+#include <cuda.h>
+
+namespace um {
+namespace fused {
+
+constexpr int CW = 16;                       // columns per tile = one 128-byte swizzle row
+constexpr int NSLOT = 3;
+constexpr int RMAX = 512;                    // rows per piece (per CTA of the cluster)
+constexpr int SLOT_BYTES = RMAX * CW * 8;    // 65536
+constexpr int BOX_ROWS = 128;
+#ifndef UM_FUSED_NW
+#define UM_FUSED_NW 8
+#endif
+constexpr int NCW = UM_FUSED_NW;             // compute warps (R / NCW rows each, state in registers)
+constexpr int NCT = NCW * 32;                // compute threads
+constexpr int NTHREADS = NCT + 96;           // + TMA producer warp + finaliser warp + partial-reducer warp
+constexpr int NSTAT = 10;                    // per column: s1, s2, q[8]
+constexpr int NREC = 10;                     // per column record: V[8], 1/sd, pad
+constexpr int GMAX = 16;                     // largest cluster (non-portable size)
+
+constexpr int OFF_SLOTS = 0;
+constexpr int OFF_SCRATCH = NSLOT * SLOT_BYTES;                 // double[NCW][CW*NSTAT]
+constexpr int OFF_STAT = OFF_SCRATCH + NCW * CW * NSTAT * 8;    // double[2][CW*NSTAT]  ([owned col][src rank][NSTAT])
+constexpr int OFF_VREC = OFF_STAT + 2 * CW * NSTAT * 8;         // double[2][CW][NREC]
+constexpr int OFF_KSH = OFF_VREC + 2 * CW * NREC * 8;           // double[NSLOT][CW]   (row 0 of the panel: variance shift)
+constexpr int OFF_BAR = OFF_KSH + NSLOT * CW * 8;               // full[3] empty[3] statready[2] vready[2]
+constexpr int SMEM_BYTES = OFF_BAR + 16 * 8;
+constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;                   // slack to align the base to 1024 (swizzle atom)
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned sa(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(unsigned bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mb_arrive_remote(unsigned cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mb_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mb_wait_cluster(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(
+          bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ unsigned map_rank(unsigned local_addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_remote(unsigned cluster_addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(cluster_addr), "d"(v) : "memory");
+}
+// remote store that completes `8` transaction bytes on the destination CTA's mbarrier: the data is visible
+// to whoever observes that barrier phase complete -- no fence, no separate arrive
+__device__ __forceinline__ void st_async(unsigned cluster_addr, double v, unsigned cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(cluster_addr),
+               "l"(__double_as_longlong(v)), "r"(cluster_bar)
+               : "memory");
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_v2f64(unsigned addr, double a, double b) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void tma_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// named barriers between the compute warps and the reducer warp: 1 = scratch holds a piece's per-warp
+// partials, 2 = scratch may be overwritten
+__device__ __forceinline__ void bar_sync_n(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NCT + 32) : "memory"); }
+__device__ __forceinline__ void bar_arrive_n(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NCT + 32) : "memory"); }
+
+struct Args {
+  i64 T, N, npad, tpad;
+  int L, G, R;              // cluster size, rows per piece
+  int batch, cpp;           // panels, chunks per panel (a chunk = the tiles c, c + cpp, ... of one panel)
+  i64 ntile;                // column tiles per panel
+  const double* zc;         // [batch][T][8]
+  double* w0;               // [batch][npad][8]
+  double* invsd;            // [batch][npad]
+  double* mun;              // [batch][npad]
+  double* blockpart;        // [batch][cpp*G][81]
+  double* pxp;              // [batch][cpp][tpad][8]
+  double* h0p;              // [batch][cpp][tpad]
+  long long* dbg;           // optional: [rank][warp][iter][8] clock64 stamps of cluster 0 (profiling aid)
+};
+
+// logical column of the phase-A fragment row m (0..7) of m-tile 0; m-tile 1 is +4.  Chosen so the
+// 16 lanes of a half-warp touch 16 distinct 8-byte bank pairs under the 128-byte swizzle.
+__device__ __forceinline__ int col_of_m(int m) { return ((m & 2) << 2) | (m & 1) | ((m & 4) >> 1); }  // 0,1,8,9,2,3,10,11
+
+// pure (non-volatile) DMMA so the compiler may schedule it between the shared-memory loads
+__device__ __forceinline__ void f_dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int KS> struct KS_BATCH { static constexpr int v = (KS % 4 == 0) ? 4 : 2; };
+// J = R / 128: rows per piece; every compute warp owns R / NCW rows of the piece
+template <int J>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_row0, const Args g) {
+  constexpr int R = 128 * J;
+  constexpr int RW = R / NCW;      // rows per compute warp (multiple of 8)
+  constexpr int KB = KS_BATCH<RW / 4>::v;  // k-steps loaded per batch
+  constexpr int MB = (RW / 8) >= 2 ? 2 : 1;  // m-tiles loaded per batch
+  constexpr int KS = RW / 4;       // phase-A k-steps (4 rows each)
+  constexpr int MT = RW / 8;       // phase-B m-tiles (8 rows each)
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  double* scratch = reinterpret_cast<double*>(smem + OFF_SCRATCH);
+  double* statbuf = reinterpret_cast<double*>(smem + OFF_STAT);
+  double* vrec = reinterpret_cast<double*>(smem + OFF_VREC);
+  double* kshs = reinterpret_cast<double*>(smem + OFF_KSH);
+  const unsigned bar0 = sa(smem + OFF_BAR);
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (3 + s); };
+  auto bar_stat = [&](int b) { return bar0 + 8u * (6 + b); };
+  auto bar_vrdy = [&](int b) { return bar0 + 8u * (8 + b); };
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = g.G;
+  const int rank = (int)cluster_rank();
+  const int cl = blockIdx.x / G, ncl = gridDim.x / G;
+  const int owned = CW / G;
+  const i64 T = g.T;
+  const int nchunks = g.batch * g.cpp;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSLOT; ++s) {
+      mb_init(bar_full(s), 1);
+      mb_init(bar_empty(s), NCW);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mb_init(bar_stat(b), 1);   // armed per piece: expect_tx(CW * NSTAT doubles) = G sources x owned columns x NSTAT
+      mb_init(bar_vrdy(b), 1);   // armed per piece: expect_tx(CW * 9 doubles)     = 16 columns x (V[8], 1/sd)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();
+
+  if (warp == NCW) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      constexpr unsigned piece_bytes = (unsigned)R * CW * 8 + CW * 8;
+      int it = 0;
+      for (int ch = cl; ch < nchunks; ch += ncl) {
+        const int b = ch / g.cpp, cidx = ch % g.cpp;
+        for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
+          const int s = it % NSLOT;
+          if (it >= NSLOT) mb_wait(bar_empty(s), (unsigned)((it / NSLOT - 1) & 1));
+          mb_expect_tx(bar_full(s), piece_bytes);
+          const unsigned dst = sa(smem + OFF_SLOTS + (size_t)s * SLOT_BYTES);
+#pragma unroll
+          for (int bx = 0; bx < J; ++bx)
+            tma_3d(dst + bx * BOX_ROWS * CW * 8, &map_x, (int)(tile * CW), rank * R + bx * BOX_ROWS, b, bar_full(s));
+          tma_3d(sa(kshs + s * CW), &map_row0, (int)(tile * CW), 0, b, bar_full(s));
+        }
+      }
+    }
+  } else if (warp == NCW + 1) {
+    // ================= finaliser: owner of columns {oc*G + rank} =================
+    // 8 lanes (l = value index) per lane group; `sub` lane groups share one column and split its G
+    // source ranks (<= 4 each); up to 4 columns per round
+    const int lg = lane >> 3, l = lane & 7;
+    const int cpr = owned < 4 ? owned : 4;
+    const int sub = 4 / cpr;
+    const int cs = lg / sub, rs = lg % sub;
+    const int nr = G / sub;               // ranks this lane sums / pushes to: min(G, 4)
+    double a_sw = 0.0, a_smw = 0.0, a_smu = 0.0, a_sww[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a_sww[c] = 0.0;
+    const double dT = (double)T;
+    int it = 0;
+    for (int ch = cl; ch < nchunks; ch += ncl) {
+      const int b = ch / g.cpp, cidx = ch % g.cpp;
+      for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
+        const int buf = it & 1, s = it % NSLOT;
+        if (lane == 0) {
+          mb_expect_tx(bar_vrdy(buf), CW * 9 * 8);
+          mb_expect_tx(bar_stat(buf), CW * NSTAT * 8);
+        }
+        mb_wait(bar_stat(buf), (unsigned)((it >> 1) & 1));
+        const double* sb = statbuf + buf * CW * NSTAT;
+        for (int oc0 = 0; oc0 < owned; oc0 += cpr) {
+          const int oc = oc0 + cs;              // < owned always (owned is a multiple of cpr)
+          const int col = oc * G + rank;
+          double S = 0.0, SS = 0.0, q = 0.0;
+          {
+            double ps[4], pss[4], pq[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const bool on = r < nr;
+              const unsigned pa = sa(sb + (oc * G + rs * nr + (on ? r : 0)) * NSTAT);
+              ps[r] = on ? lds_f64(pa) : 0.0;
+              pss[r] = on ? lds_f64(pa + 8) : 0.0;
+              pq[r] = on ? lds_f64(pa + (2 + l) * 8) : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {  // rank order inside the lane, fixed tree across lane groups
+              S += ps[r];
+              SS += pss[r];
+              q += pq[r];
+            }
+            if (sub >= 2) {
+              S += __shfl_xor_sync(0xffffffffu, S, 8);
+              SS += __shfl_xor_sync(0xffffffffu, SS, 8);
+              q += __shfl_xor_sync(0xffffffffu, q, 8);
+            }
+            if (sub == 4) {
+              S += __shfl_xor_sync(0xffffffffu, S, 16);
+              SS += __shfl_xor_sync(0xffffffffu, SS, 16);
+              q += __shfl_xor_sync(0xffffffffu, q, 16);
+            }
+          }
+          const i64 gcol = tile * CW + col;
+          const bool valid = gcol < g.N;
+          const double k0 = lds_f64(sa(kshs + s * CW + col));
+          const double dm = S / dT;
+          const double mu = k0 + dm;
+          double sd = 1.0;
+          if (T > 1) {
+            double var = (SS - S * dm) / (double)(T - 1);
+            if (var < 0.0) var = 0.0;
+            sd = sqrt(var);
+            if (sd == 0.0) sd = 1.0;  // Tprf3.scala:493-501
+          }
+          const double inv = 1.0 / sd;
+          const double m_n = mu * inv;
+          const double w = q * inv;
+          const double v = w * inv;
+          // record of this column -> every CTA of the cluster; this lane serves ranks [rs*nr, rs*nr + nr)
+          {
+            const unsigned a_v = sa(vrec + (buf * CW + col) * NREC + l);
+            const unsigned a_i = sa(vrec + (buf * CW + col) * NREC + 8);
+            const unsigned a_b = bar_vrdy(buf);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              if (r < nr) {
+                const unsigned dstrank = (unsigned)(rs * nr + r);
+                const unsigned rb = map_rank(a_b, dstrank);
+                st_async(map_rank(a_v, dstrank), v, rb);
+                if (l == 0) st_async(map_rank(a_i, dstrank), inv, rb);
+              }
+            }
+          }
+          const bool mine = valid && rs == 0;   // one lane per (column, l) writes / accumulates
+          if (mine) {
+            const i64 cix = (i64)b * g.npad + gcol;
+            g.w0[cix * 8 + l] = w;
+            if (l == 0) {
+              g.invsd[cix] = inv;
+              g.mun[cix] = m_n;
+            }
+          }
+          const double wv = mine ? w : 0.0, mv = mine ? m_n : 0.0;
+          a_sw += wv;
+          a_smw += mv * wv;
+          if (l == 0) a_smu += mv;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const double wc = __shfl_sync(0xffffffffu, wv, (lane & 24) | c);
+            a_sww[c] += wv * wc;
+          }
+        }
+      }
+      // chunk done: flush the small sums of this (panel, chunk, rank); fixed order over the 4 lane groups
+      {
+        double vals[11];
+        vals[0] = a_sw; vals[9] = a_smw; vals[10] = a_smu;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) vals[1 + c] = a_sww[c];
+#pragma unroll
+        for (int i = 0; i < 11; ++i) {
+          double x0 = __shfl_sync(0xffffffffu, vals[i], l);
+          double x1 = __shfl_sync(0xffffffffu, vals[i], 8 + l);
+          double x2 = __shfl_sync(0xffffffffu, vals[i], 16 + l);
+          double x3 = __shfl_sync(0xffffffffu, vals[i], 24 + l);
+          vals[i] = ((x0 + x1) + x2) + x3;
+        }
+        if (lg == 0) {
+          double* bp = g.blockpart + ((i64)(b * g.cpp + cidx) * G + rank) * NSMALL;
+          bp[l] = vals[0];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) bp[8 + l * 8 + c] = vals[1 + c];
+          bp[72 + l] = vals[9];
+          if (l == 0) bp[80] = vals[10];
+        }
+        a_sw = a_smw = a_smu = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a_sww[c] = 0.0;
+      }
+    }
+  } else if (warp == NCW + 2) {
+    // ================= partial reducer: per-warp partials in `scratch` -> CTA partial -> owner CTA =================
+    bar_arrive_n(2);  // scratch starts free
+    int it = 0;
+    for (int ch = cl; ch < nchunks; ch += ncl) {
+      const int cidx = ch % g.cpp;
+      for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
+        const int buf = it & 1;
+        bar_sync_n(1);
+        double acc[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int e = lane + 32 * j;   // (column c, statistic v) = e / NSTAT, e % NSTAT
+          double part[NCW];
+#pragma unroll
+          for (int w = 0; w < NCW; ++w) part[w] = lds_f64(sa(scratch + w * CW * NSTAT + e));
+#pragma unroll
+          for (int st = 1; st < NCW; st *= 2)   // fixed pairwise tree
+#pragma unroll
+            for (int w = 0; w + st < NCW; w += 2 * st) part[w] += part[w + st];
+          acc[j] = part[0];
+        }
+        bar_arrive_n(2);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int e = lane + 32 * j;
+          const int c = e / NSTAT, v = e % NSTAT;
+          const int owner = c % G, oc = c / G;
+          const unsigned dst = sa(statbuf + buf * CW * NSTAT + (oc * G + rank) * NSTAT + v);
+          st_async(map_rank(dst, owner), acc[j], map_rank(bar_stat(buf), owner));
+        }
+      }
+    }
+  } else {
+    // ================= compute warps =================
+    const int rowbase = warp * RW;   // first local row of this warp (multiple of 16)
+    const int fm = lane >> 2, fk = lane & 3;
+    // phase A: lane (m = fm, k = fk) reads x[row 4ks + k][col_of_m(m) (+4)]
+    unsigned offa[2][2];
+    int cola[2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      cola[mt] = col_of_m(fm) + 4 * mt;
+#pragma unroll
+      for (int pb = 0; pb < 2; ++pb)
+        offa[mt][pb] = (unsigned)(((((cola[mt] >> 1) ^ (4 * pb + fk)) & 7) << 4) | ((cola[mt] & 1) << 3)) + (unsigned)(rowbase + 4 * pb + fk) * 128u;
+    }
+    // phase B: lane (g = fm, k = fk) reads the 16-byte chunk 4s + k of row rm of each 8-row m-tile
+    const int rm = (fm >> 1) + 4 * (fm & 1);
+    unsigned offb[2];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) offb[s2] = (unsigned)((((4 * s2 + fk) ^ rm) & 7) << 4) + (unsigned)(rowbase + rm) * 128u;
+
+    double px[MT][2], hh[MT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) px[i][0] = px[i][1] = hh[i] = 0.0;
+
+    const bool dbg_on = g.dbg != nullptr && cl == 0 && lane == 0;
+    auto stamp = [&](int iter, int slot_) {
+      if (dbg_on && iter < 64) g.dbg[(((i64)rank * 16 + warp) * 64 + iter) * 8 + slot_] = clock64();
+    };
+    const unsigned slots0 = sa(smem + OFF_SLOTS);
+
+    auto phase_b = [&](int itb) {
+      const int buf = itb & 1, s = itb % NSLOT;
+      mb_wait(bar_vrdy(buf), (unsigned)((itb >> 1) & 1));
+      stamp(itb + 1, 5);
+      const unsigned vr = sa(vrec + buf * CW * NREC);
+      double vf[2][2], isd[2][2];
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = 8 * s2 + 2 * fk + e;
+          vf[s2][e] = lds_f64(vr + (c * NREC + fm) * 8);
+          isd[s2][e] = lds_f64(vr + (c * NREC + 8) * 8);
+        }
+      const unsigned slot = slots0 + (unsigned)s * SLOT_BYTES;
+#pragma unroll
+#pragma unroll
+      for (int m0 = 0; m0 < MT; m0 += MB) {
+        double2 x[MB][2];
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) x[i][s2] = lds_v2f64(slot + offb[s2] + (unsigned)(m0 + i) * 1024u);
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            f_dmma(px[m0 + i][0], px[m0 + i][1], x[i][s2].x, vf[s2][0]);
+            f_dmma(px[m0 + i][0], px[m0 + i][1], x[i][s2].y, vf[s2][1]);
+            hh[m0 + i] = fma(x[i][s2].x, isd[s2][0], hh[m0 + i]);
+            hh[m0 + i] = fma(x[i][s2].y, isd[s2][1], hh[m0 + i]);
+          }
+      }
+      __syncwarp();
+      if (lane == 0) mb_arrive(bar_empty(s));
+    };
+
+    int it = 0;
+    for (int ch = cl; ch < nchunks; ch += ncl) {
+      const int b = ch / g.cpp, cidx = ch % g.cpp;
+      // Zc fragments of this warp's rows (B operand of phase A): lane holds zc[row 4ks + k][l = fm]
+      double zf[KS];
+      const i64 grow0 = (i64)rank * R + rowbase;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const i64 t = grow0 + 4 * ks + fk;
+        zf[ks] = t < T ? g.zc[((i64)b * T + t) * 8 + fm] : 0.0;
+      }
+      const i64 tv = T - grow0 - fk;                 // row 4ks + k is inside the panel iff 4ks < tv
+      const int tvalid = tv > 64 ? 64 : (tv < 0 ? 0 : (int)tv);
+      const bool need_mask = grow0 + RW > T;
+      const int it_first = it;
+      for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
+        const int s = it % NSLOT;
+        stamp(it, 0);
+        mb_wait(bar_full(s), (unsigned)((it / NSLOT) & 1));
+        stamp(it, 1);
+        const unsigned slot = slots0 + (unsigned)s * SLOT_BYTES;
+        double q[2][2][2], s1[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, s2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int pb = 0; pb < 2; ++pb) q[mt][pb][0] = q[mt][pb][1] = 0.0;
+        double ksh[2];
+        ksh[0] = lds_f64(sa(kshs + s * CW + cola[0]));
+        ksh[1] = lds_f64(sa(kshs + s * CW + cola[1]));
+#pragma unroll
+        for (int kb = 0; kb < KS; kb += KB) {
+          double a[KB][2];
+#pragma unroll
+          for (int i = 0; i < KB; ++i)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) a[i][mt] = lds_f64(slot + offa[mt][i & 1] + (unsigned)(kb + (i & ~1)) * 512u);
+#pragma unroll
+          for (int i = 0; i < KB; ++i)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              f_dmma(q[mt][i & 1][0], q[mt][i & 1][1], a[i][mt], zf[kb + i]);
+              double d = a[i][mt] - ksh[mt];
+              if (need_mask && 4 * (kb + i) >= tvalid) d = 0.0;
+              s1[mt][i & 1] += d;
+              s2[mt][i & 1] = fma(d, d, s2[mt][i & 1]);
+            }
+        }
+        double t1[2], t2[2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          t1[mt] = s1[mt][0] + s1[mt][1];
+          t2[mt] = s2[mt][0] + s2[mt][1];
+          t1[mt] += __shfl_xor_sync(0xffffffffu, t1[mt], 1);
+          t2[mt] += __shfl_xor_sync(0xffffffffu, t2[mt], 1);
+          t1[mt] += __shfl_xor_sync(0xffffffffu, t1[mt], 2);
+          t2[mt] += __shfl_xor_sync(0xffffffffu, t2[mt], 2);
+        }
+        stamp(it, 2);
+        bar_sync_n(2);  // the reducer is done with the previous piece's partials
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const unsigned sp = sa(scratch + (warp * CW + cola[mt]) * NSTAT);
+          sts_v2f64(sp + (2 + 2 * fk) * 8, q[mt][0][0] + q[mt][1][0], q[mt][0][1] + q[mt][1][1]);
+          if (fk == 0) sts_v2f64(sp, t1[mt], t2[mt]);
+        }
+        bar_arrive_n(1);
+        stamp(it, 3);
+        stamp(it, 4);
+        if (it > it_first) phase_b(it - 1);
+        stamp(it, 6);
+      }
+      if (it > it_first) phase_b(it - 1);
+      // flush this chunk's PX / h0 partial
+      {
+        double* pxo = g.pxp + ((i64)(b * g.cpp + cidx) * g.tpad) * 8;
+        double* h0o = g.h0p + (i64)(b * g.cpp + cidx) * g.tpad;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          double h = hh[mt];
+          h += __shfl_xor_sync(0xffffffffu, h, 1);
+          h += __shfl_xor_sync(0xffffffffu, h, 2);
+          const i64 t = grow0 + mt * 8 + rm;
+          if (t < T) {
+            *reinterpret_cast<double2*>(pxo + t * 8 + 2 * fk) = make_double2(px[mt][0], px[mt][1]);
+            if (fk == 0) h0o[t] = h;
+          }
+          px[mt][0] = px[mt][1] = hh[mt] = 0.0;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves while a peer may still write into its shared memory
+}
+
+typedef void (*FusedKernel)(const CUtensorMap, const CUtensorMap, const Args);
+inline FusedKernel kernel_for(int R) {
+  switch (R / 128) {
+    case 1: return k_tprf_fused<1>;
+    case 2: return k_tprf_fused<2>;
+    case 3: return k_tprf_fused<3>;
+    default: return k_tprf_fused<4>;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// cluster size / rows per piece for a T-row panel; G == 0: the fused sweep does not apply
+inline void pick_shape(i64 T, int* G, int* R) {
+  *G = 0; *R = 0;
+  for (int gsz = 1; gsz <= GMAX; gsz *= 2) {
+    i64 rows = (T + gsz - 1) / gsz;
+    if (rows <= RMAX) {
+      *G = gsz;
+      *R = (int)((rows + BOX_ROWS - 1) / BOX_ROWS) * BOX_ROWS;
+      return;
+    }
+  }
+}
+
+}  // namespace fused
+}  // namespace um

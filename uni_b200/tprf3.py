@@ -95,3 +95,12 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
 def forecast3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full") -> Mat:
     """Tprf3.forecast3prf (Tprf3.scala:1290-1299)."""
     return estimate3prf(y, X, Z, procedure).forecasts
+
+
+TPRF_PATH_AUTO, TPRF_PATH_TWO_SWEEP, TPRF_PATH_FUSED = 0, 1, 2
+
+
+def set_tprf_path(path: int) -> None:
+    """0 = auto (single-read cluster sweep whenever it applies), 1 = two sweeps only, 2 = single-read
+    sweep or ValueError.  Process-wide switch for tests and profiling (um_tprf_set_path)."""
+    check(lib.um_tprf_set_path(int(path)))
