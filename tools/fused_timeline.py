@@ -29,21 +29,29 @@ u.tprfClosedForm(dy, dX, dZ)
 u.sync()
 check(lib.um_tprf_debug_stamps(None))
 st = buf.to_numpy().view(np.int64).reshape(16, 16, 64, 8)
-names = ["iter start", "full landed", "A done", "bar1+scratch+bar2", "reduce+push done", "vready seen", "B done"]
 g_ = C.c_int32(); r_ = C.c_int32(); n_ = C.c_int32()
 check(lib.um_tprf_fused_info(T, C.byref(g_), C.byref(r_), C.byref(n_)))
 G = g_.value
 print(f"T={T} N={N}: cluster {G} x {r_.value} rows, {n_.value} resident clusters")
 for rank in sorted({0, G - 1}):
-    for warp in (0, 15):
+    for warp, (a, b, c, nm) in ((0, (0, 1, 2, "A")), (3, (0, 1, 2, "A")), (4, (3, 4, 5, "B")), (7, (3, 4, 5, "B"))):
         s = st[rank, warp]
-        its = [i for i in range(8, 40) if s[i, 0] and s[i + 1, 0]]
+        its = [i for i in range(8, 40) if s[i, a] and s[i + 1, a]]
         if not its:
             continue
-        per = np.mean([s[i + 1, 0] - s[i, 0] for i in its])
-        segs = []
-        for k in range(1, 7):
-            d = [s[i, k] - s[i, k - 1] for i in its if s[i, k] and s[i, k - 1]]
-            segs.append(np.mean(d) if d else float("nan"))
-        print(f"rank {rank:2d} warp {warp:2d}: {per:7.0f} clk/piece | wait full {segs[0]:6.0f} | A {segs[1]:6.0f} | bars {segs[2]:6.0f} | "
-              f"reduce+push {segs[3]:6.0f} | wait vready {segs[4]:6.0f} | B {segs[5]:6.0f}")
+        per = np.mean([s[i + 1, a] - s[i, a] for i in its])
+        wait = np.mean([s[i, b] - s[i, a] for i in its])
+        work = np.mean([s[i, c] - s[i, b] for i in its])
+        lag = np.mean([st[rank, 4, i, 5] - st[rank, 0, i, 2] for i in its]) if nm == "A" else float("nan")
+        print(f"rank {rank:2d} warp {warp:2d} ({nm}): {per:7.0f} clk/piece | wait {wait:6.0f} | phase {nm} {work:6.0f}" +
+              (f" | end of A(i) -> end of B(i): {lag:6.0f}" if nm == "A" else ""))
+
+# exchange chain of piece i on rank 0, relative to the end of A(i) on A-warp 0
+r = 0
+its = [i for i in range(8, 40)]
+ref = st[r, 0, :, 2]
+def rel(w, k):
+    return np.mean([st[r, w, i, k] - ref[i] for i in its])
+slowA = np.mean([max(st[r, w, i, 2] for w in range(4)) - ref[i] for i in its])
+print(f"rank 0, relative to end of A(i) on warp 0: last A-warp done {slowA:6.0f} | reducer sees scratch {rel(10, 1):6.0f} | reducer pushed {rel(10, 2):6.0f} | finaliser sees all partials {rel(9, 1):6.0f} | "
+      f"finaliser pushed {rel(9, 2):6.0f} | B-warp sees records {rel(4, 4):6.0f} | B done {rel(4, 5):6.0f}")

@@ -3,20 +3,26 @@
 // The two-sweep path reads X twice because sweep 2 (PX = Xn W0) needs W0_j, which needs the whole of
 // column j.  Here a thread-block CLUSTER keeps a whole column tile (T rows x 16 columns) on chip: CTA
 // `rank` of the cluster owns rows [rank*R, rank*R + R) and pulls its (R x 16) piece with TMA
-// (SWIZZLE_128B boxes of 128 rows, one mbarrier per slot).  Per piece:
+// (SWIZZLE_128B boxes of 128 rows, one mbarrier per slot, three 64 KiB slots).  Warp roles per CTA:
 //
-//   phase A  (8 compute warps)    Zc' x (DMMA m8n8k4, M = 8 columns, K = rows) + shifted sum / sum of
-//            squares straight out of shared memory; per-warp partials -> CTA partial -> pushed through
-//            DISTRIBUTED SHARED MEMORY to the CTA that owns the column (column c -> rank c % G),
-//            with `st.async` (the store itself completes transaction bytes on the owner's mbarrier).
-//   finalise (1 warp)            the owner adds the G partials in rank order, forms mu / sd / W0 / V,
-//            pushes V_j and 1/sd_j back to every CTA of the cluster (st.async again), writes W0 etc. for the per-column outputs and accumulates sw / SWW / smw / smu.
-//   phase B  (8 compute warps)    PX += x V, h0 += x / sd for the SAME piece, still in shared memory
-//            (DMMA, M = 8 rows, K = columns), accumulators live in registers for the whole kernel.
+//   A-warps 0-3   phase A of piece i: Zc' x (DMMA m8n8k4, M = 8 columns, K = rows) + shifted sum / sum of
+//                 squares straight out of shared memory; per-lane partials go to `scratch`.
+//   B-warps 4-7   phase B of piece i (one or two pieces behind the A-warps): PX += x V, h0 += x / sd
+//                 from the SAME shared-memory slot (DMMA, M = 8 rows, K = columns); the accumulators
+//                 stay in registers for the whole kernel.  A-warp a and B-warp 4+a share an SM
+//                 sub-partition, so its FP64 pipe always has a warp in each phase to draw from.
+//   warp 8        TMA producer (one lane).
+//   warp 9        finaliser: owner of column c (rank c % G) adds the G CTA partials in a fixed tree, forms
+//                 mu / sd / W0 / V, pushes V_c and 1/sd_c to every CTA of the cluster, writes W0 etc. for
+//                 the per-column outputs and accumulates sw / SWW / smw / smu.
+//   warp 10       reducer: per-lane partials in `scratch` -> CTA partial -> owner CTA (few, larger DSMEM
+//                 messages: 8-byte remote stores are expensive, 160 per piece instead of 1024).
 //
-// Phase B of piece i runs after phase A of piece i+1, so the two DSMEM hops and the finalisation are
-// hidden behind a full piece of FP64 work; three 64 KiB slots keep one piece landing while two are in use.
-// X is read from HBM exactly once.  Everything is summed in a fixed order: results are reproducible.
+// All cross-CTA traffic is DISTRIBUTED SHARED MEMORY written with `st.async`: the store itself completes
+// transaction bytes on the destination CTA's mbarrier, so there are no fences, no cluster barriers and no
+// polling in the steady state.  Every hand-off inside a CTA is an mbarrier as well; warps never wait for
+// each other except through the data they need.  X is read from HBM exactly once; every sum has a fixed
+// order, so results are reproducible run to run.
 #pragma once
 #include <cuda.h>
 
@@ -28,22 +34,20 @@ constexpr int NSLOT = 3;
 constexpr int RMAX = 512;                    // rows per piece (per CTA of the cluster)
 constexpr int SLOT_BYTES = RMAX * CW * 8;    // 65536
 constexpr int BOX_ROWS = 128;
-#ifndef UM_FUSED_NW
-#define UM_FUSED_NW 8
-#endif
-constexpr int NCW = UM_FUSED_NW;             // compute warps (R / NCW rows each, state in registers)
-constexpr int NCT = NCW * 32;                // compute threads
-constexpr int NTHREADS = NCT + 96;           // + TMA producer warp + finaliser warp + partial-reducer warp
+constexpr int NAW = 4;                       // A-warps (= B-warps): one of each per SM sub-partition
+constexpr int NTHREADS = (2 * NAW + 3) * 32; // + TMA producer, finaliser, reducer
 constexpr int NSTAT = 10;                    // per column: s1, s2, q[8]
 constexpr int NREC = 10;                     // per column record: V[8], 1/sd, pad
 constexpr int GMAX = 16;                     // largest cluster (non-portable size)
+constexpr int SCR_W = 256;                   // scratch doubles per A-warp: q[16][8] | s1[16][4] | s2[16][4]
+constexpr int STAT_SLOT = CW * NSTAT;        // doubles per slot of the partial buffer: [owned col][src rank][NSTAT]
 
 constexpr int OFF_SLOTS = 0;
-constexpr int OFF_SCRATCH = NSLOT * SLOT_BYTES;                 // double[NCW][CW*NSTAT]
-constexpr int OFF_STAT = OFF_SCRATCH + NCW * CW * NSTAT * 8;    // double[2][CW*NSTAT]  ([owned col][src rank][NSTAT])
-constexpr int OFF_VREC = OFF_STAT + 2 * CW * NSTAT * 8;         // double[2][CW][NREC]
-constexpr int OFF_KSH = OFF_VREC + 2 * CW * NREC * 8;           // double[NSLOT][CW]   (row 0 of the panel: variance shift)
-constexpr int OFF_BAR = OFF_KSH + NSLOT * CW * 8;               // full[3] empty[3] statready[2] vready[2]
+constexpr int OFF_SCRATCH = NSLOT * SLOT_BYTES;                 // double[NAW][SCR_W]
+constexpr int OFF_STAT = OFF_SCRATCH + NAW * SCR_W * 8;         // double[NSLOT][STAT_SLOT]
+constexpr int OFF_VREC = OFF_STAT + NSLOT * STAT_SLOT * 8;      // double[NSLOT][CW][NREC]
+constexpr int OFF_KSH = OFF_VREC + NSLOT * CW * NREC * 8;       // double[NSLOT][CW]   (row 0 of the panel: variance shift)
+constexpr int OFF_BAR = OFF_KSH + NSLOT * CW * 8;               // full[3] empty[3] statready[3] vready[3] scr_full scr_free
 constexpr int SMEM_BYTES = OFF_BAR + 16 * 8;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;                   // slack to align the base to 1024 (swizzle atom)
 
@@ -89,6 +93,30 @@ __device__ __forceinline__ void st_async(unsigned cluster_addr, double v, unsign
                "l"(__double_as_longlong(v)), "r"(cluster_bar)
                : "memory");
 }
+// mbarrier wait that also yields a zero the compiler cannot see through: adding it to a shared-memory
+// address makes the (pure, freely schedulable) loads below data-dependent on the wait
+__device__ __forceinline__ unsigned mb_wait_token(unsigned bar, unsigned parity) {
+  unsigned tok;
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\nmov.u32 %0, 0;\n}"
+      : "=r"(tok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return tok;
+}
+// pure loads of the piece: schedulable between the DMMAs; ordered after the wait through the token and
+// before the slot is released through `consume`
+__device__ __forceinline__ double ldp_f64(unsigned addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double2 ldp_v2f64(unsigned addr) {
+  double2 v;
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void consume(double v) { asm volatile("" ::"d"(v) : "memory"); }
 __device__ __forceinline__ double lds_f64(unsigned addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -117,10 +145,6 @@ __device__ __forceinline__ unsigned cluster_rank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
-// named barriers between the compute warps and the reducer warp: 1 = scratch holds a piece's per-warp
-// partials, 2 = scratch may be overwritten
-__device__ __forceinline__ void bar_sync_n(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NCT + 32) : "memory"); }
-__device__ __forceinline__ void bar_arrive_n(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NCT + 32) : "memory"); }
 
 struct Args {
   i64 T, N, npad, tpad;
@@ -146,15 +170,12 @@ __device__ __forceinline__ void f_dmma(double& c0, double& c1, double a, double 
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <int KS> struct KS_BATCH { static constexpr int v = (KS % 4 == 0) ? 4 : 2; };
-// J = R / 128: rows per piece; every compute warp owns R / NCW rows of the piece
+// J = R / 128 (rows per piece); each A-warp and each B-warp owns R / 4 = 32*J rows of the piece
 template <int J>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_row0, const Args g) {
   constexpr int R = 128 * J;
-  constexpr int RW = R / NCW;      // rows per compute warp (multiple of 8)
-  constexpr int KB = KS_BATCH<RW / 4>::v;  // k-steps loaded per batch
-  constexpr int MB = (RW / 8) >= 2 ? 2 : 1;  // m-tiles loaded per batch
+  constexpr int RW = R / NAW;      // rows per A-/B-warp: 32, 64, 96 or 128
   constexpr int KS = RW / 4;       // phase-A k-steps (4 rows each)
   constexpr int MT = RW / 8;       // phase-B m-tiles (8 rows each)
   extern __shared__ unsigned char smem_raw[];
@@ -164,10 +185,11 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   double* vrec = reinterpret_cast<double*>(smem + OFF_VREC);
   double* kshs = reinterpret_cast<double*>(smem + OFF_KSH);
   const unsigned bar0 = sa(smem + OFF_BAR);
-  auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (3 + s); };
-  auto bar_stat = [&](int b) { return bar0 + 8u * (6 + b); };
-  auto bar_vrdy = [&](int b) { return bar0 + 8u * (8 + b); };
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };          // TMA landed the piece in slot s
+  auto bar_empty = [&](int s) { return bar0 + 8u * (3 + s); };   // the B-warps are done with slot s
+  auto bar_stat = [&](int s) { return bar0 + 8u * (6 + s); };    // every CTA's partials of my columns arrived
+  auto bar_vrdy = [&](int s) { return bar0 + 8u * (9 + s); };    // every column's record arrived
+  const unsigned bar_scr_full = bar0 + 8u * 12, bar_scr_free = bar0 + 8u * 13;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = g.G;
@@ -180,18 +202,173 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) {
       mb_init(bar_full(s), 1);
-      mb_init(bar_empty(s), NCW);
+      mb_init(bar_empty(s), NAW);
+      mb_init(bar_stat(s), 1);   // armed per piece: expect_tx(STAT_SLOT doubles) = owned columns x G ranks x NSTAT
+      mb_init(bar_vrdy(s), 1);   // armed per piece: expect_tx(CW * 9 doubles)     = 16 columns x (V[8], 1/sd)
     }
-    for (int b = 0; b < 2; ++b) {
-      mb_init(bar_stat(b), 1);   // armed per piece: expect_tx(CW * NSTAT doubles) = G sources x owned columns x NSTAT
-      mb_init(bar_vrdy(b), 1);   // armed per piece: expect_tx(CW * 9 doubles)     = 16 columns x (V[8], 1/sd)
-    }
+    mb_init(bar_scr_full, NAW);
+    mb_init(bar_scr_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   cluster_sync_all();
 
-  if (warp == NCW) {
+  const bool dbg_on = g.dbg != nullptr && cl == 0 && lane == 0;
+  auto stamp = [&](int iter, int slot_) {
+    if (dbg_on && iter < 64) g.dbg[(((i64)rank * 16 + warp) * 64 + iter) * 8 + slot_] = clock64();
+  };
+  const unsigned slots0 = sa(smem + OFF_SLOTS);
+  const int fm = lane >> 2, fk = lane & 3;
+
+  if (warp < NAW) {
+    // ================= A-warps: column statistics of piece `it` =================
+    const int rowbase = warp * RW;   // first local row of this warp (multiple of 32)
+    // lane (m = fm, k = fk) reads x[row 4ks + k][col_of_m(m) (+4)]
+    unsigned offa[2][2];
+    int cola[2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      cola[mt] = col_of_m(fm) + 4 * mt;
+#pragma unroll
+      for (int pb = 0; pb < 2; ++pb)
+        offa[mt][pb] = (unsigned)(((((cola[mt] >> 1) ^ (4 * pb + fk)) & 7) << 4) | ((cola[mt] & 1) << 3)) + (unsigned)(rowbase + 4 * pb + fk) * 128u;
+    }
+    int it = 0;
+    for (int ch = cl; ch < nchunks; ch += ncl) {
+      const int b = ch / g.cpp, cidx = ch % g.cpp;
+      // Zc fragments of this warp's rows (B operand): lane holds zc[row 4ks + k][l = fm]
+      double zf[KS];
+      const i64 grow0 = (i64)rank * R + rowbase;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const i64 t = grow0 + 4 * ks + fk;
+        zf[ks] = t < T ? g.zc[((i64)b * T + t) * 8 + fm] : 0.0;
+      }
+      const i64 tv = T - grow0 - fk;                 // row 4ks + k is inside the panel iff 4ks < tv
+      const int tvalid = tv > RW ? RW : (tv < 0 ? 0 : (int)tv);
+      const bool need_mask = grow0 + RW > T;
+      for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
+        const int s = it % NSLOT;
+        stamp(it, 0);
+        const unsigned tokf = mb_wait_token(bar_full(s), (unsigned)((it / NSLOT) & 1));
+        stamp(it, 1);
+        const unsigned slot = slots0 + (unsigned)s * SLOT_BYTES + tokf;
+        double q[2][2][2], s1[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, s2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int pb = 0; pb < 2; ++pb) q[mt][pb][0] = q[mt][pb][1] = 0.0;
+        double ksh[2];
+        ksh[0] = ldp_f64(sa(kshs + s * CW + cola[0]) + tokf);
+        ksh[1] = ldp_f64(sa(kshs + s * CW + cola[1]) + tokf);
+#pragma unroll
+        for (int kb = 0; kb < KS; kb += 4) {
+          double a[4][2];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) a[i][mt] = ldp_f64(slot + offa[mt][i & 1] + (unsigned)(kb + (i & ~1)) * 512u);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              f_dmma(q[mt][i & 1][0], q[mt][i & 1][1], a[i][mt], zf[kb + i]);
+              double d = a[i][mt] - ksh[mt];
+              if (need_mask && 4 * (kb + i) >= tvalid) d = 0.0;
+              s1[mt][i & 1] += d;
+              s2[mt][i & 1] = fma(d, d, s2[mt][i & 1]);
+            }
+        }
+        // per-lane partials -> scratch (the reducer adds the 4 row phases and the 4 A-warps)
+        mb_wait(bar_scr_free, (unsigned)((it & 1) ^ 1));  // the reducer is done with piece it-1 (passes at once for it = 0)
+        {
+          const unsigned sp = sa(scratch + warp * SCR_W);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            sts_v2f64(sp + (cola[mt] * 8 + 2 * fk) * 8, q[mt][0][0] + q[mt][1][0], q[mt][0][1] + q[mt][1][1]);
+            sts_f64(sp + (128 + cola[mt] * 4 + fk) * 8, s1[mt][0] + s1[mt][1]);
+            sts_f64(sp + (192 + cola[mt] * 4 + fk) * 8, s2[mt][0] + s2[mt][1]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mb_arrive(bar_scr_full);
+        stamp(it, 2);
+      }
+    }
+  } else if (warp < 2 * NAW) {
+    // ================= B-warps: PX / h0 of piece `it`, once every column's record is here =================
+    const int bw = warp - NAW;
+    const int rowbase = bw * RW;
+    // lane (g = fm, k = fk) reads the 16-byte chunk 4s + k of row rm of each 8-row m-tile
+    const int rm = (fm >> 1) + 4 * (fm & 1);
+    unsigned offb[2];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) offb[s2] = (unsigned)((((4 * s2 + fk) ^ rm) & 7) << 4) + (unsigned)(rowbase + rm) * 128u;
+    double px[MT][2], hh[MT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) px[i][0] = px[i][1] = hh[i] = 0.0;
+    int it = 0;
+    for (int ch = cl; ch < nchunks; ch += ncl) {
+      const int b = ch / g.cpp, cidx = ch % g.cpp;
+      const i64 grow0 = (i64)rank * R + rowbase;
+      for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
+        const int s = it % NSLOT;
+        stamp(it, 3);
+        const unsigned tokv = mb_wait_token(bar_vrdy(s), (unsigned)((it / NSLOT) & 1));
+        stamp(it, 4);
+        const unsigned vr = sa(vrec + s * CW * NREC) + tokv;
+        double vf[2][2], isd[2][2];
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 8 * s2 + 2 * fk + e;
+            vf[s2][e] = ldp_f64(vr + (c * NREC + fm) * 8);
+            isd[s2][e] = ldp_f64(vr + (c * NREC + 8) * 8);
+          }
+        const unsigned slot = slots0 + (unsigned)s * SLOT_BYTES + tokv;
+#pragma unroll
+        for (int m0 = 0; m0 < MT; m0 += 2) {
+          double2 x[2][2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) x[i][s2] = ldp_v2f64(slot + offb[s2] + (unsigned)(m0 + i) * 1024u);
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+              f_dmma(px[m0 + i][0], px[m0 + i][1], x[i][s2].x, vf[s2][0]);
+              f_dmma(px[m0 + i][0], px[m0 + i][1], x[i][s2].y, vf[s2][1]);
+              hh[m0 + i] = fma(x[i][s2].x, isd[s2][0], hh[m0 + i]);
+              hh[m0 + i] = fma(x[i][s2].y, isd[s2][1], hh[m0 + i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MT; ++i) consume(px[i][0]);   // every load of the slot has landed in a register
+        __syncwarp();
+        if (lane == 0) mb_arrive(bar_empty(s));
+        stamp(it, 5);
+      }
+      // flush this chunk's PX / h0 partial
+      {
+        double* pxo = g.pxp + ((i64)(b * g.cpp + cidx) * g.tpad) * 8;
+        double* h0o = g.h0p + (i64)(b * g.cpp + cidx) * g.tpad;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          double h = hh[mt];
+          h += __shfl_xor_sync(0xffffffffu, h, 1);
+          h += __shfl_xor_sync(0xffffffffu, h, 2);
+          const i64 t = grow0 + mt * 8 + rm;
+          if (t < T) {
+            *reinterpret_cast<double2*>(pxo + t * 8 + 2 * fk) = make_double2(px[mt][0], px[mt][1]);
+            if (fk == 0) h0o[t] = h;
+          }
+          px[mt][0] = px[mt][1] = hh[mt] = 0.0;
+        }
+      }
+    }
+  } else if (warp == 2 * NAW) {
     // ================= TMA producer =================
     if (lane == 0) {
       constexpr unsigned piece_bytes = (unsigned)R * CW * 8 + CW * 8;
@@ -202,7 +379,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
           const int s = it % NSLOT;
           if (it >= NSLOT) mb_wait(bar_empty(s), (unsigned)((it / NSLOT - 1) & 1));
           mb_expect_tx(bar_full(s), piece_bytes);
-          const unsigned dst = sa(smem + OFF_SLOTS + (size_t)s * SLOT_BYTES);
+          const unsigned dst = slots0 + (unsigned)s * SLOT_BYTES;
 #pragma unroll
           for (int bx = 0; bx < J; ++bx)
             tma_3d(dst + bx * BOX_ROWS * CW * 8, &map_x, (int)(tile * CW), rank * R + bx * BOX_ROWS, b, bar_full(s));
@@ -210,7 +387,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == NCW + 1) {
+  } else if (warp == 2 * NAW + 1) {
     // ================= finaliser: owner of columns {oc*G + rank} =================
     // 8 lanes (l = value index) per lane group; `sub` lane groups share one column and split its G
     // source ranks (<= 4 each); up to 4 columns per round
@@ -219,41 +396,48 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
     const int sub = 4 / cpr;
     const int cs = lg / sub, rs = lg % sub;
     const int nr = G / sub;               // ranks this lane sums / pushes to: min(G, 4)
+    unsigned rvrec[4], rvbar[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const unsigned dstrank = (unsigned)(rs * nr + (r < nr ? r : 0));
+      rvrec[r] = map_rank(sa(vrec), dstrank);
+      rvbar[r] = map_rank(bar_vrdy(0), dstrank);
+    }
     double a_sw = 0.0, a_smw = 0.0, a_smu = 0.0, a_sww[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) a_sww[c] = 0.0;
-    const double dT = (double)T;
+    const double invT = 1.0 / (double)T, invTm1 = T > 1 ? 1.0 / (double)(T - 1) : 0.0;
     int it = 0;
     for (int ch = cl; ch < nchunks; ch += ncl) {
       const int b = ch / g.cpp, cidx = ch % g.cpp;
       for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
-        const int buf = it & 1, s = it % NSLOT;
+        const int s = it % NSLOT;
         if (lane == 0) {
-          mb_expect_tx(bar_vrdy(buf), CW * 9 * 8);
-          mb_expect_tx(bar_stat(buf), CW * NSTAT * 8);
+          mb_expect_tx(bar_vrdy(s), CW * 9 * 8);
+          mb_expect_tx(bar_stat(s), STAT_SLOT * 8);
         }
-        mb_wait(bar_stat(buf), (unsigned)((it >> 1) & 1));
-        const double* sb = statbuf + buf * CW * NSTAT;
+        stamp(it, 0);
+        mb_wait(bar_stat(s), (unsigned)((it / NSLOT) & 1));
+        stamp(it, 1);
+        const unsigned sb = sa(statbuf + s * STAT_SLOT);
         for (int oc0 = 0; oc0 < owned; oc0 += cpr) {
           const int oc = oc0 + cs;              // < owned always (owned is a multiple of cpr)
           const int col = oc * G + rank;
-          double S = 0.0, SS = 0.0, q = 0.0;
+          double S, SS, q;
           {
             double ps[4], pss[4], pq[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
               const bool on = r < nr;
-              const unsigned pa = sa(sb + (oc * G + rs * nr + (on ? r : 0)) * NSTAT);
+              const unsigned pa = sb + (unsigned)((oc * G + rs * nr + (on ? r : 0)) * NSTAT) * 8;
               ps[r] = on ? lds_f64(pa) : 0.0;
               pss[r] = on ? lds_f64(pa + 8) : 0.0;
               pq[r] = on ? lds_f64(pa + (2 + l) * 8) : 0.0;
             }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {  // rank order inside the lane, fixed tree across lane groups
-              S += ps[r];
-              SS += pss[r];
-              q += pq[r];
-            }
+            // fixed tree: ranks inside the lane, then lane groups (xor 8, 16)
+            S = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+            SS = (pss[0] + pss[1]) + (pss[2] + pss[3]);
+            q = (pq[0] + pq[1]) + (pq[2] + pq[3]);
             if (sub >= 2) {
               S += __shfl_xor_sync(0xffffffffu, S, 8);
               SS += __shfl_xor_sync(0xffffffffu, SS, 8);
@@ -268,34 +452,40 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
           const i64 gcol = tile * CW + col;
           const bool valid = gcol < g.N;
           const double k0 = lds_f64(sa(kshs + s * CW + col));
-          const double dm = S / dT;
+          // short dependent chain (this warp shares the FP64 pipe with the DMMA stream, every dependent
+          // FP64 instruction costs a pipe round trip): reciprocals instead of divisions, 1/sd from an
+          // rsqrt seed + two Newton steps (relative error ~1e-16; the parity bar is 1e-9)
+          const double dm = S * invT;
           const double mu = k0 + dm;
-          double sd = 1.0;
+          double inv = 1.0;
           if (T > 1) {
-            double var = (SS - S * dm) / (double)(T - 1);
+            double var = fma(-S, dm, SS) * invTm1;
             if (var < 0.0) var = 0.0;
-            sd = sqrt(var);
-            if (sd == 0.0) sd = 1.0;  // Tprf3.scala:493-501
+            if (var != 0.0) {                      // sd == 0 -> 1 (Tprf3.scala:493-501); NaN propagates
+              double y;
+              asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(var));
+              const double hv = 0.5 * var;
+              y = y * fma(-hv * y, y, 1.5);   // seed is good to ~2^-23: 2^-45 after one step,
+              y = y * fma(-hv * y, y, 1.5);   // full double after two
+              inv = (var < 1e-290 || var > 1e290) ? 1.0 / sqrt(var) : y;
+            }
           }
-          const double inv = 1.0 / sd;
           const double m_n = mu * inv;
           const double w = q * inv;
           const double v = w * inv;
           // record of this column -> every CTA of the cluster; this lane serves ranks [rs*nr, rs*nr + nr)
           {
-            const unsigned a_v = sa(vrec + (buf * CW + col) * NREC + l);
-            const unsigned a_i = sa(vrec + (buf * CW + col) * NREC + 8);
-            const unsigned a_b = bar_vrdy(buf);
+            const unsigned o_v = (unsigned)((s * CW + col) * NREC + l) * 8;
+            const unsigned o_i = (unsigned)((s * CW + col) * NREC + 8) * 8;
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
               if (r < nr) {
-                const unsigned dstrank = (unsigned)(rs * nr + r);
-                const unsigned rb = map_rank(a_b, dstrank);
-                st_async(map_rank(a_v, dstrank), v, rb);
-                if (l == 0) st_async(map_rank(a_i, dstrank), inv, rb);
+                st_async(rvrec[r] + o_v, v, rvbar[r] + 8u * s);
+                if (l == 0) st_async(rvrec[r] + o_i, inv, rvbar[r] + 8u * s);
               }
             }
           }
+          stamp(it, 2);
           const bool mine = valid && rs == 0;   // one lane per (column, l) writes / accumulates
           if (mine) {
             const i64 cix = (i64)b * g.npad + gcol;
@@ -343,194 +533,59 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         for (int c = 0; c < 8; ++c) a_sww[c] = 0.0;
       }
     }
-  } else if (warp == NCW + 2) {
-    // ================= partial reducer: per-warp partials in `scratch` -> CTA partial -> owner CTA =================
-    bar_arrive_n(2);  // scratch starts free
+  } else {
+    // ================= reducer: lane partials in `scratch` -> CTA partial -> owner CTA =================
+    // lane handles 5 of the 160 (column, statistic) values: value 0 is s1 / s2 of column lane >> 1 (4 row
+    // phases x 4 A-warps), values 1..4 are q[column (e >> 3)][l = e & 7], e = lane + 32 (j - 1) (4 A-warps)
+    unsigned rdst[5], rbar[5];
+    {
+      const int c = lane >> 1, st = lane & 1;
+      const int owner = c % G, oc = c / G;
+      rdst[0] = map_rank(sa(statbuf + (oc * G + rank) * NSTAT + st), owner);
+      rbar[0] = map_rank(bar_stat(0), owner);
+    }
+#pragma unroll
+    for (int j = 1; j < 5; ++j) {
+      const int e = lane + 32 * (j - 1);
+      const int c = e >> 3, l = e & 7;
+      const int owner = c % G, oc = c / G;
+      rdst[j] = map_rank(sa(statbuf + (oc * G + rank) * NSTAT + 2 + l), owner);
+      rbar[j] = map_rank(bar_stat(0), owner);
+    }
+    const unsigned sbase = sa(scratch + 128 + (lane & 1) * 64 + (lane >> 1) * 4);
+    const unsigned qbase = sa(scratch + lane);
     int it = 0;
     for (int ch = cl; ch < nchunks; ch += ncl) {
       const int cidx = ch % g.cpp;
       for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
-        const int buf = it & 1;
-        bar_sync_n(1);
-        double acc[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          const int e = lane + 32 * j;   // (column c, statistic v) = e / NSTAT, e % NSTAT
-          double part[NCW];
-#pragma unroll
-          for (int w = 0; w < NCW; ++w) part[w] = lds_f64(sa(scratch + w * CW * NSTAT + e));
-#pragma unroll
-          for (int st = 1; st < NCW; st *= 2)   // fixed pairwise tree
-#pragma unroll
-            for (int w = 0; w + st < NCW; w += 2 * st) part[w] += part[w + st];
-          acc[j] = part[0];
-        }
-        bar_arrive_n(2);
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          const int e = lane + 32 * j;
-          const int c = e / NSTAT, v = e % NSTAT;
-          const int owner = c % G, oc = c / G;
-          const unsigned dst = sa(statbuf + buf * CW * NSTAT + (oc * G + rank) * NSTAT + v);
-          st_async(map_rank(dst, owner), acc[j], map_rank(bar_stat(buf), owner));
-        }
-      }
-    }
-  } else {
-    // ================= compute warps =================
-    const int rowbase = warp * RW;   // first local row of this warp (multiple of 16)
-    const int fm = lane >> 2, fk = lane & 3;
-    // phase A: lane (m = fm, k = fk) reads x[row 4ks + k][col_of_m(m) (+4)]
-    unsigned offa[2][2];
-    int cola[2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      cola[mt] = col_of_m(fm) + 4 * mt;
-#pragma unroll
-      for (int pb = 0; pb < 2; ++pb)
-        offa[mt][pb] = (unsigned)(((((cola[mt] >> 1) ^ (4 * pb + fk)) & 7) << 4) | ((cola[mt] & 1) << 3)) + (unsigned)(rowbase + 4 * pb + fk) * 128u;
-    }
-    // phase B: lane (g = fm, k = fk) reads the 16-byte chunk 4s + k of row rm of each 8-row m-tile
-    const int rm = (fm >> 1) + 4 * (fm & 1);
-    unsigned offb[2];
-#pragma unroll
-    for (int s2 = 0; s2 < 2; ++s2) offb[s2] = (unsigned)((((4 * s2 + fk) ^ rm) & 7) << 4) + (unsigned)(rowbase + rm) * 128u;
-
-    double px[MT][2], hh[MT];
-#pragma unroll
-    for (int i = 0; i < MT; ++i) px[i][0] = px[i][1] = hh[i] = 0.0;
-
-    const bool dbg_on = g.dbg != nullptr && cl == 0 && lane == 0;
-    auto stamp = [&](int iter, int slot_) {
-      if (dbg_on && iter < 64) g.dbg[(((i64)rank * 16 + warp) * 64 + iter) * 8 + slot_] = clock64();
-    };
-    const unsigned slots0 = sa(smem + OFF_SLOTS);
-
-    auto phase_b = [&](int itb) {
-      const int buf = itb & 1, s = itb % NSLOT;
-      mb_wait(bar_vrdy(buf), (unsigned)((itb >> 1) & 1));
-      stamp(itb + 1, 5);
-      const unsigned vr = sa(vrec + buf * CW * NREC);
-      double vf[2][2], isd[2][2];
-#pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int c = 8 * s2 + 2 * fk + e;
-          vf[s2][e] = lds_f64(vr + (c * NREC + fm) * 8);
-          isd[s2][e] = lds_f64(vr + (c * NREC + 8) * 8);
-        }
-      const unsigned slot = slots0 + (unsigned)s * SLOT_BYTES;
-#pragma unroll
-#pragma unroll
-      for (int m0 = 0; m0 < MT; m0 += MB) {
-        double2 x[MB][2];
-#pragma unroll
-        for (int i = 0; i < MB; ++i)
-#pragma unroll
-          for (int s2 = 0; s2 < 2; ++s2) x[i][s2] = lds_v2f64(slot + offb[s2] + (unsigned)(m0 + i) * 1024u);
-#pragma unroll
-        for (int i = 0; i < MB; ++i)
-#pragma unroll
-          for (int s2 = 0; s2 < 2; ++s2) {
-            f_dmma(px[m0 + i][0], px[m0 + i][1], x[i][s2].x, vf[s2][0]);
-            f_dmma(px[m0 + i][0], px[m0 + i][1], x[i][s2].y, vf[s2][1]);
-            hh[m0 + i] = fma(x[i][s2].x, isd[s2][0], hh[m0 + i]);
-            hh[m0 + i] = fma(x[i][s2].y, isd[s2][1], hh[m0 + i]);
-          }
-      }
-      __syncwarp();
-      if (lane == 0) mb_arrive(bar_empty(s));
-    };
-
-    int it = 0;
-    for (int ch = cl; ch < nchunks; ch += ncl) {
-      const int b = ch / g.cpp, cidx = ch % g.cpp;
-      // Zc fragments of this warp's rows (B operand of phase A): lane holds zc[row 4ks + k][l = fm]
-      double zf[KS];
-      const i64 grow0 = (i64)rank * R + rowbase;
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const i64 t = grow0 + 4 * ks + fk;
-        zf[ks] = t < T ? g.zc[((i64)b * T + t) * 8 + fm] : 0.0;
-      }
-      const i64 tv = T - grow0 - fk;                 // row 4ks + k is inside the panel iff 4ks < tv
-      const int tvalid = tv > 64 ? 64 : (tv < 0 ? 0 : (int)tv);
-      const bool need_mask = grow0 + RW > T;
-      const int it_first = it;
-      for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
         const int s = it % NSLOT;
         stamp(it, 0);
-        mb_wait(bar_full(s), (unsigned)((it / NSLOT) & 1));
+        mb_wait(bar_scr_full, (unsigned)(it & 1));
         stamp(it, 1);
-        const unsigned slot = slots0 + (unsigned)s * SLOT_BYTES;
-        double q[2][2][2], s1[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, s2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        double p[NAW][4], pq[4][NAW];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int w = 0; w < NAW; ++w)
 #pragma unroll
-          for (int pb = 0; pb < 2; ++pb) q[mt][pb][0] = q[mt][pb][1] = 0.0;
-        double ksh[2];
-        ksh[0] = lds_f64(sa(kshs + s * CW + cola[0]));
-        ksh[1] = lds_f64(sa(kshs + s * CW + cola[1]));
+          for (int k = 0; k < 4; ++k) p[w][k] = lds_f64(sbase + (w * SCR_W + k) * 8);
 #pragma unroll
-        for (int kb = 0; kb < KS; kb += KB) {
-          double a[KB][2];
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-          for (int i = 0; i < KB; ++i)
+          for (int w = 0; w < NAW; ++w) pq[j][w] = lds_f64(qbase + (w * SCR_W + 32 * j) * 8);
+        double acc[5];
+        {
+          double pw[NAW];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) a[i][mt] = lds_f64(slot + offa[mt][i & 1] + (unsigned)(kb + (i & ~1)) * 512u);
-#pragma unroll
-          for (int i = 0; i < KB; ++i)
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-              f_dmma(q[mt][i & 1][0], q[mt][i & 1][1], a[i][mt], zf[kb + i]);
-              double d = a[i][mt] - ksh[mt];
-              if (need_mask && 4 * (kb + i) >= tvalid) d = 0.0;
-              s1[mt][i & 1] += d;
-              s2[mt][i & 1] = fma(d, d, s2[mt][i & 1]);
-            }
+          for (int w = 0; w < NAW; ++w) pw[w] = (p[w][0] + p[w][1]) + (p[w][2] + p[w][3]);
+          acc[0] = (pw[0] + pw[1]) + (pw[2] + pw[3]);
         }
-        double t1[2], t2[2];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          t1[mt] = s1[mt][0] + s1[mt][1];
-          t2[mt] = s2[mt][0] + s2[mt][1];
-          t1[mt] += __shfl_xor_sync(0xffffffffu, t1[mt], 1);
-          t2[mt] += __shfl_xor_sync(0xffffffffu, t2[mt], 1);
-          t1[mt] += __shfl_xor_sync(0xffffffffu, t1[mt], 2);
-          t2[mt] += __shfl_xor_sync(0xffffffffu, t2[mt], 2);
-        }
+        for (int j = 0; j < 4; ++j) acc[1 + j] = (pq[j][0] + pq[j][1]) + (pq[j][2] + pq[j][3]);
+        consume(acc[0]); consume(acc[1]); consume(acc[2]); consume(acc[3]); consume(acc[4]);
+        __syncwarp();
+        if (lane == 0) mb_arrive(bar_scr_free);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) st_async(rdst[j] + (unsigned)s * (STAT_SLOT * 8), acc[j], rbar[j] + 8u * s);
         stamp(it, 2);
-        bar_sync_n(2);  // the reducer is done with the previous piece's partials
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const unsigned sp = sa(scratch + (warp * CW + cola[mt]) * NSTAT);
-          sts_v2f64(sp + (2 + 2 * fk) * 8, q[mt][0][0] + q[mt][1][0], q[mt][0][1] + q[mt][1][1]);
-          if (fk == 0) sts_v2f64(sp, t1[mt], t2[mt]);
-        }
-        bar_arrive_n(1);
-        stamp(it, 3);
-        stamp(it, 4);
-        if (it > it_first) phase_b(it - 1);
-        stamp(it, 6);
-      }
-      if (it > it_first) phase_b(it - 1);
-      // flush this chunk's PX / h0 partial
-      {
-        double* pxo = g.pxp + ((i64)(b * g.cpp + cidx) * g.tpad) * 8;
-        double* h0o = g.h0p + (i64)(b * g.cpp + cidx) * g.tpad;
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          double h = hh[mt];
-          h += __shfl_xor_sync(0xffffffffu, h, 1);
-          h += __shfl_xor_sync(0xffffffffu, h, 2);
-          const i64 t = grow0 + mt * 8 + rm;
-          if (t < T) {
-            *reinterpret_cast<double2*>(pxo + t * 8 + 2 * fk) = make_double2(px[mt][0], px[mt][1]);
-            if (fk == 0) h0o[t] = h;
-          }
-          px[mt][0] = px[mt][1] = hh[mt] = 0.0;
-        }
       }
     }
   }
