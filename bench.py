@@ -217,6 +217,35 @@ def matmul_sweep(u, sizes=(1024, 2048, 4096, 8192)):
     return out
 
 
+def batched_config5(u, rank, world, max_over_ranks, barrier, peak_gbs, small=False):
+    """BASELINE config 5: 4096 independent panels (T=512, N=2048, L=4), panels sharded across ranks, no collective."""
+    from uni_b200 import _lib as L_
+    from uni_b200._lib import check, lib
+    T, N, Lp, total = 512, 2048, 4, (256 if small else 4096)
+    nb = total // world + (1 if rank < total % world else 0)
+    X = u.MatD.randn(nb * T, N, seed=7000 + rank)
+    y = u.MatD.randn(nb * T, 1, seed=7100 + rank)
+    Z = u.MatD.randn(nb * T, Lp, seed=7200 + rank)
+    f = u.MatD.zeros(nb * T, 1); r2 = u.MatD.zeros(nb, 1)
+    p = lambda m: C.c_void_p(m._buf.ptr)
+    call = lambda: check(lib.um_tprf_fit_batched(L_.TPRF_CLOSED, p(y), p(X), p(Z), T, N, Lp, nb, p(f), None, p(r2)))
+    for _ in range(3):
+        call()
+    barrier()
+    ms = C.c_float(0)
+    reps = 5
+    check(lib.um_timer_start())
+    for _ in range(reps):
+        call()
+    check(lib.um_timer_stop(C.byref(ms)))
+    barrier()
+    t = max_over_ranks(ms.value / reps)
+    gbs = 8.0 * T * N * nb / (t * 1e-3) / 1e9
+    return {"panels": total, "panels_per_gpu": nb, "ms": round(t, 4), "panels_per_s": round(total / (t * 1e-3), 1),
+            "gbs_per_gpu": round(gbs, 1), "frac_hbm": round(gbs / peak_gbs, 4),
+            "tflops": round(total * tprf_flops(T, N, Lp) / (t * 1e-3) / 1e12, 2)}
+
+
 def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
@@ -300,18 +329,42 @@ def run_ours(args, rank, world, local_rank):
         if cnt.value:
             kt[nm] = tot.value / cnt.value
     check(lib.um_prof_enable(0))
-    dom = max(("colstats", "project"), key=lambda k: kt.get(k, 0.0))
+    # slot 0 ("colstats") is the single-read cluster sweep when no "project" sweep ran
+    fused = "project" not in kt
+    if fused:
+        kt["fused_sweep"] = kt.pop("colstats")
+        dom = "fused_sweep"
+    else:
+        dom = max(("colstats", "project"), key=lambda k: kt.get(k, 0.0))
     dom_ms = max_over_ranks(kt[dom])
     alg_bytes = 8.0 * T * Nl
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # DRAM bytes of the same kernel and shape from the committed ncu --set full capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_tprf_fused_traffic.json")))
+        if fused and tr["T"] == T and tr["N_local"] == Nl:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
+    FP64_PEAK = 37.0  # TFLOP/s, DMMA / DFMA issue peak measured on this pool (profiles/r1_fp64_peak.log)
+    k_tflops = tprf_flops(T, Nl, Lp) / (dom_ms * 1e-3) / 1e12
+    g_, r_, n_ = C.c_int32(), C.c_int32(), C.c_int32()
+    check(lib.um_tprf_fused_info(T, C.byref(g_), C.byref(r_), C.byref(n_)))
     roofline = {
-        "bound": "hbm", "kernel": f"k_tprf_{dom}", "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s",
-        "frac": round(achieved / peak_gbs, 4), "traffic": None, "peak_source": peak_src,
+        "bound": "hbm", "kernel": "k_tprf_fused" if fused else f"k_tprf_{dom}", "achieved": round(achieved, 1), "peak": peak_gbs,
+        "unit": "GB/s", "frac": round(achieved / peak_gbs, 4), "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes,
+        "fp64": {"achieved": round(k_tflops, 2), "peak": FP64_PEAK, "unit": "TFLOP/s", "frac": round(k_tflops / FP64_PEAK, 4),
+                 "peak_source": "measured DMMA m8n8k4 / DFMA issue peak (tools/microbench/fp64_peak.cu, profiles/r1_fp64_peak.log); "
+                                "the kernel issues 20 FP64 slots per element, counted as 4L+6 = 38 flop"},
         "kernel_ms": {k: round(v, 4) for k, v in kt.items()},
         "fit_frac_x_read_once": round((8.0 * T * N / world) / (ms_step * 1e-3) / 1e9 / peak_gbs, 4),
-        "note": "each of the two sweeps (colstats, project) reads the shard once: 8*T*N_local bytes per launch; "
-                "fit_frac_x_read_once charges the whole fit with ONE read of X (SURVEY 8d)",
+        "sweep": ({"path": "single-read cluster sweep", "cluster_ctas": g_.value, "rows_per_cta": r_.value,
+                   "resident_clusters": n_.value, "sms_used": g_.value * n_.value} if fused else {"path": "two sweeps"}),
+        "note": ("X is read from HBM once (8*T*N_local bytes per launch); the sweep is bound by FP64 issue and HBM almost "
+                 "equally (DESIGN.md 4.2)" if fused else
+                 "each of the two sweeps (colstats, project) reads the shard once: 8*T*N_local bytes per launch; "
+                 "fit_frac_x_read_once charges the whole fit with ONE read of X (SURVEY 8d)"),
     }
 
     # ---- end to end through the C-ABI host entry point (pinned host panel, H2D inside the timed region)
@@ -345,6 +398,11 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
     extras = {}
+    if not args.skip_ops:
+        try:
+            extras["batched_config5"] = batched_config5(u, rank, world, max_over_ranks, barrier, peak_gbs, small=args.small)
+        except Exception as ex:
+            extras["batched_config5"] = {"error": str(ex)[:200]}
     cpu_baseline = None
     if rank == 0 and world == 1:
         Ns = 4096

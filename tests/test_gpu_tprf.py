@@ -190,3 +190,95 @@ def test_full_size_properties(u):
     sd = c.xstd.to_numpy()
     v = X.var(0).to_numpy() * (T / (T - 1.0))
     assert close(sd * sd, v, rtol=1e-11)
+
+
+# ---- both sweeps: the single-read cluster sweep (tprf_fused.cuh) and the two-sweep path (tprf.cu) ----
+FUSED_SHAPES = [(50, 6, 2), (130, 48, 1), (256, 1000, 4), (512, 2048, 4), (600, 130, 3), (1000, 512, 8),
+                (2048, 256, 8), (4096, 320, 5), (8000, 200, 8), (8192, 1024, 8)]
+
+
+@pytest.mark.parametrize("tnl", FUSED_SHAPES)
+def test_single_read_sweep_vs_two_sweep_vs_oracle(u, tnl):
+    """Every cluster size (1..16 CTAs), ragged tails in T (rows past T zero-filled by TMA, masked in the
+    variance sums) and in N (columns past N), data with large column means (shifted sums)."""
+    from uni_b200 import tprf3
+    T, N, L = tnl
+    rng = np.random.default_rng(T + N)
+    X = rng.standard_normal((T, N)) * (1 + 3 * rng.random(N)) + 5 * rng.standard_normal(N)
+    y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, L))
+    o = to.tprf_closed_form_gram(y, X, Z)
+    oi = to.t3prf(y, X, Z)
+    res = {}
+    try:
+        for name, path in (("two", tprf3.TPRF_PATH_TWO_SWEEP), ("fused", tprf3.TPRF_PATH_FUSED)):
+            tprf3.set_tprf_path(path)
+            c = u.tprfClosedForm(*devs(u, y, X, Z))
+            it = u.t3prf(*devs(u, y, X, Z))
+            res[name] = (c, it)
+            assert close(c.forecasts.to_numpy(), o.forecasts), name
+            assert close(c.alpha.to_numpy(), o.alpha, rtol=1e-8, atol=1e-13), name
+            assert close(c.rSquared, o.r_squared), name
+            assert close(it.forecasts.to_numpy(), oi.forecasts), name
+            assert close(it.phi.to_numpy(), oi.phi, rtol=1e-8, atol=1e-13), name
+            assert close(it.sigma.to_numpy(), oi.sigma, rtol=1e-7, atol=1e-12), name
+            assert close(c.xstd.to_numpy().ravel(), X.std(axis=0, ddof=1), rtol=1e-11), name
+    finally:
+        tprf3.set_tprf_path(tprf3.TPRF_PATH_AUTO)
+    assert close(res["fused"][0].forecasts.to_numpy(), res["two"][0].forecasts.to_numpy())
+
+
+def test_single_read_sweep_requirements(u):
+    """An odd row pitch cannot be described by a TMA tensor map: auto falls back to two sweeps, forcing
+    the single-read sweep raises IllegalArgumentException's twin."""
+    from uni_b200 import tprf3
+    rng = np.random.default_rng(3)
+    T, N, L = 64, 33, 2
+    X = rng.standard_normal((T, N)); y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, L))
+    o = to.tprf_closed_form_gram(y, X, Z)
+    assert close(u.tprfClosedForm(*devs(u, y, X, Z)).forecasts.to_numpy(), o.forecasts)
+    try:
+        tprf3.set_tprf_path(tprf3.TPRF_PATH_FUSED)
+        with pytest.raises(ValueError):
+            u.tprfClosedForm(*devs(u, y, X, Z))
+    finally:
+        tprf3.set_tprf_path(tprf3.TPRF_PATH_AUTO)
+    with pytest.raises(ValueError):
+        tprf3.set_tprf_path(7)
+
+
+def test_single_read_sweep_bit_reproducible_and_matches_two_sweep_at_scale(u):
+    """T = 8192 (16-CTA clusters), N = 32768: run-to-run bit-identical; both sweeps agree to 1e-9."""
+    from uni_b200 import tprf3
+    T, N, L = 8192, 32768, 8
+    X = u.MatD.randn(T, N, seed=11); y = u.MatD.randn(T, 1, seed=12); Z = u.MatD.randn(T, L, seed=13)
+    try:
+        tprf3.set_tprf_path(tprf3.TPRF_PATH_FUSED)
+        a = u.tprfClosedForm(y, X, Z); b = u.tprfClosedForm(y, X, Z)
+        tprf3.set_tprf_path(tprf3.TPRF_PATH_TWO_SWEEP)
+        c = u.tprfClosedForm(y, X, Z)
+    finally:
+        tprf3.set_tprf_path(tprf3.TPRF_PATH_AUTO)
+    assert np.array_equal(a.forecasts.to_numpy(), b.forecasts.to_numpy())
+    assert np.array_equal(a.alpha.to_numpy(), b.alpha.to_numpy())
+    assert close(a.forecasts.to_numpy(), c.forecasts.to_numpy())
+    assert close(a.alpha.to_numpy(), c.alpha.to_numpy(), rtol=1e-8, atol=1e-14)
+
+
+def test_batched_config5_sample(u):
+    """BASELINE config 5 shape (T=512, N=2048, L=4): 64 panels, every panel against the oracle
+    (single-CTA 'clusters': no exchange between CTAs)."""
+    from uni_b200 import _lib as L_
+    B, T, N, L = 64, 512, 2048, 4
+    Xs = np.empty((B, T, N)); ys = np.empty((B, T, 1)); Zs = np.empty((B, T, L))
+    for p in range(B):
+        g = np.random.default_rng(p)
+        Xs[p] = g.standard_normal((T, N)); ys[p] = g.standard_normal((T, 1)); Zs[p] = g.standard_normal((T, L))
+    dX = u.Mat.from_numpy(Xs.reshape(B * T, N)); dy = u.Mat.from_numpy(ys.reshape(B * T, 1)); dZ = u.Mat.from_numpy(Zs.reshape(B * T, L))
+    f = u.MatD.zeros(B * T, 1); a = u.MatD.zeros(B * N, 1); r2 = u.MatD.zeros(B, 1)
+    L_.check(L_.lib.um_tprf_fit_batched(L_.TPRF_CLOSED, dy._buf.ptr, dX._buf.ptr, dZ._buf.ptr, T, N, L, B, f._buf.ptr, a._buf.ptr, r2._buf.ptr))
+    F = f.to_numpy().reshape(B, T); A = a.to_numpy().reshape(B, N); R = r2.to_numpy().ravel()
+    for p in range(B):
+        o = to.tprf_closed_form_gram(ys[p], Xs[p], Zs[p])
+        assert close(F[p], o.forecasts.ravel()), p
+        assert close(A[p], o.alpha.ravel(), rtol=1e-8, atol=1e-14), p
+        assert close(R[p], o.r_squared), p
