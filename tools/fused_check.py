@@ -29,7 +29,7 @@ for (T, N, L) in shapes:
     o = to.tprf_closed_form_gram(y, X, Z)
     dy, dX, dZ = u.Mat.from_numpy(y), u.Mat.from_numpy(X), u.Mat.from_numpy(Z)
     out = {}
-    for name, path in (("two", 1), ("fused", 2)):
+    for name, path in (("two", 1), ("fused", 2), ("grid", 3)):
         tprf3.set_tprf_path(path)
         try:
             r = u.tprfClosedForm(dy, dX, dZ)
@@ -44,6 +44,9 @@ for (T, N, L) in shapes:
             continue
         print(f"T={T} N={N} L={L} {name:5s}: yhat err/tol {relerr(v[0], o.forecasts):.3g}  alpha {relerr(v[1], o.alpha):.3g}  "
               f"r2 {abs(v[2] - o.r_squared):.2e}  iter-yhat {relerr(v[3], o.forecasts):.3g}")
+    if out.get("two") and out.get("grid"):
+        print(f"    grid vs two-sweep: yhat {relerr(out['grid'][0], out['two'][0]):.3g}  alpha {relerr(out['grid'][1], out['two'][1]):.3g}"
+              f"  phi {relerr(out['grid'][4], out['two'][4]):.3g}  sigma {relerr(out['grid'][5], out['two'][5]):.3g}  xstd {relerr(out['grid'][6], out['two'][6]):.3g}")
     if out.get("two") and out.get("fused"):
         print(f"    fused vs two-sweep: yhat {relerr(out['fused'][0], out['two'][0]):.3g}  alpha {relerr(out['fused'][1], out['two'][1]):.3g}"
               f"  phi {relerr(out['fused'][4], out['two'][4]):.3g}  sigma {relerr(out['fused'][5], out['two'][5]):.3g}  xstd {relerr(out['fused'][6], out['two'][6]):.3g}")
@@ -59,7 +62,7 @@ T, N, L = 8192, 65536, 8
 rng = np.random.default_rng(1)
 X = rng.standard_normal((T, N)); y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, L))
 dy, dX, dZ = u.Mat.from_numpy(y), u.Mat.from_numpy(X), u.Mat.from_numpy(Z)
-for name, path in (("two", 1), ("fused", 2)):
+for name, path in (("two", 1), ("fused", 2), ("grid", 3)):
     tprf3.set_tprf_path(path)
     for _ in range(3):
         r = u.tprfClosedForm(dy, dX, dZ)

@@ -741,6 +741,7 @@ __global__ void k_fill_nan(double* p, i64 n) {
 
 }  // namespace um
 #include "tprf_fused.cuh"
+#include "tprf_grid.cuh"
 namespace um {
 
 // ---- host orchestration ------------------------------------------------------------------------------------------
@@ -754,7 +755,9 @@ struct Plan3 {
   int cf_blocks;                                 // colfinal blocks per panel
   // single-read fused sweep (tprf_fused.cuh): cluster size, rows per piece, chunks per panel, clusters
   bool fused = false;
+  bool grid_sweep = false;   // tprf_grid.cuh (virtual groups over all SMs, TMEM stash) instead of hardware clusters
   int fG = 0, fR = 0, fcpp = 0, fncl = 0;
+  size_t o_gpart = 0, o_grec = 0, o_gcnt = 0;
   // workspace offsets (bytes)
   size_t o_zc, o_small, o_qp, o_s1, o_s2, o_w0, o_v, o_invsd, o_mun, o_bp, o_pxp, o_h0p, o_packed, o_sig, o_par, total;
   i64 packed_len;
@@ -780,6 +783,10 @@ static void carve(Plan3& p) {
   p.o_packed = take((size_t)batch * p.packed_len * 8);
   p.o_sig = take((size_t)batch * T * LP * 8);
   p.o_par = take((size_t)batch * PARAMS * 8);
+  if (p.grid_sweep) {
+    p.o_gpart = take((size_t)p.fncl * gridk::NX * gridk::PART_ENTRY * 16);
+    p.o_grec = take((size_t)p.fncl * gridk::NX * gridk::REC_ENTRY * 16);   // directly after o_gpart: zeroed together
+  }
   p.total = o;
 }
 
@@ -880,6 +887,29 @@ static int fused_clusters(int G, int R) {
   return n > 0 ? n : 0;
 }
 
+static int grid_groups(int G, int R) {
+  // groups of G CTAs of the grid-wide sweep, one CTA per SM (cooperative launch: all co-resident)
+  static bool attr_done[5] = {false, false, false, false, false};
+  const int j = R / 128;
+  gridk::GridKernel kern = gridk::grid_kernel_for(R);
+  if (!attr_done[j]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gridk::GSMEM_ALLOC) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    attr_done[j] = true;
+  }
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx()->device);
+  if (!coop) return 0;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, gridk::G_NTHREADS, gridk::GSMEM_ALLOC) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return 0;
+  }
+  return ctx()->sm_count / G;
+}
+
 // decide whether the fused sweep applies to this panel; fill p.fused / fG / fR / fcpp / fncl
 static void plan_fused(Plan3& p, const double* X, i64 ldx, i64 x_bs) {
   p.fused = false;
@@ -890,7 +920,17 @@ static void plan_fused(Plan3& p, const double* X, i64 ldx, i64 x_bs) {
   int G = 0, R = 0;
   fused::pick_shape(p.T, &G, &R);
   if (!G) return;
-  const int ncl = fused_clusters(G, R);
+  const int path = g_tprf_path.load();
+  int ncl = 0;
+  p.grid_sweep = false;
+  if ((path == 0 && G >= 8) || path == 3) {
+    ncl = grid_groups(G, R);
+    p.grid_sweep = ncl > 0;
+  }
+  if (!p.grid_sweep) {
+    if (path == 3) return;
+    ncl = fused_clusters(G, R);
+  }
   if (ncl <= 0) return;
   const i64 ntile = cdiv(p.N, fused::CW);
   i64 cpp;
@@ -942,6 +982,22 @@ static int run_fused(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_b
   if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return fail(UM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
   i64 nclu = (i64)p.batch * p.fcpp;
   if (nclu > p.fncl) nclu = p.fncl;
+  if (p.grid_sweep) {
+    gridk::GArgs ga;
+    ga.a = a;
+    ga.part = reinterpret_cast<uint4*>(ws + p.o_gpart);
+    ga.rec = reinterpret_cast<uint4*>(ws + p.o_grec);
+    // tags restart at 1 with every launch: clear the rings of the groups that run
+    UM_CUDA(cudaMemsetAsync(ws + p.o_gpart, 0, (p.o_grec - p.o_gpart) + (size_t)p.fncl * gridk::NX * gridk::REC_ENTRY * 16, st));
+    void* params[3] = {&mx, &m0, &ga};
+    prof_begin(0);
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(gridk::grid_kernel_for(p.fR)), dim3((unsigned)(nclu * p.fG), 1, 1),
+                                                dim3(gridk::G_NTHREADS, 1, 1), params, gridk::GSMEM_ALLOC, st);
+    prof_end(0);
+    if (e != cudaSuccess) return fail(UM_ERR_CUDA, "grid-wide 3PRF sweep launch failed: %s", cudaGetErrorString(e));
+    UM_LAUNCHED();
+    return UM_OK;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nclu * p.fG), 1, 1);
   cfg.blockDim = dim3(fused::NTHREADS, 1, 1);
@@ -1077,7 +1133,7 @@ using namespace um;
 extern "C" {
 
 int32_t um_tprf_set_path(int32_t path) {
-  if (path < 0 || path > 2) return fail(UM_ERR_ARG, "3PRF path %d outside {0 auto, 1 two-sweep, 2 fused}", path);
+  if (path < 0 || path > 3) return fail(UM_ERR_ARG, "3PRF path %d outside {0 auto, 1 two-sweep, 2 cluster sweep, 3 grid sweep}", path);
   g_tprf_path.store(path);
   return UM_OK;
 }
@@ -1093,7 +1149,15 @@ int32_t um_tprf_fused_info(int64_t T, int32_t* cluster_size, int32_t* rows_per_p
   fused::pick_shape(T, &G, &R);
   if (cluster_size) *cluster_size = G;
   if (rows_per_piece) *rows_per_piece = R;
-  if (resident_clusters) *resident_clusters = (G && fused::encode_fn()) ? fused_clusters(G, R) : 0;
+  if (resident_clusters) {
+    const int path = g_tprf_path.load();
+    int n = 0;
+    if (G && fused::encode_fn()) {
+      if ((path == 0 && G >= 8) || path == 3) n = grid_groups(G, R);
+      if (n <= 0) n = fused_clusters(G, R);
+    }
+    *resident_clusters = n;
+  }
   return UM_OK;
 }
 
@@ -1130,7 +1194,7 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
   const double* xp = static_cast<const double*>(X->data) + X->offset;
   const i64 ldx = N == 1 ? 1 : X->rs;
   Plan3 p = make_plan_for(T, N, L, 1, xp, ldx, 0);
-  if (g_tprf_path.load() == 2 && !p.fused)
+  if (g_tprf_path.load() >= 2 && !p.fused)
     return fail(UM_ERR_ARG, "fused 3PRF sweep requested but not applicable (T = %lld > %d*%d rows, X not 16-byte aligned / odd row pitch, or no cluster launch)", T, fused::GMAX, fused::RMAX);
   char* ws = static_cast<char*>(scratch(p.total));
   if (!ws) return UM_ERR_OOM;
