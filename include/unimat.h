@@ -207,9 +207,11 @@ int32_t um_tprf_fit_host(int32_t mode, const double* y, const double* X, int64_t
 int32_t um_tprf_fit_batched(int32_t mode, const double* y, const double* X, const double* Z, int64_t T,
                             int64_t N, int64_t L, int64_t batch, double* forecasts, double* alpha,
                             double* r2);
-/* Which sweep the fits use: 0 = auto (the single-read cluster sweep whenever it applies: T <= 8192,
- * X 16-byte aligned with an even row pitch; otherwise two sweeps), 1 = two sweeps only, 2 = the
- * single-read sweep or UM_ERR_ARG.  Process-wide; for tests and profiling. */
+/* Which sweep the fits use: 0 = auto (a single-read sweep whenever one applies: T <= 8192, X 16-byte
+ * aligned with an even row pitch -- thread-block clusters, plus a concurrent grid sweep on the SMs a
+ * 16- or 8-CTA cluster shape strands; otherwise two sweeps), 1 = two sweeps only, 2 = the cluster
+ * sweep or UM_ERR_ARG, 3 = the grid sweep (virtual CTA groups over all SMs, tensor-memory stash,
+ * exchange through L2) or UM_ERR_ARG.  Process-wide; for tests and profiling. */
 int32_t um_tprf_set_path(int32_t path);
 /* Shape of the single-read sweep for a T-row panel on the current device: CTAs per cluster (0 = does
  * not apply), rows of the panel each CTA keeps on chip, clusters resident at once. */

@@ -210,7 +210,7 @@ def test_single_read_sweep_vs_two_sweep_vs_oracle(u, tnl):
     oi = to.t3prf(y, X, Z)
     res = {}
     try:
-        for name, path in (("two", tprf3.TPRF_PATH_TWO_SWEEP), ("fused", tprf3.TPRF_PATH_FUSED)):
+        for name, path in (("two", tprf3.TPRF_PATH_TWO_SWEEP), ("fused", tprf3.TPRF_PATH_FUSED), ("grid", tprf3.TPRF_PATH_GRID)):
             tprf3.set_tprf_path(path)
             c = u.tprfClosedForm(*devs(u, y, X, Z))
             it = u.t3prf(*devs(u, y, X, Z))
@@ -225,6 +225,7 @@ def test_single_read_sweep_vs_two_sweep_vs_oracle(u, tnl):
     finally:
         tprf3.set_tprf_path(tprf3.TPRF_PATH_AUTO)
     assert close(res["fused"][0].forecasts.to_numpy(), res["two"][0].forecasts.to_numpy())
+    assert close(res["grid"][0].forecasts.to_numpy(), res["two"][0].forecasts.to_numpy())
 
 
 def test_single_read_sweep_requirements(u):
@@ -246,22 +247,27 @@ def test_single_read_sweep_requirements(u):
         tprf3.set_tprf_path(7)
 
 
-def test_single_read_sweep_bit_reproducible_and_matches_two_sweep_at_scale(u):
-    """T = 8192 (16-CTA clusters), N = 32768: run-to-run bit-identical; both sweeps agree to 1e-9."""
+def test_single_read_sweeps_bit_reproducible_and_match_two_sweep_at_scale(u):
+    """T = 8192 (16-CTA clusters / groups), N = 65536: every path run-to-run bit-identical (auto = clusters +
+    a concurrent grid sweep on the SMs they strand); all paths agree to 1e-9."""
     from uni_b200 import tprf3
-    T, N, L = 8192, 32768, 8
+    T, N, L = 8192, 65536, 8
     X = u.MatD.randn(T, N, seed=11); y = u.MatD.randn(T, 1, seed=12); Z = u.MatD.randn(T, L, seed=13)
+    out = {}
     try:
-        tprf3.set_tprf_path(tprf3.TPRF_PATH_FUSED)
-        a = u.tprfClosedForm(y, X, Z); b = u.tprfClosedForm(y, X, Z)
-        tprf3.set_tprf_path(tprf3.TPRF_PATH_TWO_SWEEP)
-        c = u.tprfClosedForm(y, X, Z)
+        for path in (tprf3.TPRF_PATH_TWO_SWEEP, tprf3.TPRF_PATH_FUSED, tprf3.TPRF_PATH_GRID, tprf3.TPRF_PATH_AUTO):
+            tprf3.set_tprf_path(path)
+            a = u.tprfClosedForm(y, X, Z); b = u.tprfClosedForm(y, X, Z)
+            assert np.array_equal(a.forecasts.to_numpy(), b.forecasts.to_numpy()), path
+            assert np.array_equal(a.alpha.to_numpy(), b.alpha.to_numpy()), path
+            out[path] = a
     finally:
         tprf3.set_tprf_path(tprf3.TPRF_PATH_AUTO)
-    assert np.array_equal(a.forecasts.to_numpy(), b.forecasts.to_numpy())
-    assert np.array_equal(a.alpha.to_numpy(), b.alpha.to_numpy())
-    assert close(a.forecasts.to_numpy(), c.forecasts.to_numpy())
-    assert close(a.alpha.to_numpy(), c.alpha.to_numpy(), rtol=1e-8, atol=1e-14)
+    ref = out[tprf3.TPRF_PATH_TWO_SWEEP]
+    for path, a in out.items():
+        assert close(a.forecasts.to_numpy(), ref.forecasts.to_numpy()), path
+        assert close(a.alpha.to_numpy(), ref.alpha.to_numpy(), rtol=1e-8, atol=1e-14), path
+        assert close(a.xstd.to_numpy(), ref.xstd.to_numpy(), rtol=1e-12), path
 
 
 def test_batched_config5_sample(u):

@@ -758,6 +758,10 @@ struct Plan3 {
   bool grid_sweep = false;   // tprf_grid.cuh (virtual groups over all SMs, TMEM stash) instead of hardware clusters
   int fG = 0, fR = 0, fcpp = 0, fncl = 0;
   size_t o_gpart = 0, o_grec = 0, o_gcnt = 0;
+  // split sweep: the 16-CTA cluster shape strands SMs; a grid sweep of `split_groups` virtual groups on them takes
+  // the last `split_tiles` column tiles concurrently (second stream)
+  int split_groups = 0;
+  int fcpp_out = 0;          // chunk slots per panel in the partial buffers (= fcpp, + split_groups when split)
   // workspace offsets (bytes)
   size_t o_zc, o_small, o_qp, o_s1, o_s2, o_w0, o_v, o_invsd, o_mun, o_bp, o_pxp, o_h0p, o_packed, o_sig, o_par, total;
   i64 packed_len;
@@ -783,9 +787,10 @@ static void carve(Plan3& p) {
   p.o_packed = take((size_t)batch * p.packed_len * 8);
   p.o_sig = take((size_t)batch * T * LP * 8);
   p.o_par = take((size_t)batch * PARAMS * 8);
-  if (p.grid_sweep) {
-    p.o_gpart = take((size_t)p.fncl * gridk::NX * gridk::PART_ENTRY * 16);
-    p.o_grec = take((size_t)p.fncl * gridk::NX * gridk::REC_ENTRY * 16);   // directly after o_gpart: zeroed together
+  if (p.grid_sweep || p.split_groups) {
+    const size_t groups = p.grid_sweep ? (size_t)p.fncl : (size_t)p.split_groups;
+    p.o_gpart = take(groups * gridk::NX * gridk::PART_ENTRY * 16);
+    p.o_grec = take(groups * gridk::NX * gridk::REC_ENTRY * 16);   // directly after o_gpart: zeroed together
   }
   p.total = o;
 }
@@ -834,9 +839,9 @@ static Plan3 make_plan_for(i64 T, i64 N, i64 L, i64 batch, const double* X, i64 
     // one PX / h0 partial per chunk, one small-sum partial per (chunk, cluster rank)
     Plan3 q = p;
     q.rchunks = 0;
-    q.cchunks = p.fcpp;
+    q.cchunks = p.fcpp_out;
     q.tpad = (i64)p.fG * p.fR;
-    q.cf_blocks = p.fcpp * p.fG;
+    q.cf_blocks = p.fcpp_out * p.fG;
     carve(q);
     return q;
   }
@@ -857,6 +862,26 @@ static int set_smem_attrs() {
 // ---- path selection: 0 = auto (fused when it applies), 1 = two-sweep only, 2 = fused or fail ----
 static std::atomic<int> g_tprf_path{0};
 static long long* g_fused_dbg = nullptr;  // device buffer for clock stamps (um_tprf_debug_stamps)
+// relative speed of one virtual group of the grid sweep vs one hardware cluster (measured at config 4: 5.1 ms on 9
+// groups vs 4.8 ms on 7 clusters); UM_TPRF_SPLIT_SPEED overrides, 0 disables the split
+static double g_split_share = [] {
+  const char* e = getenv("UM_TPRF_SPLIT_SPEED");
+  return e ? atof(e) : 0.73;
+}();
+
+typedef CUresult (*StreamWaitFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamWaitFn stream_wait_fn() {
+  static StreamWaitFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<StreamWaitFn>(p);
+  }
+  return fn;
+}
 
 static int fused_clusters(int G, int R) {
   // resident clusters of size G of the fused kernel (rows-per-piece variant R/128) on this device, cached
@@ -923,7 +948,7 @@ static void plan_fused(Plan3& p, const double* X, i64 ldx, i64 x_bs) {
   const int path = g_tprf_path.load();
   int ncl = 0;
   p.grid_sweep = false;
-  if ((path == 0 && G >= 8) || path == 3) {
+  if (path == 3) {
     ncl = grid_groups(G, R);
     p.grid_sweep = ncl > 0;
   }
@@ -949,6 +974,17 @@ static void plan_fused(Plan3& p, const double* X, i64 ldx, i64 x_bs) {
   if (cpp < 1) cpp = 1;
   p.fused = true;
   p.fG = G; p.fR = R; p.fcpp = (int)cpp; p.fncl = ncl;
+  p.fcpp_out = p.fcpp;
+  p.split_groups = 0;
+  // Split sweep (auto only): hardware clusters of G CTAs leave SMs stranded (7 x 16 = 112 of 148 on a B200);
+  // a concurrent grid sweep of virtual groups on those SMs takes a share of the column tiles.
+  if (path == 0 && !p.grid_sweep && p.batch == 1 && G >= 8 && g_split_share > 0.0) {
+    const int spare = (ctx()->sm_count - ncl * G) / G;
+    if (spare >= 1 && grid_groups(G, R) > 0 && ntile >= 32 * (i64)(ncl + spare) && cpp == ncl) {
+      p.split_groups = spare;
+      p.fcpp_out = p.fcpp + spare;
+    }
+  }
 }
 
 static int run_fused(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_bs) {
@@ -965,6 +1001,7 @@ static int run_fused(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_b
   a.pxp = reinterpret_cast<double*>(ws + p.o_pxp);
   a.h0p = reinterpret_cast<double*>(ws + p.o_h0p);
   a.dbg = g_fused_dbg;
+  a.started = nullptr;
   CUtensorMap mx, m0;
   const i64 bs = p.batch > 1 ? x_bs : p.T * ldx;
   cuuint64_t dims[3] = {(cuuint64_t)p.N, (cuuint64_t)p.T, (cuuint64_t)p.batch};
@@ -982,21 +1019,60 @@ static int run_fused(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_b
   if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return fail(UM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
   i64 nclu = (i64)p.batch * p.fcpp;
   if (nclu > p.fncl) nclu = p.fncl;
-  if (p.grid_sweep) {
+  a.tile_lo = 0;
+  a.cpp_out = p.fcpp_out;
+  a.cidx_off = 0;
+  auto launch_grid = [&](const fused::Args& ga_args, i64 groups, cudaStream_t gst, bool dependent) -> int {
     gridk::GArgs ga;
-    ga.a = a;
+    ga.a = ga_args;
     ga.part = reinterpret_cast<uint4*>(ws + p.o_gpart);
     ga.rec = reinterpret_cast<uint4*>(ws + p.o_grec);
-    // tags restart at 1 with every launch: clear the rings of the groups that run
-    UM_CUDA(cudaMemsetAsync(ws + p.o_gpart, 0, (p.o_grec - p.o_gpart) + (size_t)p.fncl * gridk::NX * gridk::REC_ENTRY * 16, st));
-    void* params[3] = {&mx, &m0, &ga};
-    prof_begin(0);
-    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(gridk::grid_kernel_for(p.fR)), dim3((unsigned)(nclu * p.fG), 1, 1),
-                                                dim3(gridk::G_NTHREADS, 1, 1), params, gridk::GSMEM_ALLOC, st);
-    prof_end(0);
+    if (!dependent)   // tags restart at 1 with every launch: clear the rings of the groups that run
+      UM_CUDA(cudaMemsetAsync(ws + p.o_gpart, 0, (p.o_grec - p.o_gpart) + (size_t)groups * gridk::NX * gridk::REC_ENTRY * 16, gst));
+    cudaLaunchConfig_t gc = {};
+    gc.gridDim = dim3((unsigned)(groups * p.fG), 1, 1);
+    gc.blockDim = dim3(gridk::G_NTHREADS, 1, 1);
+    gc.dynamicSmemBytes = gridk::GSMEM_ALLOC;
+    gc.stream = gst;
+    cudaLaunchAttribute ga_at[1];
+    ga_at[0].id = cudaLaunchAttributeCooperative;       // every CTA co-resident: they wait on one another through L2
+    ga_at[0].val.cooperative = 1;
+    gc.attrs = ga_at;
+    gc.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&gc, gridk::grid_kernel_for(p.fR), mx, m0, ga);
     if (e != cudaSuccess) return fail(UM_ERR_CUDA, "grid-wide 3PRF sweep launch failed: %s", cudaGetErrorString(e));
     UM_LAUNCHED();
     return UM_OK;
+  };
+  if (p.grid_sweep) {
+    prof_begin(0);
+    int s = launch_grid(a, nclu, st, false);
+    prof_end(0);
+    return s;
+  }
+  // split sweep: the last `tiles_g` column tiles go to virtual groups on the SMs the clusters leave idle
+  static thread_local cudaStream_t st2 = nullptr;
+  static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  static thread_local unsigned* started = nullptr;   // device word: clusters resident in the current launch
+  fused::Args a2 = a;
+  a.started = nullptr;
+  a2.started = nullptr;
+  bool split = p.split_groups > 0 && a.ntile >= 32 * (i64)(p.fncl + p.split_groups) && stream_wait_fn() != nullptr;
+  if (split) {
+    if (!st2) {
+      UM_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+      UM_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      UM_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+      UM_CUDA(cudaMalloc(&started, 256));
+    }
+    a.started = started;
+    const double wg = p.split_groups * g_split_share;
+    i64 tiles_g = (i64)((double)a.ntile * wg / ((double)p.fncl + wg) + 0.5);
+    if (tiles_g < p.split_groups) tiles_g = p.split_groups;
+    a2.tile_lo = a.ntile - tiles_g;
+    a2.cpp = p.split_groups;
+    a2.cidx_off = p.fcpp;
+    a.ntile = a2.tile_lo;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nclu * p.fG), 1, 1);
@@ -1008,10 +1084,26 @@ static int run_fused(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_b
   at[0].val.clusterDim.x = (unsigned)p.fG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   prof_begin(0);
+  if (split) {
+    UM_CUDA(cudaMemsetAsync(started, 0, 4, st));
+    UM_CUDA(cudaEventRecord(ev_fork, st));          // everything before the sweep (prep, the counter reset)
+    UM_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, fused::kernel_for(p.fR), mx, m0, a);
-  prof_end(0);
   if (e != cudaSuccess) return fail(UM_ERR_CUDA, "fused 3PRF sweep launch failed: %s", cudaGetErrorString(e));
   UM_LAUNCHED();
+  if (split) {
+    // second stream: held back by a stream memory wait until every cluster has reported itself resident, so
+    // the cooperative launch is placed on exactly the SMs the clusters leave idle
+    CUresult wr = stream_wait_fn()(reinterpret_cast<CUstream>(st2), reinterpret_cast<CUdeviceptr>(started), (cuuint32_t)nclu,
+                                   CU_STREAM_WAIT_VALUE_GEQ);
+    if (wr != CUDA_SUCCESS) return fail(UM_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)wr);
+    int s2 = launch_grid(a2, p.split_groups, st2, false);
+    if (s2 != UM_OK) return s2;
+    UM_CUDA(cudaEventRecord(ev_join, st2));
+    UM_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+  }
+  prof_end(0);
   return UM_OK;
 }
 
@@ -1153,7 +1245,7 @@ int32_t um_tprf_fused_info(int64_t T, int32_t* cluster_size, int32_t* rows_per_p
     const int path = g_tprf_path.load();
     int n = 0;
     if (G && fused::encode_fn()) {
-      if ((path == 0 && G >= 8) || path == 3) n = grid_groups(G, R);
+      if (path == 3) n = grid_groups(G, R);
       if (n <= 0) n = fused_clusters(G, R);
     }
     *resident_clusters = n;

@@ -30,7 +30,13 @@ namespace um {
 namespace fused {
 
 constexpr int CW = 16;                       // columns per tile = one 128-byte swizzle row
-constexpr int NSLOT = 3;
+constexpr int NSLOT = 3;                     // shared-memory TMA landing slots
+constexpr int NT = 4;                        // TMEM stash buffers per B-warp
+// The A-warps are throttled only by the three landing slots, whose release needs the B-warps' copy of piece
+// a-3, which follows phase B of piece a-6 in program order: the finaliser may be up to 5 pieces behind the
+// A-warps (and 8 behind the TMA producer).  The exchange rings must cover that.
+constexpr int NXR = 8;                       // ring entries of the partial / record buffers and their barriers
+constexpr int NK = 16;                       // ring of shift rows (written by TMA, read by the finaliser)
 constexpr int RMAX = 512;                    // rows per piece (per CTA of the cluster)
 constexpr int SLOT_BYTES = RMAX * CW * 8;    // 65536
 constexpr int BOX_ROWS = 128;
@@ -44,11 +50,13 @@ constexpr int STAT_SLOT = CW * NSTAT;        // doubles per slot of the partial 
 
 constexpr int OFF_SLOTS = 0;
 constexpr int OFF_SCRATCH = NSLOT * SLOT_BYTES;                 // double[NAW][SCR_W]
-constexpr int OFF_STAT = OFF_SCRATCH + NAW * SCR_W * 8;         // double[NSLOT][STAT_SLOT]
-constexpr int OFF_VREC = OFF_STAT + NSLOT * STAT_SLOT * 8;      // double[NSLOT][CW][NREC]
-constexpr int OFF_KSH = OFF_VREC + NSLOT * CW * NREC * 8;       // double[NSLOT][CW]   (row 0 of the panel: variance shift)
-constexpr int OFF_BAR = OFF_KSH + NSLOT * CW * 8;               // full[3] empty[3] statready[3] vready[3] scr_full scr_free
-constexpr int SMEM_BYTES = OFF_BAR + 16 * 8;
+constexpr int OFF_STAT = OFF_SCRATCH + NAW * SCR_W * 8;         // double[NXR][STAT_SLOT]
+constexpr int OFF_VREC = OFF_STAT + NXR * STAT_SLOT * 8;        // double[NXR][CW][NREC]
+constexpr int OFF_KSH = OFF_VREC + NXR * CW * NREC * 8;         // double[NK][CW]   (row 0 of the panel: variance shift)
+constexpr int OFF_BAR = OFF_KSH + NK * CW * 8;                  // full[3] empty[3] scr_full scr_free statready[NXR] vready[NXR]
+constexpr int NBAR = 8 + 2 * NXR;
+constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;                    // u32: TMEM base address
+constexpr int SMEM_BYTES = OFF_TMEM + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;                   // slack to align the base to 1024 (swizzle atom)
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -146,11 +154,32 @@ __device__ __forceinline__ unsigned cluster_rank() {
   return r;
 }
 
+// ---- tensor memory as an FP64 stash (tools/microbench/tmem_scratch.cu): 32x32b shape = lane i of the warp
+// owns TMEM lane 32*(warp%4)+i; a double is two consecutive 32-bit columns ----
+__device__ __forceinline__ void tmem_st8(unsigned taddr, double2 a, double2 b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__double2loint(a.x)), "r"(__double2hiint(a.x)), "r"(__double2loint(a.y)), "r"(__double2hiint(a.y)),
+               "r"(__double2loint(b.x)), "r"(__double2hiint(b.x)), "r"(__double2loint(b.y)), "r"(__double2hiint(b.y))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, unsigned (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
 struct Args {
   i64 T, N, npad, tpad;
   int L, G, R;              // cluster size, rows per piece
   int batch, cpp;           // panels, chunks per panel (a chunk = the tiles c, c + cpp, ... of one panel)
-  i64 ntile;                // column tiles per panel
+  i64 ntile;                // column tiles per panel (this launch sweeps tiles [tile_lo, ntile))
+  i64 tile_lo;
+  int cpp_out, cidx_off;    // chunk slots per panel in the output partials, and this launch's first slot
   const double* zc;         // [batch][T][8]
   double* w0;               // [batch][npad][8]
   double* invsd;            // [batch][npad]
@@ -158,6 +187,7 @@ struct Args {
   double* blockpart;        // [batch][cpp*G][81]
   double* pxp;              // [batch][cpp][tpad][8]
   double* h0p;              // [batch][cpp][tpad]
+  unsigned* started;        // optional: += 1 per cluster once it is resident (split sweep)
   long long* dbg;           // optional: [rank][warp][iter][8] clock64 stamps of cluster 0 (profiling aid)
 };
 
@@ -186,10 +216,11 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   double* kshs = reinterpret_cast<double*>(smem + OFF_KSH);
   const unsigned bar0 = sa(smem + OFF_BAR);
   auto bar_full = [&](int s) { return bar0 + 8u * s; };          // TMA landed the piece in slot s
-  auto bar_empty = [&](int s) { return bar0 + 8u * (3 + s); };   // the B-warps are done with slot s
-  auto bar_stat = [&](int s) { return bar0 + 8u * (6 + s); };    // every CTA's partials of my columns arrived
-  auto bar_vrdy = [&](int s) { return bar0 + 8u * (9 + s); };    // every column's record arrived
-  const unsigned bar_scr_full = bar0 + 8u * 12, bar_scr_free = bar0 + 8u * 13;
+  auto bar_empty = [&](int s) { return bar0 + 8u * (3 + s); };   // the A- and B-warps are done with slot s
+  const unsigned bar_scr_full = bar0 + 8u * 6, bar_scr_free = bar0 + 8u * 7;
+  auto bar_stat = [&](int x) { return bar0 + 8u * (8 + x); };        // every CTA's partials of my columns arrived
+  auto bar_vrdy = [&](int x) { return bar0 + 8u * (8 + NXR + x); };  // every column's record arrived
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + OFF_TMEM);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = g.G;
@@ -199,19 +230,31 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   const i64 T = g.T;
   const int nchunks = g.batch * g.cpp;
 
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sa(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) {
       mb_init(bar_full(s), 1);
-      mb_init(bar_empty(s), NAW);
-      mb_init(bar_stat(s), 1);   // armed per piece: expect_tx(STAT_SLOT doubles) = owned columns x G ranks x NSTAT
-      mb_init(bar_vrdy(s), 1);   // armed per piece: expect_tx(CW * 9 doubles)     = 16 columns x (V[8], 1/sd)
+      mb_init(bar_empty(s), 2 * NAW);   // the A-warps (phase A) and the B-warps (copy to tensor memory)
+    }
+    for (int x = 0; x < NXR; ++x) {
+      mb_init(bar_stat(x), 1);   // armed per piece: expect_tx(STAT_SLOT doubles) = owned columns x G ranks x NSTAT
+      mb_init(bar_vrdy(x), 1);   // armed per piece: expect_tx(CW * 9 doubles)     = 16 columns x (V[8], 1/sd)
     }
     mb_init(bar_scr_full, NAW);
     mb_init(bar_scr_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  tmem_fence_before();
   __syncthreads();
+  tmem_fence_after();
+  const unsigned tmem_base = *tmem_slot;
   cluster_sync_all();
+  // this cluster is resident: tell the host-side stream wait that holds back the grid sweep which is to
+  // fill the SMs the clusters cannot use (it must be placed AFTER them)
+  if (g.started != nullptr && rank == 0 && tid == 0) atomicAdd(g.started, 1u);
 
   const bool dbg_on = g.dbg != nullptr && cl == 0 && lane == 0;
   auto stamp = [&](int iter, int slot_) {
@@ -219,6 +262,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   };
   const unsigned slots0 = sa(smem + OFF_SLOTS);
   const int fm = lane >> 2, fk = lane & 3;
+  const int rm = (fm >> 1) + 4 * (fm & 1);   // row of an 8-row m-tile held by this lane in the phase-B fragment
 
   if (warp < NAW) {
     // ================= A-warps: column statistics of piece `it` =================
@@ -247,7 +291,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
       const i64 tv = T - grow0 - fk;                 // row 4ks + k is inside the panel iff 4ks < tv
       const int tvalid = tv > RW ? RW : (tv < 0 ? 0 : (int)tv);
       const bool need_mask = grow0 + RW > T;
-      for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
+      for (i64 tile = g.tile_lo + cidx; tile < g.ntile; tile += g.cpp, ++it) {
         const int s = it % NSLOT;
         stamp(it, 0);
         const unsigned tokf = mb_wait_token(bar_full(s), (unsigned)((it / NSLOT) & 1));
@@ -259,8 +303,8 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
 #pragma unroll
           for (int pb = 0; pb < 2; ++pb) q[mt][pb][0] = q[mt][pb][1] = 0.0;
         double ksh[2];
-        ksh[0] = ldp_f64(sa(kshs + s * CW + cola[0]) + tokf);
-        ksh[1] = ldp_f64(sa(kshs + s * CW + cola[1]) + tokf);
+        ksh[0] = ldp_f64(sa(kshs + (it % NK) * CW + cola[0]) + tokf);
+        ksh[1] = ldp_f64(sa(kshs + (it % NK) * CW + cola[1]) + tokf);
 #pragma unroll
         for (int kb = 0; kb < KS; kb += 4) {
           double a[4][2];
@@ -279,6 +323,11 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
               s2[mt][i & 1] = fma(d, d, s2[mt][i & 1]);
             }
         }
+        // done with the slot (the B-warp releases it too, once it has copied its rows to tensor memory)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) consume(q[mt][0][0] + q[mt][1][0]);   // every load of the slot has landed in a register
+        __syncwarp();
+        if (lane == 0) mb_arrive(bar_empty(s));
         // per-lane partials -> scratch (the reducer adds the 4 row phases and the 4 A-warps)
         mb_wait(bar_scr_free, (unsigned)((it & 1) ^ 1));  // the reducer is done with piece it-1 (passes at once for it = 0)
         {
@@ -296,64 +345,91 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
       }
     }
   } else if (warp < 2 * NAW) {
-    // ================= B-warps: PX / h0 of piece `it`, once every column's record is here =================
+    // ================= B-warps: copy piece n into tensor memory, then PX / h0 of piece n - LAG =================
+    // The B-warp stashes ITS rows of a piece (already in the phase-B fragment layout) as soon as TMA has
+    // landed it, so the shared-memory slot goes straight back to the producer; phase B of that piece runs
+    // LAG pieces later out of tensor memory, when every column's record has long arrived.
+    constexpr int LAG = 2;
     const int bw = warp - NAW;
     const int rowbase = bw * RW;
-    // lane (g = fm, k = fk) reads the 16-byte chunk 4s + k of row rm of each 8-row m-tile
-    const int rm = (fm >> 1) + 4 * (fm & 1);
+    const unsigned tm_warp = tmem_base + ((unsigned)(32 * bw) << 16);
     unsigned offb[2];
 #pragma unroll
     for (int s2 = 0; s2 < 2; ++s2) offb[s2] = (unsigned)((((4 * s2 + fk) ^ rm) & 7) << 4) + (unsigned)(rowbase + rm) * 128u;
     double px[MT][2], hh[MT];
 #pragma unroll
     for (int i = 0; i < MT; ++i) px[i][0] = px[i][1] = hh[i] = 0.0;
+
+    auto stash = [&](int n) {
+      const int s = n % NSLOT, tb = n % NT;
+      const unsigned tokf = mb_wait_token(bar_full(s), (unsigned)((n / NSLOT) & 1));
+      const unsigned slot = slots0 + (unsigned)s * SLOT_BYTES + tokf;
+      const unsigned tm = tm_warp + (unsigned)(tb * (MT * 8));
+#pragma unroll
+      for (int m0 = 0; m0 < MT; m0 += 4) {
+        double2 xb[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) xb[i][s2] = ldp_v2f64(slot + offb[s2] + (unsigned)(m0 + i) * 1024u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tmem_st8(tm + (unsigned)((m0 + i) * 8), xb[i][0], xb[i][1]);
+      }
+      __syncwarp();
+      if (lane == 0) mb_arrive(bar_empty(s));   // tmem_st8 consumed the loaded registers: the slot is free
+    };
+    auto phase_b = [&](int n) {
+      const int tb = n % NT, xr = n % NXR;
+      stamp(n, 3);
+      const unsigned tokv = mb_wait_token(bar_vrdy(xr), (unsigned)((n / NXR) & 1));
+      stamp(n, 4);
+      const unsigned vr = sa(vrec + xr * CW * NREC) + tokv;
+      double vf[2][2], isd[2][2];
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = 8 * s2 + 2 * fk + e;
+          vf[s2][e] = ldp_f64(vr + (c * NREC + fm) * 8);
+          isd[s2][e] = ldp_f64(vr + (c * NREC + 8) * 8);
+        }
+      tmem_wait_st();   // this warp's own stash stores (issued >= LAG pieces ago) are complete
+      const unsigned tm = tm_warp + (unsigned)(tb * (MT * 8));
+#pragma unroll
+      for (int m0 = 0; m0 < MT; m0 += 2) {
+        unsigned r[2][8];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) tmem_ld8(tm + (unsigned)((m0 + i) * 8), r[i]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const double x0 = __hiloint2double(r[i][4 * s2 + 1], r[i][4 * s2]);
+            const double x1 = __hiloint2double(r[i][4 * s2 + 3], r[i][4 * s2 + 2]);
+            f_dmma(px[m0 + i][0], px[m0 + i][1], x0, vf[s2][0]);
+            f_dmma(px[m0 + i][0], px[m0 + i][1], x1, vf[s2][1]);
+            hh[m0 + i] = fma(x0, isd[s2][0], hh[m0 + i]);
+            hh[m0 + i] = fma(x1, isd[s2][1], hh[m0 + i]);
+          }
+      }
+      stamp(n, 5);
+    };
+
     int it = 0;
     for (int ch = cl; ch < nchunks; ch += ncl) {
       const int b = ch / g.cpp, cidx = ch % g.cpp;
       const i64 grow0 = (i64)rank * R + rowbase;
-      for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
-        const int s = it % NSLOT;
-        stamp(it, 3);
-        const unsigned tokv = mb_wait_token(bar_vrdy(s), (unsigned)((it / NSLOT) & 1));
-        stamp(it, 4);
-        const unsigned vr = sa(vrec + s * CW * NREC) + tokv;
-        double vf[2][2], isd[2][2];
-#pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int c = 8 * s2 + 2 * fk + e;
-            vf[s2][e] = ldp_f64(vr + (c * NREC + fm) * 8);
-            isd[s2][e] = ldp_f64(vr + (c * NREC + 8) * 8);
-          }
-        const unsigned slot = slots0 + (unsigned)s * SLOT_BYTES + tokv;
-#pragma unroll
-        for (int m0 = 0; m0 < MT; m0 += 2) {
-          double2 x[2][2];
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) x[i][s2] = ldp_v2f64(slot + offb[s2] + (unsigned)(m0 + i) * 1024u);
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-              f_dmma(px[m0 + i][0], px[m0 + i][1], x[i][s2].x, vf[s2][0]);
-              f_dmma(px[m0 + i][0], px[m0 + i][1], x[i][s2].y, vf[s2][1]);
-              hh[m0 + i] = fma(x[i][s2].x, isd[s2][0], hh[m0 + i]);
-              hh[m0 + i] = fma(x[i][s2].y, isd[s2][1], hh[m0 + i]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < MT; ++i) consume(px[i][0]);   // every load of the slot has landed in a register
-        __syncwarp();
-        if (lane == 0) mb_arrive(bar_empty(s));
-        stamp(it, 5);
+      const int it_first = it;
+      for (i64 tile = g.tile_lo + cidx; tile < g.ntile; tile += g.cpp, ++it) {
+        stash(it);
+        if (it - LAG >= it_first) phase_b(it - LAG);
       }
+      for (int n = (it - LAG > it_first ? it - LAG : it_first); n < it; ++n) phase_b(n);   // drain
       // flush this chunk's PX / h0 partial
       {
-        double* pxo = g.pxp + ((i64)(b * g.cpp + cidx) * g.tpad) * 8;
-        double* h0o = g.h0p + (i64)(b * g.cpp + cidx) * g.tpad;
+        double* pxo = g.pxp + ((i64)(b * g.cpp_out + g.cidx_off + cidx) * g.tpad) * 8;
+        double* h0o = g.h0p + (i64)(b * g.cpp_out + g.cidx_off + cidx) * g.tpad;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           double h = hh[mt];
@@ -375,7 +451,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
       int it = 0;
       for (int ch = cl; ch < nchunks; ch += ncl) {
         const int b = ch / g.cpp, cidx = ch % g.cpp;
-        for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
+        for (i64 tile = g.tile_lo + cidx; tile < g.ntile; tile += g.cpp, ++it) {
           const int s = it % NSLOT;
           if (it >= NSLOT) mb_wait(bar_empty(s), (unsigned)((it / NSLOT - 1) & 1));
           mb_expect_tx(bar_full(s), piece_bytes);
@@ -383,7 +459,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
 #pragma unroll
           for (int bx = 0; bx < J; ++bx)
             tma_3d(dst + bx * BOX_ROWS * CW * 8, &map_x, (int)(tile * CW), rank * R + bx * BOX_ROWS, b, bar_full(s));
-          tma_3d(sa(kshs + s * CW), &map_row0, (int)(tile * CW), 0, b, bar_full(s));
+          tma_3d(sa(kshs + (it % NK) * CW), &map_row0, (int)(tile * CW), 0, b, bar_full(s));
         }
       }
     }
@@ -410,14 +486,14 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
     int it = 0;
     for (int ch = cl; ch < nchunks; ch += ncl) {
       const int b = ch / g.cpp, cidx = ch % g.cpp;
-      for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
-        const int s = it % NSLOT;
+      for (i64 tile = g.tile_lo + cidx; tile < g.ntile; tile += g.cpp, ++it) {
+        const int s = it % NXR;  // ring entry of the exchange buffers and barriers
         if (lane == 0) {
           mb_expect_tx(bar_vrdy(s), CW * 9 * 8);
           mb_expect_tx(bar_stat(s), STAT_SLOT * 8);
         }
         stamp(it, 0);
-        mb_wait(bar_stat(s), (unsigned)((it / NSLOT) & 1));
+        mb_wait(bar_stat(s), (unsigned)((it / NXR) & 1));
         stamp(it, 1);
         const unsigned sb = sa(statbuf + s * STAT_SLOT);
         for (int oc0 = 0; oc0 < owned; oc0 += cpr) {
@@ -451,7 +527,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
           }
           const i64 gcol = tile * CW + col;
           const bool valid = gcol < g.N;
-          const double k0 = lds_f64(sa(kshs + s * CW + col));
+          const double k0 = lds_f64(sa(kshs + (it % NK) * CW + col));
           // short dependent chain (this warp shares the FP64 pipe with the DMMA stream, every dependent
           // FP64 instruction costs a pipe round trip): reciprocals instead of divisions, 1/sd from an
           // rsqrt seed + two Newton steps (relative error ~1e-16; the parity bar is 1e-9)
@@ -521,7 +597,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
           vals[i] = ((x0 + x1) + x2) + x3;
         }
         if (lg == 0) {
-          double* bp = g.blockpart + ((i64)(b * g.cpp + cidx) * G + rank) * NSMALL;
+          double* bp = g.blockpart + ((i64)(b * g.cpp_out + g.cidx_off + cidx) * G + rank) * NSMALL;
           bp[l] = vals[0];
 #pragma unroll
           for (int c = 0; c < 8; ++c) bp[8 + l * 8 + c] = vals[1 + c];
@@ -557,8 +633,8 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
     int it = 0;
     for (int ch = cl; ch < nchunks; ch += ncl) {
       const int cidx = ch % g.cpp;
-      for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
-        const int s = it % NSLOT;
+      for (i64 tile = g.tile_lo + cidx; tile < g.ntile; tile += g.cpp, ++it) {
+        const int s = it % NXR;
         stamp(it, 0);
         mb_wait(bar_scr_full, (unsigned)(it & 1));
         stamp(it, 1);
@@ -589,7 +665,10 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
       }
     }
   }
+  tmem_fence_before();
   __syncthreads();
+  tmem_fence_after();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   cluster_sync_all();  // nobody leaves while a peer may still write into its shared memory
 }
 

@@ -29,7 +29,6 @@ namespace gridk {
 
 using namespace fused;
 
-constexpr int NT = 4;                        // TMEM stash buffers per A/B warp pair
 constexpr int NX = 8;                        // entries of the global exchange rings
 constexpr int PSTRIDE = 12;                  // doubles per (rank, column) partial: s1, s2, q[8], shift, pad
 constexpr int PART_ENTRY = GMAX * CW * PSTRIDE;   // 16-byte cells per ring entry of the partial buffer (G <= GMAX ranks)
@@ -82,23 +81,6 @@ __device__ __forceinline__ void ll_load_n(const uint4* const (&cell)[N], unsigne
     __nanosleep(200);
   }
 }
-__device__ __forceinline__ void tmem_st8(unsigned taddr, double2 a, double2 b) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-               "r"(__double2loint(a.x)), "r"(__double2hiint(a.x)), "r"(__double2loint(a.y)), "r"(__double2hiint(a.y)),
-               "r"(__double2loint(b.x)), "r"(__double2hiint(b.x)), "r"(__double2loint(b.y)), "r"(__double2hiint(b.y))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(unsigned taddr, unsigned (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
 template <int J>
 __global__ void __launch_bounds__(G_NTHREADS, 1)
 k_tprf_grid(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_row0, const GArgs ga) {
@@ -194,7 +176,7 @@ k_tprf_grid(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
       const i64 tv = T - grow0 - fk;
       const int tvalid = tv > RW ? RW : (tv < 0 ? 0 : (int)tv);
       const bool need_mask = grow0 + RW > T;
-      for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
+      for (i64 tile = g.tile_lo + cidx; tile < g.ntile; tile += g.cpp, ++it) {
         const int s = it % NSLOT, tb = it % NT;
         stamp(it, 0);
         const unsigned tokf = mb_wait_token(bar_full(s), (unsigned)((it / NSLOT) & 1));
@@ -278,7 +260,7 @@ k_tprf_grid(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
     for (int ch = cl; ch < nchunks; ch += ngroups) {
       const int b = ch / g.cpp, cidx = ch % g.cpp;
       const i64 grow0 = (i64)rank * R + rowbase;
-      for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
+      for (i64 tile = g.tile_lo + cidx; tile < g.ntile; tile += g.cpp, ++it) {
         const int tb = it % NT, e = it % NX;
         const unsigned tag = (unsigned)(it / NX + 1);
         stamp(it, 0);
@@ -335,8 +317,8 @@ k_tprf_grid(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
       }
       // flush this chunk's PX / h0 partial
       {
-        double* pxo = g.pxp + ((i64)(b * g.cpp + cidx) * g.tpad) * 8;
-        double* h0o = g.h0p + (i64)(b * g.cpp + cidx) * g.tpad;
+        double* pxo = g.pxp + ((i64)(b * g.cpp_out + g.cidx_off + cidx) * g.tpad) * 8;
+        double* h0o = g.h0p + (i64)(b * g.cpp_out + g.cidx_off + cidx) * g.tpad;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           double h = hh[mt];
@@ -358,7 +340,7 @@ k_tprf_grid(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
       int it = 0;
       for (int ch = cl; ch < nchunks; ch += ngroups) {
         const int b = ch / g.cpp, cidx = ch % g.cpp;
-        for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
+        for (i64 tile = g.tile_lo + cidx; tile < g.ntile; tile += g.cpp, ++it) {
           const int s = it % NSLOT;
           if (it >= NSLOT) mb_wait(bar_empty(s), (unsigned)((it / NSLOT - 1) & 1));
           mb_expect_tx(bar_full(s), piece_bytes);
@@ -384,7 +366,7 @@ k_tprf_grid(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
     int it = 0;
     for (int ch = cl; ch < nchunks; ch += ngroups) {
       const int b = ch / g.cpp, cidx = ch % g.cpp;
-      for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
+      for (i64 tile = g.tile_lo + cidx; tile < g.ntile; tile += g.cpp, ++it) {
         const int e = it % NX;
         const unsigned tag = (unsigned)(it / NX + 1);
         stamp(it, 0);
@@ -492,7 +474,7 @@ k_tprf_grid(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
           vals[i] = ((x0 + x1) + x2) + x3;
         }
         if (lg == 0) {
-          double* bp = g.blockpart + ((i64)(b * g.cpp + cidx) * G + rank) * NSMALL;
+          double* bp = g.blockpart + ((i64)(b * g.cpp_out + g.cidx_off + cidx) * G + rank) * NSMALL;
           bp[l] = vals[0];
 #pragma unroll
           for (int c = 0; c < 8; ++c) bp[8 + l * 8 + c] = vals[1 + c];
@@ -511,7 +493,7 @@ k_tprf_grid(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
     int it = 0;
     for (int ch = cl; ch < nchunks; ch += ngroups) {
       const int cidx = ch % g.cpp;
-      for (i64 tile = cidx; tile < g.ntile; tile += g.cpp, ++it) {
+      for (i64 tile = g.tile_lo + cidx; tile < g.ntile; tile += g.cpp, ++it) {
         const int e = it % NX;
         mb_wait(bar_scr_full, (unsigned)(it & 1));
         stamp(it, 1);

@@ -97,10 +97,10 @@ def forecast3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full")
     return estimate3prf(y, X, Z, procedure).forecasts
 
 
-TPRF_PATH_AUTO, TPRF_PATH_TWO_SWEEP, TPRF_PATH_FUSED = 0, 1, 2
+TPRF_PATH_AUTO, TPRF_PATH_TWO_SWEEP, TPRF_PATH_FUSED, TPRF_PATH_GRID = 0, 1, 2, 3
 
 
 def set_tprf_path(path: int) -> None:
-    """0 = auto (single-read cluster sweep whenever it applies), 1 = two sweeps only, 2 = single-read
-    sweep or ValueError.  Process-wide switch for tests and profiling (um_tprf_set_path)."""
+    """0 = auto (single-read sweeps whenever they apply), 1 = two sweeps only, 2 = cluster sweep or
+    ValueError, 3 = grid sweep (virtual CTA groups, tensor-memory stash) or ValueError.  Process-wide switch for tests and profiling (um_tprf_set_path)."""
     check(lib.um_tprf_set_path(int(path)))
