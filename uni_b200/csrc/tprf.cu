@@ -78,14 +78,32 @@ __device__ __forceinline__ void stage_box(double* sm, int pitch, const double* _
 // ---- prep: Zc (T x 8, zero padded), zbar, Szz, ybar, ssy ------------------------------------------------
 // small[] layout per panel: zbar[8] | Szz[64] | ybar | ssy | (pad to 80)
 constexpr int SMALL_PREP = 80;
+constexpr int FIN_CS = 8;   // cluster size of the row-parallel prep / finish kernels
+__device__ __forceinline__ unsigned t_cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void t_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void t_st_cluster(double* local_addr, unsigned rank, double v) {
+  unsigned la = (unsigned)__cvta_generic_to_shared(local_addr), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+template <int CS>   // CS > 1: a cluster of CS CTAs, each a slice of the rows (one panel only)
 __global__ void __launch_bounds__(256) k_tprf_prep(const double* __restrict__ Z, i64 z_rs, i64 z_cs, i64 z_bs,
                                                     const double* __restrict__ y, i64 y_s, i64 y_bs, i64 T, int L,
                                                     double* __restrict__ zc, double* __restrict__ small) {
   __shared__ double red[8][48];
+  __shared__ double cbuf[2][CS][48];
+  const int crank = CS > 1 ? (int)t_cluster_rank() : 0;
+  constexpr int STRIDE = 256 * CS;
   __shared__ double zbar[LP];
   __shared__ double ybar_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const i64 b = blockIdx.z;
+  const i64 b = blockIdx.z;   // CS > 1 is launched for one panel
   Z += b * z_bs;
   y += b * y_bs;
   zc += b * T * LP;
@@ -94,7 +112,7 @@ __global__ void __launch_bounds__(256) k_tprf_prep(const double* __restrict__ Z,
   double acc[LP + 1];
 #pragma unroll
   for (int l = 0; l <= LP; ++l) acc[l] = 0.0;
-  for (i64 t = tid; t < T; t += 256) {
+  for (i64 t = (i64)crank * 256 + tid; t < T; t += STRIDE) {
 #pragma unroll
     for (int l = 0; l < LP; ++l)
       if (l < L) acc[l] += Z[t * z_rs + l * z_cs];
@@ -107,9 +125,18 @@ __global__ void __launch_bounds__(256) k_tprf_prep(const double* __restrict__ Z,
     if (lane == 0) red[warp][l] = v;
   }
   __syncthreads();
+  if (CS > 1) {   // CTA totals -> every CTA of the cluster, then a rank-order sum (identical everywhere)
+    if (tid <= LP) {
+      double v = 0.0;
+      for (int w = 0; w < 8; ++w) v += red[w][tid];
+      for (unsigned r = 0; r < (unsigned)CS; ++r) t_st_cluster(&cbuf[0][crank][tid], r, v);
+    }
+    t_cluster_sync();
+  }
   if (tid <= LP) {
     double v = 0.0;
-    for (int w = 0; w < 8; ++w) v += red[w][tid];
+    if (CS > 1) for (int r = 0; r < CS; ++r) v += cbuf[0][r][tid];
+    else for (int w = 0; w < 8; ++w) v += red[w][tid];
     v /= (double)T;
     if (tid < LP) zbar[tid] = v;
     else ybar_s = v;
@@ -121,7 +148,7 @@ __global__ void __launch_bounds__(256) k_tprf_prep(const double* __restrict__ Z,
   for (int i = 0; i < 36; ++i) sz[i] = 0.0;
   double ssy = 0.0;
   const double yb = ybar_s;
-  for (i64 t = tid; t < T; t += 256) {
+  for (i64 t = (i64)crank * 256 + tid; t < T; t += STRIDE) {
     double z[LP];
 #pragma unroll
     for (int l = 0; l < LP; ++l) {
@@ -147,10 +174,20 @@ __global__ void __launch_bounds__(256) k_tprf_prep(const double* __restrict__ Z,
   if (tid < 37) {
     double v = 0.0;
     for (int w = 0; w < 8; ++w) v += red[w][tid];
-    red[0][tid] = v;
+    if (CS > 1) for (unsigned r = 0; r < (unsigned)CS; ++r) t_st_cluster(&cbuf[1][crank][tid], r, v);
+    else red[0][tid] = v;
   }
   __syncthreads();
-  if (tid == 0) {
+  if (CS > 1) {
+    t_cluster_sync();
+    if (tid < 37) {
+      double v = 0.0;
+      for (int r = 0; r < CS; ++r) v += cbuf[1][r][tid];
+      red[0][tid] = v;
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && crank == 0) {
     for (int l = 0; l < LP; ++l) small[l] = zbar[l];
     int q = 0;
     for (int a = 0; a < LP; ++a)
@@ -450,8 +487,12 @@ struct FinishArgs {
 };
 constexpr int PARAMS = 96;
 
-template <int NV>
-__device__ __forceinline__ void block_sum(double* loc, double (*red)[64], double* result, int tid) {
+// Sum of NV per-thread values over the CTA and, when the kernel runs as a cluster of CS CTAs (each CTA a slice
+// of the rows), over the cluster: every CTA writes its CTA totals into slot [rank] of EVERY CTA's `cbuf`
+// (distributed shared memory), one cluster barrier, then everyone adds the CS slots in rank order -- all
+// CTAs end up with bit-identical totals and redo the tiny serial algebra that follows redundantly.
+template <int NV, int CS>
+__device__ __forceinline__ void block_sum(double* loc, double (*red)[64], double* result, int tid, double (*cbuf)[64] = nullptr) {
   const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -460,22 +501,42 @@ __device__ __forceinline__ void block_sum(double* loc, double (*red)[64], double
     if (lane == 0) red[warp][i] = x;
   }
   __syncthreads();
-  if (tid < NV) {
-    double x = 0.0;
-    for (int w = 0; w < 8; ++w) x += red[w][tid];
-    result[tid] = x;
+  if (CS == 1) {
+    if (tid < NV) {
+      double x = 0.0;
+      for (int w = 0; w < 8; ++w) x += red[w][tid];
+      result[tid] = x;
+    }
+    __syncthreads();
+  } else {
+    if (tid < NV) {
+      double x = 0.0;
+      for (int w = 0; w < 8; ++w) x += red[w][tid];
+      const unsigned me = t_cluster_rank();
+      for (unsigned r = 0; r < (unsigned)CS; ++r) t_st_cluster(&cbuf[me][tid], r, x);
+    }
+    t_cluster_sync();
+    if (tid < NV) {
+      double x = 0.0;
+      for (int r = 0; r < CS; ++r) x += cbuf[r][tid];
+      result[tid] = x;
+    }
+    __syncthreads();
   }
-  __syncthreads();
 }
 
+template <int CS>
 __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
   __shared__ double red[8][64];
   __shared__ double tot[64];
+  __shared__ double cbuf[4][CS][64];   // one exchange buffer per reduction stage (no reuse, no second barrier)
+  const int crank = CS > 1 ? (int)t_cluster_rank() : 0;
+  constexpr int STRIDE = 256 * CS;
   __shared__ double sw[LP], smw[LP], wbar[LP], s_cl[LP], szzinv[LP * LP], m2[(LP + 1) * LP], beta[LP + 1];
   __shared__ double smu_s, ybar_s, ssy_s;
   __shared__ int singular_s;
   const int tid = threadIdx.x;
-  const i64 b = blockIdx.x;
+  const i64 b = blockIdx.x / CS;
   const i64 T = g.T;
   const int L = g.L, L1 = g.L + 1;
   const double* px = g.packed + b * g.packed_stride;
@@ -509,7 +570,7 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
     double loc[44];
 #pragma unroll
     for (int i = 0; i < 44; ++i) loc[i] = 0.0;
-    for (i64 t = tid; t < T; t += 256) {
+    for (i64 t = (i64)crank * 256 + tid; t < T; t += STRIDE) {
       double gl[LP];
       const double r = h0[t] - smu;
 #pragma unroll
@@ -523,7 +584,7 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
 #pragma unroll
       for (int l = 0; l < LP; ++l) loc[36 + l] += gl[l] * yt;
     }
-    block_sum<44>(loc, red, tot, tid);
+    block_sum<44, CS>(loc, red, tot, tid, cbuf[0]);
     if (tid == 0) {
       double core[LP * LP], inv[LP * LP], rhs[LP];
       int q = 0;
@@ -547,7 +608,7 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
     __syncthreads();
     if (g.mode == UM_TPRF_CLOSED) {
       double see = 0.0;
-      for (i64 t = tid; t < T; t += 256) {
+      for (i64 t = (i64)crank * 256 + tid; t < T; t += STRIDE) {
         const double r = h0[t] - smu;
         double f = 0.0;
 #pragma unroll
@@ -560,7 +621,7 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
         see += e * e;
       }
       double l1[1] = {see};
-      block_sum<1>(l1, red, tot, tid);
+      block_sum<1, CS>(l1, red, tot, tid, cbuf[1]);
       r2 = ssy == 0.0 ? 0.0 : 1.0 - tot[0] / ssy;  // Tprf3.scala:239-241
     }
   }
@@ -619,7 +680,7 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
     double loc[54];
 #pragma unroll
     for (int i = 0; i < 54; ++i) loc[i] = 0.0;
-    for (i64 t = tid; t < T; t += 256) {
+    for (i64 t = (i64)crank * 256 + tid; t < T; t += STRIDE) {
       double d[LP + 1];
       d[0] = 1.0;
       const double h = h0[t];
@@ -643,7 +704,7 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
 #pragma unroll
       for (int a = 0; a <= LP; ++a) loc[45 + a] += d[a] * yt;
     }
-    block_sum<54>(loc, red, tot, tid);
+    block_sum<54, CS>(loc, red, tot, tid, cbuf[2]);
     if (tid == 0) {
       double full[LP + 1][LP + 1];
       int q = 0;
@@ -663,7 +724,7 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
     }
     __syncthreads();
     double see = 0.0;
-    for (i64 t = tid; t < T; t += 256) {
+    for (i64 t = (i64)crank * 256 + tid; t < T; t += STRIDE) {
       double f = beta[0];
 #pragma unroll
       for (int l = 0; l < LP; ++l) f += sig_ws[t * LP + l] * beta[1 + l];
@@ -675,12 +736,13 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
         for (int l = 0; l < L; ++l) g.sigma[(b * T + t) * L + l] = sig_ws[t * LP + l];
     }
     double l1[1] = {see};
-    block_sum<1>(l1, red, tot, tid);
+    block_sum<1, CS>(l1, red, tot, tid, cbuf[3]);
     if (g.mode == UM_TPRF_ITER) r2 = ssy == 0.0 ? 0.0 : 1.0 - tot[0] / ssy;  // Tprf3.scala:274-275
     else r2 = 1.0 - tot[0] / ssy;                                             // Tprf3.scala:1214-1225
-    if (g.beta3 && tid < L1) g.beta3[b * L1 + tid] = beta[tid];
+    if (crank == 0 && g.beta3 && tid < L1) g.beta3[b * L1 + tid] = beta[tid];
   }
   __syncthreads();
+  if (crank != 0) return;
   if (tid < LP) {
     par[tid] = s_cl[tid];
     par[8 + tid] = wbar[tid];
@@ -1168,9 +1230,22 @@ static int run_prep(const Plan3& p, char* ws, const double* Z, i64 z_rs, i64 z_c
                     i64 y_bs) {
   dim3 grid(1, 1, (unsigned)p.batch);
     prof_begin(7);
-  k_tprf_prep<<<grid, 256, 0, ctx()->stream>>>(Z, z_rs, z_cs, z_bs, y, y_s, y_bs, p.T, (int)p.L,
-                                                reinterpret_cast<double*>(ws + p.o_zc),
-                                                reinterpret_cast<double*>(ws + p.o_small));
+  double* zc_out = reinterpret_cast<double*>(ws + p.o_zc);
+  double* small_out = reinterpret_cast<double*>(ws + p.o_small);
+  if (p.batch == 1 && p.T >= 2048) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(FIN_CS, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.stream = ctx()->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = FIN_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const int Li = (int)p.L;
+    UM_CUDA(cudaLaunchKernelEx(&cfg, k_tprf_prep<FIN_CS>, Z, z_rs, z_cs, z_bs, y, y_s, y_bs, p.T, Li, zc_out, small_out));
+  } else {
+    k_tprf_prep<1><<<grid, 256, 0, ctx()->stream>>>(Z, z_rs, z_cs, z_bs, y, y_s, y_bs, p.T, (int)p.L, zc_out, small_out);
+  }
   prof_end(7);
     UM_LAUNCHED();
   return UM_OK;
@@ -1190,7 +1265,21 @@ static int run_finish(const Plan3& p, char* ws, int mode, const double* y, i64 y
   g.params = reinterpret_cast<double*>(ws + p.o_par);
   g.r2_out = r2_dev;
     prof_begin(4);
-  k_tprf_finish<<<(unsigned)p.batch, 256, 0, ctx()->stream>>>(g);
+  if (p.batch == 1 && p.T >= 2048) {
+    // one panel: a cluster of FIN_CS CTAs, each a slice of the rows (the kernel is latency-bound on its
+    // row loops: 111 -> ~30 us at T = 8192, which is what the 8-GPU scaling of a 0.5 ms sweep needs)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(FIN_CS, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.stream = ctx()->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = FIN_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    UM_CUDA(cudaLaunchKernelEx(&cfg, k_tprf_finish<FIN_CS>, g));
+  } else {
+    k_tprf_finish<1><<<(unsigned)p.batch, 256, 0, ctx()->stream>>>(g);
+  }
   prof_end(4);
     UM_LAUNCHED();
   return UM_OK;
