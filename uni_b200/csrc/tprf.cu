@@ -530,6 +530,8 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
   __shared__ double red[8][64];
   __shared__ double tot[64];
   __shared__ double cbuf[4][CS][64];   // one exchange buffer per reduction stage (no reuse, no second barrier)
+  __shared__ double lu_a[81], lu_inv[81], lu_x[81];   // warp-cooperative small inverses (small_linalg.cuh)
+  __shared__ int lu_piv[9];
   const int crank = CS > 1 ? (int)t_cluster_rank() : 0;
   constexpr int STRIDE = 256 * CS;
   __shared__ double sw[LP], smw[LP], wbar[LP], s_cl[LP], szzinv[LP * LP], m2[(LP + 1) * LP], beta[LP + 1];
@@ -585,24 +587,23 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
       for (int l = 0; l < LP; ++l) loc[36 + l] += gl[l] * yt;
     }
     block_sum<44, CS>(loc, red, tot, tid, cbuf[0]);
-    if (tid == 0) {
-      double core[LP * LP], inv[LP * LP], rhs[LP];
-      int q = 0;
-      double full[LP][LP];
-      for (int a = 0; a < LP; ++a)
-        for (int c = a; c < LP; ++c) { full[a][c] = tot[q]; full[c][a] = tot[q]; ++q; }
-      for (int a = 0; a < L; ++a) {
-        for (int c = 0; c < L; ++c) core[a * L + c] = full[a][c];
-        rhs[a] = tot[36 + a];
+    if (tid < 32) {
+      if (tid == 0) {
+        int q = 0;
+        double full[LP][LP];
+        for (int a = 0; a < LP; ++a)
+          for (int c = a; c < LP; ++c) { full[a][c] = tot[q]; full[c][a] = tot[q]; ++q; }
+        for (int a = 0; a < L; ++a)
+          for (int c = 0; c < L; ++c) lu_a[a * L + c] = full[a][c];
       }
-      bool ok = lu_inverse_seq(core, L, inv);
-      if (!ok) singular_s = 1;
-      for (int a = 0; a < LP; ++a) {
+      __syncwarp();
+      const bool ok = lu_inverse_warp(lu_a, L, lu_inv, lu_x, lu_piv, tid);
+      if (tid == 0 && !ok) singular_s = 1;
+      if (tid < LP) {
         double s = 0.0;
-        if (ok && a < L)
-          for (int c = 0; c < L; ++c) s += inv[a * L + c] * rhs[c];
-        s_cl[a] = ok ? s : nan("");
-        if (a >= L) s_cl[a] = 0.0;
+        if (ok && tid < L)
+          for (int c = 0; c < L; ++c) s += lu_inv[tid * L + c] * tot[36 + c];
+        s_cl[tid] = tid >= L ? 0.0 : (ok ? s : nan(""));
       }
     }
     __syncthreads();
@@ -628,11 +629,14 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
 
   if (g.mode != UM_TPRF_CLOSED) {
     // ---- three-pass fit from the same accumulators ----
-    if (tid == 0) {
-      double szz[LP * LP], tmp[LP * LP];
-      for (int a = 0; a < L; ++a)
-        for (int c = 0; c < L; ++c) szz[a * L + c] = small[8 + a * LP + c];
-      bool ok = lu_inverse_seq(szz, L, tmp);
+    if (tid < 32) {
+      if (tid == 0)
+        for (int a = 0; a < L; ++a)
+          for (int c = 0; c < L; ++c) lu_a[a * L + c] = small[8 + a * LP + c];
+      __syncwarp();
+      const bool ok = lu_inverse_warp(lu_a, L, lu_inv, lu_x, lu_piv, tid);
+      if (tid == 0) {
+      const double* tmp = lu_inv;
       if (!ok) singular_s = 1;
       for (int a = 0; a < LP; ++a)
         for (int c = 0; c < LP; ++c) szzinv[a * LP + c] = (ok && a < L && c < L) ? tmp[a * L + c] : (ok ? 0.0 : nan(""));
@@ -655,14 +659,18 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
           for (int k = 0; k < L; ++k) s += sww_i[a * L + k] * szzinv[c * LP + k];
           pp[a * L + c] = s;
         }
-      double ptp[(LP + 1) * (LP + 1)], ptpinv[(LP + 1) * (LP + 1)];
+      double* ptp = lu_a;
       ptp[0] = g.n_total;
       for (int a = 0; a < L; ++a) {
         ptp[0 * L1 + 1 + a] = phisum[a];
         ptp[(1 + a) * L1 + 0] = phisum[a];
         for (int c = 0; c < L; ++c) ptp[(1 + a) * L1 + 1 + c] = 0.5 * (pp[a * L + c] + pp[c * L + a]);
       }
-      bool ok2 = lu_inverse_seq(ptp, L1, ptpinv);
+      }
+      __syncwarp();
+      const bool ok2 = lu_inverse_warp(lu_a, L1, lu_inv, lu_x, lu_piv, tid);
+      if (tid == 0) {
+      const double* ptpinv = lu_inv;
       if (!ok2) singular_s = 1;
       // Sigma[t][l] = sum_m XP[t][m] PtPinv[1+l][m],  XP[t][0] = h0[t],  XP[t][1+a] = sum_c PX[t][c] szzinv[c][a]
       // fold into m2: Sigma[t][l] = m2[0][l] h0[t] + sum_c m2[1+c][l] PX[t][c]
@@ -674,6 +682,7 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
             for (int a = 0; a < L; ++a) s += szzinv[c * LP + a] * ptpinv[(1 + l) * L1 + 1 + a];
           m2[(1 + c) * LP + l] = (ok2 || !(l < L && c < L)) ? s : nan("");
         }
+      }
       }
     }
     __syncthreads();
@@ -705,21 +714,23 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
       for (int a = 0; a <= LP; ++a) loc[45 + a] += d[a] * yt;
     }
     block_sum<54, CS>(loc, red, tot, tid, cbuf[2]);
-    if (tid == 0) {
-      double full[LP + 1][LP + 1];
-      int q = 0;
-      for (int a = 0; a <= LP; ++a)
-        for (int c = a; c <= LP; ++c) { full[a][c] = tot[q]; full[c][a] = tot[q]; ++q; }
-      double A[(LP + 1) * (LP + 1)], Ai[(LP + 1) * (LP + 1)];
-      for (int a = 0; a < L1; ++a)
-        for (int c = 0; c < L1; ++c) A[a * L1 + c] = full[a][c];
-      bool ok = lu_inverse_seq(A, L1, Ai);
-      if (!ok) singular_s = 1;
-      for (int a = 0; a <= LP; ++a) {
+    if (tid < 32) {
+      if (tid == 0) {
+        double full[LP + 1][LP + 1];
+        int q = 0;
+        for (int a = 0; a <= LP; ++a)
+          for (int c = a; c <= LP; ++c) { full[a][c] = tot[q]; full[c][a] = tot[q]; ++q; }
+        for (int a = 0; a < L1; ++a)
+          for (int c = 0; c < L1; ++c) lu_a[a * L1 + c] = full[a][c];
+      }
+      __syncwarp();
+      const bool ok = lu_inverse_warp(lu_a, L1, lu_inv, lu_x, lu_piv, tid);
+      if (tid == 0 && !ok) singular_s = 1;
+      if (tid <= LP) {
         double s = 0.0;
-        if (a < L1)
-          for (int c = 0; c < L1; ++c) s += Ai[a * L1 + c] * tot[45 + c];
-        beta[a] = a < L1 ? (ok ? s : nan("")) : 0.0;
+        if (tid < L1)
+          for (int c = 0; c < L1; ++c) s += lu_inv[tid * L1 + c] * tot[45 + c];
+        beta[tid] = tid < L1 ? (ok ? s : nan("")) : 0.0;
       }
     }
     __syncthreads();
