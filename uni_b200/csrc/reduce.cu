@@ -10,6 +10,8 @@
 // Ordering for min/max/arg*/idx* is java.lang.Double.compare with "earliest wins ties"
 // (Mat.scala:470-548,892-895; MatPandasOps.scala:20-64): reduce (total-order key, logical
 // index) pairs, which is associative and commutative, so any tree gives the scan's answer.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace um {
@@ -850,6 +852,12 @@ constexpr int OC_CAP = 2 * OC_CTA_VECS * 2;                      // 32768 with a
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Cluster barrier whose release is paid by ONE thread: the writer of the exchanged value fences, everybody
+// arrives relaxed.  (A releasing arrive makes every thread wait for its own outstanding streaming stores.)
+__device__ __forceinline__ void cluster_sync_light(bool i_wrote) {
+  if (i_wrote) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ double ld_peer_f64(const double* local_smem, unsigned rank) {
   unsigned la = (unsigned)__cvta_generic_to_shared(local_smem), ra;
   double v;
@@ -859,117 +867,154 @@ __device__ __forceinline__ double ld_peer_f64(const double* local_smem, unsigned
 }
 
 template <int CS>
-__global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const double* __restrict__ p, i64 s_lane, i64 n_red,
-                                                                       double* __restrict__ out, i64 o_lane) {
+__global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const double* __restrict__ p, i64 s_lane, i64 n_lane, i64 n_red,
+                                                                       double* __restrict__ out, i64 o_lane, long long stagger_cycles) {
+  // Persistent: cluster k takes rows k, k + #clusters, ...  While a thread normalises and stores chunk c of
+  // row i it refills the same shared-memory slot with chunk c of row i+1 (cp.async), so the next row's
+  // loads are in flight during this row's stores and have landed by the time its max pass starts; the
+  // exp phase of one CTA overlaps the load/store phase of the other CTA on the SM.
   extern __shared__ __align__(16) double2 sx[];   // chunk c of thread t at sx[c * OC_THREADS + t]
   __shared__ double sm_red[OC_THREADS / 32];
-  __shared__ double sm_x[2];                      // [0] this CTA's max, [1] this CTA's sum (read by the peer)
+  __shared__ double sm_x[2][2];                   // [row parity][0] this CTA's max, [..][1] its sum (read by the peer)
   const int t = threadIdx.x;
   unsigned rank = 0;
   if (CS > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-  const i64 row = blockIdx.x / CS;
-  const double* base = p + row * s_lane;
-  double* obase = out + row * o_lane;
+  const i64 nclusters = gridDim.x / CS;
   const i64 nv = n_red >> 1;                       // whole double2 vectors of the row
   const i64 v0 = (i64)rank * OC_CTA_VECS;          // first vector owned by this CTA
-#pragma unroll
-  for (int c = 0; c < OC_SMEM_CHUNKS; ++c) {
+  const bool odd_tail = (n_red & 1) && t == 0 && rank == 0;
+
+  auto issue_smem = [&](const double* base, int c) {
     const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
     if (v < nv) {
       unsigned sa = (unsigned)__cvta_generic_to_shared(&sx[c * OC_THREADS + t]);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(base + 2 * v) : "memory");
     }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  double2 r[OC_REG];
+  };
+  i64 row = blockIdx.x / CS;
+  if (row >= n_lane) return;   // whole cluster at once: nobody is left waiting at a cluster barrier
+  {
+    const double* base = p + row * s_lane;
 #pragma unroll
-  for (int c = 0; c < OC_REG; ++c) {
-    const i64 v = v0 + (i64)c * OC_THREADS + t;
-    r[c] = v < nv ? *reinterpret_cast<const double2*>(base + 2 * v) : make_double2(-INFINITY, -INFINITY);
+    for (int c = 0; c < OC_SMEM_CHUNKS; ++c) issue_smem(base, c);
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  const bool odd_tail = (n_red & 1) && t == 0 && rank == 0;
-  double xt = odd_tail ? base[n_red - 1] : -INFINITY;
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  // ---- max (fmax drops NaNs; a NaN still poisons the sum) ----
-  double mx = fmax(xt, fmax(fmax(r[0].x, r[0].y), fmax(r[1].x, r[1].y)));
+  // Two CTAs share an SM; left alone they fall into lockstep (both in the FP64-bound exp phase, then both in
+  // the memory phase).  Every other cluster starts half a period late so one CTA computes while the other
+  // moves data.
+  if (((blockIdx.x / CS) & 1) && n_lane > nclusters) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < stagger_cycles) {}
+  }
+  int par = 0;
+  double2 rn[OC_REG];   // register-held chunks of the NEXT row, loaded during this row's store phase
+  double xtn;
+  {
+    const double* base = p + row * s_lane;
 #pragma unroll
-  for (int c = 0; c < OC_SMEM_CHUNKS; ++c) {
-    const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
-    if (v < nv) {
-      double2 x = sx[c * OC_THREADS + t];
-      mx = fmax(mx, fmax(x.x, x.y));
+    for (int c = 0; c < OC_REG; ++c) {
+      const i64 v = v0 + (i64)c * OC_THREADS + t;
+      rn[c] = v < nv ? *reinterpret_cast<const double2*>(base + 2 * v) : make_double2(-INFINITY, -INFINITY);
     }
+    xtn = odd_tail ? base[n_red - 1] : -INFINITY;
   }
-  for (int d = 16; d > 0; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-  if ((t & 31) == 0) sm_red[t >> 5] = mx;
-  __syncthreads();
-  if (t == 0) {
-    double m = sm_red[0];
-    for (int w = 1; w < OC_THREADS / 32; ++w) m = fmax(m, sm_red[w]);
-    sm_x[0] = m;
-  }
-  __syncthreads();
-  if (CS > 1) {
-    cluster_sync_all();
-    mx = fmax(ld_peer_f64(&sm_x[0], 0), ld_peer_f64(&sm_x[0], 1));
-  } else {
-    mx = sm_x[0];
-  }
-  // ---- exp (kept on chip) and sum ----
-  double s = 0.0;
+  for (; row < n_lane; row += nclusters, par ^= 1) {
+    double* obase = out + row * o_lane;
+    const i64 nrow = row + nclusters;
+    const bool have_next = nrow < n_lane;
+    const double* nbase = p + (have_next ? nrow : row) * s_lane;
+    double2 r[OC_REG];
 #pragma unroll
-  for (int c = 0; c < OC_REG; ++c) {
-    const i64 v = v0 + (i64)c * OC_THREADS + t;
-    if (v < nv) {
-      r[c].x = fast_exp(r[c].x - mx);
-      r[c].y = fast_exp(r[c].y - mx);
-      s += r[c].x + r[c].y;
+    for (int c = 0; c < OC_REG; ++c) r[c] = rn[c];
+    double xt = xtn;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // ---- max (fmax drops NaNs; a NaN still poisons the sum) ----
+    double mx = fmax(xt, fmax(fmax(r[0].x, r[0].y), fmax(r[1].x, r[1].y)));
+#pragma unroll
+    for (int c = 0; c < OC_SMEM_CHUNKS; ++c) {
+      const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
+      if (v < nv) {
+        double2 x = sx[c * OC_THREADS + t];
+        mx = fmax(mx, fmax(x.x, x.y));
+      }
     }
-  }
-  if (odd_tail) { xt = fast_exp(xt - mx); s += xt; }
-#pragma unroll
-  for (int c = 0; c < OC_SMEM_CHUNKS; ++c) {
-    const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
-    if (v < nv) {
-      double2 x = sx[c * OC_THREADS + t];
-      x.x = fast_exp(x.x - mx);
-      x.y = fast_exp(x.y - mx);
-      s += x.x + x.y;
-      sx[c * OC_THREADS + t] = x;
+    for (int d = 16; d > 0; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if ((t & 31) == 0) sm_red[t >> 5] = mx;
+    __syncthreads();
+    if (t == 0) {
+      double m = sm_red[0];
+      for (int w = 1; w < OC_THREADS / 32; ++w) m = fmax(m, sm_red[w]);
+      sm_x[par][0] = m;
     }
-  }
-  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-  __syncthreads();
-  if ((t & 31) == 0) sm_red[t >> 5] = s;
-  __syncthreads();
-  if (t == 0) {
-    double a = sm_red[0];
-    for (int w = 1; w < OC_THREADS / 32; ++w) a += sm_red[w];
-    sm_x[1] = a;
-  }
-  __syncthreads();
-  if (CS > 1) {
-    cluster_sync_all();
-    s = ld_peer_f64(&sm_x[1], 0) + ld_peer_f64(&sm_x[1], 1);   // fixed rank order
-  } else {
-    s = sm_x[1];
-  }
-  const double inv = 1.0 / s;
-  // ---- normalise, streaming stores ----
-#pragma unroll
-  for (int c = 0; c < OC_REG; ++c) {
-    const i64 v = v0 + (i64)c * OC_THREADS + t;
-    if (v < nv) __stcs(reinterpret_cast<double2*>(obase + 2 * v), make_double2(r[c].x * inv, r[c].y * inv));
-  }
-#pragma unroll
-  for (int c = 0; c < OC_SMEM_CHUNKS; ++c) {
-    const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
-    if (v < nv) {
-      double2 x = sx[c * OC_THREADS + t];
-      __stcs(reinterpret_cast<double2*>(obase + 2 * v), make_double2(x.x * inv, x.y * inv));
+    __syncthreads();
+    if (CS > 1) {
+      cluster_sync_light(t == 0);
+      mx = fmax(ld_peer_f64(&sm_x[par][0], 0), ld_peer_f64(&sm_x[par][0], 1));
+    } else {
+      mx = sm_x[par][0];
     }
+    // ---- exp (kept on chip) and sum ----
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < OC_REG; ++c) {
+      const i64 v = v0 + (i64)c * OC_THREADS + t;
+      if (v < nv) {
+        r[c].x = fast_exp(r[c].x - mx);
+        r[c].y = fast_exp(r[c].y - mx);
+        s += r[c].x + r[c].y;
+      }
+    }
+    if (odd_tail) { xt = fast_exp(xt - mx); s += xt; }
+#pragma unroll
+    for (int c = 0; c < OC_SMEM_CHUNKS; ++c) {
+      const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
+      if (v < nv) {
+        double2 x = sx[c * OC_THREADS + t];
+        x.x = fast_exp(x.x - mx);
+        x.y = fast_exp(x.y - mx);
+        s += x.x + x.y;
+        sx[c * OC_THREADS + t] = x;
+      }
+    }
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    __syncthreads();
+    if ((t & 31) == 0) sm_red[t >> 5] = s;
+    __syncthreads();
+    if (t == 0) {
+      double a = sm_red[0];
+      for (int w = 1; w < OC_THREADS / 32; ++w) a += sm_red[w];
+      sm_x[par][1] = a;
+    }
+    __syncthreads();
+    if (CS > 1) {
+      cluster_sync_light(t == 0);
+      s = ld_peer_f64(&sm_x[par][1], 0) + ld_peer_f64(&sm_x[par][1], 1);   // fixed rank order
+    } else {
+      s = sm_x[par][1];
+    }
+    const double inv = 1.0 / s;
+    // ---- normalise, streaming stores; refill each slot with the next row's chunk as soon as it is stored ----
+#pragma unroll
+    for (int c = 0; c < OC_REG; ++c) {
+      const i64 v = v0 + (i64)c * OC_THREADS + t;
+      if (v < nv) __stcs(reinterpret_cast<double2*>(obase + 2 * v), make_double2(r[c].x * inv, r[c].y * inv));
+      rn[c] = (have_next && v < nv) ? *reinterpret_cast<const double2*>(nbase + 2 * v) : make_double2(-INFINITY, -INFINITY);
+    }
+    xtn = (have_next && odd_tail) ? nbase[n_red - 1] : -INFINITY;
+#pragma unroll
+    for (int c = 0; c < OC_SMEM_CHUNKS; ++c) {
+      const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
+      if (v < nv) {
+        double2 x = sx[c * OC_THREADS + t];
+        __stcs(reinterpret_cast<double2*>(obase + 2 * v), make_double2(x.x * inv, x.y * inv));
+      }
+      if (have_next) issue_smem(nbase, c);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (odd_tail) obase[n_red - 1] = xt * inv;
+    // sm_x is double-buffered by row parity: the peer reads [par] while this CTA may already write [par ^ 1];
+    // [par] is rewritten two rows later, after two more cluster barriers.
   }
-  if (odd_tail) obase[n_red - 1] = xt * inv;
   if (CS > 1) cluster_sync_all();   // the peer may still be reading sm_x
 }
 
@@ -981,7 +1026,9 @@ static int launch_row_onchip(const double* p, i64 s_lane, i64 n_lane, i64 n_red,
     attr = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(n_lane * CS), 1, 1);
+  i64 nclusters = (i64)ctx()->sm_count * 2 / CS;   // two CTAs per SM, all resident: the kernel is persistent
+  if (nclusters > n_lane) nclusters = n_lane;
+  cfg.gridDim = dim3((unsigned)(nclusters * CS), 1, 1);
   cfg.blockDim = dim3(OC_THREADS, 1, 1);
   cfg.dynamicSmemBytes = OC_SMEM_BYTES;
   cfg.stream = ctx()->stream;
@@ -992,7 +1039,8 @@ static int launch_row_onchip(const double* p, i64 s_lane, i64 n_lane, i64 n_red,
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  UM_CUDA(cudaLaunchKernelEx(&cfg, k_softmax_row_onchip<CS>, p, s_lane, n_red, out, o_lane));
+  static const long long stagger = [] { const char* e = getenv("UM_SOFTMAX_STAGGER"); return e ? atoll(e) : 9000LL; }();
+  UM_CUDA(cudaLaunchKernelEx(&cfg, k_softmax_row_onchip<CS>, p, s_lane, n_lane, n_red, out, o_lane, stagger));
   return UM_OK;
 }
 
