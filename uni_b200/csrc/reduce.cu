@@ -868,7 +868,7 @@ __device__ __forceinline__ double ld_peer_f64(const double* local_smem, unsigned
 
 template <int CS>
 __global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const double* __restrict__ p, i64 s_lane, i64 n_lane, i64 n_red,
-                                                                       double* __restrict__ out, i64 o_lane, long long stagger_cycles) {
+                                                                       double* __restrict__ out, i64 o_lane) {
   // Persistent: cluster k takes rows k, k + #clusters, ...  While a thread normalises and stores chunk c of
   // row i it refills the same shared-memory slot with chunk c of row i+1 (cp.async), so the next row's
   // loads are in flight during this row's stores and have landed by the time its max pass starts; the
@@ -898,13 +898,6 @@ __global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const doub
 #pragma unroll
     for (int c = 0; c < OC_SMEM_CHUNKS; ++c) issue_smem(base, c);
     asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  // Two CTAs share an SM; left alone they fall into lockstep (both in the FP64-bound exp phase, then both in
-  // the memory phase).  Every other cluster starts half a period late so one CTA computes while the other
-  // moves data.
-  if (((blockIdx.x / CS) & 1) && n_lane > nclusters) {
-    const long long t0 = clock64();
-    while (clock64() - t0 < stagger_cycles) {}
   }
   int par = 0;
   double2 rn[OC_REG];   // register-held chunks of the NEXT row, loaded during this row's store phase
@@ -1039,8 +1032,7 @@ static int launch_row_onchip(const double* p, i64 s_lane, i64 n_lane, i64 n_red,
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  static const long long stagger = [] { const char* e = getenv("UM_SOFTMAX_STAGGER"); return e ? atoll(e) : 9000LL; }();
-  UM_CUDA(cudaLaunchKernelEx(&cfg, k_softmax_row_onchip<CS>, p, s_lane, n_lane, n_red, out, o_lane, stagger));
+  UM_CUDA(cudaLaunchKernelEx(&cfg, k_softmax_row_onchip<CS>, p, s_lane, n_lane, n_red, out, o_lane));
   return UM_OK;
 }
 
