@@ -365,6 +365,46 @@ k_tprf_colfinal(const double* __restrict__ X, i64 x_bs, const double* __restrict
   }
 }
 
+// ---- sw / SWW / smw / smu from the per-column arrays (single-read sweeps with small groups, where the
+// finaliser warp owns up to 16 columns per piece and cannot afford the 8 x 8 outer products) ----------------
+__global__ void __launch_bounds__(256)
+k_tprf_smallsums(const double* __restrict__ w0, const double* __restrict__ mun, i64 N, i64 npad, int nblk,
+                 double* __restrict__ blockpart /* [panel][nblk][81]: block x < gridDim.x adds into slot x */) {
+  __shared__ double red[8][NSMALL];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const i64 b = blockIdx.z;
+  double loc[NSMALL];
+#pragma unroll
+  for (int i = 0; i < NSMALL; ++i) loc[i] = 0.0;
+  for (i64 j = (i64)blockIdx.x * 256 + tid; j < N; j += (i64)gridDim.x * 256) {
+    const i64 cidx = b * npad + j;
+    double w[LP];
+#pragma unroll
+    for (int l = 0; l < LP; ++l) w[l] = w0[cidx * LP + l];
+    const double m_n = mun[cidx];
+#pragma unroll
+    for (int a = 0; a < LP; ++a) {
+      loc[a] += w[a];
+#pragma unroll
+      for (int c = 0; c < LP; ++c) loc[8 + a * LP + c] += w[a] * w[c];
+      loc[72 + a] += m_n * w[a];
+    }
+    loc[80] += m_n;
+  }
+#pragma unroll
+  for (int i = 0; i < NSMALL; ++i) {
+    double x = loc[i];
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(0xffffffffu, x, d);
+    if (lane == 0) red[warp][i] = x;
+  }
+  __syncthreads();
+  if (tid < NSMALL) {
+    double x = 0.0;
+    for (int w = 0; w < 8; ++w) x += red[w][tid];
+    blockpart[(b * nblk + blockIdx.x) * NSMALL + tid] += x;   // the finalisers wrote zeros there
+  }
+}
+
 // ---- sweep 2: PX = Xn W0, h0 = Xn 1 ----------------------------------------------------------------------
 constexpr int C2_ROWS = 128, C2_COLS = 32, C2_PITCH = 36, C2_STAGES = 4, C2_THREADS = 256;
 constexpr int C2_STAGE_DBL = C2_ROWS * C2_PITCH + C2_COLS * ZPITCH + C2_COLS;  // 4608 + 384 + 32 = 5024
@@ -1200,6 +1240,12 @@ static int run_sweeps(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_
   if (p.fused) {
     int s = run_fused(p, ws, X, ldx, x_bs);
     if (s != UM_OK) return s;
+    if (!p.grid_sweep && fused::CW / p.fG > 4) {   // cluster sweep, small groups: the finalisers left the small sums to this kernel
+      i64 nb = cdiv(p.N, 256 * 4);
+      if (nb > p.cf_blocks) nb = p.cf_blocks;
+      k_tprf_smallsums<<<dim3((unsigned)nb, 1, (unsigned)p.batch), 256, 0, st>>>(w0, mun, p.N, p.npad, p.cf_blocks, bp);
+      UM_LAUNCHED();
+    }
   } else {
   {
     dim3 grid((unsigned)p.strips, (unsigned)p.rchunks, (unsigned)p.batch);

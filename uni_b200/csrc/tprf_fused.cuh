@@ -496,6 +496,32 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         mb_wait(bar_stat(s), (unsigned)((it / NXR) & 1));
         stamp(it, 1);
         const unsigned sb = sa(statbuf + s * STAT_SLOT);
+        // Small groups own many columns (16 at G = 1): the long chain S, SS -> 1/sd is then done ONCE, one
+        // column per lane, before the rounds, instead of 8 times redundantly in each of 4 serial rounds.
+        const bool pre = owned > 4;
+        double inv_pre = 1.0, mun_pre = 0.0;
+        if (pre && lane < owned) {
+          double S = 0.0, SS = 0.0;
+          for (int r = 0; r < G; ++r) {   // G <= 2: rank order
+            S += lds_f64(sb + (unsigned)((lane * G + r) * NSTAT) * 8);
+            SS += lds_f64(sb + (unsigned)((lane * G + r) * NSTAT + 1) * 8);
+          }
+          const double k0 = lds_f64(sa(kshs + (it % NK) * CW + lane * G + rank));
+          const double dm = S * invT;
+          if (T > 1) {
+            double var = fma(-S, dm, SS) * invTm1;
+            if (var < 0.0) var = 0.0;
+            if (var != 0.0) {
+              double y;
+              asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(var));
+              const double hv = 0.5 * var;
+              y = y * fma(-hv * y, y, 1.5);
+              y = y * fma(-hv * y, y, 1.5);
+              inv_pre = (var < 1e-290 || var > 1e290) ? 1.0 / sqrt(var) : y;
+            }
+          }
+          mun_pre = (k0 + dm) * inv_pre;
+        }
         for (int oc0 = 0; oc0 < owned; oc0 += cpr) {
           const int oc = oc0 + cs;              // < owned always (owned is a multiple of cpr)
           const int col = oc * G + rank;
@@ -531,22 +557,27 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
           // short dependent chain (this warp shares the FP64 pipe with the DMMA stream, every dependent
           // FP64 instruction costs a pipe round trip): reciprocals instead of divisions, 1/sd from an
           // rsqrt seed + two Newton steps (relative error ~1e-16; the parity bar is 1e-9)
-          const double dm = S * invT;
-          const double mu = k0 + dm;
-          double inv = 1.0;
-          if (T > 1) {
-            double var = fma(-S, dm, SS) * invTm1;
-            if (var < 0.0) var = 0.0;
-            if (var != 0.0) {                      // sd == 0 -> 1 (Tprf3.scala:493-501); NaN propagates
-              double y;
-              asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(var));
-              const double hv = 0.5 * var;
-              y = y * fma(-hv * y, y, 1.5);   // seed is good to ~2^-23: 2^-45 after one step,
-              y = y * fma(-hv * y, y, 1.5);   // full double after two
-              inv = (var < 1e-290 || var > 1e290) ? 1.0 / sqrt(var) : y;
+          double inv = 1.0, m_n;
+          if (pre) {
+            inv = __shfl_sync(0xffffffffu, inv_pre, oc);
+            m_n = __shfl_sync(0xffffffffu, mun_pre, oc);
+          } else {
+            const double dm = S * invT;
+            const double mu = k0 + dm;
+            if (T > 1) {
+              double var = fma(-S, dm, SS) * invTm1;
+              if (var < 0.0) var = 0.0;
+              if (var != 0.0) {                      // sd == 0 -> 1 (Tprf3.scala:493-501); NaN propagates
+                double y;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(var));
+                const double hv = 0.5 * var;
+                y = y * fma(-hv * y, y, 1.5);   // seed is good to ~2^-23: 2^-45 after one step,
+                y = y * fma(-hv * y, y, 1.5);   // full double after two
+                inv = (var < 1e-290 || var > 1e290) ? 1.0 / sqrt(var) : y;
+              }
             }
+            m_n = mu * inv;
           }
-          const double m_n = mu * inv;
           const double w = q * inv;
           const double v = w * inv;
           // record of this column -> every CTA of the cluster; this lane serves ranks [rs*nr, rs*nr + nr)
@@ -571,14 +602,16 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
               g.mun[cix] = m_n;
             }
           }
-          const double wv = mine ? w : 0.0, mv = mine ? m_n : 0.0;
-          a_sw += wv;
-          a_smw += mv * wv;
-          if (l == 0) a_smu += mv;
+          if (!pre) {   // (small groups: k_tprf_smallsums forms these sums from W0 / mun after the sweep)
+            const double wv = mine ? w : 0.0, mv = mine ? m_n : 0.0;
+            a_sw += wv;
+            a_smw += mv * wv;
+            if (l == 0) a_smu += mv;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const double wc = __shfl_sync(0xffffffffu, wv, (lane & 24) | c);
-            a_sww[c] += wv * wc;
+            for (int c = 0; c < 8; ++c) {
+              const double wc = __shfl_sync(0xffffffffu, wv, (lane & 24) | c);
+              a_sww[c] += wv * wc;
+            }
           }
         }
       }
