@@ -69,6 +69,7 @@ object UniMatLib:
   val um_idx_axis    = h("um_idx_axis", I(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS))
   // ---- linear algebra
   val um_matmul  = h("um_matmul", I(ADDRESS, ADDRESS, ADDRESS))
+  val um_matmul_set_f32_path = h("um_matmul_set_f32_path", I(JAVA_INT))
   val um_inverse = h("um_inverse", I(ADDRESS, ADDRESS))
   val um_solve   = h("um_solve", I(ADDRESS, ADDRESS, ADDRESS))
   // ---- 3PRF + multi-GPU

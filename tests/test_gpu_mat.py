@@ -325,6 +325,52 @@ def test_matf_ops(u):
     assert m.relu().dtype == 1 and np.array_equal(m.relu().to_numpy(), np.maximum(a, 0))
 
 
+MATF_MM_SHAPES = [(128, 32, 128), (128, 160, 256), (256, 512, 384), (384, 4096, 128), (1024, 1056, 512)]
+
+
+@pytest.mark.parametrize("mkn", MATF_MM_SHAPES)
+def test_matf_matmul_tensor_core_path(u, mkn):
+    """FP32 `*@` on the tcgen05 tensor cores (3xTF32, promoted to FP32 registers every 128 k) against float64 and
+    against the FFMA kernel.  The reference pins FP32 matmul to tolerance only (MatTest.scala MatF rows; sgemm vs
+    matmulPure, Mat.scala:3358-3377).  Bounds: element-wise the textbook sgemm bound k * 2^-24 * (|a| @ |b|), and for
+    this N(0,1) data max |err| <= 6e-6 * sqrt(k) (OpenBLAS sgemm measures ~3e-6 * sqrt(k); an accumulator left in
+    tensor memory over all of k measured 1.7e-4 * sqrt(k) at k = 4096, which this catches)."""
+    M, K, N = mkn
+    rng = np.random.default_rng(M + 3 * K + 7 * N)
+    a = rng.standard_normal((M, K)).astype(np.float32); b = rng.standard_normal((K, N)).astype(np.float32)
+    want = a.astype(np.float64) @ b.astype(np.float64)
+    bound = K * 2.0 ** -24 * (np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64))
+    da, db = dev(u, a), dev(u, b)
+    try:
+        u.set_matf_matmul_path(2)
+        got_t = (da @ db).to_numpy()
+        # a view with a different pitch and a 16-byte aligned offset stays on the tensor path
+        big = rng.standard_normal((M + 8, K + 8)).astype(np.float32)
+        got_v = (dev(u, big)._raw_slice(8, M + 8, 4, K + 4) @ db).to_numpy()
+        want_v = big[8 : M + 8, 4 : K + 4].astype(np.float64) @ b.astype(np.float64)
+        # operands it cannot take are refused, never silently rerouted, when the path is forced
+        with pytest.raises(ValueError):
+            dev(u, a.T.copy()).T @ db
+        with pytest.raises(ValueError):
+            dev(u, big)._raw_slice(8, M + 8, 3, K + 3) @ db
+        u.set_matf_matmul_path(1)
+        got_c = (da @ db).to_numpy()
+        u.set_matf_matmul_path(0)
+        got_auto = (da @ db).to_numpy()
+        got_auto_t = (dev(u, a.T.copy()).T @ db).to_numpy()    # automatic: falls back to the FFMA kernel
+    finally:
+        u.set_matf_matmul_path(0)
+    assert got_t.dtype == np.float32
+    assert np.all(np.abs(got_t - want) <= bound)
+    assert np.max(np.abs(got_t - want)) <= 6e-6 * np.sqrt(K)
+    assert np.max(np.abs(got_v - want_v)) <= 6e-6 * np.sqrt(K)
+    assert np.array_equal(got_auto, got_t), "automatic choice = tensor path for tile-multiple row-major operands"
+    assert np.array_equal(got_auto_t, got_c)
+    np.testing.assert_allclose(got_t, got_c, rtol=1e-4, atol=1e-5 * np.sqrt(K))
+    # bit-reproducible from run to run
+    assert np.array_equal((da @ db).to_numpy(), got_t)
+
+
 # ---------------------------------------------------------------- matmul / inverse / solve
 MM_SHAPES = [(1, 1, 1), (3, 5, 3), (5, 3, 5), (8, 9, 8), (64, 64, 64), (65, 63, 65), (127, 129, 131), (256, 256, 256),
              (300, 400, 300), (1, 500, 1), (500, 1, 500), (40, 650, 40), (512, 512, 512), (1000, 17, 9)]

@@ -5,10 +5,10 @@ include/unimat.h).  Importing this package loads that library and fails if it is
 """
 from . import _lib
 from ._lib import (EmptyMatrixError, SingularMatrixError, UnimatError, device_count, launch_count)
-from .mat import Mat, MatD, MatF, init, sync
+from .mat import Mat, MatD, MatF, init, set_matf_matmul_path, sync
 from . import tprf3
 from .tprf3 import Tprf3Result, estimate3prf, forecast3prf, t3prf, tprfClosedForm
 
-__all__ = ["Mat", "MatD", "MatF", "init", "sync", "tprf3", "Tprf3Result", "estimate3prf", "forecast3prf",
+__all__ = ["Mat", "MatD", "MatF", "init", "sync", "set_matf_matmul_path", "tprf3", "Tprf3Result", "estimate3prf", "forecast3prf",
            "t3prf", "tprfClosedForm", "device_count", "launch_count", "EmptyMatrixError",
            "SingularMatrixError", "UnimatError"]

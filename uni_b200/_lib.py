@@ -125,6 +125,7 @@ SIGNATURES = {
     "um_arg_all": (_i32, [_i32, VP, C.POINTER(_i64), C.POINTER(_i64)]),
     "um_idx_axis": (_i32, [_i32, VP, _i32, VP]),
     "um_matmul": (_i32, [VP, VP, VP]),
+    "um_matmul_set_f32_path": (_i32, [_i32]),
     "um_inverse": (_i32, [VP, VP]),
     "um_solve": (_i32, [VP, VP, VP]),
     "um_inverse_batched": (_i32, [VP, _i64, VP, _i64, _i64]),

@@ -10,6 +10,8 @@
 // reference copies non-BLAS-safe operands first, Mat.scala:1169).
 //
 // FP32: register-tiled FFMA kernel (float accumulate, as multiplyFloat Mat.scala:3236-3268).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace um {
@@ -265,7 +267,17 @@ static int launch_dgemm(const double* pa, i64 lda, const double* pb, i64 ldb, do
 
 }  // namespace um
 
+#include "matmul_tf32.cuh"
+
 using namespace um;
+
+static int g_f32_path = 0;   // um_matmul_set_f32_path
+
+extern "C" int32_t um_matmul_set_f32_path(int32_t path) {
+  if (path < 0 || path > 2) return um::fail(UM_ERR_ARG, "um_matmul_set_f32_path: 0 auto, 1 CUDA cores, 2 tensor cores");
+  g_f32_path = path;
+  return UM_OK;
+}
 
 extern "C" int32_t um_matmul(const um_view* a, const um_view* b, const um_view* out) {
   UM_CTX();
@@ -305,6 +317,14 @@ extern "C" int32_t um_matmul(const um_view* a, const um_view* b, const um_view* 
   if (a->dtype == UM_F32) {
     In<float> A = in_of<float>(a), B = in_of<float>(b);
     float* pc = static_cast<float*>(out->data) + out->offset;
+    // row-major, aligned, tile-multiple operands: 3xTF32 on the tcgen05 tensor cores (matmul_tf32.cuh)
+    static const bool tensor_ok = [] { const char* e = getenv("UM_MATF_TENSOR"); return !(e && e[0] == '0'); }();
+    const int path = g_f32_path;
+    if (path == 2 || (path == 0 && tensor_ok)) {
+      int r = (A.cs == 1 && B.cs == 1) ? tf32::launch(A.p, A.rs, B.p, B.rs, pc, ldc, M, N, K) : -1;
+      if (r != -1) return r;
+      if (path == 2) return fail(UM_ERR_ARG, "matmul: operands do not fit the tensor-core FP32 kernel (row-major, 16-byte aligned, M,N % 128, K % 32)");
+    }
     dim3 grid((unsigned)((N + SG_BN - 1) / SG_BN), (unsigned)((M + SG_BM - 1) / SG_BM));
     k_sgemm<<<grid, 256, 0, ctx()->stream>>>(A, B, pc, ldc, M, N, K);
     UM_LAUNCHED();

@@ -538,6 +538,15 @@ MatD = _Facade(L.F64)
 MatF = _Facade(L.F32)
 
 
+MATF_PATH_AUTO, MATF_PATH_CUDA_CORES, MATF_PATH_TENSOR = 0, 1, 2
+
+
+def set_matf_matmul_path(path: int) -> None:
+    """FP32 `@` kernel choice (um_matmul_set_f32_path; the counterpart of the reference's uni.mat.blas
+    switch, Mat.scala:299-335): 0 = automatic, 1 = FFMA kernel only, 2 = tcgen05 3xTF32 kernel or ValueError."""
+    check(lib.um_matmul_set_f32_path(int(path)))
+
+
 def init(device: int = 0) -> None:
     check(lib.um_init(device))
 
