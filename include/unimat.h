@@ -144,6 +144,24 @@ int32_t um_mask_logic(int32_t op, const um_view* a, const um_view* b /* NULL for
 int32_t um_mask_reduce(int32_t want_all, const um_view* a, int32_t axis, const um_view* out_bool,
                        int32_t* host_out);
 
+/* ---- running folds and mask-driven selection --------------
+ * cumsum / cummax / cummin (Mat.scala:3635-3745, cumExtremumD :929-964): axis 0 / 1 -> `out` of the
+ * operand's shape; axis -1 = the flat cumsum over row-major order -> `out` 1 x (rows*cols)
+ * (Mat.scala:3676-3690).  Every lane is folded sequentially in increasing index, exactly like the
+ * reference, so results are bit-identical (fixture rows cum0fnv cum1fnv cmax0fnv cmin1fnv cummaxfnv
+ * cumlast); cummax / cummin use java.lang.Double.compare's order and replace on strictly better. */
+typedef enum um_cumop { UM_CUMSUM = 0, UM_CUMMAX = 1, UM_CUMMIN = 2 } um_cumop;
+int32_t um_cumulative(int32_t kind, const um_view* a, int32_t axis, const um_view* out);
+/* Mat.where(condition, x, y) and Mat.where(condition, sx, sy) (Mat.scala:1305-1336): out(i,j) =
+ * condition(i,j) ? x(i,j) : y(i,j); shapes must match exactly (no broadcasting) */
+int32_t um_where(const um_view* cond, const um_view* x, const um_view* y, const um_view* out);
+int32_t um_where_scalar(const um_view* cond, double x, double y, const um_view* out);
+/* m(mask) (Mat.scala:4008-4021): the elements where the mask is true, in row-major order, as a
+ * 1 x k row.  Two calls because the caller owns the result: um_mask_count returns k (synchronises),
+ * um_mask_select fills a 1 x k `out`. */
+int32_t um_mask_count(const um_view* mask, int64_t* host_count);
+int32_t um_mask_select(const um_view* a, const um_view* mask, const um_view* out);
+
 /* ---- reductions (Mat.scala:2251-2279 sum, :3469-3485 mean, :4784-4805 variance, :4699-4717
  *      std, :3414-3467 sum(axis), :3487-3492 mean(axis), :4720-4739 std(axis), :2215-2249
  *      min/max, :3503-3556 min/max(axis)).  Population statistics (divide by n).  Sums use a

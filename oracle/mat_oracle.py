@@ -435,6 +435,92 @@ def max_axis(m: OMat, axis: int) -> OMat:
 
 
 # ---------------------------------------------------------------------------------------
+# running folds (Mat.scala:3635-3745; cumExtremumD :929-964)
+# ---------------------------------------------------------------------------------------
+def cumsum(m: OMat, axis=None) -> OMat:
+    """Sequential running total per lane, seeded with 0 (Mat.scala:3635-3690).  np.cumsum on a strided
+    1-D lane is the same left fold; float32 stays float32 (Numeric[Float].plus)."""
+    v = m.to2d()
+    if axis is None:  # flatten (row-major), 1 x n
+        return create(np.cumsum(v.reshape(-1), dtype=v.dtype), 1, m.rows * m.cols)
+    if axis not in (0, 1):
+        raise ValueError(f"axis must be 0 or 1, got {axis}")
+    return create(np.cumsum(v, axis=axis, dtype=v.dtype).reshape(-1), m.rows, m.cols)
+
+
+def _cum_extremum(m: OMat, axis: int, want_max: bool) -> OMat:
+    """acc = lane[0]; every cell (the first included) written after `if better(v, acc) acc = v`
+    under java.lang.Double.compare (Mat.scala:3692-3744, 929-964).  The running extremum of the
+    order keys finds where the accumulator is replaced (strictly better than everything before it); each
+    cell then copies the element of the most recent replacement, so NaN payloads and signed zeros are the
+    reference's."""
+    if axis not in (0, 1):
+        raise ValueError(f"axis must be 0 or 1, got {axis}")
+    v = m.to2d()
+    if m.rows * m.cols == 0:
+        if (axis == 0 and m.rows == 0 and m.cols > 0) or (axis == 1 and m.cols == 0 and m.rows > 0):
+            raise ValueError("cummax/cummin of an empty lane")  # apply's require, Mat.scala:3694-3699
+        return create(np.zeros(0, dtype=v.dtype), m.rows, m.cols)
+    k = total_key(v)
+    n = v.shape[axis]
+    idx = np.arange(n).reshape((n, 1) if axis == 0 else (1, n))
+    run = np.maximum.accumulate(k, axis=axis) if want_max else np.minimum.accumulate(k, axis=axis)
+    # an element starts a new run when its key is strictly better than everything before it
+    if axis == 0:
+        prev = np.vstack([np.full((1, v.shape[1]), np.iinfo(np.int64).min if want_max else np.iinfo(np.int64).max), run[:-1]])
+    else:
+        prev = np.hstack([np.full((v.shape[0], 1), np.iinfo(np.int64).min if want_max else np.iinfo(np.int64).max), run[:, :-1]])
+    starts = (k > prev) if want_max else (k < prev)
+    src = np.maximum.accumulate(np.where(starts, idx, 0), axis=axis)
+    out = np.take_along_axis(v, src, axis=axis)
+    return create(out.reshape(-1), m.rows, m.cols)
+
+
+def cummax(m: OMat, axis: int) -> OMat:
+    return _cum_extremum(m, axis, True)
+
+
+def cummin(m: OMat, axis: int) -> OMat:
+    return _cum_extremum(m, axis, False)
+
+
+# ---------------------------------------------------------------------------------------
+# mask-driven selection (Mat.scala:4008-4021 m(mask); :1305-1336 Mat.where)
+# ---------------------------------------------------------------------------------------
+def mask_select(m: OMat, mask: OMat) -> OMat:
+    if (mask.rows, mask.cols) != (m.rows, m.cols):
+        raise ValueError(f"Mask shape {mask.shape} must match matrix shape {m.shape}")
+    sel = m.to2d()[mask.to2d().astype(bool)]  # boolean indexing walks row-major, like the reference's double loop
+    return create(sel.copy(), 1, sel.size)
+
+
+def where(cond: OMat, x, y) -> OMat:
+    c = cond.to2d().astype(bool)
+    if isinstance(x, OMat):
+        if not ((cond.rows, cond.cols) == (x.rows, x.cols) == (y.rows, y.cols)):
+            raise ValueError("where: shape mismatch")
+        return create(np.where(c, x.to2d(), y.to2d()).reshape(-1), cond.rows, cond.cols)
+    return create(np.where(c, np.float64(x), np.float64(y)).reshape(-1), cond.rows, cond.cols)
+
+
+def mask_all(mask: OMat, axis=None):
+    """Mat.scala:4907-5001."""
+    v = mask.to2d().astype(bool)
+    if axis is None:
+        return bool(v.all())
+    r = v.all(axis=axis)
+    return create(r.reshape(-1), 1, mask.cols) if axis == 0 else create(r.reshape(-1), mask.rows, 1)
+
+
+def mask_any(mask: OMat, axis=None):
+    v = mask.to2d().astype(bool)
+    if axis is None:
+        return bool(v.any())
+    r = v.any(axis=axis)
+    return create(r.reshape(-1), 1, mask.cols) if axis == 0 else create(r.reshape(-1), mask.rows, 1)
+
+
+# ---------------------------------------------------------------------------------------
 # elementwise + broadcasting (Mat.scala:1989-2102,2154-2209,2514-2531,4513-4588)
 # ---------------------------------------------------------------------------------------
 _BIN = {

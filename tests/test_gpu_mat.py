@@ -134,6 +134,138 @@ def test_adversarial_rows_bit_exact(u, ref, name):
         assert not bad, (lab, bad)
 
 
+# ---------------------------------------------------------------- running folds, m(mask), Mat.where
+@pytest.mark.parametrize("n", [k for k in pc.SIZES if k])
+def test_cumulative_fixture_sizes_bit_exact(u, ref, n):
+    """cumlast / cummaxfnv rows (MatParityGen.scala:199,220): the flat cumsum is the reference's sequential fold."""
+    m = dev(u, pc.corpus()[:n].reshape(-1, 1))
+    flat = m.cumsum()
+    assert flat.shape == (1, n)
+    assert mo.bits(float(flat.to_numpy()[0, -1])) == ref[(str(n), "cumlast")]
+    me = dev(u, pc.corpus_exp()[:n].reshape(-1, 1))
+    assert mo.fnv(me.cummax(0).to_numpy().reshape(-1)) == ref[(str(n), "cummaxfnv")]
+
+
+@pytest.mark.parametrize("shape", pc.SHAPES)
+def test_cumulative_fixture_2d_bit_exact(u, ref, shape):
+    r, c = shape
+    lab = f"{r}x{c}"
+    a = pc.corpus()[: r * c].reshape(r, c)
+    m = dev(u, a)
+    f = lambda x: mo.fnv(x.to_numpy().reshape(-1))
+    got = {"cum0fnv": f(m.cumsum(0)), "cum1fnv": f(m.cumsum(1)), "cmax0fnv": f(m.cummax(0)), "cmin1fnv": f(m.cummin(1))}
+    bad = {k: (hex(v), hex(ref[(lab, k)])) for k, v in got.items() if v != ref[(lab, k)]}
+    assert not bad, bad
+    # the same folds through a transposed view (strided reads, contiguous result): bit-equal to the oracle
+    o = omat(a)
+    for ax in (0, 1):
+        assert np.array_equal(m.T.cumsum(ax).to_numpy(), mo.cumsum(o.T, ax).to2d())
+        assert np.array_equal(m.T.cummin(ax).to_numpy(), mo.cummin(o.T, ax).to2d())
+    assert np.array_equal(m.T.cumsum().to_numpy(), mo.cumsum(o.T).to2d())
+
+
+@pytest.mark.parametrize("name", sorted(pc.ADVERSARIAL))
+def test_adversarial_cumulative_and_selection_bit_exact(u, ref, name):
+    arr = np.array(pc.ADVERSARIAL[name], dtype=np.float64)
+    mats = {"col": dev(u, arr.reshape(-1, 1)), "row": dev(u, arr.reshape(1, -1)), "colT": dev(u, arr.reshape(-1, 1)).T}
+    fc = lambda x: mo.fnv_canon(x.to_numpy().reshape(-1))
+    for orient, m in mats.items():
+        lab = f"adv/{name}/{orient}"
+        pos = m.gt(0.0)
+        sel = m[pos]
+        got = {
+            "cmax0fnv": fc(m.cummax(0)), "cmax1fnv": fc(m.cummax(1)), "cmin0fnv": fc(m.cummin(0)), "cmin1fnv": fc(m.cummin(1)),
+            "mask.selfnv": fc(sel), "mask.selshape": sel.rows * 1000 + sel.cols,
+            "mask.wherefnv": fc(u.Mat.where(pos, m, m * -1.0)), "mask.wheresfnv": fc(u.Mat.where(pos, 1.0, -1.0)),
+        }
+        bad = {k: (hex(v), hex(ref[(lab, k)])) for k, v in got.items() if v != ref[(lab, k)]}
+        assert not bad, (lab, bad)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 70), (70, 1), (33, 31), (129, 257), (1000, 37), (37, 1000), (3, 5000), (2100, 130)])
+def test_cumulative_vs_oracle(u, shape):
+    r, c = shape
+    rng = np.random.default_rng(r * 31 + c)
+    a = rng.standard_normal((r, c))
+    a[rng.random((r, c)) < 0.02] = np.nan
+    a[rng.random((r, c)) < 0.02] = -0.0
+    a[rng.random((r, c)) < 0.02] = 0.0
+    a[rng.random((r, c)) < 0.01] = np.inf
+    m, o = dev(u, a), omat(a)
+    same = lambda x, y: np.array_equal(x.view(np.uint64), y.view(np.uint64))
+    for ax in (0, 1):
+        assert same(m.cummax(ax).to_numpy(), mo.cummax(o, ax).to2d())
+        assert same(m.cummin(ax).to_numpy(), mo.cummin(o, ax).to2d())
+    b = rng.standard_normal((r, c))
+    mb, ob = dev(u, b), omat(b)
+    for ax in (0, 1, None):
+        assert same(mb.cumsum(ax).to_numpy(), mo.cumsum(ob, ax).to2d())
+    if r > 2 and c > 3:   # offset slice: the pitch differs from the width
+        assert same(mb.slice(1, r, 2, c).cumsum(0).to_numpy(), mo.cumsum(mo.slice_(ob, 1, r, 2, c), 0).to2d())
+        assert same(mb.slice(1, r, 2, c).cumsum(1).to_numpy(), mo.cumsum(mo.slice_(ob, 1, r, 2, c), 1).to2d())
+        assert same(mb.slice(1, r, 2, c).cumsum().to_numpy(), mo.cumsum(mo.slice_(ob, 1, r, 2, c)).to2d())
+    f = b.astype(np.float32)
+    mf = dev(u, f)
+    assert mf.cumsum(1).dtype == 1
+    assert np.array_equal(mf.cumsum(1).to_numpy(), np.cumsum(f, axis=1, dtype=np.float32))
+    assert np.array_equal(mf.cumsum(0).to_numpy(), np.cumsum(f, axis=0, dtype=np.float32))
+    assert np.array_equal(mf.cummax(0).to_numpy(), np.maximum.accumulate(f, axis=0))
+
+
+def test_cumulative_edge_cases(u):
+    with pytest.raises(ValueError):
+        u.MatD.zeros(3, 3).cumsum(2)                       # require(axis == 0 || axis == 1), Mat.scala:3636
+    with pytest.raises(ValueError):
+        u.MatD.zeros(0, 3).cummax(0)                       # m(0, j) on an empty lane, Mat.scala:3694-3699
+    assert u.MatD.zeros(0, 3).cummax(1).shape == (0, 3)
+    assert u.MatD.zeros(0, 3).cumsum(0).shape == (0, 3)
+    assert u.MatD.zeros(0, 0).cumsum().shape == (1, 0)
+    z = dev(u, np.array([[0.0, -0.0, np.nan, 1.0, np.nan, -np.inf]]))
+    assert [mo.bits(x) for x in z.cummin(1).to_numpy()[0]] == [mo.bits(x) for x in [0.0, -0.0, -0.0, -0.0, -0.0, -np.inf]]
+    bc = dev(u, np.array([[1.0, 2.0, 3.0]])).broadcastTo(4, 3)       # stride-0 rows
+    assert np.array_equal(bc.cumsum(0).to_numpy(), np.cumsum(np.tile([[1.0, 2.0, 3.0]], (4, 1)), axis=0))
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (7, 9), (64, 64), (65, 63), (300, 41), (3, 9000), (5000, 3)])
+def test_mask_select_and_where_vs_oracle(u, shape):
+    r, c = shape
+    rng = np.random.default_rng(r + 1000 * c)
+    a = rng.standard_normal((r, c)); b = rng.standard_normal((r, c))
+    m, mb = dev(u, a), dev(u, b)
+    for thr in (-10.0, -0.5, 0.0, 1.0, 10.0):
+        mask = m.gt(thr)
+        sel = m[mask]
+        want = a[a > thr]
+        assert sel.shape == (1, want.size) and np.array_equal(sel.to_numpy().reshape(-1), want)
+        # mask and operand through transposed views: row-major order of the VIEW
+        selt = m.T[m.T.gt(thr)]
+        assert np.array_equal(selt.to_numpy().reshape(-1), a.T[a.T > thr])
+        assert np.array_equal(u.Mat.where(mask, m, mb).to_numpy(), np.where(a > thr, a, b))
+        assert np.array_equal(u.Mat.where(mask.T, m.T, mb.T).to_numpy(), np.where(a.T > thr, a.T, b.T))
+        assert np.array_equal(u.Mat.where(mask, 2.5, -1.0).to_numpy(), np.where(a > thr, 2.5, -1.0))
+    f = a.astype(np.float32)
+    mf = dev(u, f)
+    assert mf[mf.lt(0.0)].dtype == 1 and np.array_equal(mf[mf.lt(0.0)].to_numpy().reshape(-1), f[f < 0])
+    other = mb.gt(0.0)
+    assert np.array_equal(u.Mat.where(m.gt(0.0), other, ~other).to_numpy(), np.where(a > 0, b > 0, ~(b > 0)))
+    with pytest.raises(ValueError):
+        m[dev(u, np.zeros((r + 1, c))).gt(0.0)]              # Mat.scala:4010-4011
+    with pytest.raises(ValueError):
+        u.Mat.where(m.gt(0.0), m, dev(u, np.zeros((r, c + 1))))   # Mat.scala:1306-1310
+
+
+def test_mask_select_large_is_stable(u):
+    """4M elements over many blocks: positions come from an exact integer scan, so the order is row-major."""
+    m = u.MatD.randn(2048, 2048, seed=5)
+    a = m.to_numpy()
+    sel = m[m.gt(0.25)]
+    want = a[a > 0.25]
+    assert sel.shape == (1, want.size) and np.array_equal(sel.to_numpy().reshape(-1), want)
+    c0 = m.cumsum(0).to_numpy()
+    assert np.array_equal(c0, np.cumsum(a, axis=0))
+    assert np.array_equal(m.cummax(1).to_numpy(), np.maximum.accumulate(a, axis=1))
+
+
 # ---------------------------------------------------------------- elementwise / broadcasting / views
 SHAPES_EW = [(1, 1), (1, 7), (7, 1), (3, 5), (64, 64), (65, 63), (257, 129), (1000, 33), (33, 1000), (2, 4099)]
 

@@ -192,3 +192,85 @@ def test_layout_guard():
     st = mo.slice_(tall, 0, 5, 1, 3)
     assert sw.data is not wide.data and sw.offset == 0 and sw.rs == 4
     assert st.data is tall.data and st.offset == 1 and st.rs == 3
+
+
+# ---------------------------------------------------------------- running folds, m(mask), Mat.where
+@pytest.mark.parametrize("n", pc.SIZES)
+def test_cumulative_sizes(ref, n):
+    """cumlast = last of the flat cumsum (a different association order from `sum`), cummaxfnv = every element of
+    cummax(0) on the n x 1 column over corpusExp (MatParityGen.scala:199,220)."""
+    m = cvec(pc.corpus()[:n])
+    last = 0.0 if n == 0 else float(mo.cumsum(m).to_array()[-1])
+    assert mo.bits(last) == ref[(str(n), "cumlast")]
+    if n:
+        me = cvec(pc.corpus_exp()[:n])
+        assert mo.fnv(mo.cummax(me, 0).to_array()) == ref[(str(n), "cummaxfnv")]
+
+
+@pytest.mark.parametrize("shape", pc.SHAPES)
+def test_cumulative_2d_rows(ref, shape):
+    r, c = shape
+    lab = f"{r}x{c}"
+    m = mat2d(pc.corpus(), r, c)
+    got = {
+        "cum0fnv": mo.fnv(mo.cumsum(m, 0).to_array()),
+        "cum1fnv": mo.fnv(mo.cumsum(m, 1).to_array()),
+        "cmax0fnv": mo.fnv(mo.cummax(m, 0).to_array()),
+        "cmin1fnv": mo.fnv(mo.cummin(m, 1).to_array()),
+    }
+    bad = {k: (hex(v), hex(ref[(lab, k)])) for k, v in got.items() if v != ref[(lab, k)]}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("name", sorted(pc.ADVERSARIAL))
+def test_adversarial_cumulative_and_selection_rows(ref, name):
+    """NaN / signed-zero / infinity inputs: cummax, cummin both axes; all / any; m(mask); Mat.where
+    (MatParityGen.scala:801-850)."""
+    for orient, m in _adv_mats(pc.ADVERSARIAL[name]).items():
+        lab = f"adv/{name}/{orient}"
+        pos = mo.compare_scalar("gt", m, 0.0)
+        sel = mo.mask_select(m, pos)
+        got = {
+            "cmax0fnv": mo.fnv_canon(mo.cummax(m, 0).to_array()),
+            "cmax1fnv": mo.fnv_canon(mo.cummax(m, 1).to_array()),
+            "cmin0fnv": mo.fnv_canon(mo.cummin(m, 0).to_array()),
+            "cmin1fnv": mo.fnv_canon(mo.cummin(m, 1).to_array()),
+            "mask.all": int(mo.mask_all(pos)),
+            "mask.any": int(mo.mask_any(pos)),
+            "mask.all0": mo.fnv_mask(mo.mask_all(pos, 0).to_array()),
+            "mask.any0": mo.fnv_mask(mo.mask_any(pos, 0).to_array()),
+            "mask.all1": mo.fnv_mask(mo.mask_all(pos, 1).to_array()),
+            "mask.any1": mo.fnv_mask(mo.mask_any(pos, 1).to_array()),
+            "mask.selfnv": mo.fnv_canon(sel.to_array()),
+            "mask.selshape": sel.rows * 1000 + sel.cols,
+            "mask.wherefnv": mo.fnv_canon(mo.where(pos, m, mo.binary_scalar("mul", m, -1.0)).to_array()),
+            "mask.wheresfnv": mo.fnv_canon(mo.where(pos, 1.0, -1.0).to_array()),
+        }
+        bad = {k: (hex(v), hex(ref[(lab, k)])) for k, v in got.items() if v != ref[(lab, k)]}
+        assert not bad, (lab, bad)
+
+
+def test_cumulative_on_views_and_float():
+    """Reads honour offset / strides, results are plain contiguous (Mat.scala:929-964); Mat[Float] accumulates in float."""
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((7, 9))
+    m = mo.from2d(a)
+    for ax in (0, 1):
+        want = np.cumsum(a.T, axis=ax)
+        assert np.array_equal(mo.cumsum(m.T, ax).to2d(), want)
+        assert np.array_equal(mo.cummax(m.T, ax).to2d(), np.maximum.accumulate(a.T, axis=ax))
+        assert np.array_equal(mo.cummin(mo.slice_(m, 1, 6, 2, 8), ax).to2d(), np.minimum.accumulate(a[1:6, 2:8], axis=ax))
+    f = a.astype(np.float32)
+    got = mo.cumsum(mo.create(f.reshape(-1).copy(), 7, 9), 1).to2d()
+    want = np.zeros_like(f)
+    for i in range(7):
+        acc = np.float32(0)
+        for j in range(9):
+            acc = np.float32(acc + f[i, j]); want[i, j] = acc
+    assert got.dtype == np.float32 and np.array_equal(got, want)
+    z = mo.create(np.array([0.0, -0.0, np.nan, 1.0, np.nan, -np.inf]), 6, 1)
+    assert [mo.bits(x) for x in mo.cummin(z, 0).to_array()] == [mo.bits(x) for x in [0.0, -0.0, -0.0, -0.0, -0.0, -np.inf]]
+    assert np.isnan(mo.cummax(z, 0).to_array()[2:]).all() and mo.bits(mo.cummax(z, 0).to_array()[1]) == mo.bits(0.0)
+    with pytest.raises(ValueError):
+        mo.cummax(mo.create(np.zeros(0), 0, 3), 0)
+    assert mo.cummax(mo.create(np.zeros(0), 0, 3), 1).shape == (0, 3)

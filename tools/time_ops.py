@@ -13,7 +13,10 @@ ops = sys.argv[2].split(",") if len(sys.argv) > 2 else ["softmax1", "softmax0", 
 u.init(0)
 m = u.MatD.randn(n, n, seed=42)
 E = float(n) * n
+mask = m.gt(0.0)
 table = {"softmax1": (lambda: m.softmax(1), 16), "softmax0": (lambda: m.softmax(0), 16), "sigmoid": (lambda: m.sigmoid(), 16),
+         "cumsum0": (lambda: m.cumsum(0), 16), "cumsum1": (lambda: m.cumsum(1), 16), "cummax0": (lambda: m.cummax(0), 16),
+         "cummax1": (lambda: m.cummax(1), 16), "where": (lambda: u.Mat.where(mask, m, m), 17), "select": (lambda: m[mask], 13),
          "var0": (lambda: m.var(0), 8), "var1": (lambda: m.var(1), 8), "sum0": (lambda: m.sum(0), 8), "relu": (lambda: m.relu(), 16)}
 for op in ops:
     fn, bpe = table[op]

@@ -20,6 +20,7 @@ GT, LT, GTE, LTE, EQ, NE = range(6)
 ISNAN, ISINF, ISFINITE = range(3)
 AND, OR, NOT, XOR = range(4)
 SUM, MEAN, VAR, STD, MIN, MAX = range(6)
+CUMSUM, CUMMAX, CUMMIN = range(3)
 TPRF_CLOSED, TPRF_ITER, TPRF_IS_FULL = range(3)
 
 
@@ -120,6 +121,11 @@ SIGNATURES = {
     "um_classify": (_i32, [_i32, VP, VP]),
     "um_mask_logic": (_i32, [_i32, VP, VP, VP]),
     "um_mask_reduce": (_i32, [_i32, VP, _i32, VP, C.POINTER(_i32)]),
+    "um_cumulative": (_i32, [_i32, VP, _i32, VP]),
+    "um_where": (_i32, [VP, VP, VP, VP]),
+    "um_where_scalar": (_i32, [VP, _f64, _f64, VP]),
+    "um_mask_count": (_i32, [VP, C.POINTER(_i64)]),
+    "um_mask_select": (_i32, [VP, VP, VP]),
     "um_reduce_all": (_i32, [_i32, VP, C.POINTER(_f64)]),
     "um_reduce_axis": (_i32, [_i32, VP, _i32, VP]),
     "um_arg_all": (_i32, [_i32, VP, C.POINTER(_i64), C.POINTER(_i64)]),

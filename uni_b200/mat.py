@@ -220,7 +220,9 @@ class Mat:
         return self.astype(L.F32)
 
     def __getitem__(self, key):
-        """m(r, c) -> element; m(rows, cols) with ranges / `::` -> view."""
+        """m(r, c) -> element; m(rows, cols) with ranges / `::` -> view; m(mask) -> selected elements."""
+        if isinstance(key, Mat):
+            return self.select(key)
         if not isinstance(key, tuple) or len(key) != 2:
             raise ValueError("Mat indexing needs (row, col)")
         r, c = key
@@ -397,6 +399,55 @@ class Mat:
 
     def all(self, axis: Optional[int] = None): return self._mask_reduce(1, axis)
     def any(self, axis: Optional[int] = None): return self._mask_reduce(0, axis)
+
+    # ------------------------------------------------------------------ mask-driven selection
+    def select(self, mask: "Mat") -> "Mat":
+        """m(mask) (Mat.scala:4008-4021): the elements where `mask` is true, row-major order, as a 1 x k row."""
+        if not isinstance(mask, Mat) or mask.dtype != L.BOOL:
+            raise ValueError("mask select needs a Mat[Boolean]")
+        if mask.shape != self.shape:
+            raise ValueError(f"Mask shape {mask.shape} must match matrix shape {self.shape}")
+        k = C.c_int64(0)
+        check(lib.um_mask_count(mask._ref(), C.byref(k)))
+        res = Mat._alloc(1, k.value, self.dtype)
+        check(lib.um_mask_select(self._ref(), mask._ref(), res._ref()))
+        return res
+
+    @staticmethod
+    def where(condition: "Mat", x, y) -> "Mat":
+        """Mat.where(condition, x, y) (Mat.scala:1305-1336): x and y both matrices of the condition's shape,
+        or both scalars (result Mat[Double])."""
+        if not isinstance(condition, Mat) or condition.dtype != L.BOOL:
+            raise ValueError("where: condition must be a Mat[Boolean]")
+        if isinstance(x, Mat) and isinstance(y, Mat):
+            if not (condition.shape == x.shape == y.shape):
+                raise ValueError(f"where: shape mismatch: condition={condition.shape} x={x.shape} y={y.shape}")
+            if x.dtype != y.dtype:
+                raise ValueError("where: x and y must have the same element type")
+            res = Mat._alloc(x.rows, x.cols, x.dtype)
+            check(lib.um_where(condition._ref(), x._ref(), y._ref(), res._ref()))
+            return res
+        if isinstance(x, Mat) or isinstance(y, Mat):
+            raise ValueError("where: x and y must both be matrices or both be scalars")
+        res = Mat._alloc(condition.rows, condition.cols, L.F64)
+        check(lib.um_where_scalar(condition._ref(), float(x), float(y), res._ref()))
+        return res
+
+    # ------------------------------------------------------------------ running folds
+    def _cumulative(self, kind: int, axis: Optional[int]) -> "Mat":
+        if axis is None:
+            res = Mat._alloc(1, self.rows * self.cols, self.dtype)
+            check(lib.um_cumulative(kind, self._ref(), -1, res._ref()))
+            return res
+        if axis not in (0, 1):
+            raise ValueError(f"axis must be 0 or 1, got {axis}")
+        res = Mat._alloc(self.rows, self.cols, self.dtype)
+        check(lib.um_cumulative(kind, self._ref(), axis, res._ref()))
+        return res
+
+    def cumsum(self, axis: Optional[int] = None): return self._cumulative(L.CUMSUM, axis)   # Mat.scala:3635-3690
+    def cummax(self, axis: int): return self._cumulative(L.CUMMAX, axis)                    # Mat.scala:3692-3717
+    def cummin(self, axis: int): return self._cumulative(L.CUMMIN, axis)                    # Mat.scala:3719-3744
 
     # ------------------------------------------------------------------ reductions
     def _reduce(self, kind: int, axis: Optional[int]):
