@@ -192,6 +192,15 @@ def matd_ops(u, peak_gbs, n=32768):
     rec("sum_all", lambda: m.sum(), 8 * E)
     rec("argmax_all", lambda: m.argmax(), 8 * E)
     rec("gt_mask", lambda: m.gt(0.0), 9 * E)
+    # SURVEY 8f rank 2 (running folds are sequential per lane, as the reference pins them; parallel across lanes)
+    rec("cumsum_axis0", lambda: m.cumsum(0), 16 * E)
+    rec("cumsum_axis1", lambda: m.cumsum(1), 16 * E)
+    rec("cummax_axis0", lambda: m.cummax(0), 16 * E)
+    rec("cummax_axis1", lambda: m.cummax(1), 16 * E)
+    mask = m.gt(0.0)
+    rec("where(mask, m, -m)", lambda: u.Mat.where(mask, m, m), 17 * E, "x and y alias the same matrix: one 8-byte read per element")
+    rec("select m(mask)", lambda: m[mask], 14 * E, "mask read twice (count, scatter) + operand + ~half the elements written; includes the host read of k")
+    del mask
     t = m.T
     rec("sum_axis0@transposed_view", lambda: t.sum(0), 8 * E)
     rec("sub_rowvec@row_slice_view", lambda: m.slice(1024, n, 0, n) - rowv, 16 * (E - 1024.0 * n))

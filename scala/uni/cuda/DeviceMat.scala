@@ -87,6 +87,20 @@ final class DeviceMat private (val buf: DeviceBuffer, val view: MemorySegment, v
   def gt(s: Double): DeviceMat =                                                              // Mat.scala:3948-3972
     val o = like(rows, cols, DType.Bool); check(um_compare_scalar.invoke(0, view, s, o.view).asInstanceOf[Int]); o
 
+  // ---- running folds, m(mask), where (Mat.scala:3635-3745, 4008-4021, 1305-1336)
+  private def cum(kind: Int, axis: Int): DeviceMat =
+    require(axis == 0 || axis == 1, s"axis must be 0 or 1, got $axis")
+    val o = like(rows, cols); check(um_cumulative.invoke(kind, view, axis, o.view).asInstanceOf[Int]); o
+  def cumsum(axis: Int): DeviceMat = cum(0, axis)
+  def cummax(axis: Int): DeviceMat = cum(1, axis)
+  def cummin(axis: Int): DeviceMat = cum(2, axis)
+  def cumsum: DeviceMat =
+    val o = like(1, rows * cols); check(um_cumulative.invoke(0, view, -1, o.view).asInstanceOf[Int]); o
+  def apply(mask: DeviceMat): DeviceMat =
+    require(mask.rows == rows && mask.cols == cols, s"Mask shape (${mask.rows}, ${mask.cols}) must match matrix shape ($rows, $cols)")
+    val k = Arena.ofAuto().allocate(JAVA_LONG); check(um_mask_count.invoke(mask.view, k).asInstanceOf[Int])
+    val o = like(1, k.get(JAVA_LONG, 0)); check(um_mask_select.invoke(view, mask.view, o.view).asInstanceOf[Int]); o
+
   // ---- linear algebra (Mat.scala:2815-2881, 2979-3006)
   def *@(b: DeviceMat): DeviceMat =
     require(cols == b.rows, s"matmul shape mismatch: ${rows}x$cols *@ ${b.rows}x${b.cols}")
@@ -94,6 +108,10 @@ final class DeviceMat private (val buf: DeviceBuffer, val view: MemorySegment, v
   def inverse: DeviceMat = { val o = like(rows, cols); check(um_inverse.invoke(view, o.view).asInstanceOf[Int]); o }
 
 object DeviceMat:
+  def where(cond: DeviceMat, x: DeviceMat, y: DeviceMat): DeviceMat =                        // Mat.scala:1305-1321
+    val o = alloc(x.rows, x.cols, x.dtype); check(um_where.invoke(cond.view, x.view, y.view, o.view).asInstanceOf[Int]); o
+  def where(cond: DeviceMat, x: Double, y: Double): DeviceMat =                              // Mat.scala:1323-1336
+    val o = alloc(cond.rows, cond.cols); check(um_where_scalar.invoke(cond.view, x, y, o.view).asInstanceOf[Int]); o
   def alloc(rows: Long, cols: Long, dt: DType = DType.F64): DeviceMat =
     val b = DeviceBuffer.alloc(rows * cols * dt.size)
     val v = Arena.ofAuto().allocate(VIEW)

@@ -68,6 +68,11 @@ object UniMatLib:
   val um_arg_all     = h("um_arg_all", I(JAVA_INT, ADDRESS, ADDRESS, ADDRESS))
   val um_idx_axis    = h("um_idx_axis", I(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS))
   // ---- linear algebra
+  val um_cumulative  = h("um_cumulative", I(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS))
+  val um_where       = h("um_where", I(ADDRESS, ADDRESS, ADDRESS, ADDRESS))
+  val um_where_scalar = h("um_where_scalar", I(ADDRESS, JAVA_DOUBLE, JAVA_DOUBLE, ADDRESS))
+  val um_mask_count  = h("um_mask_count", I(ADDRESS, ADDRESS))
+  val um_mask_select = h("um_mask_select", I(ADDRESS, ADDRESS, ADDRESS))
   val um_matmul  = h("um_matmul", I(ADDRESS, ADDRESS, ADDRESS))
   val um_matmul_set_f32_path = h("um_matmul_set_f32_path", I(JAVA_INT))
   val um_inverse = h("um_inverse", I(ADDRESS, ADDRESS))

@@ -19,67 +19,116 @@ namespace um {
 
 enum { CUM_SUM = 0, CUM_MAX = 1, CUM_MIN = 2 };
 
+// running state of one lane: the value, and for cummax / cummin its order key (kept so that only the incoming
+// element's key is computed per step)
 template <int KIND, class T>
-__device__ __forceinline__ void cum_step(T& acc, T v) {
-  if (KIND == CUM_SUM) acc += v;
-  else if (KIND == CUM_MAX) { if (total_key(v) > total_key(acc)) acc = v; }
-  else { if (total_key(v) < total_key(acc)) acc = v; }
-}
-template <int KIND, class T>
-__device__ __forceinline__ T cum_seed(T first) { return KIND == CUM_SUM ? T(0) : first; }
+struct CumAcc {
+  T v;
+  i64 k;
+  __device__ __forceinline__ void seed(T first) {
+    if (KIND == CUM_SUM) { v = T(0); k = 0; }
+    else { v = first; k = total_key(first); }
+  }
+  __device__ __forceinline__ void step(T x) {
+    if (KIND == CUM_SUM) {
+      v += x;
+    } else {
+      const i64 kx = total_key(x);
+      const bool better = KIND == CUM_MAX ? kx > k : kx < k;
+      if (better) { v = x; k = kx; }
+    }
+  }
+};
 
-// Lanes adjacent in memory (axis 0 of a row-major matrix): thread = lane, U loads in flight per thread.
+// Lanes adjacent in memory (axis 0 of a row-major matrix): thread = lane.  The loads of the next 16 elements are
+// issued before the current 16 are folded, so 16-32 loads per thread are in flight behind the dependent chain.
+constexpr int CLT_THREADS = 64;
 template <int KIND, class T>
-__global__ void __launch_bounds__(128) k_cum_lane_per_thread(const T* __restrict__ p, i64 s_lane, i64 s_red, i64 n_lane, i64 n_red,
-                                                              T* __restrict__ out, i64 o_lane, i64 o_red) {
+__global__ void __launch_bounds__(CLT_THREADS) k_cum_lane_per_thread(const T* __restrict__ p, i64 s_lane, i64 s_red, i64 n_lane, i64 n_red,
+                                                                      T* __restrict__ out, i64 o_lane, i64 o_red) {
   constexpr int U = 16;
-  const i64 l = (i64)blockIdx.x * 128 + threadIdx.x;
+  const i64 l = (i64)blockIdx.x * CLT_THREADS + threadIdx.x;
   if (l >= n_lane) return;
   const T* q = p + l * s_lane;
   T* o = out + l * o_lane;
-  T acc = cum_seed<KIND, T>(q[0]);
+  CumAcc<KIND, T> acc;
+  acc.seed(q[0]);
+  T xa[U], xb[U];
   i64 i = 0;
-  for (; i + U <= n_red; i += U) {
-    T x[U];
+  if (n_red >= U) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) x[u] = q[(i + u) * s_red];
+    for (int u = 0; u < U; ++u) xa[u] = q[u * s_red];
+  }
+  // invariant: xa holds elements [i, i + U) whenever i + U <= n_red
+  while (i + U <= n_red) {
+    const bool more = i + 2 * U <= n_red;
+    if (more) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) xb[u] = q[(i + U + u) * s_red];
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      cum_step<KIND, T>(acc, x[u]);
-      o[(i + u) * o_red] = acc;
+      acc.step(xa[u]);
+      o[(i + u) * o_red] = acc.v;
     }
+    i += U;
+    if (!more) break;
+    const bool more2 = i + 2 * U <= n_red;
+    if (more2) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) xa[u] = q[(i + U + u) * s_red];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      acc.step(xb[u]);
+      o[(i + u) * o_red] = acc.v;
+    }
+    i += U;
+    if (!more2) break;
   }
   for (; i < n_red; ++i) {
-    cum_step<KIND, T>(acc, q[i * s_red]);
-    o[i * o_red] = acc;
+    acc.step(q[i * s_red]);
+    o[i * o_red] = acc.v;
   }
 }
 
 // Lanes whose elements are adjacent in memory (axis 1 of a row-major matrix): a warp owns 32 lanes and walks
-// them in 32 x 32 tiles -- coalesced loads into a padded shared tile, thread j folds lane j's 32 elements in
-// order carrying its accumulator across tiles, coalesced stores back out.
+// them in 32 x 32 tiles -- coalesced loads (a whole tile per warp in flight, the next tile's issued before this
+// one is folded) into a padded shared tile, thread j folds lane j's 32 elements in order carrying its accumulator
+// across tiles, coalesced stores back out.
+constexpr int CTL_WARPS = 2;
 template <int KIND, class T>
-__global__ void __launch_bounds__(128) k_cum_lane_tiles(const T* __restrict__ p, i64 s_lane, i64 s_red, i64 n_lane, i64 n_red,
-                                                         T* __restrict__ out, i64 o_lane, i64 o_red) {
-  __shared__ T tile[4][32][33];
+__global__ void __launch_bounds__(CTL_WARPS * 32) k_cum_lane_tiles(const T* __restrict__ p, i64 s_lane, i64 s_red, i64 n_lane, i64 n_red,
+                                                                    T* __restrict__ out, i64 o_lane, i64 o_red) {
+  __shared__ T tile[CTL_WARPS][32][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const i64 l0 = ((i64)blockIdx.x * 4 + w) * 32;
+  const i64 l0 = ((i64)blockIdx.x * CTL_WARPS + w) * 32;
   if (l0 >= n_lane) return;
   const int nl = (int)min((i64)32, n_lane - l0);
-  T acc = T(0);
-  if (lane < nl) acc = cum_seed<KIND, T>(p[(l0 + lane) * s_lane]);
+  CumAcc<KIND, T> acc;
+  acc.seed(lane < nl ? p[(l0 + lane) * s_lane] : T(0));
+  T x[32];
+  auto fetch = [&](i64 t0) {
+    const bool col = t0 + lane < n_red;
+#pragma unroll
+    for (int r = 0; r < 32; ++r)
+      if (col && r < nl) x[r] = p[(l0 + r) * s_lane + (t0 + lane) * s_red];
+  };
+  fetch(0);
   for (i64 t0 = 0; t0 < n_red; t0 += 32) {
     const int nt = (int)min((i64)32, n_red - t0);
     if (lane < nt) {
-#pragma unroll 8
-      for (int r = 0; r < nl; ++r) tile[w][r][lane] = p[(l0 + r) * s_lane + (t0 + lane) * s_red];
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        if (r < nl) tile[w][r][lane] = x[r];
     }
     __syncwarp();
+    if (t0 + 32 < n_red) fetch(t0 + 32);
     if (lane < nl) {
 #pragma unroll 8
       for (int k = 0; k < nt; ++k) {
-        cum_step<KIND, T>(acc, tile[w][lane][k]);
-        tile[w][lane][k] = acc;
+        acc.step(tile[w][lane][k]);
+        tile[w][lane][k] = acc.v;
       }
     }
     __syncwarp();
@@ -94,34 +143,41 @@ __global__ void __launch_bounds__(128) k_cum_lane_tiles(const T* __restrict__ p,
 // Flat running fold over the row-major element order (m.cumsum with no axis): ONE lane.  A warp loads 4 x 32
 // elements ahead, every thread folds all of them in order (the adds are the dependent chain; the shuffles are
 // not on it) and thread j keeps the values of its own positions.
-template <int KIND, class T>
+template <int KIND, class T, bool FLAT>
 __global__ void __launch_bounds__(32) k_cum_flat(const T* __restrict__ p, i64 rs, i64 cs, i64 rows, i64 cols, T* __restrict__ out) {
   constexpr int U = 4;
   const int lane = threadIdx.x;
   const i64 n = rows * cols;
-  auto at = [&](i64 e) { return p[(e / cols) * rs + (e % cols) * cs]; };
-  T acc = cum_seed<KIND, T>(n > 0 ? at(0) : T(0));
-  for (i64 e0 = 0; e0 < n; e0 += 32 * U) {
-    T x[U], mine[U];
+  auto at = [&](i64 e) { return FLAT ? p[e] : p[(e / cols) * rs + (e % cols) * cs]; };
+  CumAcc<KIND, T> acc;
+  acc.seed(n > 0 ? at(0) : T(0));
+  T x[U], xn[U];
+  auto fetch = [&](T* dst, i64 e0) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const i64 e = e0 + u * 32 + lane;
-      x[u] = e < n ? at(e) : T(0);
+      dst[u] = e < n ? at(e) : T(0);
     }
+  };
+  fetch(x, 0);
+  for (i64 e0 = 0; e0 < n; e0 += 32 * U) {
+    fetch(xn, e0 + 32 * U);   // the next 128 elements load while these are folded
+    T mine[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       mine[u] = T(0);
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
         const T v = __shfl_sync(0xffffffffu, x[u], k);
-        if (e0 + u * 32 + k < n) cum_step<KIND, T>(acc, v);   // uniform over the warp
-        if (lane == k) mine[u] = acc;
+        if (e0 + u * 32 + k < n) acc.step(v);   // uniform over the warp
+        if (lane == k) mine[u] = acc.v;
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const i64 e = e0 + u * 32 + lane;
       if (e < n) out[e] = mine[u];
+      x[u] = xn[u];
     }
   }
 }
@@ -132,7 +188,8 @@ static int cumulative_typed(const um_view* a, int axis, const um_view* out) {
   T* o = static_cast<T*>(out->data) + out->offset;
   cudaStream_t st = ctx()->stream;
   if (axis < 0) {
-    k_cum_flat<KIND, T><<<1, 32, 0, st>>>(p, a->rs, a->cs, a->rows, a->cols, o);
+    if ((a->cs == 1 || a->cols == 1) && (a->rs == a->cols || a->rows == 1)) k_cum_flat<KIND, T, true><<<1, 32, 0, st>>>(p, a->rs, a->cs, a->rows, a->cols, o);
+    else k_cum_flat<KIND, T, false><<<1, 32, 0, st>>>(p, a->rs, a->cs, a->rows, a->cols, o);
     UM_LAUNCHED();
     return UM_OK;
   }
@@ -142,9 +199,9 @@ static int cumulative_typed(const um_view* a, int axis, const um_view* out) {
   auto mag = [](i64 s) { return s < 0 ? -s : s; };
   // which index is adjacent in memory?  (a stride-0 broadcast lane axis counts as adjacent)
   if (mag(s_lane) <= mag(s_red) || n_red == 1) {
-    k_cum_lane_per_thread<KIND, T><<<(unsigned)((n_lane + 127) / 128), 128, 0, st>>>(p, s_lane, s_red, n_lane, n_red, o, o_lane, o_red);
+    k_cum_lane_per_thread<KIND, T><<<(unsigned)((n_lane + CLT_THREADS - 1) / CLT_THREADS), CLT_THREADS, 0, st>>>(p, s_lane, s_red, n_lane, n_red, o, o_lane, o_red);
   } else {
-    k_cum_lane_tiles<KIND, T><<<(unsigned)((n_lane + 127) / 128), 128, 0, st>>>(p, s_lane, s_red, n_lane, n_red, o, o_lane, o_red);
+    k_cum_lane_tiles<KIND, T><<<(unsigned)((n_lane + CTL_WARPS * 32 - 1) / (CTL_WARPS * 32)), CTL_WARPS * 32, 0, st>>>(p, s_lane, s_red, n_lane, n_red, o, o_lane, o_red);
   }
   UM_LAUNCHED();
   return UM_OK;
@@ -174,6 +231,45 @@ __global__ void __launch_bounds__(256) k_where(In<uint8_t> c, In<T> x, In<T> y, 
   }
 }
 
+// contiguous FP64 operands: two columns per thread, four rows in flight, both sources always loaded
+template <bool SCALAR>
+__global__ void __launch_bounds__(256) k_where_vec(const uint8_t* __restrict__ c, i64 c_rs, const double* __restrict__ x, i64 x_rs,
+                                                    const double* __restrict__ y, i64 y_rs, double sx, double sy, i64 rows, i64 cols,
+                                                    double* __restrict__ o, i64 o_rs) {
+  const i64 j = ((i64)blockIdx.x * 64 + (threadIdx.x & 63)) * 2;
+  if (j >= cols) return;
+  const i64 step = (i64)gridDim.y * 4;
+  i64 i = (i64)blockIdx.y * 4 + (threadIdx.x >> 6);
+  auto one = [&](i64 r, uchar2 t, double2 a, double2 b) {
+    __stcs(reinterpret_cast<double2*>(o + r * o_rs + j), make_double2(t.x ? a.x : b.x, t.y ? a.y : b.y));
+  };
+  for (; i + 3 * step < rows; i += 4 * step) {
+    uchar2 t[4];
+    double2 a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const i64 r = i + u * step;
+      t[u] = *reinterpret_cast<const uchar2*>(c + r * c_rs + j);
+      if (SCALAR) { a[u] = make_double2(sx, sx); b[u] = make_double2(sy, sy); }
+      else {
+        a[u] = *reinterpret_cast<const double2*>(x + r * x_rs + j);
+        b[u] = *reinterpret_cast<const double2*>(y + r * y_rs + j);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(i + u * step, t[u], a[u], b[u]);
+  }
+  for (; i < rows; i += step) {
+    const uchar2 t = *reinterpret_cast<const uchar2*>(c + i * c_rs + j);
+    double2 a = make_double2(sx, sx), b = make_double2(sy, sy);
+    if (!SCALAR) {
+      a = *reinterpret_cast<const double2*>(x + i * x_rs + j);
+      b = *reinterpret_cast<const double2*>(y + i * y_rs + j);
+    }
+    one(i, t, a, b);
+  }
+}
+
 template <class T>
 static int where_typed(const um_view* c, const um_view* x, const um_view* y, double sx, double sy, const um_view* out) {
   const i64 rows = c->rows, cols = c->cols;
@@ -183,6 +279,28 @@ static int where_typed(const um_view* c, const um_view* x, const um_view* y, dou
   const i64 want = ((i64)ctx()->sm_count * 16 + gx - 1) / gx;
   if (gy > want) gy = want;
   if (gy > 65535) gy = 65535;
+  if (sizeof(T) == 8 && cols % 2 == 0) {
+    auto rowvec = [&](const um_view* v, int esz) {   // rows readable as aligned 2-element vectors?
+      const char* q = static_cast<const char*>(v->data) + (size_t)v->offset * esz;
+      return v->cs == 1 && (reinterpret_cast<uintptr_t>(q) % (2 * esz)) == 0 && (rows == 1 || v->rs % 2 == 0);
+    };
+    if (rowvec(c, 1) && rowvec(out, 8) && (!x || (rowvec(x, 8) && rowvec(y, 8)))) {
+      const i64 gxv = (cols / 2 + 63) / 64;
+      i64 gyv = (rows + 15) / 16;
+      const i64 wantv = ((i64)ctx()->sm_count * 16 + gxv - 1) / gxv;
+      if (gyv > wantv) gyv = wantv;
+      if (gyv > 65535) gyv = 65535;
+      if (gyv < 1) gyv = 1;
+      dim3 gridv((unsigned)gxv, (unsigned)gyv);
+      const uint8_t* cp = static_cast<const uint8_t*>(c->data) + c->offset;
+      double* op = static_cast<double*>(out->data) + out->offset;
+      if (x) k_where_vec<false><<<gridv, 256, 0, ctx()->stream>>>(cp, c->rs, static_cast<const double*>(x->data) + x->offset, x->rs,
+                                                                 static_cast<const double*>(y->data) + y->offset, y->rs, 0, 0, rows, cols, op, out->rs);
+      else k_where_vec<true><<<gridv, 256, 0, ctx()->stream>>>(cp, c->rs, nullptr, 0, nullptr, 0, sx, sy, rows, cols, op, out->rs);
+      UM_LAUNCHED();
+      return UM_OK;
+    }
+  }
   dim3 grid((unsigned)gx, (unsigned)gy);
   if (x) k_where<T, false><<<grid, 256, 0, ctx()->stream>>>(in_of<uint8_t>(c), in_of<T>(x), in_of<T>(y), T(0), T(0), rows, cols, out_of<T>(out));
   else k_where<T, true><<<grid, 256, 0, ctx()->stream>>>(in_of<uint8_t>(c), In<T>{nullptr, 0, 0}, In<T>{nullptr, 0, 0}, (T)sx, (T)sy, rows, cols, out_of<T>(out));
@@ -194,15 +312,18 @@ static int where_typed(const um_view* c, const um_view* x, const um_view* y, dou
 constexpr int SEL_CHUNK = 4096;   // flat elements per block
 constexpr int SEL_THREADS = 256;
 
-__device__ __forceinline__ bool mask_at(const In<uint8_t>& m, i64 cols, i64 e) { return m.p[(e / cols) * m.rs + (e % cols) * m.cs] != 0; }
+// element e of the row-major order; FLAT = the view is contiguous (no 64-bit division)
+template <bool FLAT, class T>
+__device__ __forceinline__ T flat_at(const In<T>& m, i64 cols, i64 e) { return FLAT ? m.p[e] : m.p[(e / cols) * m.rs + (e % cols) * m.cs]; }
 
+template <bool FLAT>
 __global__ void __launch_bounds__(SEL_THREADS) k_sel_count(In<uint8_t> m, i64 cols, i64 n, i64* __restrict__ counts) {
   __shared__ int sm[SEL_THREADS / 32];
   const i64 e0 = (i64)blockIdx.x * SEL_CHUNK;
   int c = 0;
   for (int k = threadIdx.x; k < SEL_CHUNK; k += SEL_THREADS) {
     const i64 e = e0 + k;
-    if (e < n && mask_at(m, cols, e)) ++c;
+    if (e < n && flat_at<FLAT>(m, cols, e) != 0) ++c;
   }
   for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
@@ -239,7 +360,7 @@ __global__ void __launch_bounds__(1024) k_sel_scan(i64* __restrict__ counts, i64
   if (threadIdx.x == 0) counts[nb] = carry;
 }
 
-template <class T>
+template <class T, bool FLAT_A, bool FLAT_M>
 __global__ void __launch_bounds__(SEL_THREADS) k_sel_scatter(In<T> a, In<uint8_t> m, i64 cols, i64 n, const i64* __restrict__ offsets,
                                                               T* __restrict__ out, i64 out_n) {
   __shared__ int sm[SEL_THREADS / 32];
@@ -248,7 +369,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_scatter(In<T> a, In<uint8_t
   i64 base = offsets[blockIdx.x];
   for (int k0 = 0; k0 < SEL_CHUNK; k0 += SEL_THREADS) {
     const i64 e = e0 + k0 + threadIdx.x;
-    const bool t = e < n && mask_at(m, cols, e);
+    const bool t = e < n && flat_at<FLAT_M>(m, cols, e) != 0;
     const unsigned bal = __ballot_sync(0xffffffffu, t);
     if (lane == 0) sm[w] = __popc(bal);
     __syncthreads();
@@ -261,11 +382,84 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_scatter(In<T> a, In<uint8_t
     }
     if (t) {
       const i64 pos = base + before + __popc(bal & ((1u << lane) - 1u));
-      if (pos < out_n) out[pos] = a.p[(e / cols) * a.rs + (e % cols) * a.cs];
+      if (pos < out_n) out[pos] = flat_at<FLAT_A>(a, cols, e);
     }
     base += total;
     __syncthreads();
   }
+}
+
+// Contiguous operand and mask: a warp owns 512 consecutive elements.  All 16 coalesced loads of the mask bytes and of
+// the operand are issued up front; the mask bits stay in a register, positions come from ballots, and the only
+// block-level step is the prefix over the 8 warp totals.
+template <class T>
+__global__ void __launch_bounds__(SEL_THREADS) k_sel_scatter_flat(const T* __restrict__ a, const uint8_t* __restrict__ m, i64 n,
+                                                                   const i64* __restrict__ offsets, T* __restrict__ out, i64 out_n) {
+  __shared__ int sm[SEL_THREADS / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const i64 e0 = (i64)blockIdx.x * SEL_CHUNK + (i64)w * 512;
+  unsigned bits = 0;
+  T av[16];
+  int total = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const i64 e = e0 + k * 32 + lane;
+    const bool in = e < n;
+    const bool t = in && m[e] != 0;
+    av[k] = in ? a[e] : T(0);
+    bits |= (t ? 1u : 0u) << k;
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) total += __popc(__ballot_sync(0xffffffffu, (bits >> k) & 1u));
+  if (lane == 0) sm[w] = total;
+  __syncthreads();
+  i64 base = offsets[blockIdx.x];
+  for (int q = 0; q < w; ++q) base += sm[q];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const bool t = (bits >> k) & 1u;
+    const unsigned bal = __ballot_sync(0xffffffffu, t);
+    if (t) {
+      const i64 pos = base + __popc(bal & ((1u << lane) - 1u));
+      if (pos < out_n) out[pos] = av[k];
+    }
+    base += __popc(bal);
+  }
+}
+
+// count for a contiguous mask: 16 bytes per thread per load
+__global__ void __launch_bounds__(SEL_THREADS) k_sel_count_flat(const uint8_t* __restrict__ m, i64 n, i64* __restrict__ counts) {
+  __shared__ int sm[SEL_THREADS / 32];
+  const i64 e = (i64)blockIdx.x * SEL_CHUNK + (i64)threadIdx.x * 16;
+  int c = 0;
+  if (e + 16 <= n && (reinterpret_cast<uintptr_t>(m + e) & 15) == 0) {
+    const uint4 v = *reinterpret_cast<const uint4*>(m + e);
+    c = (__popc(__vcmpne4(v.x, 0)) + __popc(__vcmpne4(v.y, 0)) + __popc(__vcmpne4(v.z, 0)) + __popc(__vcmpne4(v.w, 0))) >> 3;
+  } else {
+    for (int k = 0; k < 16; ++k)
+      if (e + k < n && m[e + k] != 0) ++c;
+  }
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int q = 0; q < SEL_THREADS / 32; ++q) t += sm[q];
+    counts[blockIdx.x] = t;
+  }
+}
+
+static bool view_is_flat(const um_view* v) { return (v->cs == 1 || v->cols == 1) && (v->rs == v->cols || v->rows == 1); }
+
+template <class T>
+static void sel_scatter(const um_view* a, const um_view* mask, i64 n, const i64* offs, void* o, i64 out_n, unsigned g) {
+  cudaStream_t st = ctx()->stream;
+  const bool fa = view_is_flat(a), fm = view_is_flat(mask);
+  T* op = static_cast<T*>(o);
+  if (fa && fm) k_sel_scatter_flat<T><<<g, SEL_THREADS, 0, st>>>(in_of<T>(a).p, in_of<uint8_t>(mask).p, n, offs, op, out_n);
+  else if (fa) k_sel_scatter<T, true, false><<<g, SEL_THREADS, 0, st>>>(in_of<T>(a), in_of<uint8_t>(mask), a->cols, n, offs, op, out_n);
+  else if (fm) k_sel_scatter<T, false, true><<<g, SEL_THREADS, 0, st>>>(in_of<T>(a), in_of<uint8_t>(mask), a->cols, n, offs, op, out_n);
+  else k_sel_scatter<T, false, false><<<g, SEL_THREADS, 0, st>>>(in_of<T>(a), in_of<uint8_t>(mask), a->cols, n, offs, op, out_n);
 }
 
 static int sel_offsets(const um_view* mask, i64** offsets_out, i64* nb_out) {
@@ -274,7 +468,8 @@ static int sel_offsets(const um_view* mask, i64** offsets_out, i64* nb_out) {
   i64* counts = static_cast<i64*>(scratch((size_t)(nb + 1) * sizeof(i64)));
   if (!counts) return UM_ERR_OOM;
   if (nb > 0) {
-    k_sel_count<<<(unsigned)nb, SEL_THREADS, 0, ctx()->stream>>>(in_of<uint8_t>(mask), mask->cols, n, counts);
+    if (view_is_flat(mask)) k_sel_count_flat<<<(unsigned)nb, SEL_THREADS, 0, ctx()->stream>>>(in_of<uint8_t>(mask).p, n, counts);
+    else k_sel_count<false><<<(unsigned)nb, SEL_THREADS, 0, ctx()->stream>>>(in_of<uint8_t>(mask), mask->cols, n, counts);
     UM_LAUNCHED();
   }
   k_sel_scan<<<1, 1024, 0, ctx()->stream>>>(counts, nb);
@@ -367,14 +562,13 @@ int32_t um_mask_select(const um_view* a, const um_view* mask, const um_view* out
   i64 nb = 0;
   int s = sel_offsets(mask, &offs, &nb);
   if (s != UM_OK) return s;
-  cudaStream_t st = ctx()->stream;
   const unsigned g = (unsigned)nb;
   void* o = static_cast<char*>(out->data) + (size_t)out->offset * dtype_size(out->dtype);
   switch (a->dtype) {
-    case UM_F64: k_sel_scatter<double><<<g, SEL_THREADS, 0, st>>>(in_of<double>(a), in_of<uint8_t>(mask), a->cols, n, offs, static_cast<double*>(o), out->cols); break;
-    case UM_F32: k_sel_scatter<float><<<g, SEL_THREADS, 0, st>>>(in_of<float>(a), in_of<uint8_t>(mask), a->cols, n, offs, static_cast<float*>(o), out->cols); break;
-    case UM_I32: k_sel_scatter<int32_t><<<g, SEL_THREADS, 0, st>>>(in_of<int32_t>(a), in_of<uint8_t>(mask), a->cols, n, offs, static_cast<int32_t*>(o), out->cols); break;
-    default: k_sel_scatter<uint8_t><<<g, SEL_THREADS, 0, st>>>(in_of<uint8_t>(a), in_of<uint8_t>(mask), a->cols, n, offs, static_cast<uint8_t*>(o), out->cols); break;
+    case UM_F64: sel_scatter<double>(a, mask, n, offs, o, out->cols, g); break;
+    case UM_F32: sel_scatter<float>(a, mask, n, offs, o, out->cols, g); break;
+    case UM_I32: sel_scatter<int32_t>(a, mask, n, offs, o, out->cols, g); break;
+    default: sel_scatter<uint8_t>(a, mask, n, offs, o, out->cols, g); break;
   }
   UM_LAUNCHED();
   return UM_OK;
