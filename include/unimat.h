@@ -244,6 +244,11 @@ int32_t um_tprf_set_path(int32_t path);
  * (rank, warp, piece) into this device buffer of 16*16*64*8 int64 (tools/fused_timeline.py). */
 int32_t um_tprf_debug_stamps(long long* device_buf);
 int32_t um_tprf_fused_info(int64_t T, int32_t* cluster_size, int32_t* rows_per_piece, int32_t* resident_clusters);
+/* Out-of-sample point forecast of one window (t3prfTail's `yhatt`, Tprf3.scala:913-943), from the outputs of
+ * um_tprf_fit(UM_TPRF_ITER) on the window's kept rows: phi (N x L), xstd (N), beta3 (L+1), and the held-out row
+ * xt (1 x N, any column stride).  estimate3prf's OOS procedures (Tprf3.scala:1112-1199) call it once per window.
+ * Synchronises; NaN when [1|Phi]'[1|Phi] has an exact-zero pivot. */
+int32_t um_tprf_oos_forecast(const um_view* phi, const um_view* xstd, const um_view* beta3, const um_view* xt, double* host_out);
 /* accounting for bench.py: algorithmic flops/bytes of one fit */
 int32_t um_tprf_work(int64_t T, int64_t N, int64_t L, double* flops, double* bytes);
 

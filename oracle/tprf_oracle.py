@@ -165,6 +165,117 @@ def estimate3prf_is_full(y, X, Z, min_obs: int = 10) -> TprfResult:
 
 
 # ---------------------------------------------------------------------------------------
+# estimate3prf with the out-of-sample procedures
+# ---------------------------------------------------------------------------------------
+def _window_fit(yt, Xt, inv_sd, Zt, xt=None, min_obs=10):
+    """t3prfFast + t3prfTail on one window (Tprf3.scala:883-943): `Xt` unscaled, `inv_sd` = 1/column std of
+    the window; returns (yhat or None, yhatt).  `T < minObs` -> all-NaN fit, NaN forecast (:893-894)."""
+    T = yt.shape[0]
+    if T < min_obs:
+        return np.full((T, 1), np.nan), float("nan")
+    L = Zt.shape[1]
+    dZ = with_intercept(Zt)
+    ZtX = (dZ.T @ Xt) * inv_sd.reshape(1, -1)
+    B1 = lu_inverse(dZ.T @ dZ) @ ZtX
+    dP = with_intercept(B1[1:, :].T)
+    PtPinv = lu_inverse(dP.T @ dP)
+    dps = dP * inv_sd.reshape(-1, 1)
+    sigma = ((Xt @ dps) @ PtPinv.T)[:, 1 : L + 1]
+    Xaug = with_intercept(sigma)
+    beta = lu_inverse(Xaug.T @ Xaug) @ (Xaug.T @ yt)
+    yhatt = float("nan")
+    if xt is not None:
+        bo = (xt.reshape(1, -1) @ dps) @ PtPinv.T
+        yhatt = float(beta[0, 0] + bo[0, 1:] @ beta[1:, 0])
+    return Xaug @ beta, yhatt
+
+
+def _inv_std(M):
+    """invStdCols (Tprf3.scala:618-642 family): reciprocal sample std, sd == 0 -> 1."""
+    return 1.0 / nan_std_cols(M).reshape(-1)
+
+
+def encnew(e1, e2) -> float:
+    """Tprf3.scala:854-860, called as encnew(rollfore[loc], residuals[loc]) (:1235-1238)."""
+    ok = ~np.isnan(e1) & ~np.isnan(e2)
+    a, b = e1[ok], e2[ok]
+    with np.errstate(all="ignore"):
+        return float(a.size * (a * a - a * b).sum() / (b * b).sum())
+
+
+def estimate3prf(y, X, Z, procedure="IS Full", window=(0, 1), mintrain=(-1, 0), rollwin=(30, 20, 0)) -> TprfResult:
+    """`Tprf3.estimate3prf` for NaN-free input (Tprf3.scala:1056-1250), every window fitted directly (the
+    reference's FullSample downdating is an O(eps) re-association of the same sums, :742-757).
+    `Z` = proxy matrix (Right) or an int L (Left: automatic proxies).  Result: forecasts, residuals, r_squared,
+    extra = {rollfore, enc}."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    X = np.asarray(X, dtype=np.float64)
+    T, N = X.shape
+    auto = isinstance(Z, (int, np.integer))
+    L = int(Z) if auto else np.asarray(Z).shape[1]
+    Zm = None if auto else np.asarray(Z, dtype=np.float64)
+    mt = (T // 2, mintrain[1]) if mintrain[0] < 0 else tuple(mintrain)
+    win, min_nona, gap = rollwin
+    Xn = X / nan_std_cols(X)
+    forecasts = np.full((T, 1), np.nan)
+    rollfore = np.full((T, 1), np.nan)
+
+    def window_forecast(yt, Xt, Zt, xt, min_obs=10):
+        inv = _inv_std(Xt)
+        if not auto:
+            return _window_fit(yt, Xt, inv, Zt, xt, 10)[1]
+        r0, tp = yt * 1.0, float("nan")
+        for _ in range(L):  # :1134-1139: each new residual column goes in FRONT
+            yh, tp = _window_fit(yt, Xt, inv, r0, xt, min_obs)
+            r0 = np.column_stack([yt - yh, r0])
+        return tp
+
+    if procedure == "IS Full":
+        ones = np.ones(N)
+        if auto:
+            r0, fore = y * 1.0, np.full((T, 1), np.nan)
+            for _ in range(L):  # :1097-1106: residual columns are appended at the BACK
+                fore = _window_fit(y, Xn, ones, r0, None, 10)[0]
+                r0 = np.column_stack([r0, y - fore])
+            forecasts[:] = fore
+        else:
+            forecasts[:] = _window_fit(y, Xn, ones, Zm, None, 10)[0]
+    elif procedure == "OOS Cross Val":
+        for t in range(T):
+            lo, hi = max(t - window[0], 0), min(t - window[0] + window[1], T)
+            keep = np.r_[0:lo, hi:T]
+            yt = y[keep]
+            forecasts[t, 0] = window_forecast(yt, Xn[keep], None if auto else Zm[keep], Xn[t])
+            rollfore[t, 0] = yt.mean()
+    elif procedure == "OOS Recursive":
+        for t in range(mt[0] + 1 + mt[1], T):
+            end = t - 1 - mt[1]
+            yt = y[:end]
+            forecasts[t, 0] = window_forecast(yt, Xn[:end], None if auto else Zm[:end], Xn[t], mt[0])
+            rollfore[t, 0] = yt.mean()
+    elif procedure == "OOS Rolling":
+        for t in range(win + 1 + gap, T):
+            lo, hi = max(t - win - gap, 0), min(t - 1 - gap, T)
+            yt = y[lo:hi]
+            forecasts[t, 0] = window_forecast(yt, Xn[lo:hi], None if auto else Zm[lo:hi], Xn[t], min_nona)
+            rollfore[t, 0] = yt.mean()
+    else:
+        raise ValueError(f"Unknown procedure '{procedure}'. Choose: 'IS Full', 'OOS Recursive', 'OOS Cross Val', 'OOS Rolling'")
+
+    resid = y - forecasts
+    loc = ~np.isnan(resid[:, 0])
+    with np.errstate(all="ignore"):
+        if procedure == "IS Full":  # :1214-1225
+            mu = y[loc, 0].sum() / loc.sum()
+            r2 = 1.0 - float((resid[loc, 0] ** 2).sum()) / float(((y[loc, 0] - mu) ** 2).sum())
+        else:  # :1226-1233: rolling-mean denominator, ssT == 0 -> NaN
+            sst = float(((y[loc, 0] - rollfore[loc, 0]) ** 2).sum())
+            r2 = 1.0 - float((resid[loc, 0] ** 2).sum()) / sst if sst != 0.0 else float("nan")
+    enc = encnew(rollfore[loc, 0], resid[loc, 0]) if procedure == "OOS Recursive" else float("nan")
+    return TprfResult(forecasts, resid, r2, extra={"rollfore": rollfore, "enc": enc})
+
+
+# ---------------------------------------------------------------------------------------
 # scalable (Gram-reassociated) closed form -- the reference's own Rust port does this
 # ---------------------------------------------------------------------------------------
 def tprf_closed_form_gram(y, X, Z) -> TprfResult:

@@ -85,6 +85,7 @@ object UniMatLib:
     I(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS))
   // which sweep the fits use (0 auto, 1 two-sweep, 2 cluster sweep, 3 grid sweep) and its shape on this device
   val um_tprf_set_path   = h("um_tprf_set_path", I(JAVA_INT))
+  val um_tprf_oos_forecast = h("um_tprf_oos_forecast", I(ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS))
   val um_tprf_fused_info = h("um_tprf_fused_info", I(JAVA_LONG, ADDRESS, ADDRESS, ADDRESS))
   val um_comm_unique_id = h("um_comm_unique_id", I(ADDRESS))
   val um_comm_init      = h("um_comm_init", I(JAVA_INT, JAVA_INT, ADDRESS))

@@ -288,3 +288,73 @@ def test_batched_config5_sample(u):
         assert close(F[p], o.forecasts.ravel()), p
         assert close(A[p], o.alpha.ravel(), rtol=1e-8, atol=1e-14), p
         assert close(R[p], o.r_squared), p
+
+
+# ---------------------------------------------------------------- out-of-sample procedures
+@pytest.mark.parametrize("case", ["T100N10L2", "T140N12L3", "T60N25L2"])
+def test_scala_oos_rows(u, golden_dir, case):
+    """`*/oosrec`, `*/ooscv01`, `*/ooscv23`: r2, enc, every forecast and rolling mean (apps/Tprf3ParityGen.scala:50-62,95-102)."""
+    d = os.path.join(golden_dir, "tprf3-parity")
+    ref = {}
+    with open(os.path.join(d, "scala-reference.txt")) as fh:
+        for line in fh:
+            if line.startswith("#") or not line.strip():
+                continue
+            tag, key, val = line.split()
+            ref[(tag, key)] = float(val)
+    X = np.loadtxt(os.path.join(d, f"{case}_X.csv"), delimiter=",", ndmin=2)
+    y = np.loadtxt(os.path.join(d, f"{case}_y.csv"), delimiter=",", ndmin=2).reshape(-1, 1)
+    Z = np.loadtxt(os.path.join(d, f"{case}_Z.csv"), delimiter=",", ndmin=2)
+    T = X.shape[0]
+    dy, dX, dZ = devs(u, y, X, Z)
+    for tag, proc, kw in (("oosrec", "OOS Recursive", {"mintrain": (T // 2, 0)}), ("ooscv01", "OOS Cross Val", {"window": (0, 1)}),
+                          ("ooscv23", "OOS Cross Val", {"window": (2, 3)})):
+        r = u.estimate3prf(dy, dX, dZ, proc, **kw)
+        lab = f"{case}/{tag}"
+        assert close(r.rSquared, ref[(lab, "r2")]), lab
+        assert close(r.enc, ref[(lab, "enc")]), lab
+        assert close(r.forecasts.to_numpy()[:, 0], [ref[(lab, f"f{i}")] for i in range(T)]), lab
+        assert close(r.rollfore.to_numpy()[:, 0], [ref[(lab, f"roll{i}")] for i in range(T)]), lab
+        assert close(r.residuals.to_numpy(), y - r.forecasts.to_numpy())
+
+
+def test_python_reference_oos_vectors(u, golden_dir):
+    """Rolling windows, gaps and the automatic-proxy loops against the reference's NumPy implementation
+    (tests/golden/gen_tprf_oos_pyref.py) and against the oracle."""
+    from tests.test_oracle_tprf import oos_pyref_cases
+    n = 0
+    for name, y, X, Z, proc, kw, g in oos_pyref_cases(golden_dir):
+        dy, dX = u.Mat.from_numpy(y), u.Mat.from_numpy(X)
+        r = u.estimate3prf(dy, dX, Z if isinstance(Z, int) else u.Mat.from_numpy(Z), proc, **kw)
+        want = g["forecasts"]
+        got = r.forecasts.to_numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(want)), name
+        # automatic proxies feed each fit's residuals into the next fit's Z: rounding differences compound
+        tol = 1e-7 if isinstance(Z, int) else 1e-9
+        assert close(got, want, rtol=tol, atol=tol), name
+        assert close(r.rSquared, float(g["rsquare"]), rtol=tol, atol=tol), name
+        o = to.estimate3prf(y, X, Z, proc, **kw)
+        assert close(got, o.forecasts, rtol=tol, atol=tol), name
+        if proc != "IS Full":
+            assert close(r.rollfore.to_numpy(), o.extra["rollfore"]), name
+        if proc == "OOS Recursive":
+            assert close(r.enc, float(g["enc"]), rtol=max(tol, 1e-8)), name
+        n += 1
+    assert n >= 10
+
+
+def test_oos_windows_on_a_wide_panel(u):
+    """A window count small enough to run here, a panel wide enough for the single-read sweeps (N = 4096)."""
+    rng = np.random.default_rng(77)
+    T, N, Lp = 72, 4096, 3
+    X = rng.standard_normal((T, N)); y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, Lp))
+    dy, dX, dZ = devs(u, y, X, Z)
+    r = u.estimate3prf(dy, dX, dZ, "OOS Recursive", mintrain=(60, 0))
+    o = to.estimate3prf(y, X, Z, "OOS Recursive", mintrain=(60, 0))
+    assert close(r.forecasts.to_numpy(), o.forecasts) and close(r.rSquared, o.r_squared) and close(r.enc, o.extra["enc"], rtol=1e-8)
+    r = u.estimate3prf(dy, dX, dZ, "OOS Rolling", rollwin=(40, 20, 1))
+    o = to.estimate3prf(y, X, Z, "OOS Rolling", rollwin=(40, 20, 1))
+    assert close(r.forecasts.to_numpy(), o.forecasts) and close(r.rSquared, o.r_squared)
+    with pytest.raises(NotImplementedError):
+        Xn = X.copy(); Xn[3, 5] = np.nan
+        u.estimate3prf(dy, u.Mat.from_numpy(Xn), dZ, "OOS Rolling")

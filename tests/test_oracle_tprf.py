@@ -111,3 +111,63 @@ def test_edge_semantics():
     rng = np.random.default_rng(0)
     r = to.estimate3prf_is_full(rng.standard_normal((5, 1)), rng.standard_normal((5, 4)), rng.standard_normal((5, 1)))
     assert np.isnan(r.forecasts).all() and np.isnan(r.r_squared)
+
+
+# ---------------------------------------------------------------- out-of-sample procedures
+_SCALA_OOS = [("oosrec", "OOS Recursive", {}), ("ooscv01", "OOS Cross Val", {"window": (0, 1)}),
+              ("ooscv23", "OOS Cross Val", {"window": (2, 3)})]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_scala_oos_rows(golden_dir, case):
+    """Every `*/oosrec`, `*/ooscv01`, `*/ooscv23` row: r2, enc, f<i>, roll<i> (apps/Tprf3ParityGen.scala:50-62,95-102)."""
+    ref = _load_scala_ref(golden_dir)
+    y, X, Z = _panel(golden_dir, case)
+    T = X.shape[0]
+    for tag, proc, kw in _SCALA_OOS:
+        if proc == "OOS Recursive":
+            kw = {"mintrain": (T // 2, 0)}
+        r = to.estimate3prf(y, X, Z, proc, **kw)
+        lab = f"{case}/{tag}"
+        assert _close(r.r_squared, ref[(lab, "r2")]), lab
+        assert _close(r.extra["enc"], ref[(lab, "enc")]), lab
+        for i in range(T):
+            assert _close(float(r.forecasts[i, 0]), ref[(lab, f"f{i}")]), (lab, i)
+            assert _close(float(r.extra["rollfore"][i, 0]), ref[(lab, f"roll{i}")]), (lab, i)
+    isf = to.estimate3prf(y, X, Z, "IS Full")
+    assert _close(isf.r_squared, ref[(f"{case}/isfull", "r2")])
+    assert all(_close(float(isf.forecasts[i, 0]), ref[(f"{case}/isfull", f"f{i}")]) for i in range(T))
+
+
+def oos_pyref_cases(golden_dir):
+    d = os.path.join(golden_dir, "tprf_oos_pyref")
+    for f in sorted(x for x in os.listdir(d) if x.endswith(".npz")):
+        g = np.load(os.path.join(d, f))
+        rng = np.random.default_rng(int(g["seed"]))
+        T, N, L = int(g["T"]), int(g["N"]), int(g["L"])
+        X = rng.standard_normal((T, N)); y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, L))
+        kw = {k[3:]: tuple(int(v) for v in g[k]) for k in g.files if k.startswith("kw_")}
+        yield f[:-4], y, X, (L if bool(g["auto"]) else Z), str(g["procedure"]), kw, g
+
+
+def test_python_reference_oos_vectors(golden_dir):
+    """Rolling windows and the automatic-proxy loops, which the Scala fixture does not cover: outputs of the reference's
+    NumPy implementation (tests/golden/gen_tprf_oos_pyref.py)."""
+    n = 0
+    for name, y, X, Z, proc, kw, g in oos_pyref_cases(golden_dir):
+        r = to.estimate3prf(y, X, Z, proc, **kw)
+        want = g["forecasts"]
+        assert np.array_equal(np.isnan(r.forecasts), np.isnan(want)), name
+        ok = ~np.isnan(want)
+        assert np.max(np.abs(r.forecasts[ok] - want[ok]) / np.maximum(1.0, np.abs(want[ok]))) < 1e-9, name
+        assert _close(r.r_squared, float(g["rsquare"])) or abs(r.r_squared - float(g["rsquare"])) < 1e-9, name
+        if proc == "OOS Recursive":
+            assert abs(r.extra["enc"] - float(g["enc"])) <= 1e-8 * max(1.0, abs(float(g["enc"]))), name
+        n += 1
+    assert n >= 10
+
+
+def test_estimate3prf_unknown_procedure():
+    y, X, Z = np.zeros((20, 1)), np.ones((20, 3)), np.ones((20, 1))
+    with pytest.raises(ValueError):
+        to.estimate3prf(y, X, Z, "OOS Bootstrap")      # Tprf3.scala:1201-1204

@@ -1,19 +1,22 @@
 """Host-side mirror of `uni.stats.Tprf3` (src/main/scala/uni/stats/Tprf3.scala) over libunimat.
 
-`tprfClosedForm`, `t3prf`, `estimate3prf(..., "IS Full")` and `forecast3prf` keep the
-reference's names, argument meaning and error behaviour; the work is one fused device sweep
-plus an O(T L^2) finish (uni_b200/csrc/tprf.cu).  Under an active communicator
+`tprfClosedForm`, `t3prf`, `estimate3prf` (IS Full and the three out-of-sample procedures, proxy
+matrix or automatic proxies) and `forecast3prf` keep the reference's names, argument meaning and
+error behaviour; every fit is one fused device sweep plus an O(T L^2) finish (uni_b200/csrc/tprf.cu),
+an out-of-sample window adds one small launch for its held-out row (uni_b200/csrc/tprf_oos.cu).  Under an active communicator
 (`uni_b200.dist`) X is this rank's column shard and `n_total` the global predictor count.
 """
 from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
-from typing import Optional, Union
+from typing import Optional, Tuple, Union
+
+import numpy as np
 
 from . import _lib as L
 from ._lib import UmTprfOut, check, lib
-from .mat import Mat
+from .mat import Mat, MatD
 
 
 @dataclass
@@ -29,6 +32,8 @@ class Tprf3Result:
     alpha: Optional[Mat] = None     # N x 1
     xstd: Optional[Mat] = None      # 1 x N  column sample std used to normalise X
     singular: bool = False
+    rollfore: Optional[Mat] = None  # T x 1  mean of each window's y (OOS procedures, Tprf3.scala:1145)
+    enc: float = float("nan")       # ENC-NEW statistic, OOS Recursive only (Tprf3.scala:854-860,1235-1238)
 
 
 def _fit(mode: int, y: Mat, X: Mat, Z: Mat, n_total: int = 0, want_all: bool = True) -> Tprf3Result:
@@ -79,22 +84,124 @@ def t3prf(y: Mat, X: Mat, Z: Mat, n_total: int = 0) -> Tprf3Result:
 _PROCEDURES = ("IS Full", "OOS Recursive", "OOS Cross Val", "OOS Rolling")
 
 
-def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full", n_total: int = 0) -> Tprf3Result:
-    """Tprf3.estimate3prf (Tprf3.scala:1056-1250), `Right(Z)` + "IS Full" on the device.
+def _std_cols(X: Mat) -> Mat:
+    """stdCols (Tprf3.scala:550-578) for NaN-free data: sample std per column, 0 -> 1."""
+    T = X.rows
+    sd = X.std(0) * float(np.sqrt(T / (T - 1.0))) if T > 1 else MatD.ones(1, X.cols)
+    return Mat.where(sd.eq(0.0), MatD.ones(1, X.cols), sd)
+
+
+def _oos_forecast(res: Tprf3Result, xt: Mat) -> float:
+    out = C.c_double(0)
+    check(lib.um_tprf_oos_forecast(res.phi._ref(), res.xstd._ref(), res.beta3._ref(), xt._ref(), C.byref(out)))
+    return out.value
+
+
+def _window_forecast(yt: Mat, Xt: Mat, Zt: Optional[Mat], n_auto: int, xt: Mat, min_obs: int) -> float:
+    """One out-of-sample window: t3prfFast + t3prfTail's yhatt (Tprf3.scala:883-943).  The fit re-standardises the
+    window's columns by their own sample std (invStdCols of the window); automatic proxies rebuild Z from the
+    window's residuals, each new column in front (:1134-1139)."""
+    if Zt is not None:
+        if yt.rows < 10:                       # runT3prf / t3prfDowndated minObs = 10 (Tprf3.scala:893-894,951-968)
+            return float("nan")
+        return _oos_forecast(_fit(L.TPRF_ITER, yt, Xt, Zt), xt)
+    if yt.rows < min_obs:
+        return float("nan")
+    r0, tp = yt.copy(), float("nan")
+    for _ in range(n_auto):
+        res = _fit(L.TPRF_ITER, yt, Xt, r0)
+        tp = _oos_forecast(res, xt)
+        r0 = MatD.hstack(yt - res.forecasts, r0)
+    return tp
+
+
+def _rows(m: Mat, lo: int, hi: int) -> Mat:
+    return m._raw_slice(lo, hi, 0, m.cols)
+
+
+def _drop_rows(m: Mat, lo: int, hi: int) -> Mat:
+    """dropRows (Tprf3.scala:680-690): every row but the contiguous block [lo, hi), copied."""
+    parts = [p for p in (_rows(m, 0, lo), _rows(m, hi, m.rows)) if p.rows > 0]
+    return MatD.vstack(*parts) if len(parts) > 1 else parts[0].copy()
+
+
+def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full", window: Tuple[int, int] = (0, 1),
+                 mintrain: Tuple[int, int] = (-1, 0), rollwin: Tuple[int, int, int] = (30, 20, 0), n_total: int = 0) -> Tprf3Result:
+    """Tprf3.estimate3prf (Tprf3.scala:1056-1250) on the device, NaN-free input: `Z` a proxy matrix (Right) or an
+    int L (Left: automatic proxies); procedures "IS Full", "OOS Recursive", "OOS Cross Val", "OOS Rolling" with the
+    reference's `window`, `mintrain`, `rollwin` meaning.  Every window is one fused sweep over its kept rows plus
+    one launch for the held-out row; R^2 uses the rolling-mean denominator for the OOS procedures (:1226-1233).
     Unknown procedure -> ValueError, as the reference's IllegalArgumentException (:1201-1204)."""
     if procedure not in _PROCEDURES:
         raise ValueError(f"Unknown procedure '{procedure}'. Choose: 'IS Full', 'OOS Recursive', "
                          "'OOS Cross Val', 'OOS Rolling'")
-    if procedure != "IS Full":
-        raise NotImplementedError(f"'{procedure}' is a SURVEY.md section 8(f) 'next' row; only IS Full runs on the device")
-    if not isinstance(Z, Mat):
-        raise NotImplementedError("autoproxy (Left(L)) is not on the device path yet")
-    return _fit(L.TPRF_IS_FULL, y, X, Z, n_total)
+    auto = not isinstance(Z, Mat)
+    if procedure == "IS Full" and not auto:
+        return _fit(L.TPRF_IS_FULL, y, X, Z, n_total)
+    if n_total:
+        raise NotImplementedError("column-sharded panels run IS Full with a proxy matrix only")
+    n_auto = int(Z) if auto else 0
+    if auto and not 1 <= n_auto <= 8:
+        raise ValueError(f"number of automatic proxies L = {n_auto} outside [1, 8]")
+    if X.isnan().any() or y.isnan().any() or (not auto and Z.isnan().any()):
+        raise NotImplementedError("the NaN-tolerant window fits (hasNan, Tprf3.scala:1079) are not on the device path")
+    T = y.rows
+    Xn = X / _std_cols(X)                                            # Tprf3.scala:1080-1081
+
+    if procedure == "IS Full":                                       # automatic proxies, :1097-1106
+        r0, res = y.copy(), None
+        for j in range(n_auto):
+            last = j == n_auto - 1
+            res = _fit(L.TPRF_IS_FULL if last else L.TPRF_ITER, y, Xn, r0, want_all=last)
+            r0 = MatD.hstack(r0, y - res.forecasts)
+        return res
+
+    mt = (T // 2, mintrain[1]) if mintrain[0] < 0 else (int(mintrain[0]), int(mintrain[1]))
+    win, min_nona, gap = (int(v) for v in rollwin)
+    fore = np.full((T, 1), np.nan)
+    roll = np.full((T, 1), np.nan)
+    if procedure == "OOS Cross Val":                                 # :1112-1146
+        for t in range(T):
+            lo, hi = max(t - window[0], 0), min(t - window[0] + window[1], T)
+            yt = _drop_rows(y, lo, hi)
+            fore[t, 0] = _window_forecast(yt, _drop_rows(Xn, lo, hi), None if auto else _drop_rows(Z, lo, hi), n_auto,
+                                          _rows(Xn, t, t + 1), 10)
+            roll[t, 0] = yt.mean()
+    elif procedure == "OOS Recursive":                               # :1148-1179
+        for t in range(mt[0] + 1 + mt[1], T):
+            end = t - 1 - mt[1]
+            yt = _rows(y, 0, end)
+            fore[t, 0] = _window_forecast(yt, _rows(Xn, 0, end), None if auto else _rows(Z, 0, end), n_auto,
+                                          _rows(Xn, t, t + 1), mt[0])
+            roll[t, 0] = yt.mean()
+    else:                                                            # OOS Rolling, :1181-1199
+        for t in range(win + 1 + gap, T):
+            lo, hi = max(t - win - gap, 0), min(t - 1 - gap, T)
+            yt = _rows(y, lo, hi)
+            fore[t, 0] = _window_forecast(yt, _rows(Xn, lo, hi), None if auto else _rows(Z, lo, hi), n_auto,
+                                          _rows(Xn, t, t + 1), min_nona)
+            roll[t, 0] = yt.mean()
+
+    forecasts, rollfore = Mat.from_numpy(fore), Mat.from_numpy(roll)
+    residuals = y - forecasts
+    loc = ~residuals.isnan()                                         # rows with a forecast (:1207)
+    e, yl, rl = residuals[loc], y[loc], rollfore[loc]
+    r2 = enc = float("nan")
+    if e.cols > 0:
+        see = (e * e).sum()
+        d = yl - rl
+        sst = (d * d).sum()
+        if sst != 0.0:
+            r2 = 1.0 - see / sst                                     # :1226-1233 (ssT == 0 -> NaN)
+        if procedure == "OOS Recursive":                             # encnew(rollfore[loc], residuals[loc]), :854-860
+            with np.errstate(all="ignore"):
+                enc = float(np.float64(e.cols) * np.float64((rl * rl - rl * e).sum()) / np.float64(see))
+    return Tprf3Result(forecasts, residuals, r2, rollfore=rollfore, enc=enc)
 
 
-def forecast3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full") -> Mat:
+def forecast3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full", **kw) -> Mat:
     """Tprf3.forecast3prf (Tprf3.scala:1290-1299)."""
-    return estimate3prf(y, X, Z, procedure).forecasts
+    return estimate3prf(y, X, Z, procedure, **kw).forecasts
 
 
 TPRF_PATH_AUTO, TPRF_PATH_TWO_SWEEP, TPRF_PATH_FUSED, TPRF_PATH_GRID = 0, 1, 2, 3
