@@ -276,6 +276,51 @@ def estimate3prf(y, X, Z, procedure="IS Full", window=(0, 1), mintrain=(-1, 0), 
 
 
 # ---------------------------------------------------------------------------------------
+# PLS-variant closed form + predict (Tprf3.scala:299-401)
+# ---------------------------------------------------------------------------------------
+@dataclass
+class PlsModel:
+    phi: np.ndarray        # N x 1
+    sigma: np.ndarray      # T x 1
+    beta: np.ndarray       # 2 x 1
+    forecasts: np.ndarray  # T x 1
+    col_mean: np.ndarray   # 1 x N  means of the scaled X
+    col_std: np.ndarray    # 1 x N  std of the raw X
+    r_squared: float
+
+    def predict(self, row) -> float:
+        """Pls3prfModel.predict (Tprf3.scala:325-333): passes 2 and 3 for one raw row."""
+        row = np.asarray(row, dtype=np.float64).reshape(-1)
+        if row.size != self.phi.shape[0]:
+            raise ValueError(f"row length {row.size} != {self.phi.shape[0]} predictors")
+        phi = self.phi[:, 0]
+        dot = float(((row / self.col_std[0] - self.col_mean[0]) * phi).sum())
+        return float(self.beta[0, 0] + self.beta[1, 0] * (dot / float((phi * phi).sum())))
+
+
+def pls_closed_form(y, X) -> PlsModel:
+    """`Tprf3.plsClosedForm` (Tprf3.scala:360-390): no intercept in passes 1 and 2, proxy = y."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    X = np.asarray(X, dtype=np.float64)
+    if X.shape[0] != y.shape[0]:
+        raise ValueError(f"X has {X.shape[0]} rows but y has {y.shape[0]}")
+    if np.isnan(X).any() or np.isnan(y).any():
+        raise ValueError("plsClosedForm requires NaN-free input")
+    col_std = nan_std_cols(X)
+    Xn = X / col_std
+    col_mean = Xn.sum(axis=0, keepdims=True) / X.shape[0]
+    Xc = Xn - col_mean
+    yss = float((y.T @ y)[0, 0])
+    with np.errstate(all="ignore"):
+        phi = (Xc.T @ y) / yss
+        sigma = (Xc @ phi) / float((phi.T @ phi)[0, 0])
+    Xaug = with_intercept(sigma)
+    beta = lu_inverse(Xaug.T @ Xaug) @ (Xaug.T @ y)
+    f = Xaug @ beta
+    return PlsModel(phi, sigma, beta, f, col_mean, col_std, _r2_guarded(y, y - f))
+
+
+# ---------------------------------------------------------------------------------------
 # scalable (Gram-reassociated) closed form -- the reference's own Rust port does this
 # ---------------------------------------------------------------------------------------
 def tprf_closed_form_gram(y, X, Z) -> TprfResult:

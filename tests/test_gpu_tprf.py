@@ -358,3 +358,48 @@ def test_oos_windows_on_a_wide_panel(u):
     with pytest.raises(NotImplementedError):
         Xn = X.copy(); Xn[3, 5] = np.nan
         u.estimate3prf(dy, u.Mat.from_numpy(Xn), dZ, "OOS Rolling")
+
+
+# ---------------------------------------------------------------- PLS variant
+@pytest.mark.parametrize("case", ["T100N10L2", "T140N12L3", "T60N25L2"])
+def test_scala_pls_rows(u, golden_dir, case):
+    """`*/pls`: r2, b0, b1, f<i>, pred0 (apps/Tprf3ParityGen.scala:69-79,104)."""
+    d = os.path.join(golden_dir, "tprf3-parity")
+    ref = {}
+    with open(os.path.join(d, "scala-reference.txt")) as fh:
+        for line in fh:
+            if line.startswith("#") or not line.strip():
+                continue
+            tag, key, val = line.split()
+            ref[(tag, key)] = float(val)
+    X = np.loadtxt(os.path.join(d, f"{case}_X.csv"), delimiter=",", ndmin=2)
+    y = np.loadtxt(os.path.join(d, f"{case}_y.csv"), delimiter=",", ndmin=2).reshape(-1, 1)
+    T = X.shape[0]
+    m = u.plsClosedForm(u.Mat.from_numpy(y), u.Mat.from_numpy(X))
+    lab = f"{case}/pls"
+    assert close(m.rSquared, ref[(lab, "r2")])
+    assert close(m.beta.to_numpy()[:, 0], [ref[(lab, "b0")], ref[(lab, "b1")]])
+    assert close(m.forecasts.to_numpy()[:, 0], [ref[(lab, f"f{i}")] for i in range(T)])
+    assert close(m.predict(X[0]), ref[(lab, "pred0")])
+    o = to.pls_closed_form(y, X)
+    assert close(m.phi.to_numpy(), o.phi) and close(m.sigma.to_numpy(), o.sigma)
+    assert close(m.colMean.to_numpy(), o.col_mean, atol=1e-15) and close(m.colStd.to_numpy(), o.col_std)
+    assert close(m.predictAll(X[:7]).to_numpy()[:, 0], [o.predict(X[i]) for i in range(7)])
+    m2 = u.pls1Fit(X.tolist(), y[:, 0].tolist())
+    assert np.array_equal(m2.forecasts.to_numpy(), m.forecasts.to_numpy())
+    with pytest.raises(ValueError):
+        m.predict(X[0, :-1])
+    with pytest.raises(ValueError):
+        u.plsClosedForm(u.Mat.from_numpy(y[:-1]), u.Mat.from_numpy(X))
+
+
+def test_pls_wide_panel_vs_oracle(u):
+    rng = np.random.default_rng(12)
+    T, N = 512, 4096
+    X = rng.standard_normal((T, N)) * rng.uniform(0.5, 3.0, size=(1, N)) + rng.uniform(-2, 2, size=(1, N))
+    y = (X[:, :5] @ rng.standard_normal((5, 1))) + rng.standard_normal((T, 1)) + 0.7
+    m = u.plsClosedForm(u.Mat.from_numpy(y), u.Mat.from_numpy(X))
+    o = to.pls_closed_form(y, X)
+    assert close(m.forecasts.to_numpy(), o.forecasts) and close(m.rSquared, o.r_squared)
+    assert close(m.beta.to_numpy(), o.beta) and close(m.phi.to_numpy(), o.phi)
+    assert close(m.predict(X[11] * 1.01), o.predict(X[11] * 1.01))

@@ -171,3 +171,24 @@ def test_estimate3prf_unknown_procedure():
     y, X, Z = np.zeros((20, 1)), np.ones((20, 3)), np.ones((20, 1))
     with pytest.raises(ValueError):
         to.estimate3prf(y, X, Z, "OOS Bootstrap")      # Tprf3.scala:1201-1204
+
+
+# ---------------------------------------------------------------- PLS variant
+@pytest.mark.parametrize("case", CASES)
+def test_scala_pls_rows(golden_dir, case):
+    """`*/pls`: r2, b0, b1, every forecast and the raw-row prediction pred0 (apps/Tprf3ParityGen.scala:69-79,104)."""
+    ref = _load_scala_ref(golden_dir)
+    y, X, _ = _panel(golden_dir, case)
+    m = to.pls_closed_form(y, X)
+    lab = f"{case}/pls"
+    assert _close(m.r_squared, ref[(lab, "r2")])
+    assert _close(float(m.beta[0, 0]), ref[(lab, "b0")]) and _close(float(m.beta[1, 0]), ref[(lab, "b1")])
+    for i in range(X.shape[0]):
+        assert _close(float(m.forecasts[i, 0]), ref[(lab, f"f{i}")]), i
+    assert _close(m.predict(X[0]), ref[(lab, "pred0")])
+    # predicting a training row reproduces its fitted value
+    assert abs(m.predict(X[3]) - float(m.forecasts[3, 0])) < 1e-10
+    with pytest.raises(ValueError):
+        m.predict(X[0, :-1])
+    with pytest.raises(ValueError):
+        to.pls_closed_form(y[:-1], X)

@@ -204,6 +204,81 @@ def forecast3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
     return estimate3prf(y, X, Z, procedure, **kw).forecasts
 
 
+@dataclass
+class Pls3prfModel:
+    """Pls3prfModel (Tprf3.scala:299-339): the fitted PLS-variant 3PRF with the column mean / scale it normalised X
+    by, so `predict` takes a raw row."""
+    phi: Mat          # N x 1  pass-1 loadings
+    sigma: Mat        # T x 1  pass-2 factor scores
+    beta: Mat         # 2 x 1  pass-3 [intercept, slope]
+    forecasts: Mat    # T x 1
+    colMean: Mat      # 1 x N  column means of the scaled X
+    colStd: Mat       # 1 x N  column std of the raw X
+    rSquared: float
+
+    def __post_init__(self):
+        self._w = self.phi.T / self.colStd                      # 1 x N: phi_j / std_j
+        self._shift = float((self.colMean @ self.phi)[0, 0])    # sum_j mean_j phi_j
+        self._phi_ss = float((self.phi * self.phi).sum())
+        b = self.beta.to_numpy()
+        self._b0, self._b1 = float(b[0, 0]), float(b[1, 0])
+
+    def predictAll(self, rows) -> Mat:
+        """Forecast for each raw predictor row (Tprf3.scala:335-339): sigma_new = (row/std - mean).phi / phi'phi,
+        yhat = b0 + b1 sigma_new; `rows` is a k x N device matrix (or anything Mat.from_numpy takes)."""
+        r = rows if isinstance(rows, Mat) else Mat.from_numpy(np.asarray(rows, dtype=np.float64).reshape(-1, self.phi.rows))
+        if r.cols != self.phi.rows:
+            raise ValueError(f"row length {r.cols} != {self.phi.rows} predictors")
+        return ((r @ self._w.T) - self._shift) * (self._b1 / self._phi_ss) + self._b0
+
+    def predict(self, row) -> float:
+        """Forecast for one raw (un-normalised) predictor row (Tprf3.scala:325-333)."""
+        a = np.asarray(row, dtype=np.float64).reshape(1, -1) if not isinstance(row, Mat) else row
+        n = a.cols if isinstance(a, Mat) else a.shape[1]
+        if n != self.phi.rows:
+            raise ValueError(f"row length {n} != {self.phi.rows} predictors")
+        return float(self.predictAll(a)[0, 0])
+
+
+def plsClosedForm(y: Mat, X: Mat) -> Pls3prfModel:
+    """Tprf3.plsClosedForm (Tprf3.scala:360-390): the 3PRF with one automatic proxy (= y) and no intercept in passes
+    1 and 2, which coincides with one-component PLS-1.  Device work: one fused sweep with Z = y (its pass-1 slopes
+    are cov(x_j, y) / ssy_centred; the PLS loading is the same cross product over y'y), one column-mean pass and
+    one T x N by N x 1 product for the factor scores; no T x N temporary is formed."""
+    if X.rows != y.rows:
+        raise ValueError(f"X has {X.rows} rows but y has {y.rows}")
+    if X.isnan().any() or y.isnan().any():
+        raise ValueError("plsClosedForm requires NaN-free input; use estimate3prf(pls = true) for gappy data")
+    T = X.rows
+    fit = _fit(L.TPRF_ITER, y, X, y)
+    col_std = fit.xstd                                            # stdCols(X): 1 x N
+    col_mean = X.mean(0) / col_std                                # nanMeanCols(X / colStd)
+    yc = y - y.mean()
+    yss = (y * y).sum()
+    phi = fit.phi * ((yc * yc).sum() / yss)                       # Xc'y / y'y (Xc is column-centred: Xc'y = Xc'(y - ybar))
+    phi_ss = (phi * phi).sum()
+    w = phi / col_std.T                                           # N x 1
+    sigma = ((X @ w) - float((col_mean @ phi)[0, 0])) / phi_ss    # Xc phi / phi'phi
+    xaug = MatD.hstack(MatD.ones(T, 1), sigma)
+    beta = (xaug.T @ xaug).inverse() @ (xaug.T @ y)
+    forecasts = xaug @ beta
+    resid = y - forecasts
+    ssy = (yc * yc).sum()
+    rsq = 0.0 if ssy == 0.0 else 1.0 - (resid * resid).sum() / ssy
+    return Pls3prfModel(phi, sigma, beta, forecasts, col_mean, col_std, rsq)
+
+
+def pls1Fit(x, y) -> Pls3prfModel:
+    """Tprf3.pls1Fit (Tprf3.scala:392-401): plsClosedForm from host arrays, `x` row-major T x N."""
+    xa = np.asarray(x, dtype=np.float64)
+    ya = np.asarray(y, dtype=np.float64).reshape(-1)
+    if xa.size == 0:
+        raise ValueError("x is empty")
+    if xa.shape[0] != ya.size:
+        raise ValueError(f"x has {xa.shape[0]} rows but y has {ya.size}")
+    return plsClosedForm(Mat.from_numpy(ya.reshape(-1, 1)), Mat.from_numpy(xa))
+
+
 TPRF_PATH_AUTO, TPRF_PATH_TWO_SWEEP, TPRF_PATH_FUSED, TPRF_PATH_GRID = 0, 1, 2, 3
 
 
