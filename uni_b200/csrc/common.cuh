@@ -121,29 +121,49 @@ __device__ __forceinline__ i64 total_key(double x) {
 }
 __device__ __forceinline__ i64 total_key(float x) { return total_key((double)x); }
 
-// exp(x) in ~20 FP64 issue slots (libdevice's exp costs about twice that, which makes FP64
-// sigmoid / softmax compute- instead of HBM-bound): x = k ln2 + r, |r| <= ln2/2, degree-13
-// Taylor/Horner (truncation 4e-18), 2^k applied to the exponent field.  Max error < 2 ulp on
-// [-700, 700]; anything outside (and NaN) takes libdevice's exp.
+// exp(x) in 18 FP64 instructions (libdevice's exp: about 40): x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor / Horner
+// (truncation 4e-18), 2^k applied to the exponent field.  Max error < 2 ulp on [-700, 700]; anything outside (and NaN)
+// takes libdevice's exp.
+// The coefficients live in CONSTANT memory on purpose: written as literals, ptxas materialises each 64-bit immediate
+// with two UMOVs in front of its DFMA, and the sigmoid / softmax kernels -- 85 issued instructions per element, two
+// thirds of them moves -- were bound by instruction issue (81 % issue-active, FP64 pipe 40 %; profiles/
+// r1_sigmoid_softmax0_ncu_raw.csv), not by HBM.  From the constant bank each DFMA takes its coefficient as an operand.
+__constant__ double k_expc[16] = {
+    1.4426950408889634074,       // 0: 1/ln2
+    -6.93147180369123816490e-01, // 1: -ln2 high part (32 significant bits: t * hi is exact)
+    -1.90821492927058770002e-10, // 2: -ln2 low part
+    1.6059043836821613e-10,      // 3: 1/13!
+    2.08767569878681e-09,        // 4: 1/12!
+    2.505210838544172e-08,       // 5: 1/11!
+    2.755731922398589e-07,       // 6: 1/10!
+    2.7557319223985893e-06,      // 7: 1/9!
+    2.48015873015873e-05,        // 8: 1/8!
+    1.984126984126984e-04,       // 9: 1/7!
+    1.388888888888889e-03,       // 10: 1/6!
+    8.333333333333333e-03,       // 11: 1/5!
+    4.1666666666666664e-02,      // 12: 1/4!
+    1.6666666666666666e-01,      // 13: 1/3!
+    6755399441055744.0,          // 14: 1.5 * 2^52: low mantissa bits of (v + MAGIC) = rint(v)
+    0.0};
 __device__ __forceinline__ double fast_exp(double x) {
   if (!(fabs(x) <= 700.0)) return exp(x);
-  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: low mantissa bits of (v + MAGIC) = rint(v)
-  double tt = fma(x, 1.4426950408889634074, MAGIC);
+  const double* __restrict__ c = k_expc;
+  double tt = fma(x, c[0], c[14]);
   int k = __double2loint(tt);
-  double t = tt - MAGIC;
-  double r = fma(t, -6.93147180369123816490e-01, x);
-  r = fma(t, -1.90821492927058770002e-10, r);
-  double p = 1.6059043836821613e-10;          // 1/13!
-  p = fma(p, r, 2.08767569878681e-09);        // 1/12!
-  p = fma(p, r, 2.505210838544172e-08);       // 1/11!
-  p = fma(p, r, 2.755731922398589e-07);       // 1/10!
-  p = fma(p, r, 2.7557319223985893e-06);      // 1/9!
-  p = fma(p, r, 2.48015873015873e-05);        // 1/8!
-  p = fma(p, r, 1.984126984126984e-04);       // 1/7!
-  p = fma(p, r, 1.388888888888889e-03);       // 1/6!
-  p = fma(p, r, 8.333333333333333e-03);       // 1/5!
-  p = fma(p, r, 4.1666666666666664e-02);      // 1/4!
-  p = fma(p, r, 1.6666666666666666e-01);      // 1/3!
+  double t = tt - c[14];
+  double r = fma(t, c[1], x);
+  r = fma(t, c[2], r);
+  double p = c[3];
+  p = fma(p, r, c[4]);
+  p = fma(p, r, c[5]);
+  p = fma(p, r, c[6]);
+  p = fma(p, r, c[7]);
+  p = fma(p, r, c[8]);
+  p = fma(p, r, c[9]);
+  p = fma(p, r, c[10]);
+  p = fma(p, r, c[11]);
+  p = fma(p, r, c[12]);
+  p = fma(p, r, c[13]);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
