@@ -277,7 +277,8 @@ def run_ours(args, rank, world, local_rank):
             t = torch.tensor(list(b), dtype=torch.uint8, device="cuda")
             dist.broadcast(t, src=0)
             return bytes(t.cpu().tolist())
-        init_comm(rank, world, bcast)
+        if not args.debug_no_comm:
+            init_comm(rank, world, bcast)
 
     def barrier():
         u.sync()
@@ -427,6 +428,11 @@ def run_ours(args, rank, world, local_rank):
                 extras["matmul_sweep"] = matmul_sweep(u, (1024, 2048) if args.small else (1024, 2048, 4096, 8192))
             except Exception as ex:
                 extras["ops_error"] = str(ex)[:300]
+    exchange = "none (1 GPU)"
+    if world > 1 and not args.debug_no_comm:
+        p2p_ = C.c_int32(0)
+        check(lib.um_comm_transport(C.byref(p2p_)))
+        exchange = "peer memory (CUDA IPC over NVLink), one kernel" if p2p_.value else "NCCL all-gather + rank-order sum"
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -435,16 +441,19 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": "3PRF closed-form fit, T=8192 x N=262144 x L=8 FP64 panel (BASELINE config 4), "
                                    "sharded by predictor column", "T": T, "N": N, "L": Lp, "cols_per_gpu": Nl,
                        "l2": "inputs (16 GiB / n_gpus per rank) are larger than L2; no flush needed",
-                       "parallelism": f"column-shard x{world}, one packed all-reduce per fit"},
+                       "parallelism": f"column-shard x{world}, one packed all-reduce per fit", "exchange": exchange},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "wall_ms_per_step": wall_ms / args.steps, "r_squared": r.rSquared,
         }
         line.update(extras)
+        if args.debug_no_comm:
+            line["DIAGNOSTIC"] = "--debug-no-comm: shards fitted without the all-reduce; not a benchmark value"
         print(json.dumps(line), flush=True)
     if dist is not None:
         from uni_b200.dist import destroy_comm
         barrier()
-        destroy_comm()
+        if not args.debug_no_comm:
+            destroy_comm()
         dist.destroy_process_group()
 
 
@@ -457,6 +466,8 @@ def main():
     ap.add_argument("--skip-ops", action="store_true", help="skip the config-2/3 extras (MatD ops, matmul sweep)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-streamed end-to-end leg (ncu runs)")
     ap.add_argument("--small", action="store_true", help="debug: T=2048 x N=16384 panel")
+    ap.add_argument("--debug-no-comm", action="store_true",
+                    help="diagnostic only (results are per-shard, NOT a fit of the panel): N ranks fit their shards without the all-reduce")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -257,6 +257,9 @@ int32_t um_comm_unique_id(uint8_t out[128]);
 int32_t um_comm_init(int32_t rank, int32_t world, const uint8_t id[128]);
 int32_t um_comm_destroy(void);
 int32_t um_comm_info(int32_t* rank, int32_t* world);
+/* *p2p = 1 when the exchange step runs over mapped peer memory (CUDA IPC, NVLink / NVSwitch), 0 when it runs over
+ * NCCL (peer mapping unavailable, or UM_COMM_P2P=0 in the environment at um_comm_init). */
+int32_t um_comm_transport(int32_t* p2p);
 /* deterministic sum: all-gather of each rank's block + fixed rank-order add */
 int32_t um_comm_allreduce_sum_f64(double* buf, int64_t count);
 int32_t um_comm_barrier(void);

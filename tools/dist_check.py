@@ -27,6 +27,10 @@ def bcast(b):
 
 
 init_comm(rank, world, bcast)
+import ctypes as _C
+from uni_b200._lib import lib as _lib
+_p2p = _C.c_int32(0); _lib.um_comm_transport(_C.byref(_p2p))
+print(f"rank {rank}: exchange transport = {'peer memory (CUDA IPC)' if _p2p.value else 'NCCL'}", flush=True)
 ok = True
 for (T, N, L) in ((512, 4096, 4), (300, 1000, 3), (1024, 8192, 8)):
     rng = np.random.default_rng(7)
@@ -50,6 +54,27 @@ for (T, N, L) in ((512, 4096, 4), (300, 1000, 3), (1024, 8192, 8)):
     ok = ok and good
     print(f"rank {rank} T={T} N={N} L={L} shard=[{c0},{c1}) closed {e1:.3g} iter {e2:.3g} alpha {e3:.3g} phi {e4:.3g} "
           f"(x tolerance)  ranks bit-identical: {same}  R2 {c.rSquared:.6g} vs {oc.r_squared:.6g}", flush=True)
+# many back-to-back exchanges: slot parity reuse, counters, and the per-exchange cost
+import time
+buf = u.MatD.randn(1, 73809, seed=rank)
+ref_sum = None
+for trial in range(3):
+    parts = [u.MatD.randn(1, 73809, seed=r).to_numpy() for r in range(world)]
+    want = parts[0].copy()
+    for r in range(1, world):
+        want = want + parts[r]
+    b2 = buf.copy()
+    _lib.um_comm_allreduce_sum_f64(_C.c_void_p(b2._buf.ptr), 73809)
+    same = np.array_equal(b2.to_numpy(), want)
+    ok = ok and same
+    if not same:
+        print(f"rank {rank}: all-reduce trial {trial} WRONG (max diff {np.max(np.abs(b2.to_numpy() - want))})", flush=True)
+u.sync(); dist.barrier(); t0 = time.perf_counter()
+b3 = buf.copy()
+for _ in range(200):
+    _lib.um_comm_allreduce_sum_f64(_C.c_void_p(b3._buf.ptr), 73809)
+u.sync()
+print(f"rank {rank}: 200 exchanges of 73809 doubles: {(time.perf_counter() - t0) / 200 * 1e3:.4f} ms each", flush=True)
 dist.barrier()
 destroy_comm()
 dist.destroy_process_group()

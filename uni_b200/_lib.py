@@ -147,6 +147,7 @@ SIGNATURES = {
     "um_comm_init": (_i32, [_i32, _i32, C.POINTER(C.c_uint8)]),
     "um_comm_destroy": (_i32, []),
     "um_comm_info": (_i32, [C.POINTER(_i32), C.POINTER(_i32)]),
+    "um_comm_transport": (_i32, [C.POINTER(_i32)]),
     "um_comm_allreduce_sum_f64": (_i32, [_vp, _i64]),
     "um_comm_barrier": (_i32, []),
 }

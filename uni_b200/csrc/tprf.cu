@@ -31,6 +31,7 @@
 namespace um {
 
 int comm_allreduce_sum_f64_impl(double* buf, i64 count);  // comm.cu
+int comm_check_error();                                     // comm.cu: did a bounded peer wait give up? (call after a sync)
 bool comm_active();
 int comm_world();
 
@@ -1459,7 +1460,7 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
   UM_CUDA(cudaStreamSynchronize(ctx()->stream));
   out->r_squared = res[0];
   out->singular = res[1] != 0.0;
-  return UM_OK;
+  return comm_active() ? comm_check_error() : UM_OK;
 }
 
 int32_t um_tprf_fit_batched(int32_t mode, const double* y, const double* X, const double* Z, int64_t T, int64_t N, int64_t L,
@@ -1566,7 +1567,7 @@ int32_t um_tprf_fit_host(int32_t mode, const double* y, const double* X, int64_t
   UM_CUDA(cudaMemcpyAsync(res, reinterpret_cast<double*>(ws + p.o_par) + 88, 16, cudaMemcpyDeviceToHost, st));
   UM_CUDA(cudaStreamSynchronize(st));
   if (r_squared) *r_squared = res[0];
-  return UM_OK;
+  return comm_active() ? comm_check_error() : UM_OK;
 }
 
 }  // extern "C"

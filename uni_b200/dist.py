@@ -2,8 +2,9 @@
 
 One process per GPU.  X is partitioned by predictor column into contiguous blocks; y and Z are
 replicated.  The only exchange is one packed sum of T*(8+1)+81 doubles per fit, done inside
-libunimat (NCCL all-gather over NVLink + fixed rank-order add).  torch.distributed is used only
-to hand the NCCL unique id from rank 0 to the other ranks.
+libunimat: an all-gather into mapped peer memory (CUDA IPC over NVLink) + fixed rank-order add in one
+kernel, NCCL all-gather as the fallback transport.  torch.distributed is used only to hand the NCCL
+unique id from rank 0 to the other ranks.
 """
 from __future__ import annotations
 
@@ -42,3 +43,10 @@ def init_comm(rank: int, world: int, broadcast_bytes: Callable[[bytes], bytes]) 
 
 def destroy_comm() -> None:
     check(lib.um_comm_destroy())
+
+
+def transport() -> str:
+    """Which transport the exchange step uses on this rank: "p2p" (mapped peer memory) or "nccl"."""
+    p = C.c_int32(0)
+    check(lib.um_comm_transport(C.byref(p)))
+    return "p2p" if p.value else "nccl"
