@@ -403,3 +403,24 @@ def test_pls_wide_panel_vs_oracle(u):
     assert close(m.forecasts.to_numpy(), o.forecasts) and close(m.rSquared, o.r_squared)
     assert close(m.beta.to_numpy(), o.beta) and close(m.phi.to_numpy(), o.phi)
     assert close(m.predict(X[11] * 1.01), o.predict(X[11] * 1.01))
+
+
+# ---------------------------------------------------------------- multi-GPU (runs when the box has >= 2 GPUs)
+def test_sharded_fit_across_ranks(u):
+    """tools/dist_check.py under torchrun, one rank per GPU: sharded closed-form / three-pass fits vs the oracle on the
+    full panel, bit-identical forecasts on every rank, the peer-memory exchange against a host-side sum."""
+    import subprocess
+    import sys
+    n = u.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs (the 1-GPU path is covered above; host-side sharding logic in tests/test_dist_cpu.py)")
+    world = 2 if n < 4 else 4
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for env_p2p in ("1", "0"):
+        env = dict(os.environ, UM_COMM_P2P=env_p2p)
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "dist_check.py")],
+                           cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert r.stdout.count("DIST_CHECK PASS") == world
+        assert ("peer memory" in r.stdout) == (env_p2p == "1") or "NCCL" in r.stdout
