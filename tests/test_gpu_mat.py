@@ -354,7 +354,8 @@ def test_unary_and_activations(u, shape):
     np.testing.assert_allclose(m.T.sigmoid().to_numpy(), mo.sigmoid(o.T).to2d(), rtol=1e-12, atol=0, equal_nan=True)
 
 
-@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (5, 3), (64, 64), (65, 63), (300, 400), (7, 2049), (3, 9000), (2, 20000), (2, 70000), (4097, 3)])
+@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (5, 3), (64, 64), (65, 63), (300, 400), (7, 2049), (3, 9000), (2, 20000), (2, 70000), (4097, 3),
+                                   (5, 16384), (3, 32768), (3, 32766), (2, 16385)])   # rows that exactly fill one / two CTAs of the on-chip kernel, and near misses
 @pytest.mark.parametrize("axis", [0, 1])
 def test_softmax(u, shape, axis):
     rng = np.random.default_rng(3)

@@ -866,7 +866,9 @@ __device__ __forceinline__ double ld_peer_f64(const double* local_smem, unsigned
   return v;
 }
 
-template <int CS>
+// FULL = every chunk of every thread is inside the row (n_red == CS * 16384): the per-chunk bounds checks and their 64-bit
+// index arithmetic (a third of the issued instructions, ncu source page) drop out and addresses become base + immediate.
+template <int CS, bool FULL>
 __global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const double* __restrict__ p, i64 s_lane, i64 n_lane, i64 n_red,
                                                                        double* __restrict__ out, i64 o_lane) {
   // Persistent: cluster k takes rows k, k + #clusters, ...  While a thread normalises and stores chunk c of
@@ -882,11 +884,11 @@ __global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const doub
   const i64 nclusters = gridDim.x / CS;
   const i64 nv = n_red >> 1;                       // whole double2 vectors of the row
   const i64 v0 = (i64)rank * OC_CTA_VECS;          // first vector owned by this CTA
-  const bool odd_tail = (n_red & 1) && t == 0 && rank == 0;
+  const bool odd_tail = !FULL && (n_red & 1) && t == 0 && rank == 0;
 
   auto issue_smem = [&](const double* base, int c) {
     const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
-    if (v < nv) {
+    if (FULL || v < nv) {
       unsigned sa = (unsigned)__cvta_generic_to_shared(&sx[c * OC_THREADS + t]);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(base + 2 * v) : "memory");
     }
@@ -907,7 +909,7 @@ __global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const doub
 #pragma unroll
     for (int c = 0; c < OC_REG; ++c) {
       const i64 v = v0 + (i64)c * OC_THREADS + t;
-      rn[c] = v < nv ? *reinterpret_cast<const double2*>(base + 2 * v) : make_double2(-INFINITY, -INFINITY);
+      rn[c] = (FULL || v < nv) ? *reinterpret_cast<const double2*>(base + 2 * v) : make_double2(-INFINITY, -INFINITY);
     }
     xtn = odd_tail ? base[n_red - 1] : -INFINITY;
   }
@@ -926,7 +928,7 @@ __global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const doub
 #pragma unroll
     for (int c = 0; c < OC_SMEM_CHUNKS; ++c) {
       const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
-      if (v < nv) {
+      if (FULL || v < nv) {
         double2 x = sx[c * OC_THREADS + t];
         mx = fmax(mx, fmax(x.x, x.y));
       }
@@ -951,7 +953,7 @@ __global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const doub
 #pragma unroll
     for (int c = 0; c < OC_REG; ++c) {
       const i64 v = v0 + (i64)c * OC_THREADS + t;
-      if (v < nv) {
+      if (FULL || v < nv) {
         r[c].x = fast_exp(r[c].x - mx);
         r[c].y = fast_exp(r[c].y - mx);
         s += r[c].x + r[c].y;
@@ -961,7 +963,7 @@ __global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const doub
 #pragma unroll
     for (int c = 0; c < OC_SMEM_CHUNKS; ++c) {
       const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
-      if (v < nv) {
+      if (FULL || v < nv) {
         double2 x = sx[c * OC_THREADS + t];
         x.x = fast_exp(x.x - mx);
         x.y = fast_exp(x.y - mx);
@@ -990,14 +992,14 @@ __global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const doub
 #pragma unroll
     for (int c = 0; c < OC_REG; ++c) {
       const i64 v = v0 + (i64)c * OC_THREADS + t;
-      if (v < nv) __stcs(reinterpret_cast<double2*>(obase + 2 * v), make_double2(r[c].x * inv, r[c].y * inv));
-      rn[c] = (have_next && v < nv) ? *reinterpret_cast<const double2*>(nbase + 2 * v) : make_double2(-INFINITY, -INFINITY);
+      if (FULL || v < nv) __stcs(reinterpret_cast<double2*>(obase + 2 * v), make_double2(r[c].x * inv, r[c].y * inv));
+      rn[c] = (have_next && (FULL || v < nv)) ? *reinterpret_cast<const double2*>(nbase + 2 * v) : make_double2(-INFINITY, -INFINITY);
     }
     xtn = (have_next && odd_tail) ? nbase[n_red - 1] : -INFINITY;
 #pragma unroll
     for (int c = 0; c < OC_SMEM_CHUNKS; ++c) {
       const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
-      if (v < nv) {
+      if (FULL || v < nv) {
         double2 x = sx[c * OC_THREADS + t];
         __stcs(reinterpret_cast<double2*>(obase + 2 * v), make_double2(x.x * inv, x.y * inv));
       }
@@ -1011,11 +1013,11 @@ __global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const doub
   if (CS > 1) cluster_sync_all();   // the peer may still be reading sm_x
 }
 
-template <int CS>
-static int launch_row_onchip(const double* p, i64 s_lane, i64 n_lane, i64 n_red, double* out, i64 o_lane) {
+template <int CS, bool FULL>
+static int launch_row_onchip_impl(const double* p, i64 s_lane, i64 n_lane, i64 n_red, double* out, i64 o_lane) {
   static bool attr = false;
   if (!attr) {
-    UM_CUDA(cudaFuncSetAttribute(k_softmax_row_onchip<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, OC_SMEM_BYTES));
+    UM_CUDA(cudaFuncSetAttribute(k_softmax_row_onchip<CS, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, OC_SMEM_BYTES));
     attr = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -1032,8 +1034,14 @@ static int launch_row_onchip(const double* p, i64 s_lane, i64 n_lane, i64 n_red,
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  UM_CUDA(cudaLaunchKernelEx(&cfg, k_softmax_row_onchip<CS>, p, s_lane, n_lane, n_red, out, o_lane));
+  UM_CUDA(cudaLaunchKernelEx(&cfg, k_softmax_row_onchip<CS, FULL>, p, s_lane, n_lane, n_red, out, o_lane));
   return UM_OK;
+}
+
+template <int CS>
+static int launch_row_onchip(const double* p, i64 s_lane, i64 n_lane, i64 n_red, double* out, i64 o_lane) {
+  return n_red == (i64)CS * OC_CTA_VECS * 2 ? launch_row_onchip_impl<CS, true>(p, s_lane, n_lane, n_red, out, o_lane)
+                                            : launch_row_onchip_impl<CS, false>(p, s_lane, n_lane, n_red, out, o_lane);
 }
 
 template <class T, int VW>
