@@ -312,7 +312,7 @@ def test_scala_oos_rows(u, golden_dir, case):
         r = u.estimate3prf(dy, dX, dZ, proc, **kw)
         lab = f"{case}/{tag}"
         assert close(r.rSquared, ref[(lab, "r2")]), lab
-        assert close(r.enc, ref[(lab, "enc")]), lab
+        assert close(r.encnew, ref[(lab, "enc")]), lab
         assert close(r.forecasts.to_numpy()[:, 0], [ref[(lab, f"f{i}")] for i in range(T)]), lab
         assert close(r.rollfore.to_numpy()[:, 0], [ref[(lab, f"roll{i}")] for i in range(T)]), lab
         assert close(r.residuals.to_numpy(), y - r.forecasts.to_numpy())
@@ -338,7 +338,7 @@ def test_python_reference_oos_vectors(u, golden_dir):
         if proc != "IS Full":
             assert close(r.rollfore.to_numpy(), o.extra["rollfore"]), name
         if proc == "OOS Recursive":
-            assert close(r.enc, float(g["enc"]), rtol=max(tol, 1e-8)), name
+            assert close(r.encnew, float(g["enc"]), rtol=max(tol, 1e-8)), name
         n += 1
     assert n >= 10
 
@@ -351,7 +351,7 @@ def test_oos_windows_on_a_wide_panel(u):
     dy, dX, dZ = devs(u, y, X, Z)
     r = u.estimate3prf(dy, dX, dZ, "OOS Recursive", mintrain=(60, 0))
     o = to.estimate3prf(y, X, Z, "OOS Recursive", mintrain=(60, 0))
-    assert close(r.forecasts.to_numpy(), o.forecasts) and close(r.rSquared, o.r_squared) and close(r.enc, o.extra["enc"], rtol=1e-8)
+    assert close(r.forecasts.to_numpy(), o.forecasts) and close(r.rSquared, o.r_squared) and close(r.encnew, o.extra["enc"], rtol=1e-8)
     r = u.estimate3prf(dy, dX, dZ, "OOS Rolling", rollwin=(40, 20, 1))
     o = to.estimate3prf(y, X, Z, "OOS Rolling", rollwin=(40, 20, 1))
     assert close(r.forecasts.to_numpy(), o.forecasts) and close(r.rSquared, o.r_squared)

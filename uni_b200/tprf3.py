@@ -33,7 +33,11 @@ class Tprf3Result:
     xstd: Optional[Mat] = None      # 1 x N  column sample std used to normalise X
     singular: bool = False
     rollfore: Optional[Mat] = None  # T x 1  mean of each window's y (OOS procedures, Tprf3.scala:1145)
-    enc: float = float("nan")       # ENC-NEW statistic, OOS Recursive only (Tprf3.scala:854-860,1235-1238)
+    encnew: float = float("nan")    # ENC-NEW statistic, OOS Recursive only (Tprf3.scala:854-860,1235-1238)
+
+    @property
+    def y_hat(self) -> Mat:         # TprfResult alias (Tprf3.scala:93-95)
+        return self.forecasts
 
 
 def _fit(mode: int, y: Mat, X: Mat, Z: Mat, n_total: int = 0, want_all: bool = True) -> Tprf3Result:
@@ -126,7 +130,8 @@ def _drop_rows(m: Mat, lo: int, hi: int) -> Mat:
 
 
 def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full", window: Tuple[int, int] = (0, 1),
-                 mintrain: Tuple[int, int] = (-1, 0), rollwin: Tuple[int, int, int] = (30, 20, 0), n_total: int = 0) -> Tprf3Result:
+                 mintrain: Tuple[int, int] = (-1, 0), rollwin: Tuple[int, int, int] = (30, 20, 0), pls: bool = False,
+                 computeAvar: bool = False, n_total: int = 0) -> Tprf3Result:
     """Tprf3.estimate3prf (Tprf3.scala:1056-1250) on the device, NaN-free input: `Z` a proxy matrix (Right) or an
     int L (Left: automatic proxies); procedures "IS Full", "OOS Recursive", "OOS Cross Val", "OOS Rolling" with the
     reference's `window`, `mintrain`, `rollwin` meaning.  Every window is one fused sweep over its kept rows plus
@@ -135,6 +140,9 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
     if procedure not in _PROCEDURES:
         raise ValueError(f"Unknown procedure '{procedure}'. Choose: 'IS Full', 'OOS Recursive', "
                          "'OOS Cross Val', 'OOS Rolling'")
+    if pls or computeAvar:
+        raise NotImplementedError("pls = true (per-column nanOls passes, Tprf3.scala:986-1050; use plsClosedForm) and computeAvar "
+                                  "(N x N / T x T by definition, Tprf3.scala:1253-1277) are not on the device path")
     auto = not isinstance(Z, Mat)
     if procedure == "IS Full" and not auto:
         return _fit(L.TPRF_IS_FULL, y, X, Z, n_total)
@@ -196,7 +204,7 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
         if procedure == "OOS Recursive":                             # encnew(rollfore[loc], residuals[loc]), :854-860
             with np.errstate(all="ignore"):
                 enc = float(np.float64(e.cols) * np.float64((rl * rl - rl * e).sum()) / np.float64(see))
-    return Tprf3Result(forecasts, residuals, r2, rollfore=rollfore, enc=enc)
+    return Tprf3Result(forecasts, residuals, r2, rollfore=rollfore, encnew=enc)
 
 
 def forecast3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full", **kw) -> Mat:
