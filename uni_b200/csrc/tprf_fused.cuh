@@ -41,7 +41,7 @@ constexpr int RMAX = 512;                    // rows per piece (per CTA of the c
 constexpr int SLOT_BYTES = RMAX * CW * 8;    // 65536
 constexpr int BOX_ROWS = 128;
 constexpr int NAW = 4;                       // A-warps (= B-warps): one of each per SM sub-partition
-constexpr int NTHREADS = (2 * NAW + 3) * 32; // + TMA producer, finaliser, reducer
+constexpr int NTHREADS = (2 * NAW + 4) * 32; // + TMA producer, finaliser, reducer, second finaliser (small clusters)
 constexpr int NSTAT = 10;                    // per column: s1, s2, q[8]
 constexpr int NREC = 10;                     // per column record: V[8], 1/sd, pad
 constexpr int GMAX = 16;                     // largest cluster (non-portable size)
@@ -463,8 +463,13 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 2 * NAW + 1) {
+  } else if ((warp == 2 * NAW + 1 || warp == 2 * NAW + 3) && (warp == 2 * NAW + 1 || owned > 4)) {
     // ================= finaliser: owner of columns {oc*G + rank} =================
+    // Clusters of 1 or 2 CTAs own 16 / 8 columns per CTA = 4 / 2 serial rounds per piece, and this latency-bound
+    // warp then paces the whole sweep (profiles/r1_fused_timeline_g1.log): a second finaliser warp takes every
+    // other round.  Larger clusters (one round per piece) run the first one alone; the second stays idle.
+    const int fw = warp == 2 * NAW + 3 ? 1 : 0;
+    const int nfw = owned > 4 ? 2 : 1;
     // 8 lanes (l = value index) per lane group; `sub` lane groups share one column and split its G
     // source ranks (<= 4 each); up to 4 columns per round
     const int lg = lane >> 3, l = lane & 7;
@@ -488,7 +493,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
       const int b = ch / g.cpp, cidx = ch % g.cpp;
       for (i64 tile = g.tile_lo + cidx; tile < g.ntile; tile += g.cpp, ++it) {
         const int s = it % NXR;  // ring entry of the exchange buffers and barriers
-        if (lane == 0) {
+        if (lane == 0 && fw == 0) {
           mb_expect_tx(bar_vrdy(s), CW * 9 * 8);
           mb_expect_tx(bar_stat(s), STAT_SLOT * 8);
         }
@@ -522,7 +527,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
           }
           mun_pre = (k0 + dm) * inv_pre;
         }
-        for (int oc0 = 0; oc0 < owned; oc0 += cpr) {
+        for (int oc0 = fw * cpr; oc0 < owned; oc0 += cpr * nfw) {
           const int oc = oc0 + cs;              // < owned always (owned is a multiple of cpr)
           const int col = oc * G + rank;
           double S, SS, q;
@@ -629,7 +634,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
           double x3 = __shfl_sync(0xffffffffu, vals[i], 24 + l);
           vals[i] = ((x0 + x1) + x2) + x3;
         }
-        if (lg == 0) {
+        if (lg == 0 && fw == 0) {
           double* bp = g.blockpart + ((i64)(b * g.cpp_out + g.cidx_off + cidx) * G + rank) * NSMALL;
           bp[l] = vals[0];
 #pragma unroll
@@ -642,7 +647,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         for (int c = 0; c < 8; ++c) a_sww[c] = 0.0;
       }
     }
-  } else {
+  } else if (warp == 2 * NAW + 2) {
     // ================= reducer: lane partials in `scratch` -> CTA partial -> owner CTA =================
     // lane handles 5 of the 160 (column, statistic) values: value 0 is s1 / s2 of column lane >> 1 (4 row
     // phases x 4 A-warps), values 1..4 are q[column (e >> 3)][l = e & 7], e = lane + 32 (j - 1) (4 A-warps)
