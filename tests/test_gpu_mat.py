@@ -264,6 +264,13 @@ def test_mask_select_large_is_stable(u):
     c0 = m.cumsum(0).to_numpy()
     assert np.array_equal(c0, np.cumsum(a, axis=0))
     assert np.array_equal(m.cummax(1).to_numpy(), np.maximum.accumulate(a, axis=1))
+    # > 8192 blocks of 4096 elements: the block-count scan takes several rounds with a carry
+    big = u.MatD.randn(7000, 6000, seed=11)
+    ab = big.to_numpy()
+    for thr in (1.5, -0.3):
+        selb = big[big.gt(thr)]
+        wantb = ab[ab > thr]
+        assert selb.shape == (1, wantb.size) and np.array_equal(selb.to_numpy().reshape(-1), wantb)
 
 
 # ---------------------------------------------------------------- elementwise / broadcasting / views

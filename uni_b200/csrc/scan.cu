@@ -335,29 +335,54 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_count(In<uint8_t> m, i64 co
   }
 }
 
-// exclusive scan of the block counts in place; counts[nb] = total.  One block; integer sums are exact in any order.
+// exclusive scan of the block counts in place; counts[nb] = total.  One block (integer sums are exact in any order):
+// each thread folds 8 consecutive counts, warps scan with shuffles, one shared-memory step across the 32 warps; the
+// next 8192 counts are loaded before the current ones are scanned.
 __global__ void __launch_bounds__(1024) k_sel_scan(i64* __restrict__ counts, i64 nb) {
-  __shared__ i64 sm[1024];
-  __shared__ i64 carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (i64 b0 = 0; b0 < nb; b0 += 1024) {
-    const i64 b = b0 + threadIdx.x;
-    const i64 v = b < nb ? counts[b] : 0;
-    sm[threadIdx.x] = v;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-      i64 add = threadIdx.x >= d ? sm[threadIdx.x - d] : 0;
-      __syncthreads();
-      sm[threadIdx.x] += add;
-      __syncthreads();
+  constexpr int PER = 8;
+  __shared__ i64 wsum[32];
+  __shared__ i64 carry_s;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t == 0) carry_s = 0;
+  i64 v[PER], nxt[PER];
+  auto fetch = [&](i64* dst, i64 b0) {
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const i64 b = b0 + (i64)t * PER + k;
+      dst[k] = b < nb ? counts[b] : 0;
     }
-    if (b < nb) counts[b] = carry + sm[threadIdx.x] - v;
+  };
+  fetch(v, 0);
+  __syncthreads();
+  for (i64 b0 = 0; b0 < nb; b0 += 1024 * PER) {
+    fetch(nxt, b0 + 1024 * PER);
+    i64 tot = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) tot += v[k];
+    i64 inc = tot;                                   // inclusive scan of the thread totals inside the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const i64 o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) wsum[w] = inc;
     __syncthreads();
-    if (threadIdx.x == 1023) carry += sm[1023];
+    i64 wbase = 0;
+    for (int q = 0; q < w; ++q) wbase += wsum[q];
+    i64 run = carry_s + wbase + inc - tot;           // exclusive prefix of this thread's first count
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const i64 b = b0 + (i64)t * PER + k;
+      if (b < nb) counts[b] = run;
+      run += v[k];
+    }
     __syncthreads();
+    if (t == 1023) carry_s = run;                    // the last thread ends on the running total
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) v[k] = nxt[k];
   }
-  if (threadIdx.x == 0) counts[nb] = carry;
+  if (t == 0) counts[nb] = carry_s;
 }
 
 template <class T, bool FLAT_A, bool FLAT_M>
