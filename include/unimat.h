@@ -180,9 +180,9 @@ int32_t um_idx_axis(int32_t want_max, const um_view* a, int32_t axis, const um_v
  * cblas_dgemm (:3336), MatmulPure.multiply (MatmulPure.scala:78) and multiplyFloat (:3236). */
 int32_t um_matmul(const um_view* a, const um_view* b, const um_view* out);
 /* FP32 `*@` kernel choice (the reference's uni.mat.blas switch, Mat.scala:299-335, picks between a BLAS
- * sgemm and matmulPure in the same way): 0 = automatic (row-major, 16-byte aligned operands with
- * M,N % 128 == 0 and K % 32 == 0 run 3xTF32 on the tcgen05 tensor cores with FP32 promotion every
- * 128 k; everything else on the FFMA kernel), 1 = FFMA kernel only, 2 = tensor-core kernel or
+ * sgemm and matmulPure in the same way): 0 = automatic (row-major, 16-byte aligned operands whose
+ * pitches and N are multiples of 4, M*N*K >= 2^18, run 3xTF32 on the tcgen05 tensor cores with FP32
+ * promotion every 128 k, partial tiles zero-filled by TMA; everything else on the FFMA kernel), 1 = FFMA kernel only, 2 = tensor-core kernel or
  * UM_ERR_ARG.  Process-wide; for tests and profiling.  UM_MATF_TENSOR=0 in the environment makes
  * automatic mean 1. */
 int32_t um_matmul_set_f32_path(int32_t path);

@@ -465,7 +465,8 @@ def test_matf_ops(u):
     assert m.relu().dtype == 1 and np.array_equal(m.relu().to_numpy(), np.maximum(a, 0))
 
 
-MATF_MM_SHAPES = [(128, 32, 128), (128, 160, 256), (256, 512, 384), (384, 4096, 128), (1024, 1056, 512)]
+MATF_MM_SHAPES = [(128, 32, 128), (128, 160, 256), (256, 512, 384), (384, 4096, 128), (1024, 1056, 512),
+                  (200, 300, 132), (129, 1000, 128), (1000, 36, 64), (130, 132, 260), (1, 4096, 512)]   # partial tiles in M, N and K
 
 
 @pytest.mark.parametrize("mkn", MATF_MM_SHAPES)

@@ -317,13 +317,13 @@ extern "C" int32_t um_matmul(const um_view* a, const um_view* b, const um_view* 
   if (a->dtype == UM_F32) {
     In<float> A = in_of<float>(a), B = in_of<float>(b);
     float* pc = static_cast<float*>(out->data) + out->offset;
-    // row-major, aligned, tile-multiple operands: 3xTF32 on the tcgen05 tensor cores (matmul_tf32.cuh)
+    // row-major, 16-byte aligned operands: 3xTF32 on the tcgen05 tensor cores (matmul_tf32.cuh)
     static const bool tensor_ok = [] { const char* e = getenv("UM_MATF_TENSOR"); return !(e && e[0] == '0'); }();
     const int path = g_f32_path;
     if (path == 2 || (path == 0 && tensor_ok)) {
       int r = (A.cs == 1 && B.cs == 1) ? tf32::launch(A.p, A.rs, B.p, B.rs, pc, ldc, M, N, K) : -1;
       if (r != -1) return r;
-      if (path == 2) return fail(UM_ERR_ARG, "matmul: operands do not fit the tensor-core FP32 kernel (row-major, 16-byte aligned, M,N % 128, K % 32)");
+      if (path == 2) return fail(UM_ERR_ARG, "matmul: operands do not fit the tensor-core FP32 kernel (row-major, 16-byte aligned, pitches and N multiples of 4, M*N*K >= 2^18)");
     }
     dim3 grid((unsigned)((N + SG_BN - 1) / SG_BN), (unsigned)((M + SG_BM - 1) / SG_BM));
     k_sgemm<<<grid, 256, 0, ctx()->stream>>>(A, B, pc, ldc, M, N, K);

@@ -81,7 +81,7 @@ __device__ __forceinline__ void umma_commit(unsigned bar) {
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float* __restrict__ C, i64 ldc,
-               int kblocks) {
+               int kblocks, int M, int N) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const unsigned s0 = sa(smem);
@@ -248,10 +248,14 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ---- epilogue: the remaining chunks, then this thread's row of C ----
     while (promoted < nchunks) promote(promoted++);
     add_tmem(2 * BN);                  // the cross terms (complete: the last chunk's commit covers every MMA issued)
+    // edge tiles: TMA zero-filled what lies outside A and B, only the stores need the bounds (N % 4 == 0)
     const int row = m0 + 32 * q + lane;
-    float* crow = C + (i64)row * ldc + n0;
+    if (row < M) {
+      float* crow = C + (i64)row * ldc + n0;
 #pragma unroll
-    for (int j = 0; j < BN; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      for (int j = 0; j < BN; j += 4)
+        if (n0 + j < N) *reinterpret_cast<float4*>(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -277,9 +281,10 @@ inline EncodeTiledFn encode_fn() {
 
 // returns UM_OK if launched, -1 if the shape / layout is not eligible (caller falls back to the FFMA kernel)
 inline int launch(const float* A, i64 lda, const float* B, i64 ldb, float* C, i64 ldc, i64 M, i64 N, i64 K) {
-  if (M % BM || N % BN || K % BK || M <= 0 || N <= 0 || K <= 0) return -1;
+  // any M and K (partial tiles are zero-filled by TMA), N a multiple of 4 (16-byte stores); products under 2^18 multiply-adds stay on the FFMA kernel
+  if (M <= 0 || N <= 0 || K <= 0 || (N % 4) || (double)M * (double)N * (double)K < 262144.0) return -1;
   if (!aligned16(A) || !aligned16(B) || !aligned16(C) || (lda % 4) || (ldb % 4) || (ldc % 4)) return -1;
-  if (K / BK > 0x7fffffff || M >= (i64(1) << 31) || N >= (i64(1) << 31)) return -1;
+  if ((K + BK - 1) / BK > 0x7fffffff || M >= (i64(1) << 31) || N >= (i64(1) << 31)) return -1;
   EncodeTiledFn enc = encode_fn();
   if (!enc) return -1;
   static bool attr = false;
@@ -308,8 +313,8 @@ inline int launch(const float* A, i64 lda, const float* B, i64 ldb, float* C, i6
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return -1;
   }
-  dim3 grid((unsigned)(N / BN), (unsigned)(M / BM));
-  k_sgemm_tf32x3<<<grid, NTHREADS, SMEM_ALLOC, ctx()->stream>>>(ma, mb, C, ldc, (int)(K / BK));
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
+  k_sgemm_tf32x3<<<grid, NTHREADS, SMEM_ALLOC, ctx()->stream>>>(ma, mb, C, ldc, (int)((K + BK - 1) / BK), (int)M, (int)N);
   UM_LAUNCHED();
   return UM_OK;
 }
