@@ -201,6 +201,11 @@ def matd_ops(u, peak_gbs, n=32768):
     rec("where(mask, m, -m)", lambda: u.Mat.where(mask, m, m), 17 * E, "x and y alias the same matrix: one 8-byte read per element")
     rec("select m(mask)", lambda: m[mask], 14 * E, "mask read twice (count, scatter) + operand + ~half the elements written; includes the host read of k")
     del mask
+    # the NumPy-compatible PCG64 stream generated in HBM (8E bytes written; randn regenerates the
+    # stream twice -- tabulate, then emit -- and synchronises to learn how many draws it consumed)
+    g = u.NumPyRNG(0)
+    rec("rng_rand(PCG64)", lambda: g.rand(n, n), 8 * E)
+    rec("rng_randn(PCG64 ziggurat)", lambda: g.randn(n, n), 8 * E, "bit-identical to numpy default_rng.standard_normal; three kernels")
     t = m.T
     rec("sum_axis0@transposed_view", lambda: t.sum(0), 8 * E)
     rec("sub_rowvec@row_slice_view", lambda: m.slice(1024, n, 0, n) - rowv, 16 * (E - 1024.0 * n))

@@ -115,6 +115,30 @@ int32_t um_rand(const um_view* dst, uint64_t seed);
 int32_t um_get(const um_view* v, int64_t r, int64_t c, double* out);   /* m(r, c)            */
 int32_t um_set(const um_view* v, int64_t r, int64_t c, double value);  /* m(r, c) = value    */
 
+/* ---- NumPy-compatible PCG64 generator on the device -------------------------------
+ * The reference's global generator (data/NumPyRNG.scala:22-160: PCG64 XSL-RR 128, SeedSequence seeding :584-770,
+ * nextDouble :68-71, nextBoundedInt :82-110, ziggurat randn :124-160) behind MatD.setSeed / rand / randn / normal /
+ * uniform / randint (data/Mat.scala:1461-1530).  The state lives in a caller-owned POD (the Scala side keeps it where
+ * it keeps `globalRNG`); every fill consumes the stream exactly as the sequential generator would -- elements in
+ * row-major order -- and leaves the state where NumPy's would be, so fills can be mixed and continued.  `dst` must be
+ * a contiguous row-major matrix (the factories return fresh ones).  Values are bit-identical to
+ * numpy.random.default_rng(seed) except ziggurat tail draws (|z| > 3.654, 2.7e-4 of them), which go through CUDA's
+ * log1p and agree to 1 ulp.  um_rng_randn / um_rng_normal synchronise (the number of draws consumed is data-dependent). */
+typedef struct um_rng {
+  uint64_t state_hi, state_lo;   /* 128-bit LCG state                                         */
+  uint64_t inc_hi, inc_lo;       /* 128-bit increment (stream)                                */
+  int32_t has_uint32;            /* nextBoundedInt's cached high half (useUpper / cachedRaw)   */
+  uint32_t uinteger;
+} um_rng;
+int32_t um_rng_seed(um_rng* g, int64_t seed);         /* new NumPyRNG(seed); seed < 0 -> UM_ERR_ARG (NumPyRNG.scala:770) */
+int32_t um_rng_advance(um_rng* g, uint64_t draws);    /* skip `draws` 64-bit outputs (host arithmetic)                    */
+int32_t um_rng_next_u64(um_rng* g, uint64_t* out);    /* nextLong (host arithmetic; NumPyRNG.scala:58-61)                  */
+int32_t um_rng_rand(um_rng* g, const um_view* dst);                             /* MatD.rand     Mat.scala:1473 */
+int32_t um_rng_uniform(um_rng* g, double low, double high, const um_view* dst);  /* MatD.uniform  Mat.scala:1510 */
+int32_t um_rng_randn(um_rng* g, const um_view* dst);                            /* MatD.randn    Mat.scala:1480,1488 */
+int32_t um_rng_normal(um_rng* g, double mean, double sd, const um_view* dst);    /* MatD.normal   Mat.scala:1500 */
+int32_t um_rng_randint(um_rng* g, int32_t low, int32_t high, const um_view* dst_i32); /* MatD.randint Mat.scala:1525 */
+
 /* ---- elementwise (Mat.scala:1989-2102 Mat(+)Mat, :2154-2209,:2514-2531 Mat(+)scalar,
  *      :1416-1419 scalar(+)Mat, :4513-4588 in-place family = `out` aliasing `a`) ------ */
 typedef enum um_binop { UM_ADD = 0, UM_SUB = 1, UM_MUL = 2, UM_DIV = 3, UM_MAXIMUM = 4, UM_MINIMUM = 5,

@@ -110,6 +110,14 @@ SIGNATURES = {
     "um_eye": (_i32, [VP]),
     "um_randn": (_i32, [VP, C.c_uint64]),
     "um_rand": (_i32, [VP, C.c_uint64]),
+    "um_rng_seed": (_i32, [_vp, _i64]),
+    "um_rng_advance": (_i32, [_vp, C.c_uint64]),
+    "um_rng_next_u64": (_i32, [_vp, C.POINTER(C.c_uint64)]),
+    "um_rng_rand": (_i32, [_vp, VP]),
+    "um_rng_uniform": (_i32, [_vp, _f64, _f64, VP]),
+    "um_rng_randn": (_i32, [_vp, VP]),
+    "um_rng_normal": (_i32, [_vp, _f64, _f64, VP]),
+    "um_rng_randint": (_i32, [_vp, _i32, _i32, VP]),
     "um_get": (_i32, [VP, _i64, _i64, C.POINTER(_f64)]),
     "um_set": (_i32, [VP, _i64, _i64, _f64]),
     "um_binary": (_i32, [_i32, VP, VP, VP]),

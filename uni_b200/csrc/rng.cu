@@ -1,0 +1,636 @@
+// rng.cu -- NumPy-compatible PCG64 generator on the device: MatD.setSeed / rand /
+// randn / normal / uniform / randint (reference: src/main/scala/uni/data/NumPyRNG.scala:22-160 generator,
+// :584-770 SeedSequence + PCG64 seeding; src/main/scala/uni/data/Mat.scala:1461-1530 the Mat factories).
+//
+// The reference draws one element after the other from a single 128-bit LCG.  Here every thread JUMPS to its own
+// place in that stream (x -> x*A^k + C_k, the power-of-two maps are precomputed on the host and travel as kernel
+// parameters) and then walks it with the block-stride map, so consecutive threads hold consecutive draws and the
+// stores coalesce.  rand / uniform / randint consume a fixed number of draws per element and are one kernel.
+//
+// randn is NumPy's 256-level ziggurat: an ATTEMPT at stream position p consumes c(p) draws (1 for the 98.8 % that land
+// inside a strip, 2 for a wedge test, 1 + 2k for the tail loop) and yields 0 or 1 values, so the element -> position
+// map is a chain p -> p + c(p).  Three kernels keep it exact:
+//   k_zig_scan    per segment of S = 4096 positions: classify every position, evaluate the non-simple ones (each by
+//                 its own thread, jumping to p + 1 for the extra draws), then walk the chain for every entry offset
+//                 e < 16 (the overshoot a previous segment can leave behind) -> table e -> (exit offset, yields);
+//   k_zig_prefix  compose the tables in segment order -> true entry offset and first output index of every segment;
+//   k_zig_emit    regenerate the segment, walk the chain from its true entry, rank the yielding positions with
+//                 popcounts and store each value at its output index.
+// The stream is therefore consumed exactly as the sequential generator consumes it, and the generator's state after
+// the call is the state NumPy (and NumPyRNG.scala) would have.  exp / log1p in the wedge and tail branches are CUDA's
+// (<= 1 ulp); they decide accept / reject and the tail magnitude (|z| > 3.654, 2.7e-4 of the draws), every other
+// draw is integer arithmetic and one exact multiply.
+#include "common.cuh"
+#include "ziggurat_tables.cuh"
+
+namespace um {
+namespace {
+
+typedef unsigned __int128 u128;
+typedef unsigned long long u64;
+
+constexpr int RNG_THREADS = 256;
+constexpr int RNG_PER_THREAD = 16;
+constexpr int SEG = RNG_THREADS * RNG_PER_THREAD;  // positions per block / per ziggurat segment
+constexpr int SEG_WORDS = SEG / 64;
+constexpr int ZIG_ENTRIES = 16;                    // entry offsets tabulated per segment
+constexpr int ZIG_MAX_NS = 512;                    // non-simple positions a segment can list (mean 50, sd 7)
+
+inline u128 mk128(u64 hi, u64 lo) { return ((u128)hi << 64) | lo; }
+const u128 PCG_MULT = mk128(0x2360ED051FC65DA4ULL, 0x4385DF649FCCF645ULL);  // NumPyRNG.scala:36-38
+
+// x -> x * m[k] + p[k] advances the generator by 2^k draws
+struct Jump {
+  u64 mh[64], ml[64], ph[64], pl[64];
+};
+
+Jump make_jump(u128 inc) {
+  Jump j;
+  u128 m = PCG_MULT, p = inc;
+  for (int k = 0; k < 64; k++) {
+    j.mh[k] = (u64)(m >> 64); j.ml[k] = (u64)m; j.ph[k] = (u64)(p >> 64); j.pl[k] = (u64)p;
+    p = (m + 1) * p;
+    m = m * m;
+  }
+  return j;
+}
+
+u128 advance(u128 state, u128 inc, u64 delta) {
+  u128 m = PCG_MULT, p = inc;
+  while (delta) {
+    if (delta & 1) state = state * m + p;
+    p = (m + 1) * p;
+    m = m * m;
+    delta >>= 1;
+  }
+  return state;
+}
+
+inline u64 host_output(u128 s) {  // NumPyRNG.scala:53-56
+  u64 hi = (u64)(s >> 64), lo = (u64)s, x = hi ^ lo;
+  unsigned r = (unsigned)(hi >> 58);
+  return r ? (x >> r) | (x << (64 - r)) : x;
+}
+
+__device__ __forceinline__ void lcg(u64& hi, u64& lo, u64 mh, u64 ml, u64 ph, u64 pl) {
+  u64 nlo = lo * ml;
+  u64 nhi = __umul64hi(lo, ml) + lo * mh + hi * ml;
+  lo = nlo + pl;
+  hi = nhi + ph + (lo < pl ? 1ULL : 0ULL);
+}
+__device__ __forceinline__ u64 pcg_out(u64 hi, u64 lo) {
+  u64 x = hi ^ lo;
+  unsigned r = (unsigned)(hi >> 58);
+  return (x >> r) | (x << ((64 - r) & 63));
+}
+__device__ __forceinline__ void jump_to(u64& hi, u64& lo, u64 delta, const Jump& J) {
+  for (int k = 0; delta != 0; k++, delta >>= 1)
+    if (delta & 1) lcg(hi, lo, J.mh[k], J.ml[k], J.ph[k], J.pl[k]);
+}
+__device__ __forceinline__ double u01(u64 raw) { return (double)(raw >> 11) * (1.0 / 9007199254740992.0); }  // NumPyRNG.scala:68-71
+
+// ---- fixed-consumption draws: rand, uniform, randint ----------------------------------------------------------
+enum { DRAW_U01 = 0, DRAW_UNIFORM = 1, DRAW_INT = 2 };
+
+template <int KIND>
+__global__ void __launch_bounds__(RNG_THREADS) k_rng_draw(const __grid_constant__ Jump J, u64 s_hi, u64 s_lo, i64 n_raw,
+                                                         double* __restrict__ outd, int* __restrict__ outi, i64 n_out,
+                                                         double low, double span, int ilow, unsigned ibound, int pre_flag,
+                                                         int pre_val) {
+  if (KIND == DRAW_INT && pre_flag && blockIdx.x == 0 && threadIdx.x == 0) outi[-1] = pre_val;
+  i64 base = (i64)blockIdx.x * SEG + threadIdx.x;
+  if (base >= n_raw) return;
+  u64 hi = s_hi, lo = s_lo;
+  jump_to(hi, lo, (u64)base + 1, J);
+  const u64 mh = J.mh[8], ml = J.ml[8], ph = J.ph[8], pl = J.pl[8];  // stride 256 = RNG_THREADS
+#pragma unroll 4
+  for (int j = 0; j < RNG_PER_THREAD; j++) {
+    i64 p = base + (i64)j * RNG_THREADS;
+    if (p >= n_raw) break;
+    u64 raw = pcg_out(hi, lo);
+    if (KIND == DRAW_U01) {
+      outd[p] = u01(raw);
+    } else if (KIND == DRAW_UNIFORM) {
+      outd[p] = __dadd_rn(low, __dmul_rn(u01(raw), span));  // low + nextDouble() * (high - low), NumPyRNG.scala:73-74
+    } else {
+      // nextBoundedInt (NumPyRNG.scala:82-110): low half first, then the high half, (bits32 * bound) >>> 32
+      i64 o = 2 * p;
+      outi[o] = ilow + (int)(((raw & 0xffffffffULL) * (u64)ibound) >> 32);
+      if (o + 1 < n_out) outi[o + 1] = ilow + (int)(((raw >> 32) * (u64)ibound) >> 32);
+    }
+    lcg(hi, lo, mh, ml, ph, pl);
+  }
+}
+
+// ---- ziggurat ------------------------------------------------------------------------------------------------
+__device__ u64 d_zig_ki[256];
+__device__ double d_zig_wi[256];
+__device__ double d_zig_fi[256];
+
+struct ZigShared {
+  u64 ki[256];
+  double wi[256];
+  u64 ns[SEG_WORDS];        // non-simple positions (attempt needs more than its own draw)
+  u64 yes[SEG_WORDS];       // non-simple positions whose attempt yields a value
+  u64 covered[SEG_WORDS];   // positions consumed by an earlier attempt (emit only)
+  unsigned short cons[ZIG_MAX_NS];   // draws consumed, by list slot
+  unsigned short lpos[ZIG_MAX_NS];   // position, by list slot
+  double tailv[ZIG_MAX_NS];          // value of a tail attempt, by list slot (emit only)
+  unsigned short slot_of[SEG];       // list slot of a non-simple position (written for those only)
+  int nlist;
+  int overflow;
+  int prefix[SEG_WORDS + 1];
+};
+
+// one draw -> (idx, sign, rabs), NumPyRNG.scala:129-135
+__device__ __forceinline__ void zig_split(u64 raw, int& idx, int& sign, u64& rabs) {
+  idx = (int)(raw & 0xff);
+  u64 r = raw >> 8;
+  sign = (int)(r & 1);
+  rabs = (r >> 1) & 0x000fffffffffffffULL;
+}
+__device__ __forceinline__ double zig_x(u64 rabs, double w, int sign) {
+  // rabs < 2^52: exact conversion through the 2^52 exponent trick, then ONE rounded multiply (rabs.toDouble * wi)
+  double m = __longlong_as_double((long long)(rabs | 0x4330000000000000ULL)) - 4503599627370496.0;
+  double x = __dmul_rn(m, w);
+  return sign ? -x : x;
+}
+
+// Phase 1 (both kernels): generate this thread's draws, flag the non-simple ones, list them.
+// Returns the draws through raws[].
+__device__ __forceinline__ void zig_generate(ZigShared& sh, const Jump& J, u64 s_hi, u64 s_lo, i64 seg_base,
+                                             u64 (&raws)[RNG_PER_THREAD]) {
+  const int t = threadIdx.x;
+  u64 hi = s_hi, lo = s_lo;
+  jump_to(hi, lo, (u64)(seg_base + t) + 1, J);
+  const u64 mh = J.mh[8], ml = J.ml[8], ph = J.ph[8], pl = J.pl[8];
+#pragma unroll
+  for (int j = 0; j < RNG_PER_THREAD; j++) {
+    u64 raw = pcg_out(hi, lo);
+    raws[j] = raw;
+    int idx, sign;
+    u64 rabs;
+    zig_split(raw, idx, sign, rabs);
+    bool nonsimple = !(rabs < sh.ki[idx]);
+    unsigned b = __ballot_sync(0xffffffffu, nonsimple);
+    if ((t & 31) == 0) reinterpret_cast<unsigned*>(sh.ns)[(j * RNG_THREADS + t) >> 5] = b;
+    if (nonsimple) {
+      int slot = atomicAdd(&sh.nlist, 1);
+      if (slot < ZIG_MAX_NS) {
+        sh.lpos[slot] = (unsigned short)(j * RNG_THREADS + t);
+        sh.slot_of[j * RNG_THREADS + t] = (unsigned short)slot;
+      } else {
+        sh.overflow = 1;
+      }
+    }
+    lcg(hi, lo, mh, ml, ph, pl);
+  }
+}
+
+// Phase 2: one thread per listed position evaluates its attempt as if it started there (NumPyRNG.scala:139-157).
+__device__ __forceinline__ void zig_evaluate(ZigShared& sh, const Jump& J, u64 s_hi, u64 s_lo, i64 seg_base,
+                                             bool want_values) {
+  int n = min(sh.nlist, ZIG_MAX_NS);
+  for (int slot = threadIdx.x; slot < n; slot += RNG_THREADS) {
+    int p = sh.lpos[slot];
+    u64 hi = s_hi, lo = s_lo;
+    jump_to(hi, lo, (u64)(seg_base + p) + 1, J);  // state whose output is draw p
+    int idx, sign;
+    u64 rabs;
+    zig_split(pcg_out(hi, lo), idx, sign, rabs);
+    int consumed = 1;
+    bool yields;
+    double val = 0.0;
+    if (idx == 0) {
+      double xx, yy;
+      do {
+        lcg(hi, lo, J.mh[0], J.ml[0], J.ph[0], J.pl[0]);
+        xx = -UM_ZIG_INV_R * log1p(-u01(pcg_out(hi, lo)));
+        lcg(hi, lo, J.mh[0], J.ml[0], J.ph[0], J.pl[0]);
+        yy = -log1p(-u01(pcg_out(hi, lo)));
+        consumed += 2;
+      } while (!(__dadd_rn(yy, yy) > __dmul_rn(xx, xx)) && consumed < 60000);
+      yields = true;
+      val = ((rabs >> 8) & 1) ? -__dadd_rn(UM_ZIG_R, xx) : __dadd_rn(UM_ZIG_R, xx);
+    } else {
+      lcg(hi, lo, J.mh[0], J.ml[0], J.ph[0], J.pl[0]);
+      consumed = 2;
+      double x = zig_x(rabs, sh.wi[idx], sign);
+      double f1 = d_zig_fi[idx], f0 = d_zig_fi[idx - 1];
+      double lhs = __dadd_rn(__dmul_rn(__dadd_rn(f0, -f1), u01(pcg_out(hi, lo))), f1);
+      yields = lhs < exp(__dmul_rn(__dmul_rn(-0.5, x), x));
+    }
+    sh.cons[slot] = (unsigned short)consumed;
+    if (want_values) sh.tailv[slot] = val;
+    if (yields) atomicOr(&sh.yes[p >> 6], 1ULL << (p & 63));
+  }
+}
+
+// first non-simple position >= p (SEG if none)
+__device__ __forceinline__ int zig_next_ns(const ZigShared& sh, int p) {
+  int w = p >> 6;
+  u64 m = sh.ns[w] & (~0ULL << (p & 63));
+  while (m == 0) {
+    if (++w >= SEG_WORDS) return SEG;
+    m = sh.ns[w];
+  }
+  return (w << 6) + __ffsll((long long)m) - 1;
+}
+
+// Walk the chain of attempts from `entry`; returns the yields, the overshoot past the segment end in `exit_off`.
+template <bool MARK>
+__device__ __forceinline__ int zig_walk(ZigShared& sh, int entry, int& exit_off) {
+  int p = entry, count = 0;
+  while (p < SEG) {
+    int q = zig_next_ns(sh, p);
+    count += q - p;  // simple attempts: one draw, one value each
+    if (q >= SEG) { p = SEG; break; }
+    int c = sh.cons[sh.slot_of[q]];
+    count += (int)((sh.yes[q >> 6] >> (q & 63)) & 1);
+    if (MARK)
+      for (int k = q + 1; k < q + c && k < SEG; k++) sh.covered[k >> 6] |= 1ULL << (k & 63);
+    p = q + c;
+  }
+  exit_off = p - SEG;
+  return count;
+}
+
+__device__ __forceinline__ void zig_init_shared(ZigShared& sh) {
+  for (int i = threadIdx.x; i < 256; i += RNG_THREADS) { sh.ki[i] = d_zig_ki[i]; sh.wi[i] = d_zig_wi[i]; }
+  for (int i = threadIdx.x; i < SEG_WORDS; i += RNG_THREADS) { sh.yes[i] = 0; sh.covered[i] = 0; }
+  if (threadIdx.x == 0) { sh.nlist = 0; sh.overflow = 0; }
+  __syncthreads();
+}
+
+// table entry: yields | exit << 16 ; exit 0xff = unsupported (overshoot >= ZIG_ENTRIES or list overflow)
+__global__ void __launch_bounds__(RNG_THREADS) k_zig_scan(const __grid_constant__ Jump J, u64 s_hi, u64 s_lo,
+                                                         unsigned* __restrict__ table) {
+  __shared__ ZigShared sh;
+  zig_init_shared(sh);
+  const i64 seg_base = (i64)blockIdx.x * SEG;
+  u64 raws[RNG_PER_THREAD];
+  zig_generate(sh, J, s_hi, s_lo, seg_base, raws);
+  __syncthreads();
+  zig_evaluate(sh, J, s_hi, s_lo, seg_base, false);
+  __syncthreads();
+  if (threadIdx.x < ZIG_ENTRIES) {
+    int ex = 0xff, cnt = 0;
+    if (!sh.overflow) {  // (a listed position without a slot has no consumption record to walk over)
+      cnt = zig_walk<false>(sh, threadIdx.x, ex);
+      if (ex >= ZIG_ENTRIES) ex = 0xff;
+    }
+    table[(i64)blockIdx.x * ZIG_ENTRIES + threadIdx.x] = (unsigned)cnt | ((unsigned)ex << 16);
+  }
+}
+
+// result block written by k_zig_prefix / k_zig_emit: [0] total yields of all segments, [1] exit offset of the last
+// segment, [2] error flag, [3] stream position right after the draw that completed output n_out-1 (emit)
+constexpr int PREFIX_THREADS = 1024;
+struct PrefixShared {
+  i64 cnt[PREFIX_THREADS][ZIG_ENTRIES];
+  i64 base[PREFIX_THREADS];
+  unsigned char exit_[PREFIX_THREADS][ZIG_ENTRIES];
+  unsigned char entry[PREFIX_THREADS];
+  int err;
+};
+__device__ __forceinline__ void load_row(const unsigned* __restrict__ table, i64 s, unsigned (&row)[ZIG_ENTRIES]) {
+  const uint4* r = reinterpret_cast<const uint4*>(table + s * ZIG_ENTRIES);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    uint4 v = __ldg(r + q);
+    row[4 * q] = v.x; row[4 * q + 1] = v.y; row[4 * q + 2] = v.z; row[4 * q + 3] = v.w;
+  }
+}
+// One block.  Thread t owns a run of consecutive segments: (A) the run's map e -> (exit, yields) for all 16 entry
+// offsets, (B) thread 0 chains the 1024 run maps, (C) every thread replays its run from its true entry.  The table
+// rows are fetched whole (their address does not depend on the chain), so the loads pipeline.
+__global__ void __launch_bounds__(PREFIX_THREADS) k_zig_prefix(const unsigned* __restrict__ table, i64 nseg,
+                                                               unsigned char* __restrict__ seg_entry,
+                                                               i64* __restrict__ seg_base_out, i64* __restrict__ result) {
+  extern __shared__ __align__(16) unsigned char prefix_smem[];
+  PrefixShared& sh = *reinterpret_cast<PrefixShared*>(prefix_smem);
+  const int t = threadIdx.x;
+  if (t == 0) sh.err = 0;
+  const i64 run = (nseg + PREFIX_THREADS - 1) / PREFIX_THREADS;
+  const i64 s0 = min((i64)t * run, nseg), s1 = min(s0 + run, nseg);
+  {
+    int cur[ZIG_ENTRIES];
+    i64 cnt[ZIG_ENTRIES];
+#pragma unroll
+    for (int e = 0; e < ZIG_ENTRIES; e++) { cur[e] = e; cnt[e] = 0; }
+#pragma unroll 2
+    for (i64 s = s0; s < s1; s++) {
+      unsigned row[ZIG_ENTRIES];
+      load_row(table, s, row);
+#pragma unroll
+      for (int e = 0; e < ZIG_ENTRIES; e++) {
+        if (cur[e] != 0xff) {
+          unsigned v = row[cur[e]];
+          cnt[e] += v & 0xffff;
+          cur[e] = (int)(v >> 16);
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < ZIG_ENTRIES; e++) { sh.cnt[t][e] = cnt[e]; sh.exit_[t][e] = (unsigned char)cur[e]; }
+  }
+  __syncthreads();
+  if (t == 0) {
+    int cur = 0, err = 0;
+    i64 total = 0;
+    for (int k = 0; k < PREFIX_THREADS; k++) {
+      sh.entry[k] = (unsigned char)cur;
+      sh.base[k] = total;
+      if (cur == 0xff) { err = 1; continue; }
+      total += sh.cnt[k][cur];
+      cur = sh.exit_[k][cur];
+    }
+    if (cur == 0xff) err = 1;
+    sh.err = err;
+    result[0] = total;
+    result[1] = cur;
+    result[2] = err;
+  }
+  __syncthreads();
+  if (sh.err) return;
+  int cur = sh.entry[t];
+  i64 base = sh.base[t];
+#pragma unroll 2
+  for (i64 s = s0; s < s1; s++) {
+    unsigned row[ZIG_ENTRIES];
+    load_row(table, s, row);
+    seg_entry[s] = (unsigned char)cur;
+    seg_base_out[s] = base;
+    unsigned v = row[cur];
+    base += v & 0xffff;
+    cur = (int)(v >> 16);
+  }
+}
+
+__global__ void __launch_bounds__(RNG_THREADS, 3) k_zig_emit(const __grid_constant__ Jump J, u64 s_hi, u64 s_lo,
+                                                         const unsigned char* __restrict__ seg_entry,
+                                                         const i64* __restrict__ seg_base_in, double* __restrict__ out,
+                                                         i64 n_out, double mean, double sd, int affine,
+                                                         i64* __restrict__ result) {
+  __shared__ ZigShared sh;
+  if (result[2]) return;  // k_zig_prefix met a segment it cannot chain: the host reports it
+  const i64 out_base = seg_base_in[blockIdx.x];
+  if (out_base >= n_out) return;  // whole segment lies past the last wanted element
+  zig_init_shared(sh);
+  const i64 seg_base = (i64)blockIdx.x * SEG;
+  const int entry = seg_entry[blockIdx.x];
+  const int t = threadIdx.x;
+  u64 raws[RNG_PER_THREAD];
+  zig_generate(sh, J, s_hi, s_lo, seg_base, raws);
+  __syncthreads();
+  zig_evaluate(sh, J, s_hi, s_lo, seg_base, true);
+  __syncthreads();
+  if (t == 0) {
+    int ex;
+    zig_walk<true>(sh, entry, ex);
+  }
+  __syncthreads();
+  // yielding positions: started (>= entry, not covered) and (simple or accepted)
+  if (t < SEG_WORDS) {
+    u64 m = ~sh.covered[t] & (~sh.ns[t] | sh.yes[t]);
+    int lo_bit = entry - t * 64;
+    if (lo_bit >= 64) m = 0;
+    else if (lo_bit > 0) m &= ~0ULL << lo_bit;
+    sh.covered[t] = m;  // reuse: now the yield mask
+  }
+  __syncthreads();
+  if (t == 0) {
+    int acc = 0;
+    for (int w = 0; w < SEG_WORDS; w++) { sh.prefix[w] = acc; acc += __popcll(sh.covered[w]); }
+    sh.prefix[SEG_WORDS] = acc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < RNG_PER_THREAD; j++) {
+    const int p = j * RNG_THREADS + t;
+    const u64 ym = sh.covered[p >> 6];
+    if (!((ym >> (p & 63)) & 1)) continue;
+    const i64 o = out_base + sh.prefix[p >> 6] + __popcll(ym & ((1ULL << (p & 63)) - 1));
+    if (o >= n_out) continue;
+    int idx, sign;
+    u64 rabs;
+    zig_split(raws[j], idx, sign, rabs);
+    double v;
+    int consumed = 1;
+    if (rabs < sh.ki[idx]) {
+      v = zig_x(rabs, sh.wi[idx], sign);
+    } else {
+      const int slot = sh.slot_of[p];
+      consumed = sh.cons[slot];
+      v = idx == 0 ? sh.tailv[slot] : zig_x(rabs, sh.wi[idx], sign);
+    }
+    if (affine) v = __dadd_rn(mean, __dmul_rn(sd, v));  // mean + std * rng.randn(), Mat.scala:1500-1507
+    out[o] = v;
+    if (o == n_out - 1) result[3] = seg_base + p + consumed;
+  }
+}
+
+int upload_tables() {
+  static std::atomic<unsigned long long> done{0};  // one bit per device
+  Ctx* c = ctx();
+  const unsigned long long bit = 1ULL << (c->device & 63);
+  if (done.load() & bit) return UM_OK;
+  UM_CUDA(cudaMemcpyToSymbol(d_zig_ki, h_zig_ki, sizeof(h_zig_ki)));
+  UM_CUDA(cudaMemcpyToSymbol(d_zig_wi, h_zig_wi_bits, sizeof(h_zig_wi_bits)));
+  UM_CUDA(cudaMemcpyToSymbol(d_zig_fi, h_zig_fi_bits, sizeof(h_zig_fi_bits)));
+  UM_CUDA(cudaDeviceSynchronize());
+  done.fetch_or(bit);
+  return UM_OK;
+}
+
+int check_dst(const um_view* dst, int dtype, const char* what) {
+  if (dst->dtype != dtype) return fail(UM_ERR_ARG, "%s: destination dtype %d, expected %d", what, dst->dtype, dtype);
+  bool contiguous = dst->cs == 1 && (dst->rows <= 1 || dst->rs == dst->cols);
+  if (!contiguous && dst->rows * dst->cols > 0)
+    return fail(UM_ERR_ARG, "%s: destination must be a contiguous row-major matrix (the factories return fresh ones)", what);
+  return UM_OK;
+}
+
+inline u128 st_of(const um_rng* g) { return mk128(g->state_hi, g->state_lo); }
+inline u128 inc_of(const um_rng* g) { return mk128(g->inc_hi, g->inc_lo); }
+inline void st_set(um_rng* g, u128 s) { g->state_hi = (u64)(s >> 64); g->state_lo = (u64)s; }
+
+// ---- SeedSequence (NumPyRNG.scala:557-570 hashmix / mix, :635-666 mixEntropy, :685-718 generateState) ---------
+const uint32_t SS_INIT_A = 0x43b0d7e5u, SS_MULT_A = 0x931e8875u, SS_INIT_B = 0x8b51f9ddu, SS_MULT_B = 0x58f38dedu,
+               SS_MIX_L = 0xca01f9ddu, SS_MIX_R = 0x4973f715u;
+inline uint32_t ss_hashmix(uint32_t v, uint32_t& hc) {
+  v ^= hc; hc *= SS_MULT_A; v *= hc; v ^= v >> 16;
+  return v;
+}
+inline uint32_t ss_mix(uint32_t x, uint32_t y) {
+  uint32_t r = SS_MIX_L * x - SS_MIX_R * y;
+  r ^= r >> 16;
+  return r;
+}
+
+template <int KIND>
+int draw_impl(um_rng* g, const um_view* dst, double low, double span, int ilow, unsigned ibound, const char* what) {
+  UM_CTX();
+  UM_VIEW(dst);
+  if (!g) return fail(UM_ERR_ARG, "%s: null generator", what);
+  int s = check_dst(dst, KIND == DRAW_INT ? UM_I32 : UM_F64, what);
+  if (s != UM_OK) return s;
+  i64 n = dst->rows * dst->cols;
+  if (n == 0) return UM_OK;
+  double* outd = KIND == DRAW_INT ? nullptr : static_cast<double*>(dst->data) + dst->offset;
+  int* outi = KIND == DRAW_INT ? static_cast<int*>(dst->data) + dst->offset : nullptr;
+  i64 n_raw = n;
+  int pre_flag = 0, pre_val = 0;
+  if (KIND == DRAW_INT) {
+    if (g->has_uint32) {  // the cached high half of the previous draw goes first (NumPyRNG.scala:86-101)
+      pre_flag = 1;
+      pre_val = ilow + (int)(((u64)g->uinteger * (u64)ibound) >> 32);
+      g->has_uint32 = 0;
+      outi += 1;
+      n -= 1;
+    }
+    n_raw = (n + 1) / 2;
+  }
+  Jump J = make_jump(inc_of(g));
+  i64 blocks = (n_raw + SEG - 1) / SEG;
+  if (blocks == 0) blocks = 1;  // only the cached element
+  if (blocks > 0x7fffffffLL) return fail(UM_ERR_ARG, "%s: %lld elements exceed one launch", what, (long long)n);
+  k_rng_draw<KIND><<<(unsigned)blocks, RNG_THREADS, 0, ctx()->stream>>>(J, g->state_hi, g->state_lo, n_raw, outd, outi, n, low, span,
+                                                                        ilow, ibound, pre_flag, pre_val);
+  UM_LAUNCHED();
+  u128 s2 = advance(st_of(g), inc_of(g), (u64)n_raw);
+  if (KIND == DRAW_INT && (n & 1)) {
+    g->has_uint32 = 1;
+    g->uinteger = (uint32_t)(host_output(s2) >> 32);
+  }
+  st_set(g, s2);
+  return UM_OK;
+}
+
+int randn_impl(um_rng* g, const um_view* dst, double mean, double sd, int affine, const char* what) {
+  UM_CTX();
+  UM_VIEW(dst);
+  if (!g) return fail(UM_ERR_ARG, "%s: null generator", what);
+  int s = check_dst(dst, UM_F64, what);
+  if (s != UM_OK) return s;
+  i64 n = dst->rows * dst->cols;
+  if (n == 0) return UM_OK;
+  s = upload_tables();
+  if (s != UM_OK) return s;
+  double* out = static_cast<double*>(dst->data) + dst->offset;
+  cudaStream_t st = ctx()->stream;
+  const Jump J = make_jump(inc_of(g));
+  while (n > 0) {
+    // 1.0173 draws per value on average; 3 % + two segments of margin makes a second round rare
+    i64 nseg = (i64)((double)n * 1.03 / SEG) + 2;
+    if (nseg > 0x7fffffffLL) return fail(UM_ERR_ARG, "%s: too many elements for one call", what);
+    size_t tab_bytes = (size_t)nseg * ZIG_ENTRIES * sizeof(unsigned);
+    size_t base_off = (tab_bytes + 255) & ~(size_t)255;
+    size_t entry_off = base_off + (((size_t)nseg * sizeof(i64) + 255) & ~(size_t)255);
+    size_t res_off = entry_off + (((size_t)nseg + 255) & ~(size_t)255);
+    char* ws = static_cast<char*>(scratch(res_off + 64));
+    if (!ws) return UM_ERR_OOM;
+    unsigned* table = reinterpret_cast<unsigned*>(ws);
+    i64* seg_base = reinterpret_cast<i64*>(ws + base_off);
+    unsigned char* seg_entry = reinterpret_cast<unsigned char*>(ws + entry_off);
+    i64* result = reinterpret_cast<i64*>(ws + res_off);
+    UM_CUDA(cudaMemsetAsync(result, 0, 64, st));
+    k_zig_scan<<<(unsigned)nseg, RNG_THREADS, 0, st>>>(J, g->state_hi, g->state_lo, table);
+    UM_LAUNCHED();
+    UM_CUDA(cudaFuncSetAttribute(k_zig_prefix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrefixShared)));
+    k_zig_prefix<<<1, PREFIX_THREADS, sizeof(PrefixShared), st>>>(table, nseg, seg_entry, seg_base, result);
+    UM_LAUNCHED();
+    k_zig_emit<<<(unsigned)nseg, RNG_THREADS, 0, st>>>(J, g->state_hi, g->state_lo, seg_entry, seg_base, out, n, mean, sd, affine, result);
+    UM_LAUNCHED();
+    i64 res[4];
+    UM_CUDA(cudaMemcpyAsync(res, result, sizeof(res), cudaMemcpyDeviceToHost, st));
+    UM_CUDA(cudaStreamSynchronize(st));
+    if (res[2]) return fail(UM_ERR_ARG, "%s: a ziggurat tail loop ran past the %d-draw window this generator tabulates", what, ZIG_ENTRIES);
+    if (res[0] >= n) {
+      st_set(g, advance(st_of(g), inc_of(g), (u64)res[3]));
+      n = 0;
+    } else {  // the margin was too small: keep what was produced, continue behind the last segment's overshoot
+      st_set(g, advance(st_of(g), inc_of(g), (u64)(nseg * SEG + res[1])));
+      out += res[0];
+      n -= res[0];
+    }
+  }
+  return UM_OK;
+}
+
+}  // namespace
+}  // namespace um
+
+using namespace um;
+
+extern "C" {
+
+int32_t um_rng_seed(um_rng* g, int64_t seed) {
+  if (!g) return fail(UM_ERR_ARG, "um_rng_seed: null generator");
+  if (seed < 0) return fail(UM_ERR_ARG, "seed [%lld] must be non-negative", (long long)seed);  // NumPyRNG.scala:770-771
+  // entropy -> little-endian 32-bit words, at least one (NumPyRNG.scala:484-501)
+  uint32_t ent[2];
+  int nent = 0;
+  u64 v = (u64)seed;
+  do { ent[nent++] = (uint32_t)v; v >>= 32; } while (v != 0);
+  uint32_t pool[4], hc = SS_INIT_A;
+  for (int i = 0; i < 4; i++) pool[i] = ss_hashmix(i < nent ? ent[i] : 0u, hc);
+  for (int src = 0; src < 4; src++)
+    for (int dst = 0; dst < 4; dst++)
+      if (src != dst) pool[dst] = ss_mix(pool[dst], ss_hashmix(pool[src], hc));
+  // generate_state(4, uint64) = 8 uint32 words paired little-endian
+  uint32_t w32[8], hb = SS_INIT_B;
+  for (int i = 0; i < 8; i++) {
+    uint32_t d = pool[i & 3];
+    d ^= hb; hb *= SS_MULT_B; d *= hb; d ^= d >> 16;
+    w32[i] = d;
+  }
+  u64 w[4];
+  for (int i = 0; i < 4; i++) w[i] = (u64)w32[2 * i] | ((u64)w32[2 * i + 1] << 32);
+  // pcg64_set_seed / pcg_setseq_128_srandom_r (NumPyRNG.scala:761-767,780-786)
+  u128 initstate = mk128(w[0], w[1]), initseq = mk128(w[2], w[3]);
+  u128 inc = (initseq << 1) | 1;
+  u128 s = 0 * PCG_MULT + inc;
+  s += initstate;
+  s = s * PCG_MULT + inc;
+  g->state_hi = (u64)(s >> 64); g->state_lo = (u64)s;
+  g->inc_hi = (u64)(inc >> 64); g->inc_lo = (u64)inc;
+  g->has_uint32 = 0;
+  g->uinteger = 0;
+  return UM_OK;
+}
+
+int32_t um_rng_advance(um_rng* g, uint64_t draws) {
+  if (!g) return fail(UM_ERR_ARG, "um_rng_advance: null generator");
+  st_set(g, advance(st_of(g), inc_of(g), draws));
+  return UM_OK;
+}
+
+int32_t um_rng_next_u64(um_rng* g, uint64_t* out) {
+  if (!g || !out) return fail(UM_ERR_ARG, "um_rng_next_u64: null argument");
+  u128 s = st_of(g) * PCG_MULT + inc_of(g);
+  st_set(g, s);
+  *out = host_output(s);
+  return UM_OK;
+}
+
+int32_t um_rng_rand(um_rng* g, const um_view* dst) { return draw_impl<DRAW_U01>(g, dst, 0, 0, 0, 0, "um_rng_rand"); }
+
+int32_t um_rng_uniform(um_rng* g, double low, double high, const um_view* dst) {
+  return draw_impl<DRAW_UNIFORM>(g, dst, low, high - low, 0, 0, "um_rng_uniform");
+}
+
+int32_t um_rng_randint(um_rng* g, int32_t low, int32_t high, const um_view* dst_i32) {
+  // nextBoundedInt: require(bound > 0) (NumPyRNG.scala:83); high - low wraps exactly like the JVM's Int
+  int32_t bound = (int32_t)((uint32_t)high - (uint32_t)low);
+  if (bound <= 0) return fail(UM_ERR_ARG, "bound must be positive");
+  return draw_impl<DRAW_INT>(g, dst_i32, 0, 0, low, (unsigned)bound, "um_rng_randint");
+}
+
+int32_t um_rng_randn(um_rng* g, const um_view* dst) { return randn_impl(g, dst, 0.0, 1.0, 0, "um_rng_randn"); }
+
+int32_t um_rng_normal(um_rng* g, double mean, double sd, const um_view* dst) {
+  return randn_impl(g, dst, mean, sd, 1, "um_rng_normal");
+}
+
+}  // extern "C"

@@ -554,17 +554,58 @@ class _Facade:
         check(lib.um_eye(m._ref()))
         return m
 
-    def randn(self, rows, cols, seed: int = 0):
-        """Synthetic N(0,1) panel generated in HBM (a counter-based generator -- NOT the
-        reference's PCG64 stream, NumPyRNG.scala; fixture inputs come from host NumPy)."""
-        m = Mat._alloc(rows, cols, self.dtype)
-        check(lib.um_randn(m._ref(), seed))
-        return m
+    # -- random factories (Mat.scala:1461-1530).  Without `seed` they draw from the global NumPy-compatible PCG64
+    #    generator (`MatD.setSeed`), element by element in row-major order like the reference.  With an explicit
+    #    `seed=` they produce a synthetic counter-based panel instead (bench / test inputs; NOT the PCG64 stream). --
+    def setSeed(self, seed: int) -> None:
+        from . import rng
+        rng.set_seed(seed)
 
-    def rand(self, rows, cols, seed: int = 0):
-        m = Mat._alloc(rows, cols, self.dtype)
-        check(lib.um_rand(m._ref(), seed))
-        return m
+    def nextRandLong(self) -> int:
+        from . import rng
+        return rng.global_rng().nextLong()
+
+    def nextRandInt(self) -> int:  # globalRNG.nextInt() & 0xFFFFFFFFL: the LOW 32 bits (Mat.scala:1469, NumPyRNG.scala:64-66)
+        from . import rng
+        return rng.global_rng().nextLong() & 0xFFFFFFFF
+
+    def nextRandDouble(self) -> float:
+        from . import rng
+        return rng.global_rng().nextDouble()
+
+    def randn(self, rows, cols=None, seed: Optional[int] = None):
+        if seed is not None:
+            m = Mat._alloc(rows, cols, self.dtype)
+            check(lib.um_randn(m._ref(), seed))
+            return m
+        from . import rng
+        m = rng.global_rng().randn(rows, 1 if cols is None else cols)  # randn(n) is an n x 1 column (Mat.scala:1480-1482)
+        return m if self.dtype == L.F64 else m.astype(self.dtype)
+
+    rnorm = randn
+
+    def rand(self, rows, cols, seed: Optional[int] = None):
+        if seed is not None:
+            m = Mat._alloc(rows, cols, self.dtype)
+            check(lib.um_rand(m._ref(), seed))
+            return m
+        from . import rng
+        m = rng.global_rng().rand(rows, cols)
+        return m if self.dtype == L.F64 else m.astype(self.dtype)
+
+    def normal(self, mean, std, rows, cols):
+        from . import rng
+        return rng.global_rng().normal(mean, std, rows, cols)
+
+    def uniform(self, low, high, rows, cols):
+        from . import rng
+        return rng.global_rng().uniform_mat(low, high, rows, cols)
+
+    def randint(self, low, high, rows=None, cols=None):
+        from . import rng
+        if rows is None:  # randint(low, high): one Int (Mat.scala:1520-1522)
+            return int(rng.global_rng().randint(low, high, 1, 1).to_numpy()[0, 0])
+        return rng.global_rng().randint(low, high, rows, cols)
 
     def hstack(self, *mats):
         rows = mats[0].rows
