@@ -9,17 +9,26 @@
 //
 // randn is NumPy's 256-level ziggurat: an ATTEMPT at stream position p consumes c(p) draws (1 for the 98.8 % that land
 // inside a strip, 2 for a wedge test, 1 + 2k for the tail loop) and yields 0 or 1 values, so the element -> position
-// map is a chain p -> p + c(p).  Three kernels keep it exact:
-//   k_zig_scan    per segment of S = 4096 positions: classify every position, evaluate the non-simple ones (each by
-//                 its own thread, jumping to p + 1 for the extra draws), then walk the chain for every entry offset
-//                 e < 16 (the overshoot a previous segment can leave behind) -> table e -> (exit offset, yields);
-//   k_zig_prefix  compose the tables in segment order -> true entry offset and first output index of every segment;
-//   k_zig_emit    regenerate the segment, walk the chain from its true entry, rank the yielding positions with
-//                 popcounts and store each value at its output index.
+// map is a chain p -> p + c(p).  It is resolved exactly, in parallel:
+//   k_rng_block_states  generator state at the first draw of every segment (S = 4096 draws);
+//   k_zig_scan          per segment: classify every draw; the ~50 non-simple ones are listed and each is evaluated by
+//                       its own thread (jump to p + 1 for the extra draws); each then decides whether the chain from
+//                       the segment's first draw starts an attempt AT it (walk back to the nearest position no earlier
+//                       attempt can reach over, replay the few attempts in between) and marks the draws it consumes;
+//                       -> yield mask of the segment (stored), and for every entry offset e < 16 (the overshoot a
+//                       previous segment can leave behind; its chain merges with the one from 0 within a few draws)
+//                       the table e -> (exit offset, number of yields);
+//   k_zig_pf_reduce / _scan / _apply   compose the tables in segment order (a three-level scan of 16-entry maps)
+//                       -> true entry offset and first output index of every segment;
+//   k_zig_emit_fast     segments entered at offset 0 (98.8 %): regenerate the draws, store value at base + rank
+//                       (rank = popcounts of the stored mask); tail values are recomputed in place;
+//   k_zig_emit          the other segments: full resolution again from the true entry.
 // The stream is therefore consumed exactly as the sequential generator consumes it, and the generator's state after
 // the call is the state NumPy (and NumPyRNG.scala) would have.  exp / log1p in the wedge and tail branches are CUDA's
 // (<= 1 ulp); they decide accept / reject and the tail magnitude (|z| > 3.654, 2.7e-4 of the draws), every other
-// draw is integer arithmetic and one exact multiply.
+// draw is integer arithmetic and one exact multiply.  An attempt that would consume more than 32 draws, or an
+// overshoot of 16 or more (a tail loop of 8+ rounds at a segment end, p < 1e-12 per 2^31 draws) is reported as an
+// error, never emitted wrong.
 #include "common.cuh"
 #include "ziggurat_tables.cuh"
 
@@ -35,6 +44,7 @@ constexpr int SEG = RNG_THREADS * RNG_PER_THREAD;  // positions per block / per 
 constexpr int SEG_WORDS = SEG / 64;
 constexpr int ZIG_ENTRIES = 16;                    // entry offsets tabulated per segment
 constexpr int ZIG_MAX_NS = 512;                    // non-simple positions a segment can list (mean 50, sd 7)
+constexpr int ZIG_MAX_CONS = 32;                   // draws one attempt may consume (tail loop of 15 rounds: p ~ 1e-17)
 
 inline u128 mk128(u64 hi, u64 lo) { return ((u128)hi << 64) | lo; }
 const u128 PCG_MULT = mk128(0x2360ED051FC65DA4ULL, 0x4385DF649FCCF645ULL);  // NumPyRNG.scala:36-38
@@ -89,22 +99,45 @@ __device__ __forceinline__ void jump_to(u64& hi, u64& lo, u64 delta, const Jump&
 }
 __device__ __forceinline__ double u01(u64 raw) { return (double)(raw >> 11) * (1.0 / 9007199254740992.0); }  // NumPyRNG.scala:68-71
 
+// State of the generator at the first position of every block (segment): one full jump per BS_CHUNK blocks, then
+// block-stride steps.  The per-thread jump inside a block is then only log2(SEG) maps deep.
+constexpr int BS_CHUNK = 16;
+__global__ void __launch_bounds__(128) k_rng_block_states(const __grid_constant__ Jump J, u64 s_hi, u64 s_lo, i64 nblocks,
+                                                         int log2_span, ulonglong2* __restrict__ bs) {
+  i64 b0 = ((i64)blockIdx.x * 128 + threadIdx.x) * BS_CHUNK;
+  if (b0 >= nblocks) return;
+  u64 hi = s_hi, lo = s_lo;
+  jump_to(hi, lo, (u64)b0 << log2_span, J);
+  const u64 mh = J.mh[log2_span], ml = J.ml[log2_span], ph = J.ph[log2_span], pl = J.pl[log2_span];
+  for (int i = 0; i < BS_CHUNK && b0 + i < nblocks; i++) {
+    bs[b0 + i] = make_ulonglong2(hi, lo);
+    lcg(hi, lo, mh, ml, ph, pl);  // 2^log2_span draws
+  }
+}
+static_assert(SEG == 4096, "ziggurat segments are 2^12 draws (16-bit positions, block-state stride)");
+// the fixed-consumption fills amortise the per-thread jump over more draws
+constexpr int DRAW_PER_THREAD = 64;
+constexpr int DRAW_LOG2_SPAN = 14;
+constexpr int DRAW_SPAN = RNG_THREADS * DRAW_PER_THREAD;
+static_assert(DRAW_SPAN == 1 << DRAW_LOG2_SPAN, "block-state stride");
+
 // ---- fixed-consumption draws: rand, uniform, randint ----------------------------------------------------------
 enum { DRAW_U01 = 0, DRAW_UNIFORM = 1, DRAW_INT = 2 };
 
 template <int KIND>
-__global__ void __launch_bounds__(RNG_THREADS) k_rng_draw(const __grid_constant__ Jump J, u64 s_hi, u64 s_lo, i64 n_raw,
+__global__ void __launch_bounds__(RNG_THREADS) k_rng_draw(const __grid_constant__ Jump J, const ulonglong2* __restrict__ bs, i64 n_raw,
                                                          double* __restrict__ outd, int* __restrict__ outi, i64 n_out,
                                                          double low, double span, int ilow, unsigned ibound, int pre_flag,
                                                          int pre_val) {
   if (KIND == DRAW_INT && pre_flag && blockIdx.x == 0 && threadIdx.x == 0) outi[-1] = pre_val;
-  i64 base = (i64)blockIdx.x * SEG + threadIdx.x;
+  i64 base = (i64)blockIdx.x * DRAW_SPAN + threadIdx.x;
   if (base >= n_raw) return;
-  u64 hi = s_hi, lo = s_lo;
-  jump_to(hi, lo, (u64)base + 1, J);
+  const ulonglong2 b = bs[blockIdx.x];
+  u64 hi = b.x, lo = b.y;
+  jump_to(hi, lo, (u64)threadIdx.x + 1, J);
   const u64 mh = J.mh[8], ml = J.ml[8], ph = J.ph[8], pl = J.pl[8];  // stride 256 = RNG_THREADS
 #pragma unroll 4
-  for (int j = 0; j < RNG_PER_THREAD; j++) {
+  for (int j = 0; j < DRAW_PER_THREAD; j++) {
     i64 p = base + (i64)j * RNG_THREADS;
     if (p >= n_raw) break;
     u64 raw = pcg_out(hi, lo);
@@ -137,8 +170,11 @@ struct ZigShared {
   unsigned short lpos[ZIG_MAX_NS];   // position, by list slot
   double tailv[ZIG_MAX_NS];          // value of a tail attempt, by list slot (emit only)
   unsigned short slot_of[SEG];       // list slot of a non-simple position (written for those only)
+  u64 ym[SEG_WORDS];        // positions whose attempt yields a value (chain from entry 0, then the true entry)
   int nlist;
   int overflow;
+  int reach;                // max over the chain's non-simple attempts of (position + draws consumed)
+  int half;
   int prefix[SEG_WORDS + 1];
 };
 
@@ -158,11 +194,10 @@ __device__ __forceinline__ double zig_x(u64 rabs, double w, int sign) {
 
 // Phase 1 (both kernels): generate this thread's draws, flag the non-simple ones, list them.
 // Returns the draws through raws[].
-__device__ __forceinline__ void zig_generate(ZigShared& sh, const Jump& J, u64 s_hi, u64 s_lo, i64 seg_base,
-                                             u64 (&raws)[RNG_PER_THREAD]) {
+__device__ __forceinline__ void zig_generate(ZigShared& sh, const Jump& J, ulonglong2 b, u64 (&raws)[RNG_PER_THREAD]) {
   const int t = threadIdx.x;
-  u64 hi = s_hi, lo = s_lo;
-  jump_to(hi, lo, (u64)(seg_base + t) + 1, J);
+  u64 hi = b.x, lo = b.y;
+  jump_to(hi, lo, (u64)t + 1, J);
   const u64 mh = J.mh[8], ml = J.ml[8], ph = J.ph[8], pl = J.pl[8];
 #pragma unroll
   for (int j = 0; j < RNG_PER_THREAD; j++) {
@@ -188,13 +223,12 @@ __device__ __forceinline__ void zig_generate(ZigShared& sh, const Jump& J, u64 s
 }
 
 // Phase 2: one thread per listed position evaluates its attempt as if it started there (NumPyRNG.scala:139-157).
-__device__ __forceinline__ void zig_evaluate(ZigShared& sh, const Jump& J, u64 s_hi, u64 s_lo, i64 seg_base,
-                                             bool want_values) {
+__device__ __forceinline__ void zig_evaluate(ZigShared& sh, const Jump& J, ulonglong2 b, bool want_values) {
   int n = min(sh.nlist, ZIG_MAX_NS);
   for (int slot = threadIdx.x; slot < n; slot += RNG_THREADS) {
     int p = sh.lpos[slot];
-    u64 hi = s_hi, lo = s_lo;
-    jump_to(hi, lo, (u64)(seg_base + p) + 1, J);  // state whose output is draw p
+    u64 hi = b.x, lo = b.y;
+    jump_to(hi, lo, (u64)p + 1, J);  // state whose output is draw p
     int idx, sign;
     u64 rabs;
     zig_split(pcg_out(hi, lo), idx, sign, rabs);
@@ -209,7 +243,8 @@ __device__ __forceinline__ void zig_evaluate(ZigShared& sh, const Jump& J, u64 s
         lcg(hi, lo, J.mh[0], J.ml[0], J.ph[0], J.pl[0]);
         yy = -log1p(-u01(pcg_out(hi, lo)));
         consumed += 2;
-      } while (!(__dadd_rn(yy, yy) > __dmul_rn(xx, xx)) && consumed < 60000);
+      } while (!(__dadd_rn(yy, yy) > __dmul_rn(xx, xx)) && consumed < ZIG_MAX_CONS);
+      if (!(__dadd_rn(yy, yy) > __dmul_rn(xx, xx))) sh.overflow = 1;  // reported by the host, never silently wrong
       yields = true;
       val = ((rabs >> 8) & 1) ? -__dadd_rn(UM_ZIG_R, xx) : __dadd_rn(UM_ZIG_R, xx);
     } else {
@@ -228,6 +263,7 @@ __device__ __forceinline__ void zig_evaluate(ZigShared& sh, const Jump& J, u64 s
 
 // first non-simple position >= p (SEG if none)
 __device__ __forceinline__ int zig_next_ns(const ZigShared& sh, int p) {
+  if (p >= SEG) return SEG;
   int w = p >> 6;
   u64 m = sh.ns[w] & (~0ULL << (p & 63));
   while (m == 0) {
@@ -236,179 +272,375 @@ __device__ __forceinline__ int zig_next_ns(const ZigShared& sh, int p) {
   }
   return (w << 6) + __ffsll((long long)m) - 1;
 }
+__device__ __forceinline__ int zig_cons(const ZigShared& sh, int q) { return sh.cons[sh.slot_of[q]]; }
+__device__ __forceinline__ bool zig_bit(const u64* m, int p) { return (m[p >> 6] >> (p & 63)) & 1; }
 
-// Walk the chain of attempts from `entry`; returns the yields, the overshoot past the segment end in `exit_off`.
-template <bool MARK>
-__device__ __forceinline__ int zig_walk(ZigShared& sh, int entry, int& exit_off) {
-  int p = entry, count = 0;
-  while (p < SEG) {
-    int q = zig_next_ns(sh, p);
-    count += q - p;  // simple attempts: one draw, one value each
-    if (q >= SEG) { p = SEG; break; }
-    int c = sh.cons[sh.slot_of[q]];
-    count += (int)((sh.yes[q >> 6] >> (q & 63)) & 1);
-    if (MARK)
-      for (int k = q + 1; k < q + c && k < SEG; k++) sh.covered[k >> 6] |= 1ULL << (k & 63);
-    p = q + c;
+// non-simple flags of the 32 positions before q: bit i <-> position q - 32 + i (positions < 0 read as 0)
+__device__ __forceinline__ unsigned zig_window(const ZigShared& sh, int q) {
+  const int w = q >> 6, b = q & 63;
+  const u64 cur = sh.ns[w], prev = w > 0 ? sh.ns[w - 1] : 0ULL;
+  const u64 before = b == 0 ? prev : (prev >> b) | (cur << (64 - b));  // bit i <-> position q - 64 + i
+  return (unsigned)(before >> 32);
+}
+// HEAD: no earlier non-simple position could reach past q even if its attempt took place (draws consumed <= 32, so
+// 32 positions back is far enough) -> q starts an attempt whatever happened before.
+__device__ __forceinline__ bool zig_is_head(const ZigShared& sh, int q, int& prev_ns) {
+  unsigned win = zig_window(sh, q);
+  prev_ns = -1;
+  while (win) {
+    const int i = 31 - __clz(win);
+    const int r = q - 32 + i;
+    if (prev_ns < 0) prev_ns = r;
+    if (r + zig_cons(sh, r) > q) return false;
+    win &= ~(1u << i);
   }
-  exit_off = p - SEG;
-  return count;
+  return true;
+}
+// Does the chain of attempts that starts at position 0 start an attempt at the non-simple position q?
+// Walk back to the nearest head (a certain start), then replay the few attempts between it and q.
+__device__ __forceinline__ bool zig_starts_at(const ZigShared& sh, int q) {
+  int h = q, prev;
+  for (int guard = 0; guard < SEG; guard++) {
+    if (zig_is_head(sh, h, prev)) break;
+    h = prev;  // not a head: some non-simple position within 32 before h exists
+  }
+  int p = h;
+  while (p < q) p = zig_next_ns(sh, p + zig_cons(sh, p));
+  return p == q;
+}
+
+// W1 + W2: resolve the chain from entry 0 in parallel (one thread per non-simple position), leaving covered[], ym[],
+// reach.  Ends with a barrier.
+__device__ __forceinline__ void zig_chain0(ZigShared& sh) {
+  const int n = min(sh.nlist, ZIG_MAX_NS);
+  if (!sh.overflow) {
+    for (int slot = threadIdx.x; slot < n; slot += RNG_THREADS) {
+      const int q = sh.lpos[slot];
+      if (!zig_starts_at(sh, q)) continue;
+      const int c = sh.cons[slot];
+      for (int k = q + 1; k < q + c && k < SEG; k++) atomicOr(&sh.covered[k >> 6], 1ULL << (k & 63));
+      atomicMax(&sh.reach, q + c);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < SEG_WORDS) sh.ym[threadIdx.x] = ~sh.covered[threadIdx.x] & (~sh.ns[threadIdx.x] | sh.yes[threadIdx.x]);
+  __syncthreads();
+}
+
+// exclusive prefix popcounts of ym[] (prefix[SEG_WORDS] = total).  Called by every thread; ends with a barrier.
+__device__ __forceinline__ void zig_prefix(ZigShared& sh) {
+  static_assert(SEG_WORDS == 64, "two warps scan the 64 mask words");
+  const int t = threadIdx.x, lane = t & 31;
+  int c = 0, incl = 0;
+  if (t < SEG_WORDS) {
+    c = __popcll(sh.ym[t]);
+    incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (t == 31) sh.half = incl;
+  }
+  __syncthreads();
+  if (t < SEG_WORDS) {
+    const int excl = incl - c + (t >= 32 ? sh.half : 0);
+    sh.prefix[t] = excl;
+    if (t == SEG_WORDS - 1) sh.prefix[SEG_WORDS] = excl + c;
+  }
+  __syncthreads();
+}
+
+// The chain that ENTERS at position e (0 < e): walk it until it meets the chain from 0 (the first position it visits
+// that the 0-chain also starts at), which happens within a few positions.  Returns yields and exit offset for entry e.
+// FIX: rewrite ym[] for the positions before the meeting point (emit); prefix[] must be rebuilt afterwards.
+template <bool FIX>
+__device__ __forceinline__ int zig_enter(ZigShared& sh, int e, int& exit_off) {
+  const int exit0 = max(sh.reach, SEG) - SEG;
+  int p = e, cnt = 0;
+  if (FIX)
+    for (int k = 0; k < e; k++) sh.ym[k >> 6] &= ~(1ULL << (k & 63));
+  while (p < SEG && zig_bit(sh.covered, p)) {  // consumed by the 0-chain, but an attempt of this one
+    int step = 1, y = 1;
+    if (zig_bit(sh.ns, p)) { step = zig_cons(sh, p); y = (int)zig_bit(sh.yes, p); }
+    if (FIX) {
+      for (int k = p; k < p + step && k < SEG; k++) sh.ym[k >> 6] &= ~(1ULL << (k & 63));
+      if (y) sh.ym[p >> 6] |= 1ULL << (p & 63);
+    }
+    cnt += y;
+    p += step;
+  }
+  if (p >= SEG) { exit_off = p - SEG; return cnt; }
+  exit_off = exit0;
+  const int before = sh.prefix[p >> 6] + __popcll(sh.ym[p >> 6] & ((1ULL << (p & 63)) - 1));  // 0-chain yields in [0, p)
+  return cnt + sh.prefix[SEG_WORDS] - before;
 }
 
 __device__ __forceinline__ void zig_init_shared(ZigShared& sh) {
   for (int i = threadIdx.x; i < 256; i += RNG_THREADS) { sh.ki[i] = d_zig_ki[i]; sh.wi[i] = d_zig_wi[i]; }
   for (int i = threadIdx.x; i < SEG_WORDS; i += RNG_THREADS) { sh.yes[i] = 0; sh.covered[i] = 0; }
-  if (threadIdx.x == 0) { sh.nlist = 0; sh.overflow = 0; }
+  if (threadIdx.x == 0) { sh.nlist = 0; sh.overflow = 0; sh.reach = 0; }
   __syncthreads();
 }
 
 // table entry: yields | exit << 16 ; exit 0xff = unsupported (overshoot >= ZIG_ENTRIES or list overflow)
-__global__ void __launch_bounds__(RNG_THREADS) k_zig_scan(const __grid_constant__ Jump J, u64 s_hi, u64 s_lo,
-                                                         unsigned* __restrict__ table) {
+__global__ void __launch_bounds__(RNG_THREADS) k_zig_scan(const __grid_constant__ Jump J, const ulonglong2* __restrict__ bs,
+                                                         unsigned* __restrict__ table, u64* __restrict__ ym_all) {
   __shared__ ZigShared sh;
   zig_init_shared(sh);
-  const i64 seg_base = (i64)blockIdx.x * SEG;
+  const ulonglong2 b = bs[blockIdx.x];
   u64 raws[RNG_PER_THREAD];
-  zig_generate(sh, J, s_hi, s_lo, seg_base, raws);
+  zig_generate(sh, J, b, raws);
   __syncthreads();
-  zig_evaluate(sh, J, s_hi, s_lo, seg_base, false);
+  zig_evaluate(sh, J, b, false);
   __syncthreads();
+  zig_chain0(sh);
+  zig_prefix(sh);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + SEG_WORDS)  // the entry-0 yield mask, for k_zig_emit_fast
+    ym_all[(i64)blockIdx.x * SEG_WORDS + threadIdx.x - 64] = sh.ym[threadIdx.x - 64];
   if (threadIdx.x < ZIG_ENTRIES) {
     int ex = 0xff, cnt = 0;
-    if (!sh.overflow) {  // (a listed position without a slot has no consumption record to walk over)
-      cnt = zig_walk<false>(sh, threadIdx.x, ex);
+    if (!sh.overflow) {
+      if (threadIdx.x == 0) { cnt = sh.prefix[SEG_WORDS]; ex = max(sh.reach, SEG) - SEG; }
+      else cnt = zig_enter<false>(sh, threadIdx.x, ex);
       if (ex >= ZIG_ENTRIES) ex = 0xff;
     }
     table[(i64)blockIdx.x * ZIG_ENTRIES + threadIdx.x] = (unsigned)cnt | ((unsigned)ex << 16);
   }
 }
 
-// result block written by k_zig_prefix / k_zig_emit: [0] total yields of all segments, [1] exit offset of the last
-// segment, [2] error flag, [3] stream position right after the draw that completed output n_out-1 (emit)
-constexpr int PREFIX_THREADS = 1024;
-struct PrefixShared {
-  i64 cnt[PREFIX_THREADS][ZIG_ENTRIES];
-  i64 base[PREFIX_THREADS];
-  unsigned char exit_[PREFIX_THREADS][ZIG_ENTRIES];
-  unsigned char entry[PREFIX_THREADS];
-  int err;
+// result block written by the prefix kernels / k_zig_emit*: [0] total yields of all segments, [1] exit offset of the
+// last segment, [2] error flag, [3] stream position right after the draw that completed output n_out-1 (emit)
+//
+// Prefix over segments of the maps e -> (exit, yields): (1) k_zig_pf_reduce: a thread composes PF_RUN consecutive
+// segments for all 16 entries, 16 threads then compose the block's 256 thread maps -> one map per block;
+// (2) k_zig_pf_scan: one thread chains the block maps (staged through shared memory) -> every block's entry + base;
+// (3) k_zig_pf_apply: the block rebuilds its thread maps, chains them from its entry, and every thread replays its run.
+constexpr int PF_THREADS = 256;
+constexpr int PF_RUN = 8;
+constexpr int PF_SPAN = PF_THREADS * PF_RUN;  // segments per block
+struct PfShared {
+  unsigned cnt[PF_THREADS][ZIG_ENTRIES + 1];  // yields of a thread's run, per entry (<= 8 * 4096); padded against bank conflicts
+  unsigned char ex[PF_THREADS][ZIG_ENTRIES];
+  i64 tbase[PF_THREADS];
+  unsigned char tentry[PF_THREADS];
 };
-__device__ __forceinline__ void load_row(const unsigned* __restrict__ table, i64 s, unsigned (&row)[ZIG_ENTRIES]) {
-  const uint4* r = reinterpret_cast<const uint4*>(table + s * ZIG_ENTRIES);
+struct BlockMap {
+  i64 cnt[ZIG_ENTRIES];
+  int ex[ZIG_ENTRIES];
+};
+// this thread's run of segments -> sh.cnt[t][*], sh.ex[t][*]; ends with a barrier
+__device__ __forceinline__ void pf_thread_maps(PfShared& sh, const unsigned* __restrict__ table, i64 nseg) {
+  const int t = threadIdx.x;
+  const i64 s0 = min(((i64)blockIdx.x * PF_THREADS + t) * PF_RUN, nseg), s1 = min(s0 + PF_RUN, nseg);
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    uint4 v = __ldg(r + q);
-    row[4 * q] = v.x; row[4 * q + 1] = v.y; row[4 * q + 2] = v.z; row[4 * q + 3] = v.w;
+  for (int e = 0; e < ZIG_ENTRIES; e++) {
+    int cur = e;
+    unsigned cnt = 0;
+    for (i64 sg = s0; sg < s1 && cur != 0xff; sg++) {
+      const unsigned v = __ldg(table + sg * ZIG_ENTRIES + cur);  // the 16 chains share the row's two sectors
+      cnt += v & 0xffff;
+      cur = (int)(v >> 16);
+    }
+    sh.cnt[t][e] = cnt;
+    sh.ex[t][e] = (unsigned char)cur;
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(PF_THREADS) k_zig_pf_reduce(const unsigned* __restrict__ table, i64 nseg,
+                                                             BlockMap* __restrict__ maps) {
+  __shared__ PfShared sh;
+  pf_thread_maps(sh, table, nseg);
+  if (threadIdx.x < ZIG_ENTRIES) {
+    int cur = threadIdx.x;
+    i64 total = 0;
+    for (int k = 0; k < PF_THREADS && cur != 0xff; k++) {
+      total += sh.cnt[k][cur];
+      cur = sh.ex[k][cur];
+    }
+    maps[blockIdx.x].cnt[threadIdx.x] = total;
+    maps[blockIdx.x].ex[threadIdx.x] = cur;
   }
 }
-// One block.  Thread t owns a run of consecutive segments: (A) the run's map e -> (exit, yields) for all 16 entry
-// offsets, (B) thread 0 chains the 1024 run maps, (C) every thread replays its run from its true entry.  The table
-// rows are fetched whole (their address does not depend on the chain), so the loads pipeline.
-__global__ void __launch_bounds__(PREFIX_THREADS) k_zig_prefix(const unsigned* __restrict__ table, i64 nseg,
-                                                               unsigned char* __restrict__ seg_entry,
-                                                               i64* __restrict__ seg_base_out, i64* __restrict__ result) {
-  extern __shared__ __align__(16) unsigned char prefix_smem[];
-  PrefixShared& sh = *reinterpret_cast<PrefixShared*>(prefix_smem);
-  const int t = threadIdx.x;
-  if (t == 0) sh.err = 0;
-  const i64 run = (nseg + PREFIX_THREADS - 1) / PREFIX_THREADS;
-  const i64 s0 = min((i64)t * run, nseg), s1 = min(s0 + run, nseg);
-  {
-    int cur[ZIG_ENTRIES];
-    i64 cnt[ZIG_ENTRIES];
-#pragma unroll
-    for (int e = 0; e < ZIG_ENTRIES; e++) { cur[e] = e; cnt[e] = 0; }
-#pragma unroll 2
-    for (i64 s = s0; s < s1; s++) {
-      unsigned row[ZIG_ENTRIES];
-      load_row(table, s, row);
-#pragma unroll
-      for (int e = 0; e < ZIG_ENTRIES; e++) {
-        if (cur[e] != 0xff) {
-          unsigned v = row[cur[e]];
-          cnt[e] += v & 0xffff;
-          cur[e] = (int)(v >> 16);
-        }
+struct BlockStart {
+  i64 base;
+  int entry;
+  int pad;
+};
+__global__ void __launch_bounds__(128) k_zig_pf_scan(const BlockMap* __restrict__ maps, int nblocks, BlockStart* __restrict__ starts,
+                                                    i64* __restrict__ result) {
+  constexpr int STAGE = 128;
+  __shared__ BlockMap stage[STAGE];
+  __shared__ int s_cur;
+  __shared__ i64 s_total;
+  if (threadIdx.x == 0) { s_cur = 0; s_total = 0; }
+  for (int b0 = 0; b0 < nblocks; b0 += STAGE) {
+    const int nb = min(STAGE, nblocks - b0);
+    __syncthreads();
+    const int words = nb * (int)(sizeof(BlockMap) / 8);
+    for (int i = threadIdx.x; i < words; i += blockDim.x)
+      reinterpret_cast<i64*>(stage)[i] = reinterpret_cast<const i64*>(maps + b0)[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int cur = s_cur;
+      i64 total = s_total;
+      for (int k = 0; k < nb; k++) {
+        starts[b0 + k].base = total;
+        starts[b0 + k].entry = cur;
+        if (cur != 0xff) { total += stage[k].cnt[cur]; cur = stage[k].ex[cur]; }
       }
+      s_cur = cur;
+      s_total = total;
     }
-#pragma unroll
-    for (int e = 0; e < ZIG_ENTRIES; e++) { sh.cnt[t][e] = cnt[e]; sh.exit_[t][e] = (unsigned char)cur[e]; }
   }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    result[0] = s_total;
+    result[1] = s_cur;
+    result[2] = s_cur == 0xff ? 1 : 0;
+  }
+}
+__global__ void __launch_bounds__(PF_THREADS) k_zig_pf_apply(const unsigned* __restrict__ table, i64 nseg,
+                                                            const BlockStart* __restrict__ starts,
+                                                            unsigned char* __restrict__ seg_entry, i64* __restrict__ seg_base_out,
+                                                            const i64* __restrict__ result) {
+  __shared__ PfShared sh;
+  if (result[2]) return;
+  pf_thread_maps(sh, table, nseg);
+  const int t = threadIdx.x;
   if (t == 0) {
-    int cur = 0, err = 0;
-    i64 total = 0;
-    for (int k = 0; k < PREFIX_THREADS; k++) {
-      sh.entry[k] = (unsigned char)cur;
-      sh.base[k] = total;
-      if (cur == 0xff) { err = 1; continue; }
-      total += sh.cnt[k][cur];
-      cur = sh.exit_[k][cur];
+    int cur = starts[blockIdx.x].entry;
+    i64 base = starts[blockIdx.x].base;
+    for (int k = 0; k < PF_THREADS; k++) {
+      sh.tentry[k] = (unsigned char)cur;
+      sh.tbase[k] = base;
+      base += sh.cnt[k][cur];
+      cur = sh.ex[k][cur];
     }
-    if (cur == 0xff) err = 1;
-    sh.err = err;
-    result[0] = total;
-    result[1] = cur;
-    result[2] = err;
   }
   __syncthreads();
-  if (sh.err) return;
-  int cur = sh.entry[t];
-  i64 base = sh.base[t];
-#pragma unroll 2
-  for (i64 s = s0; s < s1; s++) {
-    unsigned row[ZIG_ENTRIES];
-    load_row(table, s, row);
-    seg_entry[s] = (unsigned char)cur;
-    seg_base_out[s] = base;
-    unsigned v = row[cur];
+  const i64 s0 = min(((i64)blockIdx.x * PF_THREADS + t) * PF_RUN, nseg), s1 = min(s0 + PF_RUN, nseg);
+  int cur = sh.tentry[t];
+  i64 base = sh.tbase[t];
+  for (i64 sg = s0; sg < s1; sg++) {
+    seg_entry[sg] = (unsigned char)cur;
+    seg_base_out[sg] = base;
+    const unsigned v = __ldg(table + sg * ZIG_ENTRIES + cur);
     base += v & 0xffff;
     cur = (int)(v >> 16);
   }
 }
 
-__global__ void __launch_bounds__(RNG_THREADS, 3) k_zig_emit(const __grid_constant__ Jump J, u64 s_hi, u64 s_lo,
+// Emission, common case (the segment is entered at its first position): the yield mask k_zig_scan stored is all that
+// is needed -- regenerate the draws and store each value at base + rank.  Tail draws (about one per segment) are
+// recomputed in place.
+__global__ void __launch_bounds__(RNG_THREADS) k_zig_emit_fast(const __grid_constant__ Jump J, const ulonglong2* __restrict__ bs,
+                                                              const unsigned char* __restrict__ seg_entry,
+                                                              const i64* __restrict__ seg_base_in, const u64* __restrict__ ym_all,
+                                                              double* __restrict__ out, i64 n_out, double mean, double sd,
+                                                              int affine, i64* __restrict__ result) {
+  __shared__ u64 s_ki[256];
+  __shared__ double s_wi[256];
+  __shared__ u64 s_ym[SEG_WORDS];
+  __shared__ int s_prefix[SEG_WORDS + 1];
+  __shared__ int s_half;
+  if (result[2]) return;
+  if (seg_entry[blockIdx.x] != 0) return;  // k_zig_emit handles it
+  const i64 out_base = seg_base_in[blockIdx.x];
+  if (out_base >= n_out) return;
+  const int t = threadIdx.x, lane = t & 31;
+  s_ki[t] = d_zig_ki[t];
+  s_wi[t] = d_zig_wi[t];
+  int c = 0, incl = 0;
+  if (t < SEG_WORDS) {
+    const u64 m = ym_all[(i64)blockIdx.x * SEG_WORDS + t];
+    s_ym[t] = m;
+    c = __popcll(m);
+    incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (t == 31) s_half = incl;
+  }
+  __syncthreads();
+  if (t < SEG_WORDS) s_prefix[t] = incl - c + (t >= 32 ? s_half : 0);
+  __syncthreads();
+  const ulonglong2 b = bs[blockIdx.x];
+  u64 hi = b.x, lo = b.y;
+  jump_to(hi, lo, (u64)t + 1, J);
+  const u64 mh = J.mh[8], ml = J.ml[8], ph = J.ph[8], pl = J.pl[8];
+#pragma unroll 4
+  for (int j = 0; j < RNG_PER_THREAD; j++) {
+    const int p = j * RNG_THREADS + t;
+    const u64 raw = pcg_out(hi, lo);
+    const u64 ym = s_ym[p >> 6];
+    const i64 o = out_base + s_prefix[p >> 6] + __popcll(ym & ((1ULL << (p & 63)) - 1));
+    if (((ym >> (p & 63)) & 1) && o < n_out) {
+      int idx, sign;
+      u64 rabs;
+      zig_split(raw, idx, sign, rabs);
+      double v = zig_x(rabs, s_wi[idx], sign);
+      int consumed = 1;
+      if (!(rabs < s_ki[idx])) {
+        consumed = 2;  // an accepted wedge attempt
+        if (idx == 0) {  // tail: replay its draws (NumPyRNG.scala:142-151)
+          u64 th = hi, tl = lo;
+          double xx, yy;
+          consumed = 1;
+          do {
+            lcg(th, tl, J.mh[0], J.ml[0], J.ph[0], J.pl[0]);
+            xx = -UM_ZIG_INV_R * log1p(-u01(pcg_out(th, tl)));
+            lcg(th, tl, J.mh[0], J.ml[0], J.ph[0], J.pl[0]);
+            yy = -log1p(-u01(pcg_out(th, tl)));
+            consumed += 2;
+          } while (!(__dadd_rn(yy, yy) > __dmul_rn(xx, xx)) && consumed < ZIG_MAX_CONS);
+          v = ((rabs >> 8) & 1) ? -__dadd_rn(UM_ZIG_R, xx) : __dadd_rn(UM_ZIG_R, xx);
+        }
+      }
+      if (affine) v = __dadd_rn(mean, __dmul_rn(sd, v));  // mean + std * rng.randn(), Mat.scala:1500-1507
+      out[o] = v;
+      if (o == n_out - 1) result[3] = (i64)blockIdx.x * SEG + p + consumed;
+    }
+    lcg(hi, lo, mh, ml, ph, pl);
+  }
+}
+
+__global__ void __launch_bounds__(RNG_THREADS, 3) k_zig_emit(const __grid_constant__ Jump J, const ulonglong2* __restrict__ bs,
                                                          const unsigned char* __restrict__ seg_entry,
                                                          const i64* __restrict__ seg_base_in, double* __restrict__ out,
                                                          i64 n_out, double mean, double sd, int affine,
                                                          i64* __restrict__ result) {
   __shared__ ZigShared sh;
-  if (result[2]) return;  // k_zig_prefix met a segment it cannot chain: the host reports it
+  if (result[2]) return;  // the prefix met a segment it cannot chain: the host reports it
+  if (seg_entry[blockIdx.x] == 0) return;  // k_zig_emit_fast handles it
   const i64 out_base = seg_base_in[blockIdx.x];
   if (out_base >= n_out) return;  // whole segment lies past the last wanted element
   zig_init_shared(sh);
   const i64 seg_base = (i64)blockIdx.x * SEG;
   const int entry = seg_entry[blockIdx.x];
   const int t = threadIdx.x;
+  const ulonglong2 b = bs[blockIdx.x];
   u64 raws[RNG_PER_THREAD];
-  zig_generate(sh, J, s_hi, s_lo, seg_base, raws);
+  zig_generate(sh, J, b, raws);
   __syncthreads();
-  zig_evaluate(sh, J, s_hi, s_lo, seg_base, true);
+  zig_evaluate(sh, J, b, true);
   __syncthreads();
-  if (t == 0) {
-    int ex;
-    zig_walk<true>(sh, entry, ex);
+  zig_chain0(sh);
+  if (entry > 0) {  // block-uniform
+    zig_prefix(sh);
+    if (t == 0) {
+      int ex;
+      zig_enter<true>(sh, entry, ex);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  // yielding positions: started (>= entry, not covered) and (simple or accepted)
-  if (t < SEG_WORDS) {
-    u64 m = ~sh.covered[t] & (~sh.ns[t] | sh.yes[t]);
-    int lo_bit = entry - t * 64;
-    if (lo_bit >= 64) m = 0;
-    else if (lo_bit > 0) m &= ~0ULL << lo_bit;
-    sh.covered[t] = m;  // reuse: now the yield mask
-  }
-  __syncthreads();
-  if (t == 0) {
-    int acc = 0;
-    for (int w = 0; w < SEG_WORDS; w++) { sh.prefix[w] = acc; acc += __popcll(sh.covered[w]); }
-    sh.prefix[SEG_WORDS] = acc;
-  }
-  __syncthreads();
+  zig_prefix(sh);
 #pragma unroll
   for (int j = 0; j < RNG_PER_THREAD; j++) {
     const int p = j * RNG_THREADS + t;
-    const u64 ym = sh.covered[p >> 6];
+    const u64 ym = sh.ym[p >> 6];
     if (!((ym >> (p & 63)) & 1)) continue;
     const i64 o = out_base + sh.prefix[p >> 6] + __popcll(ym & ((1ULL << (p & 63)) - 1));
     if (o >= n_out) continue;
@@ -468,6 +700,13 @@ inline uint32_t ss_mix(uint32_t x, uint32_t y) {
   return r;
 }
 
+int launch_block_states(const Jump& J, const um_rng* g, i64 nblocks, int log2_span, ulonglong2* bs) {
+  i64 threads = (nblocks + BS_CHUNK - 1) / BS_CHUNK;
+  k_rng_block_states<<<(unsigned)((threads + 127) / 128), 128, 0, ctx()->stream>>>(J, g->state_hi, g->state_lo, nblocks, log2_span, bs);
+  UM_LAUNCHED();
+  return UM_OK;
+}
+
 template <int KIND>
 int draw_impl(um_rng* g, const um_view* dst, double low, double span, int ilow, unsigned ibound, const char* what) {
   UM_CTX();
@@ -492,11 +731,15 @@ int draw_impl(um_rng* g, const um_view* dst, double low, double span, int ilow, 
     n_raw = (n + 1) / 2;
   }
   Jump J = make_jump(inc_of(g));
-  i64 blocks = (n_raw + SEG - 1) / SEG;
+  i64 blocks = (n_raw + DRAW_SPAN - 1) / DRAW_SPAN;
   if (blocks == 0) blocks = 1;  // only the cached element
   if (blocks > 0x7fffffffLL) return fail(UM_ERR_ARG, "%s: %lld elements exceed one launch", what, (long long)n);
-  k_rng_draw<KIND><<<(unsigned)blocks, RNG_THREADS, 0, ctx()->stream>>>(J, g->state_hi, g->state_lo, n_raw, outd, outi, n, low, span,
-                                                                        ilow, ibound, pre_flag, pre_val);
+  ulonglong2* bs = static_cast<ulonglong2*>(scratch((size_t)blocks * sizeof(ulonglong2)));
+  if (!bs) return UM_ERR_OOM;
+  int s0 = launch_block_states(J, g, blocks, DRAW_LOG2_SPAN, bs);
+  if (s0 != UM_OK) return s0;
+  k_rng_draw<KIND><<<(unsigned)blocks, RNG_THREADS, 0, ctx()->stream>>>(J, bs, n_raw, outd, outi, n, low, span, ilow, ibound, pre_flag,
+                                                                        pre_val);
   UM_LAUNCHED();
   u128 s2 = advance(st_of(g), inc_of(g), (u64)n_raw);
   if (KIND == DRAW_INT && (n & 1)) {
@@ -524,23 +767,41 @@ int randn_impl(um_rng* g, const um_view* dst, double mean, double sd, int affine
     // 1.0173 draws per value on average; 3 % + two segments of margin makes a second round rare
     i64 nseg = (i64)((double)n * 1.03 / SEG) + 2;
     if (nseg > 0x7fffffffLL) return fail(UM_ERR_ARG, "%s: too many elements for one call", what);
-    size_t tab_bytes = (size_t)nseg * ZIG_ENTRIES * sizeof(unsigned);
-    size_t base_off = (tab_bytes + 255) & ~(size_t)255;
-    size_t entry_off = base_off + (((size_t)nseg * sizeof(i64) + 255) & ~(size_t)255);
-    size_t res_off = entry_off + (((size_t)nseg + 255) & ~(size_t)255);
-    char* ws = static_cast<char*>(scratch(res_off + 64));
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const int pf_blocks = (int)((nseg + PF_SPAN - 1) / PF_SPAN);
+    size_t off = 0;
+    const size_t tab_off = off; off += up((size_t)nseg * ZIG_ENTRIES * sizeof(unsigned));
+    const size_t base_off = off; off += up((size_t)nseg * sizeof(i64));
+    const size_t entry_off = off; off += up((size_t)nseg);
+    const size_t bs_off = off; off += up((size_t)nseg * sizeof(ulonglong2));
+    const size_t ym_off = off; off += up((size_t)nseg * SEG_WORDS * sizeof(u64));
+    const size_t map_off = off; off += up((size_t)pf_blocks * sizeof(BlockMap));
+    const size_t start_off = off; off += up((size_t)pf_blocks * sizeof(BlockStart));
+    const size_t res_off = off; off += 64;
+    char* ws = static_cast<char*>(scratch(off));
     if (!ws) return UM_ERR_OOM;
-    unsigned* table = reinterpret_cast<unsigned*>(ws);
+    unsigned* table = reinterpret_cast<unsigned*>(ws + tab_off);
     i64* seg_base = reinterpret_cast<i64*>(ws + base_off);
     unsigned char* seg_entry = reinterpret_cast<unsigned char*>(ws + entry_off);
+    ulonglong2* bs = reinterpret_cast<ulonglong2*>(ws + bs_off);
+    u64* ym_all = reinterpret_cast<u64*>(ws + ym_off);
+    BlockMap* maps = reinterpret_cast<BlockMap*>(ws + map_off);
+    BlockStart* starts = reinterpret_cast<BlockStart*>(ws + start_off);
     i64* result = reinterpret_cast<i64*>(ws + res_off);
     UM_CUDA(cudaMemsetAsync(result, 0, 64, st));
-    k_zig_scan<<<(unsigned)nseg, RNG_THREADS, 0, st>>>(J, g->state_hi, g->state_lo, table);
+    s = launch_block_states(J, g, nseg, 12, bs);
+    if (s != UM_OK) return s;
+    k_zig_scan<<<(unsigned)nseg, RNG_THREADS, 0, st>>>(J, bs, table, ym_all);
     UM_LAUNCHED();
-    UM_CUDA(cudaFuncSetAttribute(k_zig_prefix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrefixShared)));
-    k_zig_prefix<<<1, PREFIX_THREADS, sizeof(PrefixShared), st>>>(table, nseg, seg_entry, seg_base, result);
+    k_zig_pf_reduce<<<pf_blocks, PF_THREADS, 0, st>>>(table, nseg, maps);
     UM_LAUNCHED();
-    k_zig_emit<<<(unsigned)nseg, RNG_THREADS, 0, st>>>(J, g->state_hi, g->state_lo, seg_entry, seg_base, out, n, mean, sd, affine, result);
+    k_zig_pf_scan<<<1, 128, 0, st>>>(maps, pf_blocks, starts, result);
+    UM_LAUNCHED();
+    k_zig_pf_apply<<<pf_blocks, PF_THREADS, 0, st>>>(table, nseg, starts, seg_entry, seg_base, result);
+    UM_LAUNCHED();
+    k_zig_emit_fast<<<(unsigned)nseg, RNG_THREADS, 0, st>>>(J, bs, seg_entry, seg_base, ym_all, out, n, mean, sd, affine, result);
+    UM_LAUNCHED();
+    k_zig_emit<<<(unsigned)nseg, RNG_THREADS, 0, st>>>(J, bs, seg_entry, seg_base, out, n, mean, sd, affine, result);
     UM_LAUNCHED();
     i64 res[4];
     UM_CUDA(cudaMemcpyAsync(res, result, sizeof(res), cudaMemcpyDeviceToHost, st));
