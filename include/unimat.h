@@ -139,6 +139,28 @@ int32_t um_rng_randn(um_rng* g, const um_view* dst);                            
 int32_t um_rng_normal(um_rng* g, double mean, double sd, const um_view* dst);    /* MatD.normal   Mat.scala:1500 */
 int32_t um_rng_randint(um_rng* g, int32_t low, int32_t high, const um_view* dst_i32); /* MatD.randint Mat.scala:1525 */
 
+/* ---- on-disk format -----------------------------------------------------------------
+ * `path.loadMatD` / `loadSmartD` / `loadMatF` (ext/PathExts.scala:583-590 -> io/FileOps.scala:139-188): CSV text ->
+ * matrix.  The text is parsed on the host (all cores) into a staging table, then uploaded with one copy; two steps
+ * because the caller owns the result buffer.  Cell = `big(s).toDouble` (data/Big.scala:59-64: trim, drop ',' and '$',
+ * trailing '%' divides by 100, java.math.BigDecimal grammar, anything else NaN); rows without content dropped and
+ * rows padded to the widest (io/FastCsv.scala:21,35-41); header = row 0 all non-numeric and row 1 has a numeric cell
+ * (FileOps.scala:154-166), blank header names become colN (:117-121).  `delimiter` 0 = pick the most frequent of
+ * , TAB ; | on the first content line (the reference's statistical detector io/Delimiter.scala is not reproduced). */
+int32_t um_csv_open(const char* path, int32_t delimiter, uint64_t* handle, int64_t* rows, int64_t* cols, int32_t* has_header);
+int32_t um_csv_header(uint64_t handle, int64_t col, char* buf, int64_t buflen);
+int32_t um_csv_read_host(uint64_t handle, double* dst, int64_t count);       /* the parsed table, row-major (host) */
+int32_t um_csv_upload(uint64_t handle, const um_view* dst);                  /* f64, or f32 (loadMatF: toDouble.toFloat) */
+int32_t um_csv_close(uint64_t handle);
+/* `m.saveCSV(path, sep, nanAs)` (data/Mat.scala:90-116): NaN -> nanAs, +-Infinity -> Inf / -Inf, other cells
+ * String.valueOf: java.lang.Double/Float.toString layout (shortest round-trip digits, JDK 19+), Int decimal, Boolean
+ * true/false; rows end with '\n'.  `m` must be contiguous (materialise views first). */
+int32_t um_csv_save(const um_view* m, const char* path, const char* sep, const char* nan_as);
+/* host-only helpers: one cell of saveCSV / loadMatD */
+int32_t um_csv_format_f64(double v, const char* nan_as, char* buf, int64_t buflen);
+int32_t um_csv_format_f32(float v, const char* nan_as, char* buf, int64_t buflen);
+int32_t um_csv_parse_cell(const char* text, double* out);
+
 /* ---- elementwise (Mat.scala:1989-2102 Mat(+)Mat, :2154-2209,:2514-2531 Mat(+)scalar,
  *      :1416-1419 scalar(+)Mat, :4513-4588 in-place family = `out` aliasing `a`) ------ */
 typedef enum um_binop { UM_ADD = 0, UM_SUB = 1, UM_MUL = 2, UM_DIV = 3, UM_MAXIMUM = 4, UM_MINIMUM = 5,

@@ -8,9 +8,11 @@ from ._lib import (EmptyMatrixError, SingularMatrixError, UnimatError, device_co
 from .mat import Mat, MatD, MatF, init, set_matf_matmul_path, sync
 from . import tprf3
 from . import rng
+from . import io
+from .io import MatResult, loadMatD, loadMatF, loadSmartD, saveCSV
 from .rng import NumPyRNG
 from .tprf3 import Pls3prfModel, Tprf3Result, estimate3prf, forecast3prf, pls1Fit, plsClosedForm, t3prf, tprfClosedForm
 
 __all__ = ["Mat", "MatD", "MatF", "init", "sync", "set_matf_matmul_path", "tprf3", "Tprf3Result", "estimate3prf", "forecast3prf",
-           "t3prf", "tprfClosedForm", "plsClosedForm", "pls1Fit", "Pls3prfModel", "NumPyRNG", "rng", "device_count", "launch_count", "EmptyMatrixError",
+           "t3prf", "tprfClosedForm", "plsClosedForm", "pls1Fit", "Pls3prfModel", "NumPyRNG", "rng", "io", "MatResult", "loadMatD", "loadMatF", "loadSmartD", "saveCSV", "device_count", "launch_count", "EmptyMatrixError",
            "SingularMatrixError", "UnimatError"]

@@ -118,6 +118,15 @@ SIGNATURES = {
     "um_rng_randn": (_i32, [_vp, VP]),
     "um_rng_normal": (_i32, [_vp, _f64, _f64, VP]),
     "um_rng_randint": (_i32, [_vp, _i32, _i32, VP]),
+    "um_csv_open": (_i32, [C.c_char_p, _i32, C.POINTER(C.c_uint64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32)]),
+    "um_csv_header": (_i32, [C.c_uint64, _i64, C.c_char_p, _i64]),
+    "um_csv_read_host": (_i32, [C.c_uint64, _vp, _i64]),
+    "um_csv_upload": (_i32, [C.c_uint64, VP]),
+    "um_csv_close": (_i32, [C.c_uint64]),
+    "um_csv_save": (_i32, [VP, C.c_char_p, C.c_char_p, C.c_char_p]),
+    "um_csv_format_f64": (_i32, [_f64, C.c_char_p, C.c_char_p, _i64]),
+    "um_csv_format_f32": (_i32, [C.c_float, C.c_char_p, C.c_char_p, _i64]),
+    "um_csv_parse_cell": (_i32, [C.c_char_p, C.POINTER(_f64)]),
     "um_get": (_i32, [VP, _i64, _i64, C.POINTER(_f64)]),
     "um_set": (_i32, [VP, _i64, _i64, _f64]),
     "um_binary": (_i32, [_i32, VP, VP, VP]),

@@ -507,6 +507,12 @@ class Mat:
     matmulPure = matmul   # the device has one route; both escape hatches land on it
     matmulBlas = matmul
 
+    def saveCSV(self, path, sep: str = ",", nanAs: str = "NaN") -> None:  # Mat.scala:90-116
+        from . import io
+        io.saveCSV(self, path, sep, nanAs)
+
+    writeCsv = saveCSV
+
     def inverse(self) -> "Mat":  # Mat.scala:2979-3006
         if self.rows != self.cols:
             raise ValueError(f"inverse requires square matrix, got {self.shape}")
