@@ -124,6 +124,45 @@ object DeviceMat:
     val off = Arena.ofAuto().allocate(data.length.toLong * 8); off.copyFrom(seg)
     check(um_h2d.invoke(m.buf.ptr, off, data.length.toLong * 8).asInstanceOf[Int]); m
 
+/** The global NumPy-compatible generator on the device (Mat.scala:1461-1530: setSeed / rand / randn / normal /
+ *  uniform / randint over data/NumPyRNG.scala).  The 40-byte `um_rng` state sits where `globalRNG` sits today; every
+ *  fill consumes the PCG64 stream exactly as the sequential loops do, so seeded programs print the same numbers. */
+object DeviceRandom:
+  @volatile private var g: MemorySegment = seeded(0L)                       // lazy val defaultRNG = new NumPyRNG(0)
+  private def seeded(seed: Long): MemorySegment =
+    val s = Arena.ofAuto().allocate(RNG); check(um_rng_seed.invoke(s, seed).asInstanceOf[Int]); s   // seed < 0 -> IllegalArgumentException
+  def setSeed(seed: Long): Unit = g = seeded(seed)
+  def rand(rows: Int, cols: Int): DeviceMat =
+    val o = DeviceMat.alloc(rows, cols); check(um_rng_rand.invoke(g, o.view).asInstanceOf[Int]); o
+  def randn(rows: Int, cols: Int = 1): DeviceMat =
+    val o = DeviceMat.alloc(rows, cols); check(um_rng_randn.invoke(g, o.view).asInstanceOf[Int]); o
+  def normal(mean: Double, std: Double, rows: Int, cols: Int): DeviceMat =
+    val o = DeviceMat.alloc(rows, cols); check(um_rng_normal.invoke(g, mean, std, o.view).asInstanceOf[Int]); o
+  def uniform(low: Double, high: Double, rows: Int, cols: Int): DeviceMat =
+    val o = DeviceMat.alloc(rows, cols); check(um_rng_uniform.invoke(g, low, high, o.view).asInstanceOf[Int]); o
+  def randint(low: Int, high: Int, rows: Int, cols: Int): DeviceMat =
+    val o = DeviceMat.alloc(rows, cols, DType.I32); check(um_rng_randint.invoke(g, low, high, o.view).asInstanceOf[Int]); o
+
+/** `path.loadMatD` / `m.saveCSV` (ext/PathExts.scala:583-590, io/FileOps.scala:139-188, Mat.scala:90-116). */
+object DeviceCsv:
+  def loadSmartD(path: String, delimiter: Char = 0): (Vector[String], DeviceMat) =
+    val a = Arena.ofAuto()
+    val h = a.allocate(JAVA_LONG); val r = a.allocate(JAVA_LONG); val c = a.allocate(JAVA_LONG); val hd = a.allocate(JAVA_INT)
+    check(um_csv_open.invoke(a.allocateFrom(path), delimiter.toInt, h, r, c, hd).asInstanceOf[Int])
+    val handle = h.get(JAVA_LONG, 0)
+    try
+      val m = DeviceMat.alloc(r.get(JAVA_LONG, 0), c.get(JAVA_LONG, 0))
+      check(um_csv_upload.invoke(handle, m.view).asInstanceOf[Int])
+      val buf = a.allocate(4096)
+      val headers = if hd.get(JAVA_INT, 0) == 0 then Vector.empty else Vector.tabulate(m.cols.toInt) { j =>
+        check(um_csv_header.invoke(handle, j.toLong, buf, 4096L).asInstanceOf[Int]); buf.getString(0) }
+      (headers, m)
+    finally um_csv_close.invoke(handle)
+  def loadMatD(path: String): DeviceMat = loadSmartD(path)._2
+  def saveCSV(m: DeviceMat, path: String, sep: String = ",", nanAs: String = "NaN"): Unit =
+    val a = Arena.ofAuto()
+    check(um_csv_save.invoke(m.view, a.allocateFrom(path), a.allocateFrom(sep), a.allocateFrom(nanAs)).asInstanceOf[Int])
+
 /** `uni.stats.Tprf3` on the device (Tprf3.scala:199-289, 1056-1110). */
 object DeviceTprf3:
   final case class Result(forecasts: DeviceMat, residuals: DeviceMat, rSquared: Double, alpha: Option[DeviceMat])

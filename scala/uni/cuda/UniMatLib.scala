@@ -91,6 +91,25 @@ object UniMatLib:
   val um_comm_init      = h("um_comm_init", I(JAVA_INT, JAVA_INT, ADDRESS))
   val um_comm_destroy   = h("um_comm_destroy", I())
 
+  // ---- NumPy-compatible PCG64 generator (data/NumPyRNG.scala, Mat.scala:1461-1530) and CSV ingest / egress
+  // struct um_rng { uint64 state_hi, state_lo, inc_hi, inc_lo; int32 has_uint32; uint32 uinteger; }  (40 bytes)
+  val RNG: StructLayout = MemoryLayout.structLayout(
+    JAVA_LONG.withName("state_hi"), JAVA_LONG.withName("state_lo"), JAVA_LONG.withName("inc_hi"), JAVA_LONG.withName("inc_lo"),
+    JAVA_INT.withName("has_uint32"), JAVA_INT.withName("uinteger"))
+  val um_rng_seed     = h("um_rng_seed", I(ADDRESS, JAVA_LONG))
+  val um_rng_advance  = h("um_rng_advance", I(ADDRESS, JAVA_LONG))
+  val um_rng_next_u64 = h("um_rng_next_u64", I(ADDRESS, ADDRESS))
+  val um_rng_rand     = h("um_rng_rand", I(ADDRESS, ADDRESS))
+  val um_rng_uniform  = h("um_rng_uniform", I(ADDRESS, JAVA_DOUBLE, JAVA_DOUBLE, ADDRESS))
+  val um_rng_randn    = h("um_rng_randn", I(ADDRESS, ADDRESS))
+  val um_rng_normal   = h("um_rng_normal", I(ADDRESS, JAVA_DOUBLE, JAVA_DOUBLE, ADDRESS))
+  val um_rng_randint  = h("um_rng_randint", I(ADDRESS, JAVA_INT, JAVA_INT, ADDRESS))
+  val um_csv_open     = h("um_csv_open", I(ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS))
+  val um_csv_header   = h("um_csv_header", I(JAVA_LONG, JAVA_LONG, ADDRESS, JAVA_LONG))
+  val um_csv_upload   = h("um_csv_upload", I(JAVA_LONG, ADDRESS))
+  val um_csv_close    = h("um_csv_close", I(JAVA_LONG))
+  val um_csv_save     = h("um_csv_save", I(ADDRESS, ADDRESS, ADDRESS, ADDRESS))
+
   // status -> the exception the reference throws for the same condition
   def check(status: Int): Unit =
     if status != 0 then

@@ -77,4 +77,6 @@ def test_generated_panel_to_file_and_back(u, tmp_path):
     X = u.MatD.randn(300, 40)
     p = tmp_path / "panel.csv"
     X.saveCSV(str(p))
-    assert np.array_equal(u.loadMatD(str(p)).to_numpy(), np.random.default_rng(8).standard_normal((300, 40)))
+    assert np.array_equal(u.loadMatD(str(p)).to_numpy(), X.to_numpy())   # shortest-digit text reads back bit for bit
+    want = np.random.default_rng(8).standard_normal((300, 40))
+    assert np.allclose(X.to_numpy(), want, rtol=3e-16, atol=0)

@@ -84,7 +84,7 @@ def parse_host(path, delimiter: Optional[str] = None):
 
 def saveCSV(m: Mat, path, sep: str = ",", nanAs: str = "NaN") -> None:
     """`m.saveCSV(filePath, sep, nanAs)` (Mat.scala:90-116); views are materialised first."""
-    src = m if m.isContiguous or m.size == 0 else m.copy()
+    src = m if m.isContiguous() or m.size == 0 else m.copy()
     check(lib.um_csv_save(src._ref(), os.fsencode(path), sep.encode(), nanAs.encode()))
 
 
