@@ -138,6 +138,10 @@ int32_t um_rng_uniform(um_rng* g, double low, double high, const um_view* dst); 
 int32_t um_rng_randn(um_rng* g, const um_view* dst);                            /* MatD.randn    Mat.scala:1480,1488 */
 int32_t um_rng_normal(um_rng* g, double mean, double sd, const um_view* dst);    /* MatD.normal   Mat.scala:1500 */
 int32_t um_rng_randint(um_rng* g, int32_t low, int32_t high, const um_view* dst_i32); /* MatD.randint Mat.scala:1525 */
+/* which kernels um_rng_randn / um_rng_normal use: 0 = automatic (= 1), 1 = scan / prefix / emit kernels (the stream is
+ * generated twice), 2 = single pass (generated once, segments chained by a decoupled look-back; measured slower:
+ * 17.5 vs 10.7 ms per 2^30 draws).  Same values either way.  Process-wide; for tests and profiling. */
+int32_t um_rng_set_randn_path(int32_t path);
 
 /* ---- on-disk format -----------------------------------------------------------------
  * `path.loadMatD` / `loadSmartD` / `loadMatF` (ext/PathExts.scala:583-590 -> io/FileOps.scala:139-188): CSV text ->

@@ -112,6 +112,27 @@ def test_randn_64M_draws(u):
     assert g.nextLong() & ro.M64 == int(r.bit_generator.random_raw())
 
 
+@pytest.mark.parametrize("n", [1, 4096, 4097, 100003, 1 << 22, (1 << 25) + 12345])
+def test_randn_single_pass_and_multi_kernel_paths_are_identical(u, n):
+    """Both kernel organisations consume the stream identically: same bits (tails included: same device arithmetic),
+    same generator state afterwards."""
+    from uni_b200 import rng
+    outs, states = [], []
+    try:
+        for path in (1, 2):
+            rng.set_randn_path(path)
+            g = u.NumPyRNG(2024)
+            a = g.randn(1, n).to_numpy()
+            b = g.normal(1.5, 0.25, 7, 11).to_numpy()
+            outs.append((a, b))
+            states.append(g.state)
+    finally:
+        rng.set_randn_path(0)
+    assert states[0] == states[1]
+    assert np.array_equal(bits(outs[0][0]), bits(outs[1][0])) and np.array_equal(bits(outs[0][1]), bits(outs[1][1]))
+    assert_normal_stream_equal(outs[1][0], np.random.default_rng(2024).standard_normal(n))
+
+
 def test_uniform_and_normal_transforms(u):
     g = u.NumPyRNG(3)
     r = np.random.default_rng(3)
