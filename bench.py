@@ -332,6 +332,20 @@ def run_ours(args, rank, world, local_rank):
     flops = tprf_flops(T, N, Lp)
     value = flops / (ms_step * 1e-3) / 1e12
 
+    # ---- the three-pass (iterative, Tprf3.t3prf) fit of the same panel: BASELINE config 4 names both fits
+    fit_iter = lambda: u.tprf3._fit(L_.TPRF_ITER, y, X, Z, n_total=N, want_all=False)
+    for _ in range(2):
+        fit_iter()
+    barrier()
+    check(lib.um_timer_start())
+    for _ in range(args.steps):
+        fit_iter()
+    check(lib.um_timer_stop(C.byref(ms)))
+    barrier()
+    it_ms = max_over_ranks(ms.value / args.steps)
+    iterative = {"ms_per_fit": round(it_ms, 4), "tflops": round(flops / (it_ms * 1e-3) / 1e12, 3), "steps": args.steps,
+                 "note": "Tprf3.t3prf on the same resident panel: same single-read sweep, three-pass finish"}
+
     # ---- per-kernel device times (outside the timed region) -> roofline of the dominant kernel
     check(lib.um_prof_enable(1)); check(lib.um_prof_reset())
     PROF_N = 5
@@ -413,7 +427,7 @@ def run_ours(args, rank, world, local_rank):
     except Exception as ex:  # e.g. the box cannot pin 16 GiB
         e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
-    extras = {}
+    extras = {"config4_iterative_t3prf": iterative}
     if not args.skip_ops:
         try:
             extras["batched_config5"] = batched_config5(u, rank, world, max_over_ranks, barrier, peak_gbs, small=args.small)
@@ -431,7 +445,7 @@ def run_ours(args, rank, world, local_rank):
             del X
             try:
                 extras["matd_ops_32768x32768_f64"] = matd_ops(u, peak_gbs, 4096 if args.small else 32768)
-                extras["matmul_sweep"] = matmul_sweep(u, (1024, 2048) if args.small else (1024, 2048, 4096, 8192))
+                extras["matmul_sweep"] = matmul_sweep(u, (1024, 2048) if args.small else (1024, 2048, 4096, 8192, 16384))
             except Exception as ex:
                 extras["ops_error"] = str(ex)[:300]
     exchange = "none (1 GPU)"

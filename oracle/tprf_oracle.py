@@ -190,6 +190,55 @@ def _window_fit(yt, Xt, inv_sd, Zt, xt=None, min_obs=10):
     return Xaug @ beta, yhatt
 
 
+def nan_ols(y, X, min_obs):
+    """nanOls (Tprf3.scala:807-830): rows with a NaN in y or X dropped; fewer than min_obs valid rows -> None;
+    (X'X)^-1 X'y with the LU inverse."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    valid = ~np.isnan(y[:, 0]) & ~np.isnan(X).any(axis=1)
+    if valid.sum() < min_obs:
+        return None
+    Xv, yv = X[valid], y[valid]
+    return lu_inverse(Xv.T @ Xv) @ (Xv.T @ yv)
+
+
+def nan_mean_cols(M):
+    """nanMeanCols (Tprf3.scala:506-521): mean over the non-NaN rows, NaN for an empty column."""
+    ok = ~np.isnan(M)
+    n = ok.sum(axis=0)
+    with np.errstate(all="ignore"):
+        return (np.where(ok, M, 0.0).sum(axis=0) / np.where(n > 0, n, np.nan)).reshape(1, -1)
+
+
+def t3prf_pls(yt, Xs, Zt, xt=None, min_obs=10):
+    """runT3prf's pls branch (Tprf3.scala:985-1048): `Xs` already scaled by the window's 1/std; passes 1 and 2 are
+    per-column / per-row nanOls fits WITHOUT intercept on the column-centred data, so gaps (NaN) only remove the
+    observation they sit in.  Returns (yhat T x 1, yhatt)."""
+    T, N = Xs.shape
+    L = Zt.shape[1]
+    Phi = np.full((N, L), np.nan)
+    Sigma = np.full((T, L), np.nan)
+    cm = nan_mean_cols(Xs)
+    Xc = Xs - cm
+    for i in range(N):                                   # pass 1 (:1001-1005)
+        b = nan_ols(Xc[:, i], Zt, min_obs)
+        if b is not None:
+            Phi[i, :] = b[:, 0]
+    for t in range(T):                                   # pass 2, identification floor L + 1 (:1013-1019)
+        b = nan_ols(Xc[t, :], Phi, L + 1)
+        if b is not None:
+            Sigma[t, :] = b[:, 0]
+    Xaug = with_intercept(Sigma)
+    beta = nan_ols(yt, Xaug, 1)                          # pass 3 (:1021-1023)
+    if beta is None:
+        beta = np.full((L + 1, 1), np.nan)
+    yhatt = float("nan")
+    if xt is not None:                                   # :1025-1036
+        b = nan_ols((np.asarray(xt).reshape(1, -1) - cm).ravel(), Phi, L + 1)
+        if b is not None:
+            yhatt = float(beta[0, 0] + b[:, 0] @ beta[1:, 0])
+    return Xaug @ beta, yhatt
+
+
 def _inv_std(M):
     """invStdCols (Tprf3.scala:618-642 family): reciprocal sample std, sd == 0 -> 1."""
     return 1.0 / nan_std_cols(M).reshape(-1)
@@ -203,11 +252,12 @@ def encnew(e1, e2) -> float:
         return float(a.size * (a * a - a * b).sum() / (b * b).sum())
 
 
-def estimate3prf(y, X, Z, procedure="IS Full", window=(0, 1), mintrain=(-1, 0), rollwin=(30, 20, 0)) -> TprfResult:
-    """`Tprf3.estimate3prf` for NaN-free input (Tprf3.scala:1056-1250), every window fitted directly (the
-    reference's FullSample downdating is an O(eps) re-association of the same sums, :742-757).
-    `Z` = proxy matrix (Right) or an int L (Left: automatic proxies).  Result: forecasts, residuals, r_squared,
-    extra = {rollfore, enc}."""
+def estimate3prf(y, X, Z, procedure="IS Full", window=(0, 1), mintrain=(-1, 0), rollwin=(30, 20, 0), pls=False) -> TprfResult:
+    """`Tprf3.estimate3prf` (Tprf3.scala:1056-1250), every window fitted directly (the reference's FullSample
+    downdating is an O(eps) re-association of the same sums, :742-757).  `Z` = proxy matrix (Right) or an int L
+    (Left: automatic proxies).  `pls = True` (effective with automatic proxies only, :1076) takes the per-column /
+    per-row nanOls passes and tolerates NaN gaps in X and y; without it the input must be NaN-free.  Result:
+    forecasts, residuals, r_squared, extra = {rollfore, enc}."""
     y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
     X = np.asarray(X, dtype=np.float64)
     T, N = X.shape
@@ -220,8 +270,21 @@ def estimate3prf(y, X, Z, procedure="IS Full", window=(0, 1), mintrain=(-1, 0), 
     forecasts = np.full((T, 1), np.nan)
     rollfore = np.full((T, 1), np.nan)
 
+    eff_pls = bool(pls) and auto
+
+    def nanmean(v):
+        ok = ~np.isnan(v)
+        return float(v[ok].sum() / ok.sum()) if ok.any() else float("nan")
+
     def window_forecast(yt, Xt, Zt, xt, min_obs=10):
         inv = _inv_std(Xt)
+        if eff_pls:                                       # runT3prf(..., effPls): scaled window, nanOls passes
+            Xs, xs = Xt * inv.reshape(1, -1), xt * inv
+            r0, tp = yt * 1.0, float("nan")
+            for _ in range(L):
+                yh, tp = t3prf_pls(yt, Xs, r0, xs, min_obs)
+                r0 = np.column_stack([yt - yh, r0])
+            return tp
         if not auto:
             return _window_fit(yt, Xt, inv, Zt, xt, 10)[1]
         r0, tp = yt * 1.0, float("nan")
@@ -235,7 +298,7 @@ def estimate3prf(y, X, Z, procedure="IS Full", window=(0, 1), mintrain=(-1, 0), 
         if auto:
             r0, fore = y * 1.0, np.full((T, 1), np.nan)
             for _ in range(L):  # :1097-1106: residual columns are appended at the BACK
-                fore = _window_fit(y, Xn, ones, r0, None, 10)[0]
+                fore = t3prf_pls(y, Xn, r0, None, 10)[0] if eff_pls else _window_fit(y, Xn, ones, r0, None, 10)[0]
                 r0 = np.column_stack([r0, y - fore])
             forecasts[:] = fore
         else:
@@ -246,19 +309,19 @@ def estimate3prf(y, X, Z, procedure="IS Full", window=(0, 1), mintrain=(-1, 0), 
             keep = np.r_[0:lo, hi:T]
             yt = y[keep]
             forecasts[t, 0] = window_forecast(yt, Xn[keep], None if auto else Zm[keep], Xn[t])
-            rollfore[t, 0] = yt.mean()
+            rollfore[t, 0] = nanmean(yt[:, 0]) if eff_pls else yt.mean()
     elif procedure == "OOS Recursive":
         for t in range(mt[0] + 1 + mt[1], T):
             end = t - 1 - mt[1]
             yt = y[:end]
             forecasts[t, 0] = window_forecast(yt, Xn[:end], None if auto else Zm[:end], Xn[t], mt[0])
-            rollfore[t, 0] = yt.mean()
+            rollfore[t, 0] = nanmean(yt[:, 0]) if eff_pls else yt.mean()
     elif procedure == "OOS Rolling":
         for t in range(win + 1 + gap, T):
             lo, hi = max(t - win - gap, 0), min(t - 1 - gap, T)
             yt = y[lo:hi]
             forecasts[t, 0] = window_forecast(yt, Xn[lo:hi], None if auto else Zm[lo:hi], Xn[t], min_nona)
-            rollfore[t, 0] = yt.mean()
+            rollfore[t, 0] = nanmean(yt[:, 0]) if eff_pls else yt.mean()
     else:
         raise ValueError(f"Unknown procedure '{procedure}'. Choose: 'IS Full', 'OOS Recursive', 'OOS Cross Val', 'OOS Rolling'")
 

@@ -406,6 +406,42 @@ def test_pls_wide_panel_vs_oracle(u):
 
 
 # ---------------------------------------------------------------- multi-GPU (runs when the box has >= 2 GPUs)
+def test_estimate3prf_pls_gappy_panels_vs_numpy_reference_and_oracle(u, golden_dir):
+    """estimate3prf(pls = true, automatic proxies): the per-column / per-row nanOls passes (Tprf3.scala:985-1048) as
+    masked batched problems on the device, NaN gaps included, against the reference's NumPy implementation
+    (tests/golden/tprf_pls_pyref, generator beside it) and the oracle, all four procedures."""
+    import glob
+    from tests.test_oracle_tprf import pls_kwargs, pls_panel
+    files = sorted(glob.glob(os.path.join(golden_dir, "tprf_pls_pyref", "*.npz")))
+    assert len(files) == 10
+    for f in files:
+        g = np.load(f)
+        y, X = pls_panel(int(g["seed"]), int(g["T"]), int(g["N"]), bool(g["gaps"]))
+        proc, kw = str(g["procedure"]), pls_kwargs(g)
+        r = u.estimate3prf(u.Mat.from_numpy(y), u.Mat.from_numpy(X), int(g["L"]), proc, pls=True, **kw)
+        got, want = r.forecasts.to_numpy(), g["forecasts"]
+        assert np.array_equal(np.isnan(got), np.isnan(want)), f
+        ok = ~np.isnan(want)
+        assert np.allclose(got[ok], want[ok], rtol=1e-9, atol=1e-12), (f, np.max(np.abs(got[ok] - want[ok])))
+        o = to.estimate3prf(y, X, int(g["L"]), proc, pls=True, **kw)
+        assert np.isclose(r.rSquared, o.r_squared, rtol=1e-9, atol=1e-12, equal_nan=True), f
+    # NaN input without the pls branch is refused (the intercept path would return all-NaN forecasts)
+    y, X = pls_panel(43, 90, 15, True)
+    with pytest.raises(NotImplementedError):
+        u.estimate3prf(u.Mat.from_numpy(y), u.Mat.from_numpy(X), 2, "IS Full")
+
+
+def test_pls_closed_form_agrees_with_estimate3prf_pls(u):
+    """Pls3prfSuite.scala:94-110: the closed form and the iterative pls = true fit give the same forecasts (L = 1)."""
+    for T, N, seed in ((60, 8, 1), (50, 3, 2), (200, 40, 3)):
+        rng = np.random.default_rng(seed)
+        X = rng.standard_normal((T, N)); y = rng.standard_normal((T, 1)) + X[:, :1]
+        dy, dX = u.Mat.from_numpy(y), u.Mat.from_numpy(X)
+        it = u.estimate3prf(dy, dX, 1, pls=True)
+        cf = u.plsClosedForm(dy, dX)
+        assert np.allclose(it.forecasts.to_numpy(), cf.forecasts.to_numpy(), rtol=1e-9, atol=1e-10)
+
+
 def test_sharded_fit_across_ranks(u):
     """tools/dist_check.py under torchrun, one rank per GPU: sharded closed-form / three-pass fits vs the oracle on the
     full panel, bit-identical forecasts on every rank, the peer-memory exchange against a host-side sum."""

@@ -192,3 +192,40 @@ def test_scala_pls_rows(golden_dir, case):
         m.predict(X[0, :-1])
     with pytest.raises(ValueError):
         to.pls_closed_form(y[:-1], X)
+
+
+# ---- estimate3prf(pls = True): nanOls passes, gappy panels -- pinned to the reference's NumPy implementation ----
+def _pls_cases(golden_dir):
+    import glob
+    return sorted(glob.glob(os.path.join(golden_dir, "tprf_pls_pyref", "*.npz")))
+
+
+def pls_panel(seed, T, N, gaps):
+    """tests/golden/gen_tprf_pls_pyref.py::panel"""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((T, N))
+    y = rng.standard_normal((T, 1)) + 0.5 * X[:, :1]
+    if gaps:
+        X[rng.random((T, N)) < 0.04] = np.nan
+        y[rng.choice(T, 3, replace=False), 0] = np.nan
+    return y, X
+
+
+def pls_kwargs(g):
+    return {k[3:]: tuple(int(v) for v in g[k]) for k in g.files if k.startswith("kw_")}
+
+
+def test_oracle_pls_estimate_matches_numpy_reference(golden_dir):
+    files = _pls_cases(golden_dir)
+    assert len(files) == 10
+    for f in files:
+        g = np.load(f)
+        y, X = pls_panel(int(g["seed"]), int(g["T"]), int(g["N"]), bool(g["gaps"]))
+        r = to.estimate3prf(y, X, int(g["L"]), str(g["procedure"]), pls=True, **pls_kwargs(g))
+        want = g["forecasts"]
+        assert np.array_equal(np.isnan(r.forecasts), np.isnan(want)), f
+        ok = ~np.isnan(want)
+        assert np.allclose(r.forecasts[ok], want[ok], rtol=1e-9, atol=1e-12), f
+        if str(g["procedure"]) != "IS Full":
+            rf = g["rollfore"]
+            assert np.allclose(r.extra["rollfore"][~np.isnan(rf)], rf[~np.isnan(rf)], rtol=1e-12, atol=0), f

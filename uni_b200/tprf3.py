@@ -101,6 +101,18 @@ def _oos_forecast(res: Tprf3Result, xt: Mat) -> float:
     return out.value
 
 
+def _window_forecast_pls(yt: Mat, Xt: Mat, n_auto: int, xt: Mat, min_obs: int) -> float:
+    """One out-of-sample window of the pls branch (Tprf3.scala:1122-1139): the window re-standardised by its own
+    NaN-aware std, automatic proxies rebuilt from the window's residuals, each new column in front."""
+    inv = 1.0 / _nan_std_cols(Xt)
+    Xs, xs = Xt * inv, xt * inv
+    r0, tp = yt.copy(), float("nan")
+    for _ in range(n_auto):
+        yh, tp = _t3prf_pls(yt, Xs, r0, xs, min_obs)
+        r0 = MatD.hstack(yt - yh, r0)
+    return tp
+
+
 def _window_forecast(yt: Mat, Xt: Mat, Zt: Optional[Mat], n_auto: int, xt: Mat, min_obs: int) -> float:
     """One out-of-sample window: t3prfFast + t3prfTail's yhatt (Tprf3.scala:883-943).  The fit re-standardises the
     window's columns by their own sample std (invStdCols of the window); automatic proxies rebuild Z from the
@@ -119,6 +131,116 @@ def _window_forecast(yt: Mat, Xt: Mat, Zt: Optional[Mat], n_auto: int, xt: Mat, 
     return tp
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# pls = true: per-column / per-row nanOls passes (Tprf3.scala:985-1048), gap tolerant.  The reference fits N + T
+# small regressions one after the other; here every pass is ONE masked problem: with W the 0/1 matrix of usable
+# observations and D the design (rows with a NaN zeroed), all per-lane Grams are the columns of (D (x) D)' W and all
+# right-hand sides the columns of D' (W o X) -- two skinny products over the panel -- followed by one batched
+# small inverse (um_inverse_batched) and p^2 lane-wise multiply-adds.
+# ---------------------------------------------------------------------------------------------------------------
+def _zeros_like(m: Mat) -> Mat:
+    return MatD.zeros(m.rows, m.cols)
+
+
+def _nan_to_zero(m: Mat) -> Mat:
+    return Mat.where(m.isnan(), _zeros_like(m), m)
+
+
+def _col(m: Mat, j: int) -> Mat:
+    return m._raw_slice(0, m.rows, j, j + 1)
+
+
+def _nan_std_cols(X: Mat) -> Mat:
+    """nanStdCols (Tprf3.scala:469-502): per column over the non-NaN rows, sample std; n <= 1 or sd == 0 -> 1."""
+    ok = ~X.isnan()
+    w = ok.astype(L.F64)
+    Xz = Mat.where(ok, X, _zeros_like(X))
+    n = w.sum(0)
+    one = MatD.ones(1, X.cols)
+    few = n.lte(1.0)
+    mu = Mat.where(few, MatD.zeros(1, X.cols), Xz.sum(0) / Mat.where(few, one, n))
+    d = (Xz - mu) * w
+    sd = ((d * d).sum(0) / Mat.where(few, one, n - 1.0)).sqrt()
+    return Mat.where(few | sd.eq(0.0), one, sd)
+
+
+def _inverse_batched(G: Mat, p: int) -> Mat:
+    """G: lanes x p^2, row i = a p x p matrix (row-major) -> the inverses in the same layout."""
+    out = Mat._alloc(G.rows, p * p, L.F64)
+    a0, o0 = L.UmView(), L.UmView()
+    check(lib.um_view_init(C.byref(a0), C.c_void_p(G._buf.ptr), p, p, L.F64))
+    check(lib.um_view_init(C.byref(o0), C.c_void_p(out._buf.ptr), p, p, L.F64))
+    check(lib.um_inverse_batched(C.byref(a0), p * p, C.byref(o0), p * p, G.rows))
+    return out
+
+
+def _masked_ols(Y0: Mat, W: Mat, D0: Mat, min_obs: int) -> Mat:
+    """nanOls for every column (lane) of Y0 at once.  Y0: obs x lanes with zeros where the observation is unusable,
+    W: the 0/1 usability matrix, D0: obs x p design with unusable rows zeroed.  Returns lanes x p coefficients,
+    NaN rows for lanes with fewer than min_obs usable observations (Tprf3.scala:807-830)."""
+    p, lanes = D0.cols, Y0.cols
+    DD = MatD.hstack(*[_col(D0, a) * _col(D0, b) for a in range(p) for b in range(p)])   # obs x p^2
+    G = (DD.T @ W).T.copy()                                                               # lanes x p^2
+    R = (D0.T @ Y0).T.copy()                                                              # lanes x p
+    ok = W.sum(0).T.copy().gte(float(min_obs))                                            # lanes x 1
+    okf = ok.astype(L.F64)
+    eye = Mat.from_numpy(np.eye(p).reshape(1, p * p))
+    Ginv = _inverse_batched(G * okf + eye * (1.0 - okf), p)     # lanes without a fit get the identity (never singular)
+    cols = []
+    for a in range(p):
+        acc = _col(Ginv, a * p) * _col(R, 0)
+        for b in range(1, p):
+            acc = acc + _col(Ginv, a * p + b) * _col(R, b)
+        cols.append(acc)
+    return MatD.hstack(*cols) + Mat.where(ok, 0.0, float("nan"))
+
+
+def _t3prf_pls(yt: Mat, Xs: Mat, Z: Mat, xt: Optional[Mat], min_obs: int):
+    """runT3prf's pls branch on the device (Tprf3.scala:985-1048): `Xs` = the window scaled by its 1/std, `xt` the
+    held-out row scaled the same way (or None).  Returns (yhat T x 1, yhatt)."""
+    T, N, Lz = Xs.rows, Xs.cols, Z.cols
+    okx = ~Xs.isnan()
+    wx = okx.astype(L.F64)
+    Xz = Mat.where(okx, Xs, _zeros_like(Xs))
+    n = wx.sum(0)
+    has = n.gt(0.0)                                            # nanMeanCols: an empty column has no mean (:506-521)
+    hasf = has.astype(L.F64)
+    cm0 = Mat.where(has, Xz.sum(0) / Mat.where(has, n, MatD.ones(1, N)), MatD.zeros(1, N))
+    Xc0 = (Xz - cm0) * wx                                      # centred; zero where missing
+    # pass 1: column i on Z over the rows where x_i and the whole proxy row are present
+    zf = (~Z.isnan()).all(1).astype(L.F64)                     # T x 1
+    Z0 = _nan_to_zero(Z) * zf
+    Phi = _masked_ols(Xc0 * zf, wx * zf, Z0, min_obs)          # N x L
+    # pass 2: row t on Phi over the columns where x_t and the loading are present; floor L + 1 (:1013)
+    pf = (~Phi.isnan()).all(1).astype(L.F64)                   # N x 1
+    Phi0 = _nan_to_zero(Phi) * pf
+    pft = pf.T
+    Sigma = _masked_ols((Xc0 * pft).T.copy(), (wx * pft).T.copy(), Phi0, Lz + 1)    # T x L
+    # pass 3: y on [1 | Sigma] over the rows where both are present, minObs = 1 (:1021-1023)
+    Xaug = MatD.hstack(MatD.ones(T, 1), Sigma)
+    rf = ((~yt.isnan()) & (~Sigma.isnan()).all(1)).astype(L.F64)
+    if float(rf.sum()) < 1.0:
+        beta = Mat.from_numpy(np.full((Lz + 1, 1), np.nan))
+    else:
+        A0 = _nan_to_zero(Xaug) * rf
+        beta = (A0.T @ A0).inverse() @ (A0.T @ (_nan_to_zero(yt) * rf))
+    yhat = Xaug @ beta
+    yhatt = float("nan")
+    if xt is not None:                                         # :1025-1036: pass 2 applied to the held-out row
+        okt = ~xt.isnan()
+        wt = okt.astype(L.F64) * hasf * pft                    # 1 x N
+        xc0 = (Mat.where(okt, xt, MatD.zeros(1, N)) - cm0) * wt
+        sig = _masked_ols(xc0.T.copy(), wt.T.copy(), Phi0, Lz + 1)                   # 1 x L
+        yhatt = float((MatD.hstack(MatD.ones(1, 1), sig) @ beta)[0, 0])
+    return yhat, yhatt
+
+
+def _nan_mean(v: Mat) -> float:
+    ok = ~v.isnan()
+    k = float(ok.astype(L.F64).sum())
+    return float(Mat.where(ok, v, _zeros_like(v)).sum()) / k if k > 0 else float("nan")
+
+
 def _rows(m: Mat, lo: int, hi: int) -> Mat:
     return m._raw_slice(lo, hi, 0, m.cols)
 
@@ -132,7 +254,8 @@ def _drop_rows(m: Mat, lo: int, hi: int) -> Mat:
 def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full", window: Tuple[int, int] = (0, 1),
                  mintrain: Tuple[int, int] = (-1, 0), rollwin: Tuple[int, int, int] = (30, 20, 0), pls: bool = False,
                  computeAvar: bool = False, n_total: int = 0) -> Tprf3Result:
-    """Tprf3.estimate3prf (Tprf3.scala:1056-1250) on the device, NaN-free input: `Z` a proxy matrix (Right) or an
+    """Tprf3.estimate3prf (Tprf3.scala:1056-1250) on the device (NaN-free input, or gappy input with pls = true and
+    automatic proxies -- the nanOls passes, :985-1048): `Z` a proxy matrix (Right) or an
     int L (Left: automatic proxies); procedures "IS Full", "OOS Recursive", "OOS Cross Val", "OOS Rolling" with the
     reference's `window`, `mintrain`, `rollwin` meaning.  Every window is one fused sweep over its kept rows plus
     one launch for the held-out row; R^2 uses the rolling-mean denominator for the OOS procedures (:1226-1233).
@@ -140,10 +263,10 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
     if procedure not in _PROCEDURES:
         raise ValueError(f"Unknown procedure '{procedure}'. Choose: 'IS Full', 'OOS Recursive', "
                          "'OOS Cross Val', 'OOS Rolling'")
-    if pls or computeAvar:
-        raise NotImplementedError("pls = true (per-column nanOls passes, Tprf3.scala:986-1050; use plsClosedForm) and computeAvar "
-                                  "(N x N / T x T by definition, Tprf3.scala:1253-1277) are not on the device path")
+    if computeAvar:
+        raise NotImplementedError("computeAvar (N x N / T x T by definition, Tprf3.scala:1253-1277) is not on the device path")
     auto = not isinstance(Z, Mat)
+    eff_pls = bool(pls) and auto                                    # `val effPls = pls && autoproxy` (:1076)
     if procedure == "IS Full" and not auto:
         return _fit(L.TPRF_IS_FULL, y, X, Z, n_total)
     if n_total:
@@ -151,10 +274,26 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
     n_auto = int(Z) if auto else 0
     if auto and not 1 <= n_auto <= 8:
         raise ValueError(f"number of automatic proxies L = {n_auto} outside [1, 8]")
-    if X.isnan().any() or y.isnan().any() or (not auto and Z.isnan().any()):
-        raise NotImplementedError("the NaN-tolerant window fits (hasNan, Tprf3.scala:1079) are not on the device path")
+    if not eff_pls and (X.isnan().any() or y.isnan().any() or (not auto and Z.isnan().any())):
+        raise NotImplementedError("NaN input needs pls = true with automatic proxies (the nanOls passes); the intercept path "
+                                  "spreads a NaN to every forecast (Tprf3.scala:883-901) and is not run on the device")
     T = y.rows
-    Xn = X / _std_cols(X)                                            # Tprf3.scala:1080-1081
+    Xn = X / (_nan_std_cols(X) if eff_pls else _std_cols(X))         # Tprf3.scala:1080-1081
+
+    if procedure == "IS Full" and eff_pls:                           # :1097-1106 with runT3prf's pls branch
+        r0, fore = y.copy(), None
+        for _ in range(n_auto):
+            fore, _ = _t3prf_pls(y, Xn, r0, None, 10)
+            r0 = MatD.hstack(r0, y - fore)
+        resid = y - fore
+        loc = ~resid.isnan()
+        e, yl = resid[loc], y[loc]
+        r2 = float("nan")
+        if e.cols > 0:                                               # :1214-1225, no zero guard
+            d = yl - yl.mean()
+            with np.errstate(all="ignore"):
+                r2 = float(1.0 - np.float64((e * e).sum()) / np.float64((d * d).sum()))
+        return Tprf3Result(fore, resid, r2)
 
     if procedure == "IS Full":                                       # automatic proxies, :1097-1106
         r0, res = y.copy(), None
@@ -172,23 +311,26 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
         for t in range(T):
             lo, hi = max(t - window[0], 0), min(t - window[0] + window[1], T)
             yt = _drop_rows(y, lo, hi)
-            fore[t, 0] = _window_forecast(yt, _drop_rows(Xn, lo, hi), None if auto else _drop_rows(Z, lo, hi), n_auto,
-                                          _rows(Xn, t, t + 1), 10)
-            roll[t, 0] = yt.mean()
+            fore[t, 0] = (_window_forecast_pls(yt, _drop_rows(Xn, lo, hi), n_auto, _rows(Xn, t, t + 1), 10) if eff_pls else
+                          _window_forecast(yt, _drop_rows(Xn, lo, hi), None if auto else _drop_rows(Z, lo, hi), n_auto,
+                                           _rows(Xn, t, t + 1), 10))
+            roll[t, 0] = _nan_mean(yt) if eff_pls else yt.mean()
     elif procedure == "OOS Recursive":                               # :1148-1179
         for t in range(mt[0] + 1 + mt[1], T):
             end = t - 1 - mt[1]
             yt = _rows(y, 0, end)
-            fore[t, 0] = _window_forecast(yt, _rows(Xn, 0, end), None if auto else _rows(Z, 0, end), n_auto,
-                                          _rows(Xn, t, t + 1), mt[0])
-            roll[t, 0] = yt.mean()
+            fore[t, 0] = (_window_forecast_pls(yt, _rows(Xn, 0, end), n_auto, _rows(Xn, t, t + 1), mt[0]) if eff_pls else
+                          _window_forecast(yt, _rows(Xn, 0, end), None if auto else _rows(Z, 0, end), n_auto,
+                                           _rows(Xn, t, t + 1), mt[0]))
+            roll[t, 0] = _nan_mean(yt) if eff_pls else yt.mean()
     else:                                                            # OOS Rolling, :1181-1199
         for t in range(win + 1 + gap, T):
             lo, hi = max(t - win - gap, 0), min(t - 1 - gap, T)
             yt = _rows(y, lo, hi)
-            fore[t, 0] = _window_forecast(yt, _rows(Xn, lo, hi), None if auto else _rows(Z, lo, hi), n_auto,
-                                          _rows(Xn, t, t + 1), min_nona)
-            roll[t, 0] = yt.mean()
+            fore[t, 0] = (_window_forecast_pls(yt, _rows(Xn, lo, hi), n_auto, _rows(Xn, t, t + 1), min_nona) if eff_pls else
+                          _window_forecast(yt, _rows(Xn, lo, hi), None if auto else _rows(Z, lo, hi), n_auto,
+                                           _rows(Xn, t, t + 1), min_nona))
+            roll[t, 0] = _nan_mean(yt) if eff_pls else yt.mean()
 
     forecasts, rollfore = Mat.from_numpy(fore), Mat.from_numpy(roll)
     residuals = y - forecasts
