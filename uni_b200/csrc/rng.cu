@@ -85,15 +85,25 @@ inline u64 host_output(u128 s) {  // NumPyRNG.scala:53-56
 }
 
 __device__ __forceinline__ void lcg(u64& hi, u64& lo, u64 mh, u64 ml, u64 ph, u64 pl) {
-  u64 nlo = lo * ml;
-  u64 nhi = __umul64hi(lo, ml) + lo * mh + hi * ml;
-  lo = nlo + pl;
-  hi = nhi + ph + (lo < pl ? 1ULL : 0ULL);
+  const u64 nlo = lo * ml;
+  const u64 nhi = __umul64hi(lo, ml) + lo * mh + hi * ml;
+  asm("add.cc.u64 %0, %2, %4;\n\taddc.u64 %1, %3, %5;" : "=l"(lo), "=l"(hi) : "l"(nlo), "l"(nhi), "l"(pl), "l"(ph));  // 128-bit add
 }
+// The block-stride map: A^256 mod 2^128 is a property of the multiplier alone, so it is a compile-time constant and the
+// multiplies take immediates; only the additive part depends on the stream (checked against make_jump on the host).
+constexpr u64 STRIDE256_MH = 0x61ecb5c24d95b058ULL, STRIDE256_ML = 0xf04c80a23697bc01ULL;
+__device__ __forceinline__ void lcg_stride256(u64& hi, u64& lo, u64 ph, u64 pl) { lcg(hi, lo, STRIDE256_MH, STRIDE256_ML, ph, pl); }
+// (A hand-laid 32-bit limb product -- six wide and four narrow multiply-adds -- was tried: the zero-extended addends cost
+//  a register move each and the instruction count came out the same as the compiler's 64-bit expansion.)
 __device__ __forceinline__ u64 pcg_out(u64 hi, u64 lo) {
-  u64 x = hi ^ lo;
-  unsigned r = (unsigned)(hi >> 58);
-  return (x >> r) | (x << ((64 - r) & 63));
+  // rotr64(hi ^ lo, hi >> 58) with two funnel shifts: a rotation by >= 32 swaps the halves first
+  const u64 x = hi ^ lo;
+  const unsigned r = (unsigned)(hi >> 58);
+  const unsigned xl = (unsigned)x, xh = (unsigned)(x >> 32);
+  const bool sw = (r & 32u) != 0u;
+  const unsigned a = sw ? xh : xl, b = sw ? xl : xh;
+  const unsigned rl = __funnelshift_r(a, b, r), rh = __funnelshift_r(b, a, r);  // shift amount taken mod 32
+  return ((u64)rh << 32) | rl;
 }
 __device__ __forceinline__ void jump_to(u64& hi, u64& lo, u64 delta, const Jump& J) {
   for (int k = 0; delta != 0; k++, delta >>= 1)
@@ -127,33 +137,48 @@ static_assert(DRAW_SPAN == 1 << DRAW_LOG2_SPAN, "block-state stride");
 enum { DRAW_U01 = 0, DRAW_UNIFORM = 1, DRAW_INT = 2 };
 
 template <int KIND>
+__device__ __forceinline__ void draw_store(u64 raw, i64 p, double* __restrict__ outd, int* __restrict__ outi, i64 n_out, double low,
+                                           double span, int ilow, unsigned ibound) {
+  if (KIND == DRAW_U01) {
+    outd[p] = u01(raw);
+  } else if (KIND == DRAW_UNIFORM) {
+    outd[p] = __dadd_rn(low, __dmul_rn(u01(raw), span));  // low + nextDouble() * (high - low), NumPyRNG.scala:73-74
+  } else {
+    // nextBoundedInt (NumPyRNG.scala:82-110): low half first, then the high half, (bits32 * bound) >>> 32
+    const i64 o = 2 * p;
+    outi[o] = ilow + (int)(((raw & 0xffffffffULL) * (u64)ibound) >> 32);
+    if (o + 1 < n_out) outi[o + 1] = ilow + (int)(((raw >> 32) * (u64)ibound) >> 32);
+  }
+}
+
+template <int KIND>
 __global__ void __launch_bounds__(RNG_THREADS) k_rng_draw(const __grid_constant__ Jump J, const ulonglong2* __restrict__ bs, i64 n_raw,
                                                          double* __restrict__ outd, int* __restrict__ outi, i64 n_out,
                                                          double low, double span, int ilow, unsigned ibound, int pre_flag,
                                                          int pre_val) {
   if (KIND == DRAW_INT && pre_flag && blockIdx.x == 0 && threadIdx.x == 0) outi[-1] = pre_val;
-  i64 base = (i64)blockIdx.x * DRAW_SPAN + threadIdx.x;
+  const i64 block0 = (i64)blockIdx.x * DRAW_SPAN;
+  const i64 base = block0 + threadIdx.x;
   if (base >= n_raw) return;
   const ulonglong2 b = bs[blockIdx.x];
   u64 hi = b.x, lo = b.y;
   jump_to(hi, lo, (u64)threadIdx.x + 1, J);
-  const u64 mh = J.mh[8], ml = J.ml[8], ph = J.ph[8], pl = J.pl[8];  // stride 256 = RNG_THREADS
+  const u64 ph = J.ph[8], pl = J.pl[8];  // stride 256 = RNG_THREADS
+  if (block0 + DRAW_SPAN <= n_raw) {
+    // the whole block is inside the fill (all but the last block): no per-draw bounds arithmetic
+#pragma unroll 8
+    for (int j = 0; j < DRAW_PER_THREAD; j++) {
+      draw_store<KIND>(pcg_out(hi, lo), base + (i64)j * RNG_THREADS, outd, outi, n_out, low, span, ilow, ibound);
+      lcg_stride256(hi, lo, ph, pl);
+    }
+    return;
+  }
 #pragma unroll 4
   for (int j = 0; j < DRAW_PER_THREAD; j++) {
-    i64 p = base + (i64)j * RNG_THREADS;
+    const i64 p = base + (i64)j * RNG_THREADS;
     if (p >= n_raw) break;
-    u64 raw = pcg_out(hi, lo);
-    if (KIND == DRAW_U01) {
-      outd[p] = u01(raw);
-    } else if (KIND == DRAW_UNIFORM) {
-      outd[p] = __dadd_rn(low, __dmul_rn(u01(raw), span));  // low + nextDouble() * (high - low), NumPyRNG.scala:73-74
-    } else {
-      // nextBoundedInt (NumPyRNG.scala:82-110): low half first, then the high half, (bits32 * bound) >>> 32
-      i64 o = 2 * p;
-      outi[o] = ilow + (int)(((raw & 0xffffffffULL) * (u64)ibound) >> 32);
-      if (o + 1 < n_out) outi[o + 1] = ilow + (int)(((raw >> 32) * (u64)ibound) >> 32);
-    }
-    lcg(hi, lo, mh, ml, ph, pl);
+    draw_store<KIND>(pcg_out(hi, lo), p, outd, outi, n_out, low, span, ilow, ibound);
+    lcg_stride256(hi, lo, ph, pl);
   }
 }
 
@@ -190,8 +215,8 @@ __device__ __forceinline__ void zig_split(u64 raw, int& idx, int& sign, u64& rab
 __device__ __forceinline__ double zig_x(u64 rabs, double w, int sign) {
   // rabs < 2^52: exact conversion through the 2^52 exponent trick, then ONE rounded multiply (rabs.toDouble * wi)
   double m = __longlong_as_double((long long)(rabs | 0x4330000000000000ULL)) - 4503599627370496.0;
-  double x = __dmul_rn(m, w);
-  return sign ? -x : x;
+  double x = __dmul_rn(m, w);  // >= 0: the sign is one bit to set (-0.0 for x == 0, like `sign * x`)
+  return __longlong_as_double(__double_as_longlong(x) | ((long long)sign << 63));
 }
 
 // Phase 1 (both kernels): generate this thread's draws, flag the non-simple ones, list them.
@@ -200,7 +225,7 @@ __device__ __forceinline__ void zig_generate(ZigShared& sh, const Jump& J, ulong
   const int t = threadIdx.x;
   u64 hi = b.x, lo = b.y;
   jump_to(hi, lo, (u64)t + 1, J);
-  const u64 mh = J.mh[8], ml = J.ml[8], ph = J.ph[8], pl = J.pl[8];
+  const u64 ph = J.ph[8], pl = J.pl[8];
 #pragma unroll
   for (int j = 0; j < RNG_PER_THREAD; j++) {
     u64 raw = pcg_out(hi, lo);
@@ -220,7 +245,7 @@ __device__ __forceinline__ void zig_generate(ZigShared& sh, const Jump& J, ulong
         sh.overflow = 1;
       }
     }
-    lcg(hi, lo, mh, ml, ph, pl);
+    lcg_stride256(hi, lo, ph, pl);
   }
 }
 
@@ -572,7 +597,7 @@ __global__ void __launch_bounds__(RNG_THREADS) k_zig_emit_fast(const __grid_cons
   const ulonglong2 b = bs[blockIdx.x];
   u64 hi = b.x, lo = b.y;
   jump_to(hi, lo, (u64)t + 1, J);
-  const u64 mh = J.mh[8], ml = J.ml[8], ph = J.ph[8], pl = J.pl[8];
+  const u64 ph = J.ph[8], pl = J.pl[8];
 #pragma unroll 4
   for (int j = 0; j < RNG_PER_THREAD; j++) {
     const int p = j * RNG_THREADS + t;
@@ -605,7 +630,7 @@ __global__ void __launch_bounds__(RNG_THREADS) k_zig_emit_fast(const __grid_cons
       out[o] = v;
       if (o == n_out - 1) result[3] = (i64)blockIdx.x * SEG + p + consumed;
     }
-    lcg(hi, lo, mh, ml, ph, pl);
+    lcg_stride256(hi, lo, ph, pl);
   }
 }
 
@@ -847,6 +872,7 @@ inline uint32_t ss_mix(uint32_t x, uint32_t y) {
 }
 
 int launch_block_states(const Jump& J, const um_rng* g, i64 nblocks, int log2_span, ulonglong2* bs) {
+  if (J.mh[8] != STRIDE256_MH || J.ml[8] != STRIDE256_ML) return fail(UM_ERR_CUDA, "rng: stride-256 multiplier constant is wrong");
   i64 threads = (nblocks + BS_CHUNK - 1) / BS_CHUNK;
   k_rng_block_states<<<(unsigned)((threads + 127) / 128), 128, 0, ctx()->stream>>>(J, g->state_hi, g->state_lo, nblocks, log2_span, bs);
   UM_LAUNCHED();
