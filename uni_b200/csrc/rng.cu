@@ -30,6 +30,7 @@
 // overshoot of 16 or more (a tail loop of 8+ rounds at a segment end, p < 1e-12 per 2^31 draws) is reported as an
 // error, never emitted wrong.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "ziggurat_tables.cuh"
@@ -128,8 +129,8 @@ __global__ void __launch_bounds__(128) k_rng_block_states(const __grid_constant_
 }
 static_assert(SEG == 4096, "ziggurat segments are 2^12 draws (16-bit positions, block-state stride)");
 // the fixed-consumption fills amortise the per-thread jump over more draws
-constexpr int DRAW_PER_THREAD = 64;
-constexpr int DRAW_LOG2_SPAN = 14;
+constexpr int DRAW_PER_THREAD = 128;
+constexpr int DRAW_LOG2_SPAN = 15;
 constexpr int DRAW_SPAN = RNG_THREADS * DRAW_PER_THREAD;
 static_assert(DRAW_SPAN == 1 << DRAW_LOG2_SPAN, "block-state stride");
 
@@ -598,40 +599,47 @@ __global__ void __launch_bounds__(RNG_THREADS) k_zig_emit_fast(const __grid_cons
   u64 hi = b.x, lo = b.y;
   jump_to(hi, lo, (u64)t + 1, J);
   const u64 ph = J.ph[8], pl = J.pl[8];
+  // INNER: every value of this segment lands before the last wanted element (all but the final segments), so the
+  // output-range tests drop out of the loop
+  auto body = [&](auto inner_tag) {
+    constexpr bool INNER = decltype(inner_tag)::value;
 #pragma unroll 4
-  for (int j = 0; j < RNG_PER_THREAD; j++) {
-    const int p = j * RNG_THREADS + t;
-    const u64 raw = pcg_out(hi, lo);
-    const u64 ym = s_ym[p >> 6];
-    const i64 o = out_base + s_prefix[p >> 6] + __popcll(ym & ((1ULL << (p & 63)) - 1));
-    if (((ym >> (p & 63)) & 1) && o < n_out) {
-      int idx, sign;
-      u64 rabs;
-      zig_split(raw, idx, sign, rabs);
-      double v = zig_x(rabs, s_wi[idx], sign);
-      int consumed = 1;
-      if (!(rabs < s_ki[idx])) {
-        consumed = 2;  // an accepted wedge attempt
-        if (idx == 0) {  // tail: replay its draws (NumPyRNG.scala:142-151)
-          u64 th = hi, tl = lo;
-          double xx, yy;
-          consumed = 1;
-          do {
-            lcg(th, tl, J.mh[0], J.ml[0], J.ph[0], J.pl[0]);
-            xx = -UM_ZIG_INV_R * log1p(-u01(pcg_out(th, tl)));
-            lcg(th, tl, J.mh[0], J.ml[0], J.ph[0], J.pl[0]);
-            yy = -log1p(-u01(pcg_out(th, tl)));
-            consumed += 2;
-          } while (!(__dadd_rn(yy, yy) > __dmul_rn(xx, xx)) && consumed < ZIG_MAX_CONS);
-          v = ((rabs >> 8) & 1) ? -__dadd_rn(UM_ZIG_R, xx) : __dadd_rn(UM_ZIG_R, xx);
+    for (int j = 0; j < RNG_PER_THREAD; j++) {
+      const int p = j * RNG_THREADS + t;
+      const u64 raw = pcg_out(hi, lo);
+      const u64 ym = s_ym[p >> 6];
+      const i64 o = out_base + s_prefix[p >> 6] + __popcll(ym & ((1ULL << (p & 63)) - 1));
+      if (((ym >> (p & 63)) & 1) && (INNER || o < n_out)) {
+        int idx, sign;
+        u64 rabs;
+        zig_split(raw, idx, sign, rabs);
+        double v = zig_x(rabs, s_wi[idx], sign);
+        int consumed = 1;
+        if (!(rabs < s_ki[idx])) {
+          consumed = 2;  // an accepted wedge attempt
+          if (idx == 0) {  // tail: replay its draws (NumPyRNG.scala:142-151)
+            u64 th = hi, tl = lo;
+            double xx, yy;
+            consumed = 1;
+            do {
+              lcg(th, tl, J.mh[0], J.ml[0], J.ph[0], J.pl[0]);
+              xx = -UM_ZIG_INV_R * log1p(-u01(pcg_out(th, tl)));
+              lcg(th, tl, J.mh[0], J.ml[0], J.ph[0], J.pl[0]);
+              yy = -log1p(-u01(pcg_out(th, tl)));
+              consumed += 2;
+            } while (!(__dadd_rn(yy, yy) > __dmul_rn(xx, xx)) && consumed < ZIG_MAX_CONS);
+            v = ((rabs >> 8) & 1) ? -__dadd_rn(UM_ZIG_R, xx) : __dadd_rn(UM_ZIG_R, xx);
+          }
         }
+        if (affine) v = __dadd_rn(mean, __dmul_rn(sd, v));  // mean + std * rng.randn(), Mat.scala:1500-1507
+        out[o] = v;
+        if (!INNER && o == n_out - 1) result[3] = (i64)blockIdx.x * SEG + p + consumed;
       }
-      if (affine) v = __dadd_rn(mean, __dmul_rn(sd, v));  // mean + std * rng.randn(), Mat.scala:1500-1507
-      out[o] = v;
-      if (o == n_out - 1) result[3] = (i64)blockIdx.x * SEG + p + consumed;
+      lcg_stride256(hi, lo, ph, pl);
     }
-    lcg_stride256(hi, lo, ph, pl);
-  }
+  };
+  if (out_base + SEG < n_out) body(std::true_type{});
+  else body(std::false_type{});
 }
 
 __global__ void __launch_bounds__(RNG_THREADS, 3) k_zig_emit(const __grid_constant__ Jump J, const ulonglong2* __restrict__ bs,
