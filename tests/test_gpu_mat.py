@@ -570,3 +570,30 @@ def test_launch_counter_moves(u):
     m = u.MatD.ones(8, 8)
     (m + m).sum()
     assert u.launch_count() > n0
+
+
+def test_mask_select_staged_kernel_and_offset_reuse(u):
+    """m(mask) through the shared-memory staged scatter (contiguous f64 / f32 operands) and the reuse of the count's
+    block offsets by the fill that follows it: same result as NumPy for ragged sizes, and a mask that is CHANGED
+    between um_mask_count and um_mask_select (another library call in between) must not see stale offsets."""
+    import ctypes as C
+    rng = np.random.default_rng(77)
+    for shape in [(1, 1), (3, 5), (1, 4095), (1, 4096), (1, 4097), (257, 129), (1000, 1037), (2048, 2048)]:
+        a = rng.standard_normal(shape)
+        for frac in (0.0, 0.03, 0.5, 1.0):
+            mk = rng.random(shape) < frac
+            for arr in (a, a.astype(np.float32)):
+                got = dev(u, arr)[dev(u, mk)].to_numpy()
+                assert np.array_equal(got.ravel(), arr[mk]), (shape, frac, arr.dtype)
+    # stale offsets: count on one mask, flip the mask in place, then fill
+    a = rng.standard_normal((300, 70)); mk = rng.random((300, 70)) < 0.5
+    da, dm = dev(u, a), dev(u, mk)
+    k = C.c_int64(0)
+    u._lib.check(u._lib.lib.um_mask_count(dm._ref(), C.byref(k)))
+    assert k.value == int(mk.sum())
+    flipped = ~dm                                    # a library call in between ...
+    u._lib.check(u._lib.lib.um_copy(flipped._ref(), dm._ref()))   # ... that rewrites the mask buffer in place
+    k2 = int((~mk).sum())
+    res = u.Mat._alloc(1, k2, u._lib.F64)
+    u._lib.check(u._lib.lib.um_mask_select(da._ref(), dm._ref(), res._ref()))
+    assert np.array_equal(res.to_numpy().ravel(), a[~mk])

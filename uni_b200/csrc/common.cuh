@@ -24,6 +24,8 @@ struct Ctx {
 
 Ctx* ctx();  // lazily initialised on device 0 (or the device chosen by um_init)
 int ensure_ctx();
+unsigned long long op_epoch();  // content-changing library calls made by this host thread so far
+void op_epoch_passive();
 int fail(int code, const char* fmt, ...);
 void* scratch(size_t bytes);  // nullptr + error set on failure
 extern std::atomic<long long> g_launches;

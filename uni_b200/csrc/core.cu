@@ -65,7 +65,14 @@ static int init_ctx(int device) {
   return UM_OK;
 }
 
+// Counts the library calls of the calling host thread that touch the device (every such entry point passes through
+// ensure_ctx): lets um_mask_select recognise that nothing ran on this thread since the um_mask_count of the same mask.
+static thread_local unsigned long long t_epoch = 0;
+unsigned long long op_epoch() { return t_epoch; }
+void op_epoch_passive() { --t_epoch; }  // the current call cannot change the contents of any existing buffer (malloc / free)
+
 int ensure_ctx() {
+  ++t_epoch;
   if (t_ctx.stream) {
     cudaSetDevice(t_ctx.device);
     return UM_OK;
@@ -211,6 +218,7 @@ int32_t um_device_props(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,
 
 int32_t um_malloc(size_t bytes, void** out) {
   UM_CTX();
+  op_epoch_passive();
   if (!out) return fail(UM_ERR_ARG, "null out");
   *out = nullptr;
   if (bytes == 0) bytes = 16;
@@ -225,6 +233,7 @@ int32_t um_malloc(size_t bytes, void** out) {
 int32_t um_free(void* ptr) {
   if (!ptr) return UM_OK;
   UM_CTX();
+  op_epoch_passive();
   UM_CUDA(cudaFreeAsync(ptr, ctx()->stream));
   return UM_OK;
 }

@@ -338,8 +338,12 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_count(In<uint8_t> m, i64 co
 // exclusive scan of the block counts in place; counts[nb] = total.  One block (integer sums are exact in any order):
 // each thread folds 8 consecutive counts, warps scan with shuffles, one shared-memory step across the 32 warps; the
 // next 8192 counts are loaded before the current ones are scanned.
-__global__ void __launch_bounds__(1024) k_sel_scan(i64* __restrict__ counts, i64 nb) {
+// Block b scans counts[b * chunk, min(nb, (b + 1) * chunk)) and stores its total in total_out[b]; with one block and
+// chunk >= nb that is the whole array and total_out = counts + nb.
+__global__ void __launch_bounds__(1024) k_sel_scan(i64* __restrict__ counts_all, i64 nb_all, i64 chunk, i64* __restrict__ total_out) {
   constexpr int PER = 8;
+  i64* __restrict__ counts = counts_all + (i64)blockIdx.x * chunk;
+  const i64 nb = min(chunk, nb_all - (i64)blockIdx.x * chunk);
   __shared__ i64 wsum[32];
   __shared__ i64 carry_s;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -382,8 +386,17 @@ __global__ void __launch_bounds__(1024) k_sel_scan(i64* __restrict__ counts, i64
 #pragma unroll
     for (int k = 0; k < PER; ++k) v[k] = nxt[k];
   }
-  if (t == 0) counts[nb] = carry_s;
+  if (t == 0) total_out[blockIdx.x] = carry_s;
 }
+// second level: add the scanned chunk totals back; the grand total goes to counts[nb]
+__global__ void __launch_bounds__(1024) k_sel_scan_add(i64* __restrict__ counts, i64 nb, i64 chunk, const i64* __restrict__ chunk_off,
+                                                        i64 nchunk) {
+  const i64 add = chunk_off[blockIdx.x];
+  const i64 b0 = (i64)blockIdx.x * chunk, b1 = min(nb, b0 + chunk);
+  for (i64 b = b0 + threadIdx.x; b < b1; b += 1024) counts[b] += add;
+  if (blockIdx.x == 0 && threadIdx.x == 0) counts[nb] = chunk_off[nchunk];
+}
+constexpr i64 SEL_SCAN_CHUNK = 8192;  // one pass of the 1024-thread scan
 
 template <class T, bool FLAT_A, bool FLAT_M>
 __global__ void __launch_bounds__(SEL_THREADS) k_sel_scatter(In<T> a, In<uint8_t> m, i64 cols, i64 n, const i64* __restrict__ offsets,
@@ -452,6 +465,73 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_scatter_flat(const T* __res
   }
 }
 
+// Contiguous operand and mask, staged through shared memory so that BOTH directions are coalesced: the block's 4096
+// operand elements are loaded with unit-stride warp loads into a staging buffer, every thread owns 16 consecutive mask
+// bytes (one 16-byte load), its selected elements are moved to their place (exclusive scan of the per-thread
+// counts), and the block's k_b selected elements leave with unit-stride stores.  Needs a 16-byte aligned
+// mask pointer; 32 KB of shared memory for 8-byte elements (compaction in place).
+template <class T>
+__global__ void __launch_bounds__(SEL_THREADS) k_sel_scatter_staged(const T* __restrict__ a, const uint8_t* __restrict__ m, i64 n,
+                                                                     const i64* __restrict__ offsets, T* __restrict__ out, i64 out_n) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  T* stage = reinterpret_cast<T*>(sel_smem);
+  __shared__ int wsum[SEL_THREADS / 32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const i64 e0 = (i64)blockIdx.x * SEL_CHUNK;
+  // operand: unit-stride loads
+#pragma unroll
+  for (int k = 0; k < SEL_CHUNK / SEL_THREADS; ++k) {
+    const i64 e = e0 + k * SEL_THREADS + t;
+    if (e < n) stage[k * SEL_THREADS + t] = a[e];
+  }
+  // mask: 16 consecutive bytes per thread -> one bit each
+  unsigned bits = 0;
+  const i64 me = e0 + (i64)t * 16;
+  if (me + 16 <= n) {
+    const uint4 v = *reinterpret_cast<const uint4*>(m + me);
+    const unsigned wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const unsigned nz = __vcmpne4(wds[q], 0u);  // 0xff per non-zero byte
+      bits |= (((nz >> 0) & 1u) | ((nz >> 7) & 2u) | ((nz >> 14) & 4u) | ((nz >> 21) & 8u)) << (4 * q);
+    }
+  } else {
+    for (int k = 0; k < 16; ++k)
+      if (me + k < n && m[me + k] != 0) bits |= 1u << k;
+  }
+  const int c = __popc(bits);
+  int inc = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();  // staging buffer and warp totals complete
+  int off = inc - c, total = 0;
+#pragma unroll
+  for (int q = 0; q < SEL_THREADS / 32; ++q) {
+    if (q < w) off += wsum[q];
+    total += wsum[q];
+  }
+  // compact IN PLACE: every thread first takes its 16 elements into registers (the rotation (k + t) keeps the
+  // 16-element-strided reads off one bank), then -- after a barrier -- drops the selected ones at its offset, which
+  // is never beyond its own first element
+  T v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = stage[t * 16 + ((k + t) & 15)];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int kk = (k + t) & 15;
+    if ((bits >> kk) & 1u) stage[off + __popc(bits & ((1u << kk) - 1u))] = v[k];
+  }
+  __syncthreads();
+  const i64 base = offsets[blockIdx.x];
+  for (int i = t; i < total; i += SEL_THREADS)
+    if (base + i < out_n) out[base + i] = stage[i];
+}
+
 // count for a contiguous mask: 16 bytes per thread per load
 __global__ void __launch_bounds__(SEL_THREADS) k_sel_count_flat(const uint8_t* __restrict__ m, i64 n, i64* __restrict__ counts) {
   __shared__ int sm[SEL_THREADS / 32];
@@ -481,24 +561,55 @@ static void sel_scatter(const um_view* a, const um_view* mask, i64 n, const i64*
   cudaStream_t st = ctx()->stream;
   const bool fa = view_is_flat(a), fm = view_is_flat(mask);
   T* op = static_cast<T*>(o);
-  if (fa && fm) k_sel_scatter_flat<T><<<g, SEL_THREADS, 0, st>>>(in_of<T>(a).p, in_of<uint8_t>(mask).p, n, offs, op, out_n);
+  if (fa && fm && sizeof(T) >= 4 && aligned16(in_of<uint8_t>(mask).p)) {
+    const size_t smem = (size_t)SEL_CHUNK * sizeof(T);
+    cudaFuncSetAttribute(k_sel_scatter_staged<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // per device; cheap
+    k_sel_scatter_staged<T><<<g, SEL_THREADS, smem, st>>>(in_of<T>(a).p, in_of<uint8_t>(mask).p, n, offs, op, out_n);
+  } else if (fa && fm) k_sel_scatter_flat<T><<<g, SEL_THREADS, 0, st>>>(in_of<T>(a).p, in_of<uint8_t>(mask).p, n, offs, op, out_n);
   else if (fa) k_sel_scatter<T, true, false><<<g, SEL_THREADS, 0, st>>>(in_of<T>(a), in_of<uint8_t>(mask), a->cols, n, offs, op, out_n);
   else if (fm) k_sel_scatter<T, false, true><<<g, SEL_THREADS, 0, st>>>(in_of<T>(a), in_of<uint8_t>(mask), a->cols, n, offs, op, out_n);
   else k_sel_scatter<T, false, false><<<g, SEL_THREADS, 0, st>>>(in_of<T>(a), in_of<uint8_t>(mask), a->cols, n, offs, op, out_n);
 }
 
+// m(mask) is two calls (count, then fill the caller-allocated row).  The block offsets the count produced are still in
+// this thread's scratch buffer when the fill follows immediately: remembered with the mask's view and the thread's
+// call counter, reused only if no other device-touching call was made by this thread in between.
+struct SelCache {
+  const void* data = nullptr;
+  i64 offset = 0, rows = 0, cols = 0, rs = 0, cs = 0, nb = 0;
+  i64* offsets = nullptr;
+  unsigned long long epoch = 0;
+};
+static thread_local SelCache t_sel;
+static bool sel_cache_hit(const um_view* mask, unsigned long long epoch_now) {
+  return t_sel.offsets && t_sel.data == mask->data && t_sel.offset == mask->offset && t_sel.rows == mask->rows &&
+         t_sel.cols == mask->cols && t_sel.rs == mask->rs && t_sel.cs == mask->cs && t_sel.epoch + 1 == epoch_now &&
+         t_sel.offsets == ctx()->scratch;
+}
+
 static int sel_offsets(const um_view* mask, i64** offsets_out, i64* nb_out) {
   const i64 n = mask->rows * mask->cols;
   const i64 nb = (n + SEL_CHUNK - 1) / SEL_CHUNK;
-  i64* counts = static_cast<i64*>(scratch((size_t)(nb + 1) * sizeof(i64)));
+  const i64 nchunk = (nb + SEL_SCAN_CHUNK - 1) / SEL_SCAN_CHUNK;
+  i64* counts = static_cast<i64*>(scratch((size_t)(nb + 1 + nchunk + 1) * sizeof(i64)));
   if (!counts) return UM_ERR_OOM;
   if (nb > 0) {
     if (view_is_flat(mask)) k_sel_count_flat<<<(unsigned)nb, SEL_THREADS, 0, ctx()->stream>>>(in_of<uint8_t>(mask).p, n, counts);
     else k_sel_count<false><<<(unsigned)nb, SEL_THREADS, 0, ctx()->stream>>>(in_of<uint8_t>(mask), mask->cols, n, counts);
     UM_LAUNCHED();
   }
-  k_sel_scan<<<1, 1024, 0, ctx()->stream>>>(counts, nb);
-  UM_LAUNCHED();
+  if (nchunk <= 1) {
+    k_sel_scan<<<1, 1024, 0, ctx()->stream>>>(counts, nb, nb > 0 ? nb : 1, counts + nb);
+    UM_LAUNCHED();
+  } else {  // chunks scanned in parallel, their totals scanned by one block, then added back
+    i64* tot = counts + nb + 1;
+    k_sel_scan<<<(unsigned)nchunk, 1024, 0, ctx()->stream>>>(counts, nb, SEL_SCAN_CHUNK, tot);
+    UM_LAUNCHED();
+    k_sel_scan<<<1, 1024, 0, ctx()->stream>>>(tot, nchunk, nchunk, tot + nchunk);
+    UM_LAUNCHED();
+    k_sel_scan_add<<<(unsigned)nchunk, 1024, 0, ctx()->stream>>>(counts, nb, SEL_SCAN_CHUNK, tot, nchunk);
+    UM_LAUNCHED();
+  }
   *offsets_out = counts;
   *nb_out = nb;
   return UM_OK;
@@ -571,11 +682,13 @@ int32_t um_mask_count(const um_view* mask, int64_t* host_count) {
   UM_CUDA(cudaMemcpyAsync(&total, offs + nb, sizeof(i64), cudaMemcpyDeviceToHost, ctx()->stream));
   UM_CUDA(cudaStreamSynchronize(ctx()->stream));
   *host_count = total;
+  t_sel = SelCache{mask->data, mask->offset, mask->rows, mask->cols, mask->rs, mask->cs, nb, offs, op_epoch()};
   return UM_OK;
 }
 
 int32_t um_mask_select(const um_view* a, const um_view* mask, const um_view* out) {
   UM_CTX();
+  const unsigned long long epoch_now = op_epoch();
   UM_VIEW(a); UM_VIEW(mask); UM_VIEW(out);
   UM_REQUIRE(mask->dtype == UM_BOOL, "mask select needs a boolean mask");
   UM_REQUIRE(mask->rows == a->rows && mask->cols == a->cols, "Mask shape %lldx%lld must match matrix shape %lldx%lld", (i64)mask->rows,
@@ -585,8 +698,14 @@ int32_t um_mask_select(const um_view* a, const um_view* mask, const um_view* out
   if (n == 0 || out->cols == 0) return UM_OK;
   i64* offs = nullptr;
   i64 nb = 0;
-  int s = sel_offsets(mask, &offs, &nb);
-  if (s != UM_OK) return s;
+  if (sel_cache_hit(mask, epoch_now)) {
+    offs = t_sel.offsets;
+    nb = t_sel.nb;
+  } else {
+    int s = sel_offsets(mask, &offs, &nb);
+    if (s != UM_OK) return s;
+  }
+  t_sel.offsets = nullptr;
   const unsigned g = (unsigned)nb;
   void* o = static_cast<char*>(out->data) + (size_t)out->offset * dtype_size(out->dtype);
   switch (a->dtype) {
