@@ -175,6 +175,23 @@ def test_matd_factories_use_the_global_generator(u):
     assert u.MatD.rand(7, 0).shape == (7, 0)
 
 
+def test_fills_into_contiguous_row_blocks_of_a_larger_matrix(u):
+    """The C ABI fills any contiguous view: consecutive row blocks of one matrix filled by consecutive calls hold the
+    same numbers as one fill of the whole matrix (how bench.py builds the config-4 panel in 1 GiB chunks)."""
+    import ctypes as C
+    rows, cols = 37, 501
+    whole = u.NumPyRNG(12).randn(rows, cols).to_numpy()
+    g = u.NumPyRNG(12)
+    m = u.MatD.zeros(rows, cols)
+    for r0, r1 in ((0, 5), (5, 6), (6, 30), (30, 37)):
+        u._lib.check(u._lib.lib.um_rng_randn(C.byref(g._g), m._raw_slice(r0, r1, 0, cols)._ref()))
+    assert np.array_equal(bits(m.to_numpy()), bits(whole))
+    g2, m2 = u.NumPyRNG(12), u.MatD.zeros(rows, cols)
+    for r0, r1 in ((0, 20), (20, 37)):
+        u._lib.check(u._lib.lib.um_rng_rand(C.byref(g2._g), m2._raw_slice(r0, r1, 0, cols)._ref()))
+    assert np.array_equal(bits(m2.to_numpy()), bits(np.random.default_rng(12).random((rows, cols))))
+
+
 def test_fills_reject_strided_destinations(u):
     import ctypes as C
     g = u.NumPyRNG(0)
