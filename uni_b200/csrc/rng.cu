@@ -128,6 +128,25 @@ __global__ void __launch_bounds__(128) k_rng_block_states(const __grid_constant_
   }
 }
 static_assert(SEG == 4096, "ziggurat segments are 2^12 draws (16-bit positions, block-state stride)");
+// For the ziggurat kernels: the state at the first draw of every WARP of every segment (draw seg * 4096 + 32 w, w < 8),
+// so a thread's own jump is at most 32 draws (6 maps instead of 9).
+constexpr int ZIG_WARPS = RNG_THREADS / 32;
+__global__ void __launch_bounds__(128) k_zig_warp_states(const __grid_constant__ Jump J, u64 s_hi, u64 s_lo, i64 nseg,
+                                                        ulonglong2* __restrict__ ws) {
+  i64 b0 = ((i64)blockIdx.x * 128 + threadIdx.x) * BS_CHUNK;
+  if (b0 >= nseg) return;
+  u64 hi = s_hi, lo = s_lo;
+  jump_to(hi, lo, (u64)b0 << 12, J);
+  for (int i = 0; i < BS_CHUNK && b0 + i < nseg; i++) {
+    u64 h = hi, l = lo;
+#pragma unroll
+    for (int w = 0; w < ZIG_WARPS; w++) {
+      ws[(b0 + i) * ZIG_WARPS + w] = make_ulonglong2(h, l);
+      lcg(h, l, J.mh[5], J.ml[5], J.ph[5], J.pl[5]);
+    }
+    lcg(hi, lo, J.mh[12], J.ml[12], J.ph[12], J.pl[12]);
+  }
+}
 // the fixed-consumption fills amortise the per-thread jump over more draws
 constexpr int DRAW_PER_THREAD = 128;
 constexpr int DRAW_LOG2_SPAN = 15;
@@ -222,10 +241,12 @@ __device__ __forceinline__ double zig_x(u64 rabs, double w, int sign) {
 
 // Phase 1 (both kernels): generate this thread's draws, flag the non-simple ones, list them.
 // Returns the draws through raws[].
-__device__ __forceinline__ void zig_generate(ZigShared& sh, const Jump& J, ulonglong2 b, u64 (&raws)[RNG_PER_THREAD]) {
+__device__ __forceinline__ void zig_generate(ZigShared& sh, const Jump& J, const ulonglong2* __restrict__ wsb,
+                                             u64 (&raws)[RNG_PER_THREAD]) {
   const int t = threadIdx.x;
+  const ulonglong2 b = wsb[t >> 5];
   u64 hi = b.x, lo = b.y;
-  jump_to(hi, lo, (u64)t + 1, J);
+  jump_to(hi, lo, (u64)(t & 31) + 1, J);
   const u64 ph = J.ph[8], pl = J.pl[8];
 #pragma unroll
   for (int j = 0; j < RNG_PER_THREAD; j++) {
@@ -416,9 +437,10 @@ __global__ void __launch_bounds__(RNG_THREADS) k_zig_scan(const __grid_constant_
                                                          unsigned* __restrict__ table, u64* __restrict__ ym_all) {
   __shared__ ZigShared sh;
   zig_init_shared(sh);
-  const ulonglong2 b = bs[blockIdx.x];
+  const ulonglong2* wsb = bs + (i64)blockIdx.x * ZIG_WARPS;
+  const ulonglong2 b = wsb[0];
   u64 raws[RNG_PER_THREAD];
-  zig_generate(sh, J, b, raws);
+  zig_generate(sh, J, wsb, raws);
   __syncthreads();
   zig_evaluate(sh, J, b, false);
   __syncthreads();
@@ -595,9 +617,9 @@ __global__ void __launch_bounds__(RNG_THREADS) k_zig_emit_fast(const __grid_cons
   __syncthreads();
   if (t < SEG_WORDS) s_prefix[t] = incl - c + (t >= 32 ? s_half : 0);
   __syncthreads();
-  const ulonglong2 b = bs[blockIdx.x];
+  const ulonglong2 b = bs[(i64)blockIdx.x * ZIG_WARPS + (t >> 5)];
   u64 hi = b.x, lo = b.y;
-  jump_to(hi, lo, (u64)t + 1, J);
+  jump_to(hi, lo, (u64)lane + 1, J);
   const u64 ph = J.ph[8], pl = J.pl[8];
   // INNER: every value of this segment lands before the last wanted element (all but the final segments), so the
   // output-range tests drop out of the loop
@@ -656,9 +678,10 @@ __global__ void __launch_bounds__(RNG_THREADS, 3) k_zig_emit(const __grid_consta
   const i64 seg_base = (i64)blockIdx.x * SEG;
   const int entry = seg_entry[blockIdx.x];
   const int t = threadIdx.x;
-  const ulonglong2 b = bs[blockIdx.x];
+  const ulonglong2* wsb = bs + (i64)blockIdx.x * ZIG_WARPS;
+  const ulonglong2 b = wsb[0];
   u64 raws[RNG_PER_THREAD];
-  zig_generate(sh, J, b, raws);
+  zig_generate(sh, J, wsb, raws);
   __syncthreads();
   zig_evaluate(sh, J, b, true);
   __syncthreads();
@@ -732,9 +755,10 @@ __global__ void __launch_bounds__(RNG_THREADS, 3) k_zig_onepass(const __grid_con
   zig_init_shared(sh);  // ends with a barrier
   const i64 seg = s_seg;
   const i64 seg_base = seg * SEG;
-  const ulonglong2 b = bs[seg];
+  const ulonglong2* wsb = bs + seg * ZIG_WARPS;
+  const ulonglong2 b = wsb[0];
   u64 raws[RNG_PER_THREAD];
-  zig_generate(sh, J, b, raws);
+  zig_generate(sh, J, wsb, raws);
   __syncthreads();
   zig_evaluate(sh, J, b, true);
   __syncthreads();
@@ -943,6 +967,7 @@ int randn_impl(um_rng* g, const um_view* dst, double mean, double sd, int affine
   double* out = static_cast<double*>(dst->data) + dst->offset;
   cudaStream_t st = ctx()->stream;
   const Jump J = make_jump(inc_of(g));
+  if (J.mh[8] != STRIDE256_MH || J.ml[8] != STRIDE256_ML) return fail(UM_ERR_CUDA, "rng: stride-256 multiplier constant is wrong");
   while (n > 0) {
     // 1.0173 draws per value on average; 3 % + two segments of margin makes a second round rare
     i64 nseg = (i64)((double)n * 1.03 / SEG) + 2;
@@ -953,7 +978,7 @@ int randn_impl(um_rng* g, const um_view* dst, double mean, double sd, int affine
     const size_t tab_off = off; off += up((size_t)nseg * ZIG_ENTRIES * sizeof(unsigned));
     const size_t base_off = off; off += up((size_t)nseg * sizeof(i64));
     const size_t entry_off = off; off += up((size_t)nseg);
-    const size_t bs_off = off; off += up((size_t)nseg * sizeof(ulonglong2));
+    const size_t bs_off = off; off += up((size_t)nseg * ZIG_WARPS * sizeof(ulonglong2));
     const size_t ym_off = off; off += up((size_t)nseg * SEG_WORDS * sizeof(u64));
     const size_t map_off = off; off += up(std::max((size_t)pf_blocks * sizeof(BlockMap), (size_t)nseg * sizeof(int)));
     const size_t start_off = off; off += up((size_t)pf_blocks * sizeof(BlockStart));
@@ -969,8 +994,11 @@ int randn_impl(um_rng* g, const um_view* dst, double mean, double sd, int affine
     BlockStart* starts = reinterpret_cast<BlockStart*>(ws + start_off);
     i64* result = reinterpret_cast<i64*>(ws + res_off);
     UM_CUDA(cudaMemsetAsync(result, 0, 64, st));
-    s = launch_block_states(J, g, nseg, 12, bs);
-    if (s != UM_OK) return s;
+    {
+      const i64 threads = (nseg + BS_CHUNK - 1) / BS_CHUNK;
+      k_zig_warp_states<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(J, g->state_hi, g->state_lo, nseg, bs);
+      UM_LAUNCHED();
+    }
     if (g_randn_path.load() == 2) {
       // single pass: the table area doubles as the published maps; seg_base / seg_entry areas hold the inclusive results
       unsigned* flag = reinterpret_cast<unsigned*>(ym_all);            // nseg words (+1 ticket) inside the unused mask area
