@@ -133,6 +133,29 @@ def test_randn_single_pass_and_multi_kernel_paths_are_identical(u, n):
     assert_normal_stream_equal(outs[1][0], np.random.default_rng(2024).standard_normal(n))
 
 
+def test_randn_one_call_of_2_30_draws_equals_chunked_calls(u):
+    """Size-independent property at BASELINE scale (32768^2 = 2^30 draws, more than 128 prefix blocks): one fill of
+    the whole matrix holds exactly the numbers of eight consecutive fills of its row blocks (each of a size the
+    NumPy comparisons above cover), and both generators end in the same state."""
+    import ctypes as C
+    rows, cols = 32768, 32768
+    g1 = u.NumPyRNG(31)
+    a = g1.randn(rows, cols)
+    g2 = u.NumPyRNG(31)
+    b = u.Mat._alloc(rows, cols, u._lib.F64)
+    step = rows // 8
+    for r0 in range(0, rows, step):
+        u._lib.check(u._lib.lib.um_rng_randn(C.byref(g2._g), b._raw_slice(r0, r0 + step, 0, cols)._ref()))
+    assert g1.state == g2.state
+    assert a.ne(b).any() is False
+    del a, b
+    a = u.NumPyRNG(32).rand(rows, cols)
+    g3, b = u.NumPyRNG(32), u.Mat._alloc(rows, cols, u._lib.F64)
+    for r0 in range(0, rows, step):
+        u._lib.check(u._lib.lib.um_rng_rand(C.byref(g3._g), b._raw_slice(r0, r0 + step, 0, cols)._ref()))
+    assert a.ne(b).any() is False
+
+
 def test_uniform_and_normal_transforms(u):
     g = u.NumPyRNG(3)
     r = np.random.default_rng(3)
