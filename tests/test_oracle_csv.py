@@ -108,3 +108,39 @@ def test_abi_parses_files_like_the_oracle(golden_dir, nasty, tmp_path):
     assert np.array_equal(io.parse_host(str(tmp_path / "big.csv"))[1], big)
     with pytest.raises(ValueError, match="cannot read"):
         io.parse_host(str(tmp_path / "missing.csv"))
+
+
+def test_abi_readers_agree_with_oracle_on_random_ragged_files(tmp_path):
+    """Differential test of both readers of csv.cu -- the parallel quote-free one and the sequential quoted one (forced by
+    appending one quoted field) -- against the oracle: ragged rows, blank and delimiter-only rows, \\n / \\r\\n / \\r line
+    ends, a BOM, all four delimiters, with and without a header row."""
+    import random
+    from uni_b200 import io
+    random.seed(3)
+    cells = ["1", "-2.5", "3e2", "abc", "", "  7 ", "1,5", "$4", "12%", "NaN", "1e400", "-0", ".5", "5.", "+3", "x y", "0x1", "1e-400", "--1", "+-2"]
+
+    def gen(delim, eol, bom, header, nrows):
+        rows = []
+        if header:
+            rows.append(delim.join(random.choice(["id", "name", "", " px ", "v"]) for _ in range(random.randint(1, 5))))
+        for _ in range(nrows):
+            k = random.randint(0, 6)
+            if k == 0:
+                rows.append(random.choice(["", "   ", "\t" if delim != "\t" else " ", delim, delim + " " + delim]))
+            else:
+                cs = [random.choice(cells) for _ in range(k)]
+                if delim == ",":
+                    cs = [c for c in cs if "," not in c] or ["1"]
+                rows.append(delim.join(cs))
+        txt = eol.join(rows) + (eol if random.random() < 0.5 else "")
+        return (b"\xef\xbb\xbf" if bom else b"") + txt.encode()
+
+    p = tmp_path / "r.csv"
+    for _ in range(400):
+        delim = random.choice([",", ";", "\t", "|"])
+        data = gen(delim, random.choice(["\n", "\r\n", "\r"]), random.random() < 0.2, random.random() < 0.5, random.randint(0, 12))
+        for blob in (data, data + (b'\n"9"' if data and not data.endswith((b"\n", b"\r")) else b'"9"')):
+            p.write_bytes(blob)
+            h, a = io.parse_host(str(p), delim)
+            ho, ao = co.load_smart(str(p), delim)
+            assert h == ho and a.shape == ao.shape and np.array_equal(a, ao, equal_nan=True), blob

@@ -43,6 +43,29 @@ inline bool is_space(unsigned char c) { return c <= ' '; }  // String.trim: code
 double parse_cell(const char* p, size_t n) {
   while (n && is_space((unsigned char)p[0])) { p++; n--; }
   while (n && is_space((unsigned char)p[n - 1])) n--;
+  if (n == 0) return NAN;
+  {
+    // fast path: a plain literal (no ',' '$' '%'): from_chars reads java.math.BigDecimal's grammar once a leading '+' is
+    // dropped and a non-numeric first character ("inf", "nan") is refused; it must consume the whole field
+    bool plain = true;
+    for (size_t i = 0; i < n; i++)
+      if (p[i] == ',' || p[i] == '$' || p[i] == '%') { plain = false; break; }
+    if (plain) {
+      const char* q = p;
+      size_t m = n;
+      if (*q == '+') {
+        q++; m--;
+        if (m == 0 || *q == '+' || *q == '-') return NAN;
+      }
+      const char first = (*q == '-' && m > 1) ? q[1] : *q;
+      if (!((first >= '0' && first <= '9') || first == '.')) return NAN;
+      double v = 0.0;
+      const auto r = std::from_chars(q, q + m, v);
+      if (r.ec == std::errc() && r.ptr == q + m) return v == 0.0 ? 0.0 : v;
+      if (r.ec != std::errc::result_out_of_range) return NAN;
+      // overflow / underflow: the general routine below decides between Infinity and 0
+    }
+  }
   char buf[96];
   size_t m = 0;
   for (size_t i = 0; i < n; i++) {
@@ -146,6 +169,117 @@ void split_rows(const std::string& text, char delim, std::string& store, std::ve
   if (row_start.back() != fields.size()) fields.resize(row_start.back());
 }
 
+// Quote-free text (every numeric matrix file): rows are independent, so the text is cut at line ends into one byte range per
+// thread.  Pass A counts content rows and the widest row of each range, pass B converts the cells straight into the table.
+// '\r' and '\n' both end a row (the empty row inside "\r\n" has no content and is dropped like any blank row).
+struct PlainRange {
+  size_t a = 0, b = 0;
+  int64_t rows = 0;
+  size_t width = 0;
+};
+// on_row returns false to stop.  A row has content when some field is non-blank (FastCsv.isContentRow): a line of
+// delimiters and blanks only is dropped.
+template <class RowFn>
+void plain_rows(const char* s, size_t a, size_t b, char delim, RowFn&& on_row) {
+  size_t ls = a;
+  while (ls < b) {
+    size_t le = ls;
+    bool content = false;
+    while (le < b && s[le] != '\n' && s[le] != '\r') {
+      if (!is_space((unsigned char)s[le]) && s[le] != delim) content = true;
+      le++;
+    }
+    if (content && !on_row(ls, le)) return;
+    ls = le + 1;
+  }
+}
+inline size_t plain_width(const char* s, size_t ls, size_t le, char delim) {
+  size_t w = 1;
+  for (size_t i = ls; i < le; i++)
+    if (s[i] == delim) w++;
+  return w;
+}
+void open_plain(const std::string& text, char delim, CsvTable* t) {
+  const char* s = text.data();
+  const size_t n = text.size();
+  size_t i0 = 0;
+  if (n >= 3 && (unsigned char)s[0] == 0xEF && (unsigned char)s[1] == 0xBB && (unsigned char)s[2] == 0xBF) i0 = 3;
+  const int nthreads = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), (n - i0) / (1u << 18) + 1);
+  std::vector<PlainRange> rg((size_t)nthreads);
+  size_t prev = i0;
+  for (int k = 0; k < nthreads; k++) {
+    size_t e = k + 1 == nthreads ? n : i0 + (n - i0) / (size_t)nthreads * (size_t)(k + 1);
+    if (e < prev) e = prev;
+    while (e < n && s[e] != '\n' && s[e] != '\r') e++;  // end the range at a line end
+    if (e < n) e++;
+    rg[(size_t)k].a = prev;
+    rg[(size_t)k].b = e;
+    prev = e;
+  }
+  auto run = [&](auto&& fn) {
+    if (nthreads == 1) { fn(0); return; }
+    std::vector<std::thread> pool;
+    for (int k = 0; k < nthreads; k++) pool.emplace_back(fn, k);
+    for (auto& th : pool) th.join();
+  };
+  run([&](int k) {
+    PlainRange& r = rg[(size_t)k];
+    plain_rows(s, r.a, r.b, delim, [&](size_t ls, size_t le) {
+      r.rows++;
+      r.width = std::max(r.width, plain_width(s, ls, le, delim));
+      return true;
+    });
+  });
+  int64_t nrows_all = 0;
+  size_t width = 0;
+  for (auto& r : rg) { nrows_all += r.rows; width = std::max(width, r.width); }
+  if (nrows_all == 0) return;
+  // the first two content rows decide the header (FileOps.scala:154-166)
+  std::vector<std::pair<size_t, size_t>> head;
+  plain_rows(s, i0, n, delim, [&](size_t ls, size_t le) {
+    head.emplace_back(ls, le);
+    return head.size() < 2;
+  });
+  auto row_cells = [&](size_t ls, size_t le, auto&& on_cell) {
+    size_t c = 0, fs = ls;
+    for (size_t i = ls; i <= le; i++)
+      if (i == le || s[i] == delim) { on_cell(c++, fs, i); fs = i + 1; }
+  };
+  int64_t header = 0;
+  if (nrows_all > 1) {
+    bool row0_text = true, row1_data = false;
+    row_cells(head[0].first, head[0].second, [&](size_t, size_t a, size_t b) { if (!std::isnan(parse_cell(s + a, b - a))) row0_text = false; });
+    row_cells(head[1].first, head[1].second, [&](size_t, size_t a, size_t b) { if (!std::isnan(parse_cell(s + a, b - a))) row1_data = true; });
+    if (row0_text && row1_data) header = 1;
+  }
+  if (header) {  // namedHeaders (FileOps.scala:117-121)
+    t->headers.assign(width, std::string());
+    row_cells(head[0].first, head[0].second, [&](size_t c, size_t a, size_t b) {
+      while (a < b && is_space((unsigned char)s[a])) a++;
+      while (b > a && is_space((unsigned char)s[b - 1])) b--;
+      t->headers[c].assign(s + a, b - a);
+    });
+    for (size_t c = 0; c < width; c++)
+      if (t->headers[c].empty()) t->headers[c] = "col" + std::to_string(c + 1);
+  }
+  t->has_header = header != 0;
+  t->rows = nrows_all - header;
+  t->cols = (int64_t)width;
+  t->data.assign((size_t)t->rows * width, NAN);  // cells a short row does not have stay NaN (FastCsv.rectangular)
+  std::vector<int64_t> first((size_t)nthreads + 1, 0);
+  for (int k = 0; k < nthreads; k++) first[(size_t)k + 1] = first[(size_t)k] + rg[(size_t)k].rows;
+  run([&](int k) {
+    int64_t r = first[(size_t)k];
+    plain_rows(s, rg[(size_t)k].a, rg[(size_t)k].b, delim, [&](size_t ls, size_t le) {
+      const int64_t out_r = r++ - header;
+      if (out_r < 0) return true;
+      double* dst = t->data.data() + (size_t)out_r * width;
+      row_cells(ls, le, [&](size_t c, size_t a, size_t b) { dst[c] = parse_cell(s + a, b - a); });
+      return true;
+    });
+  });
+}
+
 char detect_delimiter(const std::string& text) {
   size_t i = 0;
   while (i < text.size()) {  // first line with content
@@ -247,6 +381,19 @@ int32_t um_csv_open(const char* path, int32_t delimiter, uint64_t* handle, int64
   while ((got = fread(chunk, 1, sizeof(chunk), f)) > 0) text.append(chunk, got);
   fclose(f);
   const char delim = delimiter > 0 ? (char)delimiter : detect_delimiter(text);
+  if (memchr(text.data(), '"', text.size()) == nullptr) {  // no quoted field anywhere: rows can be cut apart in parallel
+    CsvTable* tp = new CsvTable();
+    open_plain(text, delim, tp);
+    {
+      std::lock_guard<std::mutex> lk(g_csv_mu);
+      *handle = g_csv_next++;
+      g_csv[*handle] = tp;
+    }
+    *rows = tp->rows;
+    *cols = tp->cols;
+    if (has_header) *has_header = tp->has_header ? 1 : 0;
+    return UM_OK;
+  }
   std::string store;
   std::vector<Field> fields;
   std::vector<size_t> row_start;
