@@ -85,3 +85,20 @@ def test_ziggurat_tables_shape():
     ki, wi, fi = ro.ziggurat_tables()
     assert ki[1] == 0 and fi[0] == 1.0 and abs(wi[255] * 2.0**52 - ro.ZIG_R) < 1e-12
     assert abs(1.0 / ro.ZIG_R - ro.ZIG_INV_R) < 1e-16
+
+
+def test_abi_jump_ahead_is_additive_and_matches_numpy_advance():
+    """um_rng_advance (the host twin of the per-thread jumps the kernels take): advance(a) then advance(b) equals
+    advance(a + b) equals NumPy's PCG64.advance, for deltas spanning every bit of a 64-bit count."""
+    import uni_b200 as u
+    rng = np.random.default_rng(77)
+    for seed in (0, 5, 2**40 + 1):
+        for _ in range(20):
+            a = int(rng.integers(0, 2**62)) >> int(rng.integers(0, 62))
+            b = int(rng.integers(0, 2**62)) >> int(rng.integers(0, 62))
+            g1, g2 = u.NumPyRNG(seed), u.NumPyRNG(seed)
+            g1.advance(a); g1.advance(b)
+            g2.advance(a + b)
+            ref = np.random.PCG64(seed); ref.advance(a + b)
+            assert g1.state == g2.state == (ref.state["state"]["state"], ref.state["state"]["inc"])
+            assert g1.nextLong() & ro.M64 == int(ref.random_raw())
