@@ -251,6 +251,8 @@ typedef struct um_tprf_out {
   double* forecasts;   /* T                                                            */
   double* residuals;   /* T                                                            */
   double* alpha;       /* N_local      closed form / IS Full `alpha` (Tprf3.scala:207,1240-1250) */
+  /* the four pass-1/2/3 fields are filled for EVERY mode, UM_TPRF_CLOSED included: tprfClosedForm
+   * returns them too (Tprf3.scala:211-231,243-252) and they equal t3prf's */
   double* phi;         /* N_local x L  pass-1 slopes (Tprf3.scala:263-264)                 */
   double* phi_hat;     /* (L+1) x N_local  B1 incl. intercept row (Tprf3.scala:263)        */
   double* sigma;       /* T x L        pass-2 factors (Tprf3.scala:266-267)                */
@@ -258,13 +260,19 @@ typedef struct um_tprf_out {
   double* xstd;        /* N_local      column sample std (nanStdCols, Tprf3.scala:469-502) */
   /* host scalars, written after a stream sync */
   double r_squared;    /* closed/t3prf: ssy==0 -> 0 (Tprf3.scala:239-241); IS Full: unguarded (:1214-1225) */
-  int32_t singular;    /* 1 if a small solve hit an exact-zero pivot                       */
+  int32_t singular;    /* 1 if a small solve hit an exact-zero pivot: the call then returns UM_ERR_SINGULAR
+                        * (ArithmeticException in the reference, Mat.scala:990) and the outputs that needed
+                        * that inverse hold NaN                                                          */
 } um_tprf_out;
 
 typedef enum um_tprf_mode {
   UM_TPRF_CLOSED = 0,   /* Tprf3.tprfClosedForm  (Tprf3.scala:199-252)                     */
   UM_TPRF_ITER = 1,     /* Tprf3.t3prf           (Tprf3.scala:260-289)                     */
-  UM_TPRF_IS_FULL = 2   /* Tprf3.estimate3prf(.., "IS Full") (Tprf3.scala:1056-1110,1206-1250) */
+  UM_TPRF_IS_FULL = 2,  /* Tprf3.estimate3prf(.., "IS Full") (Tprf3.scala:1056-1110,1206-1250): T < 10 -> NaN
+                         * fit; pass 3 is nanOls (rows with a NaN in y or Sigma left out, :929-931); R^2 over
+                         * the rows that have a residual, no zero guard                                  */
+  UM_TPRF_WINDOW = 3    /* one out-of-sample window of estimate3prf: runT3prf -> t3prfFast -> t3prfTail
+                         * (Tprf3.scala:883-943) = t3prf's passes 1 and 2 with the nanOls pass 3             */
 } um_tprf_mode;
 
 /* Single-GPU (or this rank's column shard when a communicator is active: X holds the local
@@ -297,7 +305,7 @@ int32_t um_tprf_fused_info(int64_t T, int32_t* cluster_size, int32_t* rows_per_p
 /* Out-of-sample point forecast of one window (t3prfTail's `yhatt`, Tprf3.scala:913-943), from the outputs of
  * um_tprf_fit(UM_TPRF_ITER) on the window's kept rows: phi (N x L), xstd (N), beta3 (L+1), and the held-out row
  * xt (1 x N, any column stride).  estimate3prf's OOS procedures (Tprf3.scala:1112-1199) call it once per window.
- * Synchronises; NaN when [1|Phi]'[1|Phi] has an exact-zero pivot. */
+ * Synchronises; UM_ERR_SINGULAR (and NaN) when [1|Phi]'[1|Phi] has an exact-zero pivot. */
 int32_t um_tprf_oos_forecast(const um_view* phi, const um_view* xstd, const um_view* beta3, const um_view* xt, double* host_out);
 /* accounting for bench.py: algorithmic flops/bytes of one fit */
 int32_t um_tprf_work(int64_t T, int64_t N, int64_t L, double* flops, double* bytes);

@@ -182,7 +182,11 @@ def _window_fit(yt, Xt, inv_sd, Zt, xt=None, min_obs=10):
     dps = dP * inv_sd.reshape(-1, 1)
     sigma = ((Xt @ dps) @ PtPinv.T)[:, 1 : L + 1]
     Xaug = with_intercept(sigma)
-    beta = lu_inverse(Xaug.T @ Xaug) @ (Xaug.T @ yt)
+    # pass 3 is nanOls(y, Xaug, minObs = 1) (Tprf3.scala:929-931): rows with a NaN in y or Sigma are left out; no
+    # usable row -> NaN coefficients.  On NaN-free data it is the plain normal-equations solve.
+    beta = nan_ols(yt, Xaug, 1)
+    if beta is None:
+        beta = np.full((L + 1, 1), np.nan)
     yhatt = float("nan")
     if xt is not None:
         bo = (xt.reshape(1, -1) @ dps) @ PtPinv.T
@@ -271,6 +275,7 @@ def estimate3prf(y, X, Z, procedure="IS Full", window=(0, 1), mintrain=(-1, 0), 
     rollfore = np.full((T, 1), np.nan)
 
     eff_pls = bool(pls) and auto
+    has_nan = bool(np.isnan(X).any() or np.isnan(y).any() or (Zm is not None and np.isnan(Zm).any()))   # Tprf3.scala:1078
 
     def nanmean(v):
         ok = ~np.isnan(v)
@@ -309,19 +314,19 @@ def estimate3prf(y, X, Z, procedure="IS Full", window=(0, 1), mintrain=(-1, 0), 
             keep = np.r_[0:lo, hi:T]
             yt = y[keep]
             forecasts[t, 0] = window_forecast(yt, Xn[keep], None if auto else Zm[keep], Xn[t])
-            rollfore[t, 0] = nanmean(yt[:, 0]) if eff_pls else yt.mean()
+            rollfore[t, 0] = nanmean(yt[:, 0]) if (eff_pls or has_nan) else yt.mean()   # colMean(yt, hasNan)
     elif procedure == "OOS Recursive":
         for t in range(mt[0] + 1 + mt[1], T):
             end = t - 1 - mt[1]
             yt = y[:end]
             forecasts[t, 0] = window_forecast(yt, Xn[:end], None if auto else Zm[:end], Xn[t], mt[0])
-            rollfore[t, 0] = nanmean(yt[:, 0]) if eff_pls else yt.mean()
+            rollfore[t, 0] = nanmean(yt[:, 0]) if (eff_pls or has_nan) else yt.mean()   # colMean(yt, hasNan)
     elif procedure == "OOS Rolling":
         for t in range(win + 1 + gap, T):
             lo, hi = max(t - win - gap, 0), min(t - 1 - gap, T)
             yt = y[lo:hi]
             forecasts[t, 0] = window_forecast(yt, Xn[lo:hi], None if auto else Zm[lo:hi], Xn[t], min_nona)
-            rollfore[t, 0] = nanmean(yt[:, 0]) if eff_pls else yt.mean()
+            rollfore[t, 0] = nanmean(yt[:, 0]) if (eff_pls or has_nan) else yt.mean()   # colMean(yt, hasNan)
     else:
         raise ValueError(f"Unknown procedure '{procedure}'. Choose: 'IS Full', 'OOS Recursive', 'OOS Cross Val', 'OOS Rolling'")
 

@@ -109,6 +109,12 @@ def test_all_outputs_vs_oracle(u, tnl):
     assert close(it.phiHat.to_numpy(), oi.phi_hat, rtol=1e-8, atol=1e-12)
     assert close(it.sigma.to_numpy(), oi.sigma, rtol=1e-8, atol=1e-11)
     assert close(it.beta3.to_numpy(), oi.beta3, rtol=1e-7, atol=1e-11)
+    # tprfClosedForm carries the pass-1/2/3 fields too (Tprf3.scala:211-231,243-252): they are t3prf's
+    assert close(c.phi.to_numpy(), oi.phi, rtol=1e-8, atol=1e-12) and close(c.phiHat.to_numpy(), oi.phi_hat, rtol=1e-8, atol=1e-12)
+    assert close(c.sigma.to_numpy(), oi.sigma, rtol=1e-8, atol=1e-11) and close(c.beta3.to_numpy(), oi.beta3, rtol=1e-7, atol=1e-11)
+    if N <= 300:
+        assert close(c.phi.to_numpy(), oc.phi, rtol=1e-8, atol=1e-12) and close(c.sigma.to_numpy(), oc.sigma, rtol=1e-8, atol=1e-11)
+        assert close(c.beta3.to_numpy(), oc.beta3, rtol=1e-7, atol=1e-11) and close(c.phiHat.to_numpy(), oc.phi_hat, rtol=1e-8, atol=1e-12)
     # tprfClosedForm == t3prf == IS Full (TprfSuite.scala:20-34)
     assert close(c.forecasts.to_numpy(), it.forecasts.to_numpy())
     if T >= 10:
@@ -355,9 +361,63 @@ def test_oos_windows_on_a_wide_panel(u):
     r = u.estimate3prf(dy, dX, dZ, "OOS Rolling", rollwin=(40, 20, 1))
     o = to.estimate3prf(y, X, Z, "OOS Rolling", rollwin=(40, 20, 1))
     assert close(r.forecasts.to_numpy(), o.forecasts) and close(r.rSquared, o.r_squared)
-    with pytest.raises(NotImplementedError):
-        Xn = X.copy(); Xn[3, 5] = np.nan
-        u.estimate3prf(dy, u.Mat.from_numpy(Xn), dZ, "OOS Rolling")
+    # NaN input without pls (Tprf3.scala:883-943): a NaN in X spreads through every window that holds its row and
+    # through the forecast of its own row; windows clear of it still forecast
+    Xn = X.copy(); Xn[3, 5] = np.nan
+    r = u.estimate3prf(dy, u.Mat.from_numpy(Xn), dZ, "OOS Rolling", rollwin=(40, 20, 1))
+    o = to.estimate3prf(y, Xn, Z, "OOS Rolling", rollwin=(40, 20, 1))
+    f = r.forecasts.to_numpy()
+    assert np.array_equal(np.isnan(f), np.isnan(o.forecasts)) and np.isfinite(f).any() and np.isnan(f[42:45]).all()
+    assert close(f, o.forecasts) and close(r.rSquared, o.r_squared)
+    # a NaN in y only takes its row out of pass 3 (nanOls, :929-931) and out of R^2 (`loc`, :1207)
+    yn = y.copy(); yn[50, 0] = np.nan
+    r = u.estimate3prf(u.Mat.from_numpy(yn), dX, dZ, "OOS Recursive", mintrain=(60, 0))
+    o = to.estimate3prf(yn, X, Z, "OOS Recursive", mintrain=(60, 0))
+    assert close(r.forecasts.to_numpy(), o.forecasts) and close(r.rSquared, o.r_squared)
+    assert np.isfinite(r.forecasts.to_numpy()[61:]).all()
+
+
+def test_nan_input_is_full(u):
+    """estimate3prf "IS Full" with NaN input and no pls: X or Z -> every forecast NaN, R^2 NaN; y -> that row dropped
+    from pass 3 and from R^2, the other rows forecast (Tprf3.scala:883-943, 1206-1225)."""
+    rng = np.random.default_rng(5)
+    T, N, Lp = 64, 300, 3
+    X = rng.standard_normal((T, N)); y = rng.standard_normal((T, 1)) + X[:, :1]; Z = rng.standard_normal((T, Lp)) + X[:, :Lp]
+    Xn = X.copy(); Xn[10, 7] = np.nan
+    r = u.estimate3prf(*devs(u, y, Xn, Z))
+    assert np.isnan(r.forecasts.to_numpy()).all() and np.isnan(r.rSquared) and not r.singular
+    Zn = Z.copy(); Zn[5, 1] = np.nan
+    r = u.estimate3prf(*devs(u, y, X, Zn))
+    assert np.isnan(r.forecasts.to_numpy()).all() and np.isnan(r.rSquared)
+    yn = y.copy(); yn[20, 0] = np.nan
+    r = u.estimate3prf(*devs(u, yn, X, Z))
+    o = to.estimate3prf(yn, X, Z)
+    f = r.forecasts.to_numpy()
+    assert np.isfinite(f).all() and close(f, o.forecasts) and close(r.rSquared, o.r_squared)
+    assert np.isnan(r.residuals.to_numpy()[20, 0]) and np.isnan(r.alpha.to_numpy()).all()   # alpha = ... (XtJt y): NaN (:1245-1248)
+    # t3prf / tprfClosedForm take the plain products: a NaN anywhere poisons them (Tprf3.scala:229-231,268-269)
+    assert np.isnan(u.t3prf(*devs(u, yn, X, Z)).forecasts.to_numpy()).all()
+    assert np.isnan(u.tprfClosedForm(*devs(u, yn, X, Z)).forecasts.to_numpy()).all()
+
+
+def test_singular_gram_raises(u):
+    """An exact-zero pivot in a fit's small inverse is the reference's ArithmeticException("Matrix is singular or nearly
+    singular") (Mat.scala:990): duplicated / constant proxy columns, in every fit and in an out-of-sample window."""
+    rng = np.random.default_rng(6)
+    T, N = 48, 200
+    X = rng.standard_normal((T, N)); y = rng.standard_normal((T, 1))
+    z = np.round(rng.standard_normal((T, 1)) * 8) / 8          # exactly representable: the duplicate cancels exactly
+    Zdup = np.column_stack([z, z])
+    for fit in (u.tprfClosedForm, u.t3prf, u.estimate3prf):
+        with pytest.raises(u.SingularMatrixError):
+            fit(*devs(u, y, X, Zdup))
+    Zc = np.column_stack([z, np.zeros(T)])                      # a constant (zero) proxy: dZ'dZ has a zero pivot
+    with pytest.raises(u.SingularMatrixError):
+        u.t3prf(*devs(u, y, X, Zc))
+    with pytest.raises(u.SingularMatrixError):
+        u.estimate3prf(*devs(u, y, X, Zdup), "OOS Recursive", mintrain=(40, 0))
+    ok = u.t3prf(*devs(u, y, X, np.column_stack([z, rng.standard_normal(T)])))
+    assert not ok.singular and np.isfinite(ok.forecasts.to_numpy()).all()
 
 
 # ---------------------------------------------------------------- PLS variant
@@ -425,10 +485,11 @@ def test_estimate3prf_pls_gappy_panels_vs_numpy_reference_and_oracle(u, golden_d
         assert np.allclose(got[ok], want[ok], rtol=1e-9, atol=1e-12), (f, np.max(np.abs(got[ok] - want[ok])))
         o = to.estimate3prf(y, X, int(g["L"]), proc, pls=True, **kw)
         assert np.isclose(r.rSquared, o.r_squared, rtol=1e-9, atol=1e-12, equal_nan=True), f
-    # NaN input without the pls branch is refused (the intercept path would return all-NaN forecasts)
+    # the same gappy panel without pls: the matrix passes spread the NaNs to every forecast (Tprf3.scala:883-943)
     y, X = pls_panel(43, 90, 15, True)
-    with pytest.raises(NotImplementedError):
-        u.estimate3prf(u.Mat.from_numpy(y), u.Mat.from_numpy(X), 2, "IS Full")
+    r = u.estimate3prf(u.Mat.from_numpy(y), u.Mat.from_numpy(X), 2, "IS Full")
+    o = to.estimate3prf(y, X, 2, "IS Full")
+    assert np.isnan(r.forecasts.to_numpy()).all() and np.isnan(o.forecasts).all() and np.isnan(r.rSquared)
 
 
 def test_pls_closed_form_agrees_with_estimate3prf_pls(u):

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libunimat.so")
+# UNIMAT_LIB: development override (A/B timing of kernel variants built side by side); the product path is the in-tree library
+LIB_PATH = os.environ.get("UNIMAT_LIB") or os.path.join(_HERE, "libunimat.so")
 
 UM_OK, UM_ERR_ARG, UM_ERR_SINGULAR, UM_ERR_EMPTY, UM_ERR_CUDA, UM_ERR_NCCL, UM_ERR_OOM = range(7)
 F64, F32, BOOL, I32 = 0, 1, 2, 3
@@ -21,7 +22,7 @@ ISNAN, ISINF, ISFINITE = range(3)
 AND, OR, NOT, XOR = range(4)
 SUM, MEAN, VAR, STD, MIN, MAX = range(6)
 CUMSUM, CUMMAX, CUMMIN = range(3)
-TPRF_CLOSED, TPRF_ITER, TPRF_IS_FULL = range(3)
+TPRF_CLOSED, TPRF_ITER, TPRF_IS_FULL, TPRF_WINDOW = range(4)
 
 
 class UmView(C.Structure):

@@ -520,6 +520,7 @@ struct FinishArgs {
   const double* small;          // prep output (zbar | Szz | ybar | ssy), SMALL_PREP per panel
   const double* y; i64 y_s, y_bs;
   i64 T; int L; double n_total; int mode;
+  int want3;                                           // CLOSED only: also run the three-pass finish for sigma / beta3 / phi (Tprf3.scala:211-231)
   double* forecasts; double* residuals; i64 f_bs;     // per panel stride (elements); may be null
   double* sigma; double* beta3;                        // single-panel outputs (may be null)
   double* sigma_ws;                                    // T x 8 workspace per panel
@@ -570,7 +571,7 @@ template <int CS>
 __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
   __shared__ double red[8][64];
   __shared__ double tot[64];
-  __shared__ double cbuf[4][CS][64];   // one exchange buffer per reduction stage (no reuse, no second barrier)
+  __shared__ double cbuf[5][CS][64];   // one exchange buffer per reduction stage (no reuse, no second barrier)
   __shared__ double lu_a[81], lu_inv[81], lu_x[81];   // warp-cooperative small inverses (small_linalg.cuh)
   __shared__ int lu_piv[9];
   const int crank = CS > 1 ? (int)t_cluster_rank() : 0;
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
   const double ybar = ybar_s, ssy = ssy_s, smu = smu_s;
   double r2 = 0.0;
 
-  if (g.mode != UM_TPRF_ITER) {
+  if (g.mode != UM_TPRF_ITER && g.mode != UM_TPRF_WINDOW) {
     // ---- closed form: G = PX - 1 smw' - (h0 - smu) wbar' ; s = (G'G)^-1 G'y ----
     double loc[44];
 #pragma unroll
@@ -668,7 +669,11 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
     }
   }
 
-  if (g.mode != UM_TPRF_CLOSED) {
+  // tprfClosedForm also returns the pass-1/2/3 quantities (phi, sigma, beta3, phiHat: Tprf3.scala:211-231,243-252),
+  // which are those of t3prf: the same block runs for CLOSED when they were asked for, without touching yhat / R^2
+  const bool three = g.mode != UM_TPRF_CLOSED || g.want3 != 0;
+  const bool three_fc = g.mode != UM_TPRF_CLOSED;
+  if (three) {
     // ---- three-pass fit from the same accumulators ----
     if (tid < 32) {
       if (tid == 0)
@@ -727,9 +732,13 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
       }
     }
     __syncthreads();
-    double loc[54];
+    // estimate3prf's pass 3 is nanOls(y, [1 | Sigma], minObs = 1) (Tprf3.scala:929-931, 807-830): rows with a NaN in y
+    // or Sigma are left out of the normal equations, fewer than one usable row -> NaN coefficients.  t3prf and
+    // tprfClosedForm take the plain product (:268-269, :229-231), where a NaN poisons the fit.
+    const bool nan_rows = g.mode == UM_TPRF_IS_FULL || g.mode == UM_TPRF_WINDOW;
+    double loc[55];
 #pragma unroll
-    for (int i = 0; i < 54; ++i) loc[i] = 0.0;
+    for (int i = 0; i < 55; ++i) loc[i] = 0.0;
     for (i64 t = (i64)crank * 256 + tid; t < T; t += STRIDE) {
       double d[LP + 1];
       d[0] = 1.0;
@@ -745,16 +754,23 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
         d[1 + l] = l < L ? s : 0.0;
         sig_ws[t * LP + l] = d[1 + l];
       }
+      const double yt = y[t * g.y_s];
+      if (nan_rows) {
+        bool ok = yt == yt;
+#pragma unroll
+        for (int a = 1; a <= LP; ++a) ok = ok && d[a] == d[a];
+        if (!ok) continue;
+        loc[54] += 1.0;
+      }
       int q = 0;
 #pragma unroll
       for (int a = 0; a <= LP; ++a)
 #pragma unroll
         for (int c = a; c <= LP; ++c) loc[q++] += d[a] * d[c];
-      const double yt = y[t * g.y_s];
 #pragma unroll
       for (int a = 0; a <= LP; ++a) loc[45 + a] += d[a] * yt;
     }
-    block_sum<54, CS>(loc, red, tot, tid, cbuf[2]);
+    block_sum<55, CS>(loc, red, tot, tid, cbuf[2]);
     if (tid < 32) {
       if (tid == 0) {
         double full[LP + 1][LP + 1];
@@ -765,32 +781,62 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
           for (int c = 0; c < L1; ++c) lu_a[a * L1 + c] = full[a][c];
       }
       __syncwarp();
-      const bool ok = lu_inverse_warp(lu_a, L1, lu_inv, lu_x, lu_piv, tid);
-      if (tid == 0 && !ok) singular_s = 1;
+      const bool none = nan_rows && tot[54] < 1.0;   // no usable row: NaN coefficients, not a singular-matrix error
+      const bool ok = none ? false : lu_inverse_warp(lu_a, L1, lu_inv, lu_x, lu_piv, tid);
+      if (tid == 0 && !ok && !none) singular_s = 1;
       if (tid <= LP) {
         double s = 0.0;
-        if (tid < L1)
+        if (tid < L1 && ok)
           for (int c = 0; c < L1; ++c) s += lu_inv[tid * L1 + c] * tot[45 + c];
         beta[tid] = tid < L1 ? (ok ? s : nan("")) : 0.0;
       }
     }
     __syncthreads();
-    double see = 0.0;
+    double see = 0.0, sy = 0.0, cnt = 0.0;
     for (i64 t = (i64)crank * 256 + tid; t < T; t += STRIDE) {
       double f = beta[0];
 #pragma unroll
-      for (int l = 0; l < LP; ++l) f += sig_ws[t * LP + l] * beta[1 + l];
-      const double e = y[t * g.y_s] - f;
-      if (fc) fc[t] = f;
-      if (rs) rs[t] = e;
-      see += e * e;
+      for (int l = 0; l < LP; ++l)
+        if (l < L) f += sig_ws[t * LP + l] * beta[1 + l];
+      const double yt = y[t * g.y_s];
+      const double e = yt - f;
+      if (three_fc) {
+        if (fc) fc[t] = f;
+        if (rs) rs[t] = e;
+      }
+      if (!nan_rows || e == e) {   // IS Full: R^2 over the rows with a residual (`loc`, Tprf3.scala:1207)
+        see += e * e;
+        sy += yt;
+        cnt += 1.0;
+      }
       if (g.sigma)
         for (int l = 0; l < L; ++l) g.sigma[(b * T + t) * L + l] = sig_ws[t * LP + l];
     }
-    double l1[1] = {see};
-    block_sum<1, CS>(l1, red, tot, tid, cbuf[3]);
-    if (g.mode == UM_TPRF_ITER) r2 = ssy == 0.0 ? 0.0 : 1.0 - tot[0] / ssy;  // Tprf3.scala:274-275
-    else r2 = 1.0 - tot[0] / ssy;                                             // Tprf3.scala:1214-1225
+    double l3[3] = {see, sy, cnt};
+    block_sum<3, CS>(l3, red, tot, tid, cbuf[3]);
+    const double see_tot = tot[0];
+    if (g.mode == UM_TPRF_ITER || g.mode == UM_TPRF_WINDOW) r2 = ssy == 0.0 ? 0.0 : 1.0 - see_tot / ssy;  // Tprf3.scala:274-275
+    else if (g.mode == UM_TPRF_IS_FULL) {
+      // 1 - sum e^2 / sum (y - mean)^2 over `loc`, mean over `loc` too, no zero guard (Tprf3.scala:1214-1225)
+      const double mu = tot[1] / tot[2];
+      __syncthreads();   // everyone has read tot[] before the next reduction overwrites it
+      double syy = 0.0;
+      for (i64 t = (i64)crank * 256 + tid; t < T; t += STRIDE) {
+        double f = beta[0];
+#pragma unroll
+        for (int l = 0; l < LP; ++l)
+          if (l < L) f += sig_ws[t * LP + l] * beta[1 + l];
+        const double yt = y[t * g.y_s];
+        const double e = yt - f;
+        if (e == e) {
+          const double dd = yt - mu;
+          syy += dd * dd;
+        }
+      }
+      double l1[1] = {syy};
+      block_sum<1, CS>(l1, red, tot, tid, cbuf[4]);
+      r2 = 1.0 - see_tot / tot[0];
+    }
     if (crank == 0 && g.beta3 && tid < L1) g.beta3[b * L1 + tid] = beta[tid];
   }
   __syncthreads();
@@ -800,7 +846,7 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
     par[8 + tid] = wbar[tid];
     par[80 + tid] = small[tid];
   }
-  if (tid < LP * LP) par[16 + tid] = (g.mode != UM_TPRF_CLOSED) ? szzinv[tid] : 0.0;
+  if (tid < LP * LP) par[16 + tid] = three ? szzinv[tid] : 0.0;
   if (tid == 0) {
     par[88] = r2;
     par[89] = (double)singular_s;
@@ -856,6 +902,7 @@ __global__ void k_fill_nan(double* p, i64 n) {
 }  // namespace um
 #include "tprf_fused.cuh"
 #include "tprf_grid.cuh"
+#include "tprf_sym.cuh"
 namespace um {
 
 // ---- host orchestration ------------------------------------------------------------------------------------------
@@ -983,6 +1030,16 @@ static double g_split_share = [] {
   return e ? atof(e) : 0.73;
 }();
 
+// cluster sweep kernel: symmetric compute warps (tprf_sym.cuh) unless UM_TPRF_SYM=0 (the round-1 A-/B-warp kernel, kept
+// for side-by-side measurements)
+static const bool g_use_sym = [] {
+  const char* e = getenv("UM_TPRF_SYM");
+  return !(e && atoi(e) == 0);
+}();
+static fused::FusedKernel cluster_kernel_for(int R) { return g_use_sym ? sym::kernel_for(R) : fused::kernel_for(R); }
+static int cluster_threads() { return g_use_sym ? sym::NTHREADS : fused::NTHREADS; }
+static int cluster_smem() { return g_use_sym ? sym::SMEM_ALLOC : fused::SMEM_ALLOC; }
+
 typedef CUresult (*StreamWaitFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 static StreamWaitFn stream_wait_fn() {
   static StreamWaitFn fn = nullptr;
@@ -1002,9 +1059,9 @@ static int fused_clusters(int G, int R) {
   static int cache[5][fused::GMAX + 1] = {{0}};
   static bool attr_done[5] = {false, false, false, false, false};
   const int j = R / 128;
-  fused::FusedKernel kern = fused::kernel_for(R);
+  fused::FusedKernel kern = cluster_kernel_for(R);
   if (!attr_done[j]) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::SMEM_ALLOC) != cudaSuccess ||
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cluster_smem()) != cudaSuccess ||
         cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
       cudaGetLastError();
       return 0;
@@ -1014,8 +1071,8 @@ static int fused_clusters(int G, int R) {
   if (cache[j][G]) return cache[j][G] > 0 ? cache[j][G] : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(G * 64), 1, 1);
-  cfg.blockDim = dim3(fused::NTHREADS, 1, 1);
-  cfg.dynamicSmemBytes = fused::SMEM_ALLOC;
+  cfg.blockDim = dim3((unsigned)cluster_threads(), 1, 1);
+  cfg.dynamicSmemBytes = (size_t)cluster_smem();
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = (unsigned)G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1190,8 +1247,8 @@ static int run_fused(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_b
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nclu * p.fG), 1, 1);
-  cfg.blockDim = dim3(fused::NTHREADS, 1, 1);
-  cfg.dynamicSmemBytes = fused::SMEM_ALLOC;
+  cfg.blockDim = dim3((unsigned)cluster_threads(), 1, 1);
+  cfg.dynamicSmemBytes = (size_t)cluster_smem();
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1203,7 +1260,7 @@ static int run_fused(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_b
     UM_CUDA(cudaEventRecord(ev_fork, st));          // everything before the sweep (prep, the counter reset)
     UM_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, fused::kernel_for(p.fR), mx, m0, a);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, cluster_kernel_for(p.fR), mx, m0, a);
   if (e != cudaSuccess) return fail(UM_ERR_CUDA, "fused 3PRF sweep launch failed: %s", cudaGetErrorString(e));
   UM_LAUNCHED();
   if (split) {
@@ -1310,8 +1367,10 @@ static int run_prep(const Plan3& p, char* ws, const double* Z, i64 z_rs, i64 z_c
 }
 
 static int run_finish(const Plan3& p, char* ws, int mode, const double* y, i64 y_s, i64 y_bs, double n_total,
-                      double* forecasts, double* residuals, i64 f_bs, double* sigma, double* beta3, double* r2_dev) {
+                      double* forecasts, double* residuals, i64 f_bs, double* sigma, double* beta3, double* r2_dev,
+                      bool want3 = false) {
   FinishArgs g;
+  g.want3 = (mode == UM_TPRF_CLOSED && want3) ? 1 : 0;
   g.packed = reinterpret_cast<double*>(ws + p.o_packed);
   g.packed_stride = p.packed_len;
   g.small = reinterpret_cast<double*>(ws + p.o_small);
@@ -1411,7 +1470,7 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
   UM_CTX();
   UM_VIEW(y); UM_VIEW(X); UM_VIEW(Z);
   if (!out) return fail(UM_ERR_ARG, "null out");
-  UM_REQUIRE(mode >= UM_TPRF_CLOSED && mode <= UM_TPRF_IS_FULL, "unknown 3PRF mode %d", mode);
+  UM_REQUIRE(mode >= UM_TPRF_CLOSED && mode <= UM_TPRF_WINDOW, "unknown 3PRF mode %d", mode);
   UM_REQUIRE(X->dtype == UM_F64 && y->dtype == UM_F64 && Z->dtype == UM_F64, "3PRF needs f64 inputs");
   const i64 T = X->rows, N = X->cols, L = Z->cols;
   UM_REQUIRE(y->rows == T && y->cols == 1, "y must be %lld x 1, got %lldx%lld", T, (i64)y->rows, (i64)y->cols);
@@ -1424,8 +1483,15 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
   out->singular = 0;
   if (mode == UM_TPRF_IS_FULL && T < 10) {
     // T < minObs => all-NaN forecasts (Tprf3.scala:893-894)
+    // every requested output is defined on return (the reference has no fit to report either)
     int s = fill_nan(out->forecasts, T);
     if (s == UM_OK) s = fill_nan(out->residuals, T);
+    if (s == UM_OK) s = fill_nan(out->alpha, N);
+    if (s == UM_OK) s = fill_nan(out->phi, N * L);
+    if (s == UM_OK) s = fill_nan(out->phi_hat, N * (L + 1));
+    if (s == UM_OK) s = fill_nan(out->sigma, T * L);
+    if (s == UM_OK) s = fill_nan(out->beta3, L + 1);
+    if (s == UM_OK) s = fill_nan(out->xstd, N);
     if (s != UM_OK) return s;
     UM_CUDA(cudaStreamSynchronize(ctx()->stream));
     return UM_OK;
@@ -1451,7 +1517,8 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
     prof_end(6);
     if (s != UM_OK) return s;
   }
-  s = run_finish(p, ws, mode, yp, y->rs, 0, (double)n_total, out->forecasts, out->residuals, 0, out->sigma, out->beta3, nullptr);
+  const bool want3 = out->sigma || out->beta3 || out->phi || out->phi_hat;
+  s = run_finish(p, ws, mode, yp, y->rs, 0, (double)n_total, out->forecasts, out->residuals, 0, out->sigma, out->beta3, nullptr, want3);
   if (s != UM_OK) return s;
   s = run_outputs(p, ws, mode, out->alpha, out->phi, out->phi_hat, out->xstd, N);
   if (s != UM_OK) return s;
@@ -1460,13 +1527,20 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
   UM_CUDA(cudaStreamSynchronize(ctx()->stream));
   out->r_squared = res[0];
   out->singular = res[1] != 0.0;
-  return comm_active() ? comm_check_error() : UM_OK;
+  if (comm_active()) {
+    const int cs = comm_check_error();
+    if (cs != UM_OK) return cs;
+  }
+  // an exact-zero pivot in any of the small inverses: the reference's `.inverse` throws (Mat.scala:990); the
+  // outputs that depended on it hold NaN
+  if (out->singular) return fail(UM_ERR_SINGULAR, "Matrix is singular or nearly singular");
+  return UM_OK;
 }
 
 int32_t um_tprf_fit_batched(int32_t mode, const double* y, const double* X, const double* Z, int64_t T, int64_t N, int64_t L,
                             int64_t batch, double* forecasts, double* alpha, double* r2) {
   UM_CTX();
-  UM_REQUIRE(mode >= UM_TPRF_CLOSED && mode <= UM_TPRF_IS_FULL, "unknown 3PRF mode %d", mode);
+  UM_REQUIRE(mode >= UM_TPRF_CLOSED && mode <= UM_TPRF_WINDOW, "unknown 3PRF mode %d", mode);
   UM_REQUIRE(y && X && Z, "null input");
   UM_REQUIRE(L >= 1 && L <= LP, "number of proxies L = %lld outside [1, %d]", (i64)L, LP);
   UM_REQUIRE(T >= 1 && N >= 1 && batch >= 0, "bad panel shape");
@@ -1490,7 +1564,7 @@ int32_t um_tprf_fit_host(int32_t mode, const double* y, const double* X, int64_t
                          int64_t N_local, int64_t L, int64_t n_total, double* forecasts_host, double* alpha_host,
                          double* r_squared) {
   UM_CTX();
-  UM_REQUIRE(mode >= UM_TPRF_CLOSED && mode <= UM_TPRF_IS_FULL, "unknown 3PRF mode %d", mode);
+  UM_REQUIRE(mode >= UM_TPRF_CLOSED && mode <= UM_TPRF_WINDOW, "unknown 3PRF mode %d", mode);
   UM_REQUIRE(y && X && Z, "null input");
   UM_REQUIRE(L >= 1 && L <= LP, "number of proxies L = %lld outside [1, %d]", (i64)L, LP);
   UM_REQUIRE(T >= 1 && N_local >= 1 && ldx >= N_local, "bad panel shape");
@@ -1567,7 +1641,12 @@ int32_t um_tprf_fit_host(int32_t mode, const double* y, const double* X, int64_t
   UM_CUDA(cudaMemcpyAsync(res, reinterpret_cast<double*>(ws + p.o_par) + 88, 16, cudaMemcpyDeviceToHost, st));
   UM_CUDA(cudaStreamSynchronize(st));
   if (r_squared) *r_squared = res[0];
-  return comm_active() ? comm_check_error() : UM_OK;
+  if (comm_active()) {
+    const int cs = comm_check_error();
+    if (cs != UM_OK) return cs;
+  }
+  if (res[1] != 0.0) return fail(UM_ERR_SINGULAR, "Matrix is singular or nearly singular");
+  return UM_OK;
 }
 
 }  // extern "C"

@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(OOS_THREADS) k_tprf_oos_forecast(const double*
         if (a < D && b < D) { ptp[a * D + b] = x; ptp[b * D + a] = x; }
       }
     double y = nan("");
+    out[1] = 1.0;                              // singular unless the inverse goes through
     if (lu_inverse_seq(ptp, D, inv)) {
+      out[1] = 0.0;
       y = beta[0];
       for (int b = 1; b < D; ++b) {
         double bo = 0.0;                       // bo_b = sum_a d_a * PtPinv[b][a]
@@ -97,14 +99,18 @@ extern "C" int32_t um_tprf_oos_forecast(const um_view* phi, const um_view* xstd,
   UM_REQUIRE(xstd->rows * xstd->cols == N && (xstd->cols == 1 ? xstd->rs : xstd->cs) == 1, "xstd must be a contiguous vector of N = %lld", N);
   UM_REQUIRE(beta3->rows * beta3->cols == L + 1 && (beta3->cols == 1 ? (beta3->rs == 1 || L == 0) : beta3->cs == 1), "beta3 must be a contiguous vector of L+1");
   UM_REQUIRE(xt->rows == 1 && xt->cols == N, "the held-out row must be 1 x %lld, got %lldx%lld", N, (i64)xt->rows, (i64)xt->cols);
-  double* dev = static_cast<double*>(scratch(sizeof(double)));
+  double* dev = static_cast<double*>(scratch(2 * sizeof(double)));
   if (!dev) return UM_ERR_OOM;
   k_tprf_oos_forecast<<<1, OOS_THREADS, 0, ctx()->stream>>>(static_cast<const double*>(phi->data) + phi->offset,
                                                             static_cast<const double*>(xstd->data) + xstd->offset,
                                                             static_cast<const double*>(beta3->data) + beta3->offset,
                                                             static_cast<const double*>(xt->data) + xt->offset, xt->cs, N, (int)L, dev);
   UM_LAUNCHED();
-  UM_CUDA(cudaMemcpyAsync(host_out, dev, sizeof(double), cudaMemcpyDeviceToHost, ctx()->stream));
+  double res[2];
+  UM_CUDA(cudaMemcpyAsync(res, dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx()->stream));
   UM_CUDA(cudaStreamSynchronize(ctx()->stream));
+  *host_out = res[0];
+  // [1 | Phi]'[1 | Phi] with an exact-zero pivot: `.inverse` throws in t3prfTail (Tprf3.scala:913-943, Mat.scala:990)
+  if (res[1] != 0.0) return fail(UM_ERR_SINGULAR, "Matrix is singular or nearly singular");
   return UM_OK;
 }

@@ -1,53 +1,76 @@
-// tprf_fused.cuh -- the single-read 3PRF sweep (included by tprf.cu).
+// tprf_sym.cuh -- the single-read 3PRF cluster sweep with SYMMETRIC compute warps (included by tprf.cu after
+// tprf_fused.cuh, whose PTX wrappers, fragment maps and Args it reuses).
 //
-// The two-sweep path reads X twice because sweep 2 (PX = Xn W0) needs W0_j, which needs the whole of
-// column j.  Here a thread-block CLUSTER keeps a whole column tile (T rows x 16 columns) on chip: CTA
-// `rank` of the cluster owns rows [rank*R, rank*R + R) and pulls its (R x 16) piece with TMA
-// (SWIZZLE_128B boxes of 128 rows, one mbarrier per slot, three 64 KiB slots).  Warp roles per CTA:
+// Geometry is that of tprf_fused.cuh: a cluster of G CTAs keeps a column tile (T rows x 16 columns) on chip, CTA
+// `rank` owns rows [rank*R, rank*R + R) and pulls its (R x 16) piece with TMA into one of three 64 KiB slots.
+// What changed is who does the arithmetic.  tprf_fused.cuh had one A-warp (column statistics) and one B-warp
+// (projection) per SM sub-partition; ncu (profiles/r2_fused_asym_stalls.txt) showed the A-warp on the critical path
+// with its own fixed-latency stalls (1800 clocks per piece) and the B-warp's FP64-pipe time (1150 clocks) simply
+// ADDING UP, while the B-warp idled a third of the time waiting for work: 2560 pipe clocks took 3900.
 //
-//   A-warps 0-3   phase A of piece i: Zc' x (DMMA m8n8k4, M = 8 columns, K = rows) + shifted sum / sum of
-//                 squares straight out of shared memory; per-lane partials go to `scratch`.
-//   B-warps 4-7   phase B of piece i (one or two pieces behind the A-warps): PX += x V, h0 += x / sd
-//                 from the SAME shared-memory slot (DMMA, M = 8 rows, K = columns); the accumulators
-//                 stay in registers for the whole kernel.  A-warp a and B-warp 4+a share an SM
-//                 sub-partition, so its FP64 pipe always has a warp in each phase to draw from.
-//   warp 8        TMA producer (one lane).
-//   warp 9        finaliser: owner of column c (rank c % G) adds the G CTA partials in a fixed tree, forms
-//                 mu / sd / W0 / V, pushes V_c and 1/sd_c to every CTA of the cluster, writes W0 etc. for
-//                 the per-column outputs and accumulates sw / SWW / smw / smu.
-//   warp 10       reducer: per-lane partials in `scratch` -> CTA partial -> owner CTA (few, larger DSMEM
-//                 messages: 8-byte remote stores are expensive, 160 per piece instead of 1024).
-//
-// All cross-CTA traffic is DISTRIBUTED SHARED MEMORY written with `st.async`: the store itself completes
-// transaction bytes on the destination CTA's mbarrier, so there are no fences, no cluster barriers and no
-// polling in the steady state.  Every hand-off inside a CTA is an mbarrier as well; warps never wait for
-// each other except through the data they need.  X is read from HBM exactly once; every sum has a fixed
-// order, so results are reproducible run to run.
+// Here all 16 compute warps (four per sub-partition) are alike.  Warp w owns rows [w*RW, w*RW + RW) of every piece
+// (RW = R/16 = 8, 16, 24 or 32) and does, for piece n:
+//     phase A  column statistics of its rows: Zc' x by DMMA (M = 8 columns, K = rows) + shifted sum / sum of squares,
+//              and, from the same slot, its rows once more in the phase-B fragment layout -> TENSOR MEMORY
+//     phase B  of piece n - LAG out of tensor memory: PX += x V (DMMA, M = 8 rows, K = columns), h0 += x / sd
+// so every warp always has work, the four warps of a sub-partition cover one another's latencies, and the slot goes
+// back to the TMA producer as soon as phase A has read it.  The exchange is unchanged: per-warp partials -> `scratch`
+// -> reducer warp -> owner CTA (st.async into distributed shared memory, completing bytes on the owner's mbarrier)
+// -> finaliser warp (mu, sd, W0, V) -> record to every CTA of the cluster.  Every sum has a fixed order.
 #pragma once
-#include <cuda.h>
-#include <type_traits>
 
 namespace um {
-namespace fused {
+namespace sym {
 
-constexpr int CW = 16;                       // columns per tile = one 128-byte swizzle row
-constexpr int NSLOT = 3;                     // shared-memory TMA landing slots
-constexpr int NT = 4;                        // TMEM stash buffers per B-warp
-// The A-warps are throttled only by the three landing slots, whose release needs the B-warps' copy of piece
-// a-3, which follows phase B of piece a-6 in program order: the finaliser may be up to 5 pieces behind the
-// A-warps (and 8 behind the TMA producer).  The exchange rings must cover that.
-constexpr int NXR = 8;                       // ring entries of the partial / record buffers and their barriers
-constexpr int NK = 16;                       // ring of shift rows (written by TMA, read by the finaliser)
-constexpr int RMAX = 512;                    // rows per piece (per CTA of the cluster)
-constexpr int SLOT_BYTES = RMAX * CW * 8;    // 65536
-constexpr int BOX_ROWS = 128;
-constexpr int NAW = 4;                       // A-warps (= B-warps): one of each per SM sub-partition
-constexpr int NTHREADS = (2 * NAW + 4) * 32; // + TMA producer, finaliser, reducer, second finaliser (small clusters)
-constexpr int NSTAT = 10;                    // per column: s1, s2, q[8]
-constexpr int NREC = 10;                     // per column record: V[8], 1/sd, pad
-constexpr int GMAX = 16;                     // largest cluster (non-portable size)
-constexpr int SCR_W = 256;                   // scratch doubles per A-warp: q[16][8] | s1[16][4] | s2[16][4]
-constexpr int STAT_SLOT = CW * NSTAT;        // doubles per slot of the partial buffer: [owned col][src rank][NSTAT]
+using fused::Args;
+using fused::CW;
+using fused::NSLOT;
+using fused::NT;
+using fused::NK;
+using fused::RMAX;
+using fused::SLOT_BYTES;
+using fused::BOX_ROWS;
+using fused::NSTAT;
+using fused::NREC;
+using fused::GMAX;
+using fused::STAT_SLOT;
+using fused::sa;
+using fused::mb_init;
+using fused::mb_expect_tx;
+using fused::mb_arrive;
+using fused::mb_wait;
+using fused::mb_wait_token;
+using fused::map_rank;
+using fused::st_async;
+using fused::ldp_f64;
+using fused::ldp_v2f64;
+using fused::lds_f64;
+using fused::sts_f64;
+using fused::sts_v2f64;
+using fused::consume;
+using fused::tma_3d;
+using fused::cluster_sync_all;
+using fused::cluster_rank;
+using fused::tmem_st8;
+using fused::tmem_ld8;
+using fused::tmem_wait_ld;
+using fused::tmem_wait_st;
+using fused::tmem_fence_before;
+using fused::tmem_fence_after;
+using fused::col_of_m;
+using fused::f_dmma;
+
+constexpr int NAW = 8;                       // A-warps (= B-warps): TWO of each per SM sub-partition
+constexpr int NCW = 2 * NAW;                 // compute warps
+constexpr int W_TMA = NCW, W_FIN = NCW + 1, W_RED = NCW + 2, W_FIN2 = NCW + 3;
+constexpr int NTHREADS = (NCW + 4) * 32;     // 640
+constexpr int LAG = 2;                       // phase B runs this many pieces behind phase A (NT = 4 stash buffers)
+// Ring depth of the partial / record buffers and their barriers.  The A-warps are throttled only by the three landing
+// slots, whose release needs the B-warps' copy of piece a-3, which follows phase B of piece a-4-LAG in program order:
+// the finaliser may be up to 6 pieces behind the A-warps.  The exchange rings must cover that.
+constexpr int NXR = 8;
+constexpr int SCR_W = 160;                   // scratch doubles per compute warp: q[16 cols][8] | s1[16] | s2[16]
+constexpr int DBG_WARPS = 32;                // warps per rank in the debug stamp buffer
 
 constexpr int OFF_SLOTS = 0;
 constexpr int OFF_SCRATCH = NSLOT * SLOT_BYTES;                 // double[NAW][SCR_W]
@@ -59,159 +82,18 @@ constexpr int NBAR = 8 + 2 * NXR;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;                    // u32: TMEM base address
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;                   // slack to align the base to 1024 (swizzle atom)
+static_assert(SMEM_ALLOC <= 232448, "shared memory of the symmetric sweep exceeds 227 KB");
+static_assert(NSLOT + 2 + LAG < NXR && LAG < NT, "exchange rings / stash buffers too shallow for LAG");
 
-// ---- PTX wrappers ------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned sa(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mb_init(unsigned bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mb_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mb_arrive(unsigned bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mb_arrive_remote(unsigned cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mb_wait(unsigned bar, unsigned parity) {
-  asm volatile(
-      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void mb_wait_cluster(unsigned bar, unsigned parity) {
-  asm volatile(
-      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(
-          bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ unsigned map_rank(unsigned local_addr, unsigned rank) {
-  unsigned r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void st_remote(unsigned cluster_addr, double v) {
-  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(cluster_addr), "d"(v) : "memory");
-}
-// remote store that completes `8` transaction bytes on the destination CTA's mbarrier: the data is visible
-// to whoever observes that barrier phase complete -- no fence, no separate arrive
-__device__ __forceinline__ void st_async(unsigned cluster_addr, double v, unsigned cluster_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(cluster_addr),
-               "l"(__double_as_longlong(v)), "r"(cluster_bar)
-               : "memory");
-}
-// mbarrier wait that also yields a zero the compiler cannot see through: adding it to a shared-memory
-// address makes the (pure, freely schedulable) loads below data-dependent on the wait
-__device__ __forceinline__ unsigned mb_wait_token(unsigned bar, unsigned parity) {
-  unsigned tok;
-  asm volatile(
-      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\nmov.u32 %0, 0;\n}"
-      : "=r"(tok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return tok;
-}
-// pure loads of the piece: schedulable between the DMMAs; ordered after the wait through the token and
-// before the slot is released through `consume`
-__device__ __forceinline__ double ldp_f64(unsigned addr) {
-  double v;
-  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ double2 ldp_v2f64(unsigned addr) {
-  double2 v;
-  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void consume(double v) { asm volatile("" ::"d"(v) : "memory"); }
-// ptxas reorders freely inside a basic block but not across a warp-level barrier: a (free, the warp is converged)
-// WARPSYNC pins the instruction order chosen in the source where the order matters (independent DMMA chains)
-__device__ __forceinline__ void sched_fence() { __syncwarp(); }
-__device__ __forceinline__ double lds_f64(unsigned addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ double2 lds_v2f64(unsigned addr) {
-  double2 v;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts_f64(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
-__device__ __forceinline__ void sts_v2f64(unsigned addr, double a, double b) {
-  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
-}
-__device__ __forceinline__ void tma_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ unsigned cluster_rank() {
-  unsigned r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-
-// ---- tensor memory as an FP64 stash (tools/microbench/tmem_scratch.cu): 32x32b shape = lane i of the warp
-// owns TMEM lane 32*(warp%4)+i; a double is two consecutive 32-bit columns ----
-__device__ __forceinline__ void tmem_st8(unsigned taddr, double2 a, double2 b) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-               "r"(__double2loint(a.x)), "r"(__double2hiint(a.x)), "r"(__double2loint(a.y)), "r"(__double2hiint(a.y)),
-               "r"(__double2loint(b.x)), "r"(__double2hiint(b.x)), "r"(__double2loint(b.y)), "r"(__double2hiint(b.y))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(unsigned taddr, unsigned (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-struct Args {
-  i64 T, N, npad, tpad;
-  int L, G, R;              // cluster size, rows per piece
-  int batch, cpp;           // panels, chunks per panel (a chunk = the tiles c, c + cpp, ... of one panel)
-  i64 ntile;                // column tiles per panel (this launch sweeps tiles [tile_lo, ntile))
-  i64 tile_lo;
-  int cpp_out, cidx_off;    // chunk slots per panel in the output partials, and this launch's first slot
-  const double* zc;         // [batch][T][8]
-  double* w0;               // [batch][npad][8]
-  double* invsd;            // [batch][npad]
-  double* mun;              // [batch][npad]
-  double* blockpart;        // [batch][cpp*G][81]
-  double* pxp;              // [batch][cpp][tpad][8]
-  double* h0p;              // [batch][cpp][tpad]
-  unsigned* started;        // optional: += 1 per cluster once it is resident (split sweep)
-  long long* dbg;           // optional: [rank][warp][iter][8] clock64 stamps of cluster 0 (profiling aid)
-};
-
-// logical column of the phase-A fragment row m (0..7) of m-tile 0; m-tile 1 is +4.  Chosen so the
-// 16 lanes of a half-warp touch 16 distinct 8-byte bank pairs under the 128-byte swizzle.
-__device__ __forceinline__ int col_of_m(int m) { return ((m & 2) << 2) | (m & 1) | ((m & 4) >> 1); }  // 0,1,8,9,2,3,10,11
-
-// pure (non-volatile) DMMA so the compiler may schedule it between the shared-memory loads
-__device__ __forceinline__ void f_dmma(double& c0, double& c1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-// J = R / 128 (rows per piece); each A-warp and each B-warp owns R / 4 = 32*J rows of the piece
+// J = R / 128 (rows per piece); every compute warp owns RW = 8 J rows of the piece
 template <int J>
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_row0, const Args g) {
+k_tprf_sym(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_row0, const Args g) {
   constexpr int R = 128 * J;
-  constexpr int RW = R / NAW;      // rows per A-/B-warp: 32, 64, 96 or 128
-  constexpr int KS = RW / 4;       // phase-A k-steps (4 rows each)
-  constexpr int MT = RW / 8;       // phase-B m-tiles (8 rows each)
+  constexpr int RW = R / NAW;      // rows per A-warp and per B-warp: 16, 32, 48 or 64
+  constexpr int KS = RW / 4;       // phase-A k-steps (4 rows each) = 4 J
+  constexpr int MT = RW / 8;       // m-tiles (8 rows each) = 2 J
+  constexpr int TCOLS = MT * 8;    // 32-bit TMEM columns of one stash buffer of one warp
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   double* scratch = reinterpret_cast<double*>(smem + OFF_SCRATCH);
@@ -220,7 +102,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   double* kshs = reinterpret_cast<double*>(smem + OFF_KSH);
   const unsigned bar0 = sa(smem + OFF_BAR);
   auto bar_full = [&](int s) { return bar0 + 8u * s; };          // TMA landed the piece in slot s
-  auto bar_empty = [&](int s) { return bar0 + 8u * (3 + s); };   // the A- and B-warps are done with slot s
+  auto bar_empty = [&](int s) { return bar0 + 8u * (3 + s); };   // every compute warp has read its rows of slot s
   const unsigned bar_scr_full = bar0 + 8u * 6, bar_scr_free = bar0 + 8u * 7;
   auto bar_stat = [&](int x) { return bar0 + 8u * (8 + x); };        // every CTA's partials of my columns arrived
   auto bar_vrdy = [&](int x) { return bar0 + 8u * (8 + NXR + x); };  // every column's record arrived
@@ -241,7 +123,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) {
       mb_init(bar_full(s), 1);
-      mb_init(bar_empty(s), 2 * NAW);   // the A-warps (phase A) and the B-warps (copy to tensor memory)
+      mb_init(bar_empty(s), NCW);
     }
     for (int x = 0; x < NXR; ++x) {
       mb_init(bar_stat(x), 1);   // armed per piece: expect_tx(STAT_SLOT doubles) = owned columns x G ranks x NSTAT
@@ -262,15 +144,15 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
 
   const bool dbg_on = g.dbg != nullptr && cl == 0 && lane == 0;
   auto stamp = [&](int iter, int slot_) {
-    if (dbg_on && iter < 64) g.dbg[(((i64)rank * 16 + warp) * 64 + iter) * 8 + slot_] = clock64();
+    if (dbg_on && iter < 64) g.dbg[(((i64)rank * DBG_WARPS + warp) * 64 + iter) * 8 + slot_] = clock64();
   };
   const unsigned slots0 = sa(smem + OFF_SLOTS);
   const int fm = lane >> 2, fk = lane & 3;
   const int rm = (fm >> 1) + 4 * (fm & 1);   // row of an 8-row m-tile held by this lane in the phase-B fragment
 
   if (warp < NAW) {
-    // ================= A-warps: column statistics of piece `it` =================
-    const int rowbase = warp * RW;   // first local row of this warp (multiple of 32)
+    // ================= A-warps: column statistics of piece `it` (rows [warp*RW, +RW)) =================
+    const int rowbase = warp * RW;   // first local row of this warp (multiple of 16)
     // one 16-byte load feeds both m-tiles: lane (m = fm, k = fk) reads x[row 4ks + k][columns 2c, 2c + 1] with
     // c = chunk(fm); m-tile 0 = the even columns, m-tile 1 = the odd ones.  chunk() makes the 8 lanes of a
     // quarter-warp (two fm values x four rows) touch 8 distinct 16-byte bank groups under the 128-byte swizzle.
@@ -279,6 +161,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
     unsigned offv[2];
 #pragma unroll
     for (int pb = 0; pb < 2; ++pb) offv[pb] = (unsigned)(((chunk ^ (4 * pb + fk)) & 7) << 4) + (unsigned)(rowbase + 4 * pb + fk) * 128u;
+    const unsigned scr = sa(scratch + warp * SCR_W);
     int it = 0;
     for (int ch = cl; ch < nchunks; ch += ncl) {
       const int b = ch / g.cpp, cidx = ch % g.cpp;
@@ -306,36 +189,26 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
           for (int pb = 0; pb < 2; ++pb) q[mt][pb][0] = q[mt][pb][1] = 0.0;
         const double2 kshv = ldp_v2f64(sa(kshs + (it % NK) * CW + cola[0]) + tokf);
         const double ksh[2] = {kshv.x, kshv.y};
-        // One GROUP = two k-steps (rows 8g + fk and 8g + 4 + fk) x two m-tiles = four DMMAs on four INDEPENDENT
-        // accumulators, then a scheduling fence.  Without the fence ptxas sorts the fully unrolled body chain by
-        // chain (16 dependent DMMAs in a row; a dependent DMMA issues every ~26 clocks instead of every 16,
-        // profiles/r1_dmma_chain.log).  The loads of group g + 1 are issued before the math of group g.
+        // The DMMA takes the SHIFTED value d = x - k, not x: Zc is centred, so sum_t (x_t - k) zc_t = sum_t x_t zc_t,
+        // and d -- which the two sums need anyway -- is then ready before the DMMA issues, whose 16 clocks cover its
+        // latency for the sums behind it.  One group = two k-steps x two m-tiles = four DMMAs on four independent
+        // accumulators; the fence keeps ptxas from sorting them chain by chain; loads run one group ahead.
         auto phase_a = [&](auto masked) {
           constexpr bool MASK = decltype(masked)::value;
-          // The DMMA takes the SHIFTED value d = x - k, not x: Zc is centred, so sum_t (x_t - k) zc_t = sum_t x_t zc_t,
-          // and d -- which the two sums need anyway -- then has to be ready BEFORE the DMMA issues, whose 16 clocks
-          // cover the latency of d for the sums behind it (with x as the operand ptxas emitted DMMA, d = x - k,
-          // 8 idle clocks, s1 += d).  Loads run AHEAD groups (of two k-steps x two m-tiles) ahead: under the TMA
-          // writes and the B-warps' reads a shared-memory load takes far longer than in isolation (ncu: 20 % of the
-          // A-warp's time was short-scoreboard stall with one group of lookahead).
-          constexpr int NG = KS / 2;
-          constexpr int AHEAD = NG >= 3 ? 3 : NG;
-          double2 a[AHEAD + 1][2];
+          double2 a_cur[2], a_nxt[2];
 #pragma unroll
-          for (int h = 0; h < AHEAD; ++h)
+          for (int pb = 0; pb < 2; ++pb) a_cur[pb] = ldp_v2f64(slot + offv[pb]);
 #pragma unroll
-            for (int pb = 0; pb < 2; ++pb) a[h][pb] = ldp_v2f64(slot + offv[pb] + (unsigned)h * 1024u);
+          for (int gk = 0; gk < KS / 2; ++gk) {
+            if (gk + 1 < KS / 2) {
 #pragma unroll
-          for (int gk = 0; gk < NG; ++gk) {
-            if (gk + AHEAD < NG) {
-#pragma unroll
-              for (int pb = 0; pb < 2; ++pb) a[AHEAD][pb] = ldp_v2f64(slot + offv[pb] + (unsigned)(gk + AHEAD) * 1024u);
+              for (int pb = 0; pb < 2; ++pb) a_nxt[pb] = ldp_v2f64(slot + offv[pb] + (unsigned)(gk + 1) * 1024u);
             }
             double d[2][2];
 #pragma unroll
             for (int pb = 0; pb < 2; ++pb) {
-              d[pb][0] = a[0][pb].x - ksh[0];
-              d[pb][1] = a[0][pb].y - ksh[1];
+              d[pb][0] = a_cur[pb].x - ksh[0];
+              d[pb][1] = a_cur[pb].y - ksh[1];
               if (MASK && 4 * (2 * gk + pb) >= tvalid) d[pb][0] = d[pb][1] = 0.0;
             }
 #pragma unroll
@@ -352,29 +225,36 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
                 s2[mt][pb] = fma(d[pb][mt], d[pb][mt], s2[mt][pb]);
 #endif
               }
-            sched_fence();   // keeps the four accumulator chains interleaved (ptxas would sort them chain by chain)
+            fused::sched_fence();
 #pragma unroll
-            for (int h = 0; h < AHEAD; ++h)
-#pragma unroll
-              for (int pb = 0; pb < 2; ++pb) a[h][pb] = a[h + 1][pb];
+            for (int pb = 0; pb < 2; ++pb) a_cur[pb] = a_nxt[pb];
           }
         };
         if (need_mask) phase_a(std::true_type{});
         else phase_a(std::false_type{});
-        // done with the slot (the B-warp releases it too, once it has copied its rows to tensor memory)
+        // done with the slot (the B-warps release it too, once they have copied their rows to tensor memory)
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) consume(q[mt][0][0] + q[mt][1][0]);   // every load of the slot has landed in a register
         __syncwarp();
         if (lane == 0) mb_arrive(bar_empty(s));
-        // per-lane partials -> scratch (the reducer adds the 4 row phases and the 4 A-warps)
-        mb_wait(bar_scr_free, (unsigned)((it & 1) ^ 1));  // the reducer is done with piece it-1 (passes at once for it = 0)
-        {
-          const unsigned sp = sa(scratch + warp * SCR_W);
+        // warp partials -> scratch: q per (column, l); s1 / s2 per column after the fixed xor tree over the 4 row phases
+        double t1[2], t2[2];
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            sts_v2f64(sp + (cola[mt] * 8 + 2 * fk) * 8, q[mt][0][0] + q[mt][1][0], q[mt][0][1] + q[mt][1][1]);
-            sts_f64(sp + (128 + cola[mt] * 4 + fk) * 8, s1[mt][0] + s1[mt][1]);
-            sts_f64(sp + (192 + cola[mt] * 4 + fk) * 8, s2[mt][0] + s2[mt][1]);
+        for (int mt = 0; mt < 2; ++mt) {
+          t1[mt] = s1[mt][0] + s1[mt][1];
+          t2[mt] = s2[mt][0] + s2[mt][1];
+          t1[mt] += __shfl_xor_sync(0xffffffffu, t1[mt], 1);
+          t2[mt] += __shfl_xor_sync(0xffffffffu, t2[mt], 1);
+          t1[mt] += __shfl_xor_sync(0xffffffffu, t1[mt], 2);
+          t2[mt] += __shfl_xor_sync(0xffffffffu, t2[mt], 2);
+        }
+        mb_wait(bar_scr_free, (unsigned)((it & 1) ^ 1));  // the reducer is done with piece it-1 (passes at once for it = 0)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          sts_v2f64(scr + (cola[mt] * 8 + 2 * fk) * 8, q[mt][0][0] + q[mt][1][0], q[mt][0][1] + q[mt][1][1]);
+          if (fk == 0) {
+            sts_f64(scr + (128 + cola[mt]) * 8, t1[mt]);
+            sts_f64(scr + (144 + cola[mt]) * 8, t2[mt]);
           }
         }
         __syncwarp();
@@ -382,15 +262,12 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         stamp(it, 2);
       }
     }
-  } else if (warp < 2 * NAW) {
+  } else if (warp < NCW) {
     // ================= B-warps: copy piece n into tensor memory, then PX / h0 of piece n - LAG =================
-    // The B-warp stashes ITS rows of a piece (already in the phase-B fragment layout) as soon as TMA has
-    // landed it, so the shared-memory slot goes straight back to the producer; phase B of that piece runs
-    // LAG pieces later out of tensor memory, when every column's record has long arrived.
-    constexpr int LAG = 2;
     const int bw = warp - NAW;
     const int rowbase = bw * RW;
-    const unsigned tm_warp = tmem_base + ((unsigned)(32 * bw) << 16);
+    // tensor memory: a warp may touch lanes [32 (warp % 4), +32); the two B-warps of a quarter split its 512 columns
+    const unsigned tm_warp = tmem_base + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((bw >> 2) * (NT * TCOLS));
     unsigned offb[2];
 #pragma unroll
     for (int s2 = 0; s2 < 2; ++s2) offb[s2] = (unsigned)((((4 * s2 + fk) ^ rm) & 7) << 4) + (unsigned)(rowbase + rm) * 128u;
@@ -402,16 +279,18 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
       const int s = n % NSLOT, tb = n % NT;
       const unsigned tokf = mb_wait_token(bar_full(s), (unsigned)((n / NSLOT) & 1));
       const unsigned slot = slots0 + (unsigned)s * SLOT_BYTES + tokf;
-      const unsigned tm = tm_warp + (unsigned)(tb * (MT * 8));
+      const unsigned tm = tm_warp + (unsigned)(tb * TCOLS);
 #pragma unroll
       for (int m0 = 0; m0 < MT; m0 += 4) {
         double2 xb[4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int s2 = 0; s2 < 2; ++s2) xb[i][s2] = ldp_v2f64(slot + offb[s2] + (unsigned)(m0 + i) * 1024u);
+          for (int s2 = 0; s2 < 2; ++s2)
+            if (m0 + i < MT) xb[i][s2] = ldp_v2f64(slot + offb[s2] + (unsigned)(m0 + i) * 1024u);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) tmem_st8(tm + (unsigned)((m0 + i) * 8), xb[i][0], xb[i][1]);
+        for (int i = 0; i < 4; ++i)
+          if (m0 + i < MT) tmem_st8(tm + (unsigned)((m0 + i) * 8), xb[i][0], xb[i][1]);
       }
       __syncwarp();
       if (lane == 0) mb_arrive(bar_empty(s));   // tmem_st8 consumed the loaded registers: the slot is free
@@ -432,7 +311,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
           isd[s2][e] = ldp_f64(vr + (c * NREC + 8) * 8);
         }
       tmem_wait_st();   // this warp's own stash stores (issued >= LAG pieces ago) are complete
-      const unsigned tm = tm_warp + (unsigned)(tb * (MT * 8));
+      const unsigned tm = tm_warp + (unsigned)(tb * TCOLS);
 #pragma unroll
       for (int m0 = 0; m0 < MT; m0 += 2) {
         unsigned r[2][8];
@@ -440,22 +319,21 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         for (int i = 0; i < 2; ++i) tmem_ld8(tm + (unsigned)((m0 + i) * 8), r[i]);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+        for (int s2 = 0; s2 < 2; ++s2)
 #pragma unroll
-          for (int s2 = 0; s2 < 2; ++s2) {
-            const double x0 = __hiloint2double(r[i][4 * s2 + 1], r[i][4 * s2]);
-            const double x1 = __hiloint2double(r[i][4 * s2 + 3], r[i][4 * s2 + 2]);
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const double x = __hiloint2double(r[i][4 * s2 + 2 * e + 1], r[i][4 * s2 + 2 * e]);
 #ifndef ABL_NODMMA_B
-            f_dmma(px[m0 + i][0], px[m0 + i][1], x0, vf[s2][0]);
-            f_dmma(px[m0 + i][0], px[m0 + i][1], x1, vf[s2][1]);
+              f_dmma(px[m0 + i][0], px[m0 + i][1], x, vf[s2][e]);
 #else
-            px[m0 + i][0] += x0; px[m0 + i][1] += x1;
+              px[m0 + i][0] += x;
 #endif
 #ifndef ABL_NOHH
-            hh[m0 + i] = fma(x0, isd[s2][0], hh[m0 + i]);
-            hh[m0 + i] = fma(x1, isd[s2][1], hh[m0 + i]);
+              hh[m0 + i] = fma(x, isd[s2][e], hh[m0 + i]);
 #endif
-          }
+            }
       }
       stamp(n, 5);
     };
@@ -488,7 +366,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 2 * NAW) {
+  } else if (warp == W_TMA) {
     // ================= TMA producer =================
     if (lane == 0) {
       constexpr unsigned piece_bytes = (unsigned)R * CW * 8 + CW * 8;
@@ -507,12 +385,12 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         }
       }
     }
-  } else if ((warp == 2 * NAW + 1 || warp == 2 * NAW + 3) && (warp == 2 * NAW + 1 || owned > 4)) {
+  } else if ((warp == W_FIN || warp == W_FIN2) && (warp == W_FIN || owned > 4)) {
     // ================= finaliser: owner of columns {oc*G + rank} =================
     // Clusters of 1 or 2 CTAs own 16 / 8 columns per CTA = 4 / 2 serial rounds per piece, and this latency-bound
-    // warp then paces the whole sweep (profiles/r1_fused_timeline_g1.log): a second finaliser warp takes every
-    // other round.  Larger clusters (one round per piece) run the first one alone; the second stays idle.
-    const int fw = warp == 2 * NAW + 3 ? 1 : 0;
+    // warp then paces the whole sweep: a second finaliser warp takes every other round.  Larger clusters (one round
+    // per piece) run the first one alone; the second stays idle.
+    const int fw = warp == W_FIN2 ? 1 : 0;
     const int nfw = owned > 4 ? 2 : 1;
     // 8 lanes (l = value index) per lane group; `sub` lane groups share one column and split its G
     // source ranks (<= 4 each); up to 4 columns per round
@@ -691,27 +569,21 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         for (int c = 0; c < 8; ++c) a_sww[c] = 0.0;
       }
     }
-  } else if (warp == 2 * NAW + 2) {
-    // ================= reducer: lane partials in `scratch` -> CTA partial -> owner CTA =================
-    // lane handles 5 of the 160 (column, statistic) values: value 0 is s1 / s2 of column lane >> 1 (4 row
-    // phases x 4 A-warps), values 1..4 are q[column (e >> 3)][l = e & 7], e = lane + 32 (j - 1) (4 A-warps)
+  } else if (warp == W_RED) {
+    // ================= reducer: warp partials in `scratch` -> CTA partial -> owner CTA =================
+    // lane handles values v = lane + 32 j (j = 0..4) of the 160 per warp: v < 128 is q[column v >> 3][l = v & 7],
+    // 128 + c is s1 of column c, 144 + c is s2; the 8 A-warps are added in a fixed tree
     unsigned rdst[5], rbar[5];
-    {
-      const int c = lane >> 1, st = lane & 1;
-      const int owner = c % G, oc = c / G;
-      rdst[0] = map_rank(sa(statbuf + (oc * G + rank) * NSTAT + st), owner);
-      rbar[0] = map_rank(bar_stat(0), owner);
-    }
 #pragma unroll
-    for (int j = 1; j < 5; ++j) {
-      const int e = lane + 32 * (j - 1);
-      const int c = e >> 3, l = e & 7;
+    for (int j = 0; j < 5; ++j) {
+      const int v = lane + 32 * j;
+      const int c = v < 128 ? (v >> 3) : ((v - 128) & 15);
+      const int st = v < 128 ? 2 + (v & 7) : (v < 144 ? 0 : 1);
       const int owner = c % G, oc = c / G;
-      rdst[j] = map_rank(sa(statbuf + (oc * G + rank) * NSTAT + 2 + l), owner);
+      rdst[j] = map_rank(sa(statbuf + (oc * G + rank) * NSTAT + st), owner);
       rbar[j] = map_rank(bar_stat(0), owner);
     }
-    const unsigned sbase = sa(scratch + 128 + (lane & 1) * 64 + (lane >> 1) * 4);
-    const unsigned qbase = sa(scratch + lane);
+    const unsigned vbase = sa(scratch + lane);
     int it = 0;
     for (int ch = cl; ch < nchunks; ch += ncl) {
       const int cidx = ch % g.cpp;
@@ -720,24 +592,14 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         stamp(it, 0);
         mb_wait(bar_scr_full, (unsigned)(it & 1));
         stamp(it, 1);
-        double p[NAW][4], pq[4][NAW];
-#pragma unroll
-        for (int w = 0; w < NAW; ++w)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) p[w][k] = lds_f64(sbase + (w * SCR_W + k) * 8);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int w = 0; w < NAW; ++w) pq[j][w] = lds_f64(qbase + (w * SCR_W + 32 * j) * 8);
         double acc[5];
-        {
-          double pw[NAW];
 #pragma unroll
-          for (int w = 0; w < NAW; ++w) pw[w] = (p[w][0] + p[w][1]) + (p[w][2] + p[w][3]);
-          acc[0] = (pw[0] + pw[1]) + (pw[2] + pw[3]);
+        for (int j = 0; j < 5; ++j) {
+          double p[NAW];
+#pragma unroll
+          for (int w = 0; w < NAW; ++w) p[w] = lds_f64(vbase + (unsigned)(w * SCR_W + 32 * j) * 8);
+          acc[j] = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[1 + j] = (pq[j][0] + pq[j][1]) + (pq[j][2] + pq[j][3]);
         consume(acc[0]); consume(acc[1]); consume(acc[2]); consume(acc[3]); consume(acc[4]);
         __syncwarp();
         if (lane == 0) mb_arrive(bar_scr_free);
@@ -754,46 +616,15 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   cluster_sync_all();  // nobody leaves while a peer may still write into its shared memory
 }
 
-typedef void (*FusedKernel)(const CUtensorMap, const CUtensorMap, const Args);
-inline FusedKernel kernel_for(int R) {
+typedef void (*SymKernel)(const CUtensorMap, const CUtensorMap, const Args);
+inline SymKernel kernel_for(int R) {
   switch (R / 128) {
-    case 1: return k_tprf_fused<1>;
-    case 2: return k_tprf_fused<2>;
-    case 3: return k_tprf_fused<3>;
-    default: return k_tprf_fused<4>;
+    case 1: return k_tprf_sym<1>;
+    case 2: return k_tprf_sym<2>;
+    case 3: return k_tprf_sym<3>;
+    default: return k_tprf_sym<4>;
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-inline EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
-        qr == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// cluster size / rows per piece for a T-row panel; G == 0: the fused sweep does not apply
-inline void pick_shape(i64 T, int* G, int* R) {
-  *G = 0; *R = 0;
-  for (int gsz = 1; gsz <= GMAX; gsz *= 2) {
-    i64 rows = (T + gsz - 1) / gsz;
-    if (rows <= RMAX) {
-      *G = gsz;
-      *R = (int)((rows + BOX_ROWS - 1) / BOX_ROWS) * BOX_ROWS;
-      return;
-    }
-  }
-}
-
-}  // namespace fused
+}  // namespace sym
 }  // namespace um

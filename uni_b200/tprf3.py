@@ -62,13 +62,15 @@ def _fit(mode: int, y: Mat, X: Mat, Z: Mat, n_total: int = 0, want_all: bool = T
         if mode in (L.TPRF_CLOSED, L.TPRF_IS_FULL):
             res.alpha = Mat._alloc(N, 1, L.F64)
             out.alpha = res.alpha._buf.ptr
-        if mode in (L.TPRF_ITER, L.TPRF_IS_FULL):
+        if True:   # phi / phiHat / sigma / beta3 are part of every result, tprfClosedForm included (Tprf3.scala:211-231,243-252)
             res.phi = Mat._alloc(N, Lp, L.F64)
             res.phiHat = Mat._alloc(Lp + 1, N, L.F64)
             res.sigma = Mat._alloc(T, Lp, L.F64)
             res.beta3 = Mat._alloc(Lp + 1, 1, L.F64)
             out.phi, out.phi_hat = res.phi._buf.ptr, res.phiHat._buf.ptr
             out.sigma, out.beta3 = res.sigma._buf.ptr, res.beta3._buf.ptr
+    # a singular Gram (exact-zero pivot) raises SingularMatrixError, as every `.inverse` of the reference's fits does
+    # (ArithmeticException, Mat.scala:990)
     check(lib.um_tprf_fit(mode, y._ref(), X._ref(), Z._ref(), int(n_total), C.byref(out)))
     res.rSquared = out.r_squared
     res.singular = bool(out.singular)
@@ -120,12 +122,12 @@ def _window_forecast(yt: Mat, Xt: Mat, Zt: Optional[Mat], n_auto: int, xt: Mat, 
     if Zt is not None:
         if yt.rows < 10:                       # runT3prf / t3prfDowndated minObs = 10 (Tprf3.scala:893-894,951-968)
             return float("nan")
-        return _oos_forecast(_fit(L.TPRF_ITER, yt, Xt, Zt), xt)
+        return _oos_forecast(_fit(L.TPRF_WINDOW, yt, Xt, Zt), xt)
     if yt.rows < min_obs:
         return float("nan")
     r0, tp = yt.copy(), float("nan")
     for _ in range(n_auto):
-        res = _fit(L.TPRF_ITER, yt, Xt, r0)
+        res = _fit(L.TPRF_WINDOW, yt, Xt, r0)
         tp = _oos_forecast(res, xt)
         r0 = MatD.hstack(yt - res.forecasts, r0)
     return tp
@@ -274,11 +276,12 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
     n_auto = int(Z) if auto else 0
     if auto and not 1 <= n_auto <= 8:
         raise ValueError(f"number of automatic proxies L = {n_auto} outside [1, 8]")
-    if not eff_pls and (X.isnan().any() or y.isnan().any() or (not auto and Z.isnan().any())):
-        raise NotImplementedError("NaN input needs pls = true with automatic proxies (the nanOls passes); the intercept path "
-                                  "spreads a NaN to every forecast (Tprf3.scala:883-901) and is not run on the device")
+    # NaN input without pls takes the same matrix passes as clean input (Tprf3.scala:883-943): a NaN in X or Z inside a
+    # window spreads to that window's whole fit (every product it touches), a NaN in y only removes its row from pass 3
+    # (nanOls, :929-931); `hasNan` just switches the column std to the NaN-aware one (:1078-1080)
+    has_nan = bool(X.isnan().any() or y.isnan().any() or (not auto and Z.isnan().any()))
     T = y.rows
-    Xn = X / (_nan_std_cols(X) if eff_pls else _std_cols(X))         # Tprf3.scala:1080-1081
+    Xn = X / (_nan_std_cols(X) if (eff_pls or has_nan) else _std_cols(X))   # Tprf3.scala:1080-1081
 
     if procedure == "IS Full" and eff_pls:                           # :1097-1106 with runT3prf's pls branch
         r0, fore = y.copy(), None
@@ -299,7 +302,7 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
         r0, res = y.copy(), None
         for j in range(n_auto):
             last = j == n_auto - 1
-            res = _fit(L.TPRF_IS_FULL if last else L.TPRF_ITER, y, Xn, r0, want_all=last)
+            res = _fit(L.TPRF_IS_FULL if last else L.TPRF_WINDOW, y, Xn, r0, want_all=last)
             r0 = MatD.hstack(r0, y - res.forecasts)
         return res
 
@@ -314,7 +317,7 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
             fore[t, 0] = (_window_forecast_pls(yt, _drop_rows(Xn, lo, hi), n_auto, _rows(Xn, t, t + 1), 10) if eff_pls else
                           _window_forecast(yt, _drop_rows(Xn, lo, hi), None if auto else _drop_rows(Z, lo, hi), n_auto,
                                            _rows(Xn, t, t + 1), 10))
-            roll[t, 0] = _nan_mean(yt) if eff_pls else yt.mean()
+            roll[t, 0] = _nan_mean(yt) if (eff_pls or has_nan) else yt.mean()   # colMean(yt, hasNan)
     elif procedure == "OOS Recursive":                               # :1148-1179
         for t in range(mt[0] + 1 + mt[1], T):
             end = t - 1 - mt[1]
@@ -322,7 +325,7 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
             fore[t, 0] = (_window_forecast_pls(yt, _rows(Xn, 0, end), n_auto, _rows(Xn, t, t + 1), mt[0]) if eff_pls else
                           _window_forecast(yt, _rows(Xn, 0, end), None if auto else _rows(Z, 0, end), n_auto,
                                            _rows(Xn, t, t + 1), mt[0]))
-            roll[t, 0] = _nan_mean(yt) if eff_pls else yt.mean()
+            roll[t, 0] = _nan_mean(yt) if (eff_pls or has_nan) else yt.mean()   # colMean(yt, hasNan)
     else:                                                            # OOS Rolling, :1181-1199
         for t in range(win + 1 + gap, T):
             lo, hi = max(t - win - gap, 0), min(t - 1 - gap, T)
@@ -330,7 +333,7 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
             fore[t, 0] = (_window_forecast_pls(yt, _rows(Xn, lo, hi), n_auto, _rows(Xn, t, t + 1), min_nona) if eff_pls else
                           _window_forecast(yt, _rows(Xn, lo, hi), None if auto else _rows(Z, lo, hi), n_auto,
                                            _rows(Xn, t, t + 1), min_nona))
-            roll[t, 0] = _nan_mean(yt) if eff_pls else yt.mean()
+            roll[t, 0] = _nan_mean(yt) if (eff_pls or has_nan) else yt.mean()   # colMean(yt, hasNan)
 
     forecasts, rollfore = Mat.from_numpy(fore), Mat.from_numpy(roll)
     residuals = y - forecasts
