@@ -334,8 +334,8 @@ def estimate3prf(y, X, Z, procedure="IS Full", window=(0, 1), mintrain=(-1, 0), 
     loc = ~np.isnan(resid[:, 0])
     with np.errstate(all="ignore"):
         if procedure == "IS Full":  # :1214-1225
-            mu = y[loc, 0].sum() / loc.sum()
-            r2 = 1.0 - float((resid[loc, 0] ** 2).sum()) / float(((y[loc, 0] - mu) ** 2).sum())
+            mu = np.float64(y[loc, 0].sum()) / np.float64(loc.sum())          # no usable row: 0/0 = NaN, as the JVM's
+            r2 = float(1.0 - np.float64((resid[loc, 0] ** 2).sum()) / np.float64(((y[loc, 0] - mu) ** 2).sum()))
         else:  # :1226-1233: rolling-mean denominator, ssT == 0 -> NaN
             sst = float(((y[loc, 0] - rollfore[loc, 0]) ** 2).sum())
             r2 = 1.0 - float((resid[loc, 0] ** 2).sum()) / sst if sst != 0.0 else float("nan")

@@ -47,6 +47,10 @@ constexpr int NSTAT = 10;                    // per column: s1, s2, q[8]
 constexpr int NREC = 10;                     // per column record: V[8], 1/sd, pad
 constexpr int GMAX = 16;                     // largest cluster (non-portable size)
 constexpr int SCR_W = 256;                   // scratch doubles per A-warp: q[16][8] | s1[16][4] | s2[16][4]
+constexpr int REG_A = 208, REG_S = 128;       // setmaxnreg targets: A-warps up, special warps down (B-warps keep 168)
+// the A-warps can only take what the special warps gave back to the CTA's pool (the kernel starts at 168 per thread,
+// 65536 / 384 rounded down to a multiple of 8): asking for more spins forever in setmaxnreg.inc
+static_assert(REG_A - 168 <= 168 - REG_S && REG_A % 8 == 0 && REG_S % 8 == 0, "setmaxnreg budget");
 constexpr int STAT_SLOT = CW * NSTAT;        // doubles per slot of the partial buffer: [owned col][src rank][NSTAT]
 
 constexpr int OFF_SLOTS = 0;
@@ -55,9 +59,11 @@ constexpr int OFF_STAT = OFF_SCRATCH + NAW * SCR_W * 8;         // double[NXR][S
 constexpr int OFF_VREC = OFF_STAT + NXR * STAT_SLOT * 8;        // double[NXR][CW][NREC]
 constexpr int OFF_KSH = OFF_VREC + NXR * CW * NREC * 8;         // double[NK][CW]   (row 0 of the panel: variance shift)
 constexpr int OFF_BAR = OFF_KSH + NK * CW * 8;                  // full[3] empty[3] scr_full scr_free statready[NXR] vready[NXR]
-constexpr int NBAR = 8 + 2 * NXR;
+constexpr int NBAR = 8 + 2 * NXR + 2 * NAW * NT;              // + stash_full[NAW][NT] stash_free[NAW][NT]
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;                    // u32: TMEM base address
-constexpr int SMEM_BYTES = OFF_TMEM + 16;
+constexpr int OFF_FIN2 = OFF_TMEM + 16;                         // double[11][8]: second finaliser's small sums -> first finaliser
+constexpr int SMEM_BYTES = OFF_FIN2 + 11 * 8 * 8;
+static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory of the cluster sweep exceeds 227 KB");
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;                   // slack to align the base to 1024 (swizzle atom)
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -220,7 +226,9 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   double* kshs = reinterpret_cast<double*>(smem + OFF_KSH);
   const unsigned bar0 = sa(smem + OFF_BAR);
   auto bar_full = [&](int s) { return bar0 + 8u * s; };          // TMA landed the piece in slot s
-  auto bar_empty = [&](int s) { return bar0 + 8u * (3 + s); };   // the A- and B-warps are done with slot s
+  auto bar_empty = [&](int s) { return bar0 + 8u * (3 + s); };   // the A-warps are done with slot s
+  auto bar_st_full = [&](int q, int t) { return bar0 + 8u * (8 + 2 * NXR + q * NT + t); };             // A-warp q stashed a piece in buffer t
+  auto bar_st_free = [&](int q, int t) { return bar0 + 8u * (8 + 2 * NXR + NAW * NT + q * NT + t); };  // B-warp 4+q is done with it
   const unsigned bar_scr_full = bar0 + 8u * 6, bar_scr_free = bar0 + 8u * 7;
   auto bar_stat = [&](int x) { return bar0 + 8u * (8 + x); };        // every CTA's partials of my columns arrived
   auto bar_vrdy = [&](int x) { return bar0 + 8u * (8 + NXR + x); };  // every column's record arrived
@@ -241,7 +249,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) {
       mb_init(bar_full(s), 1);
-      mb_init(bar_empty(s), 2 * NAW);   // the A-warps (phase A) and the B-warps (copy to tensor memory)
+      mb_init(bar_empty(s), NAW);       // the A-warps (phase A + copy to tensor memory)
     }
     for (int x = 0; x < NXR; ++x) {
       mb_init(bar_stat(x), 1);   // armed per piece: expect_tx(STAT_SLOT doubles) = owned columns x G ranks x NSTAT
@@ -249,6 +257,11 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
     }
     mb_init(bar_scr_full, NAW);
     mb_init(bar_scr_free, 1);
+    for (int q = 0; q < NAW; ++q)
+      for (int t = 0; t < NT; ++t) {
+        mb_init(bar_st_full(q, t), 1);
+        mb_init(bar_st_free(q, t), 1);
+      }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tmem_fence_before();
@@ -268,6 +281,15 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   const int fm = lane >> 2, fk = lane & 3;
   const int rm = (fm >> 1) + 4 * (fm & 1);   // row of an 8-row m-tile held by this lane in the phase-B fragment
 
+  // Register re-allocation between the three warpgroups (warps 0-3 A, 4-7 B, 8-11 producer / finaliser / reducer):
+  // the A-warps hold the Zc fragments of their 128 rows (64 registers) on top of the accumulators, and ptxas, capped
+  // at 168 registers, sank every shared-memory load to just in front of its use -- a lookahead of ~50 clocks, less
+  // than the load's latency under the TMA writes and the B-warps' reads.  The special warps give registers back.
+  if (warp < NAW) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_A));
+  } else if (warp >= 2 * NAW) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_S));
+  }
   if (warp < NAW) {
     // ================= A-warps: column statistics of piece `it` =================
     const int rowbase = warp * RW;   // first local row of this warp (multiple of 32)
@@ -279,6 +301,14 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
     unsigned offv[2];
 #pragma unroll
     for (int pb = 0; pb < 2; ++pb) offv[pb] = (unsigned)(((chunk ^ (4 * pb + fk)) & 7) << 4) + (unsigned)(rowbase + 4 * pb + fk) * 128u;
+    // The A-warp also copies its rows, in the phase-B fragment layout, into TENSOR MEMORY for B-warp 4 + warp (same
+    // sub-partition = same tensor-memory lane quarter): the slot is released by the A-warps alone, the B-warps never
+    // touch shared-memory slots and run phase B up to NT pieces later.  lane (rm, fk) holds x[row 8m + rm][cols 2fk,
+    // 2fk+1 and 8+2fk, 8+2fk+1].
+    unsigned offb[2];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) offb[s2] = (unsigned)((((4 * s2 + fk) ^ rm) & 7) << 4) + (unsigned)(rowbase + rm) * 128u;
+    const unsigned tm_warp = tmem_base + ((unsigned)(32 * warp) << 16);
     int it = 0;
     for (int ch = cl; ch < nchunks; ch += ncl) {
       const int b = ch / g.cpp, cidx = ch % g.cpp;
@@ -294,11 +324,16 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
       const int tvalid = tv > RW ? RW : (tv < 0 ? 0 : (int)tv);
       const bool need_mask = grow0 + RW > T;
       for (i64 tile = g.tile_lo + cidx; tile < g.ntile; tile += g.cpp, ++it) {
-        const int s = it % NSLOT;
+        const int s = it % NSLOT, tb = it % NT;
         stamp(it, 0);
         const unsigned tokf = mb_wait_token(bar_full(s), (unsigned)((it / NSLOT) & 1));
         stamp(it, 1);
         const unsigned slot = slots0 + (unsigned)s * SLOT_BYTES + tokf;
+        if (it >= NT) {   // the B-warp has finished with this stash buffer
+          mb_wait(bar_st_free(warp, tb), (unsigned)((it / NT - 1) & 1));
+          tmem_fence_after();
+        }
+        const unsigned tm = tm_warp + (unsigned)(tb * (MT * 8));
         double q[2][2][2], s1[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, s2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
@@ -320,16 +355,21 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
           // A-warp's time was short-scoreboard stall with one group of lookahead).
           constexpr int NG = KS / 2;
           constexpr int AHEAD = NG >= 3 ? 3 : NG;
-          double2 a[AHEAD + 1][2];
+          double2 a[AHEAD + 1][2], xb[AHEAD + 1][2];
 #pragma unroll
-          for (int h = 0; h < AHEAD; ++h)
+          for (int h = 0; h < AHEAD; ++h) {
 #pragma unroll
             for (int pb = 0; pb < 2; ++pb) a[h][pb] = ldp_v2f64(slot + offv[pb] + (unsigned)h * 1024u);
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) xb[h][s2] = ldp_v2f64(slot + offb[s2] + (unsigned)h * 1024u);
+          }
 #pragma unroll
           for (int gk = 0; gk < NG; ++gk) {
             if (gk + AHEAD < NG) {
 #pragma unroll
               for (int pb = 0; pb < 2; ++pb) a[AHEAD][pb] = ldp_v2f64(slot + offv[pb] + (unsigned)(gk + AHEAD) * 1024u);
+#pragma unroll
+              for (int s2 = 0; s2 < 2; ++s2) xb[AHEAD][s2] = ldp_v2f64(slot + offb[s2] + (unsigned)(gk + AHEAD) * 1024u);
             }
             double d[2][2];
 #pragma unroll
@@ -352,20 +392,29 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
                 s2[mt][pb] = fma(d[pb][mt], d[pb][mt], s2[mt][pb]);
 #endif
               }
+            tmem_st8(tm + (unsigned)(gk * 8), xb[0][0], xb[0][1]);   // group gk = rows 8 gk .. 8 gk + 7 = m-tile gk of the stash
             sched_fence();   // keeps the four accumulator chains interleaved (ptxas would sort them chain by chain)
 #pragma unroll
-            for (int h = 0; h < AHEAD; ++h)
+            for (int h = 0; h < AHEAD; ++h) {
 #pragma unroll
               for (int pb = 0; pb < 2; ++pb) a[h][pb] = a[h + 1][pb];
+#pragma unroll
+              for (int s2 = 0; s2 < 2; ++s2) xb[h][s2] = xb[h + 1][s2];
+            }
           }
         };
         if (need_mask) phase_a(std::true_type{});
         else phase_a(std::false_type{});
-        // done with the slot (the B-warp releases it too, once it has copied its rows to tensor memory)
+        // done with the slot; the stash buffer goes to the B-warp
+        tmem_wait_st();
+        tmem_fence_before();
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) consume(q[mt][0][0] + q[mt][1][0]);   // every load of the slot has landed in a register
         __syncwarp();
-        if (lane == 0) mb_arrive(bar_empty(s));
+        if (lane == 0) {
+          mb_arrive(bar_st_full(warp, tb));
+          mb_arrive(bar_empty(s));
+        }
         // per-lane partials -> scratch (the reducer adds the 4 row phases and the 4 A-warps)
         mb_wait(bar_scr_free, (unsigned)((it & 1) ^ 1));  // the reducer is done with piece it-1 (passes at once for it = 0)
         {
@@ -383,39 +432,14 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
       }
     }
   } else if (warp < 2 * NAW) {
-    // ================= B-warps: copy piece n into tensor memory, then PX / h0 of piece n - LAG =================
-    // The B-warp stashes ITS rows of a piece (already in the phase-B fragment layout) as soon as TMA has
-    // landed it, so the shared-memory slot goes straight back to the producer; phase B of that piece runs
-    // LAG pieces later out of tensor memory, when every column's record has long arrived.
-    constexpr int LAG = 2;
+    // ================= B-warps: PX / h0 of piece n out of tensor memory, once every column's record is there =================
     const int bw = warp - NAW;
     const int rowbase = bw * RW;
     const unsigned tm_warp = tmem_base + ((unsigned)(32 * bw) << 16);
-    unsigned offb[2];
-#pragma unroll
-    for (int s2 = 0; s2 < 2; ++s2) offb[s2] = (unsigned)((((4 * s2 + fk) ^ rm) & 7) << 4) + (unsigned)(rowbase + rm) * 128u;
     double px[MT][2], hh[MT];
 #pragma unroll
     for (int i = 0; i < MT; ++i) px[i][0] = px[i][1] = hh[i] = 0.0;
 
-    auto stash = [&](int n) {
-      const int s = n % NSLOT, tb = n % NT;
-      const unsigned tokf = mb_wait_token(bar_full(s), (unsigned)((n / NSLOT) & 1));
-      const unsigned slot = slots0 + (unsigned)s * SLOT_BYTES + tokf;
-      const unsigned tm = tm_warp + (unsigned)(tb * (MT * 8));
-#pragma unroll
-      for (int m0 = 0; m0 < MT; m0 += 4) {
-        double2 xb[4][2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int s2 = 0; s2 < 2; ++s2) xb[i][s2] = ldp_v2f64(slot + offb[s2] + (unsigned)(m0 + i) * 1024u);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) tmem_st8(tm + (unsigned)((m0 + i) * 8), xb[i][0], xb[i][1]);
-      }
-      __syncwarp();
-      if (lane == 0) mb_arrive(bar_empty(s));   // tmem_st8 consumed the loaded registers: the slot is free
-    };
     auto phase_b = [&](int n) {
       const int tb = n % NT, xr = n % NXR;
       stamp(n, 3);
@@ -431,7 +455,8 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
           vf[s2][e] = ldp_f64(vr + (c * NREC + fm) * 8);
           isd[s2][e] = ldp_f64(vr + (c * NREC + 8) * 8);
         }
-      tmem_wait_st();   // this warp's own stash stores (issued >= LAG pieces ago) are complete
+      mb_wait(bar_st_full(bw, tb), (unsigned)((n / NT) & 1));   // A-warp bw has stashed piece n (long ago, normally)
+      tmem_fence_after();
       const unsigned tm = tm_warp + (unsigned)(tb * (MT * 8));
 #pragma unroll
       for (int m0 = 0; m0 < MT; m0 += 2) {
@@ -457,6 +482,9 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
 #endif
           }
       }
+      tmem_fence_before();
+      __syncwarp();
+      if (lane == 0) mb_arrive(bar_st_free(bw, tb));
       stamp(n, 5);
     };
 
@@ -464,12 +492,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
     for (int ch = cl; ch < nchunks; ch += ncl) {
       const int b = ch / g.cpp, cidx = ch % g.cpp;
       const i64 grow0 = (i64)rank * R + rowbase;
-      const int it_first = it;
-      for (i64 tile = g.tile_lo + cidx; tile < g.ntile; tile += g.cpp, ++it) {
-        stash(it);
-        if (it - LAG >= it_first) phase_b(it - LAG);
-      }
-      for (int n = (it - LAG > it_first ? it - LAG : it_first); n < it; ++n) phase_b(n);   // drain
+      for (i64 tile = g.tile_lo + cidx; tile < g.ntile; tile += g.cpp, ++it) phase_b(it);
       // flush this chunk's PX / h0 partial
       {
         double* pxo = g.pxp + ((i64)(b * g.cpp_out + g.cidx_off + cidx) * g.tpad) * 8;
@@ -507,13 +530,19 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         }
       }
     }
-  } else if ((warp == 2 * NAW + 1 || warp == 2 * NAW + 3) && (warp == 2 * NAW + 1 || owned > 4)) {
+  } else if (warp == 2 * NAW + 1 || warp == 2 * NAW + 3) {
     // ================= finaliser: owner of columns {oc*G + rank} =================
     // Clusters of 1 or 2 CTAs own 16 / 8 columns per CTA = 4 / 2 serial rounds per piece, and this latency-bound
     // warp then paces the whole sweep (profiles/r1_fused_timeline_g1.log): a second finaliser warp takes every
     // other round.  Larger clusters (one round per piece) run the first one alone; the second stays idle.
+    // Larger clusters (one round per piece): the two finaliser warps take the PIECES in turn -- the per-piece chain
+    // (sum the G partials, 1/sd, V, push, outputs, small sums: ~2500 clocks on a sub-partition whose FP64 pipe is busy
+    // with DMMAs) is otherwise the serial stage that paces the sweep once phase A is fast.
     const int fw = warp == 2 * NAW + 3 ? 1 : 0;
-    const int nfw = owned > 4 ? 2 : 1;
+    const bool piece_split = owned <= 4;
+    const int nfw = piece_split ? 1 : 2;
+    const int fwr = piece_split ? 0 : fw;      // round offset inside a piece (small clusters only)
+    double* fin2 = reinterpret_cast<double*>(smem + OFF_FIN2);
     // 8 lanes (l = value index) per lane group; `sub` lane groups share one column and split its G
     // source ranks (<= 4 each); up to 4 columns per round
     const int lg = lane >> 3, l = lane & 7;
@@ -537,7 +566,8 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
       const int b = ch / g.cpp, cidx = ch % g.cpp;
       for (i64 tile = g.tile_lo + cidx; tile < g.ntile; tile += g.cpp, ++it) {
         const int s = it % NXR;  // ring entry of the exchange buffers and barriers
-        if (lane == 0 && fw == 0) {
+        if (piece_split && (it & 1) != fw) continue;
+        if (lane == 0 && (piece_split || fw == 0)) {
           mb_expect_tx(bar_vrdy(s), CW * 9 * 8);
           mb_expect_tx(bar_stat(s), STAT_SLOT * 8);
         }
@@ -571,7 +601,7 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
           }
           mun_pre = (k0 + dm) * inv_pre;
         }
-        for (int oc0 = fw * cpr; oc0 < owned; oc0 += cpr * nfw) {
+        for (int oc0 = fwr * cpr; oc0 < owned; oc0 += cpr * nfw) {
           const int oc = oc0 + cs;              // < owned always (owned is a multiple of cpr)
           const int col = oc * G + rank;
           double S, SS, q;
@@ -677,6 +707,18 @@ k_tprf_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
           double x2 = __shfl_sync(0xffffffffu, vals[i], 16 + l);
           double x3 = __shfl_sync(0xffffffffu, vals[i], 24 + l);
           vals[i] = ((x0 + x1) + x2) + x3;
+        }
+        if (piece_split) {   // second finaliser -> first, through shared memory; the sum order is fixed (first + second)
+          if (fw == 1 && lg == 0) {
+#pragma unroll
+            for (int i = 0; i < 11; ++i) fin2[i * 8 + l] = vals[i];
+          }
+          asm volatile("bar.sync 1, 64;" ::: "memory");
+          if (fw == 0) {
+#pragma unroll
+            for (int i = 0; i < 11; ++i) vals[i] += fin2[i * 8 + l];
+          }
+          asm volatile("bar.sync 1, 64;" ::: "memory");   // the buffer may be rewritten at the end of the next chunk
         }
         if (lg == 0 && fw == 0) {
           double* bp = g.blockpart + ((i64)(b * g.cpp_out + g.cidx_off + cidx) * G + rank) * NSMALL;

@@ -150,15 +150,12 @@ k_tprf_grid(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
   } else if (warp < NAW) {
     // ================= A-warps: column statistics of piece `it` + stash for the B-warp =================
     const int rowbase = warp * RW;
-    unsigned offa[2][2];
-    int cola[2];
+    // one 16-byte load feeds both m-tiles of phase A (even / odd columns), as in tprf_fused.cuh
+    const int chunk = ((fm & 1) << 2) | (fm >> 1);
+    const int cola[2] = {2 * chunk, 2 * chunk + 1};
+    unsigned offv[2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      cola[mt] = col_of_m(fm) + 4 * mt;
-#pragma unroll
-      for (int pb = 0; pb < 2; ++pb)
-        offa[mt][pb] = (unsigned)(((((cola[mt] >> 1) ^ (4 * pb + fk)) & 7) << 4) | ((cola[mt] & 1) << 3)) + (unsigned)(rowbase + 4 * pb + fk) * 128u;
-    }
+    for (int pb = 0; pb < 2; ++pb) offv[pb] = (unsigned)(((chunk ^ (4 * pb + fk)) & 7) << 4) + (unsigned)(rowbase + 4 * pb + fk) * 128u;
     unsigned offb[2];
 #pragma unroll
     for (int s2 = 0; s2 < 2; ++s2) offb[s2] = (unsigned)((((4 * s2 + fk) ^ rm) & 7) << 4) + (unsigned)(rowbase + rm) * 128u;
@@ -187,41 +184,65 @@ k_tprf_grid(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int pb = 0; pb < 2; ++pb) q[mt][pb][0] = q[mt][pb][1] = 0.0;
-        double ksh[2];
-        ksh[0] = ldp_f64(sa(kshs + s * CW + cola[0]) + tokf);
-        ksh[1] = ldp_f64(sa(kshs + s * CW + cola[1]) + tokf);
+        const double2 kshv = ldp_v2f64(sa(kshs + s * CW + cola[0]) + tokf);
+        const double ksh[2] = {kshv.x, kshv.y};
         if (it >= NT) {   // the B-warp has finished with this stash buffer
           mb_wait(bar_st_free(warp, tb), (unsigned)((it / NT - 1) & 1));
           tmem_fence_after();
         }
         stamp(it, 2);
         const unsigned tm = tm_warp + (unsigned)(tb * TCOLS);
+        // groups of two k-steps (8 rows): four DMMAs on four independent accumulators, fed with the shifted value
+        // d = x - k (see tprf_fused.cuh), + the same 8 rows once more in the phase-B layout -> tensor memory (one
+        // m-tile); loads run AHEAD groups ahead, the fence keeps the accumulator chains interleaved
+        auto phase_a = [&](auto masked) {
+          constexpr bool MASK = decltype(masked)::value;
+          constexpr int NG = KS / 2;
+          constexpr int AHEAD = NG >= 2 ? 2 : NG;
+          double2 a[AHEAD + 1][2], xb[AHEAD + 1][2];
 #pragma unroll
-        for (int kb = 0; kb < KS; kb += 4) {
-          double a[4][2];
+          for (int h = 0; h < AHEAD; ++h) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+            for (int pb = 0; pb < 2; ++pb) a[h][pb] = ldp_v2f64(slot + offv[pb] + (unsigned)h * 1024u);
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) a[i][mt] = ldp_f64(slot + offa[mt][i & 1] + (unsigned)(kb + (i & ~1)) * 512u);
-          // the same 16 rows once more in the phase-B layout -> tensor memory (2 m-tiles of 8 rows)
-          double2 xb[2][2];
+            for (int s2 = 0; s2 < 2; ++s2) xb[h][s2] = ldp_v2f64(slot + offb[s2] + (unsigned)h * 1024u);
+          }
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
+          for (int gk = 0; gk < NG; ++gk) {
+            if (gk + AHEAD < NG) {
 #pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) xb[i][s2] = ldp_v2f64(slot + offb[s2] + (unsigned)(kb / 2 + i) * 1024u);
+              for (int pb = 0; pb < 2; ++pb) a[AHEAD][pb] = ldp_v2f64(slot + offv[pb] + (unsigned)(gk + AHEAD) * 1024u);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+              for (int s2 = 0; s2 < 2; ++s2) xb[AHEAD][s2] = ldp_v2f64(slot + offb[s2] + (unsigned)(gk + AHEAD) * 1024u);
+            }
+            double d[2][2];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-              f_dmma(q[mt][i & 1][0], q[mt][i & 1][1], a[i][mt], zf[kb + i]);
-              double d = a[i][mt] - ksh[mt];
-              if (need_mask && 4 * (kb + i) >= tvalid) d = 0.0;
-              s1[mt][i & 1] += d;
-              s2[mt][i & 1] = fma(d, d, s2[mt][i & 1]);
+            for (int pb = 0; pb < 2; ++pb) {
+              d[pb][0] = a[0][pb].x - ksh[0];
+              d[pb][1] = a[0][pb].y - ksh[1];
+              if (MASK && 4 * (2 * gk + pb) >= tvalid) d[pb][0] = d[pb][1] = 0.0;
             }
 #pragma unroll
-          for (int i = 0; i < 2; ++i) tmem_st8(tm + (unsigned)((kb / 2 + i) * 8), xb[i][0], xb[i][1]);
-        }
+            for (int pb = 0; pb < 2; ++pb)
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt) {
+                f_dmma(q[mt][pb][0], q[mt][pb][1], d[pb][mt], zf[2 * gk + pb]);
+                s1[mt][pb] += d[pb][mt];
+                s2[mt][pb] = fma(d[pb][mt], d[pb][mt], s2[mt][pb]);
+              }
+            tmem_st8(tm + (unsigned)(gk * 8), xb[0][0], xb[0][1]);
+            sched_fence();
+#pragma unroll
+            for (int h = 0; h < AHEAD; ++h) {
+#pragma unroll
+              for (int pb = 0; pb < 2; ++pb) a[h][pb] = a[h + 1][pb];
+#pragma unroll
+              for (int s2 = 0; s2 < 2; ++s2) xb[h][s2] = xb[h + 1][s2];
+            }
+          }
+        };
+        if (need_mask) phase_a(std::true_type{});
+        else phase_a(std::false_type{});
         tmem_wait_st();
         tmem_fence_before();
 #pragma unroll
@@ -486,7 +507,7 @@ k_tprf_grid(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
         for (int c = 0; c < 8; ++c) a_sww[c] = 0.0;
       }
     }
-  } else {
+  } else if (warp == 2 * NAW + 2) {
     // ================= reducer: lane partials in `scratch` -> CTA partial -> ring entry in global memory =================
     const unsigned sbase = sa(scratch + 128 + (lane & 1) * 64 + (lane >> 1) * 4);
     const unsigned qbase = sa(scratch + lane);
