@@ -22,7 +22,7 @@ dy, dX, dZ = u.Mat.from_numpy(y), u.Mat.from_numpy(X), u.Mat.from_numpy(Z)
 tprf3.set_tprf_path(2)
 for _ in range(2):
     u.tprfClosedForm(dy, dX, dZ)
-SYM = os.environ.get("UM_TPRF_SYM", "1") != "0"
+SYM = False   # (the symmetric-warp experiment of round 2 used a 32-warp stamp layout; see git history)
 WPR = 32 if SYM else 16                      # warps per rank in the stamp buffer
 n = 16 * WPR * 64 * 8
 buf = Mat.from_numpy(np.zeros((n, 1)))      # 8-byte cells, reinterpreted as int64

@@ -902,7 +902,6 @@ __global__ void k_fill_nan(double* p, i64 n) {
 }  // namespace um
 #include "tprf_fused.cuh"
 #include "tprf_grid.cuh"
-#include "tprf_sym.cuh"
 namespace um {
 
 // ---- host orchestration ------------------------------------------------------------------------------------------
@@ -1030,15 +1029,9 @@ static double g_split_share = [] {
   return e ? atof(e) : 0.73;
 }();
 
-// cluster sweep kernel: symmetric compute warps (tprf_sym.cuh) unless UM_TPRF_SYM=0 (the round-1 A-/B-warp kernel, kept
-// for side-by-side measurements)
-static const bool g_use_sym = [] {
-  const char* e = getenv("UM_TPRF_SYM");
-  return !(e && atoi(e) == 0);
-}();
-static fused::FusedKernel cluster_kernel_for(int R) { return g_use_sym ? sym::kernel_for(R) : fused::kernel_for(R); }
-static int cluster_threads() { return g_use_sym ? sym::NTHREADS : fused::NTHREADS; }
-static int cluster_smem() { return g_use_sym ? sym::SMEM_ALLOC : fused::SMEM_ALLOC; }
+static fused::FusedKernel cluster_kernel_for(int R) { return fused::kernel_for(R); }
+static int cluster_threads() { return fused::NTHREADS; }
+static int cluster_smem() { return fused::SMEM_ALLOC; }
 
 typedef CUresult (*StreamWaitFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 static StreamWaitFn stream_wait_fn() {

@@ -3,20 +3,27 @@
 // The two-sweep path reads X twice because sweep 2 (PX = Xn W0) needs W0_j, which needs the whole of
 // column j.  Here a thread-block CLUSTER keeps a whole column tile (T rows x 16 columns) on chip: CTA
 // `rank` of the cluster owns rows [rank*R, rank*R + R) and pulls its (R x 16) piece with TMA
-// (SWIZZLE_128B boxes of 128 rows, one mbarrier per slot, three 64 KiB slots).  Warp roles per CTA:
+// (SWIZZLE_128B boxes of 128 rows, one mbarrier per slot, three 64 KiB slots).  Warp roles per CTA (round 2:
+// profiles/README.md has the measurements behind each choice):
 //
-//   A-warps 0-3   phase A of piece i: Zc' x (DMMA m8n8k4, M = 8 columns, K = rows) + shifted sum / sum of
-//                 squares straight out of shared memory; per-lane partials go to `scratch`.
-//   B-warps 4-7   phase B of piece i (one or two pieces behind the A-warps): PX += x V, h0 += x / sd
-//                 from the SAME shared-memory slot (DMMA, M = 8 rows, K = columns); the accumulators
-//                 stay in registers for the whole kernel.  A-warp a and B-warp 4+a share an SM
-//                 sub-partition, so its FP64 pipe always has a warp in each phase to draw from.
+//   A-warps 0-3   phase A of piece i: Zc' (x - k) (DMMA m8n8k4, M = 8 columns, K = rows; k = the column's first row)
+//                 + shifted sum / sum of squares straight out of shared memory; per-lane partials go to `scratch`.
+//                 The same warp copies its 128 rows, in the phase-B fragment layout, into TENSOR MEMORY (four
+//                 64 KiB pieces deep) for the B-warp of its sub-partition, so the slot goes back to the producer
+//                 as soon as phase A is done and the B-warps never touch a slot.
+//   B-warps 4-7   phase B of piece i, as soon as every column's record is there (normally one or two pieces behind
+//                 the A-warps): PX += x V, h0 += x / sd out of tensor memory (DMMA, M = 8 rows, K = columns); the
+//                 accumulators stay in registers for the whole kernel.  A-warp a and B-warp 4+a share an SM
+//                 sub-partition (= a tensor-memory lane quarter), so its FP64 pipe has a warp in each phase to draw on.
 //   warp 8        TMA producer (one lane).
-//   warp 9        finaliser: owner of column c (rank c % G) adds the G CTA partials in a fixed tree, forms
+//   warps 9, 11   finalisers: owner of column c (rank c % G) adds the G CTA partials in a fixed tree, forms
 //                 mu / sd / W0 / V, pushes V_c and 1/sd_c to every CTA of the cluster, writes W0 etc. for
-//                 the per-column outputs and accumulates sw / SWW / smw / smu.
+//                 the per-column outputs and accumulates sw / SWW / smw / smu.  The two warps take the pieces in
+//                 turn (large clusters) or the rounds of one piece (clusters of 1 or 2 CTAs).
 //   warp 10       reducer: per-lane partials in `scratch` -> CTA partial -> owner CTA (few, larger DSMEM
 //                 messages: 8-byte remote stores are expensive, 160 per piece instead of 1024).
+// The A-warps run with 208 registers, the special warps with 128 (setmaxnreg): the Zc fragments of 128 rows alone
+// are 64 registers, and with less ptxas sinks the shared-memory loads to just before their use.
 //
 // All cross-CTA traffic is DISTRIBUTED SHARED MEMORY written with `st.async`: the store itself completes
 // transaction bytes on the destination CTA's mbarrier, so there are no fences, no cluster barriers and no
@@ -33,9 +40,9 @@ namespace fused {
 constexpr int CW = 16;                       // columns per tile = one 128-byte swizzle row
 constexpr int NSLOT = 3;                     // shared-memory TMA landing slots
 constexpr int NT = 4;                        // TMEM stash buffers per B-warp
-// The A-warps are throttled only by the three landing slots, whose release needs the B-warps' copy of piece
-// a-3, which follows phase B of piece a-6 in program order: the finaliser may be up to 5 pieces behind the
-// A-warps (and 8 behind the TMA producer).  The exchange rings must cover that.
+// The A-warps are throttled by the three landing slots and by the NT stash buffers: phase A of piece a needs the
+// B-warp done with piece a - NT, i.e. every finaliser's record of it.  No CTA is more than NT pieces ahead of any
+// finaliser (the TMA producer NT + NSLOT); the exchange rings must cover that.
 constexpr int NXR = 8;                       // ring entries of the partial / record buffers and their barriers
 constexpr int NK = 16;                       // ring of shift rows (written by TMA, read by the finaliser)
 constexpr int RMAX = 512;                    // rows per piece (per CTA of the cluster)
