@@ -300,6 +300,38 @@ def cublas_dgemm_tflops(u, sizes):
     return out
 
 
+def oos_rows(u, small=False):
+    """estimate3prf's out-of-sample procedures, every window of a procedure in one launch
+    (um_tprf_oos_windows).  650 x 40 x 2 is the reference's published shape (README.md:315-317: Scala 1.65 ms Recursive /
+    5.7 ms Cross Val); the wide panel is this repo's.  GPU figure = whole host call (window setup, launch, copy-back, R^2),
+    best of 7 by wall clock; cpu = the NumPy restatement (oracle.estimate3prf, one run) on the same input."""
+    import numpy as np
+    from oracle import tprf_oracle as to
+    out = {}
+    shapes = ((650, 40, 2, True),) if small else ((650, 40, 2, True), (200, 16384, 4, False))
+    for T, N, Lp, with_cpu in shapes:
+        rng = np.random.default_rng(1)
+        X = rng.standard_normal((T, N)); y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, Lp))
+        dy, dX, dZ = u.Mat.from_numpy(y), u.Mat.from_numpy(X), u.Mat.from_numpy(Z)
+        for proc in ("OOS Recursive", "OOS Cross Val"):
+            call = lambda: u.estimate3prf(dy, dX, dZ, proc)
+            r = call(); u.sync()
+            best = 1e30
+            for _ in range(7):
+                t0 = time.perf_counter(); r = call(); u.sync(); best = min(best, time.perf_counter() - t0)
+            nwin = int(np.isfinite(r.forecasts.to_numpy()).sum())
+            e = {"ms": round(best * 1e3, 3), "windows": nwin, "windows_per_s": round(nwin / best, 1), "r_squared": r.rSquared}
+            if with_cpu:
+                t0 = time.perf_counter(); o = to.estimate3prf(y, X, Z, proc); t = time.perf_counter() - t0
+                e["cpu"] = {"numpy_port_ms": round(t * 1e3, 1), "cores": host_cores(),
+                            "max_abs_forecast_diff": float(np.nanmax(np.abs(o.forecasts - r.forecasts.to_numpy())))}
+            out[f"{proc} T={T} N={N} L={Lp}"] = e
+    out["note"] = ("recorded on the build container (profiles/r2_reference_python_cpu.json, 8 cores): the unmodified reference "
+                   "py/tprf3fast.py takes 75 ms (Recursive) / 102 ms (Cross Val) at 650 x 40 x 2; the reference README publishes "
+                   "1.65 / 5.7 ms for its Scala implementation")
+    return out
+
+
 def cpu_config5(panels=16):
     import numpy as np
     from oracle import tprf_oracle as to
@@ -710,6 +742,7 @@ def run_ours(args, rank, world, local_rank):
                                                "same box, a yardstick only; " + cpu_mm["note"])
                 if isinstance(extras.get("batched_config5"), dict) and "error" not in extras["batched_config5"]:
                     extras["batched_config5"]["cpu"] = cpu_config5()
+                extras["oos_procedures"] = oos_rows(u, small=args.small)
             except Exception as ex:
                 extras["ops_error"] = str(ex)[:300]
     exchange = "none (1 GPU)"

@@ -302,6 +302,19 @@ int32_t um_tprf_set_path(int32_t path);
  * (rank, warp, piece) into this device buffer of 16*16*64*8 int64 (tools/fused_timeline.py). */
 int32_t um_tprf_debug_stamps(long long* device_buf);
 int32_t um_tprf_fused_info(int64_t T, int32_t* cluster_size, int32_t* rows_per_piece, int32_t* resident_clusters);
+/* ALL out-of-sample windows of estimate3prf's Cross Val / Recursive / Rolling procedures in one launch (Tprf3.scala:1112-1199:
+ * the reference's `.par` loop over runT3prf -> t3prfFast -> t3prfTail, :883-943).  Xn: the globally standardised panel (T x N,
+ * cs == 1), or -- standardize != 0 -- the RAW panel, which the call first divides by nanStdCols (Tprf3.scala:469-502,1078-1081);
+ * Z: the proxy matrix (T x L), or NULL for `n_auto` automatic proxies (each window rebuilds them from its own
+ * residuals, newest column in front, :1134-1139).  Window k keeps rows [lo[k], hi[k]) (kind 0: Recursive, Rolling) or every row
+ * BUT [lo[k], hi[k]) (kind 1: Cross Val) and forecasts row held[k]; it is re-standardised by its own column std (invStdCols).
+ * Fewer than min_obs kept rows -> NaN.  Outputs (host arrays of nwin): the forecasts `yhatt` and the mean of the window's y
+ * (`rollfore`, over its non-NaN entries: colMean(yt, hasNan), which on NaN-free y is the plain mean).  NaN semantics are the reference's: a NaN in X or Z
+ * inside a window spreads to its forecast, a NaN in y only leaves pass 3 (nanOls).  One CTA per window, one synchronisation
+ * at the end; UM_ERR_SINGULAR if any window hit an exact-zero pivot (ArithmeticException out of the parallel loop). */
+int32_t um_tprf_oos_windows(const um_view* y, const um_view* Xn, const um_view* Z, int32_t n_auto, int32_t kind,
+                            const int32_t* lo, const int32_t* hi, const int32_t* held, int64_t nwin, int32_t min_obs,
+                            int32_t standardize, double* fore_host, double* roll_host);
 /* Out-of-sample point forecast of one window (t3prfTail's `yhatt`, Tprf3.scala:913-943), from the outputs of
  * um_tprf_fit(UM_TPRF_ITER) on the window's kept rows: phi (N x L), xstd (N), beta3 (L+1), and the held-out row
  * xt (1 x N, any column stride).  estimate3prf's OOS procedures (Tprf3.scala:1112-1199) call it once per window.

@@ -158,6 +158,8 @@ SIGNATURES = {
     "um_tprf_fit_host": (_i32, [_i32, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, C.POINTER(_f64)]),
     "um_tprf_fit_batched": (_i32, [_i32, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "um_tprf_oos_forecast": (_i32, [VP, VP, VP, VP, C.POINTER(_f64)]),
+    "um_tprf_oos_windows": (_i32, [VP, VP, VP, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _i64, _i32, _i32,
+                            C.POINTER(_f64), C.POINTER(_f64)]),
     "um_tprf_work": (_i32, [_i64, _i64, _i64, C.POINTER(_f64), C.POINTER(_f64)]),
     "um_tprf_set_path": (_i32, [_i32]),
     "um_tprf_debug_stamps": (_i32, [_vp]),

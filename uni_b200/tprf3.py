@@ -279,9 +279,10 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
     # NaN input without pls takes the same matrix passes as clean input (Tprf3.scala:883-943): a NaN in X or Z inside a
     # window spreads to that window's whole fit (every product it touches), a NaN in y only removes its row from pass 3
     # (nanOls, :929-931); `hasNan` just switches the column std to the NaN-aware one (:1078-1080)
-    has_nan = bool(X.isnan().any() or y.isnan().any() or (not auto and Z.isnan().any()))
     T = y.rows
-    Xn = X / (_nan_std_cols(X) if (eff_pls or has_nan) else _std_cols(X))   # Tprf3.scala:1080-1081
+    oos_batched = procedure != "IS Full" and not eff_pls              # um_tprf_oos_windows standardises the panel itself
+    has_nan = False if oos_batched else bool(X.isnan().any() or y.isnan().any() or (not auto and Z.isnan().any()))
+    Xn = None if oos_batched else X / (_nan_std_cols(X) if (eff_pls or has_nan) else _std_cols(X))   # Tprf3.scala:1080-1081
 
     if procedure == "IS Full" and eff_pls:                           # :1097-1106 with runT3prf's pls branch
         r0, fore = y.copy(), None
@@ -310,7 +311,33 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
     win, min_nona, gap = (int(v) for v in rollwin)
     fore = np.full((T, 1), np.nan)
     roll = np.full((T, 1), np.nan)
-    if procedure == "OOS Cross Val":                                 # :1112-1146
+    if not eff_pls:
+        # every window of the procedure in ONE launch (um_tprf_oos_windows: one CTA per window, no per-window
+        # synchronisation) -- the reference's `.par` loop over the windows (:1117,1151,1177)
+        if procedure == "OOS Cross Val":                             # the window drops rows [lo, hi), :1112-1146
+            ts = np.arange(T)
+            lo = np.maximum(ts - window[0], 0); hi = np.minimum(ts - window[0] + window[1], T)
+            kind, min_obs = 1, 10
+        elif procedure == "OOS Recursive":                           # rows [0, end), :1148-1179
+            ts = np.arange(mt[0] + 1 + mt[1], T)
+            lo = np.zeros_like(ts); hi = ts - 1 - mt[1]
+            kind, min_obs = 0, (mt[0] if auto else 10)
+        else:                                                        # OOS Rolling: rows [lo, hi), :1181-1199
+            ts = np.arange(win + 1 + gap, T)
+            lo = np.maximum(ts - win - gap, 0); hi = np.minimum(ts - 1 - gap, T)
+            kind, min_obs = 0, (min_nona if auto else 10)
+        if ts.size:
+            hi = np.maximum(hi, lo)
+            lo32, hi32, ts32 = (np.ascontiguousarray(a, dtype=np.int32) for a in (lo, hi, ts))
+            f = np.empty(ts.size); rl = np.empty(ts.size)
+            ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+            dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+            Xc = X if (X.cs == 1 or X.cols == 1) else X.copy()      # the RAW panel: the call standardises it (nanStdCols) itself
+            check(lib.um_tprf_oos_windows(y._ref(), Xc._ref(), None if auto else Z._ref(), n_auto, kind, ip(lo32), ip(hi32), ip(ts32),
+                                          ts.size, int(min_obs), 1, dp(f), dp(rl)))
+            fore[ts, 0] = f
+            roll[ts, 0] = rl
+    elif procedure == "OOS Cross Val":                               # :1112-1146
         for t in range(T):
             lo, hi = max(t - window[0], 0), min(t - window[0] + window[1], T)
             yt = _drop_rows(y, lo, hi)
@@ -335,20 +362,23 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
                                            _rows(Xn, t, t + 1), min_nona))
             roll[t, 0] = _nan_mean(yt) if (eff_pls or has_nan) else yt.mean()   # colMean(yt, hasNan)
 
-    forecasts, rollfore = Mat.from_numpy(fore), Mat.from_numpy(roll)
-    residuals = y - forecasts
-    loc = ~residuals.isnan()                                         # rows with a forecast (:1207)
-    e, yl, rl = residuals[loc], y[loc], rollfore[loc]
+    # point estimates over the rows that have a forecast (`loc`, :1207): T-long vectors, summed on the host in the
+    # reference's order (sequential while loops, :1226-1238) -- one copy of y down, three small vectors up
+    yh = y.to_numpy()
+    res = yh - fore
+    loc = ~np.isnan(res[:, 0])
     r2 = enc = float("nan")
-    if e.cols > 0:
-        see = (e * e).sum()
-        d = yl - rl
-        sst = (d * d).sum()
-        if sst != 0.0:
-            r2 = 1.0 - see / sst                                     # :1226-1233 (ssT == 0 -> NaN)
-        if procedure == "OOS Recursive":                             # encnew(rollfore[loc], residuals[loc]), :854-860
-            with np.errstate(all="ignore"):
-                enc = float(np.float64(e.cols) * np.float64((rl * rl - rl * e).sum()) / np.float64(see))
+    if loc.any():
+        e, rl = res[loc, 0], roll[loc, 0]
+        with np.errstate(all="ignore"):
+            see = float(np.add.reduce(e * e))
+            d = yh[loc, 0] - rl
+            sst = float(np.add.reduce(d * d))
+            if sst != 0.0:
+                r2 = 1.0 - see / sst                                 # :1226-1233 (ssT == 0 -> NaN)
+            if procedure == "OOS Recursive":                         # encnew(rollfore[loc], residuals[loc]), :854-860
+                enc = float(np.float64(e.size) * np.float64(np.add.reduce(rl * rl - rl * e)) / np.float64(see))
+    forecasts, rollfore, residuals = Mat.from_numpy(fore), Mat.from_numpy(roll), Mat.from_numpy(res)
     return Tprf3Result(forecasts, residuals, r2, rollfore=rollfore, encnew=enc)
 
 
