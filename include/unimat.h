@@ -65,11 +65,17 @@ typedef struct um_view {
 int32_t um_version(void);
 const char* um_last_error(void);
 int32_t um_device_count(int32_t* out);
-int32_t um_init(int32_t device);            /* selects the device for the calling thread */
+/* Binds the calling host thread to `device` (own stream, own scratch).  One device per process: the first um_init
+ * fixes it, a later um_init with another device returns UM_ERR_ARG, and host threads that never call um_init (a JVM
+ * Cleaner or ForkJoin worker) inherit it on their first library call. */
+int32_t um_init(int32_t device);
 int32_t um_shutdown(void);
 int32_t um_sync(void);                      /* synchronise the calling thread's stream   */
 int32_t um_device_props(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* total_mem);
 int32_t um_malloc(size_t bytes, void** out);      /* stream-ordered pool (cudaMallocAsync)   */
+/* May be called from ANY host thread (JVM Cleaner, Python GC): the block remembers the device and stream it was
+ * allocated on and the free is queued there, after everything the allocating thread launched on it.  Never opens a
+ * context; a pointer that is not a live um_malloc block returns UM_ERR_ARG. */
 int32_t um_free(void* ptr);
 int32_t um_malloc_host(size_t bytes, void** out); /* pinned host memory for staging          */
 int32_t um_free_host(void* ptr);
@@ -138,10 +144,6 @@ int32_t um_rng_uniform(um_rng* g, double low, double high, const um_view* dst); 
 int32_t um_rng_randn(um_rng* g, const um_view* dst);                            /* MatD.randn    Mat.scala:1480,1488 */
 int32_t um_rng_normal(um_rng* g, double mean, double sd, const um_view* dst);    /* MatD.normal   Mat.scala:1500 */
 int32_t um_rng_randint(um_rng* g, int32_t low, int32_t high, const um_view* dst_i32); /* MatD.randint Mat.scala:1525 */
-/* which kernels um_rng_randn / um_rng_normal use: 0 = automatic (= 1), 1 = scan / prefix / emit kernels (the stream is
- * generated twice), 2 = single pass (generated once, segments chained by a decoupled look-back; measured slower:
- * 17.5 vs 10.7 ms per 2^30 draws).  Same values either way.  Process-wide; for tests and profiling. */
-int32_t um_rng_set_randn_path(int32_t path);
 
 /* ---- on-disk format -----------------------------------------------------------------
  * `path.loadMatD` / `loadSmartD` / `loadMatF` (ext/PathExts.scala:583-590 -> io/FileOps.scala:139-188): CSV text ->
@@ -275,8 +277,9 @@ typedef enum um_tprf_mode {
                          * (Tprf3.scala:883-943) = t3prf's passes 1 and 2 with the nanOls pass 3             */
 } um_tprf_mode;
 
-/* Single-GPU (or this rank's column shard when a communicator is active: X holds the local
- * N_local columns, y and Z are replicated, n_total = N over all ranks).  X: T x N_local f64
+/* n_total <= 0: a fit of the panel held in X (communicator or not -- nothing is exchanged).  n_total > 0 with an
+ * active communicator of more than one rank: X is this rank's column shard (N_local columns, y and Z replicated,
+ * n_total = N over all ranks) and the packed partial sums are all-reduced once.  X: T x N_local f64
  * view with cs == 1; y: T x 1; Z: T x L, L <= 8. */
 int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_view* Z, int64_t n_total,
                     um_tprf_out* out);

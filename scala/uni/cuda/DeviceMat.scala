@@ -15,7 +15,10 @@ final class DeviceBuffer(val ptr: MemorySegment, val bytes: Long):
 object DeviceBuffer:
   private val cleaner = Cleaner.create()
   private final class Free(p: MemorySegment) extends Runnable:
-    def run(): Unit = um_free.invoke(p)
+    // runs on the Cleaner's thread: um_free queues the free on the allocating thread's stream and device (unimat.h)
+    def run(): Unit =
+      val rc = um_free.invoke(p).asInstanceOf[Int]
+      if rc != 0 then System.err.println(s"libunimat: um_free failed ($rc): ${lastError()}")
   def alloc(bytes: Long): DeviceBuffer =
     val out = Arena.global().allocate(ADDRESS)
     check(um_malloc.invoke(math.max(bytes, 1L), out).asInstanceOf[Int])

@@ -113,24 +113,16 @@ def test_randn_64M_draws(u):
 
 
 @pytest.mark.parametrize("n", [1, 4096, 4097, 100003, 1 << 22, (1 << 25) + 12345])
-def test_randn_single_pass_and_multi_kernel_paths_are_identical(u, n):
-    """Both kernel organisations consume the stream identically: same bits (tails included: same device arithmetic),
-    same generator state afterwards."""
-    from uni_b200 import rng
-    outs, states = [], []
-    try:
-        for path in (1, 2):
-            rng.set_randn_path(path)
-            g = u.NumPyRNG(2024)
-            a = g.randn(1, n).to_numpy()
-            b = g.normal(1.5, 0.25, 7, 11).to_numpy()
-            outs.append((a, b))
-            states.append(g.state)
-    finally:
-        rng.set_randn_path(0)
-    assert states[0] == states[1]
-    assert np.array_equal(bits(outs[0][0]), bits(outs[1][0])) and np.array_equal(bits(outs[0][1]), bits(outs[1][1]))
-    assert_normal_stream_equal(outs[1][0], np.random.default_rng(2024).standard_normal(n))
+def test_randn_lengths_straddling_segments(u, n):
+    """Stream lengths on either side of the 4096-draw segment and of the prefix levels: values, a following affine
+    fill and the generator state afterwards all equal NumPy's."""
+    g = u.NumPyRNG(2024)
+    r = np.random.default_rng(2024)
+    assert_normal_stream_equal(g.randn(1, n).to_numpy(), r.standard_normal(n))
+    got, want = g.normal(1.5, 0.25, 7, 11).to_numpy().ravel(), r.normal(1.5, 0.25, 77)
+    ok = np.abs((want - 1.5) / 0.25) <= R - 1e-6
+    assert np.array_equal(bits(got[ok]), bits(want[ok])) and np.allclose(got, want, rtol=1e-15, atol=0)
+    assert g.nextLong() & ro.M64 == int(r.bit_generator.random_raw())
 
 
 def test_randn_one_call_of_2_30_draws_equals_chunked_calls(u):

@@ -119,7 +119,6 @@ SIGNATURES = {
     "um_rng_randn": (_i32, [_vp, VP]),
     "um_rng_normal": (_i32, [_vp, _f64, _f64, VP]),
     "um_rng_randint": (_i32, [_vp, _i32, _i32, VP]),
-    "um_rng_set_randn_path": (_i32, [_i32]),
     "um_csv_open": (_i32, [C.c_char_p, _i32, C.POINTER(C.c_uint64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32)]),
     "um_csv_header": (_i32, [C.c_uint64, _i64, C.c_char_p, _i64]),
     "um_csv_read_host": (_i32, [C.c_uint64, _vp, _i64]),

@@ -134,7 +134,21 @@ int comm_check_error() {
 int comm_allreduce_sum_f64_impl(double* buf, i64 count) {
   if (!g_comm.comm) return fail(UM_ERR_NCCL, "communicator not initialised");
   if (g_comm.world == 1 || count == 0) return UM_OK;
-  if (g_p2p.ok && count <= P2P_CAP && (reinterpret_cast<uintptr_t>(buf) & 15) == 0) return p2p_allreduce(buf, count);
+  // the transport choice must be the same on every rank: it depends only on what was agreed at um_comm_init and on
+  // the (common) count, never on a rank-local property of the buffer
+  if (g_p2p.ok && count <= P2P_CAP) {
+    if (reinterpret_cast<uintptr_t>(buf) & 15) {  // a view at an odd element offset: bounce through an aligned block
+      static thread_local double* bounce = nullptr;
+      if (!bounce) UM_CUDA(cudaMalloc(&bounce, (size_t)P2P_CAP * sizeof(double)));
+      cudaStream_t st = ctx()->stream;
+      UM_CUDA(cudaMemcpyAsync(bounce, buf, (size_t)count * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      const int s = p2p_allreduce(bounce, count);
+      if (s != UM_OK) return s;
+      UM_CUDA(cudaMemcpyAsync(buf, bounce, (size_t)count * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      return UM_OK;
+    }
+    return p2p_allreduce(buf, count);
+  }
   cudaStream_t st = ctx()->stream;
   if (count > g_comm.capacity) {
     if (g_comm.gather) {

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -14,6 +15,14 @@ static thread_local char t_err[512] = "";
 static thread_local Ctx t_ctx;
 std::atomic<long long> g_launches{0};
 static std::once_flag g_pool_once[64];
+// The device the process chose with its first um_init: host threads that never called um_init themselves (a JVM
+// Cleaner / ForkJoin worker, Python's GC running off the owning thread) inherit it instead of opening device 0.
+static std::atomic<int> g_default_device{-1};
+// Every um_malloc block remembers the device and stream it was allocated on, so um_free can be called from ANY host
+// thread: the free is queued on the owner's stream (ordered after everything that thread submitted) on the owner's device.
+struct Owner { int device; cudaStream_t stream; };
+static std::mutex g_alloc_mu;
+static std::unordered_map<void*, Owner> g_allocs;
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -53,6 +62,8 @@ static int init_ctx(int device) {
     UM_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
   }
   c.device = device;
+  int none = -1;
+  g_default_device.compare_exchange_strong(none, device);
   if (device < 64) {
     std::call_once(g_pool_once[device], [device]() {
       cudaMemPool_t pool;
@@ -77,7 +88,8 @@ int ensure_ctx() {
     cudaSetDevice(t_ctx.device);
     return UM_OK;
   }
-  return init_ctx(0);
+  const int d = g_default_device.load();
+  return init_ctx(d >= 0 ? d : 0);
 }
 
 void* scratch(size_t bytes) {
@@ -181,7 +193,14 @@ int32_t um_device_count(int32_t* out) {
   return UM_OK;
 }
 
-int32_t um_init(int32_t device) { return init_ctx(device); }
+int32_t um_init(int32_t device) {
+  // One device per process (one process per GPU): kernel attributes, occupancy results and the peer-memory exchange
+  // are cached process-wide, so a second device in the same process is refused instead of silently reusing them.
+  const int d = g_default_device.load();
+  if (d >= 0 && device != d)
+    return fail(UM_ERR_ARG, "um_init(%d): this process is bound to device %d (libunimat is one process per GPU)", device, d);
+  return init_ctx(device);
+}
 
 int32_t um_shutdown(void) {
   Ctx& c = *ctx();
@@ -227,14 +246,35 @@ int32_t um_malloc(size_t bytes, void** out) {
     cudaGetLastError();
     return fail(UM_ERR_OOM, "um_malloc(%zu): %s", bytes, cudaGetErrorString(e));
   }
+  {
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    g_allocs[*out] = Owner{ctx()->device, ctx()->stream};
+  }
   return UM_OK;
 }
 
 int32_t um_free(void* ptr) {
   if (!ptr) return UM_OK;
-  UM_CTX();
-  op_epoch_passive();
-  UM_CUDA(cudaFreeAsync(ptr, ctx()->stream));
+  // no UM_CTX(): a free must never open a context (a Cleaner thread would open device 0 on every rank)
+  Owner o{-1, nullptr};
+  {
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    auto it = g_allocs.find(ptr);
+    if (it == g_allocs.end()) return fail(UM_ERR_ARG, "um_free(%p): not a live um_malloc block", ptr);
+    o = it->second;
+    g_allocs.erase(it);
+  }
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (cur != o.device) UM_CUDA(cudaSetDevice(o.device));
+  // queued on the owner's stream: ordered after every kernel the owning thread launched on the block
+  cudaError_t e = cudaFreeAsync(ptr, o.stream);
+  if (e != cudaSuccess) {  // the owner re-initialised onto another device and its stream is gone
+    cudaGetLastError();
+    e = cudaFree(ptr);
+  }
+  if (cur >= 0 && cur != o.device) cudaSetDevice(cur);
+  if (e != cudaSuccess) return fail(UM_ERR_CUDA, "um_free(%p): %s", ptr, cudaGetErrorString(e));
   return UM_OK;
 }
 

@@ -720,151 +720,6 @@ __global__ void __launch_bounds__(RNG_THREADS, 3) k_zig_emit(const __grid_consta
   }
 }
 
-// ---- single-pass ziggurat ---------------------------------------------------------------------------------------
-// The same resolution as k_zig_scan + prefix + emit, but the stream is generated ONCE: a block keeps its draws in
-// registers, publishes its 16-entry map, learns its true entry offset and first output index from its predecessors
-// by a decoupled look-back (the maps compose associatively: warp 0 folds predecessor maps right to left until it meets
-// a segment whose inclusive result is published), publishes its own inclusive result, and emits.  Segments are
-// handed out by an atomic ticket, so a block only ever waits for blocks that were scheduled before it.
-// Measured (2^30 draws): 17.5 ms against 10.7 ms for the three-kernel path -- the ~440 resident blocks reach their
-// look-back together and each walks its predecessors one dependent L2 read at a time, and the kernel keeps 16 draws
-// per thread live (80 registers, 3 blocks per SM).  Kept behind um_rng_set_randn_path(2) and pinned by the tests
-// (both paths must produce identical bits); NOT the default.
-__device__ __forceinline__ unsigned ld_flag(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_flag(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__global__ void __launch_bounds__(RNG_THREADS, 3) k_zig_onepass(const __grid_constant__ Jump J, const ulonglong2* __restrict__ bs,
-                                                               unsigned* __restrict__ ticket, unsigned* __restrict__ flag,
-                                                               unsigned* __restrict__ agg, i64* __restrict__ incl_cnt,
-                                                               int* __restrict__ incl_exit, i64 nseg, double* __restrict__ out,
-                                                               i64 n_out, double mean, double sd, int affine,
-                                                               i64* __restrict__ result) {
-  __shared__ ZigShared sh;
-  __shared__ unsigned s_map[ZIG_ENTRIES];
-  __shared__ unsigned s_seg;
-  __shared__ int s_entry;
-  __shared__ i64 s_base;
-  const int t = threadIdx.x, lane = t & 31;
-  if (t == 0) s_seg = atomicAdd(ticket, 1u);
-  zig_init_shared(sh);  // ends with a barrier
-  const i64 seg = s_seg;
-  const i64 seg_base = seg * SEG;
-  const ulonglong2* wsb = bs + seg * ZIG_WARPS;
-  const ulonglong2 b = wsb[0];
-  u64 raws[RNG_PER_THREAD];
-  zig_generate(sh, J, wsb, raws);
-  __syncthreads();
-  zig_evaluate(sh, J, b, true);
-  __syncthreads();
-  zig_chain0(sh);
-  zig_prefix(sh);
-  if (t < 32) {
-    const int e = lane & (ZIG_ENTRIES - 1);
-    // this segment's map
-    int ex = 0xff, cnt = 0;
-    if (!sh.overflow) {
-      if (e == 0) { cnt = sh.prefix[SEG_WORDS]; ex = max(sh.reach, SEG) - SEG; }
-      else cnt = zig_enter<false>(sh, e, ex);
-      if (ex >= ZIG_ENTRIES) ex = 0xff;
-    }
-    const unsigned packed = (unsigned)cnt | ((unsigned)ex << 16);
-    if (lane < ZIG_ENTRIES) {
-      s_map[e] = packed;
-      agg[seg * ZIG_ENTRIES + e] = packed;
-      __threadfence();
-    }
-    __syncwarp();
-    int ent = 0;
-    i64 base = 0;
-    if (seg > 0) {
-      if (lane == 0) st_flag(flag + seg, 1u);
-      int f_ex = e;       // composed map of the segments between the look-back cursor and this one
-      i64 f_cnt = 0;
-      for (i64 j = seg - 1;; j--) {
-        unsigned f;
-        do { f = ld_flag(flag + j); } while (f == 0u);
-        if (f == 2u) {
-          const int pex = __ldcg(incl_exit + j);
-          const i64 pc = __ldcg(incl_cnt + j);
-          const int src = pex == 0xff ? 0 : pex;
-          const int fe = __shfl_sync(0xffffffffu, f_ex, src);
-          const i64 fc = __shfl_sync(0xffffffffu, f_cnt, src);
-          ent = pex == 0xff ? 0xff : fe;
-          base = pc + fc;
-          break;
-        }
-        const unsigned a = __ldcg(agg + j * ZIG_ENTRIES + e);
-        const int aex = (int)(a >> 16);
-        const int src = aex == 0xff ? 0 : aex;
-        const int ne = __shfl_sync(0xffffffffu, f_ex, src);
-        const i64 nc = __shfl_sync(0xffffffffu, f_cnt, src);
-        f_ex = aex == 0xff ? 0xff : ne;
-        f_cnt = (i64)(a & 0xffffu) + nc;
-      }
-    }
-    if (lane == 0) {
-      int oex = 0xff;
-      i64 ocnt = base;
-      if (ent != 0xff) {
-        const unsigned m = s_map[ent];
-        oex = (int)(m >> 16);
-        ocnt = base + (i64)(m & 0xffffu);
-      }
-      incl_cnt[seg] = ocnt;
-      incl_exit[seg] = oex;
-      __threadfence();
-      st_flag(flag + seg, 2u);
-      if (oex == 0xff) result[2] = 1;
-      if (seg == nseg - 1) { result[0] = ocnt; result[1] = oex; }
-      s_entry = ent;
-      s_base = base;
-    }
-  }
-  __syncthreads();
-  const int entry = s_entry;
-  const i64 out_base = s_base;
-  if (entry == 0xff || out_base >= n_out) return;
-  if (entry > 0) {  // block-uniform
-    if (t == 0) {
-      int ex;
-      zig_enter<true>(sh, entry, ex);
-    }
-    __syncthreads();
-    zig_prefix(sh);
-  }
-#pragma unroll
-  for (int j = 0; j < RNG_PER_THREAD; j++) {
-    const int p = j * RNG_THREADS + t;
-    const u64 ym = sh.ym[p >> 6];
-    if (!((ym >> (p & 63)) & 1)) continue;
-    const i64 o = out_base + sh.prefix[p >> 6] + __popcll(ym & ((1ULL << (p & 63)) - 1));
-    if (o >= n_out) continue;
-    int idx, sign;
-    u64 rabs;
-    zig_split(raws[j], idx, sign, rabs);
-    double v;
-    int consumed = 1;
-    if (rabs < sh.ki[idx]) {
-      v = zig_x(rabs, sh.wi[idx], sign);
-    } else {
-      const int slot = sh.slot_of[p];
-      consumed = sh.cons[slot];
-      v = idx == 0 ? sh.tailv[slot] : zig_x(rabs, sh.wi[idx], sign);
-    }
-    if (affine) v = __dadd_rn(mean, __dmul_rn(sd, v));
-    out[o] = v;
-    if (o == n_out - 1) result[3] = seg_base + p + consumed;
-  }
-}
-
-std::atomic<int> g_randn_path{0};  // 0 = automatic (scan / prefix / emit kernels), 1 = those kernels, 2 = single pass
-
 int upload_tables() {
   static std::atomic<unsigned long long> done{0};  // one bit per device
   Ctx* c = ctx();
@@ -999,16 +854,6 @@ int randn_impl(um_rng* g, const um_view* dst, double mean, double sd, int affine
       k_zig_warp_states<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(J, g->state_hi, g->state_lo, nseg, bs);
       UM_LAUNCHED();
     }
-    if (g_randn_path.load() == 2) {
-      // single pass: the table area doubles as the published maps; seg_base / seg_entry areas hold the inclusive results
-      unsigned* flag = reinterpret_cast<unsigned*>(ym_all);            // nseg words (+1 ticket) inside the unused mask area
-      unsigned* ticket = flag + nseg;
-      UM_CUDA(cudaMemsetAsync(flag, 0, ((size_t)nseg + 1) * sizeof(unsigned), st));
-      int* incl_exit = reinterpret_cast<int*>(maps);                  // sized below: see `map_off`
-      k_zig_onepass<<<(unsigned)nseg, RNG_THREADS, 0, st>>>(J, bs, ticket, flag, table, seg_base, incl_exit, nseg, out, n, mean, sd,
-                                                            affine, result);
-      UM_LAUNCHED();
-    } else {
     k_zig_scan<<<(unsigned)nseg, RNG_THREADS, 0, st>>>(J, bs, table, ym_all);
     UM_LAUNCHED();
     k_zig_pf_reduce<<<pf_blocks, PF_THREADS, 0, st>>>(table, nseg, maps);
@@ -1021,7 +866,6 @@ int randn_impl(um_rng* g, const um_view* dst, double mean, double sd, int affine
     UM_LAUNCHED();
     k_zig_emit<<<(unsigned)nseg, RNG_THREADS, 0, st>>>(J, bs, seg_entry, seg_base, out, n, mean, sd, affine, result);
     UM_LAUNCHED();
-    }
     i64 res[4];
     UM_CUDA(cudaMemcpyAsync(res, result, sizeof(res), cudaMemcpyDeviceToHost, st));
     UM_CUDA(cudaStreamSynchronize(st));
@@ -1105,12 +949,6 @@ int32_t um_rng_randint(um_rng* g, int32_t low, int32_t high, const um_view* dst_
   int32_t bound = (int32_t)((uint32_t)high - (uint32_t)low);
   if (bound <= 0) return fail(UM_ERR_ARG, "bound must be positive");
   return draw_impl<DRAW_INT>(g, dst_i32, 0, 0, low, (unsigned)bound, "um_rng_randint");
-}
-
-int32_t um_rng_set_randn_path(int32_t path) {
-  if (path < 0 || path > 2) return fail(UM_ERR_ARG, "um_rng_set_randn_path: 0 (automatic), 1 (scan / prefix / emit) or 2 (single pass)");
-  g_randn_path.store(path);
-  return UM_OK;
 }
 
 int32_t um_rng_randn(um_rng* g, const um_view* dst) { return randn_impl(g, dst, 0.0, 1.0, 0, "um_rng_randn"); }

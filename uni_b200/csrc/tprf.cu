@@ -1471,6 +1471,9 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
   UM_REQUIRE(L >= 1 && L <= LP, "number of proxies L = %lld outside [1, %d]", L, LP);
   UM_REQUIRE(T >= 1 && N >= 1, "empty panel");
   UM_REQUIRE(X->cs == 1 || N == 1, "X must be row-contiguous (cs == 1); materialise the view first");
+  // n_total > 0 declares a column-sharded fit (partials are summed over the communicator); n_total <= 0 is a fit of
+  // the panel this rank holds, communicator or not (replicated rows must never be summed across ranks)
+  const bool sharded = n_total > 0 && comm_active() && comm_world() > 1;
   if (n_total <= 0) n_total = N;
   out->r_squared = nan("");
   out->singular = 0;
@@ -1504,7 +1507,7 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
   if (s != UM_OK) return s;
   s = run_sweeps(p, ws, xp, ldx, 0, 0);
   if (s != UM_OK) return s;
-  if (comm_active() && comm_world() > 1) {
+  if (sharded) {
     prof_begin(6);
     s = comm_allreduce_sum_f64_impl(reinterpret_cast<double*>(ws + p.o_packed), p.packed_len);
     prof_end(6);
@@ -1561,6 +1564,7 @@ int32_t um_tprf_fit_host(int32_t mode, const double* y, const double* X, int64_t
   UM_REQUIRE(y && X && Z, "null input");
   UM_REQUIRE(L >= 1 && L <= LP, "number of proxies L = %lld outside [1, %d]", (i64)L, LP);
   UM_REQUIRE(T >= 1 && N_local >= 1 && ldx >= N_local, "bad panel shape");
+  const bool sharded = n_total > 0 && comm_active() && comm_world() > 1;
   if (n_total <= 0) n_total = N_local;
   Ctx& c = *ctx();
   // column blocks of CB columns are staged through two device buffers: H2D of block k+1 (copy
@@ -1615,7 +1619,7 @@ int32_t um_tprf_fit_host(int32_t mode, const double* y, const double* X, int64_t
     UM_CUDA(cudaMemcpyAsync(w0_keep + c0 * LP, ws + p.o_w0, (size_t)w * LP * 8, cudaMemcpyDeviceToDevice, st));
     UM_CUDA(cudaEventRecord(ev_free[bsel], st));
   }
-  if (comm_active() && comm_world() > 1) {
+  if (sharded) {
     s = comm_allreduce_sum_f64_impl(reinterpret_cast<double*>(ws + p.o_packed), p.packed_len);
     if (s != UM_OK) return s;
   }

@@ -77,11 +77,6 @@ class NumPyRNG:
         return self._fill(lib.um_rng_randint, Mat._alloc(rows, cols, L.I32), int(low), int(high))
 
 
-def set_randn_path(path: int) -> None:
-    """um_rng_set_randn_path: 0 = automatic, 1 = scan / prefix / emit kernels, 2 = single-pass kernel (tests, profiling)."""
-    check(lib.um_rng_set_randn_path(int(path)))
-
-
 # `private[data] lazy val defaultRNG = new NumPyRNG(0)`, `@volatile var globalRNG` (Mat.scala:1460-1461)
 _global: NumPyRNG | None = None
 
