@@ -110,6 +110,46 @@ object UniMatLib:
   val um_csv_close    = h("um_csv_close", I(JAVA_LONG))
   val um_csv_save     = h("um_csv_save", I(ADDRESS, ADDRESS, ADDRESS, ADDRESS))
 
+  // ---- the rest of include/unimat.h (tests/test_abi_cpu.py::test_scala_binding_matches_header keeps this file and
+  //      the header in step: every prototype has exactly one handle with the same argument layouts)
+  // device / lifecycle / raw memory
+  val um_version      = h("um_version", I())
+  val um_device_count = h("um_device_count", I(ADDRESS))
+  val um_shutdown     = h("um_shutdown", I())
+  val um_device_props = h("um_device_props", I(ADDRESS, ADDRESS, ADDRESS, ADDRESS))
+  val um_d2d          = h("um_d2d", I(ADDRESS, ADDRESS, JAVA_LONG))
+  val um_memset       = h("um_memset", I(ADDRESS, JAVA_INT, JAVA_LONG))
+  val um_h2d_2d       = h("um_h2d_2d", I(ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG))
+  // measurement hooks (apps/Tprf3Bench.scala's stopwatch becomes device events)
+  val um_launch_count = h("um_launch_count", I(ADDRESS))
+  val um_timer_start  = h("um_timer_start", I())
+  val um_timer_stop   = h("um_timer_stop", I(ADDRESS))
+  val um_prof_enable  = h("um_prof_enable", I(JAVA_INT))
+  val um_prof_reset   = h("um_prof_reset", I())
+  val um_prof_read    = h("um_prof_read", I(JAVA_INT, ADDRESS, ADDRESS))
+  val um_tprf_work    = h("um_tprf_work", I(JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS))
+  val um_tprf_debug_stamps = h("um_tprf_debug_stamps", I(ADDRESS))
+  // layout queries (Mat.scala:1865-1876 isWeirdLayout, isContiguous), factories (MatD.eye, counter-based fills)
+  val um_view_is_weird      = h("um_view_is_weird", I(ADDRESS, ADDRESS))
+  val um_view_is_contiguous = h("um_view_is_contiguous", I(ADDRESS, ADDRESS))
+  val um_eye   = h("um_eye", I(ADDRESS))
+  val um_randn = h("um_randn", I(ADDRESS, JAVA_LONG))
+  val um_rand  = h("um_rand", I(ADDRESS, JAVA_LONG))
+  // batched small inverse (the nanOls passes of estimate3prf(pls = true)) and the out-of-sample procedures in one launch
+  val um_inverse_batched  = h("um_inverse_batched", I(ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG, JAVA_LONG))
+  val um_tprf_oos_windows = h("um_tprf_oos_windows",
+    I(ADDRESS, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS))
+  // communicator queries and the raw exchange
+  val um_comm_info              = h("um_comm_info", I(ADDRESS, ADDRESS))
+  val um_comm_transport         = h("um_comm_transport", I(ADDRESS))
+  val um_comm_allreduce_sum_f64 = h("um_comm_allreduce_sum_f64", I(ADDRESS, JAVA_LONG))
+  val um_comm_barrier           = h("um_comm_barrier", I())
+  // CSV cells on the host (FileOps.scala:139-188, Mat.scala:90-116)
+  val um_csv_read_host  = h("um_csv_read_host", I(JAVA_LONG, ADDRESS, JAVA_LONG))
+  val um_csv_format_f64 = h("um_csv_format_f64", I(JAVA_DOUBLE, ADDRESS, ADDRESS, JAVA_LONG))
+  val um_csv_format_f32 = h("um_csv_format_f32", I(JAVA_FLOAT, ADDRESS, ADDRESS, JAVA_LONG))
+  val um_csv_parse_cell = h("um_csv_parse_cell", I(ADDRESS, ADDRESS))
+
   // status -> the exception the reference throws for the same condition
   def check(status: Int): Unit =
     if status != 0 then

@@ -30,6 +30,42 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib.um_version() == 1
 
 
+def _c_layout(t):
+    """C parameter type -> the Panama ValueLayout the Scala binding must name for it."""
+    if "*" in t or "[" in t:   # arrays decay to pointers
+        return "ADDRESS"
+    t = re.sub(r"\bconst\b", "", t).strip()
+    if t.startswith(("long long", "unsigned long long")):
+        return "JAVA_LONG"
+    return {"int32_t": "JAVA_INT", "uint32_t": "JAVA_INT", "int": "JAVA_INT", "int64_t": "JAVA_LONG", "uint64_t": "JAVA_LONG",
+            "size_t": "JAVA_LONG", "double": "JAVA_DOUBLE", "float": "JAVA_FLOAT"}[t.split()[0]]
+
+
+def test_scala_binding_matches_header():
+    """scala/uni/cuda/UniMatLib.scala cannot be compiled here (no JVM), so it is parsed: every prototype of the header
+    has exactly one downcall handle, with the same number of arguments and the matching Panama layout for each."""
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "unimat.h")).read(), flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"([A-Za-z_0-9\* ]+?)\b(um_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        a = [] if args.strip() in ("", "void") else [_c_layout(x.strip()) for x in args.split(",")]
+        protos[name] = ("ADDRESS" if "*" in ret else "JAVA_INT", a)
+    assert sorted(protos) == header_symbols()
+    sc = open(os.path.join(ROOT, "scala", "uni", "cuda", "UniMatLib.scala")).read()
+    handles = re.findall(r'val\s+(um_[a-z0-9_]+)\s*=\s*h\("(um_[a-z0-9_]+)",\s*(I\(([^)]*)\)|FunctionDescriptor\.of\(([^)]*)\))\)', sc)
+    seen = {}
+    for val, name, _, iargs, fargs in handles:
+        assert val == name, f"handle {val} binds {name}"
+        assert name not in seen, f"{name} bound twice"
+        if fargs:
+            parts = [x.strip() for x in fargs.split(",") if x.strip()]
+            seen[name] = (parts[0], parts[1:])
+        else:
+            seen[name] = ("JAVA_INT", [x.strip() for x in iargs.split(",") if x.strip()])
+    assert sorted(seen) == sorted(protos), (sorted(set(protos) - set(seen)), sorted(set(seen) - set(protos)))
+    for name, sig in protos.items():
+        assert seen[name] == sig, f"{name}: header {sig} vs Scala {seen[name]}"
+
+
 def test_struct_layout_matches_header():
     from uni_b200._lib import UmTprfOut, UmView
     assert C.sizeof(UmView) == 56 and UmView.rows.offset == 16 and UmView.dtype.offset == 48
