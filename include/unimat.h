@@ -182,6 +182,11 @@ int32_t um_unary(int32_t op, const um_view* a, const um_view* out);
 
 /* softmax(axis) (MatMathOps.scala:156-226); out is f64 */
 int32_t um_softmax(const um_view* a, int32_t axis, const um_view* out);
+/* softmax over strided lanes (axis 0 of a row-major matrix): 0 = automatic (large FP64 row-major matrices of up to
+ * 32768 rows take the single-read strip kernel: a column strip held in tensor memory across a thread-block cluster,
+ * softmax_strip.cuh; everything else the two-read kernels), 1 = two-read kernels only, 2 = strip kernel or
+ * UM_ERR_ARG.  Process-wide; for tests and profiling. */
+int32_t um_softmax_set_axis0_path(int32_t path);
 
 /* ---- masks: IEEE compare -> Mat[Boolean] (Mat.scala:2564-2582,3948-4003), isnan/isinf/
  *      isfinite (:4214-4225), && || ! (:5157-5170) ------------------------------------ */
@@ -238,6 +243,10 @@ int32_t um_matmul(const um_view* a, const um_view* b, const um_view* out);
  * UM_ERR_ARG.  Process-wide; for tests and profiling.  UM_MATF_TENSOR=0 in the environment makes
  * automatic mean 1. */
 int32_t um_matmul_set_f32_path(int32_t path);
+/* FP64 `*@` CTA tile: 0 = automatic (64 x 64 tiles, two CTAs per SM, whenever 128 x 128 tiles would leave SMs idle
+ * or a mostly empty last wave -- 1024^2 and 2048^2 of BASELINE config 3; 128 x 128 otherwise), 64 / 128 = forced.
+ * Process-wide; for tests and profiling. */
+int32_t um_matmul_set_f64_tile(int32_t tile);
 /* inverse (Mat.scala:2979-3006): LU with partial pivoting (luDecomposeD :970-1001); exact-zero
  * pivot -> UM_ERR_SINGULAR.  Batched form: `batch` matrices `stride_*` elements apart. */
 int32_t um_inverse(const um_view* a, const um_view* out);

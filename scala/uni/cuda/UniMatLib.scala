@@ -57,6 +57,7 @@ object UniMatLib:
   val um_binary_scalar  = h("um_binary_scalar", I(JAVA_INT, ADDRESS, JAVA_DOUBLE, JAVA_INT, ADDRESS))
   val um_unary          = h("um_unary", I(JAVA_INT, ADDRESS, ADDRESS))
   val um_softmax        = h("um_softmax", I(ADDRESS, JAVA_INT, ADDRESS))
+  val um_softmax_set_axis0_path = h("um_softmax_set_axis0_path", I(JAVA_INT))
   val um_compare_scalar = h("um_compare_scalar", I(JAVA_INT, ADDRESS, JAVA_DOUBLE, ADDRESS))
   val um_compare        = h("um_compare", I(JAVA_INT, ADDRESS, ADDRESS, ADDRESS))
   val um_classify       = h("um_classify", I(JAVA_INT, ADDRESS, ADDRESS))
@@ -75,6 +76,7 @@ object UniMatLib:
   val um_mask_select = h("um_mask_select", I(ADDRESS, ADDRESS, ADDRESS))
   val um_matmul  = h("um_matmul", I(ADDRESS, ADDRESS, ADDRESS))
   val um_matmul_set_f32_path = h("um_matmul_set_f32_path", I(JAVA_INT))
+  val um_matmul_set_f64_tile = h("um_matmul_set_f64_tile", I(JAVA_INT))
   val um_inverse = h("um_inverse", I(ADDRESS, ADDRESS))
   val um_solve   = h("um_solve", I(ADDRESS, ADDRESS, ADDRESS))
   // ---- 3PRF + multi-GPU

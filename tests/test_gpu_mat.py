@@ -1,6 +1,7 @@
 """GPU parity tests for the Mat operator path: CUDA (through the C ABI / uni_b200 mirror) vs the
 CPU oracle and the reference's bit-pattern fixture.  Bit-exact for masks, arg*/idx*, min/max and
 exact elementwise ops; FP sums within rel 1e-12 scaled by sum|x|."""
+import math
 import os
 
 import numpy as np
@@ -385,6 +386,84 @@ def test_softmax_special_lanes(u):
     assert mf.softmax().dtype == 0 and mf.sigmoid().dtype == 0   # Mat[Double] even for MatF
 
 
+STRIP_SHAPES = [(1, 2), (5, 16), (127, 18), (128, 32), (129, 34), (300, 46), (2048, 64), (2049, 50), (4097, 130),
+                (8192, 256), (16385, 34), (20000, 66), (32768, 48), (1000, 3000)]   # 1, 2, 4, 8, 16-CTA clusters; ragged rows and strips
+
+
+@pytest.mark.parametrize("shape", STRIP_SHAPES)
+def test_softmax_axis0_strip_kernel(u, shape):
+    """softmax(0) through the single-read strip kernel (forced): against the oracle, against the two-read kernels,
+    and on a view whose row pitch differs from its width; every cluster size, boxes hanging over the last row and
+    strips hanging over the last column."""
+    T, N = shape
+    rng = np.random.default_rng(T * 31 + N)
+    a = rng.standard_normal((T, N)) * 2.0 + 0.25
+    want = mo.softmax(omat(a), 0).to2d()
+    m = dev(u, a)
+    try:
+        u.set_softmax_axis0_path(2)
+        got = m.softmax(0).to_numpy()
+        again = m.softmax(0).to_numpy()
+        big = rng.standard_normal((T + 3, N + 6))
+        got_v = dev(u, big)._raw_slice(2, T + 2, 4, N + 4).softmax(0).to_numpy()
+        u.set_softmax_axis0_path(1)
+        two = m.softmax(0).to_numpy()
+    finally:
+        u.set_softmax_axis0_path(0)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(got, two, rtol=1e-12, atol=0)
+    assert np.array_equal(got, again), "run-to-run reproducible"
+    np.testing.assert_allclose(got_v, mo.softmax(omat(big[2 : T + 2, 4 : N + 4].copy()), 0).to2d(), rtol=1e-12, atol=0)
+    np.testing.assert_allclose(got.sum(axis=0), 1.0, rtol=0, atol=1e-12)
+
+
+def test_softmax_axis0_strip_kernel_special_lanes(u):
+    """Lanes the shifted form must hand to the reference's arithmetic (wide spread, +-Inf, a non-finite first row) next
+    to ordinary ones in the same strips, NaN lanes, and a strip where only the LAST CTA of the cluster sees the value."""
+    T, N = 5000, 40
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((T, N))
+    a[17, 1] = np.nan
+    a[0, 2] = np.nan
+    a[4999, 3] = np.inf
+    a[0, 4] = np.inf
+    a[123, 5] = -np.inf
+    a[0, 6] = -np.inf
+    a[:, 7] = -np.inf
+    a[2500, 8] = 900.0               # max - k > 300
+    a[4000, 9] = -900.0              # k - min > 300
+    a[:, 10] = np.linspace(-400.0, 400.0, T)
+    a[0, 17] = 1e308; a[1, 17] = -1e308
+    a[4999, 20] = 350.0
+    a[:, 21] = 0.0
+    a[3, 33] = -np.inf; a[4998, 33] = np.nan
+    want = mo.softmax(omat(a), 0).to2d()
+    try:
+        u.set_softmax_axis0_path(2)
+        got = dev(u, a).softmax(0).to_numpy()
+        u.set_softmax_axis0_path(1)
+        two = dev(u, a).softmax(0).to_numpy()
+    finally:
+        u.set_softmax_axis0_path(0)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=0, equal_nan=True)
+    np.testing.assert_allclose(two, want, rtol=1e-12, atol=0, equal_nan=True)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+
+
+def test_softmax_axis0_strip_kernel_refuses_what_it_cannot_take(u):
+    a = np.random.default_rng(1).standard_normal((64, 33))
+    try:
+        u.set_softmax_axis0_path(2)
+        with pytest.raises(ValueError):
+            dev(u, a).softmax(0)                        # odd column count
+        with pytest.raises(ValueError):
+            dev(u, a.astype(np.float32)).softmax(0)     # FP32 input
+    finally:
+        u.set_softmax_axis0_path(0)
+    with pytest.raises(ValueError):
+        u.set_softmax_axis0_path(3)
+
+
 # ---------------------------------------------------------------- reductions
 RED_SHAPES = [(1, 1), (1, 9), (9, 1), (3, 5), (5, 3), (64, 64), (65, 63), (257, 256), (300, 400), (4097, 33), (33, 4097), (2, 70001), (70001, 2)]
 
@@ -597,3 +676,114 @@ def test_mask_select_staged_kernel_and_offset_reuse(u):
     res = u.Mat._alloc(1, k2, u._lib.F64)
     u._lib.check(u._lib.lib.um_mask_select(da._ref(), dm._ref(), res._ref()))
     assert np.array_equal(res.to_numpy().ravel(), a[~mk])
+
+
+@pytest.mark.parametrize("tile", [64, 128])
+@pytest.mark.parametrize("mkn", [(1, 1, 1), (65, 63, 65), (127, 129, 131), (300, 400, 300), (1000, 17, 9), (1024, 512, 1024)])
+def test_matmul_f64_both_cta_tiles(u, mkn, tile):
+    """The 64 x 64 and the 128 x 128 CTA tile of the FP64 `*@` kernel, each forced: same contract, all four operand
+    orientations, partial tiles in every dimension; the automatic choice equals one of them bit for bit."""
+    M, K, N = mkn
+    rng = np.random.default_rng(M + 5 * K + 11 * N)
+    a = rng.standard_normal((M, K)); b = rng.standard_normal((K, N))
+    want = a @ b
+    tol = dict(rtol=1e-9, atol=1e-12 * K)
+    da, db, dat, dbt = dev(u, a), dev(u, b), dev(u, a.T.copy()).T, dev(u, b.T.copy()).T
+    try:
+        u.set_matd_matmul_tile(tile)
+        got = (da @ db).to_numpy()
+        np.testing.assert_allclose(got, want, **tol)
+        for x, yv in ((dat, db), (da, dbt), (dat, dbt)):
+            np.testing.assert_allclose((x @ yv).to_numpy(), want, **tol)
+        assert np.array_equal((da @ db).to_numpy(), got), "run-to-run reproducible"
+        u.set_matd_matmul_tile(0)
+        auto = (da @ db).to_numpy()
+        u.set_matd_matmul_tile(192 - tile)
+        other = (da @ db).to_numpy()
+    finally:
+        u.set_matd_matmul_tile(0)
+    assert np.array_equal(auto, got) or np.array_equal(auto, other)
+    with pytest.raises(ValueError):
+        u.set_matd_matmul_tile(96)
+
+
+# ---------------------------------------------------------------- BASELINE config sizes (configs 2 and 3)
+@pytest.mark.parametrize("n,dtype", [(4096, np.float64), (8192, np.float64), (4096, np.float32), (8192, np.float32)])
+def test_matmul_at_config3_sizes(u, n, dtype):
+    """`a *@ b` at the sizes of BASELINE config 3 (the sweep 1024^2 .. 16384^2): sampled rows and columns of the
+    n x n product against NumPy in float64.  FP64: the BLAS-vs-pure contract of MatmulModeSuite.scala:66-83;
+    FP32: the sgemm bound k * 2^-24 * (|a| @ |b|) and 6e-6 * sqrt(k) on N(0,1) data (as the small-shape tests)."""
+    f64 = dtype is np.float64
+    a = u.MatD.randn(n, n, seed=31 + n) if f64 else u.MatF.randn(n, n, seed=31 + n)
+    b = u.MatD.randn(n, n, seed=77 + n) if f64 else u.MatF.randn(n, n, seed=77 + n)
+    c = a @ b
+    ha, hb, hc = a.to_numpy(), b.to_numpy(), c.to_numpy()
+    assert hc.dtype == dtype and hc.shape == (n, n)
+    rows = np.array([0, 1, 127, 128, 129, n // 2 - 1, n // 2, n - 129, n - 2, n - 1])
+    cols = np.array([0, 5, 127, 128, n // 3, n - 128, n - 1])
+    want_r = ha[rows].astype(np.float64) @ hb.astype(np.float64)
+    want_c = ha.astype(np.float64) @ hb[:, cols].astype(np.float64)
+    if f64:
+        tol = dict(rtol=1e-9, atol=1e-12 * n)
+        np.testing.assert_allclose(hc[rows], want_r, **tol)
+        np.testing.assert_allclose(hc[:, cols], want_c, **tol)
+        # a transposed left operand is read in place (mmfnv / tmmfnv operands): (a.T).T-free check against the same rows
+        ct = (a.T @ b).to_numpy()
+        np.testing.assert_allclose(ct[rows], ha[:, rows].T @ hb, **tol)
+    else:
+        bound_r = n * 2.0 ** -24 * (np.abs(ha[rows]).astype(np.float64) @ np.abs(hb).astype(np.float64))
+        assert np.all(np.abs(hc[rows] - want_r) <= bound_r)
+        assert np.max(np.abs(hc[rows] - want_r)) <= 6e-6 * np.sqrt(n)
+        assert np.max(np.abs(hc[:, cols] - want_c)) <= 6e-6 * np.sqrt(n)
+
+
+def test_config2_ops_at_32768_squared(u):
+    """BASELINE config 2 at full size (32768 x 32768 FP64, 8 GiB): every op of the config is checked against a second
+    method on sampled lanes -- NumPy on the lanes copied back -- and through size-independent identities."""
+    n = 32768
+    m = u.MatD.randn(n, n, seed=2024)
+    lanes = [0, 1, 63, 64, 4095, n // 2 + 3, n - 2, n - 1]
+    cols = {j: m.slice(0, n, j, j + 1).to_numpy().ravel() for j in lanes}
+    rows = {i: m.slice(i, i + 1, 0, n).to_numpy().ravel() for i in lanes}
+    s0, s1 = m.sum(0).to_numpy().ravel(), m.sum(1).to_numpy().ravel()
+    mean0, mean1 = m.mean(0), m.mean(1)
+    v0, v1 = m.var(0).to_numpy().ravel(), m.var(1).to_numpy().ravel()
+    sd0 = m.std(0).to_numpy().ravel()
+    for j in lanes:
+        c, r = cols[j], rows[j]
+        assert abs(s0[j] - math.fsum(c)) <= 1e-12 * np.abs(c).sum() and abs(s1[j] - math.fsum(r)) <= 1e-12 * np.abs(r).sum()
+        np.testing.assert_allclose(v0[j], c.var(), rtol=1e-12)
+        np.testing.assert_allclose(v1[j], r.var(), rtol=1e-12)
+        np.testing.assert_allclose(sd0[j], c.std(), rtol=1e-12)
+    # a sum of the axis sums is the whole-matrix sum either way (a checksum of checksums)
+    tot = m.sum()
+    scale = 1e-12 * n * n
+    assert abs(math.fsum(s0) - tot) <= scale and abs(math.fsum(s1) - tot) <= scale
+    np.testing.assert_allclose(mean0.to_numpy().ravel(), s0 / n, rtol=1e-15)
+    # m - m.mean(0): the centred matrix has column sums ~ 0 and the sampled lanes equal NumPy's bit for bit
+    cen = m - mean0
+    mu0 = mean0.to_numpy().ravel()
+    for j in lanes:
+        assert np.array_equal(cen.slice(0, n, j, j + 1).to_numpy().ravel(), cols[j] - mu0[j])
+    assert np.max(np.abs(cen.sum(0).to_numpy())) <= 1e-12 * n * 8
+    del cen
+    cen1 = m - mean1
+    mu1 = mean1.to_numpy().ravel()
+    for i in lanes:
+        assert np.array_equal(cen1.slice(i, i + 1, 0, n).to_numpy().ravel(), rows[i] - mu1[i])
+    del cen1
+    sg = m.sigmoid()
+    for i in lanes:
+        np.testing.assert_allclose(sg.slice(i, i + 1, 0, n).to_numpy().ravel(), 1.0 / (1.0 + np.exp(-rows[i])), rtol=1e-12)
+    del sg
+    for ax, lanes_of in ((0, cols), (1, rows)):
+        sm = m.softmax(ax)
+        for j in lanes:
+            x = lanes_of[j]
+            got = (sm.slice(0, n, j, j + 1) if ax == 0 else sm.slice(j, j + 1, 0, n)).to_numpy().ravel()
+            e = np.exp(x - x.max())
+            np.testing.assert_allclose(got, e / e.sum(), rtol=1e-12, atol=0)
+        # every lane of a softmax sums to one
+        lane_sums = sm.sum(ax).to_numpy().ravel()
+        assert np.max(np.abs(lane_sums - 1.0)) <= 1e-12
+        del sm

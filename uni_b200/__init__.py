@@ -5,7 +5,7 @@ include/unimat.h).  Importing this package loads that library and fails if it is
 """
 from . import _lib
 from ._lib import (EmptyMatrixError, SingularMatrixError, UnimatError, device_count, launch_count)
-from .mat import Mat, MatD, MatF, init, set_matf_matmul_path, sync
+from .mat import Mat, MatD, MatF, init, set_matd_matmul_tile, set_matf_matmul_path, set_softmax_axis0_path, sync
 from . import tprf3
 from . import rng
 from . import io
@@ -13,6 +13,6 @@ from .io import MatResult, loadMatD, loadMatF, loadSmartD, saveCSV
 from .rng import NumPyRNG
 from .tprf3 import Pls3prfModel, Tprf3Result, estimate3prf, forecast3prf, pls1Fit, plsClosedForm, t3prf, tprfClosedForm
 
-__all__ = ["Mat", "MatD", "MatF", "init", "sync", "set_matf_matmul_path", "tprf3", "Tprf3Result", "estimate3prf", "forecast3prf",
+__all__ = ["Mat", "MatD", "MatF", "init", "sync", "set_matf_matmul_path", "set_matd_matmul_tile", "set_softmax_axis0_path", "tprf3", "Tprf3Result", "estimate3prf", "forecast3prf",
            "t3prf", "tprfClosedForm", "plsClosedForm", "pls1Fit", "Pls3prfModel", "NumPyRNG", "rng", "io", "MatResult", "loadMatD", "loadMatF", "loadSmartD", "saveCSV", "device_count", "launch_count", "EmptyMatrixError",
            "SingularMatrixError", "UnimatError"]

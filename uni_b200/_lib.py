@@ -134,6 +134,7 @@ SIGNATURES = {
     "um_binary_scalar": (_i32, [_i32, VP, _f64, _i32, VP]),
     "um_unary": (_i32, [_i32, VP, VP]),
     "um_softmax": (_i32, [VP, _i32, VP]),
+    "um_softmax_set_axis0_path": (_i32, [_i32]),
     "um_compare_scalar": (_i32, [_i32, VP, _f64, VP]),
     "um_compare": (_i32, [_i32, VP, VP, VP]),
     "um_classify": (_i32, [_i32, VP, VP]),
@@ -150,6 +151,7 @@ SIGNATURES = {
     "um_idx_axis": (_i32, [_i32, VP, _i32, VP]),
     "um_matmul": (_i32, [VP, VP, VP]),
     "um_matmul_set_f32_path": (_i32, [_i32]),
+    "um_matmul_set_f64_tile": (_i32, [_i32]),
     "um_inverse": (_i32, [VP, VP]),
     "um_solve": (_i32, [VP, VP, VP]),
     "um_inverse_batched": (_i32, [VP, _i64, VP, _i64, _i64]),

@@ -12,15 +12,24 @@
 // FP32: register-tiled FFMA kernel (float accumulate, as multiplyFloat Mat.scala:3236-3268).
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace um {
 
-constexpr int MM_BM = 128, MM_BN = 128, MM_BK = 16, MM_STAGES = 3, MM_THREADS = 256;
+// Two CTA tiles: 128 x 128 (one CTA per SM) and 64 x 64 (warp tile 32 x 16, two CTAs per SM).  DMMA is slow enough
+// (16 FMA per clock per sub-partition) that the small tile loses nothing in the inner loop; it exists because a
+// 1024^2 product is only 64 large tiles on 148 SMs and a 2048^2 one is 1.73 waves of them (launch_dgemm picks).
+constexpr int MM_BK = 16, MM_STAGES = 3, MM_THREADS = 256;
 constexpr int MM_PK = MM_BK + 4;     // pitch when the k dimension is contiguous (20 doubles)
-constexpr int MM_PMN = MM_BM + 4;    // pitch when the m/n dimension is contiguous (132 doubles)
-constexpr int MM_TILE_ELEMS = MM_BM * MM_PK;  // 2560 >= 16 * 132 = 2112: one operand stage
-constexpr int MM_SMEM_BYTES = MM_STAGES * 2 * MM_TILE_ELEMS * 8;  // 122880
+template <int TILE> struct MMShape {
+  static constexpr int PMN = TILE + 4;                 // pitch when the m/n dimension is contiguous (132 / 68 doubles)
+  static constexpr int TILE_ELEMS = TILE * MM_PK;      // 2560 >= 16 * 132, 1280 >= 16 * 68: one operand stage
+  static constexpr int SMEM_BYTES = MM_STAGES * 2 * TILE_ELEMS * 8;  // 122880 / 61440
+  static constexpr int MI = TILE / 16, NJ = TILE / 32; // DMMA tiles per warp (2 x 4 warps)
+};
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -43,12 +52,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // Stage one operand tile.  The operand is a (outer x inner) box where `inner` is the
 // memory-contiguous dimension: KMAJOR -> outer = m (or n), inner = k (box 128 x 16, pitch 20);
 // otherwise outer = k, inner = m (or n) (box 16 x 128, pitch 132).  g(o, i) = p[o*ld + i].
-template <bool KMAJOR, bool VEC16>
+template <int TILE, bool KMAJOR, bool VEC16>
 __device__ __forceinline__ void stage_tile(double* sm, const double* __restrict__ p, i64 ld, i64 o0, i64 i0,
                                            i64 o_lim, i64 i_lim, int tid) {
-  constexpr int OUTER = KMAJOR ? MM_BM : MM_BK;
-  constexpr int INNER = KMAJOR ? MM_BK : MM_BM;
-  constexpr int PITCH = KMAJOR ? MM_PK : MM_PMN;
+  constexpr int OUTER = KMAJOR ? TILE : MM_BK;
+  constexpr int INNER = KMAJOR ? MM_BK : TILE;
+  constexpr int PITCH = KMAJOR ? MM_PK : MMShape<TILE>::PMN;
   constexpr int CH = VEC16 ? 2 : 1;               // doubles per cp.async
   constexpr int CPR = INNER / CH;                 // chunks per box row
   constexpr int TOTAL = OUTER * CPR;
@@ -67,31 +76,33 @@ __device__ __forceinline__ void stage_tile(double* sm, const double* __restrict_
 
 // C[m][n] = sum_k A(m,k) B(k,n).  A(m,k) = pa[m*a_rs + k*a_cs] with one of the strides == 1,
 // same for B.  AK: A is k-contiguous (a_cs == 1); BK_: B is k-contiguous (b_rs == 1).
-template <bool AK, bool BKM, bool VEC16>
-__global__ void __launch_bounds__(MM_THREADS, 1)
+template <int TILE, bool AK, bool BKM, bool VEC16>
+__global__ void __launch_bounds__(MM_THREADS, TILE == 128 ? 1 : 2)
 k_dgemm(const double* __restrict__ pa, i64 lda, const double* __restrict__ pb, i64 ldb, double* __restrict__ pc, i64 ldc,
         i64 M, i64 N, i64 K) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
-  const i64 m0 = (i64)blockIdx.y * MM_BM, n0 = (i64)blockIdx.x * MM_BN;
+  using S = MMShape<TILE>;
+  constexpr int MM_PMN = S::PMN, MM_TILE_ELEMS = S::TILE_ELEMS, MI = S::MI, NJ = S::NJ;
+  const i64 m0 = (i64)blockIdx.y * TILE, n0 = (i64)blockIdx.x * TILE;
   const int KT = (int)((K + MM_BK - 1) / MM_BK);
 
   auto stage = [&](int s, int kt) {
     double* sa = smem + (size_t)s * 2 * MM_TILE_ELEMS;
     double* sb = sa + MM_TILE_ELEMS;
     const i64 k0 = (i64)kt * MM_BK;
-    if (AK) stage_tile<true, VEC16>(sa, pa, lda, m0, k0, M, K, tid);     // outer m, inner k
-    else stage_tile<false, VEC16>(sa, pa, lda, k0, m0, K, M, tid);       // outer k, inner m
-    if (BKM) stage_tile<true, VEC16>(sb, pb, ldb, n0, k0, N, K, tid);    // outer n, inner k
-    else stage_tile<false, VEC16>(sb, pb, ldb, k0, n0, K, N, tid);       // outer k, inner n
+    if (AK) stage_tile<TILE, true, VEC16>(sa, pa, lda, m0, k0, M, K, tid);     // outer m, inner k
+    else stage_tile<TILE, false, VEC16>(sa, pa, lda, k0, m0, K, M, tid);       // outer k, inner m
+    if (BKM) stage_tile<TILE, true, VEC16>(sb, pb, ldb, n0, k0, N, K, tid);    // outer n, inner k
+    else stage_tile<TILE, false, VEC16>(sb, pb, ldb, k0, n0, K, N, tid);       // outer k, inner n
   };
 
-  double acc[8][4][2];
+  double acc[MI][NJ][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
   for (int s = 0; s < MM_STAGES - 1; ++s) {
@@ -112,33 +123,33 @@ k_dgemm(const double* __restrict__ pa, i64 lda, const double* __restrict__ pb, i
     const double* sb = sa + MM_TILE_ELEMS;
 #pragma unroll
     for (int kk = 0; kk < MM_BK; kk += 4) {
-      double af[8], bf[4];
+      double af[MI], bf[NJ];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int m = wm * 64 + i * 8 + fr;
+      for (int i = 0; i < MI; ++i) {
+        int m = wm * (TILE / 2) + i * 8 + fr;
         af[i] = AK ? sa[m * MM_PK + kk + fk] : sa[(kk + fk) * MM_PMN + m];
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int n = wn * 32 + j * 8 + fr;
+      for (int j = 0; j < NJ; ++j) {
+        int n = wn * (TILE / 4) + j * 8 + fr;
         bf[j] = BKM ? sb[n * MM_PK + kk + fk] : sb[(kk + fk) * MM_PMN + n];
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
   }
   cp_async_wait<0>();
 
   // epilogue: lane holds C[row = fr][col = 2*fk, 2*fk+1] of each 8x8 tile
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    i64 m = m0 + wm * 64 + i * 8 + fr;
+  for (int i = 0; i < MI; ++i) {
+    i64 m = m0 + wm * (TILE / 2) + i * 8 + fr;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      i64 n = n0 + wn * 32 + j * 8 + 2 * fk;
+    for (int j = 0; j < NJ; ++j) {
+      i64 n = n0 + wn * (TILE / 4) + j * 8 + 2 * fk;
       double* dst = pc + m * ldc + n;
       if (n + 1 < N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
         *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
@@ -241,28 +252,44 @@ k_sgemm(In<float> a, In<float> b, float* __restrict__ pc, i64 ldc, i64 M, i64 N,
   }
 }
 
+static std::atomic<int> g_f64_tile{0};   // um_matmul_set_f64_tile: 0 = automatic, 64 / 128 forced (tests, profiling)
+
+template <int TILE, bool AK, bool BKM, bool VEC16>
+static int launch_dgemm_tile(const double* pa, i64 lda, const double* pb, i64 ldb, double* pc, i64 ldc, i64 M, i64 N, i64 K) {
+  dim3 grid((unsigned)((N + TILE - 1) / TILE), (unsigned)((M + TILE - 1) / TILE));
+  static std::once_flag once;   // one device per process (um_init)
+  cudaError_t attr = cudaSuccess;
+  std::call_once(once, [&] {
+    attr = cudaFuncSetAttribute(k_dgemm<TILE, AK, BKM, VEC16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MMShape<TILE>::SMEM_BYTES);
+  });
+  UM_CUDA(attr);
+  k_dgemm<TILE, AK, BKM, VEC16><<<grid, MM_THREADS, MMShape<TILE>::SMEM_BYTES, ctx()->stream>>>(pa, lda, pb, ldb, pc, ldc, M, N, K);
+  UM_LAUNCHED();
+  return UM_OK;
+}
+
+// Tile choice: time ~ waves x work per tile.  128 x 128 tiles run one per SM; 64 x 64 tiles run two per SM sharing
+// its FP64 pipe, i.e. a quarter of the work each at (about) the same per-SM rate, with a few per cent more L2 traffic
+// and prologue per flop.  The small tile wins whenever the large one leaves SMs idle or its last wave mostly empty.
+static int pick_dgemm_tile(i64 M, i64 N) {
+  const int forced = g_f64_tile.load();
+  if (forced == 64 || forced == 128) return forced;
+  const i64 sms = ctx()->sm_count > 0 ? ctx()->sm_count : 148;
+  const i64 t128 = ((M + 127) / 128) * ((N + 127) / 128), t64 = ((M + 63) / 64) * ((N + 63) / 64);
+  const double c128 = 4.0 * (double)((t128 + sms - 1) / sms);
+  const double c64 = 1.06 * (double)((t64 + sms - 1) / sms);
+  return c64 < c128 ? 64 : 128;
+}
+
 template <bool AK, bool BKM>
 static int launch_dgemm(const double* pa, i64 lda, const double* pb, i64 ldb, double* pc, i64 ldc, i64 M, i64 N, i64 K,
                         bool vec16) {
-  dim3 grid((unsigned)((N + MM_BN - 1) / MM_BN), (unsigned)((M + MM_BM - 1) / MM_BM));
-  cudaStream_t st = ctx()->stream;
-  if (vec16) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      UM_CUDA(cudaFuncSetAttribute(k_dgemm<AK, BKM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
-      attr_done = true;
-    }
-    k_dgemm<AK, BKM, true><<<grid, MM_THREADS, MM_SMEM_BYTES, st>>>(pa, lda, pb, ldb, pc, ldc, M, N, K);
-  } else {
-    static bool attr_done = false;
-    if (!attr_done) {
-      UM_CUDA(cudaFuncSetAttribute(k_dgemm<AK, BKM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
-      attr_done = true;
-    }
-    k_dgemm<AK, BKM, false><<<grid, MM_THREADS, MM_SMEM_BYTES, st>>>(pa, lda, pb, ldb, pc, ldc, M, N, K);
+  if (pick_dgemm_tile(M, N) == 64) {
+    if (vec16) return launch_dgemm_tile<64, AK, BKM, true>(pa, lda, pb, ldb, pc, ldc, M, N, K);
+    return launch_dgemm_tile<64, AK, BKM, false>(pa, lda, pb, ldb, pc, ldc, M, N, K);
   }
-  UM_LAUNCHED();
-  return UM_OK;
+  if (vec16) return launch_dgemm_tile<128, AK, BKM, true>(pa, lda, pb, ldb, pc, ldc, M, N, K);
+  return launch_dgemm_tile<128, AK, BKM, false>(pa, lda, pb, ldb, pc, ldc, M, N, K);
 }
 
 }  // namespace um
@@ -276,6 +303,12 @@ static int g_f32_path = 0;   // um_matmul_set_f32_path
 extern "C" int32_t um_matmul_set_f32_path(int32_t path) {
   if (path < 0 || path > 2) return um::fail(UM_ERR_ARG, "um_matmul_set_f32_path: 0 auto, 1 CUDA cores, 2 tensor cores");
   g_f32_path = path;
+  return UM_OK;
+}
+
+extern "C" int32_t um_matmul_set_f64_tile(int32_t tile) {
+  if (tile != 0 && tile != 64 && tile != 128) return um::fail(UM_ERR_ARG, "um_matmul_set_f64_tile: 0 (automatic), 64 or 128");
+  um::g_f64_tile.store(tile);
   return UM_OK;
 }
 

@@ -589,7 +589,9 @@ struct SoftKP {
   __device__ static Acc finish(const Local& l, double k, double n) {
     if (n == 0.0) return Acc{-INFINITY, 0.0};
     double d = l.mx - k;
-    if (!(d <= 600.0) && !(l.s != l.s && d == d)) return Acc{0.0, -1.0};  // overflow risk (not a plain NaN lane)
+    // |d| > 600: exp(x - k) may have overflowed (d >> 0) or the whole chunk underflowed to s = 0 against a huge k
+    // (d << 0: 0 * exp(k - mx) = 0 * Inf would poison the merge) -- not a plain NaN lane: redo it with the online form
+    if (!(d <= 600.0 && d >= -600.0) && !(l.s != l.s && d == d)) return Acc{0.0, -1.0};
     if (!(fabs(k) <= 1.7e308)) return Acc{0.0, -1.0};
     return Acc{l.mx, l.s * fast_exp(k - l.mx)};   // re-base on the local max
   }
@@ -1061,6 +1063,13 @@ static int softmax_contig(const T* p, i64 s_lane, i64 n_lane, i64 n_red, double*
   return UM_OK;
 }
 
+}  // namespace um
+#include "softmax_strip.cuh"
+namespace um {
+// softmax over strided lanes (axis 0 of a row-major matrix): 0 = automatic (the single-read strip kernel for large
+// FP64 matrices it fits, the two-read kernels otherwise), 1 = two-read only, 2 = strip kernel or UM_ERR_ARG
+static std::atomic<int> g_softmax0_path{0};
+
 template <class T>
 static int softmax_typed(const um_view* a, int axis, const um_view* out) {
   Plan pl = plan_axis<T>(a, axis);
@@ -1074,6 +1083,18 @@ static int softmax_typed(const um_view* a, int axis, const um_view* out) {
                aligned16(o) && (pl.n_lane == 1 || o_lane % VW == 0);
     return vec ? softmax_contig<T, VW>(p, pl.s_lane, pl.n_lane, pl.n_red, o, o_lane)
                : softmax_contig<T, 1>(p, pl.s_lane, pl.n_lane, pl.n_red, o, o_lane);
+  }
+  if (sizeof(T) == 8 && pl.mode == 1 && pl.s_lane == 1 && o_lane == 1) {
+    const int path = g_softmax0_path.load();
+    // automatic: the matrix must be large enough to be HBM-bound (the two-read kernels re-read from L2 below that)
+    const bool want = path == 2 || (path == 0 && pl.n_red >= 512 && pl.n_lane >= 1024 && pl.n_red * pl.n_lane >= (i64(1) << 23));
+    if (want) {
+      const int rc = sms::launch(reinterpret_cast<const double*>(p), pl.s_red, pl.n_red, pl.n_lane, o, o_red);
+      if (rc != -1) return rc;
+    }
+    if (path == 2) return fail(UM_ERR_ARG, "softmax: operands do not fit the single-read strip kernel (FP64, row-major, even columns and pitches, 16-byte aligned, <= 32768 rows)");
+  } else if (g_softmax0_path.load() == 2 && axis == 0) {
+    return fail(UM_ERR_ARG, "softmax: operands do not fit the single-read strip kernel (FP64 row-major input and output)");
   }
   // two-pass: online (max, sum) per lane, then normalise
   SoftP::Acc* part = nullptr;
@@ -1220,6 +1241,17 @@ int32_t um_mask_reduce(int32_t want_all, const um_view* a, int32_t axis, const u
 }
 
 }  // extern "C"
+
+extern "C" int32_t um_dbg_softmax_stamps(long long* host_out) {   // DEBUG
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host_out, sms::g_stamps, sizeof(long long) * 4 * 256) == cudaSuccess ? 0 : 5;
+}
+
+extern "C" int32_t um_softmax_set_axis0_path(int32_t path) {
+  if (path < 0 || path > 2) return fail(UM_ERR_ARG, "um_softmax_set_axis0_path: 0 (automatic), 1 (two-read kernels), 2 (single-read strip kernel)");
+  g_softmax0_path.store(path);
+  return UM_OK;
+}
 
 extern "C" int32_t um_softmax(const um_view* a, int32_t axis, const um_view* out) {
   UM_CTX();

@@ -645,6 +645,17 @@ def set_matf_matmul_path(path: int) -> None:
     check(lib.um_matmul_set_f32_path(int(path)))
 
 
+def set_softmax_axis0_path(path: int) -> None:
+    """softmax(0) kernel choice (um_softmax_set_axis0_path): 0 = automatic, 1 = two-read kernels, 2 = single-read strip
+    kernel or ValueError."""
+    check(lib.um_softmax_set_axis0_path(int(path)))
+
+
+def set_matd_matmul_tile(tile: int) -> None:
+    """FP64 `@` CTA tile (um_matmul_set_f64_tile): 0 = automatic, 64 or 128 forced (tests, profiling)."""
+    check(lib.um_matmul_set_f64_tile(int(tile)))
+
+
 def init(device: int = 0) -> None:
     check(lib.um_init(device))
 
