@@ -416,7 +416,9 @@ def matd_ops(u, peak_gbs, n=32768):
     rec("relu", lambda: m.relu(), 16 * E)
     rec("sigmoid", lambda: m.sigmoid(), 16 * E)
     rec("softmax_axis1", lambda: m.softmax(1), 16 * E, "single read: lane held in registers across a 4-CTA cluster")
-    rec("softmax_axis0", lambda: m.softmax(0), 16 * E, "two-read implementation (24E bytes moved)")
+    rec("softmax_axis0", lambda: m.softmax(0), 16 * E,
+        "single read for 85 % of the columns: 16-column strips held in tensor memory across 16-CTA clusters (softmax_strip.cuh); "
+        "the other 15 % run through the two-read kernels at the same time on the SMs and issue slots the clusters leave idle")
     rec("sum_axis0", lambda: m.sum(0), 8 * E)
     rec("sum_axis1", lambda: m.sum(1), 8 * E)
     rec("mean_axis0", lambda: m.mean(0), 8 * E)

@@ -8,7 +8,7 @@ from uni_b200._lib import lib, check
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 u.init(0)
 m = u.MatD.randn(n, n, seed=42)
-for ax, path, name in ((0, 1, "two-read"), (0, 2, "strip"), (1, 0, "row on chip")):
+for ax, path, name in ((0, 1, "two-read"), (0, 2, "strip"), (0, 0, "auto: strip + two-read split"), (1, 0, "row on chip")):
     u.set_softmax_axis0_path(path)
     for _ in range(3):
         r = m.softmax(ax)

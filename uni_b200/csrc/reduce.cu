@@ -1069,34 +1069,12 @@ namespace um {
 // softmax over strided lanes (axis 0 of a row-major matrix): 0 = automatic (the single-read strip kernel for large
 // FP64 matrices it fits, the two-read kernels otherwise), 1 = two-read only, 2 = strip kernel or UM_ERR_ARG
 static std::atomic<int> g_softmax0_path{0};
+// share of the columns the automatic path hands to the two-read kernels next to the strip kernel (UM_SMS_SPLIT overrides)
+static const double g_softmax0_split = [] { const char* e = getenv("UM_SMS_SPLIT"); return e ? atof(e) : 0.15; }();
 
+// two-read softmax over strided (or generic) lanes: online (max, sum) per lane, then normalise
 template <class T>
-static int softmax_typed(const um_view* a, int axis, const um_view* out) {
-  Plan pl = plan_axis<T>(a, axis);
-  const T* p = static_cast<const T*>(pl.p);
-  double* o = static_cast<double*>(out->data) + out->offset;
-  const i64 o_lane = axis == 0 ? out->cs : out->rs;
-  const i64 o_red = axis == 0 ? out->rs : out->cs;
-  if (pl.mode == 0 && (o_red == 1 || pl.n_red == 1)) {
-    constexpr int VW = 16 / sizeof(double);  // output vectors are double2
-    bool vec = (reinterpret_cast<uintptr_t>(p) % (sizeof(T) * VW) == 0) && (pl.n_lane == 1 || pl.s_lane % VW == 0) &&
-               aligned16(o) && (pl.n_lane == 1 || o_lane % VW == 0);
-    return vec ? softmax_contig<T, VW>(p, pl.s_lane, pl.n_lane, pl.n_red, o, o_lane)
-               : softmax_contig<T, 1>(p, pl.s_lane, pl.n_lane, pl.n_red, o, o_lane);
-  }
-  if (sizeof(T) == 8 && pl.mode == 1 && pl.s_lane == 1 && o_lane == 1) {
-    const int path = g_softmax0_path.load();
-    // automatic: the matrix must be large enough to be HBM-bound (the two-read kernels re-read from L2 below that)
-    const bool want = path == 2 || (path == 0 && pl.n_red >= 512 && pl.n_lane >= 1024 && pl.n_red * pl.n_lane >= (i64(1) << 23));
-    if (want) {
-      const int rc = sms::launch(reinterpret_cast<const double*>(p), pl.s_red, pl.n_red, pl.n_lane, o, o_red);
-      if (rc != -1) return rc;
-    }
-    if (path == 2) return fail(UM_ERR_ARG, "softmax: operands do not fit the single-read strip kernel (FP64, row-major, even columns and pitches, 16-byte aligned, <= 32768 rows)");
-  } else if (g_softmax0_path.load() == 2 && axis == 0) {
-    return fail(UM_ERR_ARG, "softmax: operands do not fit the single-read strip kernel (FP64 row-major input and output)");
-  }
-  // two-pass: online (max, sum) per lane, then normalise
+static int softmax_two_read(const Plan& pl, const T* p, double* o, i64 o_lane, i64 o_red) {
   SoftP::Acc* part = nullptr;
   int chunks = 0;
   // two extra lanes' worth of Acc slots hold the per-lane (m, 1/s) vectors of the vectorised pass
@@ -1129,6 +1107,63 @@ static int softmax_typed(const um_view* a, int axis, const um_view* out) {
   k_softmax_norm<T><<<grid, block, 0, ctx()->stream>>>(p, pl.s_lane, pl.s_red, pl.n_lane, pl.n_red, part, chunks, o, o_lane, o_red);
   UM_LAUNCHED();
   return UM_OK;
+}
+
+template <class T>
+static int softmax_typed(const um_view* a, int axis, const um_view* out) {
+  Plan pl = plan_axis<T>(a, axis);
+  const T* p = static_cast<const T*>(pl.p);
+  double* o = static_cast<double*>(out->data) + out->offset;
+  const i64 o_lane = axis == 0 ? out->cs : out->rs;
+  const i64 o_red = axis == 0 ? out->rs : out->cs;
+  if (pl.mode == 0 && (o_red == 1 || pl.n_red == 1)) {
+    constexpr int VW = 16 / sizeof(double);  // output vectors are double2
+    bool vec = (reinterpret_cast<uintptr_t>(p) % (sizeof(T) * VW) == 0) && (pl.n_lane == 1 || pl.s_lane % VW == 0) &&
+               aligned16(o) && (pl.n_lane == 1 || o_lane % VW == 0);
+    return vec ? softmax_contig<T, VW>(p, pl.s_lane, pl.n_lane, pl.n_red, o, o_lane)
+               : softmax_contig<T, 1>(p, pl.s_lane, pl.n_lane, pl.n_red, o, o_lane);
+  }
+  if (sizeof(T) == 8 && pl.mode == 1 && pl.s_lane == 1 && o_lane == 1) {
+    const int path = g_softmax0_path.load();
+    // automatic: the matrix must be large enough to be HBM-bound (the two-read kernels re-read from L2 below that)
+    const bool want = path == 2 || (path == 0 && pl.n_red >= 512 && pl.n_lane >= 1024 && pl.n_red * pl.n_lane >= (i64(1) << 23));
+    if (want) {
+      // Split: the 16-CTA clusters of the strip kernel reach 112 of the 148 SMs and leave half of the FP64 issue slots
+      // of those unused, so (automatic path, wide matrices) the last columns go to the two-read kernels on a second
+      // stream at the same time; they fill the idle SMs and the gaps.  The strip kernel is launched first.
+      i64 n2 = 0;
+      if (path == 0 && pl.n_lane >= 8192 && g_softmax0_split > 0.0) n2 = (i64)((double)pl.n_lane * g_softmax0_split) / 16 * 16;
+      const i64 n1 = pl.n_lane - n2;
+      static thread_local cudaStream_t st2 = nullptr;
+      static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+      if (n2 > 0 && !st2) {
+        UM_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+        UM_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        UM_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+      }
+      if (n2 > 0) UM_CUDA(cudaEventRecord(ev_fork, ctx()->stream));
+      const int rc = sms::launch(reinterpret_cast<const double*>(p), pl.s_red, pl.n_red, n1, o, o_red);
+      if (rc != -1) {
+        if (rc != UM_OK || n2 == 0) return rc;
+        Plan pr = pl;
+        pr.p = p + n1;
+        pr.n_lane = n2;
+        cudaStream_t main_st = ctx()->stream;
+        UM_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
+        ctx()->stream = st2;
+        const int rc2 = softmax_two_read<T>(pr, p + n1, o + n1, o_lane, o_red);
+        ctx()->stream = main_st;
+        if (rc2 != UM_OK) return rc2;
+        UM_CUDA(cudaEventRecord(ev_join, st2));
+        UM_CUDA(cudaStreamWaitEvent(main_st, ev_join, 0));
+        return UM_OK;
+      }
+    }
+    if (path == 2) return fail(UM_ERR_ARG, "softmax: operands do not fit the single-read strip kernel (FP64, row-major, even columns and pitches, 16-byte aligned, <= 32768 rows)");
+  } else if (g_softmax0_path.load() == 2 && axis == 0) {
+    return fail(UM_ERR_ARG, "softmax: operands do not fit the single-read strip kernel (FP64 row-major input and output)");
+  }
+  return softmax_two_read<T>(pl, p, o, o_lane, o_red);
 }
 
 }  // namespace um
@@ -1241,11 +1276,6 @@ int32_t um_mask_reduce(int32_t want_all, const um_view* a, int32_t axis, const u
 }
 
 }  // extern "C"
-
-extern "C" int32_t um_dbg_softmax_stamps(long long* host_out) {   // DEBUG
-  cudaDeviceSynchronize();
-  return cudaMemcpyFromSymbol(host_out, sms::g_stamps, sizeof(long long) * 4 * 256) == cudaSuccess ? 0 : 5;
-}
 
 extern "C" int32_t um_softmax_set_axis0_path(int32_t path) {
   if (path < 0 || path > 2) return fail(UM_ERR_ARG, "um_softmax_set_axis0_path: 0 (automatic), 1 (two-read kernels), 2 (single-read strip kernel)");

@@ -7,21 +7,20 @@
 // owns rows [rank * R, rank * R + R), R <= 2048, and its 2048 x 16 doubles = 256 KB fill the SM's TENSOR MEMORY
 // exactly (tcgen05.st / tcgen05.ld, a double as two 32-bit columns; shared memory is only the TMA landing ring).
 //
-//   phase A  the strip streams in through a ring of 8 TMA boxes (128 rows x 16 columns); the 8 compute warps form
+//   phase A  the strip streams in through a ring of 8 TMA boxes (128 rows x 16 columns); the 16 compute warps form
 //            e = exp(x - k) (k = row 0 of the column, the same shift on every CTA: the sums add up without a
-//            re-base), keep sum e / max x / min x per column and park e in tensor memory;
+//            re-base), keep sum e per column and the range of x - k, and park e in tensor memory;
 //   exchange CTA partials -> every CTA of the cluster through distributed shared memory, ONE cluster barrier per strip
-//            (double-buffered slots), rank-order sums: S = sum e, and the range of the column;
+//            (double-buffered slots), rank-order sums: S = sum e, and whether anyone saw an out-of-range element;
 //   phase B  out = e * (1 / S) straight from tensor memory to HBM (16-byte stores, full 128-byte row segments), while
 //            the TMA producer already fills the ring with the next strip.
 //
 // exp(x - k) / sum exp(x - k) is the reference's exp(x - max) / sum exp(x - max) with the common factor exp(max - k)
 // cancelled.  That is exact arithmetic as long as nothing leaves the normal range, so a strip is only finished this
-// way when every column has max - k <= 300 and k - min <= 300 (every e within e^+-300, every quotient normal).  Any
-// other column -- a spread beyond that, +-Inf anywhere, a non-finite k -- sends its strip down the reference's own
-// arithmetic: the exact max is known from the exchange, so the cluster re-reads the strip from global memory twice
-// (sum exp(x - max), then exp(x - max) / sum).  NaN needs no special case: it poisons S and with it the whole lane,
-// which is what the reference returns.
+// way when every element has -690 <= x - k <= 300 (every e a normal number, the sum far from overflow).  Anything else
+// -- a wider spread, NaN, +-Inf, a non-finite k -- sends its strip down the reference's own arithmetic: the cluster
+// re-reads the strip from global memory three times (max, sum exp(x - max), exp(x - max) / sum).  The range test
+// runs on the integer pipe, on the high word of x - k.
 #pragma once
 #include <cuda.h>
 
@@ -173,8 +172,6 @@ __device__ __forceinline__ void st_global_v2(double* p, double a, double b) {
   asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 
-__device__ long long g_stamps[4 * 256];   // DEBUG: globaltimer stamps of cluster 0 / rank 0
-__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 // exp(d) in 12 FP64 instructions and without a branch: d = (32 q + j) ln2/32 + r, |r| <= ln2/64, 2^(j/32) from a
 // 32-entry table in shared memory, degree-6 Taylor for exp(r) (truncation 3.5e-18), 2^q into the exponent field.
@@ -229,7 +226,6 @@ struct Args {
   i64 T, N;
   int G, R;                     // cluster size, rows per CTA (multiple of PR)
   i64 nstrip;
-  int stagger_ns;               // start offset between consecutive clusters
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_softmax_strip(const __grid_constant__ CUtensorMap mx_map, const Args g) {
@@ -261,14 +257,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_softmax_strip(const __grid_cons
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   cluster_sync_all();   // every CTA's barriers and exchange buffers exist before anyone pushes into them
-  // All clusters start together and a strip takes everyone the same time, so left alone they stay in lockstep: every
-  // SM in the compute-bound phase A at once (HBM idle), then every SM writing at once (phase B at the HBM write limit).
-  // A one-off stagger of a fraction of the strip period per cluster spreads reads, exp and writes evenly over time.
-  if (nclusters > 1 && g.nstrip > 4 * nclusters) {
-    const long long wait_ns = (long long)g.stagger_ns * cluster_id;
-    const long long t0 = gtime();
-    while (gtime() - t0 < wait_ns) __nanosleep(200);
-  }
 
   if (warp == NCW) {
     // ---- TMA producer: one lane issues, the whole warp takes part in the CTA / cluster barriers ----
@@ -317,8 +305,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_softmax_strip(const __grid_cons
       double s0 = 0.0, s1 = 0.0;
       int hpos = (int)0x80000000;   // signed max of the high words of d
       unsigned hneg = 0u;           // unsigned max of the high words of d
-      const bool stamp = blockIdx.x == 0 && tid == 0 && strip_it < 256;
-      if (stamp) g_stamps[4 * strip_it] = gtime();
       // ---- phase A ----
       for (int p = 0; p < npiece; ++p, ++it) {
         const unsigned s = it % NSLOT, use = it / NSLOT;
@@ -356,7 +342,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_softmax_strip(const __grid_cons
         tmem_st8(tbase + (unsigned)p * (unsigned)TW, e);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      if (stamp) g_stamps[4 * strip_it + 1] = gtime();
       // ---- CTA partial: the rows of one column pair sit in the lanes with equal (lane & 7) ----
       s0 += __shfl_xor_sync(0xffffffffu, s0, 8); s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
       s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
@@ -372,19 +357,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_softmax_strip(const __grid_cons
           double a = sm.red[0][val][cc];
 #pragma unroll
           for (int w = 1; w < NCW; ++w) a += sm.red[w][val][cc];   // val 1: the number of warps that saw an odd element
-          for (int r = 0; r < G; ++r) st_cluster(&sm.exch[par][rank][val][cc], (unsigned)r, a);
+#pragma unroll
+          for (int r = 0; r < GMAX; ++r)
+            if (r < G) st_cluster(&sm.exch[par][rank][val][cc], (unsigned)r, a);
         }
       }
       cluster_sync_all();
       // every thread adds the ranks' partials of its own two columns, in rank order: bit-identical everywhere
       double S0 = 0.0, S1 = 0.0;
       bool slow = false;
-      for (int r = 0; r < G; ++r) {
-        const double2 ps = *reinterpret_cast<const double2*>(&sm.exch[par][r][0][2 * c2]);
-        S0 += ps.x; S1 += ps.y;
-        slow |= sm.exch[par][r][1][0] != 0.0;
-      }
-      if (stamp) g_stamps[4 * strip_it + 2] = gtime();
+#pragma unroll
+      for (int r = 0; r < GMAX; ++r)   // unrolled: the loads go out together, the adds keep their order
+        if (r < G) {
+          const double2 ps = *reinterpret_cast<const double2*>(&sm.exch[par][r][0][2 * c2]);
+          S0 += ps.x; S1 += ps.y;
+          slow |= sm.exch[par][r][1][0] != 0.0;
+        }
       if (!slow) {
         // ---- phase B ----
         const double c0 = 1.0 / S0, c1 = 1.0 / S1;
@@ -461,7 +449,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_softmax_strip(const __grid_cons
             st_global_v2(g.out + (row_lo + r) * g.ldo + col, exp(xv.x - M0) / d0, exp(xv.y - M1) / d1);
           }
       }
-      if (stamp) g_stamps[4 * strip_it + 3] = gtime();
     }
   }
   // nobody leaves while a peer may still push into its shared memory; then give the tensor memory back
@@ -534,11 +521,6 @@ static int launch(const double* x, i64 ldx, i64 T, i64 N, double* out, i64 ldo) 
   a.x = x; a.ldx = ldx; a.out = out; a.ldo = ldo; a.T = T; a.N = N; a.G = G; a.R = R;
   a.nstrip = (N + CW - 1) / CW;
   i64 nclusters = a.nstrip < ncl ? a.nstrip : ncl;
-  {
-    // a strip costs about 6 ns per row of a CTA's share (12 us at 2048 rows); spread the clusters over one period
-    static const int env = [] { const char* e = getenv("UM_SMS_STAGGER_NS"); return e ? atoi(e) : -1; }();
-    a.stagger_ns = env >= 0 ? env : (int)((6 * (i64)R) / (nclusters > 0 ? nclusters : 1));
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nclusters * G), 1, 1);
   cfg.blockDim = dim3(NTHREADS, 1, 1);
