@@ -31,8 +31,6 @@
 namespace um {
 
 int comm_allreduce_sum_f64_impl(double* buf, i64 count);  // comm.cu
-bool comm_can_gather(const double* buf, i64 count);        // comm.cu: the exchange is one peer-memory kernel that can gather its input
-int comm_allreduce_gather_f64(double* buf, i64 count, const GatherSrc& gs);
 int comm_check_error();                                     // comm.cu: did a bounded peer wait give up? (call after a sync)
 bool comm_active();
 int comm_world();
@@ -518,12 +516,6 @@ k_tprf_gather(const double* __restrict__ pxp, const double* __restrict__ h0p, in
 
 // ---- finish: one CTA per panel -----------------------------------------------------------------------------
 struct FinishArgs {
-  // nchunk > 0 (one panel, cluster launch): the kernel gathers the sweep's chunk partials itself -- same sums in the
-  // same order as k_tprf_gather, written to `packed_w` by the thread that reads them back -- instead of reading a
-  // packed buffer a separate gather (or the all-reduce) filled
-  const double* pxp; const double* h0p; int nchunk; i64 tpad;
-  const double* blockpart; int nblk;
-  double* packed_w;
   const double* packed; i64 packed_stride;
   const double* small;          // prep output (zbar | Szz | ybar | ssy), SMALL_PREP per panel
   const double* y; i64 y_s, y_bs;
@@ -593,44 +585,13 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
   const int L = g.L, L1 = g.L + 1;
   const double* px = g.packed + b * g.packed_stride;
   const double* h0 = px + T * LP;
-  const double* sm = h0 + T;  // sw[8] | SWW[64] | smw[8] | smu   (re-pointed at shared memory by the fused gather)
+  const double* sm = h0 + T;  // sw[8] | SWW[64] | smw[8] | smu
   const double* small = g.small + b * SMALL_PREP;
   const double* y = g.y + b * g.y_bs;
   double* par = g.params + b * PARAMS;
   double* fc = g.forecasts ? g.forecasts + b * g.f_bs : nullptr;
   double* rs = g.residuals ? g.residuals + b * g.f_bs : nullptr;
   double* sig_ws = g.sigma_ws + b * T * LP;
-  if (g.nchunk > 0) {
-    // gather, fused: this thread's rows of PX and h0 (every later loop maps rows to threads the same way, so each
-    // thread only ever reads back what it wrote itself) and, redundantly in every CTA, the 81 small sums
-    __shared__ double sm_s[NSMALL];
-    double* pw = g.packed_w + b * g.packed_stride;
-    for (i64 t = (i64)crank * 256 + tid; t < T; t += STRIDE) {
-      double acc[LP + 1];
-#pragma unroll
-      for (int l = 0; l <= LP; ++l) acc[l] = 0.0;
-      for (int c = 0; c < g.nchunk; ++c) {
-        const double2* src = reinterpret_cast<const double2*>(g.pxp + ((i64)c * g.tpad + t) * LP);
-#pragma unroll
-        for (int l = 0; l < LP / 2; ++l) {
-          const double2 v = src[l];
-          acc[2 * l] += v.x; acc[2 * l + 1] += v.y;
-        }
-        acc[LP] += g.h0p[(i64)c * g.tpad + t];
-      }
-#pragma unroll
-      for (int l = 0; l < LP; ++l) pw[t * LP + l] = acc[l];
-      pw[T * LP + t] = acc[LP];
-    }
-    if (tid < NSMALL) {
-      double a = 0.0;
-      for (int k = 0; k < g.nblk; ++k) a += g.blockpart[(i64)k * NSMALL + tid];
-      sm_s[tid] = a;
-      if (crank == 0) pw[T * (LP + 1) + tid] = a;
-    }
-    __syncthreads();
-    sm = sm_s;
-  }
   if (tid < LP) {
     sw[tid] = sm[tid];
     smw[tid] = sm[72 + tid];
@@ -1312,7 +1273,7 @@ static int run_fused(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_b
 
 // sweeps over one resident X block (T x N, row pitch ldx), writing / accumulating the packed buffer.
 // `ws` is the carved workspace; prep must already have run.
-static int run_sweeps(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_bs, int accumulate, bool gather = true) {
+static int run_sweeps(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_bs, int accumulate) {
   cudaStream_t st = ctx()->stream;
   double* zc = reinterpret_cast<double*>(ws + p.o_zc);
   double* qp = reinterpret_cast<double*>(ws + p.o_qp);
@@ -1361,7 +1322,7 @@ static int run_sweeps(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_
     UM_LAUNCHED();
   }
   }
-  if (gather) {
+  {
     i64 gx = cdiv(p.packed_len, 256);
     if (gx > 1024) gx = 1024;
     dim3 grid((unsigned)gx, 1, (unsigned)p.batch);
@@ -1400,18 +1361,8 @@ static int run_prep(const Plan3& p, char* ws, const double* Z, i64 z_rs, i64 z_c
 
 static int run_finish(const Plan3& p, char* ws, int mode, const double* y, i64 y_s, i64 y_bs, double n_total,
                       double* forecasts, double* residuals, i64 f_bs, double* sigma, double* beta3, double* r2_dev,
-                      bool want3 = false, bool gather_here = false) {
+                      bool want3 = false) {
   FinishArgs g;
-  g.nchunk = 0;
-  g.pxp = g.h0p = g.blockpart = nullptr; g.tpad = p.tpad; g.nblk = 0;
-  g.packed_w = reinterpret_cast<double*>(ws + p.o_packed);
-  if (gather_here) {
-    g.pxp = reinterpret_cast<double*>(ws + p.o_pxp);
-    g.h0p = reinterpret_cast<double*>(ws + p.o_h0p);
-    g.blockpart = reinterpret_cast<double*>(ws + p.o_bp);
-    g.nchunk = (int)p.cchunks;
-    g.nblk = p.cf_blocks;
-  }
   g.want3 = (mode == UM_TPRF_CLOSED && want3) ? 1 : 0;
   g.packed = reinterpret_cast<double*>(ws + p.o_packed);
   g.packed_stride = p.packed_len;
@@ -1554,29 +1505,16 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
   const double* zp = static_cast<const double*>(Z->data) + Z->offset;
   s = run_prep(p, ws, zp, Z->rs, Z->cs, 0, yp, y->rs, 0);
   if (s != UM_OK) return s;
-  // No separate gather launch on the fit's serial tail: on one rank the finish kernel sums the sweep's chunk partials
-  // itself; sharded, the peer-memory exchange kernel does (its pushes ARE the gather).  Only the NCCL transport needs
-  // the packed buffer formed first.
-  double* packed = reinterpret_cast<double*>(ws + p.o_packed);
-  const bool xgather = sharded && comm_can_gather(packed, p.packed_len);
-  s = run_sweeps(p, ws, xp, ldx, 0, 0, /*gather=*/sharded && !xgather);
+  s = run_sweeps(p, ws, xp, ldx, 0, 0);
   if (s != UM_OK) return s;
   if (sharded) {
     prof_begin(6);
-    if (xgather) {
-      GatherSrc gs;
-      gs.pxp = reinterpret_cast<double*>(ws + p.o_pxp); gs.h0p = reinterpret_cast<double*>(ws + p.o_h0p);
-      gs.blockpart = reinterpret_cast<double*>(ws + p.o_bp);
-      gs.T = p.T; gs.tpad = p.tpad; gs.nchunk = (int)p.cchunks; gs.nblk = p.cf_blocks;
-      s = comm_allreduce_gather_f64(packed, p.packed_len, gs);
-    } else
     s = comm_allreduce_sum_f64_impl(reinterpret_cast<double*>(ws + p.o_packed), p.packed_len);
     prof_end(6);
     if (s != UM_OK) return s;
   }
   const bool want3 = out->sigma || out->beta3 || out->phi || out->phi_hat;
-  s = run_finish(p, ws, mode, yp, y->rs, 0, (double)n_total, out->forecasts, out->residuals, 0, out->sigma, out->beta3, nullptr, want3,
-                 /*gather_here=*/!sharded);
+  s = run_finish(p, ws, mode, yp, y->rs, 0, (double)n_total, out->forecasts, out->residuals, 0, out->sigma, out->beta3, nullptr, want3);
   if (s != UM_OK) return s;
   s = run_outputs(p, ws, mode, out->alpha, out->phi, out->phi_hat, out->xstd, N);
   if (s != UM_OK) return s;
