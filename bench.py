@@ -415,7 +415,7 @@ def matd_ops(u, peak_gbs, n=32768):
     rec("neg", lambda: -m, 16 * E)
     rec("relu", lambda: m.relu(), 16 * E)
     rec("sigmoid", lambda: m.sigmoid(), 16 * E)
-    rec("softmax_axis1", lambda: m.softmax(1), 16 * E, "single read: lane held in registers across a 4-CTA cluster")
+    rec("softmax_axis1", lambda: m.softmax(1), 16 * E, "single read: the 256 KB row held in registers + shared memory across a 2-CTA cluster")
     rec("softmax_axis0", lambda: m.softmax(0), 16 * E,
         "single read for 85 % of the columns: 16-column strips held in tensor memory across 16-CTA clusters (softmax_strip.cuh); "
         "the other 15 % run through the two-read kernels at the same time on the SMs and issue slots the clusters leave idle")
