@@ -31,6 +31,8 @@
 namespace um {
 
 int comm_allreduce_sum_f64_impl(double* buf, i64 count);  // comm.cu
+bool comm_can_gather(const double* buf, i64 count);        // comm.cu: the exchange is one peer-memory kernel that can gather its input
+int comm_allreduce_gather_f64(double* buf, i64 count, const GatherSrc& gs);
 int comm_check_error();                                     // comm.cu: did a bounded peer wait give up? (call after a sync)
 bool comm_active();
 int comm_world();
@@ -1273,7 +1275,7 @@ static int run_fused(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_b
 
 // sweeps over one resident X block (T x N, row pitch ldx), writing / accumulating the packed buffer.
 // `ws` is the carved workspace; prep must already have run.
-static int run_sweeps(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_bs, int accumulate) {
+static int run_sweeps(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_bs, int accumulate, bool gather = true) {
   cudaStream_t st = ctx()->stream;
   double* zc = reinterpret_cast<double*>(ws + p.o_zc);
   double* qp = reinterpret_cast<double*>(ws + p.o_qp);
@@ -1322,7 +1324,7 @@ static int run_sweeps(const Plan3& p, char* ws, const double* X, i64 ldx, i64 x_
     UM_LAUNCHED();
   }
   }
-  {
+  if (gather) {
     i64 gx = cdiv(p.packed_len, 256);
     if (gx > 1024) gx = 1024;
     dim3 grid((unsigned)gx, 1, (unsigned)p.batch);
@@ -1505,10 +1507,23 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
   const double* zp = static_cast<const double*>(Z->data) + Z->offset;
   s = run_prep(p, ws, zp, Z->rs, Z->cs, 0, yp, y->rs, 0);
   if (s != UM_OK) return s;
-  s = run_sweeps(p, ws, xp, ldx, 0, 0);
+  // Sharded over peer memory, the exchange kernel forms this rank's packed block from the sweep's chunk partials
+  // itself (its pushes ARE the gather: 32 CTAs, the same sums in the same order): no separate gather launch on the
+  // serial tail of a 0.6 ms fit.  One rank and the NCCL transport keep the gather kernel (gathering inside the 8-CTA
+  // finish kernel was tried and cost what the launch saved).
+  double* packed = reinterpret_cast<double*>(ws + p.o_packed);
+  const bool xgather = sharded && comm_can_gather(packed, p.packed_len);
+  s = run_sweeps(p, ws, xp, ldx, 0, 0, /*gather=*/!xgather);
   if (s != UM_OK) return s;
   if (sharded) {
     prof_begin(6);
+    if (xgather) {
+      GatherSrc gs;
+      gs.pxp = reinterpret_cast<double*>(ws + p.o_pxp); gs.h0p = reinterpret_cast<double*>(ws + p.o_h0p);
+      gs.blockpart = reinterpret_cast<double*>(ws + p.o_bp);
+      gs.T = p.T; gs.tpad = p.tpad; gs.nchunk = (int)p.cchunks; gs.nblk = p.cf_blocks;
+      s = comm_allreduce_gather_f64(packed, p.packed_len, gs);
+    } else
     s = comm_allreduce_sum_f64_impl(reinterpret_cast<double*>(ws + p.o_packed), p.packed_len);
     prof_end(6);
     if (s != UM_OK) return s;
