@@ -167,6 +167,23 @@ def test_batched_matches_single(u):
         assert close(F[p], o.forecasts.ravel()) and close(A[p], o.alpha.ravel(), rtol=1e-8) and close(R[p], o.r_squared)
 
 
+def test_batched_more_panels_than_a_grid_dimension(u):
+    """70 000 tiny panels in one call (the panel index is a grid dimension <= 65535: the call slices): sampled panels on
+    either side of the slice boundary against the oracle, every R^2 finite."""
+    from uni_b200 import _lib as L_
+    B, T, N, L = 70000, 16, 32, 2
+    dX = u.MatD.randn(B * T, N, seed=5); dy = u.MatD.randn(B * T, 1, seed=6); dZ = u.MatD.randn(B * T, L, seed=7)
+    f = u.MatD.zeros(B * T, 1); r2 = u.MatD.zeros(B, 1)
+    L_.check(L_.lib.um_tprf_fit_batched(L_.TPRF_CLOSED, dy._buf.ptr, dX._buf.ptr, dZ._buf.ptr, T, N, L, B, f._buf.ptr, None, r2._buf.ptr))
+    R = r2.to_numpy().ravel()
+    assert np.isfinite(R).all()
+    for p in (0, 1, 65534, 65535, 65536, 69999):
+        Xp = dX.slice(p * T, (p + 1) * T, 0, N).to_numpy(); yp = dy.slice(p * T, (p + 1) * T, 0, 1).to_numpy()
+        Zp = dZ.slice(p * T, (p + 1) * T, 0, L).to_numpy()
+        o = to.tprf_closed_form_gram(yp, Xp, Zp)
+        assert close(f.slice(p * T, (p + 1) * T, 0, 1).to_numpy().ravel(), o.forecasts.ravel()) and close(R[p], o.r_squared)
+
+
 def test_host_streamed_fit(u):
     import ctypes as C
     from uni_b200 import _lib as L_

@@ -72,9 +72,8 @@ __global__ void __launch_bounds__(256) k_rank_order_sum(const double* __restrict
 // of the slots in rank order.  All P2P_CTAS CTAs are resident at once (32 <= SM count, the stream is otherwise idle),
 // and every CTA posts before it waits, so no rank can wait on a store that is itself waiting.  The wait is bounded
 // (~4 s): a peer that died must not leave this GPU spinning; the give-up is reported through *err.
-template <bool GATHER>
 __global__ void __launch_bounds__(256) k_p2p_allreduce(double* __restrict__ buf, i64 count, P2PDev d, int parity, unsigned expect,
-                                                        int* err, const GatherSrc gs) {
+                                                        int* err) {
   const i64 nvec = count >> 1;
   const size_t slot = ((size_t)parity * d.world + d.rank) * P2P_CAP * sizeof(double);
   const double2* src = reinterpret_cast<const double2*>(buf);
@@ -82,14 +81,12 @@ __global__ void __launch_bounds__(256) k_p2p_allreduce(double* __restrict__ buf,
   const i64 per = (nvec + gridDim.x - 1) / gridDim.x;
   const i64 v0 = min((i64)blockIdx.x * per, nvec), v1 = min(v0 + per, nvec);
   for (i64 i = v0 + threadIdx.x; i < v1; i += 256) {
-    // GATHER: this rank's block does not exist yet -- it is formed here from the sweep's chunk partials (the same
-    // sums, in the same order, as the separate gather kernel)
-    const double2 v = GATHER ? make_double2(gather_packed(gs, 2 * i), gather_packed(gs, 2 * i + 1)) : src[i];
+    const double2 v = src[i];
     for (int r = 0; r < d.world; ++r) reinterpret_cast<double2*>(d.peer[r] + slot)[i] = v;
   }
   const bool tail = (count & 1) && blockIdx.x == gridDim.x - 1;
   if (tail && threadIdx.x == 0) {
-    const double v = GATHER ? gather_packed(gs, count - 1) : buf[count - 1];
+    const double v = buf[count - 1];
     for (int r = 0; r < d.world; ++r) reinterpret_cast<double*>(d.peer[r] + slot)[count - 1] = v;
   }
   __threadfence_system();
@@ -121,13 +118,9 @@ __global__ void __launch_bounds__(256) k_p2p_allreduce(double* __restrict__ buf,
   }
 }
 
-static int p2p_allreduce(double* buf, i64 count, const GatherSrc* gs = nullptr) {
+static int p2p_allreduce(double* buf, i64 count) {
   const unsigned e = ++g_p2p.epoch;
-  if (gs)
-    k_p2p_allreduce<true><<<P2P_CTAS, 256, 0, ctx()->stream>>>(buf, count, g_p2p.dev, (int)(e & 1u), e * (unsigned)P2P_CTAS, g_p2p.err_dev, *gs);
-  else
-    k_p2p_allreduce<false><<<P2P_CTAS, 256, 0, ctx()->stream>>>(buf, count, g_p2p.dev, (int)(e & 1u), e * (unsigned)P2P_CTAS, g_p2p.err_dev,
-                                                              GatherSrc{});
+  k_p2p_allreduce<<<P2P_CTAS, 256, 0, ctx()->stream>>>(buf, count, g_p2p.dev, (int)(e & 1u), e * (unsigned)P2P_CTAS, g_p2p.err_dev);
   UM_LAUNCHED();
   return UM_OK;
 }
@@ -136,17 +129,6 @@ static int p2p_allreduce(double* buf, i64 count, const GatherSrc* gs = nullptr) 
 int comm_check_error() {
   if (g_p2p.err_host && *g_p2p.err_host) return fail(UM_ERR_NCCL, "peer-memory exchange timed out waiting for another rank");
   return UM_OK;
-}
-
-// True when the exchange of `count` doubles runs as ONE peer-memory kernel that can gather its own input
-// (comm_allreduce_gather_f64); false -> the caller gathers first and calls comm_allreduce_sum_f64_impl.
-bool comm_can_gather(const double* buf, i64 count) {
-  return g_comm.comm && g_comm.world > 1 && g_p2p.ok && count <= P2P_CAP && (reinterpret_cast<uintptr_t>(buf) & 15) == 0;
-}
-// all-reduce of the packed 3PRF buffer whose local contribution is still in chunk partials: buf receives the total
-int comm_allreduce_gather_f64(double* buf, i64 count, const GatherSrc& gs) {
-  if (!comm_can_gather(buf, count)) return fail(UM_ERR_ARG, "comm_allreduce_gather_f64: peer-memory exchange not available");
-  return p2p_allreduce(buf, count, &gs);
 }
 
 int comm_allreduce_sum_f64_impl(double* buf, i64 count) {

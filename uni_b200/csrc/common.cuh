@@ -183,29 +183,4 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return r;
 }
 
-// The 3PRF sweep leaves per-chunk partials (PX[chunk][tpad][8], h0[chunk][tpad], small[block][81]); the packed buffer
-// PX[T][8] | h0[T] | small[81] is their sum over chunks / blocks in index order.  Kernels that consume the packed buffer
-// once (the finish kernel on one GPU, the peer-memory exchange on several) gather it themselves through this.
-struct GatherSrc {
-  const double* pxp; const double* h0p; const double* blockpart;
-  i64 T, tpad;
-  int nchunk, nblk;
-};
-__device__ __forceinline__ double gather_packed(const GatherSrc& g, i64 e) {
-  double s = 0.0;
-  if (e < g.T * 8) {
-#pragma unroll 8   // the loads of eight chunks go out together; the adds keep the chunk order
-    for (int c = 0; c < g.nchunk; ++c) s += __ldcg(g.pxp + (i64)c * g.tpad * 8 + e);
-  } else if (e < g.T * 9) {
-    const i64 t = e - g.T * 8;
-#pragma unroll 8
-    for (int c = 0; c < g.nchunk; ++c) s += __ldcg(g.h0p + (i64)c * g.tpad + t);
-  } else {
-    const i64 i = e - g.T * 9;
-#pragma unroll 8
-    for (int k = 0; k < g.nblk; ++k) s += __ldcg(g.blockpart + (i64)k * 81 + i);
-  }
-  return s;
-}
-
 }  // namespace um

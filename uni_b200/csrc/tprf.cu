@@ -31,8 +31,6 @@
 namespace um {
 
 int comm_allreduce_sum_f64_impl(double* buf, i64 count);  // comm.cu
-bool comm_can_gather(const double* buf, i64 count);        // comm.cu: the exchange is one peer-memory kernel that can gather its input
-int comm_allreduce_gather_f64(double* buf, i64 count, const GatherSrc& gs);
 int comm_check_error();                                     // comm.cu: did a bounded peer wait give up? (call after a sync)
 bool comm_active();
 int comm_world();
@@ -1507,23 +1505,12 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
   const double* zp = static_cast<const double*>(Z->data) + Z->offset;
   s = run_prep(p, ws, zp, Z->rs, Z->cs, 0, yp, y->rs, 0);
   if (s != UM_OK) return s;
-  // Sharded over peer memory, the exchange kernel forms this rank's packed block from the sweep's chunk partials
-  // itself (its pushes ARE the gather: 32 CTAs, the same sums in the same order): no separate gather launch on the
-  // serial tail of a 0.6 ms fit.  One rank and the NCCL transport keep the gather kernel (gathering inside the 8-CTA
-  // finish kernel was tried and cost what the launch saved).
-  double* packed = reinterpret_cast<double*>(ws + p.o_packed);
-  const bool xgather = sharded && comm_can_gather(packed, p.packed_len);
-  s = run_sweeps(p, ws, xp, ldx, 0, 0, /*gather=*/!xgather);
+  // (gathering the chunk partials inside the finish kernel, or inside the exchange kernel, was tried in round 2: the
+  // 8- and 32-CTA kernels take longer over it than the 1024-CTA gather launch they save)
+  s = run_sweeps(p, ws, xp, ldx, 0, 0);
   if (s != UM_OK) return s;
   if (sharded) {
     prof_begin(6);
-    if (xgather) {
-      GatherSrc gs;
-      gs.pxp = reinterpret_cast<double*>(ws + p.o_pxp); gs.h0p = reinterpret_cast<double*>(ws + p.o_h0p);
-      gs.blockpart = reinterpret_cast<double*>(ws + p.o_bp);
-      gs.T = p.T; gs.tpad = p.tpad; gs.nchunk = (int)p.cchunks; gs.nblk = p.cf_blocks;
-      s = comm_allreduce_gather_f64(packed, p.packed_len, gs);
-    } else
     s = comm_allreduce_sum_f64_impl(reinterpret_cast<double*>(ws + p.o_packed), p.packed_len);
     prof_end(6);
     if (s != UM_OK) return s;
@@ -1548,15 +1535,8 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
   return UM_OK;
 }
 
-int32_t um_tprf_fit_batched(int32_t mode, const double* y, const double* X, const double* Z, int64_t T, int64_t N, int64_t L,
-                            int64_t batch, double* forecasts, double* alpha, double* r2) {
-  UM_CTX();
-  UM_REQUIRE(mode >= UM_TPRF_CLOSED && mode <= UM_TPRF_WINDOW, "unknown 3PRF mode %d", mode);
-  UM_REQUIRE(y && X && Z, "null input");
-  UM_REQUIRE(L >= 1 && L <= LP, "number of proxies L = %lld outside [1, %d]", (i64)L, LP);
-  UM_REQUIRE(T >= 1 && N >= 1 && batch >= 0, "bad panel shape");
-  UM_REQUIRE(batch <= 65535, "batch %lld > 65535: split the call", (i64)batch);
-  if (batch == 0) return UM_OK;
+static int fit_batched_chunk(int32_t mode, const double* y, const double* X, const double* Z, int64_t T, int64_t N, int64_t L,
+                             int64_t batch, double* forecasts, double* alpha, double* r2) {
   Plan3 p = make_plan_for(T, N, L, batch, X, N, T * N);
   char* ws = static_cast<char*>(scratch(p.total));
   if (!ws) return UM_ERR_OOM;
@@ -1569,6 +1549,24 @@ int32_t um_tprf_fit_batched(int32_t mode, const double* y, const double* X, cons
   s = run_finish(p, ws, mode, y, 1, T, (double)N, forecasts, nullptr, T, nullptr, nullptr, r2);
   if (s != UM_OK) return s;
   return run_outputs(p, ws, mode, alpha, nullptr, nullptr, nullptr, N);
+}
+
+int32_t um_tprf_fit_batched(int32_t mode, const double* y, const double* X, const double* Z, int64_t T, int64_t N, int64_t L,
+                            int64_t batch, double* forecasts, double* alpha, double* r2) {
+  UM_CTX();
+  UM_REQUIRE(mode >= UM_TPRF_CLOSED && mode <= UM_TPRF_WINDOW, "unknown 3PRF mode %d", mode);
+  UM_REQUIRE(y && X && Z, "null input");
+  UM_REQUIRE(L >= 1 && L <= LP, "number of proxies L = %lld outside [1, %d]", (i64)L, LP);
+  UM_REQUIRE(T >= 1 && N >= 1 && batch >= 0, "bad panel shape");
+  // the panel index is a grid dimension (<= 65535): any number of panels goes through in slices of that, in stream order
+  constexpr int64_t SLICE = 65535;
+  for (int64_t b0 = 0; b0 < batch; b0 += SLICE) {
+    const int64_t nb = batch - b0 < SLICE ? batch - b0 : SLICE;
+    const int s = fit_batched_chunk(mode, y + b0 * T, X + b0 * T * N, Z + b0 * T * L, T, N, L, nb, forecasts ? forecasts + b0 * T : nullptr,
+                                    alpha ? alpha + b0 * N : nullptr, r2 ? r2 + b0 : nullptr);
+    if (s != UM_OK) return s;
+  }
+  return UM_OK;
 }
 
 int32_t um_tprf_fit_host(int32_t mode, const double* y, const double* X, int64_t ldx, const double* Z, int64_t T,
