@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(256) k_rank_order_sum(const double* __restrict
 // (~4 s): a peer that died must not leave this GPU spinning; the give-up is reported through *err.
 __global__ void __launch_bounds__(256) k_p2p_allreduce(double* __restrict__ buf, i64 count, P2PDev d, int parity, unsigned expect,
                                                         int* err) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched as a programmatic dependent (of the gather)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the finish kernel may become resident meanwhile
   const i64 nvec = count >> 1;
   const size_t slot = ((size_t)parity * d.world + d.rank) * P2P_CAP * sizeof(double);
   const double2* src = reinterpret_cast<const double2*>(buf);
@@ -120,7 +122,15 @@ __global__ void __launch_bounds__(256) k_p2p_allreduce(double* __restrict__ buf,
 
 static int p2p_allreduce(double* buf, i64 count) {
   const unsigned e = ++g_p2p.epoch;
-  k_p2p_allreduce<<<P2P_CTAS, 256, 0, ctx()->stream>>>(buf, count, g_p2p.dev, (int)(e & 1u), e * (unsigned)P2P_CTAS, g_p2p.err_dev);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(P2P_CTAS, 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.stream = ctx()->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  UM_CUDA(cudaLaunchKernelEx(&cfg, k_p2p_allreduce, buf, count, g_p2p.dev, (int)(e & 1u), e * (unsigned)P2P_CTAS, g_p2p.err_dev));
   UM_LAUNCHED();
   return UM_OK;
 }

@@ -494,6 +494,9 @@ __global__ void __launch_bounds__(256)
 k_tprf_gather(const double* __restrict__ pxp, const double* __restrict__ h0p, int nchunk, i64 T, i64 tpad,
               const double* __restrict__ blockpart, int nblk, double* __restrict__ packed, i64 packed_stride,
               int accumulate) {
+  // the next kernel in the stream (exchange or finish, launched with programmatic stream serialisation) may be made
+  // resident while this one runs; it waits (griddepcontrol.wait) for this grid's completion before it reads anything
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const i64 b = blockIdx.z;
   double* out = packed + b * packed_stride;
   const i64 total = T * (LP + 1) + NSMALL;
@@ -526,6 +529,8 @@ struct FinishArgs {
   double* sigma_ws;                                    // T x 8 workspace per panel
   double* params;                                      // per panel: s[8] | wbar[8] | szzinv[64] | zbar[8] | r2 | singular
   double* r2_out;                                      // per panel r2 (device), may be null
+  double* host_res;                                    // mapped pinned host memory (r2 | singular) of a single-panel fit, may be null:
+                                                       // the fit's two host scalars arrive with the kernel, no copy-engine round trip
 };
 constexpr int PARAMS = 96;
 
@@ -569,6 +574,7 @@ __device__ __forceinline__ void block_sum(double* loc, double (*red)[64], double
 
 template <int CS>
 __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched as a programmatic dependent
   __shared__ double red[8][64];
   __shared__ double tot[64];
   __shared__ double cbuf[5][CS][64];   // one exchange buffer per reduction stage (no reuse, no second barrier)
@@ -851,6 +857,10 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
     par[88] = r2;
     par[89] = (double)singular_s;
     if (g.r2_out) g.r2_out[b] = r2;
+    if (g.host_res) {
+      g.host_res[0] = r2;
+      g.host_res[1] = (double)singular_s;
+    }
   }
 }
 
@@ -1361,8 +1371,9 @@ static int run_prep(const Plan3& p, char* ws, const double* Z, i64 z_rs, i64 z_c
 
 static int run_finish(const Plan3& p, char* ws, int mode, const double* y, i64 y_s, i64 y_bs, double n_total,
                       double* forecasts, double* residuals, i64 f_bs, double* sigma, double* beta3, double* r2_dev,
-                      bool want3 = false) {
+                      bool want3 = false, double* host_res = nullptr) {
   FinishArgs g;
+  g.host_res = host_res;
   g.want3 = (mode == UM_TPRF_CLOSED && want3) ? 1 : 0;
   g.packed = reinterpret_cast<double*>(ws + p.o_packed);
   g.packed_stride = p.packed_len;
@@ -1382,10 +1393,12 @@ static int run_finish(const Plan3& p, char* ws, int mode, const double* y, i64 y
     cfg.gridDim = dim3(FIN_CS, 1, 1);
     cfg.blockDim = dim3(256, 1, 1);
     cfg.stream = ctx()->stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = FIN_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // launch latency hidden behind the gather / exchange
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
     UM_CUDA(cudaLaunchKernelEx(&cfg, k_tprf_finish<FIN_CS>, g));
   } else {
     k_tprf_finish<1><<<(unsigned)p.batch, 256, 0, ctx()->stream>>>(g);
@@ -1407,6 +1420,19 @@ static int run_outputs(const Plan3& p, char* ws, int mode, double* alpha, double
                                                    p.N, p.npad, (int)p.L, mode, alpha, phi, phi_hat, xstd, out_bs);
   prof_end(5);
     UM_LAUNCHED();
+  return UM_OK;
+}
+
+// 64 bytes of mapped pinned host memory per host thread: the finish kernel of a single-panel fit stores r2 / singular
+// there, so the host reads them after the stream synchronisation without a separate device-to-host copy
+static int host_result_block(double** host, double** dev) {
+  static thread_local double* h = nullptr;
+  static thread_local double* d = nullptr;
+  if (!h) {
+    UM_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h), 64, cudaHostAllocMapped));
+    UM_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0));
+  }
+  *host = h; *dev = d;
   return UM_OK;
 }
 
@@ -1516,12 +1542,13 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
     if (s != UM_OK) return s;
   }
   const bool want3 = out->sigma || out->beta3 || out->phi || out->phi_hat;
-  s = run_finish(p, ws, mode, yp, y->rs, 0, (double)n_total, out->forecasts, out->residuals, 0, out->sigma, out->beta3, nullptr, want3);
+  double *res = nullptr, *res_dev = nullptr;
+  s = host_result_block(&res, &res_dev);
+  if (s != UM_OK) return s;
+  s = run_finish(p, ws, mode, yp, y->rs, 0, (double)n_total, out->forecasts, out->residuals, 0, out->sigma, out->beta3, nullptr, want3, res_dev);
   if (s != UM_OK) return s;
   s = run_outputs(p, ws, mode, out->alpha, out->phi, out->phi_hat, out->xstd, N);
   if (s != UM_OK) return s;
-  double res[2];
-  UM_CUDA(cudaMemcpyAsync(res, reinterpret_cast<double*>(ws + p.o_par) + 88, 16, cudaMemcpyDeviceToHost, ctx()->stream));
   UM_CUDA(cudaStreamSynchronize(ctx()->stream));
   out->r_squared = res[0];
   out->singular = res[1] != 0.0;
