@@ -172,6 +172,45 @@ __device__ __forceinline__ double fast_exp(double x) {
   return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
+// The table-based exp of the strip softmax kernel (softmax_strip.cuh): x = (32 q + j) ln2/32 + r, |r| <= ln2/64,
+// 2^(j/32) from a 32-entry table the kernel copies into SHARED memory, degree-6 Taylor for exp(r): 12 FP64
+// instructions, <= 2 ulp on [-700, 700].  As a replacement for fast_exp everywhere (table read per lane through
+// the read-only global path) it measured SLOWER -- sigmoid 3.19 -> 3.30 ms, softmax(1) 3.20 -> 3.56 ms at 32768^2:
+// those kernels are not short of FP64 issue slots, and a per-lane divergent load costs more than six DFMA.
+__constant__ double k_exp2_32[32] = {
+    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924,
+    1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332,
+    1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832, 1.4142135623730951, 1.4451808069770467,
+    1.4768261459394993, 1.5091644275934228, 1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965,
+    1.681792830507429, 1.718619298122478, 1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103,
+    1.9152065613971474, 1.9571441241754002};
+__constant__ double k_exp32c[10] = {
+    46.16624130844683,        // 0: 32 / ln2
+    -0.02166084938653512,     // 1: -(ln2 / 32) high part (32 significant bits: t * hi is exact for |t| < 2^21)
+    -5.9631716539705866e-12,  // 2: -(ln2 / 32) low part
+    6755399441055744.0,       // 3: 1.5 * 2^52: low mantissa bits of (v + MAGIC) = rint(v)
+    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,   // 4..7
+    0.0, 0.0};
+// the polynomial part: exp(x) / 2^(j/32) scaled into place, and j; valid for |x| <= 700
+__device__ __forceinline__ double exp32_core(double x, int* k_out) {
+  const double* __restrict__ c = k_exp32c;
+  double tt = fma(x, c[0], c[3]);
+  *k_out = __double2loint(tt);
+  const double t = tt - c[3];
+  double r = fma(t, c[1], x);
+  r = fma(t, c[2], r);
+  double p = c[4];
+  p = fma(p, r, c[5]);
+  p = fma(p, r, c[6]);
+  p = fma(p, r, c[7]);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return p;
+}
+__device__ __forceinline__ double exp32_scale(double p, int k) {   // p * 2^(k >> 5)
+  return __hiloint2double(__double2hiint(p) + ((k << 15) & 0xfff00000), __double2loint(p));
+}
 // 1/d for normal, finite d (callers: d in [1, 2^40]): MUFU seed (2^-23) + two Newton steps.
 __device__ __forceinline__ double fast_rcp(double d) {
   double r;

@@ -173,45 +173,18 @@ __device__ __forceinline__ void st_global_v2(double* p, double a, double b) {
 }
 
 
-// exp(d) in 12 FP64 instructions and without a branch: d = (32 q + j) ln2/32 + r, |r| <= ln2/64, 2^(j/32) from a
-// 32-entry table in shared memory, degree-6 Taylor for exp(r) (truncation 3.5e-18), 2^q into the exponent field.
-// Error <= 2 ulp on [-700, 700].  Branch-free on purpose: the eight elements a thread handles per box are eight
+// fast_exp's arithmetic (common.cuh: 12 FP64 instructions, 32-entry table) with the table in shared memory and
+// WITHOUT its range branch.  Branch-free on purpose: the eight elements a thread handles per box are eight
 // independent chains the scheduler can interleave (with fast_exp's range test every element sat in its own
 // reconvergence region and, at two warps per sub-partition, the phase ran at the latency of one Horner chain).
 // Outside [-700, 700] (and for NaN / Inf) the value is garbage: such an element always sends its strip down the slow
 // path (the range tracking below), which recomputes everything from global memory.
-__constant__ double k_exp2_32[32] = {
-    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924,
-    1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332,
-    1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832, 1.4142135623730951, 1.4451808069770467,
-    1.4768261459394993, 1.5091644275934228, 1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965,
-    1.681792830507429, 1.718619298122478, 1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103,
-    1.9152065613971474, 1.9571441241754002};
-__constant__ double k_exp32c[10] = {
-    46.16624130844683,        // 0: 32 / ln2
-    -0.02166084938653512,     // 1: -(ln2 / 32) high part (32 significant bits: t * hi is exact for |t| < 2^21)
-    -5.9631716539705866e-12,  // 2: -(ln2 / 32) low part
-    6755399441055744.0,       // 3: 1.5 * 2^52
-    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,   // 4..7
-    0.0, 0.0};
 __device__ __forceinline__ double exp_shifted(double x, unsigned tab) {
-  const double* __restrict__ c = k_exp32c;
-  double tt = fma(x, c[0], c[3]);
-  const int k = __double2loint(tt);
-  const double t = tt - c[3];
-  double r = fma(t, c[1], x);
-  r = fma(t, c[2], r);
-  double p = c[4];
-  p = fma(p, r, c[5]);
-  p = fma(p, r, c[6]);
-  p = fma(p, r, c[7]);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
+  int k;
+  double p = exp32_core(x, &k);
   double tj;
   asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab + (((unsigned)k << 3) & 0xf8u)));
-  p *= tj;
-  return __hiloint2double(__double2hiint(p) + ((k << 15) & 0xfff00000), __double2loint(p));
+  return exp32_scale(p * tj, k);
 }
 // Range tracking on the high word of d = x - k, on the integer pipe (the FP64 pipe and the issue slots are what phase A
 // runs out of): as a SIGNED int the high word orders the positive doubles, +Inf and the positive NaNs above everything
