@@ -174,9 +174,10 @@ __device__ __forceinline__ double fast_exp(double x) {
 
 // The table-based exp of the strip softmax kernel (softmax_strip.cuh): x = (32 q + j) ln2/32 + r, |r| <= ln2/64,
 // 2^(j/32) from a 32-entry table the kernel copies into SHARED memory, degree-6 Taylor for exp(r): 12 FP64
-// instructions, <= 2 ulp on [-700, 700].  As a replacement for fast_exp everywhere (table read per lane through
-// the read-only global path) it measured SLOWER -- sigmoid 3.19 -> 3.30 ms, softmax(1) 3.20 -> 3.56 ms at 32768^2:
-// those kernels are not short of FP64 issue slots, and a per-lane divergent load costs more than six DFMA.
+// instructions, <= 2 ulp on [-700, 700].  WHERE THE TABLE LIVES decides everything: read per lane through the
+// read-only global path (a drop-in replacement for fast_exp) it measured slower than the 18-instruction polynomial
+// (sigmoid 3.19 -> 3.30 ms, softmax(1) 3.20 -> 3.56 ms at 32768^2); from shared memory it is faster (sigmoid 3.19 ->
+// 2.79 ms = 0.94 of HBM).  So the kernels that can afford 256 bytes of shared memory use exp_tab_nonpos below.
 __constant__ double k_exp2_32[32] = {
     1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924,
     1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332,
@@ -210,6 +211,17 @@ __device__ __forceinline__ double exp32_core(double x, int* k_out) {
 }
 __device__ __forceinline__ double exp32_scale(double p, int k) {   // p * 2^(k >> 5)
   return __hiloint2double(__double2hiint(p) + ((k << 15) & 0xfff00000), __double2loint(p));
+}
+// exp(d) for d <= 0 (or NaN), `tab` = the shared-memory address of a copy of k_exp2_32: the table form, then -- a
+// branch normal data never takes -- libdevice's exp for d < -700 (denormal results), -Inf and NaN
+__device__ __forceinline__ double exp_tab_nonpos(double d, unsigned tab) {
+  int k;
+  const double p = exp32_core(d, &k);
+  double tj;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab + (((unsigned)k << 3) & 0xf8u)));
+  double z = exp32_scale(p * tj, k);
+  if (!(d >= -700.0)) z = exp(d);
+  return z;
 }
 // 1/d for normal, finite d (callers: d in [1, 2^40]): MUFU seed (2^-23) + two Newton steps.
 __device__ __forceinline__ double fast_rcp(double d) {

@@ -6,6 +6,8 @@
 // rows are 16-byte addressable (cs == 1, or cs == 0 -> splat), otherwise one element at a
 // time through the stride equation.  Dense same-shape operands collapse to one long row.
 // HBM-bound: no shared memory, loads issued before any compute, grid >> 148 SMs.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace um {
@@ -67,12 +69,17 @@ struct UCast { template <class TI, class TO> __device__ TO apply(TI x) const { r
 // sigmoid: x >= 0 ? 1/(1+exp(-x)) : (e = exp(x); e/(1+e)); NaN takes the second branch
 // (MatMathOps.scala:103-107); computed in double, as the reference widens to Double.
 struct USigmoid {
+  static constexpr bool exptab = true;   // k_unary gives the functor a copy of the 2^(j/32) table in shared memory
+  unsigned tab;
   template <class TI, class TO>
   __device__ TO apply(TI xi) const {
     // same two formulas with z = exp(-|x|): x >= 0 -> 1/(1+z), else z/(1+z); the division is
-    // num * rcp(1+z) with 1+z in [1,2] (<= 2 ulp from the reference's IEEE divide)
+    // num * rcp(1+z) with 1+z in [1,2] (<= 2 ulp from the reference's IEEE divide).
+    // exp: the 12-instruction table form of common.cuh with the table in shared memory (per-lane index: the constant
+    // bank would serialise it, the global read-only path measured slower than six more DFMA); arguments below -700
+    // (denormal results) and NaN are redone by libdevice's exp afterwards -- a branch normal data never takes.
     double x = (double)xi;
-    double z = fast_exp(-fabs(x));
+    const double z = exp_tab_nonpos(-fabs(x), tab);
     double num = (x >= 0.0) ? 1.0 : z;
     return (TO)(num * fast_rcp(1.0 + z));
   }
@@ -125,8 +132,18 @@ struct FLogic {
 struct UNot { template <class TI, class TO> __device__ TO apply(TI x) const { return (TO)(x == 0); } };
 
 // ---- kernels -----------------------------------------------------------------------------
+template <class F, class = void> struct wants_exptab : std::false_type {};
+template <class F> struct wants_exptab<F, std::enable_if_t<F::exptab>> : std::true_type {};
+
 template <int VW, class F, class TA, class TO>
 __global__ void __launch_bounds__(EW_THREADS) k_unary(F f, In<TA> a, Out<TO> o, i64 rows, i64 cols) {
+  if constexpr (wants_exptab<F>::value) {
+    __shared__ double s_tab[32];
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    if (t < 32) s_tab[t] = k_exp2_32[t];
+    __syncthreads();
+    f.tab = (unsigned)__cvta_generic_to_shared(s_tab);
+  }
   const int TX = blockDim.x, TY = blockDim.y;
   const i64 cbase = ((i64)blockIdx.x * EW_UNROLL * TX + threadIdx.x) * VW;
   for (i64 r = (i64)blockIdx.y * TY + threadIdx.y; r < rows; r += (i64)gridDim.y * TY) {

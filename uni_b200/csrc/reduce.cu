@@ -644,6 +644,10 @@ __global__ void __launch_bounds__(256) k_softmax_lane_stats(const SoftP::Acc* __
 __global__ void __launch_bounds__(256) k_softmax_norm_vec(const double* __restrict__ p, i64 s_red, i64 n_lane, i64 n_red,
                                                            const double* __restrict__ m_in, const double* __restrict__ inv_in,
                                                            double* __restrict__ out, i64 o_red) {
+  __shared__ double s_tab[32];   // 2^(j/32) for exp_tab_nonpos (x - m <= 0 here)
+  if (threadIdx.y == 0) s_tab[threadIdx.x] = k_exp2_32[threadIdx.x];
+  __syncthreads();
+  const unsigned tab = (unsigned)__cvta_generic_to_shared(s_tab);
   const i64 l = ((i64)blockIdx.x * 32 + threadIdx.x) * 2;
   if (l >= n_lane) return;  // n_lane is even on this path
   const double2 m = *reinterpret_cast<const double2*>(m_in + l);
@@ -656,13 +660,13 @@ __global__ void __launch_bounds__(256) k_softmax_norm_vec(const double* __restri
     for (int u = 0; u < 4; ++u) x[u] = *reinterpret_cast<const double2*>(p + (i + u * step) * s_red + l);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      double2 o = make_double2(fast_exp(x[u].x - m.x) * inv.x, fast_exp(x[u].y - m.y) * inv.y);
+      double2 o = make_double2(exp_tab_nonpos(x[u].x - m.x, tab) * inv.x, exp_tab_nonpos(x[u].y - m.y, tab) * inv.y);
       __stcs(reinterpret_cast<double2*>(out + (i + u * step) * o_red + l), o);
     }
   }
   for (; i < n_red; i += step) {
     double2 x = *reinterpret_cast<const double2*>(p + i * s_red + l);
-    double2 o = make_double2(fast_exp(x.x - m.x) * inv.x, fast_exp(x.y - m.y) * inv.y);
+    double2 o = make_double2(exp_tab_nonpos(x.x - m.x, tab) * inv.x, exp_tab_nonpos(x.y - m.y, tab) * inv.y);
     __stcs(reinterpret_cast<double2*>(out + i * o_red + l), o);
   }
 }
@@ -879,6 +883,9 @@ __global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const doub
   // exp phase of one CTA overlaps the load/store phase of the other CTA on the SM.
   extern __shared__ __align__(16) double2 sx[];   // chunk c of thread t at sx[c * OC_THREADS + t]
   __shared__ double sm_red[OC_THREADS / 32];
+  __shared__ double s_tab[32];                    // 2^(j/32): the table exp of common.cuh (exp_tab_nonpos)
+  if (threadIdx.x < 32) s_tab[threadIdx.x] = k_exp2_32[threadIdx.x];   // published by the first barrier below
+  const unsigned tab = (unsigned)__cvta_generic_to_shared(s_tab);
   __shared__ double sm_x[2][2];                   // [row parity][0] this CTA's max, [..][1] its sum (read by the peer)
   const int t = threadIdx.x;
   unsigned rank = 0;
@@ -956,19 +963,19 @@ __global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const doub
     for (int c = 0; c < OC_REG; ++c) {
       const i64 v = v0 + (i64)c * OC_THREADS + t;
       if (FULL || v < nv) {
-        r[c].x = fast_exp(r[c].x - mx);
-        r[c].y = fast_exp(r[c].y - mx);
+        r[c].x = exp_tab_nonpos(r[c].x - mx, tab);
+        r[c].y = exp_tab_nonpos(r[c].y - mx, tab);
         s += r[c].x + r[c].y;
       }
     }
-    if (odd_tail) { xt = fast_exp(xt - mx); s += xt; }
+    if (odd_tail) { xt = exp_tab_nonpos(xt - mx, tab); s += xt; }
 #pragma unroll
     for (int c = 0; c < OC_SMEM_CHUNKS; ++c) {
       const i64 v = v0 + (i64)(OC_REG + c) * OC_THREADS + t;
       if (FULL || v < nv) {
         double2 x = sx[c * OC_THREADS + t];
-        x.x = fast_exp(x.x - mx);
-        x.y = fast_exp(x.y - mx);
+        x.x = exp_tab_nonpos(x.x - mx, tab);
+        x.y = exp_tab_nonpos(x.y - mx, tab);
         s += x.x + x.y;
         sx[c * OC_THREADS + t] = x;
       }
