@@ -787,3 +787,40 @@ def test_config2_ops_at_32768_squared(u):
         lane_sums = sm.sum(ax).to_numpy().ravel()
         assert np.max(np.abs(lane_sums - 1.0)) <= 1e-12
         del sm
+
+
+# ---------------------------------------------------------------- allocator / device rules (include/unimat.h)
+def test_free_from_another_host_thread_and_one_device_per_process(u):
+    """um_free may run on a thread that never touched the library (a JVM Cleaner, Python's GC): the block is released
+    on the device and stream it was allocated on and no context is opened; a pointer that is not a live block is
+    refused; a worker thread without um_init inherits the process's device; a second device is refused."""
+    import ctypes as C
+    import threading
+    from uni_b200._lib import lib
+    a = np.random.default_rng(0).standard_normal((257, 129))
+    m = dev(u, a)
+    s = (m + m).to_numpy()
+    ptrs = []
+    for _ in range(4):
+        p = C.c_void_p()
+        assert lib.um_malloc(1 << 20, C.byref(p)) == 0
+        ptrs.append(p.value)
+    out = {}
+
+    def worker():
+        out["free"] = [lib.um_free(C.c_void_p(p)) for p in ptrs]
+        out["twice"] = lib.um_free(C.c_void_p(ptrs[0]))           # no longer a live block
+        out["foreign"] = lib.um_free(C.c_void_p(0x1000))
+        w = dev(u, a)                                              # first library call of this thread: inherits the device
+        out["sum"] = (w + w).to_numpy()
+        del w
+
+    t = threading.Thread(target=worker)
+    t.start(); t.join()
+    assert out["free"] == [0, 0, 0, 0] and out["twice"] != 0 and out["foreign"] != 0
+    assert np.array_equal(out["sum"], s)
+    # the freed blocks are back in the pool and the owning thread goes on working
+    assert np.array_equal((m + m).to_numpy(), s)
+    other = 1 if u.device_count() > 1 else 7
+    assert lib.um_init(other) != 0          # another device (or one that does not exist): refused
+    assert lib.um_init(0) == 0
