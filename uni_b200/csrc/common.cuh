@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "unimat.h"
 
@@ -233,5 +234,9 @@ __device__ __forceinline__ double fast_rcp(double d) {
   r = fma(r, e, r);
   return r;
 }
+
+// One-time host-side setup shared by all host threads (kernel attributes, occupancy results, driver entry points):
+// the functions that own such static state take this lock (one device per process, so the state is per process).
+std::mutex& plan_mutex();
 
 }  // namespace um

@@ -34,6 +34,11 @@ int fail(int code, const char* fmt, ...) {
 
 Ctx* ctx() { return &t_ctx; }
 
+std::mutex& plan_mutex() {
+  static std::mutex m;
+  return m;
+}
+
 static int init_ctx(int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);

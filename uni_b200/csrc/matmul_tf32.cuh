@@ -267,6 +267,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 inline EncodeTiledFn encode_fn() {
+  std::lock_guard<std::mutex> plan_lock(plan_mutex());
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -287,13 +288,16 @@ inline int launch(const float* A, i64 lda, const float* B, i64 ldb, float* C, i6
   if ((K + BK - 1) / BK > 0x7fffffff || M >= (i64(1) << 31) || N >= (i64(1) << 31)) return -1;
   EncodeTiledFn enc = encode_fn();
   if (!enc) return -1;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(k_sgemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC) != cudaSuccess) {
-      cudaGetLastError();
-      return -1;
+  {
+    std::lock_guard<std::mutex> plan_lock(plan_mutex());
+    static bool attr = false;
+    if (!attr) {
+      if (cudaFuncSetAttribute(k_sgemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+      }
+      attr = true;
     }
-    attr = true;
   }
   CUtensorMap ma, mb;
   cuuint32_t es[2] = {1, 1};

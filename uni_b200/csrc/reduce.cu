@@ -1024,10 +1024,13 @@ __global__ void __launch_bounds__(OC_THREADS, 2) k_softmax_row_onchip(const doub
 
 template <int CS, bool FULL>
 static int launch_row_onchip_impl(const double* p, i64 s_lane, i64 n_lane, i64 n_red, double* out, i64 o_lane) {
-  static bool attr = false;
-  if (!attr) {
-    UM_CUDA(cudaFuncSetAttribute(k_softmax_row_onchip<CS, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, OC_SMEM_BYTES));
-    attr = true;
+  {
+    std::lock_guard<std::mutex> plan_lock(plan_mutex());
+    static bool attr = false;
+    if (!attr) {
+      UM_CUDA(cudaFuncSetAttribute(k_softmax_row_onchip<CS, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, OC_SMEM_BYTES));
+      attr = true;
+    }
   }
   cudaLaunchConfig_t cfg = {};
   i64 nclusters = (i64)ctx()->sm_count * 2 / CS;   // two CTAs per SM, all resident: the kernel is persistent

@@ -454,6 +454,7 @@ static bool pick_shape(i64 T, int* G, int* R) {
 }
 
 static int resident_clusters(int G) {
+  std::lock_guard<std::mutex> plan_lock(plan_mutex());
   static int cache[GMAX + 1];
   static bool have[GMAX + 1];
   if (have[G]) return cache[G];

@@ -1019,6 +1019,7 @@ static Plan3 make_plan_for(i64 T, i64 N, i64 L, i64 batch, const double* X, i64 
 }
 
 static int set_smem_attrs() {
+  std::lock_guard<std::mutex> plan_lock(plan_mutex());
   static bool done = false;
   if (done) return UM_OK;
   UM_CUDA(cudaFuncSetAttribute(k_tprf_colstats<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
@@ -1045,6 +1046,7 @@ static int cluster_smem() { return fused::SMEM_ALLOC; }
 
 typedef CUresult (*StreamWaitFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 static StreamWaitFn stream_wait_fn() {
+  std::lock_guard<std::mutex> plan_lock(plan_mutex());
   static StreamWaitFn fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -1058,6 +1060,7 @@ static StreamWaitFn stream_wait_fn() {
 }
 
 static int fused_clusters(int G, int R) {
+  std::lock_guard<std::mutex> plan_lock(plan_mutex());
   // resident clusters of size G of the fused kernel (rows-per-piece variant R/128) on this device, cached
   static int cache[5][fused::GMAX + 1] = {{0}};
   static bool attr_done[5] = {false, false, false, false, false};
@@ -1087,6 +1090,7 @@ static int fused_clusters(int G, int R) {
 }
 
 static int grid_groups(int G, int R) {
+  std::lock_guard<std::mutex> plan_lock(plan_mutex());
   // groups of G CTAs of the grid-wide sweep, one CTA per SM (cooperative launch: all co-resident)
   static bool attr_done[5] = {false, false, false, false, false};
   const int j = R / 128;

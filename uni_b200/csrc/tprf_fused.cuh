@@ -818,6 +818,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline EncodeTiledFn encode_fn() {
+  std::lock_guard<std::mutex> plan_lock(plan_mutex());
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
   if (!tried) {
