@@ -14,7 +14,8 @@ X = u.MatD.randn(T, N, seed=1000); y = u.MatD.randn(T, 1, seed=2); Z = u.MatD.ra
 names = ["colstats/sweep", "colfinal", "project", "gather", "finish", "outputs", "allreduce", "prep"]
 for path, name in ((0, "auto"), (2, "cluster only")):
     tprf3.set_tprf_path(path)
-    fit = lambda: tprf3._fit(L_.TPRF_CLOSED, y, X, Z, n_total=N, want_all=False)
+    MODE = int(os.environ.get("UM_MODE", L_.TPRF_CLOSED))
+    fit = lambda: tprf3._fit(MODE, y, X, Z, n_total=N, want_all=False)
     for _ in range(5):
         fit()
     ms = C.c_float(0)

@@ -681,60 +681,67 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
   const bool three_fc = g.mode != UM_TPRF_CLOSED;
   if (three) {
     // ---- three-pass fit from the same accumulators ----
+    // The small dense algebra between the sweeps' sums and pass 2 used to run on ONE thread with its operands in
+    // global memory (about 2 000 dependent multiply-adds, ~90 us of a 120 us kernel): it now runs across warp 0, 64
+    // matrix entries two per lane, operands staged in shared memory, one __syncwarp per stage.
+    __shared__ double sww_s[LP * LP], swwi_s[LP * LP], pp_s[LP * LP], phisum_s[LP];
+    if (tid < LP * LP) sww_s[tid] = sm[8 + tid];
+    __syncthreads();
     if (tid < 32) {
-      if (tid == 0)
-        for (int a = 0; a < L; ++a)
-          for (int c = 0; c < L; ++c) lu_a[a * L + c] = small[8 + a * LP + c];
+      for (int e = tid; e < L * L; e += 32) lu_a[e] = small[8 + (e / L) * LP + (e % L)];
       __syncwarp();
       const bool ok = lu_inverse_warp(lu_a, L, lu_inv, lu_x, lu_piv, tid);
-      if (tid == 0) {
-      const double* tmp = lu_inv;
-      if (!ok) singular_s = 1;
-      for (int a = 0; a < LP; ++a)
-        for (int c = 0; c < LP; ++c) szzinv[a * LP + c] = (ok && a < L && c < L) ? tmp[a * L + c] : (ok ? 0.0 : nan(""));
+      if (tid == 0 && !ok) singular_s = 1;
+      for (int e = tid; e < LP * LP; e += 32) {
+        const int a = e / LP, c = e % LP;
+        szzinv[e] = (ok && a < L && c < L) ? lu_inv[a * L + c] : (ok ? 0.0 : nan(""));
+      }
+      __syncwarp();
       // [1|Phi]'[1|Phi] with Phi = W0 Szz^-1  (Tprf3.scala:265-266)
-      double phisum[LP], sww_i[LP * LP], pp[LP * LP];
-      for (int a = 0; a < L; ++a) {
+      if (tid < L) {
         double s = 0.0;
-        for (int c = 0; c < L; ++c) s += szzinv[a * LP + c] * sw[c];
-        phisum[a] = s;
+        for (int c = 0; c < L; ++c) s += szzinv[tid * LP + c] * sw[c];
+        phisum_s[tid] = s;
       }
-      for (int a = 0; a < L; ++a)      // sww_i = Szz^-1 * SWW
-        for (int c = 0; c < L; ++c) {
-          double s = 0.0;
-          for (int k = 0; k < L; ++k) s += szzinv[a * LP + k] * sm[8 + k * LP + c];
-          sww_i[a * L + c] = s;
-        }
-      for (int a = 0; a < L; ++a)      // pp = sww_i * Szz^-1' (Szz^-1 symmetric up to rounding)
-        for (int c = 0; c < L; ++c) {
-          double s = 0.0;
-          for (int k = 0; k < L; ++k) s += sww_i[a * L + k] * szzinv[c * LP + k];
-          pp[a * L + c] = s;
-        }
+      for (int e = tid; e < LP * LP; e += 32) {      // sww_i = Szz^-1 * SWW
+        const int a = e / LP, c = e % LP;
+        double s = 0.0;
+        if (a < L && c < L)
+          for (int k = 0; k < L; ++k) s += szzinv[a * LP + k] * sww_s[k * LP + c];
+        swwi_s[e] = s;
+      }
+      __syncwarp();
+      for (int e = tid; e < LP * LP; e += 32) {      // pp = sww_i * Szz^-1' (Szz^-1 symmetric up to rounding)
+        const int a = e / LP, c = e % LP;
+        double s = 0.0;
+        if (a < L && c < L)
+          for (int k = 0; k < L; ++k) s += swwi_s[a * LP + k] * szzinv[c * LP + k];
+        pp_s[e] = s;
+      }
+      __syncwarp();
       double* ptp = lu_a;
-      ptp[0] = g.n_total;
-      for (int a = 0; a < L; ++a) {
-        ptp[0 * L1 + 1 + a] = phisum[a];
-        ptp[(1 + a) * L1 + 0] = phisum[a];
-        for (int c = 0; c < L; ++c) ptp[(1 + a) * L1 + 1 + c] = 0.5 * (pp[a * L + c] + pp[c * L + a]);
+      if (tid == 0) ptp[0] = g.n_total;
+      if (tid < L) {
+        ptp[0 * L1 + 1 + tid] = phisum_s[tid];
+        ptp[(1 + tid) * L1 + 0] = phisum_s[tid];
       }
+      for (int e = tid; e < L * L; e += 32) {
+        const int a = e / L, c = e % L;
+        ptp[(1 + a) * L1 + 1 + c] = 0.5 * (pp_s[a * LP + c] + pp_s[c * LP + a]);
       }
       __syncwarp();
       const bool ok2 = lu_inverse_warp(lu_a, L1, lu_inv, lu_x, lu_piv, tid);
-      if (tid == 0) {
+      if (tid == 0 && !ok2) singular_s = 1;
       const double* ptpinv = lu_inv;
-      if (!ok2) singular_s = 1;
       // Sigma[t][l] = sum_m XP[t][m] PtPinv[1+l][m],  XP[t][0] = h0[t],  XP[t][1+a] = sum_c PX[t][c] szzinv[c][a]
       // fold into m2: Sigma[t][l] = m2[0][l] h0[t] + sum_c m2[1+c][l] PX[t][c]
-      for (int l = 0; l < LP; ++l) {
-        m2[0 * LP + l] = (l < L) ? (ok2 ? ptpinv[(1 + l) * L1 + 0] : nan("")) : 0.0;
-        for (int c = 0; c < LP; ++c) {
-          double s = 0.0;
-          if (l < L && c < L)
-            for (int a = 0; a < L; ++a) s += szzinv[c * LP + a] * ptpinv[(1 + l) * L1 + 1 + a];
-          m2[(1 + c) * LP + l] = (ok2 || !(l < L && c < L)) ? s : nan("");
-        }
-      }
+      if (tid < LP) m2[0 * LP + tid] = (tid < L) ? (ok2 ? ptpinv[(1 + tid) * L1 + 0] : nan("")) : 0.0;
+      for (int e = tid; e < LP * LP; e += 32) {
+        const int c = e / LP, l = e % LP;
+        double s = 0.0;
+        if (l < L && c < L)
+          for (int a = 0; a < L; ++a) s += szzinv[c * LP + a] * ptpinv[(1 + l) * L1 + 1 + a];
+        m2[(1 + c) * LP + l] = (ok2 || !(l < L && c < L)) ? s : nan("");
       }
     }
     __syncthreads();
