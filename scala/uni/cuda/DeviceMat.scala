@@ -47,6 +47,16 @@ final class DeviceMat private (val buf: DeviceBuffer, val view: MemorySegment, v
     if need.get(JAVA_INT, 0) != 0 then s.matCopy else s      // Internal.create's layout guard (Mat.scala:1865-1876)
   def broadcastTo(r: Int, c: Int): DeviceMat = derived(v => um_view_broadcast.invoke(view, r.toLong, c.toLong, v).asInstanceOf[Int])
   def matCopy: DeviceMat = { val o = like(rows, cols); check(um_copy.invoke(view, o.view).asInstanceOf[Int]); o }
+  /** Row-major host copy (Mat.toArray): views are materialised first, then one D2H copy. */
+  def toArray: Array[Double] =
+    val c = if isContiguousView then this else matCopy
+    val n = rows.toLong * cols.toLong
+    val seg = Arena.ofAuto().allocate(n * 8)
+    check(um_d2h.invoke(seg, MemorySegment.ofAddress(c.buf.ptr.address() + c.L("offset") * 8), n * 8).asInstanceOf[Int])
+    seg.toArray(JAVA_DOUBLE)
+  private def isContiguousView: Boolean =
+    val o = Arena.ofAuto().allocate(JAVA_INT)
+    check(um_view_is_contiguous.invoke(view, o).asInstanceOf[Int]); o.get(JAVA_INT, 0) != 0
 
   // ---- elementwise (Mat.scala:1989-2102, 2154-2209, 2514-2531, 4513-4588)
   private def bin(op: Int, b: DeviceMat): DeviceMat =
@@ -166,16 +176,74 @@ object DeviceCsv:
     val a = Arena.ofAuto()
     check(um_csv_save.invoke(m.view, a.allocateFrom(path), a.allocateFrom(sep), a.allocateFrom(nanAs)).asInstanceOf[Int])
 
-/** `uni.stats.Tprf3` on the device (Tprf3.scala:199-289, 1056-1110). */
+/** `uni.stats.Tprf3` on the device (Tprf3.scala:199-289, 883-943, 1056-1250): the Scala twin of uni_b200/tprf3.py. */
 object DeviceTprf3:
-  final case class Result(forecasts: DeviceMat, residuals: DeviceMat, rSquared: Double, alpha: Option[DeviceMat])
-  private def fit(mode: Int, y: DeviceMat, X: DeviceMat, Z: DeviceMat): Result =
-    val f = DeviceMat.alloc(X.rows, 1); val r = DeviceMat.alloc(X.rows, 1); val a = DeviceMat.alloc(X.cols, 1)
+  /** Tprf3Result (Tprf3.scala:243-252): every field of the reference's record; `alpha` only where the reference has it. */
+  final case class Result(forecasts: DeviceMat, residuals: DeviceMat, rSquared: Double, alpha: Option[DeviceMat],
+                          phi: DeviceMat, phiHat: DeviceMat, sigma: DeviceMat, beta3: DeviceMat, xstd: DeviceMat)
+  /** estimate3prf's out-of-sample record: T-long host vectors (NaN where a window has no forecast), R^2, ENC-NEW. */
+  final case class OosResult(forecasts: Array[Double], rollfore: Array[Double], rSquared: Double, encNew: Double)
+
+  /** nTotal > 0 declares X this rank's column shard of an nTotal-column panel (um_comm_init done): one all-reduce per fit. */
+  private def fit(mode: Int, y: DeviceMat, X: DeviceMat, Z: DeviceMat, nTotal: Long = 0L): Result =
+    val (t, n, l) = (X.rows.toLong, X.cols.toLong, Z.cols.toLong)
+    val f = DeviceMat.alloc(t, 1); val r = DeviceMat.alloc(t, 1); val a = DeviceMat.alloc(n, 1)
+    val phi = DeviceMat.alloc(n, l); val phiHat = DeviceMat.alloc(l + 1, n); val sigma = DeviceMat.alloc(t, l)
+    val beta3 = DeviceMat.alloc(l + 1, 1); val xstd = DeviceMat.alloc(1, n)
     val out = Arena.ofAuto().allocate(TPRF_OUT)
     out.set(ADDRESS, 0, f.buf.ptr); out.set(ADDRESS, 8, r.buf.ptr)
-    if mode != 1 then out.set(ADDRESS, 16, a.buf.ptr)
-    check(um_tprf_fit.invoke(mode, y.view, X.view, Z.view, 0L, out).asInstanceOf[Int])
-    Result(f, r, out.get(JAVA_DOUBLE, 64), if mode != 1 then Some(a) else None)
-  def tprfClosedForm(y: DeviceMat, X: DeviceMat, Z: DeviceMat): Result = fit(0, y, X, Z)
-  def t3prf(y: DeviceMat, X: DeviceMat, Z: DeviceMat): Result          = fit(1, y, X, Z)
-  def estimate3prfIsFull(y: DeviceMat, X: DeviceMat, Z: DeviceMat): Result = fit(2, y, X, Z)
+    if mode != 1 then out.set(ADDRESS, 16, a.buf.ptr)            // t3prf has no alpha (Tprf3.scala:260-289)
+    out.set(ADDRESS, 24, phi.buf.ptr); out.set(ADDRESS, 32, phiHat.buf.ptr)
+    out.set(ADDRESS, 40, sigma.buf.ptr); out.set(ADDRESS, 48, beta3.buf.ptr); out.set(ADDRESS, 56, xstd.buf.ptr)
+    check(um_tprf_fit.invoke(mode, y.view, X.view, Z.view, nTotal, out).asInstanceOf[Int])   // status 2 -> ArithmeticException
+    Result(f, r, out.get(JAVA_DOUBLE, 64), if mode != 1 then Some(a) else None, phi, phiHat, sigma, beta3, xstd)
+  def tprfClosedForm(y: DeviceMat, X: DeviceMat, Z: DeviceMat, nTotal: Long = 0L): Result = fit(0, y, X, Z, nTotal)
+  def t3prf(y: DeviceMat, X: DeviceMat, Z: DeviceMat, nTotal: Long = 0L): Result          = fit(1, y, X, Z, nTotal)
+  def estimate3prfIsFull(y: DeviceMat, X: DeviceMat, Z: DeviceMat, nTotal: Long = 0L): Result = fit(2, y, X, Z, nTotal)
+
+  /** estimate3prf(..., "OOS Recursive" | "OOS Cross Val" | "OOS Rolling") (Tprf3.scala:1112-1199): the window table the
+   *  reference's `.par` loop walks, then ONE um_tprf_oos_windows call (every window's standardisation, three passes --
+   *  automatic proxies rebuilt per window when `proxies` is Left(L) -- and held-out forecast in one launch), then the
+   *  point estimates over the rows that have a forecast (:1207, 1226-1238, encnew :854-860). */
+  def estimate3prfOos(y: DeviceMat, X: DeviceMat, proxies: Either[Int, DeviceMat], procedure: String,
+                      window: (Int, Int) = (0, 1), mintrain: (Int, Int) = (-1, 0), rollwin: (Int, Int, Int) = (30, 20, 0)): OosResult =
+    val t = y.rows
+    val auto = proxies.isLeft
+    val nAuto = proxies.left.getOrElse(0)
+    val mt = if mintrain._1 < 0 then (t / 2, mintrain._2) else mintrain
+    val (win, minNoNa, gap) = rollwin
+    // (held-out row, lo, hi, kind, minObs): kind 0 keeps rows [lo, hi), kind 1 drops them
+    val (ts, lo, hi, kind, minObs) = procedure match
+      case "OOS Cross Val" =>
+        val ts = (0 until t).toArray
+        (ts, ts.map(i => math.max(i - window._1, 0)), ts.map(i => math.min(i - window._1 + window._2, t)), 1, 10)
+      case "OOS Recursive" =>
+        val ts = (mt._1 + 1 + mt._2 until t).toArray
+        (ts, ts.map(_ => 0), ts.map(i => i - 1 - mt._2), 0, if auto then mt._1 else 10)
+      case "OOS Rolling" =>
+        val ts = (win + 1 + gap until t).toArray
+        (ts, ts.map(i => math.max(i - win - gap, 0)), ts.map(i => math.min(i - 1 - gap, t)), 0, if auto then minNoNa else 10)
+      case other => throw IllegalArgumentException(s"Unknown procedure '$other'. Choose: 'IS Full', 'OOS Recursive', 'OOS Cross Val', 'OOS Rolling'")
+    val fore = Array.fill(t)(Double.NaN); val roll = Array.fill(t)(Double.NaN)
+    if ts.nonEmpty then
+      val a = Arena.ofAuto()
+      val seg = (v: Array[Int]) => a.allocateFrom(JAVA_INT, v*)
+      val fOut = a.allocate(JAVA_DOUBLE, ts.length.toLong); val rOut = a.allocate(JAVA_DOUBLE, ts.length.toLong)
+      val hi2 = hi.zip(lo).map((h, l) => math.max(h, l))
+      val xc = if X.cs == 1 || X.cols == 1 then X else X.matCopy            // the RAW panel: the call standardises it itself
+      val z = proxies.fold(_ => MemorySegment.NULL, _.view)
+      check(um_tprf_oos_windows.invoke(y.view, xc.view, z, nAuto, kind, seg(lo), seg(hi2), seg(ts), ts.length.toLong,
+                                       minObs, 1, fOut, rOut).asInstanceOf[Int])
+      for (i, k) <- ts.zipWithIndex do
+        fore(i) = fOut.getAtIndex(JAVA_DOUBLE, k.toLong); roll(i) = rOut.getAtIndex(JAVA_DOUBLE, k.toLong)
+    // R^2 with the rolling-mean denominator and ENC-NEW, summed in the reference's order
+    val yh = y.toArray
+    var see = 0.0; var sst = 0.0; var enc = 0.0; var cnt = 0
+    var i = 0
+    while i < t do
+      val e = yh(i) - fore(i)
+      if !e.isNaN then
+        see += e * e; val d = yh(i) - roll(i); sst += d * d; enc += roll(i) * roll(i) - roll(i) * e; cnt += 1
+      i += 1
+    val r2 = if cnt > 0 && sst != 0.0 then 1.0 - see / sst else Double.NaN
+    OosResult(fore, roll, r2, if procedure == "OOS Recursive" && cnt > 0 then cnt.toDouble * enc / see else Double.NaN)
