@@ -316,6 +316,27 @@ def test_broadcast_shape_errors(u):
         a.iadd(c)
 
 
+@pytest.mark.parametrize("op,sym", [("add", "iadd"), ("sub", "isub"), ("mul", "imul"), ("div", "idiv")])
+def test_inplace_family_scalar_and_mat_forms(u, op, sym):
+    """`:+= :-= :*= :/=` (Mat.scala:4513-4588), each with a scalar and with an equal-shape Mat, on a contiguous matrix,
+    a transposed view and a row-slice view: bit-identical to the oracle, the receiver is returned, division by zero
+    and by -0.0 give the IEEE results."""
+    rng = np.random.default_rng(11)
+    a = rng.standard_normal((33, 18)); b = rng.standard_normal((33, 18))
+    b[4, 5] = 0.0; b[6, 7] = -0.0
+    for make_view, make_ref in ((lambda m: m, lambda r: r), (lambda m: m.T, lambda r: r.T),
+                                (lambda m: m.slice(3, 29, 0, 18), lambda r: mo.slice_(r, 3, 29, 0, 18))):
+        m, ref_ = dev(u, a), mo.from2d(a)
+        v, rv = make_view(m), make_ref(ref_)
+        other = b if v.shape == b.shape else (b.T.copy() if v.shape == b.T.shape else b[3:29].copy())
+        with np.errstate(all="ignore"):
+            assert getattr(v, sym)(1.75) is v
+            mo.inplace_scalar(op, rv, 1.75)
+            assert getattr(v, sym)(dev(u, other)) is v
+            mo.inplace_mat(op, rv, mo.from2d(other))
+        assert np.array_equal(m.to_numpy(), ref_.to2d(), equal_nan=True)
+
+
 def test_inplace_through_views(u):
     rng = np.random.default_rng(5)
     a = rng.standard_normal((40, 30))
