@@ -400,6 +400,7 @@ def matd_ops(u, peak_gbs, n=32768):
     out = {}
 
     def rec(name, fn, alg_bytes, note=None):
+        time.sleep(1.0)   # every op is measured from the same rested state (76 back-to-back 8 GiB ops heat the part)
         ms = time_op(u, fn)
         gbs = alg_bytes / (ms * 1e-3) / 1e9
         out[name] = {"ms": round(ms, 4), "gbs": round(gbs, 1), "frac_hbm": round(gbs / peak_gbs, 4)}
@@ -591,6 +592,9 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- SURVEY 8d / apps/Tprf3Bench.scala:186-203: median of 25 individually timed fits (the contract's ms_per_step above is
     # the mean over --steps back-to-back fits; both are reported)
+    # (the sweep draws enough power that a B200 sheds ~7 % of its speed after about a second of back-to-back fits --
+    # tools/iter_vs_closed.py: 3.87 -> 4.13 ms; every figure of this section starts from the same rested state)
+    time.sleep(3.0)
     per_fit = []
     for _ in range(25):
         check(lib.um_timer_start())
@@ -602,6 +606,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- the three-pass (iterative, Tprf3.t3prf) fit of the same panel: BASELINE config 4 names both fits
     fit_iter = lambda: u.tprf3._fit(L_.TPRF_ITER, y, X, Z, n_total=N, want_all=False)
+    time.sleep(3.0)
     for _ in range(2):
         fit_iter()
     barrier()
