@@ -256,18 +256,21 @@ def encnew(e1, e2) -> float:
         return float(a.size * (a * a - a * b).sum() / (b * b).sum())
 
 
-def estimate3prf(y, X, Z, procedure="IS Full", window=(0, 1), mintrain=(-1, 0), rollwin=(30, 20, 0), pls=False) -> TprfResult:
+def estimate3prf(y, X, Z, procedure="IS Full", window=(0, 1), mintrain=(-1, 0), rollwin=(30, 20, 0), pls=False,
+                 compute_avar=False) -> TprfResult:
     """`Tprf3.estimate3prf` (Tprf3.scala:1056-1250), every window fitted directly (the reference's FullSample
     downdating is an O(eps) re-association of the same sums, :742-757).  `Z` = proxy matrix (Right) or an int L
     (Left: automatic proxies).  `pls = True` (effective with automatic proxies only, :1076) takes the per-column /
     per-row nanOls passes and tolerates NaN gaps in X and y; without it the input must be NaN-free.  Result:
-    forecasts, residuals, r_squared, extra = {rollfore, enc}."""
+    forecasts, residuals, r_squared, extra = {rollfore, enc}; with `compute_avar` ("IS Full" only, :1252-1277) also
+    extra["avar_alpha"] (N x N) and extra["avar_forecasts"] (T x T)."""
     y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
     X = np.asarray(X, dtype=np.float64)
     T, N = X.shape
     auto = isinstance(Z, (int, np.integer))
     L = int(Z) if auto else np.asarray(Z).shape[1]
     Zm = None if auto else np.asarray(Z, dtype=np.float64)
+    z_final = None
     mt = (T // 2, mintrain[1]) if mintrain[0] < 0 else tuple(mintrain)
     win, min_nona, gap = rollwin
     Xn = X / nan_std_cols(X)
@@ -304,10 +307,12 @@ def estimate3prf(y, X, Z, procedure="IS Full", window=(0, 1), mintrain=(-1, 0), 
             r0, fore = y * 1.0, np.full((T, 1), np.nan)
             for _ in range(L):  # :1097-1106: residual columns are appended at the BACK
                 fore = t3prf_pls(y, Xn, r0, None, 10)[0] if eff_pls else _window_fit(y, Xn, ones, r0, None, 10)[0]
+                z_final = r0            # the proxies of the LAST fit (:1102), before its residual is appended
                 r0 = np.column_stack([r0, y - fore])
             forecasts[:] = fore
         else:
             forecasts[:] = _window_fit(y, Xn, ones, Zm, None, 10)[0]
+            z_final = Zm
     elif procedure == "OOS Cross Val":
         for t in range(T):
             lo, hi = max(t - window[0], 0), min(t - window[0] + window[1], T)
@@ -340,7 +345,35 @@ def estimate3prf(y, X, Z, procedure="IS Full", window=(0, 1), mintrain=(-1, 0), 
             sst = float(((y[loc, 0] - rollfore[loc, 0]) ** 2).sum())
             r2 = 1.0 - float((resid[loc, 0] ** 2).sum()) / sst if sst != 0.0 else float("nan")
     enc = encnew(rollfore[loc, 0], resid[loc, 0]) if procedure == "OOS Recursive" else float("nan")
-    return TprfResult(forecasts, resid, r2, extra={"rollfore": rollfore, "enc": enc})
+    extra = {"rollfore": rollfore, "enc": enc}
+    if compute_avar and procedure == "IS Full" and z_final is not None:
+        extra["avar_alpha"], extra["avar_forecasts"] = avar_estimates(Xn, z_final, resid)
+    return TprfResult(forecasts, resid, r2, extra=extra)
+
+
+def avar_estimates(Xn, zf, resid):
+    """The asymptotic-variance block of estimate3prf("IS Full", computeAvar = true) (Tprf3.scala:1252-1277): Xn the
+    standardised panel (T x N), zf the proxies of the final fit (T x L), resid the in-sample residuals (T x 1).
+    Every J(T) / J(N) factor of the formulas is a column / row centring (:1255-1262); the T-term sum of weighted outer
+    products (:1266-1270) is accumulated row by row as the reference does.  Returns (alpha avar N x N, forecast avar T x T)."""
+    Xn = np.asarray(Xn, dtype=np.float64); zf = np.asarray(zf, dtype=np.float64)
+    T, N = Xn.shape
+    centre_rows = lambda M: M - M.mean(axis=1, keepdims=True)
+    Xc, Zc = center_columns(Xn), center_columns(zf)
+    xz = Xc.T @ zf                                  # Xn' J(T) zf          N x L
+    zx = centre_rows(Zc.T @ Xn)                     # zf' J(T) Xn J(N)     L x N
+    xx = centre_rows(Xc.T @ Xn)                     # Xn' J(T) Xn J(N)     N x N
+    a = xz * (1.0 / T)
+    b = (zx @ xx @ xz) * (float(T) ** -3 * float(N) ** -2)
+    c = zx * (1.0 / T / N)
+    omega_a = center_columns(a) @ lu_inverse(b) @ c
+    xm = Xn.sum(axis=0) / float(T)
+    acc = np.zeros((N, N))
+    for t in range(T):
+        d = (Xn[t] - xm).reshape(1, -1)
+        acc = acc + (d.T @ d) * (float(resid[t, 0]) ** 2 / T)
+    alpha_avar = omega_a @ acc @ omega_a.T
+    return alpha_avar, (Xc @ alpha_avar @ Xc.T) * float(N) ** -2
 
 
 # ---------------------------------------------------------------------------------------

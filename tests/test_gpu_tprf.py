@@ -86,6 +86,29 @@ def test_python_reference_vectors(u, golden_dir):
         assert abs(r.rSquared - float(g["rsquare"])) < 1e-10, f
 
 
+def test_compute_avar_vs_python_reference(u, golden_dir):
+    """estimate3prf("IS Full", computeAvar = true) on the device (Tprf3.scala:1252-1277) against the reference's NumPy
+    outputs: avar.alpha (N x N) and avar.forecasts (T x T), proxy matrix and automatic proxies; rule of
+    Tprf3ParitySuite (atol 1e-12 + rtol 1e-9), loosened to 1e-8 for the products of products."""
+    d = os.path.join(golden_dir, "tprf_avar_pyref")
+    names = sorted(x for x in os.listdir(d) if x.endswith(".npz"))
+    assert len(names) >= 5
+    for f in names:
+        g = np.load(os.path.join(d, f))
+        rng = np.random.default_rng(int(g["seed"]))
+        T, N, L = int(g["T"]), int(g["N"]), int(g["L"])
+        X = rng.standard_normal((T, N)); y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, L))
+        dy, dX, dZ = devs(u, y, X, Z)
+        r = u.estimate3prf(dy, dX, L if bool(g["auto"]) else dZ, "IS Full", computeAvar=True)
+        assert close(r.forecasts.to_numpy(), g["forecasts"]), f
+        assert r.avar is not None and r.avar.alpha.shape == (N, N) and r.avar.forecasts.shape == (T, T)
+        assert close(r.avar.alpha.to_numpy(), g["avar_alpha"], rtol=1e-8), f
+        assert close(r.avar.forecasts.to_numpy(), g["avar_forecasts"], rtol=1e-8), f
+    # ignored outside "IS Full", absent by default
+    assert u.estimate3prf(dy, dX, dZ, "OOS Recursive", computeAvar=True).avar is None
+    assert u.estimate3prf(dy, dX, dZ).avar is None
+
+
 SHAPES = [(10, 3, 1), (33, 7, 1), (50, 6, 2), (100, 64, 3), (127, 65, 2), (129, 200, 8), (512, 2048, 4), (300, 1000, 5), (1000, 130, 7)]
 
 

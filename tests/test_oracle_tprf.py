@@ -87,6 +87,28 @@ def test_python_reference_vectors(golden_dir):
             assert abs(r.r_squared - float(g["rsquare"])) < 1e-10
 
 
+def test_python_reference_avar_vectors(golden_dir):
+    """estimate3prf("IS Full", computeAvar = true) (Tprf3.scala:1252-1277) against outputs of the reference's own NumPy
+    implementation (tests/golden/gen_tprf_avar_pyref.py): proxy matrix and automatic proxies."""
+    d = os.path.join(golden_dir, "tprf_avar_pyref")
+    names = sorted(f for f in os.listdir(d) if f.endswith(".npz"))
+    assert len(names) >= 5
+    for f in names:
+        g = np.load(os.path.join(d, f))
+        rng = np.random.default_rng(int(g["seed"]))
+        T, N, L = int(g["T"]), int(g["N"]), int(g["L"])
+        X = rng.standard_normal((T, N)); y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, L))
+        r = to.estimate3prf(y, X, L if bool(g["auto"]) else Z, "IS Full", compute_avar=True)
+        np.testing.assert_allclose(r.forecasts, g["forecasts"], rtol=1e-9, atol=1e-12, err_msg=f)
+        assert r.extra["avar_alpha"].shape == (N, N) and r.extra["avar_forecasts"].shape == (T, T)
+        np.testing.assert_allclose(r.extra["avar_alpha"], g["avar_alpha"], rtol=1e-9, atol=1e-12, err_msg=f)
+        np.testing.assert_allclose(r.extra["avar_forecasts"], g["avar_forecasts"], rtol=1e-9, atol=1e-12, err_msg=f)
+        # both are symmetric positive semi-definite by construction
+        assert np.allclose(r.extra["avar_alpha"], r.extra["avar_alpha"].T, rtol=1e-9, atol=1e-12)
+    # computeAvar is ignored outside "IS Full" (:1253)
+    assert "avar_alpha" not in to.estimate3prf(y, X, Z, "OOS Recursive", compute_avar=True).extra
+
+
 def test_sharded_partials_sum_to_full_fit():
     rng = np.random.default_rng(3)
     T, N, L = 120, 48, 3

@@ -11,8 +11,8 @@ from . import rng
 from . import io
 from .io import MatResult, loadMatD, loadMatF, loadSmartD, saveCSV
 from .rng import NumPyRNG
-from .tprf3 import Pls3prfModel, Tprf3Result, estimate3prf, forecast3prf, pls1Fit, plsClosedForm, t3prf, tprfClosedForm
+from .tprf3 import AvarEstimates, Pls3prfModel, Tprf3Result, estimate3prf, forecast3prf, pls1Fit, plsClosedForm, t3prf, tprfClosedForm
 
-__all__ = ["Mat", "MatD", "MatF", "init", "sync", "set_matf_matmul_path", "set_matd_matmul_tile", "set_softmax_axis0_path", "tprf3", "Tprf3Result", "estimate3prf", "forecast3prf",
+__all__ = ["Mat", "MatD", "MatF", "init", "sync", "set_matf_matmul_path", "set_matd_matmul_tile", "set_softmax_axis0_path", "tprf3", "Tprf3Result", "AvarEstimates", "estimate3prf", "forecast3prf",
            "t3prf", "tprfClosedForm", "plsClosedForm", "pls1Fit", "Pls3prfModel", "NumPyRNG", "rng", "io", "MatResult", "loadMatD", "loadMatF", "loadSmartD", "saveCSV", "device_count", "launch_count", "EmptyMatrixError",
            "SingularMatrixError", "UnimatError"]

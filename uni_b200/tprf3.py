@@ -20,6 +20,13 @@ from .mat import Mat, MatD
 
 
 @dataclass
+class AvarEstimates:
+    """AvarEstimates (Tprf3.scala:94-99): asymptotic variance of alpha (N x N) and of the forecasts (T x T)."""
+    alpha: Mat
+    forecasts: Mat
+
+
+@dataclass
 class Tprf3Result:
     """Tprf3Result (Tprf3.scala:72-92): device-resident fields."""
     forecasts: Mat
@@ -34,6 +41,7 @@ class Tprf3Result:
     singular: bool = False
     rollfore: Optional[Mat] = None  # T x 1  mean of each window's y (OOS procedures, Tprf3.scala:1145)
     encnew: float = float("nan")    # ENC-NEW statistic, OOS Recursive only (Tprf3.scala:854-860,1235-1238)
+    avar: Optional[AvarEstimates] = None   # estimate3prf("IS Full", computeAvar = true) only (Tprf3.scala:1252-1277)
 
     @property
     def y_hat(self) -> Mat:         # TprfResult alias (Tprf3.scala:93-95)
@@ -88,6 +96,30 @@ def t3prf(y: Mat, X: Mat, Z: Mat, n_total: int = 0) -> Tprf3Result:
 
 
 _PROCEDURES = ("IS Full", "OOS Recursive", "OOS Cross Val", "OOS Rolling")
+
+
+def _avar(Xn: Mat, zf: Mat, resid: Mat) -> AvarEstimates:
+    """The asymptotic-variance block of estimate3prf("IS Full", computeAvar = true) (Tprf3.scala:1252-1277) with the
+    device operators the reference spells it in: every J(T) / J(N) factor is a column / row centring (:1255-1262),
+    `*@`, one L x L `.inverse`.  The reference's T-term loop of weighted outer products (:1266-1270) is ONE product:
+    sum_t (r_t^2 / T) d_t' d_t = (Xc o r)' (Xc o r) / T with d_t the centred row.  N x N and T x T by definition: meant
+    for the small panels the reference uses it on."""
+    T, N = Xn.rows, Xn.cols
+    Xc = Xn - Xn.mean(0)
+    Zc = zf - zf.mean(0)
+    xz = Xc.T @ zf                                   # Xn' J(T) zf          N x L
+    t1 = Zc.T @ Xn
+    zx = t1 - t1.mean(1)                             # zf' J(T) Xn J(N)     L x N
+    t2 = Xc.T @ Xn
+    xx = t2 - t2.mean(1)                             # Xn' J(T) Xn J(N)     N x N
+    a = xz * (1.0 / T)
+    b = (zx @ xx @ xz) * (float(T) ** -3 * float(N) ** -2)
+    c = zx * (1.0 / T / N)
+    omega_a = (a - a.mean(0)) @ b.inverse() @ c
+    w = Xc * resid                                   # rows scaled by their residual (T x 1 broadcast)
+    acc = (w.T @ w) * (1.0 / T)
+    alpha_avar = omega_a @ acc @ omega_a.T
+    return AvarEstimates(alpha_avar, (Xc @ alpha_avar @ Xc.T) * float(N) ** -2)
 
 
 def _std_cols(X: Mat) -> Mat:
@@ -265,12 +297,17 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
     if procedure not in _PROCEDURES:
         raise ValueError(f"Unknown procedure '{procedure}'. Choose: 'IS Full', 'OOS Recursive', "
                          "'OOS Cross Val', 'OOS Rolling'")
-    if computeAvar:
-        raise NotImplementedError("computeAvar (N x N / T x T by definition, Tprf3.scala:1253-1277) is not on the device path")
     auto = not isinstance(Z, Mat)
     eff_pls = bool(pls) and auto                                    # `val effPls = pls && autoproxy` (:1076)
+    want_avar = bool(computeAvar) and procedure == "IS Full"        # `if computeAvar && procedure == "IS Full"` (:1253)
+    if want_avar and n_total:
+        raise NotImplementedError("computeAvar is N x N by definition: not for column-sharded panels")
     if procedure == "IS Full" and not auto:
-        return _fit(L.TPRF_IS_FULL, y, X, Z, n_total)
+        res = _fit(L.TPRF_IS_FULL, y, X, Z, n_total)
+        if want_avar:
+            nan_in = bool(X.isnan().any() or y.isnan().any() or Z.isnan().any())
+            res.avar = _avar(X / (_nan_std_cols(X) if nan_in else _std_cols(X)), Z, res.residuals)
+        return res
     if n_total:
         raise NotImplementedError("column-sharded panels run IS Full with a proxy matrix only")
     n_auto = int(Z) if auto else 0
@@ -285,9 +322,10 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
     Xn = None if oos_batched else X / (_nan_std_cols(X) if (eff_pls or has_nan) else _std_cols(X))   # Tprf3.scala:1080-1081
 
     if procedure == "IS Full" and eff_pls:                           # :1097-1106 with runT3prf's pls branch
-        r0, fore = y.copy(), None
+        r0, fore, zf = y.copy(), None, None
         for _ in range(n_auto):
             fore, _ = _t3prf_pls(y, Xn, r0, None, 10)
+            zf = r0                                                  # zFinal: the proxies of the last fit (:1102)
             r0 = MatD.hstack(r0, y - fore)
         resid = y - fore
         loc = ~resid.isnan()
@@ -297,14 +335,17 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
             d = yl - yl.mean()
             with np.errstate(all="ignore"):
                 r2 = float(1.0 - np.float64((e * e).sum()) / np.float64((d * d).sum()))
-        return Tprf3Result(fore, resid, r2)
+        return Tprf3Result(fore, resid, r2, avar=_avar(Xn, zf, resid) if want_avar else None)
 
     if procedure == "IS Full":                                       # automatic proxies, :1097-1106
-        r0, res = y.copy(), None
+        r0, res, zf = y.copy(), None, None
         for j in range(n_auto):
             last = j == n_auto - 1
             res = _fit(L.TPRF_IS_FULL if last else L.TPRF_WINDOW, y, Xn, r0, want_all=last)
+            zf = r0                                                  # zFinal: the proxies of the last fit (:1102)
             r0 = MatD.hstack(r0, y - res.forecasts)
+        if want_avar:
+            res.avar = _avar(Xn, zf, res.residuals)
         return res
 
     mt = (T // 2, mintrain[1]) if mintrain[0] < 0 else (int(mintrain[0]), int(mintrain[1]))
