@@ -572,7 +572,9 @@ __device__ __forceinline__ void block_sum(double* loc, double (*red)[64], double
   }
 }
 
-template <int CS>
+// THREE = false: the closed form alone (tprfClosedForm without the pass-1/2/3 fields): the three-pass block is compiled
+// out -- the kernel runs once per fit on eight CTAs, so what it costs is mostly instructions fetched, not executed
+template <int CS, bool THREE>
 __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
   asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched as a programmatic dependent
   __shared__ double red[8][64];
@@ -677,9 +679,9 @@ __global__ void __launch_bounds__(256) k_tprf_finish(FinishArgs g) {
 
   // tprfClosedForm also returns the pass-1/2/3 quantities (phi, sigma, beta3, phiHat: Tprf3.scala:211-231,243-252),
   // which are those of t3prf: the same block runs for CLOSED when they were asked for, without touching yhat / R^2
-  const bool three = g.mode != UM_TPRF_CLOSED || g.want3 != 0;
+  const bool three = THREE && (g.mode != UM_TPRF_CLOSED || g.want3 != 0);
   const bool three_fc = g.mode != UM_TPRF_CLOSED;
-  if (three) {
+  if constexpr (THREE) if (three) {
     // ---- three-pass fit from the same accumulators ----
     // The small dense algebra between the sweeps' sums and pass 2 used to run on ONE thread with its operands in
     // global memory (about 2 000 dependent multiply-adds, ~90 us of a 120 us kernel): it now runs across warp 0, 64
@@ -1410,9 +1412,11 @@ static int run_finish(const Plan3& p, char* ws, int mode, const double* y, i64 y
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // launch latency hidden behind the gather / exchange
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 2;
-    UM_CUDA(cudaLaunchKernelEx(&cfg, k_tprf_finish<FIN_CS>, g));
+    if (mode == UM_TPRF_CLOSED && !g.want3) UM_CUDA(cudaLaunchKernelEx(&cfg, k_tprf_finish<FIN_CS, false>, g));
+    else UM_CUDA(cudaLaunchKernelEx(&cfg, k_tprf_finish<FIN_CS, true>, g));
   } else {
-    k_tprf_finish<1><<<(unsigned)p.batch, 256, 0, ctx()->stream>>>(g);
+    if (mode == UM_TPRF_CLOSED && !g.want3) k_tprf_finish<1, false><<<(unsigned)p.batch, 256, 0, ctx()->stream>>>(g);
+    else k_tprf_finish<1, true><<<(unsigned)p.batch, 256, 0, ctx()->stream>>>(g);
   }
   prof_end(4);
     UM_LAUNCHED();
