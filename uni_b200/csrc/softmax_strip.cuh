@@ -33,7 +33,7 @@ constexpr int NSLOT = 8;                  // landing ring: 8 x 16 KB in flight p
 constexpr int PIECE_BYTES = PR * CW * 8;  // 16384
 constexpr int RMAX = 2048;                // rows per CTA: 2048 x 16 doubles = all 512 tensor-memory columns
 constexpr int GMAX = 16;
-constexpr int NCW = 16;                   // compute warps: four per sub-partition (the exp chains need the latency hiding)
+constexpr int NCW = 16;                   // compute warps: four per sub-partition (8 measured the same; 16 keeps 95 registers per thread)
 constexpr int NCOMP = NCW * 32;
 constexpr int NTHREADS = NCOMP + 32;      // + TMA producer warp
 constexpr int RG = NCOMP / 8;             // row groups of a box: thread = (row group, column pair)
