@@ -308,7 +308,7 @@ def oos_rows(u, small=False):
     import numpy as np
     from oracle import tprf_oracle as to
     out = {}
-    shapes = ((650, 40, 2, True),) if small else ((650, 40, 2, True), (200, 16384, 4, False))
+    shapes = ((650, 40, 2, True),) if small else ((650, 40, 2, True), (200, 16384, 4, True))   # the wide CPU runs take ~2 + 7 s
     for T, N, Lp, with_cpu in shapes:
         rng = np.random.default_rng(1)
         X = rng.standard_normal((T, N)); y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, Lp))
