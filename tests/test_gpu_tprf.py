@@ -150,6 +150,81 @@ def test_all_outputs_vs_oracle(u, tnl):
     assert np.array_equal(c2.forecasts.to_numpy(), c.forecasts.to_numpy())
 
 
+WIDE_SHAPES = [(60, 40, 9), (120, 300, 12), (200, 64, 16), (512, 2048, 10), (1000, 130, 24), (40, 100, 9)]
+
+
+@pytest.mark.parametrize("tnl", WIDE_SHAPES)
+def test_more_than_eight_proxies_vs_oracle(u, tnl):
+    """Tprf3.scala:199-289 take any L; beyond the 8 proxies of the fused sweeps the fit runs on the library's operators
+    (uni_b200/csrc/tprf_wide.cu): every field of all three fits against the oracle."""
+    T, N, L = tnl
+    rng = np.random.default_rng(T + N + L)
+    X = rng.standard_normal((T, N)) * rng.uniform(0.5, 3.0, size=(1, N)) + rng.uniform(-2, 2, size=(1, N))
+    y = rng.standard_normal((T, 1)) + 0.3 * X[:, :1]
+    Z = rng.standard_normal((T, L)) + 0.2 * X[:, : min(L, N)].mean(axis=1, keepdims=True)
+    dy, dX, dZ = devs(u, y, X, Z)
+    oc = to.tprf_closed_form_literal(y, X, Z) if N <= 300 else to.tprf_closed_form_gram(y, X, Z)
+    oi = to.t3prf(y, X, Z)
+    c = u.tprfClosedForm(dy, dX, dZ)
+    assert close(c.forecasts.to_numpy(), oc.forecasts) and close(c.rSquared, oc.r_squared)
+    assert close(c.residuals.to_numpy(), y - oc.forecasts, atol=1e-11)
+    assert close(c.alpha.to_numpy(), oc.alpha, rtol=1e-8, atol=1e-13)
+    assert close(c.xstd.to_numpy(), to.nan_std_cols(X), rtol=1e-12)
+    it = u.t3prf(dy, dX, dZ)
+    assert close(it.forecasts.to_numpy(), oi.forecasts) and close(it.rSquared, oi.r_squared)
+    for r in (it, c):                      # tprfClosedForm carries the pass-1/2/3 fields too (Tprf3.scala:211-231)
+        assert r.phi.shape == (N, L) and r.phiHat.shape == (L + 1, N) and r.sigma.shape == (T, L) and r.beta3.shape == (L + 1, 1)
+        assert close(r.phi.to_numpy(), oi.phi, rtol=1e-8, atol=1e-12)
+        assert close(r.phiHat.to_numpy(), oi.phi_hat, rtol=1e-8, atol=1e-12)
+        assert close(r.sigma.to_numpy(), oi.sigma, rtol=1e-8, atol=1e-11)
+        assert close(r.beta3.to_numpy(), oi.beta3, rtol=1e-7, atol=1e-11)
+    of = to.estimate3prf_is_full(y, X, Z)
+    isf = u.estimate3prf(dy, dX, dZ)
+    assert close(isf.forecasts.to_numpy(), of.forecasts) and close(isf.rSquared, of.r_squared)
+    assert close(isf.alpha.to_numpy(), of.alpha, rtol=1e-8, atol=1e-13)
+    # strided inputs: X and Z as column slices of wider matrices (row pitch > cols), y as a column of a T x 3 matrix
+    XX = u.Mat.from_numpy(np.column_stack([np.full(T, 7.0), X, np.zeros((T, 2))]))._raw_slice(0, T, 1, 1 + N)
+    ZZ = u.Mat.from_numpy(np.column_stack([np.zeros(T), Z, np.ones(T)]))._raw_slice(0, T, 1, 1 + L)
+    yy = u.Mat.from_numpy(np.column_stack([y, y * 2, y * 3]))._raw_slice(0, T, 0, 1)
+    c2 = u.tprfClosedForm(yy, XX, ZZ)
+    assert close(c2.forecasts.to_numpy(), oc.forecasts) and close(c2.alpha.to_numpy(), oc.alpha, rtol=1e-8, atol=1e-13)
+
+
+def test_more_than_eight_proxies_procedures_and_errors(u):
+    """Out-of-sample procedures and automatic proxies with L > 8 (per-window fits on the operator path), the
+    reference's singular-matrix error, constant columns and T < minObs."""
+    rng = np.random.default_rng(5)
+    T, N, L = 80, 60, 9
+    X = rng.standard_normal((T, N)); y = rng.standard_normal((T, 1)) + 0.5 * X[:, :3].sum(axis=1, keepdims=True)
+    Z = rng.standard_normal((T, L))
+    dy, dX, dZ = devs(u, y, X, Z)
+    r = u.estimate3prf(dy, dX, dZ, "OOS Recursive", mintrain=(60, 0))
+    o = to.estimate3prf(y, X, Z, "OOS Recursive", mintrain=(60, 0))
+    assert close(r.forecasts.to_numpy(), o.forecasts) and close(r.rSquared, o.r_squared) and close(r.encnew, o.extra["enc"], rtol=1e-8)
+    r = u.estimate3prf(dy, dX, dZ, "OOS Cross Val", window=(1, 3))
+    o = to.estimate3prf(y, X, Z, "OOS Cross Val", window=(1, 3))
+    assert close(r.forecasts.to_numpy(), o.forecasts) and close(r.rSquared, o.r_squared)
+    r = u.estimate3prf(dy, dX, 9, "IS Full")                    # nine automatic proxies (Tprf3.scala:1097-1106)
+    o = to.estimate3prf(y, X, 9, "IS Full")
+    assert close(r.forecasts.to_numpy(), o.forecasts, rtol=1e-7, atol=1e-9) and close(r.rSquared, o.r_squared, rtol=1e-7)
+    # duplicated proxy -> ArithmeticException("Matrix is singular or nearly singular") (Mat.scala:990)
+    z = np.round(rng.standard_normal((T, 1)) * 8) / 8
+    Zdup = np.column_stack([Z[:, :8], z, z])
+    for fit in (u.tprfClosedForm, u.t3prf, u.estimate3prf):
+        with pytest.raises(u.SingularMatrixError):
+            fit(*devs(u, y, X, Zdup))
+    # constant column -> sd := 1.0; T < minObs -> NaN fit; ssy == 0 -> R^2 = 0
+    Xc = X.copy(); Xc[:, 3] = 2.5
+    rc = u.tprfClosedForm(*devs(u, y, Xc, Z))
+    assert rc.xstd.to_numpy()[0, 3] == 1.0
+    assert close(rc.forecasts.to_numpy(), to.tprf_closed_form_literal(y, Xc, Z).forecasts)
+    s = u.estimate3prf(*devs(u, y[:5], X[:5], Z[:5]))
+    assert np.isnan(s.forecasts.to_numpy()).all() and np.isnan(s.rSquared)
+    assert u.t3prf(*devs(u, np.ones((T, 1)), X, Z)).rSquared == 0.0
+    Xn = X.copy(); Xn[7, 2] = np.nan
+    assert np.isnan(u.tprfClosedForm(*devs(u, y, Xn, Z)).forecasts.to_numpy()).all()
+
+
 def test_edge_semantics(u):
     """TprfCoverageSuite.scala:176-230."""
     rng = np.random.default_rng(4)

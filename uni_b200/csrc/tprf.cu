@@ -923,6 +923,8 @@ __global__ void k_fill_nan(double* p, i64 n) {
 #include "tprf_grid.cuh"
 namespace um {
 
+int tprf_fit_wide(int mode, const um_view* y, const um_view* X, const um_view* Z, um_tprf_out* out);  // tprf_wide.cu, L > LP
+
 // ---- host orchestration ------------------------------------------------------------------------------------------
 static i64 cdiv(i64 a, i64 b) { return (a + b - 1) / b; }
 static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
@@ -1509,7 +1511,7 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
   const i64 T = X->rows, N = X->cols, L = Z->cols;
   UM_REQUIRE(y->rows == T && y->cols == 1, "y must be %lld x 1, got %lldx%lld", T, (i64)y->rows, (i64)y->cols);
   UM_REQUIRE(Z->rows == T, "Z must have %lld rows, got %lld", T, (i64)Z->rows);
-  UM_REQUIRE(L >= 1 && L <= LP, "number of proxies L = %lld outside [1, %d]", L, LP);
+  UM_REQUIRE(L >= 1, "number of proxies L = %lld < 1", L);
   UM_REQUIRE(T >= 1 && N >= 1, "empty panel");
   UM_REQUIRE(X->cs == 1 || N == 1, "X must be row-contiguous (cs == 1); materialise the view first");
   // n_total > 0 declares a column-sharded fit (partials are summed over the communicator); n_total <= 0 is a fit of
@@ -1532,6 +1534,19 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
     if (s != UM_OK) return s;
     UM_CUDA(cudaStreamSynchronize(ctx()->stream));
     return UM_OK;
+  }
+  if (L > LP) {
+    // more proxies than one DMMA fragment holds: the same accumulators from the library's own operators (tprf_wide.cu)
+    if (sharded) return fail(UM_ERR_ARG, "column-sharded fits take L <= %d proxies (L = %lld)", LP, L);
+    const int sw = tprf_fit_wide(mode, y, X, Z, out);
+    if (sw == UM_ERR_SINGULAR) {
+      out->singular = 1;
+      int sf = fill_nan(out->forecasts, T);
+      if (sf == UM_OK) sf = fill_nan(out->residuals, T);
+      if (sf == UM_OK) UM_CUDA(cudaStreamSynchronize(ctx()->stream));
+      return fail(UM_ERR_SINGULAR, "Matrix is singular or nearly singular");
+    }
+    return sw;
   }
   const double* xp = static_cast<const double*>(X->data) + X->offset;
   const i64 ldx = N == 1 ? 1 : X->rs;

@@ -130,6 +130,14 @@ def _std_cols(X: Mat) -> Mat:
 
 
 def _oos_forecast(res: Tprf3Result, xt: Mat) -> float:
+    if res.phi.cols > 8:
+        # more proxies than the one-launch forecast holds: t3prfTail's `bo = (xt o 1/sd) [1|Phi] ([1|Phi]'[1|Phi])^-T`,
+        # `yhatt = b0 + bo[1:] . b[1:]` (Tprf3.scala:933-941) with the device operators
+        N, Lz = res.phi.rows, res.phi.cols
+        dP = MatD.hstack(MatD.ones(N, 1), res.phi)
+        bo = ((xt / res.xstd) @ dP) @ (dP.T @ dP).inverse().T
+        b = res.beta3
+        return float(b[0, 0]) + float((bo._raw_slice(0, 1, 1, Lz + 1) @ b._raw_slice(1, Lz + 1, 0, 1))[0, 0])
     out = C.c_double(0)
     check(lib.um_tprf_oos_forecast(res.phi._ref(), res.xstd._ref(), res.beta3._ref(), xt._ref(), C.byref(out)))
     return out.value
@@ -311,13 +319,14 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
     if n_total:
         raise NotImplementedError("column-sharded panels run IS Full with a proxy matrix only")
     n_auto = int(Z) if auto else 0
-    if auto and not 1 <= n_auto <= 8:
-        raise ValueError(f"number of automatic proxies L = {n_auto} outside [1, 8]")
+    if auto and n_auto < 1:
+        raise ValueError(f"number of automatic proxies L = {n_auto} < 1")
+    wide = (n_auto if auto else Z.cols) > 8                           # beyond the one-launch window kernel: per-window fits
     # NaN input without pls takes the same matrix passes as clean input (Tprf3.scala:883-943): a NaN in X or Z inside a
     # window spreads to that window's whole fit (every product it touches), a NaN in y only removes its row from pass 3
     # (nanOls, :929-931); `hasNan` just switches the column std to the NaN-aware one (:1078-1080)
     T = y.rows
-    oos_batched = procedure != "IS Full" and not eff_pls              # um_tprf_oos_windows standardises the panel itself
+    oos_batched = procedure != "IS Full" and not eff_pls and not wide # um_tprf_oos_windows standardises the panel itself
     has_nan = False if oos_batched else bool(X.isnan().any() or y.isnan().any() or (not auto and Z.isnan().any()))
     Xn = None if oos_batched else X / (_nan_std_cols(X) if (eff_pls or has_nan) else _std_cols(X))   # Tprf3.scala:1080-1081
 
@@ -352,7 +361,7 @@ def estimate3prf(y: Mat, X: Mat, Z: Union[Mat, int], procedure: str = "IS Full",
     win, min_nona, gap = (int(v) for v in rollwin)
     fore = np.full((T, 1), np.nan)
     roll = np.full((T, 1), np.nan)
-    if not eff_pls:
+    if oos_batched:
         # every window of the procedure in ONE launch (um_tprf_oos_windows: one CTA per window, no per-window
         # synchronisation) -- the reference's `.par` loop over the windows (:1117,1151,1177)
         if procedure == "OOS Cross Val":                             # the window drops rows [lo, hi), :1112-1146
