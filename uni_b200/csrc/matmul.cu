@@ -74,6 +74,27 @@ __device__ __forceinline__ void stage_tile(double* sm, const double* __restrict_
   }
 }
 
+// One pass of stage_tile's loop (iteration `it` of TOTAL / MM_THREADS): the main loop spreads the copies of the next
+// k-tile between the DMMA batches of the current one, so the two warps of a sub-partition never spend the start of a
+// k-tile on address arithmetic together with the tensor pipe idle.
+template <int TILE, bool KMAJOR, bool VEC16>
+__device__ __forceinline__ void stage_tile_part(double* sm, const double* __restrict__ p, i64 ld, i64 o0, i64 i0,
+                                                i64 o_lim, i64 i_lim, int tid, int it) {
+  constexpr int INNER = KMAJOR ? MM_BK : TILE;
+  constexpr int PITCH = KMAJOR ? MM_PK : MMShape<TILE>::PMN;
+  constexpr int CH = VEC16 ? 2 : 1;
+  constexpr int CPR = INNER / CH;
+  const int c = tid + it * MM_THREADS;
+  int o = c / CPR, i = (c % CPR) * CH;
+  i64 go = o0 + o, gi = i0 + i;
+  i64 rem = (go < o_lim) ? (i_lim - gi) : 0;
+  int nvalid = rem <= 0 ? 0 : (rem >= CH ? CH : (int)rem);
+  const double* src = nvalid ? (p + go * ld + gi) : p;
+  double* dst = sm + o * PITCH + i;
+  if (VEC16) cp_async16(dst, src, nvalid * 8);
+  else cp_async8(dst, src, nvalid * 8);
+}
+
 // C[m][n] = sum_k A(m,k) B(k,n).  A(m,k) = pa[m*a_rs + k*a_cs] with one of the strides == 1,
 // same for B.  AK: A is k-contiguous (a_cs == 1); BK_: B is k-contiguous (b_rs == 1).
 template <int TILE, bool AK, bool BKM, bool VEC16>
@@ -110,15 +131,30 @@ k_dgemm(const double* __restrict__ pa, i64 lda, const double* __restrict__ pb, i
     cp_async_commit();
   }
 
+  // copies of one operand tile per thread, and how many of the 2 * ITERS (A then B) go after each of the 4 k-steps
+  constexpr int ITERS = TILE * MM_BK / (VEC16 ? 2 : 1) / MM_THREADS;
+  constexpr int PER = 2 * ITERS / (MM_BK / 4);
+  static_assert(2 * ITERS % (MM_BK / 4) == 0, "staging units must split evenly over the k-steps");
+  auto stage_part = [&](int s, int kt, int u) {
+    double* sa = smem + (size_t)s * 2 * MM_TILE_ELEMS;
+    double* sb = sa + MM_TILE_ELEMS;
+    const i64 k0 = (i64)kt * MM_BK;
+    if (u < ITERS) {
+      if (AK) stage_tile_part<TILE, true, VEC16>(sa, pa, lda, m0, k0, M, K, tid, u);
+      else stage_tile_part<TILE, false, VEC16>(sa, pa, lda, k0, m0, K, M, tid, u);
+    } else {
+      if (BKM) stage_tile_part<TILE, true, VEC16>(sb, pb, ldb, n0, k0, N, K, tid, u - ITERS);
+      else stage_tile_part<TILE, false, VEC16>(sb, pb, ldb, k0, n0, K, N, tid, u - ITERS);
+    }
+  };
+
   const int fr = lane >> 2, fk = lane & 3;  // fragment row (m or n) and k index
   for (int kt = 0; kt < KT; ++kt) {
     cp_async_wait<MM_STAGES - 2>();
     __syncthreads();
-    {
-      int nk = kt + MM_STAGES - 1;
-      if (nk < KT) stage(nk % MM_STAGES, nk);
-      cp_async_commit();
-    }
+    const int nk = kt + MM_STAGES - 1;
+    const bool more = nk < KT;
+    const int ns = nk % MM_STAGES;   // the stage read in iteration kt - 1: free since the barrier above
     const double* sa = smem + (size_t)(kt % MM_STAGES) * 2 * MM_TILE_ELEMS;
     const double* sb = sa + MM_TILE_ELEMS;
 #pragma unroll
@@ -135,10 +171,16 @@ k_dgemm(const double* __restrict__ pa, i64 lda, const double* __restrict__ pb, i
         bf[j] = BKM ? sb[n * MM_PK + kk + fk] : sb[(kk + fk) * MM_PMN + n];
       }
 #pragma unroll
-      for (int i = 0; i < MI; ++i)
+      for (int i = 0; i < MI; ++i) {
 #pragma unroll
         for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        if (i == MI / 2 - 1 && more) {
+#pragma unroll
+          for (int u = 0; u < PER; ++u) stage_part(ns, nk, (kk / 4) * PER + u);
+        }
+      }
     }
+    cp_async_commit();
   }
   cp_async_wait<0>();
 
