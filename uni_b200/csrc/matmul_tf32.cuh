@@ -8,9 +8,9 @@
 //
 // One CTA (192 threads) per 128 x 128 tile of C, K in blocks of 32 floats (= one 128-byte swizzle row):
 //   warp 0      TMA producer: A tile 128 x 32 (K-major) and B tile 32 x 128 (four 32 x 32 boxes, N-major as it
-//               lies in memory), SWIZZLE_128B, 2-stage ring, `full` mbarriers
-//   warps 2-5   splitter: A is rewritten in place to `hi` with `lo` beside it (element-wise, so the swizzle does
-//               not matter); B is TRANSPOSED on the way into K-major swizzled hi / lo tiles (an N-major TF32
+//               lies in memory), SWIZZLE_128B, into a 3-entry landing ring, `full` mbarriers
+//   warps 2-9   splitter (two per SM sub-partition): landing entry -> 2-stage operand ring; A as `hi` with `lo`
+//               beside it (element-wise, so the swizzle does not matter); B is TRANSPOSED on the way into K-major swizzled hi / lo tiles (an N-major TF32
 //               operand made tcgen05.mma return zeros on this part: measured, so both operands are fed
 //               K-major); fence.proxy.async, `ready` mbarrier; afterwards the epilogue: tcgen05.ld of the
 //               128 x 128 FP32 accumulator -> global memory
@@ -27,13 +27,17 @@ namespace tf32 {
 constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int STAGES = 2;
 constexpr int TILE_BYTES = BM * BK * 4;                    // 16384: A tile; B tile has the same size
-constexpr int STAGE_BYTES = 5 * TILE_BYTES;                // A_hi | A_lo | B_hi | B_lo | B as landed
-constexpr int OFF_BAR = STAGES * STAGE_BYTES;              // full[2] ready[2] empty[2] acc_full[2] acc_free[2]
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;                // operand ring entry: A_hi | A_lo | B_hi | B_lo
+constexpr int NRAW = 3;                                    // landing ring (TMA destinations): A | B as they lie in memory
+constexpr int RAW_BYTES = 2 * TILE_BYTES;
+constexpr int OFF_RAW = STAGES * STAGE_BYTES;
+constexpr int OFF_BAR = OFF_RAW + NRAW * RAW_BYTES;        // raw_full[3] raw_empty[3] ready[2] empty[2] acc_full[2] acc_free[2]
 constexpr int CHUNK = 4;                                   // k-blocks accumulated in tensor memory before promotion to registers
 constexpr int OFF_TMEM = OFF_BAR + 16 * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;
-constexpr int NTHREADS = 192;
+constexpr int NSPLIT = 256;                                // splitter / epilogue threads: 8 warps, two per SM sub-partition
+constexpr int NTHREADS = 64 + NSPLIT;
 
 __device__ __forceinline__ unsigned sa(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mb_init(unsigned bar, int count) {
@@ -86,11 +90,12 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const unsigned s0 = sa(smem);
   const unsigned bar0 = s0 + OFF_BAR;
-  auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_ready = [&](int s) { return bar0 + 8u * (2 + s); };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (4 + s); };
-  auto bar_acc_full = [&](int b) { return bar0 + 8u * (6 + b); };
-  auto bar_acc_free = [&](int b) { return bar0 + 8u * (8 + b); };
+  auto bar_full = [&](int r) { return bar0 + 8u * r; };                  // landing entry r holds block kb (TMA bytes)
+  auto bar_raw_empty = [&](int r) { return bar0 + 8u * (NRAW + r); };    // every splitter thread has read entry r
+  auto bar_ready = [&](int s) { return bar0 + 8u * (2 * NRAW + s); };    // operand stage s is split and visible to the tensor core
+  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * NRAW + 2 + s); };  // the MMAs that read operand stage s have retired
+  auto bar_acc_full = [&](int b) { return bar0 + 8u * (2 * NRAW + 4 + b); };
+  auto bar_acc_free = [&](int b) { return bar0 + 8u * (2 * NRAW + 6 + b); };
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + OFF_TMEM);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -100,14 +105,17 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
+    for (int r = 0; r < NRAW; ++r) {
+      mb_init(bar_full(r), 1);
+      mb_init(bar_raw_empty(r), NSPLIT);
+    }
     for (int s = 0; s < STAGES; ++s) {
-      mb_init(bar_full(s), 1);
-      mb_init(bar_ready(s), 128);
+      mb_init(bar_ready(s), NSPLIT);
       mb_init(bar_empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mb_init(bar_acc_full(b), 1);
-      mb_init(bar_acc_free(b), 128);
+      mb_init(bar_acc_free(b), NSPLIT);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -118,15 +126,18 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
+      // The landing ring is released by the splitters, not by the MMAs: the loads run NRAW blocks ahead of the
+      // split instead of waiting for the tensor core to retire a stage (with one ring for both, a k-block cost
+      // (TMA latency + split + MMA) / 2)
       for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % STAGES;
-        if (kb >= STAGES) mb_wait(bar_empty(s), (unsigned)((kb / STAGES - 1) & 1));
-        mb_expect_tx(bar_full(s), 2 * TILE_BYTES);
-        const unsigned st = s0 + (unsigned)s * STAGE_BYTES;
-        tma_2d(st, &map_a, kb * BK, m0, bar_full(s));                                // A: [128 rows m][32 k]
+        const int r = kb % NRAW;
+        if (kb >= NRAW) mb_wait(bar_raw_empty(r), (unsigned)((kb / NRAW - 1) & 1));
+        mb_expect_tx(bar_full(r), 2 * TILE_BYTES);
+        const unsigned st = s0 + OFF_RAW + (unsigned)r * RAW_BYTES;
+        tma_2d(st, &map_a, kb * BK, m0, bar_full(r));                                // A: [128 rows m][32 k]
 #pragma unroll
         for (int j = 0; j < 4; ++j)                                                 // B: 4 boxes of [32 rows k][32 n]
-          tma_2d(st + 4 * TILE_BYTES + j * 4096, &map_b, n0 + 32 * j, kb * BK, bar_full(s));
+          tma_2d(st + TILE_BYTES + j * 4096, &map_b, n0 + 32 * j, kb * BK, bar_full(r));
       }
     }
   } else if (warp == 1) {
@@ -164,17 +175,19 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ---- splitter: 128 threads, 2 x 4096 floats per stage ----
+    // ---- splitter: 256 threads, 2 x 4096 floats per stage ----
     const int t = tid - 64;
     const int q = warp & 3;            // the TMEM lane quarter this warp may access = 32 rows of the tile
-    float acc[BN];
+    const int half = (warp - 2) >> 2;  // two warps share a lane quarter: columns [64 half, 64 half + 64) of the tile each
+    constexpr int HN = BN / 2;
+    float acc[HN];
 #pragma unroll
-    for (int j = 0; j < BN; ++j) acc[j] = 0.0f;
-    auto add_tmem = [&](int col) {     // acc += 128 tensor-memory columns from `col` (this thread: one row)
+    for (int j = 0; j < HN; ++j) acc[j] = 0.0f;
+    auto add_tmem = [&](int col) {     // acc += this warp's 64 of the 128 tensor-memory columns from `col` (this thread: one row)
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < HN; c0 += 32) {
         unsigned r[32];
-        const unsigned taddr = tmem_d + ((unsigned)(32 * q) << 16) + (unsigned)(col + c0);
+        const unsigned taddr = tmem_d + ((unsigned)(32 * q) << 16) + (unsigned)(col + HN * half + c0);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
             "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\ttcgen05.wait::ld.sync.aligned;"
@@ -203,8 +216,15 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // chunk c is complete once the stage ring has moved STAGES blocks past its last block (the slot of that
       // block was refilled, so its MMAs have retired): promote it here, without ever waiting
       if (promoted < nchunks - 1 && kb >= (promoted + 1) * CHUNK + STAGES) promote(promoted++);
-      mb_wait(bar_full(s), (unsigned)((kb / STAGES) & 1));
+      const int r = kb % NRAW;
+      mb_wait(bar_full(r), (unsigned)((kb / NRAW) & 1));
+      if (kb >= STAGES) {   // the MMAs of block kb - STAGES have read this operand stage
+        mb_wait(bar_empty(s), (unsigned)((kb / STAGES - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
       unsigned char* stg = smem + (size_t)s * STAGE_BYTES;
+      const unsigned char* raw = smem + OFF_RAW + (size_t)r * RAW_BYTES;
+      const float4* araw = reinterpret_cast<const float4*>(raw);
       float4* hi = reinterpret_cast<float4*>(stg);
       float4* lo = reinterpret_cast<float4*>(stg + TILE_BYTES);
       // hi = x rounded to nearest TF32 (11 significant bits), lo = (x - hi) rounded to nearest TF32: with
@@ -215,19 +235,19 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         l.x = rn(x.x - h.x); l.y = rn(x.y - h.y); l.z = rn(x.z - h.z); l.w = rn(x.w - h.w);
       };
 #pragma unroll 4
-      for (int i = t; i < TILE_BYTES / 16; i += 128) {   // A: element-wise, in place
+      for (int i = t; i < TILE_BYTES / 16; i += NSPLIT) {   // A: element-wise (the swizzle does not matter)
         float4 h, l;
-        split4(hi[i], h, l);
+        split4(araw[i], h, l);
         hi[i] = h;
         lo[i] = l;
       }
       // B: landed as 4 boxes [32 k][32 n] (128-byte rows, 16-byte chunk c of row k at chunk c ^ (k & 7)); written
       // K-major [128 n][32 k] with the same swizzle rule on the row index n
-      const unsigned char* braw = stg + 4 * TILE_BYTES;
+      const unsigned char* braw = raw + TILE_BYTES;
       unsigned char* bhi = stg + 2 * TILE_BYTES;
       unsigned char* blo = stg + 3 * TILE_BYTES;
-#pragma unroll 2
-      for (int idx = t; idx < BN * (BK / 4); idx += 128) {
+#pragma unroll 4
+      for (int idx = t; idx < BN * (BK / 4); idx += NSPLIT) {
         const int n = idx & (BN - 1), kc = idx >> 7;   // consecutive threads: consecutive n, same 4 k's
         const unsigned char* src = braw + (n >> 5) * 4096 + (n & 3) * 4;
         const int nc = (n & 31) >> 2;
@@ -244,6 +264,7 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       mb_arrive(bar_ready(s));
+      mb_arrive(bar_raw_empty(r));
     }
     // ---- epilogue: the remaining chunks, then this thread's row of C ----
     while (promoted < nchunks) promote(promoted++);
@@ -251,10 +272,11 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // edge tiles: TMA zero-filled what lies outside A and B, only the stores need the bounds (N % 4 == 0)
     const int row = m0 + 32 * q + lane;
     if (row < M) {
-      float* crow = C + (i64)row * ldc + n0;
+      const int nh = n0 + HN * half;
+      float* crow = C + (i64)row * ldc + nh;
 #pragma unroll
-      for (int j = 0; j < BN; j += 4)
-        if (n0 + j < N) *reinterpret_cast<float4*>(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      for (int j = 0; j < HN; j += 4)
+        if (nh + j < N) *reinterpret_cast<float4*>(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
