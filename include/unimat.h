@@ -239,9 +239,11 @@ int32_t um_matmul(const um_view* a, const um_view* b, const um_view* out);
 /* FP32 `*@` kernel choice (the reference's uni.mat.blas switch, Mat.scala:299-335, picks between a BLAS
  * sgemm and matmulPure in the same way): 0 = automatic (row-major, 16-byte aligned operands whose
  * pitches and N are multiples of 4, M*N*K >= 2^18, run 3xTF32 on the tcgen05 tensor cores with FP32
- * promotion every 128 k, partial tiles zero-filled by TMA; everything else on the FFMA kernel), 1 = FFMA kernel only, 2 = tensor-core kernel or
- * UM_ERR_ARG.  Process-wide; for tests and profiling.  UM_MATF_TENSOR=0 in the environment makes
- * automatic mean 1. */
+ * promotion every 128 k, partial tiles zero-filled by TMA; everything else on the FFMA kernel; from 2^30 multiply-adds up the
+ * hi / lo operands are split once in global memory -- a temporary of 8 (M + N) K bytes from the pool -- instead of in shared
+ * memory, same bits), 1 = FFMA kernel only, 2 = tensor-core kernel with the split in shared memory or UM_ERR_ARG,
+ * 3 = tensor-core kernel with the split in global memory or UM_ERR_ARG.  Process-wide; for tests and profiling.
+ * UM_MATF_TENSOR=0 in the environment makes automatic mean 1. */
 int32_t um_matmul_set_f32_path(int32_t path);
 /* FP64 `*@` CTA tile: 0 = automatic (64 x 64 tiles, two CTAs per SM, whenever 128 x 128 tiles would leave SMs idle
  * or a mostly empty last wave -- 1024^2 and 2048^2 of BASELINE config 3; 128 x 128 otherwise), 64 / 128 = forced.

@@ -594,6 +594,15 @@ def test_matf_matmul_tensor_core_path(u, mkn):
             dev(u, a.T.copy()).T @ db
         with pytest.raises(ValueError):
             dev(u, big)._raw_slice(8, M + 8, 3, K + 3) @ db
+        # operands split once in global memory (what automatic takes from 2^30 multiply-adds up): the same bits
+        u.set_matf_matmul_path(3)
+        got_p = (da @ db).to_numpy()
+        got_pv = (dev(u, big)._raw_slice(8, M + 8, 4, K + 4) @ db).to_numpy()
+        ragged = (dev(u, big)._raw_slice(8, M + 8, 4, K + 1) @ dev(u, b[: K - 3])).to_numpy() if K > 3 else None   # K % 4 != 0
+        with pytest.raises(ValueError):
+            dev(u, a.T.copy()).T @ db
+        u.set_matf_matmul_path(2)
+        ragged_t = (dev(u, big)._raw_slice(8, M + 8, 4, K + 1) @ dev(u, b[: K - 3])).to_numpy() if K > 3 else None
         u.set_matf_matmul_path(1)
         got_c = (da @ db).to_numpy()
         u.set_matf_matmul_path(0)
@@ -605,6 +614,10 @@ def test_matf_matmul_tensor_core_path(u, mkn):
     assert np.all(np.abs(got_t - want) <= bound)
     assert np.max(np.abs(got_t - want)) <= 6e-6 * np.sqrt(K)
     assert np.max(np.abs(got_v - want_v)) <= 6e-6 * np.sqrt(K)
+    assert np.array_equal(got_p, got_t) and np.array_equal(got_pv, got_v), "split in global memory = split in shared memory, bit for bit"
+    if ragged is not None:
+        assert np.array_equal(ragged, ragged_t)
+        assert np.max(np.abs(ragged - big[8 : M + 8, 4 : K + 1].astype(np.float64) @ b[: K - 3].astype(np.float64))) <= 6e-6 * np.sqrt(K)
     assert np.array_equal(got_auto, got_t), "automatic choice = tensor path for tile-multiple row-major operands"
     assert np.array_equal(got_auto_t, got_c)
     np.testing.assert_allclose(got_t, got_c, rtol=1e-4, atol=1e-5 * np.sqrt(K))

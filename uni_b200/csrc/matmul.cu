@@ -343,7 +343,7 @@ using namespace um;
 static int g_f32_path = 0;   // um_matmul_set_f32_path
 
 extern "C" int32_t um_matmul_set_f32_path(int32_t path) {
-  if (path < 0 || path > 2) return um::fail(UM_ERR_ARG, "um_matmul_set_f32_path: 0 auto, 1 CUDA cores, 2 tensor cores");
+  if (path < 0 || path > 3) return um::fail(UM_ERR_ARG, "um_matmul_set_f32_path: 0 auto, 1 CUDA cores, 2 tensor cores (operands split in shared memory), 3 tensor cores (operands split once in global memory)");
   g_f32_path = path;
   return UM_OK;
 }
@@ -395,10 +395,10 @@ extern "C" int32_t um_matmul(const um_view* a, const um_view* b, const um_view* 
     // row-major, 16-byte aligned operands: 3xTF32 on the tcgen05 tensor cores (matmul_tf32.cuh)
     static const bool tensor_ok = [] { const char* e = getenv("UM_MATF_TENSOR"); return !(e && e[0] == '0'); }();
     const int path = g_f32_path;
-    if (path == 2 || (path == 0 && tensor_ok)) {
-      int r = (A.cs == 1 && B.cs == 1) ? tf32::launch(A.p, A.rs, B.p, B.rs, pc, ldc, M, N, K) : -1;
+    if (path >= 2 || (path == 0 && tensor_ok)) {
+      int r = (A.cs == 1 && B.cs == 1) ? tf32::launch(A.p, A.rs, B.p, B.rs, pc, ldc, M, N, K, path) : -1;
       if (r != -1) return r;
-      if (path == 2) return fail(UM_ERR_ARG, "matmul: operands do not fit the tensor-core FP32 kernel (row-major, 16-byte aligned, pitches and N multiples of 4, M*N*K >= 2^18)");
+      if (path >= 2) return fail(UM_ERR_ARG, "matmul: operands do not fit the tensor-core FP32 kernel (row-major, 16-byte aligned, pitches and N multiples of 4, M*N*K >= 2^18)");
     }
     dim3 grid((unsigned)((N + SG_BN - 1) / SG_BN), (unsigned)((M + SG_BM - 1) / SG_BM));
     k_sgemm<<<grid, 256, 0, ctx()->stream>>>(A, B, pc, ldc, M, N, K);

@@ -18,6 +18,16 @@
 //               tcgen05.commit frees the stage / hands the accumulator to the epilogue
 // Operands must be row-contiguous, 16-byte aligned, with M, N multiples of 128 and K a multiple of 32;
 // everything else stays on the register-tiled FFMA kernel.
+//
+// From 2^30 multiply-adds up the split does not happen in shared memory at all (k_sgemm_tf32x3<true>): k_split_a /
+// k_split_bt write A_hi, A_lo and the TRANSPOSED B_hi', B_lo' to global memory once (12 bytes of traffic per operand
+// element, 3 % of the product's time at 8192^3), and the product kernel is TMA -> three 64 KB operand stages -> MMA,
+// with warps 2-9 left to promote and store.  Shared-memory traffic per k-block falls from 224 KB (TMA 32 + split
+// 32 + 64 + MMA reads 96) to 160 KB, the splitter's barriers disappear, and the bound moves to the L2: 64 KB per
+// k-block and CTA is 1 500 clocks at the ~6 300 B / clk the L2 delivers to 148 SMs.  Results are bit-identical
+// to the shared-memory split (same rounding, same MMA order; tools/matf_paths.py).  Tiles are rasterised in bands
+// of 8 tile rows so that the resident CTAs share their A and B panels in L2 (16384^3: 133 -> 143 TFLOP/s for the
+// shared-memory split).
 #pragma once
 #include <cuda.h>
 
@@ -36,6 +46,7 @@ constexpr int CHUNK = 4;                                   // k-blocks accumulat
 constexpr int OFF_TMEM = OFF_BAR + 16 * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;
+constexpr int RASTER = 8;                                  // tile rows per rasterisation band
 constexpr int NSPLIT = 256;                                // splitter / epilogue threads: 8 warps, two per SM sub-partition
 constexpr int NTHREADS = 64 + NSPLIT;
 
@@ -83,9 +94,14 @@ __device__ __forceinline__ void umma_commit(unsigned bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// PRE = the operands arrive already split and K-major (k_split_a / k_split_bt below wrote A_hi, A_lo, B_hi', B_lo' to
+// global memory): the TMA fills the operand ring directly (three 64 KB stages, map_a / map_a2 = A_hi / A_lo, map_b /
+// map_b2 = B_hi' / B_lo'), nothing is split in shared memory and warps 2-9 only promote and store.
+template <bool PRE>
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float* __restrict__ C, i64 ldc,
-               int kblocks, int M, int N) {
+k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2, float* __restrict__ C, i64 ldc,
+               int kblocks, int M, int N, int tiles_m, int tiles_n) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const unsigned s0 = sa(smem);
@@ -98,7 +114,17 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   auto bar_acc_free = [&](int b) { return bar0 + 8u * (2 * NRAW + 6 + b); };
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + OFF_TMEM);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // tiles in bands of RASTER tile rows, column by column inside a band: the CTAs resident at one time share RASTER
+  // row panels of A and ~148 / RASTER column panels of B in L2 (row-major order re-read all of B per tile row)
+  int tm, tn;
+  {
+    const int bid = (int)blockIdx.x, band = bid / (RASTER * tiles_n), rem = bid % (RASTER * tiles_n);
+    const int rows = tiles_m - band * RASTER < RASTER ? tiles_m - band * RASTER : RASTER;
+    tm = band * RASTER + rem % rows;
+    tn = rem / rows;
+  }
+  const int m0 = tm * BM, n0 = tn * BN;
+  constexpr int PSTAGES = 3;   // PRE: operand ring entries
 
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sa(tmem_slot)), "r"(512) : "memory");
@@ -107,7 +133,7 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (tid == 0) {
     for (int r = 0; r < NRAW; ++r) {
       mb_init(bar_full(r), 1);
-      mb_init(bar_raw_empty(r), NSPLIT);
+      mb_init(bar_raw_empty(r), PRE ? 1 : NSPLIT);   // PRE: operand stage r, released by the MMA warp's commit
     }
     for (int s = 0; s < STAGES; ++s) {
       mb_init(bar_ready(s), NSPLIT);
@@ -129,6 +155,18 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // The landing ring is released by the splitters, not by the MMAs: the loads run NRAW blocks ahead of the
       // split instead of waiting for the tensor core to retire a stage (with one ring for both, a k-block cost
       // (TMA latency + split + MMA) / 2)
+      if (PRE) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int s = kb % PSTAGES;
+          if (kb >= PSTAGES) mb_wait(bar_raw_empty(s), (unsigned)((kb / PSTAGES - 1) & 1));
+          mb_expect_tx(bar_full(s), 4 * TILE_BYTES);
+          const unsigned st = s0 + (unsigned)s * STAGE_BYTES;
+          tma_2d(st, &map_a, kb * BK, m0, bar_full(s));
+          tma_2d(st + TILE_BYTES, &map_a2, kb * BK, m0, bar_full(s));
+          tma_2d(st + 2 * TILE_BYTES, &map_b, kb * BK, n0, bar_full(s));
+          tma_2d(st + 3 * TILE_BYTES, &map_b2, kb * BK, n0, bar_full(s));
+        }
+      } else
       for (int kb = 0; kb < kblocks; ++kb) {
         const int r = kb % NRAW;
         if (kb >= NRAW) mb_wait(bar_raw_empty(r), (unsigned)((kb / NRAW - 1) & 1));
@@ -151,14 +189,15 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // truncating add per 8 k instead of three.
       const unsigned tmem_corr = tmem_d + 2u * BN;
       for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % STAGES;
+        const int s = kb % (PRE ? PSTAGES : STAGES);
         const int chunk = kb / CHUNK, buf = chunk & 1;
         if (kb % CHUNK == 0 && chunk >= 2) {
           mb_wait(bar_acc_free(buf), (unsigned)((chunk / 2 - 1) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const unsigned tmem_acc = tmem_d + (unsigned)(buf * BN);
-        mb_wait(bar_ready(s), (unsigned)((kb / STAGES) & 1));
+        if (PRE) mb_wait(bar_full(s), (unsigned)((kb / PSTAGES) & 1));
+        else mb_wait(bar_ready(s), (unsigned)((kb / STAGES) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const unsigned st = s0 + (unsigned)s * STAGE_BYTES;
         const unsigned a_hi = st, a_lo = st + TILE_BYTES, b_hi = st + 2 * TILE_BYTES, b_lo = st + 3 * TILE_BYTES;
@@ -170,7 +209,7 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           umma_tf32(tmem_corr, dah, dbl, (kb | kk) ? 1u : 0u);
           umma_tf32(tmem_corr, dal, dbh, 1u);
         }
-        umma_commit(bar_empty(s));   // the stage may be refilled once these MMAs have read it
+        umma_commit(PRE ? bar_raw_empty(s) : bar_empty(s));   // the stage may be refilled once these MMAs have read it
         if (kb % CHUNK == CHUNK - 1 || kb == kblocks - 1) umma_commit(bar_acc_full(buf));
       }
     }
@@ -211,6 +250,7 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     };
     const int nchunks = (kblocks + CHUNK - 1) / CHUNK;
     int promoted = 0;
+    if (!PRE)
     for (int kb = 0; kb < kblocks; ++kb) {
       const int s = kb % STAGES;
       // chunk c is complete once the stage ring has moved STAGES blocks past its last block (the slot of that
@@ -285,6 +325,56 @@ k_sgemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512) : "memory");
 }
 
+// ---- pre-pass of the PRE kernel: operands split once, in global memory ----
+__device__ __forceinline__ float rn_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+
+// A (M x K, pitch lda, 16-byte aligned rows) -> hi, lo (M x Kp, Kp = K rounded up to 4; the pad is zero)
+__global__ void __launch_bounds__(256) k_split_a(const float* __restrict__ A, i64 lda, i64 M, i64 K, i64 Kp, float* __restrict__ hi,
+                                                  float* __restrict__ lo) {
+  const i64 cpr = Kp >> 2, total = M * cpr;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
+    const i64 m = i / cpr, k = (i % cpr) << 2;
+    float4 x;
+    if (k + 4 <= K) x = *reinterpret_cast<const float4*>(A + m * lda + k);
+    else {
+      const float* r = A + m * lda;
+      x.x = k < K ? r[k] : 0.0f; x.y = k + 1 < K ? r[k + 1] : 0.0f; x.z = k + 2 < K ? r[k + 2] : 0.0f; x.w = 0.0f;
+    }
+    float4 h, l;
+    h.x = rn_tf32(x.x); h.y = rn_tf32(x.y); h.z = rn_tf32(x.z); h.w = rn_tf32(x.w);
+    l.x = rn_tf32(x.x - h.x); l.y = rn_tf32(x.y - h.y); l.z = rn_tf32(x.z - h.z); l.w = rn_tf32(x.w - h.w);
+    *reinterpret_cast<float4*>(hi + m * Kp + k) = h;
+    *reinterpret_cast<float4*>(lo + m * Kp + k) = l;
+  }
+}
+
+// B (K x N, pitch ldb) -> hi', lo' (N x Kp): transposed through a 32 x 33 shared-memory tile, both sides coalesced
+__global__ void __launch_bounds__(256) k_split_bt(const float* __restrict__ B, i64 ldb, i64 K, i64 N, i64 Kp, float* __restrict__ hi,
+                                                   float* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const i64 tiles_n = (N + 31) >> 5, tiles_k = (Kp + 31) >> 5, total = tiles_n * tiles_k;
+  for (i64 t = blockIdx.x; t < total; t += gridDim.x) {
+    const i64 n0 = (t % tiles_n) << 5, k0 = (t / tiles_n) << 5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const i64 k = k0 + ty + 8 * j, n = n0 + tx;
+      tile[ty + 8 * j][tx] = (k < K && n < N) ? B[k * ldb + n] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const i64 n = n0 + ty + 8 * j, k = k0 + tx;
+      if (n < N && k < Kp) {
+        const float x = tile[tx][ty + 8 * j], h = rn_tf32(x);
+        hi[n * Kp + k] = h;
+        lo[n * Kp + k] = rn_tf32(x - h);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -303,7 +393,10 @@ inline EncodeTiledFn encode_fn() {
 }
 
 // returns UM_OK if launched, -1 if the shape / layout is not eligible (caller falls back to the FFMA kernel)
-inline int launch(const float* A, i64 lda, const float* B, i64 ldb, float* C, i64 ldc, i64 M, i64 N, i64 K) {
+// mode: 0 = automatic (operands split once in global memory from PRE_MIN_WORK multiply-adds up, in shared memory below),
+// 2 = split in shared memory, 3 = split in global memory
+constexpr double PRE_MIN_WORK = 1073741824.0;   // 2^30 = 1024^3: measured faster from there up, pre-pass included
+inline int launch(const float* A, i64 lda, const float* B, i64 ldb, float* C, i64 ldc, i64 M, i64 N, i64 K, int mode) {
   // any M and K (partial tiles are zero-filled by TMA), N a multiple of 4 (16-byte stores); products under 2^18 multiply-adds stay on the FFMA kernel
   if (M <= 0 || N <= 0 || K <= 0 || (N % 4) || (double)M * (double)N * (double)K < 262144.0) return -1;
   if (!aligned16(A) || !aligned16(B) || !aligned16(C) || (lda % 4) || (ldb % 4) || (ldc % 4)) return -1;
@@ -314,15 +407,54 @@ inline int launch(const float* A, i64 lda, const float* B, i64 ldb, float* C, i6
     std::lock_guard<std::mutex> plan_lock(plan_mutex());
     static bool attr = false;
     if (!attr) {
-      if (cudaFuncSetAttribute(k_sgemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC) != cudaSuccess) {
+      if (cudaFuncSetAttribute(k_sgemm_tf32x3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC) != cudaSuccess ||
+          cudaFuncSetAttribute(k_sgemm_tf32x3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC) != cudaSuccess) {
         cudaGetLastError();
         return -1;
       }
       attr = true;
     }
   }
+  const i64 tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  if (tiles_m * tiles_n > 0x7fffffff) return -1;
+  const int kblocks = (int)((K + BK - 1) / BK);
   CUtensorMap ma, mb;
   cuuint32_t es[2] = {1, 1};
+  if (mode == 3 || (mode == 0 && (double)M * (double)N * (double)K >= PRE_MIN_WORK)) {
+    // ---- operands split (and B transposed) once, in global memory; the product kernel is then TMA -> MMA only ----
+    const i64 Kp = (K + 3) & ~i64(3);
+    void* tmp = nullptr;
+    const size_t a_elems = (size_t)M * Kp, b_elems = (size_t)N * Kp;
+    if (um_malloc((2 * a_elems + 2 * b_elems) * sizeof(float), &tmp) != UM_OK) return UM_ERR_OOM;
+    float* a_hi = static_cast<float*>(tmp);
+    float* a_lo = a_hi + a_elems;
+    float* b_hi = a_lo + a_elems;
+    float* b_lo = b_hi + b_elems;
+    const int sms = ctx()->sm_count;
+    k_split_a<<<sms * 8, 256, 0, ctx()->stream>>>(A, lda, M, K, Kp, a_hi, a_lo);
+    k_split_bt<<<sms * 8, 256, 0, ctx()->stream>>>(B, ldb, K, N, Kp, b_hi, b_lo);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    CUtensorMap m4[4];
+    float* ptr[4] = {a_hi, a_lo, b_hi, b_lo};
+    bool ok = true;
+    for (int i = 0; i < 4 && ok; ++i) {
+      cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)(i < 2 ? M : N)};
+      cuuint64_t strides[1] = {(cuuint64_t)Kp * 4};
+      cuuint32_t box[2] = {BK, (cuuint32_t)(i < 2 ? BM : BN)};
+      ok = enc(&m4[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr[i], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    int rc = UM_OK;
+    if (ok) {
+      k_sgemm_tf32x3<true><<<(unsigned)(tiles_m * tiles_n), NTHREADS, SMEM_ALLOC, ctx()->stream>>>(m4[0], m4[2], m4[1], m4[3], C, ldc, kblocks, (int)M,
+                                                                                                 (int)N, (int)tiles_m, (int)tiles_n);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      if (cudaGetLastError() != cudaSuccess) rc = fail(UM_ERR_CUDA, "k_sgemm_tf32x3<pre-split> launch failed");
+    }
+    um_free(tmp);   // stream-ordered: after the product
+    if (!ok) return mode == 3 ? fail(UM_ERR_ARG, "matmul: tensor map for the pre-split operands rejected") : -1;
+    return rc;
+  }
   {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
     cuuint64_t strides[1] = {(cuuint64_t)lda * 4};
@@ -339,8 +471,8 @@ inline int launch(const float* A, i64 lda, const float* B, i64 ldb, float* C, i6
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return -1;
   }
-  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
-  k_sgemm_tf32x3<<<grid, NTHREADS, SMEM_ALLOC, ctx()->stream>>>(ma, mb, C, ldc, (int)((K + BK - 1) / BK), (int)M, (int)N);
+  k_sgemm_tf32x3<false><<<(unsigned)(tiles_m * tiles_n), NTHREADS, SMEM_ALLOC, ctx()->stream>>>(ma, mb, ma, mb, C, ldc, kblocks, (int)M,
+                                                                                            (int)N, (int)tiles_m, (int)tiles_n);
   UM_LAUNCHED();
   return UM_OK;
 }

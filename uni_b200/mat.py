@@ -641,7 +641,8 @@ MATF_PATH_AUTO, MATF_PATH_CUDA_CORES, MATF_PATH_TENSOR = 0, 1, 2
 
 def set_matf_matmul_path(path: int) -> None:
     """FP32 `@` kernel choice (um_matmul_set_f32_path; the counterpart of the reference's uni.mat.blas
-    switch, Mat.scala:299-335): 0 = automatic, 1 = FFMA kernel only, 2 = tcgen05 3xTF32 kernel or ValueError."""
+    switch, Mat.scala:299-335): 0 = automatic, 1 = FFMA kernel only, 2 = tcgen05 3xTF32 kernel with the hi / lo split in shared memory or ValueError,
+    3 = the same kernel with the operands split once in global memory (what automatic picks from 2^30 multiply-adds up)."""
     check(lib.um_matmul_set_f32_path(int(path)))
 
 
