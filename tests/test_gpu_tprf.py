@@ -150,7 +150,7 @@ def test_all_outputs_vs_oracle(u, tnl):
     assert np.array_equal(c2.forecasts.to_numpy(), c.forecasts.to_numpy())
 
 
-WIDE_SHAPES = [(60, 40, 9), (120, 300, 12), (200, 64, 16), (512, 2048, 10), (1000, 130, 24), (40, 100, 9)]
+WIDE_SHAPES = [(60, 40, 9), (120, 300, 12), (200, 64, 16), (512, 2048, 10), (1000, 130, 24), (40, 100, 9), (1100, 1300, 17), (300, 4096, 33)]
 
 
 @pytest.mark.parametrize("tnl", WIDE_SHAPES)

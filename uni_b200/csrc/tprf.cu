@@ -923,8 +923,6 @@ __global__ void k_fill_nan(double* p, i64 n) {
 #include "tprf_grid.cuh"
 namespace um {
 
-int tprf_fit_wide(int mode, const um_view* y, const um_view* X, const um_view* Z, um_tprf_out* out);  // tprf_wide.cu, L > LP
-
 // ---- host orchestration ------------------------------------------------------------------------------------------
 static i64 cdiv(i64 a, i64 b) { return (a + b - 1) / b; }
 static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
@@ -1453,6 +1451,65 @@ static int host_result_block(double** host, double** dev) {
   return UM_OK;
 }
 
+// L > LP: the accumulators are column-separable in Z, so the fused sweep runs once per group of 8 proxies (X is read
+// ceil(L / 8) times) and its W0 / PX blocks are copied out of the workspace before anything else may reuse it
+static int fit_wide(int mode, const um_view* y, const um_view* X, const um_view* Z, um_tprf_out* out) {
+  const i64 T = X->rows, N = X->cols, L = Z->cols;
+  const double* xp = static_cast<const double*>(X->data) + X->offset;
+  const i64 ldx = N == 1 ? 1 : X->rs;
+  const double* yp = static_cast<const double*>(y->data) + y->offset;
+  const double* zp = static_cast<const double*>(Z->data) + Z->offset;
+  auto even = [](i64 n) { return (n + 1) & ~i64(1); };
+  const i64 n_w0 = even(N * L), n_px = even(T * L), n_h0 = even(T), n_v = even(N);
+  void* blk = nullptr;
+  int s = um_malloc((size_t)(n_w0 + n_px + n_h0 + 2 * n_v) * 8, &blk);
+  if (s != UM_OK) return s;
+  struct Free { void* p; ~Free() { um_free(p); } } guard{blk};
+  double* base = static_cast<double*>(blk);
+  TprfWideAcc acc;
+  um_view_init(&acc.W0, base, N, L, UM_F64);
+  um_view_init(&acc.PX, base + n_w0, T, L, UM_F64);
+  um_view_init(&acc.h0, base + n_w0 + n_px, T, 1, UM_F64);
+  um_view_init(&acc.isd, base + n_w0 + n_px + n_h0, 1, N, UM_F64);
+  um_view_init(&acc.m, base + n_w0 + n_px + n_h0 + n_v, 1, N, UM_F64);
+  s = set_smem_attrs();
+  if (s != UM_OK) return s;
+  auto strided = [](double* p, i64 rows, i64 cols, i64 rs) {
+    um_view v;
+    um_view_init(&v, p, rows, cols, UM_F64);
+    v.rs = rs;
+    return v;
+  };
+  for (i64 g0 = 0; g0 < L; g0 += LP) {
+    const i64 Lg = L - g0 < LP ? L - g0 : LP;
+    Plan3 p = make_plan_for(T, N, Lg, 1, xp, ldx, 0);
+    char* ws = static_cast<char*>(scratch(p.total));
+    if (!ws) return UM_ERR_OOM;
+    s = run_prep(p, ws, zp + g0 * Z->cs, Z->rs, Z->cs, 0, yp, y->rs, 0);
+    if (s != UM_OK) return s;
+    s = run_sweeps(p, ws, xp, ldx, 0, 0);
+    if (s != UM_OK) return s;
+    double* packed = reinterpret_cast<double*>(ws + p.o_packed);
+    const um_view w_src = strided(reinterpret_cast<double*>(ws + p.o_w0), N, Lg, LP);
+    const um_view p_src = strided(packed, T, Lg, LP);
+    um_view w_dst, p_dst;
+    um_view_slice(&acc.W0, 0, N, g0, g0 + Lg, &w_dst, nullptr);
+    um_view_slice(&acc.PX, 0, T, g0, g0 + Lg, &p_dst, nullptr);
+    s = um_copy(&w_src, &w_dst);
+    if (s == UM_OK) s = um_copy(&p_src, &p_dst);
+    if (s == UM_OK && g0 == 0) {
+      const um_view h_src = strided(packed + T * LP, T, 1, 1);
+      const um_view i_src = strided(reinterpret_cast<double*>(ws + p.o_invsd), 1, N, N);
+      const um_view m_src = strided(reinterpret_cast<double*>(ws + p.o_mun), 1, N, N);
+      s = um_copy(&h_src, &acc.h0);
+      if (s == UM_OK) s = um_copy(&i_src, &acc.isd);
+      if (s == UM_OK) s = um_copy(&m_src, &acc.m);
+    }
+    if (s != UM_OK) return s;
+  }
+  return tprf_fit_wide(mode, y, Z, N, acc, out);
+}
+
 static int fill_nan(double* p, i64 n) {
   if (!p || n == 0) return UM_OK;
   k_fill_nan<<<(unsigned)cdiv(n, 256), 256, 0, ctx()->stream>>>(p, n);
@@ -1536,9 +1593,9 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
     return UM_OK;
   }
   if (L > LP) {
-    // more proxies than one DMMA fragment holds: the same accumulators from the library's own operators (tprf_wide.cu)
+    // more proxies than one DMMA fragment holds: one fused sweep per group of 8, finish by operators (tprf_wide.cu)
     if (sharded) return fail(UM_ERR_ARG, "column-sharded fits take L <= %d proxies (L = %lld)", LP, L);
-    const int sw = tprf_fit_wide(mode, y, X, Z, out);
+    const int sw = fit_wide(mode, y, X, Z, out);
     if (sw == UM_ERR_SINGULAR) {
       out->singular = 1;
       int sf = fill_nan(out->forecasts, T);

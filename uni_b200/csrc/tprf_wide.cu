@@ -1,14 +1,15 @@
-// tprf_wide.cu -- the 3PRF fits for MORE than 8 proxies (L > LP of tprf.cu).
+// tprf_wide.cu -- the finish of the 3PRF fits for MORE than 8 proxies (L > LP of tprf.cu).
 //
 // The reference's fits take any L (Tprf3.scala:199-289: `Z: MatD` of T x L).  The fused sweeps of tprf.cu keep the
-// proxies in the N = 8 dimension of one DMMA fragment; wider proxy sets are rare (Kelly-Pruitt use 1-3, the
-// reference's tests at most 5) and take this path instead: the SAME re-association (DESIGN.md section 4.1 -- the
-// accumulators W0, PX, h0, sw, SWW, smw, smu, never an N x N or N x T factor) spelled with the library's own device
-// operators -- three products over the panel (X'Zc, X V, X (1/sd)') on the FP64 tensor pipe (`*@`, matmul.cu), axis
-// reductions, broadcast elementwise ops and `.inverse` in the reference's LU order -- so X is read five times
-// instead of once.  Results: closed form (Tprf3.scala:199-209), the three OLS passes (:211-231,260-289), IS Full
-// (:883-943,1214-1250).  A singular small system surfaces as UM_ERR_SINGULAR exactly where the reference's
-// `.inverse` would throw (Mat.scala:990).
+// proxies in the N = 8 dimension of one DMMA fragment, and their finish kernel keeps every small system in registers
+// and shared memory sized for 8.  Wider proxy sets are rare (Kelly-Pruitt use 1-3, the reference's tests at most 5):
+// um_tprf_fit runs the fused sweep once per group of 8 proxies -- the accumulators of DESIGN.md section 4.1 are
+// column-separable in Z: W0 and PX group by group, h0 / 1/sd / mu/sd the same in every group -- and hands them to
+// this file, which forms the small sums (sw, SWW, smw, smu) and both finishes with the library's own device
+// operators (`*@` on the FP64 tensor pipe, axis reductions, broadcast elementwise ops, `.inverse` in the reference's
+// LU order).  X is read ceil(L / 8) times.  Results: closed form (Tprf3.scala:199-209), the three OLS passes
+// (:211-231,260-289), IS Full (:883-943,1214-1250).  A singular small system surfaces as UM_ERR_SINGULAR exactly where
+// the reference's `.inverse` would throw (Mat.scala:990).
 #include <cmath>
 #include <vector>
 
@@ -58,68 +59,100 @@ int out_or_tmp(Pool& pool, double* p, i64 r, i64 c, um_view* v) {
   return pool.mat(r, c, v);
 }
 
+// ---- out (m x n) = A' B for tall operands (A: K x m, B: K x n, K >> m, n): `*@` would give the whole contraction to
+// ONE CTA tile (36 ms at K = 262144); here every CTA takes a block of rows and writes its partial m x n, and the
+// partials are added by the library's fixed-tree axis reduction (run-to-run reproducible).
+constexpr int GR_ROWS = 16, GR_MAXW = 64, GR_THREADS = 256, GR_Q = 16;   // m, n <= 64 and m n <= 4096
+
+__global__ void __launch_bounds__(GR_THREADS) k_tall_gram(const double* __restrict__ A, i64 a_rs, i64 a_cs, int m,
+                                                          const double* __restrict__ B, i64 b_rs, i64 b_cs, int n, i64 K,
+                                                          i64 rows_per_cta, double* __restrict__ part) {
+  __shared__ double sa[GR_ROWS][GR_MAXW + 1], sb[GR_ROWS][GR_MAXW + 1];
+  const int tid = threadIdx.x, mn = m * n;
+  int oi[GR_Q], oj[GR_Q];
+  double acc[GR_Q];
+#pragma unroll
+  for (int q = 0; q < GR_Q; ++q) {
+    const int idx = tid + q * GR_THREADS;
+    oi[q] = idx < mn ? idx / n : 0;
+    oj[q] = idx < mn ? idx % n : 0;
+    acc[q] = 0.0;
+  }
+  const i64 k_lo = (i64)blockIdx.x * rows_per_cta;
+  const i64 k_hi = k_lo + rows_per_cta < K ? k_lo + rows_per_cta : K;
+  for (i64 k0 = k_lo; k0 < k_hi; k0 += GR_ROWS) {
+    for (int e = tid; e < GR_ROWS * m; e += GR_THREADS) {
+      const int r = e / m, i = e % m;
+      sa[r][i] = k0 + r < k_hi ? A[(k0 + r) * a_rs + i * a_cs] : 0.0;
+    }
+    for (int e = tid; e < GR_ROWS * n; e += GR_THREADS) {
+      const int r = e / n, j = e % n;
+      sb[r][j] = k0 + r < k_hi ? B[(k0 + r) * b_rs + j * b_cs] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < GR_Q; ++q) {
+      if (q * GR_THREADS < mn) {
+#pragma unroll
+        for (int r = 0; r < GR_ROWS; ++r) acc[q] = fma(sa[r][oi[q]], sb[r][oj[q]], acc[q]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < GR_Q; ++q) {
+    const int idx = tid + q * GR_THREADS;
+    if (idx < mn) part[(i64)blockIdx.x * mn + idx] = acc[q];
+  }
+}
+
+// out must be a contiguous m x n matrix
+int tall_gram(Pool& pool, const um_view& A, const um_view& B, const um_view& out) {
+  const i64 K = A.rows, m = A.cols, n = B.cols;
+  if (m > GR_MAXW || n > GR_MAXW || m * n > GR_Q * GR_THREADS || K < 256) {   // very wide proxy sets, short operands: the general product
+    const um_view At = tr(A);
+    return um_matmul(&At, &B, &out);
+  }
+  i64 rows = (K + 4 * ctx()->sm_count - 1) / (4 * ctx()->sm_count);
+  if (rows < 256) rows = 256;
+  rows = (rows + GR_ROWS - 1) / GR_ROWS * GR_ROWS;
+  const i64 ctas = (K + rows - 1) / rows;
+  um_view part, flat;
+  W_(pool.mat(ctas, m * n, &part));
+  k_tall_gram<<<(unsigned)ctas, GR_THREADS, 0, ctx()->stream>>>(static_cast<const double*>(A.data) + A.offset, A.rs, A.cs, (int)m,
+                                                                static_cast<const double*>(B.data) + B.offset, B.rs, B.cs, (int)n, K, rows,
+                                                                static_cast<double*>(part.data));
+  UM_LAUNCHED();
+  W_(um_view_init(&flat, static_cast<double*>(out.data) + out.offset, 1, m * n, UM_F64));
+  return um_reduce_axis(UM_SUM, &part, 0, &flat);
+}
+
 }  // namespace
 
-int tprf_fit_wide(int mode, const um_view* y, const um_view* X, const um_view* Z, um_tprf_out* out) {
-  const i64 T = X->rows, N = X->cols, L = Z->cols, D = L + 1;
+int tprf_fit_wide(int mode, const um_view* y, const um_view* Z, i64 N, const TprfWideAcc& acc, um_tprf_out* out) {
+  const i64 T = Z->rows, L = Z->cols, D = L + 1;
   Pool pool;
   const bool closed_wanted = mode == UM_TPRF_CLOSED || (mode == UM_TPRF_IS_FULL && out->alpha);
   const bool three_wanted = mode != UM_TPRF_CLOSED || out->phi || out->phi_hat || out->sigma || out->beta3;
-
-  // ---- column statistics: sample std (n <= 1 or sd == 0 -> 1, Tprf3.scala:469-502), mu/sd ----
-  um_view mu, sd, isd, m;
-  W_(pool.mat(1, N, &mu));
-  W_(out_or_tmp(pool, out->xstd, 1, N, &sd));
-  W_(pool.mat(1, N, &isd));
-  W_(pool.mat(1, N, &m));
-  W_(um_reduce_axis(UM_MEAN, X, 0, &mu));
-  if (T > 1) {
-    um_view zero_b, zero_f;
-    W_(pool.mat(1, N, &zero_b, UM_BOOL));
-    W_(pool.mat(1, N, &zero_f));
-    W_(um_reduce_axis(UM_STD, X, 0, &sd));                                      // population std
-    W_(um_binary_scalar(UM_MUL, &sd, std::sqrt((double)T / (double)(T - 1)), 0, &sd));
-    W_(um_compare_scalar(UM_EQ, &sd, 0.0, &zero_b));
-    W_(um_copy(&zero_b, &zero_f));                                              // 1.0 where sd == 0
-    W_(um_binary(UM_ADD, &sd, &zero_f, &sd));
-  } else {
-    W_(um_fill(&sd, 1.0));
+  // from the sweeps: W0 = diag(1/sd) (X - mu)' Zc (N x L), PX = Xn W0 (T x L), h0 = Xn 1 (T x 1), 1/sd and mu/sd (1 x N)
+  um_view W0 = acc.W0, PX = acc.PX, h0 = acc.h0, isd = acc.isd, m = acc.m;
+  if (out->xstd) {   // column sample std (n <= 1 or sd == 0 -> 1, Tprf3.scala:469-502)
+    um_view xs;
+    W_(um_view_init(&xs, out->xstd, 1, N, UM_F64));
+    W_(um_binary_scalar(UM_DIV, &isd, 1.0, 1, &xs));
   }
-  W_(um_binary_scalar(UM_DIV, &sd, 1.0, 1, &isd));                              // 1 / sd
-  W_(um_binary(UM_MUL, &mu, &isd, &m));
-  const um_view isd_t = tr(isd), mu_t = tr(mu);
 
   // ---- proxies centred; y centred ----
-  um_view zbar, Zc, csz, ybar, yc;
+  um_view zbar, Zc, ybar, yc, NL;
   W_(pool.mat(1, L, &zbar));
   W_(pool.mat(T, L, &Zc));
-  W_(pool.mat(1, L, &csz));
   W_(pool.mat(1, 1, &ybar));
   W_(pool.mat(T, 1, &yc));
+  W_(pool.mat(N, L, &NL));
   W_(um_reduce_axis(UM_MEAN, Z, 0, &zbar));
   W_(um_binary(UM_SUB, Z, &zbar, &Zc));
-  W_(um_reduce_axis(UM_SUM, &Zc, 0, &csz));
   W_(um_reduce_axis(UM_MEAN, y, 0, &ybar));
   W_(um_binary(UM_SUB, y, &ybar, &yc));
-
-  // ---- W0 = diag(1/sd) (X - mu)' Zc   (N x L);  V = diag(1/sd) W0 ----
-  um_view W0, V, NL;
-  W_(pool.mat(N, L, &W0));
-  W_(pool.mat(N, L, &V));
-  W_(pool.mat(N, L, &NL));
-  const um_view Xt = tr(*X);
-  W_(um_matmul(&Xt, &Zc, &W0));
-  W_(um_matmul(&mu_t, &csz, &NL));          // the rounding residue of 1'Zc, scaled by the column means
-  W_(um_binary(UM_SUB, &W0, &NL, &W0));
-  W_(um_binary(UM_MUL, &W0, &isd_t, &W0));
-  W_(um_binary(UM_MUL, &W0, &isd_t, &V));
-
-  // ---- PX = Xn W0 (T x L), h0 = Xn 1 (T x 1): two more products over the panel ----
-  um_view PX, h0;
-  W_(pool.mat(T, L, &PX));
-  W_(pool.mat(T, 1, &h0));
-  W_(um_matmul(X, &V, &PX));
-  W_(um_matmul(X, &isd_t, &h0));
 
   um_view fc, rs;
   W_(out_or_tmp(pool, out->forecasts, T, 1, &fc));
@@ -140,15 +173,14 @@ int tprf_fit_wide(int mode, const um_view* y, const um_view* X, const um_view* Z
     W_(pool.mat(L, 1, &s));
     W_(um_reduce_axis(UM_SUM, &W0, 0, &sw));
     W_(um_binary_scalar(UM_DIV, &sw, (double)N, 0, &sw));                       // wbar
-    W_(um_matmul(&m, &W0, &smw));
+    W_(tall_gram(pool, tr(m), W0, smw));                                        // smw = (mu/sd) W0
     W_(um_reduce_axis(UM_SUM, &m, 1, &smu));
     W_(um_binary(UM_SUB, &PX, &smw, &G));
     W_(um_binary(UM_SUB, &h0, &smu, &r));
     W_(um_matmul(&r, &sw, &RW));
     W_(um_binary(UM_SUB, &G, &RW, &G));
-    const um_view Gt = tr(G);
-    W_(um_matmul(&Gt, &G, &core));
-    W_(um_matmul(&Gt, &yc, &rhs));
+    W_(tall_gram(pool, G, G, core));
+    W_(tall_gram(pool, G, yc, rhs));
     W_(um_inverse(&core, &core_i));
     W_(um_matmul(&core_i, &rhs, &s));
     if (mode == UM_TPRF_CLOSED) {
@@ -179,8 +211,7 @@ int tprf_fit_wide(int mode, const um_view* y, const um_view* X, const um_view* Z
     W_(pool.mat(D, 1, &Xty));
     W_(out_or_tmp(pool, out->beta3, D, 1, &beta));
     // pass 1: Phi = W0 (Zc'Zc)^-1 (the slopes of x_j/sd_j on [1 | Z], Tprf3.scala:263-264)
-    const um_view Zct = tr(Zc);
-    W_(um_matmul(&Zct, &Zc, &Szz));
+    W_(tall_gram(pool, Zc, Zc, Szz));
     W_(um_inverse(&Szz, &Szz_i));
     W_(um_matmul(&W0, &Szz_i, &Phi));
     const um_view Phit = tr(Phi);
@@ -196,8 +227,7 @@ int tprf_fit_wide(int mode, const um_view* y, const um_view* X, const um_view* Z
     const um_view dP0 = sl(dP, 0, N, 0, 1), dP1 = sl(dP, 0, N, 1, D);
     W_(um_fill(&dP0, 1.0));
     W_(um_copy(&Phi, &dP1));
-    const um_view dPt = tr(dP);
-    W_(um_matmul(&dPt, &dP, &PtP));
+    W_(tall_gram(pool, dP, dP, PtP));
     W_(um_inverse(&PtP, &PtP_i));
     const um_view XdP0 = sl(XdP, 0, T, 0, 1), XdP1 = sl(XdP, 0, T, 1, D);
     W_(um_copy(&h0, &XdP0));
@@ -212,9 +242,8 @@ int tprf_fit_wide(int mode, const um_view* y, const um_view* X, const um_view* Z
     }
     // pass 3: y on [1 | Sigma] (Tprf3.scala:268-269)
     W_(um_fill(&Xa0, 1.0));
-    const um_view Xat = tr(Xaug);
-    W_(um_matmul(&Xat, &Xaug, &XtX));
-    W_(um_matmul(&Xat, y, &Xty));
+    W_(tall_gram(pool, Xaug, Xaug, XtX));
+    W_(tall_gram(pool, Xaug, *y, Xty));
     W_(um_inverse(&XtX, &XtX_i));
     W_(um_matmul(&XtX_i, &Xty, &beta));
     if (mode != UM_TPRF_CLOSED) W_(um_matmul(&Xaug, &beta, &fc));
