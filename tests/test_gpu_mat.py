@@ -647,6 +647,27 @@ def test_matmul_f64(u, mkn):
         np.testing.assert_allclose((dev(u, big).slice(1, M + 1, 3, K + 3) @ dev(u, b)).to_numpy(), big[1 : M + 1, 3 : K + 3] @ b, **tol)
 
 
+@pytest.mark.parametrize("mkn", [(33, 20000, 17), (64, 65536, 64), (1, 300000, 9), (9, 4096, 1), (200, 50000, 130), (8, 2047, 8)])
+def test_matmul_f64_long_contractions_are_split_along_k(u, mkn):
+    """A' A of a tall matrix, normal equations, `row *@ tall`: few output tiles and a long K.  The product is split along K
+    over the grid and the partial C's are added in a fixed tree (matmul.cu launch_dgemm): element-wise the textbook bound
+    K eps (|a| @ |b|) with room to spare, every operand orientation, run-to-run bit-reproducible."""
+    M, K, N = mkn
+    rng = np.random.default_rng(M + 13 * N + K)
+    a = rng.standard_normal((M, K)) + 0.5; b = rng.standard_normal((K, N)) - 0.25
+    want = a @ b
+    bound = 1e-14 * np.sqrt(K) * (np.abs(a) @ np.abs(b)) + 1e-300
+    da, db, dat, dbt = dev(u, a), dev(u, b), dev(u, a.T.copy()).T, dev(u, b.T.copy()).T
+    got = (da @ db).to_numpy()
+    assert np.all(np.abs(got - want) <= bound)
+    for x, yv in ((dat, db), (da, dbt), (dat, dbt)):
+        assert np.all(np.abs((x @ yv).to_numpy() - want) <= bound)
+    assert np.array_equal((da @ db).to_numpy(), got)
+    # the Gram of a tall matrix through a transposed view, as the reference's OLS spells it (`X.T *@ X`)
+    g = (db.T @ db).to_numpy()
+    assert np.all(np.abs(g - b.T @ b) <= 1e-14 * np.sqrt(K) * (np.abs(b).T @ np.abs(b)))
+
+
 def test_matmul_matches_pinned_oracle(u):
     a = pc.corpus()[: 65 * 63].reshape(65, 63)
     m = dev(u, a)

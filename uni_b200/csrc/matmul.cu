@@ -97,17 +97,22 @@ __device__ __forceinline__ void stage_tile_part(double* sm, const double* __rest
 
 // C[m][n] = sum_k A(m,k) B(k,n).  A(m,k) = pa[m*a_rs + k*a_cs] with one of the strides == 1,
 // same for B.  AK: A is k-contiguous (a_cs == 1); BK_: B is k-contiguous (b_rs == 1).
-template <int TILE, bool AK, bool BKM, bool VEC16>
+template <int TILE, bool AK, bool BKM, bool VEC16, bool SPLIT>
 __global__ void __launch_bounds__(MM_THREADS, TILE == 128 ? 1 : 2)
 k_dgemm(const double* __restrict__ pa, i64 lda, const double* __restrict__ pb, i64 ldb, double* __restrict__ pc, i64 ldc,
-        i64 M, i64 N, i64 K) {
+        i64 M, i64 N, i64 K, int kt_per, i64 split_stride) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
   using S = MMShape<TILE>;
   constexpr int MM_PMN = S::PMN, MM_TILE_ELEMS = S::TILE_ELEMS, MI = S::MI, NJ = S::NJ;
   const i64 m0 = (i64)blockIdx.y * TILE, n0 = (i64)blockIdx.x * TILE;
-  const int KT = (int)((K + MM_BK - 1) / MM_BK);
+  // split-K (few output tiles, long K): blockIdx.z takes k-tiles [kt0, kt1) and writes its own partial C
+  const int KT_all = (int)((K + MM_BK - 1) / MM_BK);
+  // (a separate instantiation: the extra index arithmetic cost the unsplit kernel 3 % at 4096^2)
+  const int kt0 = SPLIT ? (int)blockIdx.z * kt_per : 0;
+  const int kt1 = SPLIT ? (kt0 + kt_per < KT_all ? kt0 + kt_per : KT_all) : KT_all;
+  if (SPLIT) pc += (i64)blockIdx.z * split_stride;
 
   auto stage = [&](int s, int kt) {
     double* sa = smem + (size_t)s * 2 * MM_TILE_ELEMS;
@@ -127,7 +132,7 @@ k_dgemm(const double* __restrict__ pa, i64 lda, const double* __restrict__ pb, i
 
 #pragma unroll
   for (int s = 0; s < MM_STAGES - 1; ++s) {
-    if (s < KT) stage(s, s);
+    if (kt0 + s < kt1) stage(s, kt0 + s);
     cp_async_commit();
   }
 
@@ -149,13 +154,13 @@ k_dgemm(const double* __restrict__ pa, i64 lda, const double* __restrict__ pb, i
   };
 
   const int fr = lane >> 2, fk = lane & 3;  // fragment row (m or n) and k index
-  for (int kt = 0; kt < KT; ++kt) {
+  for (int kt = kt0; kt < kt1; ++kt) {
     cp_async_wait<MM_STAGES - 2>();
     __syncthreads();
     const int nk = kt + MM_STAGES - 1;
-    const bool more = nk < KT;
-    const int ns = nk % MM_STAGES;   // the stage read in iteration kt - 1: free since the barrier above
-    const double* sa = smem + (size_t)(kt % MM_STAGES) * 2 * MM_TILE_ELEMS;
+    const bool more = nk < kt1;
+    const int ns = (nk - kt0) % MM_STAGES;   // the stage read in iteration kt - 1: free since the barrier above
+    const double* sa = smem + (size_t)((kt - kt0) % MM_STAGES) * 2 * MM_TILE_ELEMS;
     const double* sb = sa + MM_TILE_ELEMS;
 #pragma unroll
     for (int kk = 0; kk < MM_BK; kk += 4) {
@@ -297,15 +302,23 @@ k_sgemm(In<float> a, In<float> b, float* __restrict__ pc, i64 ldc, i64 M, i64 N,
 static std::atomic<int> g_f64_tile{0};   // um_matmul_set_f64_tile: 0 = automatic, 64 / 128 forced (tests, profiling)
 
 template <int TILE, bool AK, bool BKM, bool VEC16>
-static int launch_dgemm_tile(const double* pa, i64 lda, const double* pb, i64 ldb, double* pc, i64 ldc, i64 M, i64 N, i64 K) {
-  dim3 grid((unsigned)((N + TILE - 1) / TILE), (unsigned)((M + TILE - 1) / TILE));
+static int launch_dgemm_tile(const double* pa, i64 lda, const double* pb, i64 ldb, double* pc, i64 ldc, i64 M, i64 N, i64 K,
+                             int splits, int kt_per, i64 split_stride) {
+  dim3 grid((unsigned)((N + TILE - 1) / TILE), (unsigned)((M + TILE - 1) / TILE), (unsigned)splits);
   static std::once_flag once;   // one device per process (um_init)
   cudaError_t attr = cudaSuccess;
   std::call_once(once, [&] {
-    attr = cudaFuncSetAttribute(k_dgemm<TILE, AK, BKM, VEC16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MMShape<TILE>::SMEM_BYTES);
+    attr = cudaFuncSetAttribute(k_dgemm<TILE, AK, BKM, VEC16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MMShape<TILE>::SMEM_BYTES);
+    if (attr == cudaSuccess)
+      attr = cudaFuncSetAttribute(k_dgemm<TILE, AK, BKM, VEC16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MMShape<TILE>::SMEM_BYTES);
   });
   UM_CUDA(attr);
-  k_dgemm<TILE, AK, BKM, VEC16><<<grid, MM_THREADS, MMShape<TILE>::SMEM_BYTES, ctx()->stream>>>(pa, lda, pb, ldb, pc, ldc, M, N, K);
+  if (splits > 1)
+    k_dgemm<TILE, AK, BKM, VEC16, true><<<grid, MM_THREADS, MMShape<TILE>::SMEM_BYTES, ctx()->stream>>>(pa, lda, pb, ldb, pc, ldc, M, N, K, kt_per,
+                                                                                                        split_stride);
+  else
+    k_dgemm<TILE, AK, BKM, VEC16, false><<<grid, MM_THREADS, MMShape<TILE>::SMEM_BYTES, ctx()->stream>>>(pa, lda, pb, ldb, pc, ldc, M, N, K, kt_per,
+                                                                                                         split_stride);
   UM_LAUNCHED();
   return UM_OK;
 }
@@ -324,14 +337,50 @@ static int pick_dgemm_tile(i64 M, i64 N) {
 }
 
 template <bool AK, bool BKM>
+static int launch_dgemm_split(int tile, const double* pa, i64 lda, const double* pb, i64 ldb, double* pc, i64 ldc, i64 M, i64 N, i64 K,
+                              bool vec16, int splits, int kt_per, i64 split_stride) {
+  if (tile == 64) {
+    if (vec16) return launch_dgemm_tile<64, AK, BKM, true>(pa, lda, pb, ldb, pc, ldc, M, N, K, splits, kt_per, split_stride);
+    return launch_dgemm_tile<64, AK, BKM, false>(pa, lda, pb, ldb, pc, ldc, M, N, K, splits, kt_per, split_stride);
+  }
+  if (vec16) return launch_dgemm_tile<128, AK, BKM, true>(pa, lda, pb, ldb, pc, ldc, M, N, K, splits, kt_per, split_stride);
+  return launch_dgemm_tile<128, AK, BKM, false>(pa, lda, pb, ldb, pc, ldc, M, N, K, splits, kt_per, split_stride);
+}
+
+// Few output tiles and a long contraction (A' A of a tall matrix, the normal equations of an OLS: the commonest
+// product in the reference's statistics code) would leave the whole of K to a handful of CTAs -- ONE for an L x L
+// Gram, 2.2 us per 16 k.  Such products are split along K over blockIdx.z into partial C's, summed by the library's
+// fixed-tree axis reduction (run-to-run reproducible; the split depends only on the shape and the SM count).
+template <bool AK, bool BKM>
 static int launch_dgemm(const double* pa, i64 lda, const double* pb, i64 ldb, double* pc, i64 ldc, i64 M, i64 N, i64 K,
                         bool vec16) {
-  if (pick_dgemm_tile(M, N) == 64) {
-    if (vec16) return launch_dgemm_tile<64, AK, BKM, true>(pa, lda, pb, ldb, pc, ldc, M, N, K);
-    return launch_dgemm_tile<64, AK, BKM, false>(pa, lda, pb, ldb, pc, ldc, M, N, K);
+  const int tile = pick_dgemm_tile(M, N);
+  const i64 sms = ctx()->sm_count > 0 ? ctx()->sm_count : 148;
+  const i64 tiles = ((M + tile - 1) / tile) * ((N + tile - 1) / tile);
+  const i64 target = (tile == 64 ? 2 : 1) * sms;       // resident CTAs
+  const int KT = (int)((K + MM_BK - 1) / MM_BK);
+  i64 splits = 1;
+  if (ldc == N && K >= 2048 && 2 * tiles <= target) {
+    splits = target / tiles;
+    if (splits > K / 512) splits = K / 512;            // at least 32 k-tiles per split
+    if (splits > 256) splits = 256;
+    while (splits > 1 && (double)splits * (double)M * (double)N * 8.0 > 268435456.0) --splits;
   }
-  if (vec16) return launch_dgemm_tile<128, AK, BKM, true>(pa, lda, pb, ldb, pc, ldc, M, N, K);
-  return launch_dgemm_tile<128, AK, BKM, false>(pa, lda, pb, ldb, pc, ldc, M, N, K);
+  if (splits <= 1) return launch_dgemm_split<AK, BKM>(tile, pa, lda, pb, ldb, pc, ldc, M, N, K, vec16, 1, KT, 0);
+  const int kt_per = (int)((KT + splits - 1) / splits);
+  splits = (KT + kt_per - 1) / kt_per;
+  void* part = nullptr;
+  int s = um_malloc((size_t)splits * (size_t)M * (size_t)N * 8, &part);
+  if (s != UM_OK) return s;
+  s = launch_dgemm_split<AK, BKM>(tile, pa, lda, pb, ldb, static_cast<double*>(part), N, M, N, K, vec16, (int)splits, kt_per, M * N);
+  if (s == UM_OK) {
+    um_view pv, ov;
+    um_view_init(&pv, part, splits, M * N, UM_F64);
+    um_view_init(&ov, pc, 1, M * N, UM_F64);
+    s = um_reduce_axis(UM_SUM, &pv, 0, &ov);
+  }
+  um_free(part);   // stream-ordered
+  return s;
 }
 
 }  // namespace um

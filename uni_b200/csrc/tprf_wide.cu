@@ -59,72 +59,11 @@ int out_or_tmp(Pool& pool, double* p, i64 r, i64 c, um_view* v) {
   return pool.mat(r, c, v);
 }
 
-// ---- out (m x n) = A' B for tall operands (A: K x m, B: K x n, K >> m, n): `*@` would give the whole contraction to
-// ONE CTA tile (36 ms at K = 262144); here every CTA takes a block of rows and writes its partial m x n, and the
-// partials are added by the library's fixed-tree axis reduction (run-to-run reproducible).
-constexpr int GR_ROWS = 16, GR_MAXW = 64, GR_THREADS = 256, GR_Q = 16;   // m, n <= 64 and m n <= 4096
-
-__global__ void __launch_bounds__(GR_THREADS) k_tall_gram(const double* __restrict__ A, i64 a_rs, i64 a_cs, int m,
-                                                          const double* __restrict__ B, i64 b_rs, i64 b_cs, int n, i64 K,
-                                                          i64 rows_per_cta, double* __restrict__ part) {
-  __shared__ double sa[GR_ROWS][GR_MAXW + 1], sb[GR_ROWS][GR_MAXW + 1];
-  const int tid = threadIdx.x, mn = m * n;
-  int oi[GR_Q], oj[GR_Q];
-  double acc[GR_Q];
-#pragma unroll
-  for (int q = 0; q < GR_Q; ++q) {
-    const int idx = tid + q * GR_THREADS;
-    oi[q] = idx < mn ? idx / n : 0;
-    oj[q] = idx < mn ? idx % n : 0;
-    acc[q] = 0.0;
-  }
-  const i64 k_lo = (i64)blockIdx.x * rows_per_cta;
-  const i64 k_hi = k_lo + rows_per_cta < K ? k_lo + rows_per_cta : K;
-  for (i64 k0 = k_lo; k0 < k_hi; k0 += GR_ROWS) {
-    for (int e = tid; e < GR_ROWS * m; e += GR_THREADS) {
-      const int r = e / m, i = e % m;
-      sa[r][i] = k0 + r < k_hi ? A[(k0 + r) * a_rs + i * a_cs] : 0.0;
-    }
-    for (int e = tid; e < GR_ROWS * n; e += GR_THREADS) {
-      const int r = e / n, j = e % n;
-      sb[r][j] = k0 + r < k_hi ? B[(k0 + r) * b_rs + j * b_cs] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < GR_Q; ++q) {
-      if (q * GR_THREADS < mn) {
-#pragma unroll
-        for (int r = 0; r < GR_ROWS; ++r) acc[q] = fma(sa[r][oi[q]], sb[r][oj[q]], acc[q]);
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int q = 0; q < GR_Q; ++q) {
-    const int idx = tid + q * GR_THREADS;
-    if (idx < mn) part[(i64)blockIdx.x * mn + idx] = acc[q];
-  }
-}
-
-// out must be a contiguous m x n matrix
-int tall_gram(Pool& pool, const um_view& A, const um_view& B, const um_view& out) {
-  const i64 K = A.rows, m = A.cols, n = B.cols;
-  if (m > GR_MAXW || n > GR_MAXW || m * n > GR_Q * GR_THREADS || K < 256) {   // very wide proxy sets, short operands: the general product
-    const um_view At = tr(A);
-    return um_matmul(&At, &B, &out);
-  }
-  i64 rows = (K + 4 * ctx()->sm_count - 1) / (4 * ctx()->sm_count);
-  if (rows < 256) rows = 256;
-  rows = (rows + GR_ROWS - 1) / GR_ROWS * GR_ROWS;
-  const i64 ctas = (K + rows - 1) / rows;
-  um_view part, flat;
-  W_(pool.mat(ctas, m * n, &part));
-  k_tall_gram<<<(unsigned)ctas, GR_THREADS, 0, ctx()->stream>>>(static_cast<const double*>(A.data) + A.offset, A.rs, A.cs, (int)m,
-                                                                static_cast<const double*>(B.data) + B.offset, B.rs, B.cs, (int)n, K, rows,
-                                                                static_cast<double*>(part.data));
-  UM_LAUNCHED();
-  W_(um_view_init(&flat, static_cast<double*>(out.data) + out.offset, 1, m * n, UM_F64));
-  return um_reduce_axis(UM_SUM, &part, 0, &flat);
+// out (m x n) = A' B for tall operands (A: K x m, B: K x n, K >> m, n): `*@` splits such a contraction along K
+// (matmul.cu launch_dgemm) and adds the partial products in a fixed tree
+int tall_gram(const um_view& A, const um_view& B, const um_view& out) {
+  const um_view At = tr(A);
+  return um_matmul(&At, &B, &out);
 }
 
 }  // namespace
@@ -173,14 +112,14 @@ int tprf_fit_wide(int mode, const um_view* y, const um_view* Z, i64 N, const Tpr
     W_(pool.mat(L, 1, &s));
     W_(um_reduce_axis(UM_SUM, &W0, 0, &sw));
     W_(um_binary_scalar(UM_DIV, &sw, (double)N, 0, &sw));                       // wbar
-    W_(tall_gram(pool, tr(m), W0, smw));                                        // smw = (mu/sd) W0
+    W_(tall_gram(tr(m), W0, smw));                                        // smw = (mu/sd) W0
     W_(um_reduce_axis(UM_SUM, &m, 1, &smu));
     W_(um_binary(UM_SUB, &PX, &smw, &G));
     W_(um_binary(UM_SUB, &h0, &smu, &r));
     W_(um_matmul(&r, &sw, &RW));
     W_(um_binary(UM_SUB, &G, &RW, &G));
-    W_(tall_gram(pool, G, G, core));
-    W_(tall_gram(pool, G, yc, rhs));
+    W_(tall_gram(G, G, core));
+    W_(tall_gram(G, yc, rhs));
     W_(um_inverse(&core, &core_i));
     W_(um_matmul(&core_i, &rhs, &s));
     if (mode == UM_TPRF_CLOSED) {
@@ -211,7 +150,7 @@ int tprf_fit_wide(int mode, const um_view* y, const um_view* Z, i64 N, const Tpr
     W_(pool.mat(D, 1, &Xty));
     W_(out_or_tmp(pool, out->beta3, D, 1, &beta));
     // pass 1: Phi = W0 (Zc'Zc)^-1 (the slopes of x_j/sd_j on [1 | Z], Tprf3.scala:263-264)
-    W_(tall_gram(pool, Zc, Zc, Szz));
+    W_(tall_gram(Zc, Zc, Szz));
     W_(um_inverse(&Szz, &Szz_i));
     W_(um_matmul(&W0, &Szz_i, &Phi));
     const um_view Phit = tr(Phi);
@@ -227,7 +166,7 @@ int tprf_fit_wide(int mode, const um_view* y, const um_view* Z, i64 N, const Tpr
     const um_view dP0 = sl(dP, 0, N, 0, 1), dP1 = sl(dP, 0, N, 1, D);
     W_(um_fill(&dP0, 1.0));
     W_(um_copy(&Phi, &dP1));
-    W_(tall_gram(pool, dP, dP, PtP));
+    W_(tall_gram(dP, dP, PtP));
     W_(um_inverse(&PtP, &PtP_i));
     const um_view XdP0 = sl(XdP, 0, T, 0, 1), XdP1 = sl(XdP, 0, T, 1, D);
     W_(um_copy(&h0, &XdP0));
@@ -242,8 +181,8 @@ int tprf_fit_wide(int mode, const um_view* y, const um_view* Z, i64 N, const Tpr
     }
     // pass 3: y on [1 | Sigma] (Tprf3.scala:268-269)
     W_(um_fill(&Xa0, 1.0));
-    W_(tall_gram(pool, Xaug, Xaug, XtX));
-    W_(tall_gram(pool, Xaug, *y, Xty));
+    W_(tall_gram(Xaug, Xaug, XtX));
+    W_(tall_gram(Xaug, *y, Xty));
     W_(um_inverse(&XtX, &XtX_i));
     W_(um_matmul(&XtX_i, &Xty, &beta));
     if (mode != UM_TPRF_CLOSED) W_(um_matmul(&Xaug, &beta, &fc));
