@@ -293,7 +293,7 @@ typedef enum um_tprf_mode {
  * n_total = N over all ranks) and the packed partial sums are all-reduced once.  X: T x N_local f64
  * view with cs == 1; y: T x 1; Z: T x L, any L >= 1 (Tprf3.scala:199-289 take any proxy count): L <= 8 runs the
  * single-read fused sweep, L > 8 one such sweep per group of 8 proxies and a finish on the library's own operators
- * (tprf_wide.cu; single-device fits only -- a column-sharded call with L > 8 is UM_ERR_ARG). */
+ * (tprf_wide.cu; column-sharded fits included: the sums over predictors are completed across the ranks). */
 int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_view* Z, int64_t n_total,
                     um_tprf_out* out);
 /* Same fit with y/X/Z in HOST memory (row-major, ldx elements between rows of X): the panel is

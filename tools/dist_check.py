@@ -32,7 +32,7 @@ from uni_b200._lib import lib as _lib
 _p2p = _C.c_int32(0); _lib.um_comm_transport(_C.byref(_p2p))
 print(f"rank {rank}: exchange transport = {'peer memory (CUDA IPC)' if _p2p.value else 'NCCL'}", flush=True)
 ok = True
-for (T, N, L) in ((512, 4096, 4), (300, 1000, 3), (1024, 8192, 8)):
+for (T, N, L) in ((512, 4096, 4), (300, 1000, 3), (1024, 8192, 8), (640, 6000, 13), (2048, 16384, 20)):   # L > 8: one sweep per group of 8 + operator finish
     rng = np.random.default_rng(7)
     X = rng.standard_normal((T, N)) * 2 + 0.3; y = rng.standard_normal((T, 1)); Z = rng.standard_normal((T, L))
     c0, c1 = shard_range(N, rank, world)

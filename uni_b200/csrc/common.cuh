@@ -34,7 +34,8 @@ extern std::atomic<long long> g_launches;
 // accumulators of a 3PRF fit with more than 8 proxies, filled group by group by the fused sweeps (tprf.cu) and finished
 // with the library's operators (tprf_wide.cu): W0 N x L, PX T x L, h0 T x 1, isd = 1/sd and m = mu/sd 1 x N
 struct TprfWideAcc { um_view W0, PX, h0, isd, m; };
-int tprf_fit_wide(int mode, const um_view* y, const um_view* Z, i64 N, const TprfWideAcc& acc, um_tprf_out* out);
+int tprf_fit_wide(int mode, const um_view* y, const um_view* Z, i64 N, const TprfWideAcc& acc, double n_total, bool sharded,
+                  um_tprf_out* out);
 
 // per-kernel event timing (bench harness): UM_PROF_BEGIN(slot) ... launch ... UM_PROF_END(slot)
 bool prof_on();

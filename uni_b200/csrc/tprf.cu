@@ -1453,7 +1453,7 @@ static int host_result_block(double** host, double** dev) {
 
 // L > LP: the accumulators are column-separable in Z, so the fused sweep runs once per group of 8 proxies (X is read
 // ceil(L / 8) times) and its W0 / PX blocks are copied out of the workspace before anything else may reuse it
-static int fit_wide(int mode, const um_view* y, const um_view* X, const um_view* Z, um_tprf_out* out) {
+static int fit_wide(int mode, const um_view* y, const um_view* X, const um_view* Z, double n_total, bool sharded, um_tprf_out* out) {
   const i64 T = X->rows, N = X->cols, L = Z->cols;
   const double* xp = static_cast<const double*>(X->data) + X->offset;
   const i64 ldx = N == 1 ? 1 : X->rs;
@@ -1507,7 +1507,9 @@ static int fit_wide(int mode, const um_view* y, const um_view* X, const um_view*
     }
     if (s != UM_OK) return s;
   }
-  return tprf_fit_wide(mode, y, Z, N, acc, out);
+  s = tprf_fit_wide(mode, y, Z, N, acc, n_total, sharded, out);
+  if (s == UM_OK && sharded) s = comm_check_error();   // tprf_fit_wide ends with a stream synchronisation
+  return s;
 }
 
 static int fill_nan(double* p, i64 n) {
@@ -1594,8 +1596,7 @@ int32_t um_tprf_fit(int32_t mode, const um_view* y, const um_view* X, const um_v
   }
   if (L > LP) {
     // more proxies than one DMMA fragment holds: one fused sweep per group of 8, finish by operators (tprf_wide.cu)
-    if (sharded) return fail(UM_ERR_ARG, "column-sharded fits take L <= %d proxies (L = %lld)", LP, L);
-    const int sw = fit_wide(mode, y, X, Z, out);
+    const int sw = fit_wide(mode, y, X, Z, (double)n_total, sharded, out);
     if (sw == UM_ERR_SINGULAR) {
       out->singular = 1;
       int sf = fill_nan(out->forecasts, T);

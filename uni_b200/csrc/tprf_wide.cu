@@ -17,6 +17,8 @@
 
 namespace um {
 
+int comm_allreduce_sum_f64_impl(double* buf, i64 count);  // comm.cu
+
 namespace {
 
 #define W_(call)                  \
@@ -68,13 +70,22 @@ int tall_gram(const um_view& A, const um_view& B, const um_view& out) {
 
 }  // namespace
 
-int tprf_fit_wide(int mode, const um_view* y, const um_view* Z, i64 N, const TprfWideAcc& acc, um_tprf_out* out) {
+int tprf_fit_wide(int mode, const um_view* y, const um_view* Z, i64 N, const TprfWideAcc& acc, double n_total, bool sharded,
+                  um_tprf_out* out) {
   const i64 T = Z->rows, L = Z->cols, D = L + 1;
   Pool pool;
   const bool closed_wanted = mode == UM_TPRF_CLOSED || (mode == UM_TPRF_IS_FULL && out->alpha);
   const bool three_wanted = mode != UM_TPRF_CLOSED || out->phi || out->phi_hat || out->sigma || out->beta3;
   // from the sweeps: W0 = diag(1/sd) (X - mu)' Zc (N x L), PX = Xn W0 (T x L), h0 = Xn 1 (T x 1), 1/sd and mu/sd (1 x N)
   um_view W0 = acc.W0, PX = acc.PX, h0 = acc.h0, isd = acc.isd, m = acc.m;
+  // column-sharded fit: every sum over predictors is completed across the ranks (rank-order sums: all ranks hold
+  // the same bits); W0, 1/sd, mu/sd, alpha, Phi stay this rank's columns
+  auto allsum = [&](const um_view& v) -> int {
+    if (!sharded) return UM_OK;
+    return comm_allreduce_sum_f64_impl(static_cast<double*>(v.data) + v.offset, v.rows * v.cols);   // contiguous buffers only
+  };
+  W_(allsum(PX));
+  W_(allsum(h0));
   if (out->xstd) {   // column sample std (n <= 1 or sd == 0 -> 1, Tprf3.scala:469-502)
     um_view xs;
     W_(um_view_init(&xs, out->xstd, 1, N, UM_F64));
@@ -111,9 +122,12 @@ int tprf_fit_wide(int mode, const um_view* y, const um_view* Z, i64 N, const Tpr
     W_(pool.mat(L, 1, &rhs));
     W_(pool.mat(L, 1, &s));
     W_(um_reduce_axis(UM_SUM, &W0, 0, &sw));
-    W_(um_binary_scalar(UM_DIV, &sw, (double)N, 0, &sw));                       // wbar
+    W_(allsum(sw));
+    W_(um_binary_scalar(UM_DIV, &sw, n_total, 0, &sw));                         // wbar
     W_(tall_gram(tr(m), W0, smw));                                        // smw = (mu/sd) W0
+    W_(allsum(smw));
     W_(um_reduce_axis(UM_SUM, &m, 1, &smu));
+    W_(allsum(smu));
     W_(um_binary(UM_SUB, &PX, &smw, &G));
     W_(um_binary(UM_SUB, &h0, &smu, &r));
     W_(um_matmul(&r, &sw, &RW));
@@ -167,6 +181,7 @@ int tprf_fit_wide(int mode, const um_view* y, const um_view* Z, i64 N, const Tpr
     W_(um_fill(&dP0, 1.0));
     W_(um_copy(&Phi, &dP1));
     W_(tall_gram(dP, dP, PtP));
+    W_(allsum(PtP));
     W_(um_inverse(&PtP, &PtP_i));
     const um_view XdP0 = sl(XdP, 0, T, 0, 1), XdP1 = sl(XdP, 0, T, 1, D);
     W_(um_copy(&h0, &XdP0));
