@@ -619,6 +619,26 @@ def run_ours(args, rank, world, local_rank):
     iterative = {"ms_per_fit": round(it_ms, 4), "tflops": round(flops / (it_ms * 1e-3) / 1e12, 3), "steps": args.steps,
                  "note": "Tprf3.t3prf on the same resident panel: same single-read sweep, three-pass finish"}
 
+    # ---- more proxies than one DMMA fragment holds (the reference's fits take any L): one fused sweep per group of 8
+    # proxies + operator finish (csrc/tprf_wide.cu), here L = 16 on the same resident panel
+    try:
+        Z16 = u.MatD.randn(T, 16, seed=77)
+        fit16 = lambda: u.tprf3._fit(L_.TPRF_CLOSED, y, X, Z16, n_total=N, want_all=False)
+        time.sleep(1.0)
+        fit16()
+        barrier()
+        check(lib.um_timer_start())
+        for _ in range(3):
+            r16 = fit16()
+        check(lib.um_timer_stop(C.byref(ms)))
+        barrier()
+        w_ms = max_over_ranks(ms.value / 3)
+        wide = {"L": 16, "ms_per_fit": round(w_ms, 4), "tflops": round(tprf_flops(T, N, 16) / (w_ms * 1e-3) / 1e12, 3),
+                "x_reads": 2, "r_squared": r16.rSquared}
+        del Z16, r16
+    except Exception as ex:
+        wide = {"error": str(ex)[:200]}
+
     # ---- per-kernel device times (outside the timed region) -> roofline of the dominant kernel
     check(lib.um_prof_enable(1)); check(lib.um_prof_reset())
     PROF_N = 5
@@ -705,7 +725,7 @@ def run_ours(args, rank, world, local_rank):
     except Exception as ex:  # e.g. the box cannot pin 16 GiB
         e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
-    extras = {"config4_iterative_t3prf": iterative}
+    extras = {"config4_iterative_t3prf": iterative, "config4_closed_form_16_proxies": wide}
     if not args.skip_ops:
         try:
             extras["batched_config5"] = batched_config5(u, rank, world, max_over_ranks, barrier, peak_gbs, small=args.small)
