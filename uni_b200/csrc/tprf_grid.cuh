@@ -313,12 +313,17 @@ k_tprf_grid(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
         tmem_fence_after();
         stamp(it, 2);
         const unsigned tm = tm_warp + (unsigned)(tb * TCOLS);
+        unsigned tr2[2][2][8];   // next pair's tensor-memory loads in flight during this pair's math (as tprf_fused.cuh)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) tmem_ld8(tm + (unsigned)(i * 8), tr2[0][i]);
 #pragma unroll
         for (int m0 = 0; m0 < MT; m0 += 2) {
-          unsigned r[2][8];
-#pragma unroll
-          for (int i = 0; i < 2; ++i) tmem_ld8(tm + (unsigned)((m0 + i) * 8), r[i]);
           tmem_wait_ld();
+          unsigned (&r)[2][8] = tr2[(m0 >> 1) & 1];
+          if (m0 + 2 < MT) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) tmem_ld8(tm + (unsigned)((m0 + 2 + i) * 8), tr2[((m0 >> 1) & 1) ^ 1][i]);
+          }
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
