@@ -243,7 +243,8 @@ int32_t um_matmul(const um_view* a, const um_view* b, const um_view* out);
  * hi / lo operands are split once in global memory -- a temporary of 8 (M + N) K bytes from the pool -- instead of in shared
  * memory, same bits), 1 = FFMA kernel only, 2 = tensor-core kernel with the split in shared memory or UM_ERR_ARG,
  * 3 = tensor-core kernel with the split in global memory or UM_ERR_ARG.  Process-wide; for tests and profiling.
- * UM_MATF_TENSOR=0 in the environment makes automatic mean 1. */
+ * UM_MATF_TENSOR=0 in the environment makes automatic mean 1.  Automatic also promotes a product with few output
+ * tiles and K >= 8192 (A' A of a tall MatF) to the split-K FP64 kernel and rounds the result to FP32 once. */
 int32_t um_matmul_set_f32_path(int32_t path);
 /* FP64 `*@` CTA tile: 0 = automatic (64 x 64 tiles, two CTAs per SM, whenever 128 x 128 tiles would leave SMs idle
  * or a mostly empty last wave -- 1024^2 and 2048^2 of BASELINE config 3; 128 x 128 otherwise), 64 / 128 = forced.

@@ -668,6 +668,24 @@ def test_matmul_f64_long_contractions_are_split_along_k(u, mkn):
     assert np.all(np.abs(g - b.T @ b) <= 1e-14 * np.sqrt(K) * (np.abs(b).T @ np.abs(b)))
 
 
+@pytest.mark.parametrize("mkn", [(33, 20000, 17), (1, 300000, 9), (64, 65536, 64), (130, 8192, 200)])
+def test_matf_long_contractions(u, mkn):
+    """MatF `*@` with few output tiles and a long K (A' A of a tall matrix) is promoted to the split-K FP64 path and
+    rounded to FP32 once: within half an ulp of the float64 product, every orientation, bit-reproducible."""
+    M, K, N = mkn
+    rng = np.random.default_rng(M + 17 * N + K)
+    a = (rng.standard_normal((M, K)) + 0.5).astype(np.float32); b = (rng.standard_normal((K, N)) - 0.25).astype(np.float32)
+    want = a.astype(np.float64) @ b.astype(np.float64)
+    da, db, dat, dbt = dev(u, a), dev(u, b), dev(u, a.T.copy()).T, dev(u, b.T.copy()).T
+    got = (da @ db).to_numpy()
+    assert got.dtype == np.float32
+    tol = 2.0 ** -23 * np.abs(want) + 1e-13 * np.sqrt(K) * (np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64))
+    assert np.all(np.abs(got - want) <= tol)
+    for x, yv in ((dat, db), (da, dbt), (dat, dbt)):
+        assert np.all(np.abs((x @ yv).to_numpy() - want) <= tol)
+    assert np.array_equal((da @ db).to_numpy(), got)
+
+
 def test_matmul_matches_pinned_oracle(u):
     a = pc.corpus()[: 65 * 63].reshape(65, 63)
     m = dev(u, a)

@@ -439,6 +439,30 @@ extern "C" int32_t um_matmul(const um_view* a, const um_view* b, const um_view* 
     return UM_OK;
   }
   if (a->dtype == UM_F32) {
+    // Few output tiles and a long contraction (A' A of a tall MatF): both FP32 kernels would leave all of K to a handful
+    // of CTAs (8 ms for 33 x 262144 x 33).  Such a product is promoted to FP64 and takes the split-K DMMA path above --
+    // every FP32 product is exact in FP64 and the sum is rounded to FP32 once, which is at least as accurate as the
+    // reference's float accumulation (Mat.scala:3236-3268).  Automatic choice only; the operands' copies are capped at 1 GiB.
+    {
+      const i64 sms = ctx()->sm_count > 0 ? ctx()->sm_count : 148;
+      const i64 t128 = ((M + 127) / 128) * ((N + 127) / 128);
+      if (g_f32_path == 0 && K >= 8192 && 2 * t128 <= sms && (double)(M + N) * (double)K * 8.0 <= 1073741824.0) {
+        void* blk = nullptr;
+        int s = um_malloc((size_t)(M * K + K * N + M * N) * 8, &blk);
+        if (s != UM_OK) return s;
+        double* p64 = static_cast<double*>(blk);
+        um_view a64, b64, c64;
+        um_view_init(&a64, p64, M, K, UM_F64);
+        um_view_init(&b64, p64 + M * K, K, N, UM_F64);
+        um_view_init(&c64, p64 + M * K + K * N, M, N, UM_F64);
+        s = um_copy(a, &a64);
+        if (s == UM_OK) s = um_copy(b, &b64);
+        if (s == UM_OK) s = um_matmul(&a64, &b64, &c64);
+        if (s == UM_OK) s = um_copy(&c64, out);
+        um_free(blk);   // stream-ordered
+        return s;
+      }
+    }
     In<float> A = in_of<float>(a), B = in_of<float>(b);
     float* pc = static_cast<float*>(out->data) + out->offset;
     // row-major, 16-byte aligned operands: 3xTF32 on the tcgen05 tensor cores (matmul_tf32.cuh)
