@@ -225,6 +225,32 @@ def test_more_than_eight_proxies_procedures_and_errors(u):
     assert np.isnan(u.tprfClosedForm(*devs(u, y, Xn, Z)).forecasts.to_numpy()).all()
 
 
+def test_more_than_eight_proxies_batched_and_host_calls(u):
+    """um_tprf_fit_batched and um_tprf_fit_host with L > 8: panel by panel / the panel made resident once."""
+    import ctypes as C
+    from uni_b200 import _lib as L_
+    B, T, N, L = 3, 64, 200, 11
+    rng = [np.random.default_rng(40 + p) for p in range(B)]
+    Xs = np.stack([g.standard_normal((T, N)) for g in rng]); ys = np.stack([g.standard_normal((T, 1)) for g in rng])
+    Zs = np.stack([g.standard_normal((T, L)) for g in rng])
+    dX = u.Mat.from_numpy(Xs.reshape(B * T, N)); dy = u.Mat.from_numpy(ys.reshape(B * T, 1)); dZ = u.Mat.from_numpy(Zs.reshape(B * T, L))
+    f = u.MatD.zeros(B * T, 1); a = u.MatD.zeros(B * N, 1); r2 = u.MatD.zeros(B, 1)
+    L_.check(L_.lib.um_tprf_fit_batched(L_.TPRF_CLOSED, dy._buf.ptr, dX._buf.ptr, dZ._buf.ptr, T, N, L, B, f._buf.ptr, a._buf.ptr, r2._buf.ptr))
+    F = f.to_numpy().reshape(B, T); A = a.to_numpy().reshape(B, N); R = r2.to_numpy().ravel()
+    for p in range(B):
+        o = to.tprf_closed_form_gram(ys[p], Xs[p], Zs[p])
+        assert close(F[p], o.forecasts.ravel()) and close(A[p], o.alpha.ravel(), rtol=1e-8) and close(R[p], o.r_squared)
+    T, N, L = 96, 5000, 10
+    g = np.random.default_rng(9)
+    Xw = g.standard_normal((T, N + 6)); X = Xw[:, 3 : N + 3]            # a host panel with a row pitch > N
+    y = g.standard_normal((T, 1)); Z = g.standard_normal((T, L))
+    fh = np.zeros(T); ah = np.zeros(N); r2h = C.c_double(0)
+    vp = lambda arr: arr.ctypes.data_as(C.c_void_p)
+    L_.check(L_.lib.um_tprf_fit_host(L_.TPRF_CLOSED, vp(y), C.c_void_p(Xw.ctypes.data + 3 * 8), N + 6, vp(Z), T, N, L, N, vp(fh), vp(ah), C.byref(r2h)))
+    o = to.tprf_closed_form_gram(y, np.ascontiguousarray(X), Z)
+    assert close(fh, o.forecasts.ravel()) and close(ah, o.alpha.ravel(), rtol=1e-8, atol=1e-13) and close(r2h.value, o.r_squared)
+
+
 def test_edge_semantics(u):
     """TprfCoverageSuite.scala:176-230."""
     rng = np.random.default_rng(4)

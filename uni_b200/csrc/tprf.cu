@@ -1671,8 +1671,24 @@ int32_t um_tprf_fit_batched(int32_t mode, const double* y, const double* X, cons
   UM_CTX();
   UM_REQUIRE(mode >= UM_TPRF_CLOSED && mode <= UM_TPRF_WINDOW, "unknown 3PRF mode %d", mode);
   UM_REQUIRE(y && X && Z, "null input");
-  UM_REQUIRE(L >= 1 && L <= LP, "number of proxies L = %lld outside [1, %d]", (i64)L, LP);
+  UM_REQUIRE(L >= 1, "number of proxies L = %lld < 1", (i64)L);
   UM_REQUIRE(T >= 1 && N >= 1 && batch >= 0, "bad panel shape");
+  if (L > LP) {
+    // more than 8 proxies: panel by panel through um_tprf_fit (one sweep per group of 8 proxies + operator finish)
+    for (int64_t b = 0; b < batch; ++b) {
+      um_view yv, xv, zv;
+      um_view_init(&yv, const_cast<double*>(y) + b * T, T, 1, UM_F64);
+      um_view_init(&xv, const_cast<double*>(X) + b * T * N, T, N, UM_F64);
+      um_view_init(&zv, const_cast<double*>(Z) + b * T * L, T, L, UM_F64);
+      um_tprf_out o = {};
+      o.forecasts = forecasts ? forecasts + b * T : nullptr;
+      o.alpha = alpha ? alpha + b * N : nullptr;
+      const int s = um_tprf_fit(mode, &yv, &xv, &zv, 0, &o);
+      if (s != UM_OK) return s;
+      if (r2) UM_CUDA(cudaMemcpy(r2 + b, &o.r_squared, 8, cudaMemcpyHostToDevice));
+    }
+    return UM_OK;
+  }
   // the panel index is a grid dimension (<= 65535): any number of panels goes through in slices of that, in stream order
   constexpr int64_t SLICE = 65535;
   for (int64_t b0 = 0; b0 < batch; b0 += SLICE) {
@@ -1690,8 +1706,39 @@ int32_t um_tprf_fit_host(int32_t mode, const double* y, const double* X, int64_t
   UM_CTX();
   UM_REQUIRE(mode >= UM_TPRF_CLOSED && mode <= UM_TPRF_WINDOW, "unknown 3PRF mode %d", mode);
   UM_REQUIRE(y && X && Z, "null input");
-  UM_REQUIRE(L >= 1 && L <= LP, "number of proxies L = %lld outside [1, %d]", (i64)L, LP);
+  UM_REQUIRE(L >= 1, "number of proxies L = %lld < 1", (i64)L);
   UM_REQUIRE(T >= 1 && N_local >= 1 && ldx >= N_local, "bad panel shape");
+  if (L > LP) {
+    // more than 8 proxies need ceil(L / 8) reads of X: the panel is made resident once instead of streamed per group
+    void* blk = nullptr;
+    const size_t nx = (size_t)T * N_local, nz = (size_t)T * L;
+    int s = um_malloc((nx + nz + 2 * (size_t)T + (size_t)N_local) * 8, &blk);
+    if (s != UM_OK) return s;
+    struct Free { void* p; ~Free() { um_free(p); } } guard{blk};
+    double* dx = static_cast<double*>(blk);
+    double* dzz = dx + nx;
+    double* dyy = dzz + nz;
+    double* dff = dyy + T;
+    double* daa = dff + T;
+    cudaStream_t st = ctx()->stream;
+    UM_CUDA(cudaMemcpy2DAsync(dx, (size_t)N_local * 8, X, (size_t)ldx * 8, (size_t)N_local * 8, (size_t)T, cudaMemcpyHostToDevice, st));
+    UM_CUDA(cudaMemcpyAsync(dzz, Z, nz * 8, cudaMemcpyHostToDevice, st));
+    UM_CUDA(cudaMemcpyAsync(dyy, y, (size_t)T * 8, cudaMemcpyHostToDevice, st));
+    um_view yv, xv, zv;
+    um_view_init(&yv, dyy, T, 1, UM_F64);
+    um_view_init(&xv, dx, T, N_local, UM_F64);
+    um_view_init(&zv, dzz, T, L, UM_F64);
+    um_tprf_out o = {};
+    o.forecasts = dff;
+    o.alpha = alpha_host ? daa : nullptr;
+    s = um_tprf_fit(mode, &yv, &xv, &zv, n_total, &o);
+    if (s != UM_OK) return s;
+    if (forecasts_host) UM_CUDA(cudaMemcpyAsync(forecasts_host, dff, (size_t)T * 8, cudaMemcpyDeviceToHost, st));
+    if (alpha_host) UM_CUDA(cudaMemcpyAsync(alpha_host, daa, (size_t)N_local * 8, cudaMemcpyDeviceToHost, st));
+    UM_CUDA(cudaStreamSynchronize(st));
+    if (r_squared) *r_squared = o.r_squared;
+    return UM_OK;
+  }
   const bool sharded = n_total > 0 && comm_active() && comm_world() > 1;
   if (n_total <= 0) n_total = N_local;
   Ctx& c = *ctx();
