@@ -371,7 +371,7 @@ static int launch_dgemm(const double* pa, i64 lda, const double* pb, i64 ldb, do
   splits = (KT + kt_per - 1) / kt_per;
   void* part = nullptr;
   int s = um_malloc((size_t)splits * (size_t)M * (size_t)N * 8, &part);
-  if (s != UM_OK) return s;
+  if (s != UM_OK) return launch_dgemm_split<AK, BKM>(tile, pa, lda, pb, ldb, pc, ldc, M, N, K, vec16, 1, KT, 0);   // no room: unsplit
   s = launch_dgemm_split<AK, BKM>(tile, pa, lda, pb, ldb, static_cast<double*>(part), N, M, N, K, vec16, (int)splits, kt_per, M * N);
   if (s == UM_OK) {
     um_view pv, ov;
@@ -449,7 +449,7 @@ extern "C" int32_t um_matmul(const um_view* a, const um_view* b, const um_view* 
       if (g_f32_path == 0 && K >= 8192 && 2 * t128 <= sms && (double)(M + N) * (double)K * 8.0 <= 1073741824.0) {
         void* blk = nullptr;
         int s = um_malloc((size_t)(M * K + K * N + M * N) * 8, &blk);
-        if (s != UM_OK) return s;
+        if (s == UM_OK) {
         double* p64 = static_cast<double*>(blk);
         um_view a64, b64, c64;
         um_view_init(&a64, p64, M, K, UM_F64);
@@ -461,6 +461,7 @@ extern "C" int32_t um_matmul(const um_view* a, const um_view* b, const um_view* 
         if (s == UM_OK) s = um_copy(&c64, out);
         um_free(blk);   // stream-ordered
         return s;
+        }   // no room for the copies: the FP32 kernels below
       }
     }
     In<float> A = in_of<float>(a), B = in_of<float>(b);

@@ -425,7 +425,9 @@ inline int launch(const float* A, i64 lda, const float* B, i64 ldb, float* C, i6
     const i64 Kp = (K + 3) & ~i64(3);
     void* tmp = nullptr;
     const size_t a_elems = (size_t)M * Kp, b_elems = (size_t)N * Kp;
-    if (um_malloc((2 * a_elems + 2 * b_elems) * sizeof(float), &tmp) != UM_OK) return UM_ERR_OOM;
+    const bool have = um_malloc((2 * a_elems + 2 * b_elems) * sizeof(float), &tmp) == UM_OK;
+    if (!have && mode == 3) return UM_ERR_OOM;   // automatic: no room for the temporary -> the shared-memory split below
+    if (have) {
     float* a_hi = static_cast<float*>(tmp);
     float* a_lo = a_hi + a_elems;
     float* b_hi = a_lo + a_elems;
@@ -454,6 +456,7 @@ inline int launch(const float* A, i64 lda, const float* B, i64 ldb, float* C, i6
     um_free(tmp);   // stream-ordered: after the product
     if (!ok) return mode == 3 ? fail(UM_ERR_ARG, "matmul: tensor map for the pre-split operands rejected") : -1;
     return rc;
+    }
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
